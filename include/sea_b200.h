@@ -1,0 +1,195 @@
+/*
+ * sea_b200.h -- C ABI of libsea_b200.so: the B200 (sm_100a) implementation of the per-layer
+ * SEA / Perlin attention forward of gmlwns2000/sea-attention.
+ *
+ * Every entry point replaces one python-level operator of the reference (cited as file:line,
+ * relative to the reference root).  Conventions, shared by all entries:
+ *   - all tensor pointers are DEVICE pointers owned by the caller; the library never allocates,
+ *     frees, or synchronises; work is enqueued on `stream` (a cudaStream_t passed as void*);
+ *   - tensors are dense row-major with the innermost dimension contiguous; where the reference
+ *     accepts strided views the entry takes explicit element strides;
+ *   - `dtype` is one of SEA_DTYPE_*: it is the storage type of activations (q, k, v, outputs);
+ *     all arithmetic accumulates in fp32;
+ *   - return value: 0 on success, a negative SEA_ERR_* code otherwise; sea_last_error() returns a
+ *     thread-local human readable message for the last failure;
+ *   - flat-CSR container (the reference's batched torch.sparse_csr_tensor of shape
+ *     [N, T_DST, H*T_SRC], causal_resize_m_to_t.py:757-762): crow [N, T_DST+1], col [N, Z];
+ *     a column id encodes (head, source token) as h*T_SRC + j; inside a row entries are head-major
+ *     and, inside one compressed pixel, descending in j.  `idx64` selects int64 (torch boundary)
+ *     or int32 (internal) indices for BOTH crow and col.
+ */
+#ifndef SEA_B200_H_
+#define SEA_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SEA_DTYPE_F32 0
+#define SEA_DTYPE_BF16 1
+#define SEA_DTYPE_F16 2
+
+#define SEA_OK 0
+#define SEA_ERR_INVALID (-1)   /* bad argument / unsupported shape */
+#define SEA_ERR_CUDA (-2)      /* a CUDA runtime call or launch failed */
+#define SEA_ERR_UNSUPPORTED (-3)
+
+#define SEA_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define SEA_API __attribute__((visibility("default")))
+#else
+#define SEA_API
+#endif
+
+SEA_API int sea_abi_version(void);
+SEA_API const char* sea_last_error(void);
+/* Compute capability major*10+minor of the current device, or a negative error. */
+SEA_API int sea_device_arch(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * a7  grouped top-k  (attention.py:774-947; helper variant ops/kernels/causal_topk_masking.py:31)
+ * keys: fp32, logical shape [N, H, T, P] with element strides (sn, sh, st), P contiguous.
+ * group_mode 0 ('causal_batch', attention.py:843-849): one group per (n, t) = all heads, flat index
+ *              h*P+m;  k_per_group [N*T] fp32 = the reference's per_item_top_k (already rounded and
+ *              clamped >= 1, attention.py:856,866).
+ * group_mode 1 ('query', :850-853): one group per (n, h, t), k_per_group [N] (per item).
+ * alive  <=>  rank by descending key < k_per_group[group]; equal keys: LOWER flat index wins.
+ * row_valid (nullable, u8 [N, T]): 0 marks a padded query row -> all dead (attention.py:928-931).
+ * mask_bits out: u32 words, [N, T, ceil(H*P/32)], bit (h*P+m) of row (n, t).
+ */
+SEA_API int sea_topk_mask_bits(const float* keys, int64_t sn, int64_t sh, int64_t st,
+                       const float* k_per_group, const uint8_t* row_valid,
+                       uint32_t* mask_bits, int N, int H, int T, int P, int group_mode, void* stream);
+
+/* 0/1 float mask [N,H,T,P] (the reference's partial_attention_mask of the benchmarking branch,
+ * attention.py:916-917) <-> bit mask. */
+SEA_API int sea_mask_float_to_bits(const float* mask, int64_t sn, int64_t sh, int64_t st, uint32_t* mask_bits,
+                           int N, int H, int T, int P, void* stream);
+SEA_API int sea_mask_bits_to_float(const uint32_t* mask_bits, float* mask, int N, int H, int T, int P, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a8  resize_from_m_to_t_csr  (causal_resize_m_to_t.py:910-1007 -> scan_col METHOD 1 :648-762 ->
+ *     __scan_col_4_compute :493-572, triton_round :214-264).
+ * Pass 1 (count): crow[n, 0] = 0, crow[n, t+1] = sum over rows <= t of min(int(ve-vs)*alive, k).
+ * Pass 2 (fill):  col[n, crow[n,t] ...] per SURVEY appendix C.3; tail col[n, crow[n,T_DST]:Z) = 0.
+ * T_DST query rows are the LAST T_DST of T_SRC tokens (target_width[-T_DST:], :954-957).
+ */
+SEA_API int sea_csr_count(const uint32_t* mask_bits, void* crow, int idx64,
+                  int N, int H, int T_DST, int P, int T_SRC, int k, int is_causal, void* stream);
+SEA_API int sea_csr_fill(const uint32_t* mask_bits, const void* crow, void* col, int idx64, int64_t Z,
+                 int N, int H, int T_DST, int P, int T_SRC, int k, int is_causal, void* stream);
+
+/* flat_csr_to_dense (ops/kernels/flat_csr_to_dense.py:3-36): out [N,H,T_DST,T_SRC] fp32, zero filled
+ * then out[n,h,t,j] = values[n,z] (values == NULL -> 1.0). */
+SEA_API int sea_flat_csr_to_dense(const void* crow, const void* col, int idx64, const float* values, int64_t Z,
+                          float* out, int N, int H, int T_DST, int T_SRC, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a9  flat_csr_masked_bmm (ops/kernels/flat_csr_masked_bmm.py:137-195): SDDMM, unscaled,
+ *     out_values[n,z] = <a[n,h,row,:], b[n,h,j,:]> accumulated in fp32.
+ * a, b: `dtype`, element strides (n, h, t), d contiguous.
+ */
+SEA_API int sea_flat_csr_masked_bmm(const void* crow, const void* col, int idx64, int64_t Z,
+                            const void* a, int64_t a_sn, int64_t a_sh, int64_t a_st,
+                            const void* b, int64_t b_sn, int64_t b_sh, int64_t b_st,
+                            int dtype, float* out_values,
+                            int N, int H, int T_DST, int T_SRC, int D, void* stream);
+
+/* a10 flat_csr_softmax (ops/kernels/flat_csr_softmax.py:127-176): softmax inside each (row, head). */
+SEA_API int sea_flat_csr_softmax(const void* crow, const void* col, int idx64, int64_t Z,
+                         const float* in_values, float* out_values,
+                         int N, int H, int T_DST, int T_SRC, void* stream);
+
+/* a11 flat_csr_elmul (ops/kernels/flat_csr_elmul.py:110-162): out[z] = in[z] * dense[n,h,row,j];
+ * dense fp32 with element strides (n,h,tdst,tsrc); stride 0 allowed (attention.py:1170). */
+SEA_API int sea_flat_csr_elmul(const void* crow, const void* col, int idx64, int64_t Z,
+                       const float* in_values, float* out_values,
+                       const float* dense, int64_t d_sn, int64_t d_sh, int64_t d_st, int64_t d_sj,
+                       int N, int H, int T_DST, int T_SRC, void* stream);
+
+/* a12 flat_csr_sdbmm (ops/kernels/flat_csr_sdbmm.py:323-439): out[n,h,row,:] = sum_z p[z] V[n,h,j,:],
+ * out fp32 [N,H,T_DST,D] contiguous (zeroed by the call).  Never truncates (the reference silently
+ * drops entries beyond MAX_ROW_T, :382-388). */
+SEA_API int sea_flat_csr_sdbmm(const void* crow, const void* col, int idx64, int64_t Z, const float* values,
+                       const void* v, int64_t v_sn, int64_t v_sh, int64_t v_st, int dtype,
+                       float* out, int N, int H, int T_DST, int T_SRC, int D, void* stream);
+
+/* a16 resize_from_m_to_t (ops/kernels/resize_m_to_t.py:6-73), training=False, oversampled=None|1.0:
+ * out[n,h,t,j] = x[n,h,t, floor((cs-0.5)/L*P - 1e-4)] for valid j (cs = 1-based rank of j among the
+ * valid source tokens of row t, L = their count), `fill` elsewhere.  attention_mask additive fp32,
+ * causal: [N,1,T1,T2]; non causal: [N,1,1,T2] (row stride 0). */
+SEA_API int sea_resize_m_to_t_dense(const float* x, float fill, const float* attention_mask, int64_t m_sn, int64_t m_st,
+                            float* out, int N, int H, int T1, int P, int T2, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a2+a3  causal Performer estimate  (performer_pytorch.FastAttention, causal + generalized ReLU
+ *        features; call sites attention.py:159-164, 504-508, 527-534, 559-572).
+ *   v_for_atten = cat(pos_emb[t], v[n,h,t])            (width 2*D, attention.py:504-508)
+ *   phi(x) = relu(D^-1/4 x P^T) + 1e-3 ; out_t = phi(q_t) S_t / (phi(q_t) . (z_t + 1e-6))
+ * Also emits the causal running mean of v (attention.py:1237-1241) from the same pass.
+ * q,k,v: `dtype`, strides (n,h,t); pos_emb fp32 [>=T, D]; proj fp32 [F, D];
+ * ctx out: `dtype` [N,H,T,2D]; cumavg out (nullable): `dtype` [N,H,T,D];
+ * workspace: fp32, at least sea_performer_workspace_floats(N,H,T,D,F) elements.
+ */
+SEA_API int64_t sea_performer_workspace_floats(int N, int H, int T, int D, int F);
+SEA_API int sea_performer_causal_fwd(const void* q, int64_t q_sn, int64_t q_sh, int64_t q_st,
+                             const void* k, int64_t k_sn, int64_t k_sh, int64_t k_st,
+                             const void* v, int64_t v_sn, int64_t v_sh, int64_t v_st,
+                             const float* pos_emb, const float* proj, int dtype,
+                             void* ctx, void* cumavg, float* workspace,
+                             int N, int H, int T, int D, int F, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a4  predictor MLP (attention.py:190-196,242-245,289-291,577-625) for the causal predictor:
+ *   x = cat(ctx[2D], v[D]) -> Linear(3D,2D) -> LayerNorm -> GELU = t_pred
+ *   dec = Linear(2D, S*W)(t_pred), S = 2 splits, W = P/4; ChannelSplit -> channel c = h*S+s
+ *   first CNN LayerNorm(W) (attention.py:267) is applied here, per (c, t), over W
+ *   scales = Linear(2D, 2)(t_pred)
+ * outputs: cnn_in channels-last [N, T, W, C=H*S] (`dtype`), scales fp32 [N,H,T,2],
+ *          t_pred (nullable, `dtype`, [N,H,T,2D]).
+ * All weights fp32, torch layout ([out, in]).
+ */
+SEA_API int sea_predictor_mlp_fwd(const void* ctx, const void* v, int64_t v_sn, int64_t v_sh, int64_t v_st, int dtype,
+                          const float* enc_w, const float* enc_b, const float* enc_ln_w, const float* enc_ln_b,
+                          const float* dec_w, const float* dec_b, const float* cnn_ln_w, const float* cnn_ln_b,
+                          const float* scl_w, const float* scl_b,
+                          void* cnn_in, float* scales, void* t_pred,
+                          int N, int H, int T, int D, int S, int W, void* stream);
+
+/* a5  one CausalConv2d(C,C,3,padding=2,dilation=2,causal) + ReLU (modules.py:96-192;
+ *     attention.py:271-274) on channels-last activations [N,T,W,C]:
+ *   y[t,w,o] = relu(b[o] + sum_{i,j<3} sum_c Wt[o,c,i,j] x[t-4+2i, w-2+2j, c])   (zero outside)
+ * weight fp32 in the reference layout [O, C, 5, 3] (rows 3..4 are the masked-out taps). */
+SEA_API int sea_causal_conv3x3_dil2_relu(const void* x, const float* weight, const float* bias, void* y, int dtype,
+                                 int N, int T, int W, int C, int O, void* stream);
+
+/* a5 tail + a6  (attention.py:275-280, 670-673): nearest x4 along W, CausalConv2d(C,H,1,padding=1)
+ * (width P+2, the two pad columns equal the bias), area-resize to P, LayerNorm(P), softmax(P).
+ * x channels-last [N,T,W,C]; weight fp32 [H, C]; probs out fp32 [N,H,T,P]; scores out nullable. */
+SEA_API int sea_predictor_tail_fwd(const void* x, int dtype, const float* weight, const float* bias,
+                           const float* ln_w, const float* ln_b, float* probs, float* scores,
+                           int N, int H, int T, int W, int C, int P, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a9-a14 fused sparse attention of the benchmarking branch (attention.py:1151-1173, 1237-1244,
+ * 1279-1282): per (row, head) scores -> softmax -> * sigmoid(scales[...,0]) (if use_scaler) ->
+ * sum p V -> out = ctx*sigmoid(scales[...,1]) + (1-sigmoid(.))*cumavg -> [N, T_DST, H*D].
+ * probs_values (nullable, fp32 [N,Z]) receives the scaled probabilities (the reference's
+ * partial_attention_probs.values()).  Requires head-major entries inside a row (what a8 emits).
+ * cumavg nullable (then out = ctx, layout still [N,T_DST,H*D]).
+ */
+SEA_API int sea_sparse_attention_fwd(const void* crow, const void* col, int idx64, int64_t Z,
+                             const void* q, int64_t q_sn, int64_t q_sh, int64_t q_st,
+                             const void* k, int64_t k_sn, int64_t k_sh, int64_t k_st,
+                             const void* v, int64_t v_sn, int64_t v_sh, int64_t v_st,
+                             const float* scales, const void* cumavg, int use_scaler, int dtype,
+                             void* out, float* probs_values,
+                             int N, int H, int T_DST, int T_SRC, int D, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SEA_B200_H_ */

@@ -1,0 +1,161 @@
+"""TEST INFRASTRUCTURE ONLY -- generates tests/golden/*.npz by running the UNMODIFIED reference
+(imported from /root/reference; see oracle/ref_harness.py) in the build container.
+
+    python oracle/make_golden.py            # writes tests/golden/*.npz (minutes; Triton interpreter)
+
+The reference's dense torch path runs natively on CPU; its Triton kernels run through Triton's numpy
+interpreter (TRITON_INTERPRET=1) with the shims documented in ref_harness.py.  Nothing of the
+reference is copied: inputs that only a nested reference function can produce (the Perlin-noise
+scores of causal_resize_m_to_t.py:1023-1044) are obtained by compiling that function's AST from the
+reference file at run time.
+"""
+import ast
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(_HERE))
+from oracle import ref_harness as rh  # noqa: E402
+
+GOLDEN = os.path.join(os.path.dirname(_HERE), 'tests', 'golden')
+
+# Keys of the reference state_dict the hot path never touches (attention.py:185-189, 315-318): dropped
+# from the fixtures to keep them small.
+_UNUSED = ('attention_predictor_enc_per_layer.', 'norm_performer.', 'norm_partial.', 'norm_random.', 'norm.',
+           'performer_proj_updater.', 'attention_predictor_enc_head_embd')
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+def _extract_nested_function(path, outer, inner):
+    tree = ast.parse(open(path).read())
+    for node in ast.walk(tree):
+        if isinstance(node, ast.FunctionDef) and node.name == outer:
+            for sub in node.body:
+                if isinstance(sub, ast.FunctionDef) and sub.name == inner:
+                    mod = ast.Module(body=[sub], type_ignores=[])
+                    ns = {'torch': torch, 'math': __import__('math')}
+                    exec(compile(mod, path, 'exec'), ns)
+                    return ns[inner]
+    raise KeyError(inner)
+
+
+def golden_kat_causal_resize():
+    """Default config of causal_resize_m_to_t.py:1136-1165 (causal N1 H1 T64 T_M8 K16, seed 42); the
+    expected per-row nnz is printed in src/poc/neko/visualize_ops_causal_resize.ipynb:29-35 / :51-57."""
+    rh.load_reference()
+    import torch.nn.functional as F
+    from src.utils import seed
+    from src.models.perlin_attention.ops import resize_from_m_to_t_csr, resize_from_m_to_t, flat_csr_to_dense
+    from src.models.perlin_attention.ops.kernels.causal_topk_masking import causal_topk_masking
+    path = os.path.join(rh.REFERENCE_ROOT, 'src/models/perlin_attention/ops/kernels/causal_resize_m_to_t.py')
+    rand_perlin_2d = _extract_nested_function(path, 'test_config', 'rand_perlin_2d')
+    N, H, T, T_M, K = 1, 1, 64, 8, 16
+    seed()
+    FP_MIN = torch.finfo(torch.float16).min * 0.5
+    scores = F.interpolate(rand_perlin_2d((128, 128), (16, 16)).view(1, 1, 128, 128), (T, T_M)).expand(N, H, T, T_M).contiguous()
+    probs = torch.softmax(scores, dim=-1)
+    cm = ((torch.arange(T).view(1, T) > torch.arange(T).view(T, 1)) * FP_MIN).view(1, 1, T, T)
+    cmask = causal_topk_masking(probs, k=K * 1.0, attention_mask=cm[:, :, -1:, :], dst_attention_mask=cm[:, :, :, :1],
+                                causal_attention_mask=cm, is_causal=True)
+    csr = resize_from_m_to_t_csr(cmask, 0, K, target_width=T, is_causal=True, oversampled=1.0)
+    dense_from_csr = flat_csr_to_dense(csr, T, H)
+    dense = resize_from_m_to_t(cmask, 0, attention_mask=cm, target_width=T, is_causal=True, k=K, oversampled=1.0)
+    nnz_notebook = [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 14, 15, 15, 16, 15, 15, 14, 15, 15, 12, 14, 13,
+                    14, 15, 15, 16, 12, 12, 14, 15, 13, 15, 15, 15, 15, 16, 11, 11, 11, 12, 12, 12, 12, 13, 14, 12, 13, 13,
+                    14, 14, 14, 14, 15, 16, 15, 16, 15, 16]
+    got = dense_from_csr[0, 0].sum(-1).long().tolist()
+    assert got == nnz_notebook, 'reference run does not reproduce its own notebook table'
+    assert dense[0, 0].sum(-1).long().tolist() == nnz_notebook
+    np.savez_compressed(os.path.join(GOLDEN, 'kat_causal_resize.npz'),
+                        probs=_np(probs), compressed_mask=_np(cmask), crow=_np(csr.crow_indices()),
+                        col=_np(csr.col_indices()), dense=_np(dense).astype(np.uint8),
+                        nnz_per_row_notebook=np.array(nnz_notebook, dtype=np.int64), meta=np.array([N, H, T, T_M, K]))
+    print('kat_causal_resize ok')
+
+
+def golden_kat_causal_conv():
+    """src/poc/neko/test_causal_conv.ipynb:65 with the printed table :42-47."""
+    rh.load_reference()
+    from src.models.perlin_attention.modules import CausalConv2d
+    x = torch.eye(8).view(1, 1, 8, 8)
+    c = CausalConv2d(1, 3, 3, padding=1, stride=2, causal=True)
+    c.bias.data.fill_(0)
+    c.weight.data.fill_(1)
+    out = c(x)
+    table = [[1, 0, 0, 0], [2, 2, 0, 0], [0, 2, 2, 0], [0, 0, 2, 2]]
+    assert out.long()[0, 0].tolist() == table
+    np.savez_compressed(os.path.join(GOLDEN, 'kat_causal_conv.npz'), x=_np(x), weight=_np(c.weight),
+                        weight_mask=_np(c.weight_mask), bias=_np(c.bias), out=_np(out), table=np.array(table))
+    print('kat_causal_conv ok')
+
+
+def _run_layer(m, q, k, v, mask, benchmarking):
+    from src.utils import get_bench
+    m.benchmarking = benchmarking
+    get_bench().activate_temp_buffers = True
+    get_bench().reset_temp_buffers()
+    with torch.no_grad():
+        out = m(q, k, v, q, k, v, q, k, mask, None, None)
+    bufs = {k_: v_[-1] for k_, v_ in get_bench().buffers.items()}
+    get_bench().activate_temp_buffers = False
+    return out, bufs
+
+
+def golden_layer(name, H, d, T, k, P, nbf, causal, k_flatten_dim=None, seed_inputs=1234):
+    """One PerlinAttention layer, dense path (benchmarking=False) and sparse path (benchmarking=True,
+    Triton interpreted), fp32, random-init, no padding (test_perlin_opt_causality.py:110-173 style)."""
+    t0 = time.time()
+    m = rh.build_reference_attention(H, d, T, k, P, nbf, causal, k_flatten_dim=k_flatten_dim)
+    g = torch.Generator().manual_seed(seed_inputs)
+    q = torch.randn(1, H, T, d, generator=g) * (d ** -0.5 if causal else 1.0)   # OPT pre-scales q (perlin_opt.py:562)
+    kk = torch.randn(1, H, T, d, generator=g)
+    v = torch.randn(1, H, T, d, generator=g)
+    if causal:
+        mask = rh.causal_additive_mask(T, torch.float32)
+    else:
+        mask = torch.zeros(1, 1, 1, T)
+    out_d, buf_d = _run_layer(m, q, kk, v, mask, False)
+    out_s, buf_s = _run_layer(m, q, kk, v, mask, True)
+    csr = out_s.partial_attention_mask
+    sd = {k_: _np(v_) for k_, v_ in m.state_dict().items() if not k_.startswith(_UNUSED)}
+    keep = ['performer_context_layer', 't_attention_predictor', 'estimated_attention_score_dec_row',
+            'estimated_attention_score', 'estimated_attention_probs', 'per_item_top_k', 'estimated_scales',
+            'average_context_layer', 'partial_context_layer_1', 'partial_context_layer']
+    fx = {'sd.' + k_: v_ for k_, v_ in sd.items()}
+    fx.update(q=_np(q), k=_np(kk), v=_np(v))
+    for b in keep:
+        if b in buf_d and buf_d[b] is not None:
+            fx['dense.' + b] = _np(buf_d[b]).astype(np.float32)
+    fx['dense.mask_before_interp_alive'] = np.packbits((_np(buf_d['partial_attention_mask_before_interp']) > -1))
+    fx['dense.partial_attention_mask_alive'] = np.packbits((_np(buf_d['partial_attention_mask']) > -1))
+    fx['sparse.mask_before_interp'] = np.packbits(_np(buf_s['partial_attention_mask_before_interp']) > 0.5)
+    fx['sparse.crow'] = _np(csr.crow_indices()).astype(np.int64)
+    fx['sparse.col'] = _np(csr.col_indices()).astype(np.int32)
+    fx['sparse.probs_values'] = _np(out_s.partial_attention_probs.values()).astype(np.float32)
+    fx['sparse.context_layer'] = _np(out_s.context_layer).astype(np.float32)
+    fx['sparse.estimated_attention_probs'] = _np(out_s.estimated_attention_probs).astype(np.float32)
+    fx['meta'] = np.array([1, H, d, T, k, P, nbf, int(causal)])
+    np.savez_compressed(os.path.join(GOLDEN, name + '.npz'), **fx)
+    err = (out_d.context_layer - out_s.context_layer).abs().max().item()
+    print(f'{name}: dense-vs-sparse context max err {err:.3e}  nnz {int(csr.crow_indices()[0, -1])}  ({time.time() - t0:.0f}s)')
+
+
+def main():
+    os.makedirs(GOLDEN, exist_ok=True)
+    golden_kat_causal_resize()
+    golden_kat_causal_conv()
+    golden_layer('layer_causal_h4_t128', H=4, d=64, T=128, k=8, P=32, nbf=8, causal=True)
+    golden_layer('layer_causal_h3_t100', H=3, d=32, T=100, k=6, P=16, nbf=4, causal=True)
+    if '--with-bert' in sys.argv:
+        golden_layer('layer_bert_h4_t64', H=4, d=64, T=64, k=8, P=32, nbf=1, causal=False, k_flatten_dim='batch')
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,85 @@
+"""ctypes binding of libsea_b200.so (C ABI: include/sea_b200.h).
+
+There is NO fallback: if the library is missing or an entry fails, the call raises.  PyTorch is only
+used by the callers for device memory and streams; every pointer crossing this boundary is a raw
+`data_ptr()`.
+"""
+import ctypes
+import os
+import re
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, 'lib', 'libsea_b200.so')
+HEADER_PATH = os.path.join(os.path.dirname(_PKG), 'include', 'sea_b200.h')
+
+SEA_DTYPE_F32, SEA_DTYPE_BF16, SEA_DTYPE_F16 = 0, 1, 2
+
+_lib = None
+
+
+class SeaError(RuntimeError):
+    pass
+
+
+def declared_symbols():
+    """Names of every SEA_API entry point the header declares."""
+    text = open(HEADER_PATH).read()
+    return sorted(set(re.findall(r'SEA_API\s+[\w\s\*]+?\b(sea_\w+)\s*\(', text)))
+
+
+_c = ctypes
+_P, _I, _L, _F = _c.c_void_p, _c.c_int, _c.c_int64, _c.c_float
+
+_SIGNATURES = {
+    'sea_abi_version': (_I, []),
+    'sea_last_error': (_c.c_char_p, []),
+    'sea_device_arch': (_I, []),
+    'sea_topk_mask_bits': (_I, [_P, _L, _L, _L, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    'sea_mask_float_to_bits': (_I, [_P, _L, _L, _L, _P, _I, _I, _I, _I, _P]),
+    'sea_mask_bits_to_float': (_I, [_P, _P, _I, _I, _I, _I, _P]),
+    'sea_csr_count': (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    'sea_csr_fill': (_I, [_P, _P, _P, _I, _L, _I, _I, _I, _I, _I, _I, _I, _P]),
+    'sea_flat_csr_to_dense': (_I, [_P, _P, _I, _P, _L, _P, _I, _I, _I, _I, _P]),
+    'sea_flat_csr_masked_bmm': (_I, [_P, _P, _I, _L, _P, _L, _L, _L, _P, _L, _L, _L, _I, _P, _I, _I, _I, _I, _I, _P]),
+    'sea_flat_csr_softmax': (_I, [_P, _P, _I, _L, _P, _P, _I, _I, _I, _I, _P]),
+    'sea_flat_csr_elmul': (_I, [_P, _P, _I, _L, _P, _P, _P, _L, _L, _L, _L, _I, _I, _I, _I, _P]),
+    'sea_flat_csr_sdbmm': (_I, [_P, _P, _I, _L, _P, _P, _L, _L, _L, _I, _P, _I, _I, _I, _I, _I, _P]),
+    'sea_resize_m_to_t_dense': (_I, [_P, _F, _P, _L, _L, _P, _I, _I, _I, _I, _I, _P]),
+    'sea_performer_workspace_floats': (_L, [_I, _I, _I, _I, _I]),
+    'sea_performer_causal_fwd': (_I, [_P, _L, _L, _L, _P, _L, _L, _L, _P, _L, _L, _L, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    'sea_predictor_mlp_fwd': (_I, [_P, _P, _L, _L, _L, _I] + [_P] * 10 + [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    'sea_causal_conv3x3_dil2_relu': (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    'sea_predictor_tail_fwd': (_I, [_P, _I, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    'sea_sparse_attention_fwd': (_I, [_P, _P, _I, _L, _P, _L, _L, _L, _P, _L, _L, _L, _P, _L, _L, _L, _P, _P, _I, _I, _P, _P,
+                                      _I, _I, _I, _I, _I, _P]),
+}
+
+
+def load():
+    """Loads the shared library (once).  Raises SeaError when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise SeaError(f'{LIB_PATH} not found: build it with `python sea-attention_b200/build.py` '
+                       f'(or __graft_entry__.build()); there is no fallback path')
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGNATURES.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError as e:
+            raise SeaError(f'{LIB_PATH} does not export {name}') from e
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def call(name, *args):
+    """Calls an int-returning entry; raises SeaError with the library's message on failure."""
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        msg = lib.sea_last_error()
+        raise SeaError(f'{name} failed (code {rc}): {msg.decode() if msg else ""}')
+    return rc

@@ -1,0 +1,302 @@
+"""Drop-in `PerlinAttention` (reference: src/models/perlin_attention/attention.py:133-1359).
+
+Same constructor `(config, perlin_config)`, same parameter / buffer names (so reference checkpoints
+load with `load_state_dict`), same 12-argument `forward` and the same `PerlinAttentionOutput` tuple --
+but the forward is a fixed sequence of hand-written sm_100a kernels reached through the C ABI of
+libsea_b200.so (see include/sea_b200.h, ops.py).  The nn.Modules below only HOLD parameters; their
+torch forward is never used, and there is no CPU / eager fallback: unsupported modes raise.
+
+What runs on the device per call (causal prefill, the reference's `benchmarking` branch, attention.py
+:518-573, 595-673, 774-947, 1036-1042, 1151-1173, 1208-1282):
+  performer (3 launches) -> predictor MLP -> conv x2 -> predictor tail (+softmax) -> grouped top-k ->
+  CSR count+scan -> CSR fill -> fused sparse attention (+scaler, +running-mean mix, +permute)
+with ZERO host synchronisations (the reference has >= 8 `.item()`/`nonzero()` syncs).
+"""
+import math
+import os
+from typing import NamedTuple, Optional
+
+import torch
+from torch import nn
+
+from . import ops
+from ._lib import SeaError
+from .config import PerlinAttentionConfig, get_default_config
+
+
+class PerlinAttentionOutput(NamedTuple):
+    """Field-for-field the reference's output tuple (attention.py:84-106)."""
+    loss: torch.Tensor
+    context_layer: torch.Tensor
+    partial_attention_probs: torch.Tensor
+    partial_attention_mask: torch.Tensor
+    estimated_attention_probs_m: torch.Tensor
+    estimated_attention_probs: torch.Tensor
+    dense_attention_probs: torch.Tensor
+    key_for_score: torch.Tensor
+    state: object
+
+    def to(self, device):
+        mv = lambda t: t.to(device) if isinstance(t, torch.Tensor) else t
+        return PerlinAttentionOutput(*[mv(f) for f in self])
+
+
+# ----------------------------------------------------------------------------- parameter containers
+class _Holder(nn.Module):
+    """Keeps a child under a fixed attribute name so state_dict keys equal the reference's
+    (`ModuleBenchmark.module`, attention.py:108-121; `KeepRes.net`, modules.py:42-55)."""
+
+    def __init__(self, attr: str, child: nn.Module):
+        super().__init__()
+        setattr(self, attr, child)
+
+    def forward(self, *a, **kw):
+        raise SeaError('parameter container: the CUDA path never calls torch forwards')
+
+
+class _CausalConvParams(nn.Module):
+    """Parameters of the reference's CausalConv2d (modules.py:96-142): weight [O,C,2k-1,k] whose first k
+    rows are the live taps, a 0/1 `weight_mask` buffer, bias [O]; PyTorch Conv2d default init."""
+
+    def __init__(self, in_ch: int, out_ch: int, ksize: int):
+        super().__init__()
+        seed_conv = nn.Conv2d(in_ch, out_ch, ksize)
+        w = torch.zeros((out_ch, in_ch, 2 * ksize - 1, ksize))
+        w[:, :, :ksize, :] = seed_conv.weight.data
+        m = torch.zeros_like(w)
+        m[:, :, :ksize, :] = 1.0
+        self.weight = nn.Parameter(w)
+        self.bias = nn.Parameter(seed_conv.bias.data.clone())
+        self.register_buffer('weight_mask', m)
+
+
+def _orthogonal_chunk(cols):
+    qm, _ = torch.linalg.qr(torch.randn((cols, cols)), mode='reduced')
+    return qm.t()
+
+
+def gaussian_orthogonal_random_matrix(nb_rows: int, nb_columns: int) -> torch.Tensor:
+    """Performer projection (FAVOR+, Choromanski et al.): stacked orthogonal blocks rescaled by the
+    norms of fresh Gaussian rows (performer-pytorch `ortho_scaling=0`)."""
+    blocks = [_orthogonal_chunk(nb_columns) for _ in range(nb_rows // nb_columns)]
+    rem = nb_rows - (nb_rows // nb_columns) * nb_columns
+    if rem > 0:
+        blocks.append(_orthogonal_chunk(nb_columns)[:rem])
+    mat = torch.cat(blocks)
+    mult = torch.randn((nb_rows, nb_columns)).norm(dim=1)
+    return torch.diag(mult) @ mat
+
+
+class _PerformerParams(nn.Module):
+    """Holds `projection_matrix` under the name the reference's `FastAttention` registers it
+    (attention.py:159-164) and offers `redraw_projection_matrix` for `ProjectionUpdater`."""
+
+    def __init__(self, dim_heads: int, nb_features: int, causal: bool):
+        super().__init__()
+        self.dim_heads, self.nb_features, self.causal = dim_heads, nb_features, causal
+        self.generalized_attention = causal
+        self.register_buffer('projection_matrix', gaussian_orthogonal_random_matrix(nb_features, dim_heads))
+
+    @torch.no_grad()
+    def redraw_projection_matrix(self, device=None):
+        self.projection_matrix.copy_(gaussian_orthogonal_random_matrix(self.nb_features, self.dim_heads))
+
+
+class ProjectionUpdater(nn.Module):
+    """Mirror of src/models/common/performer.py:5-36 (training-time feature redraw)."""
+
+    def __init__(self, instance, feature_redraw_interval):
+        super().__init__()
+        self.instance = instance
+        self.feature_redraw_interval = feature_redraw_interval
+        self.register_buffer('calls_since_last_redraw', torch.tensor(0))
+
+    def fix_projections_(self):
+        self.feature_redraw_interval = None
+
+    def redraw_projections(self, device=None):
+        if not self.training:
+            return
+        if self.feature_redraw_interval is not None and self.calls_since_last_redraw >= self.feature_redraw_interval:
+            for m in self.instance.modules():
+                if isinstance(m, _PerformerParams):
+                    m.redraw_projection_matrix(device)
+            self.calls_since_last_redraw.zero_()
+            return
+        self.calls_since_last_redraw += 1
+
+
+def _k_per_row_causal(H: int, k: float, k_oversample: float, P: int, T_SRC: int, T_DST: int, device) -> torch.Tensor:
+    """per_item_top_k of attention.py:849,856,866, evaluated with the same torch fp32 ops (round half
+    even, clamp >= 1).  Depends on shapes only, so it is cached by the module."""
+    tl_ = torch.arange(T_SRC - T_DST + 1, T_SRC + 1, dtype=torch.long, device=device)
+    kt = H * ((k * k_oversample * P) / tl_)
+    return torch.clamp_min(torch.round(kt), 1).float().contiguous()
+
+
+def _csr_alloc_upper_bound(H: int, k: int, P: int, T_SRC: int, T_DST: int, k_per_row: torch.Tensor) -> int:
+    """Upper bound of the nnz of one batch item: a row keeps at most K_t pixels, each at most
+    min(ceil(L/P), k) wide, and never more than H*L entries (L = causal length)."""
+    L = torch.arange(T_SRC - T_DST + 1, T_SRC + 1, dtype=torch.float64)
+    width = torch.clamp(torch.ceil(L / P) + 1, max=float(k))   # +1: slack for fp32 rounding of the pixel bounds
+    per_row = torch.minimum(k_per_row.double().cpu().clamp(max=float(H * P)) * width, H * L)
+    return int(per_row.sum().item()) + 32
+
+
+class PerlinAttention(nn.Module):
+    def __init__(self, config, perlin_config: PerlinAttentionConfig = None):
+        super().__init__()
+        self.config = config
+        self.pconfig = perlin_config if perlin_config is not None else get_default_config()
+        pc = self.pconfig
+        self.num_attention_heads = config.num_attention_heads
+        self.attention_head_size = int(config.hidden_size / config.num_attention_heads)
+        self.all_head_size = self.num_attention_heads * self.attention_head_size
+        H, d, P = self.num_attention_heads, self.attention_head_size, pc.attention_predictor_length
+
+        # set from outside by the reference harnesses (benchmark_bert.py:172-173)
+        self.benchmarking = False
+        # analogue of HF `output_attentions`: materialise partial_attention_probs / _mask CSR tensors
+        self.output_attentions = False
+        # one tiny host read of N*T booleans to reject padded batches (set False under CUDA graphs)
+        self.check_padding = True
+
+        self.performer_nb_features = int(d * math.log(d) / pc.performer_nb_factor)
+        self.performer = _PerformerParams(d, self.performer_nb_features, causal=pc.causal)
+        self.performer_proj_updater = ProjectionUpdater(self.performer, 1000)
+        self.register_buffer('attention_predictor_enc_head_embd', torch.eye(H))
+        self.attention_predictor_enc_per_layer = nn.Sequential(
+            nn.Linear(3 * d * H, 2 * d * H), nn.LayerNorm(2 * d * H), nn.GELU())
+        self.attention_predictor_enc = nn.Sequential(nn.Linear(3 * d, 2 * d), nn.LayerNorm(2 * d), nn.GELU())
+        if not pc.causal:
+            self.attention_predictor_dec_row_down_scale = 2
+            self.attention_predictor_dec_row_splits = 4
+            S = 4
+            self.attention_predictor_dec_row_out_ch = (P // 2) * S
+            self.attention_predictor_dec_row = nn.Sequential(nn.Linear(2 * d, self.attention_predictor_dec_row_out_ch), nn.Identity())
+            self.attention_predictor_cnn = nn.Sequential(_Holder('net', nn.Sequential(
+                nn.Conv2d(S * H, 4 * H, 3, padding=1, stride=(2, 1)), nn.ReLU(),
+                nn.Conv2d(4 * H, 4 * H, 3, padding=1), nn.ReLU(),
+                nn.Identity(),
+                nn.Conv2d(4 * H, H, 3, padding=1))))
+        else:
+            inner_ch = int(os.environ.get('PERLIN_HOTFIX_OPT_INNER_CH', '2'))
+            if int(os.environ.get('PERLIN_HOTFIX_OPT_DEEPER', '0')) == 1:
+                raise SeaError('PERLIN_HOTFIX_OPT_DEEPER predictor variant is not implemented')
+            self.attention_predictor_dec_row_down_scale = 4
+            self.attention_predictor_dec_row_splits = inner_ch
+            self.attention_predictor_dec_row_out_ch = (P // 4) * inner_ch
+            self.attention_predictor_dec_row = nn.Sequential(nn.Linear(2 * d, self.attention_predictor_dec_row_out_ch), nn.Identity())
+            C = inner_ch * H
+            self.attention_predictor_cnn = nn.Sequential(
+                _Holder('module', nn.LayerNorm(P // 4)),
+                _Holder('module', _Holder('net', nn.Sequential(
+                    _Holder('module', _CausalConvParams(C, C, 3)), nn.ReLU(),
+                    _Holder('module', _CausalConvParams(C, C, 3)), nn.ReLU(),
+                    _Holder('module', nn.Identity()),
+                    _Holder('module', _CausalConvParams(C, H, 1))))),
+                _Holder('module', nn.LayerNorm(P)))
+        self.attention_predictor_dec_scaler = nn.Sequential(nn.Linear(2 * d, 2))
+        self.norm_performer = nn.LayerNorm(config.hidden_size)
+        self.norm_partial = nn.LayerNorm(config.hidden_size)
+        self.norm_random = nn.LayerNorm(config.hidden_size)
+        self.norm = nn.LayerNorm(config.hidden_size)
+        self.register_buffer('_v_eye', None, persistent=False)
+        self.v_eye_learned = nn.Parameter(torch.rand((1, 1, d, d)))
+        max_pos = config.max_position_embeddings if hasattr(config, 'max_position_embeddings') else 2048
+        self.v_eye_learned_causal = nn.Parameter(torch.randn((1, 1, max_pos, d)))
+        self._shape_cache = {}
+
+    # ------------------------------------------------------------------------------------------------
+    def _weights_fp32(self):
+        f = lambda t: t.detach().float().contiguous()
+        enc, dec, scl, cnn = self.attention_predictor_enc, self.attention_predictor_dec_row, self.attention_predictor_dec_scaler, self.attention_predictor_cnn
+        net = cnn[1].module.net
+        return {
+            'enc_w': f(enc[0].weight), 'enc_b': f(enc[0].bias), 'enc_ln_w': f(enc[1].weight), 'enc_ln_b': f(enc[1].bias),
+            'dec_w': f(dec[0].weight), 'dec_b': f(dec[0].bias), 'scl_w': f(scl[0].weight), 'scl_b': f(scl[0].bias),
+            'cnn_ln_w': f(cnn[0].module.weight), 'cnn_ln_b': f(cnn[0].module.bias),
+            'conv1_w': f(net[0].module.weight), 'conv1_b': f(net[0].module.bias),
+            'conv2_w': f(net[2].module.weight), 'conv2_b': f(net[2].module.bias),
+            'conv3_w': f(net[5].module.weight).reshape(net[5].module.weight.shape[0], -1), 'conv3_b': f(net[5].module.bias),
+            'out_ln_w': f(cnn[2].module.weight), 'out_ln_b': f(cnn[2].module.bias),
+            'proj': f(self.performer.projection_matrix), 'pos': f(self.v_eye_learned_causal).reshape(-1, self.attention_head_size),
+        }
+
+    def _shape_consts(self, H, P, T_SRC, T_DST, device):
+        key = (H, P, T_SRC, T_DST, self.pconfig.k, self.pconfig.k_oversample, str(device))
+        hit = self._shape_cache.get(key)
+        if hit is None:
+            kpr = _k_per_row_causal(H, self.pconfig.k, self.pconfig.k_oversample, P, T_SRC, T_DST, device)
+            hit = (kpr, _csr_alloc_upper_bound(H, self.pconfig.k, P, T_SRC, T_DST, kpr))
+            self._shape_cache[key] = hit
+        return hit
+
+    def forward(self, q, k, v, q_for_atten, k_for_atten, v_for_atten, q_for_score, k_for_score, attention_mask,
+                attention_scores_truth, context_layer_truth, last_state=None):
+        pc = self.pconfig
+        dynamic_k = int(os.environ.get('DYNAMIC_K', '0'))     # attention.py:348-351
+        if dynamic_k > 0:
+            pc.k = dynamic_k
+        if int(os.environ.get('QUERY_SKIPS', '1')) != 1:
+            raise SeaError('QUERY_SKIPS > 1 (attention.py:598) is not implemented')
+        if not q.is_cuda:
+            raise SeaError('PerlinAttention (sea-attention_b200) runs on CUDA tensors only; there is no CPU path')
+        if not pc.causal:
+            raise SeaError('non-causal (BERT) PerlinAttention is not implemented yet (SURVEY 8f-3)')
+        if pc.use_cache or last_state is not None:
+            raise SeaError('use_cache / PerlinAttentionState decoding is not implemented yet (SURVEY 8f-2)')
+        if self.training or attention_scores_truth is not None or context_layer_truth is not None:
+            raise SeaError('the training branch (dense path + KD losses, attention.py:707-765, 1066-1133) is not implemented yet '
+                           '(SURVEY 8f-1); call under eval() without teacher tensors')
+        if pc.attention_predictor_method != 'mlp' or pc.attention_predictor_backend != 'performer' or pc.attention_predictor_enc_per_layer:
+            raise SeaError('only the mlp predictor with the performer backend is implemented')
+        if pc.context_output_method != 'mix' or pc.random_lookup or pc.out_add_performer_context:
+            raise SeaError("only context_output_method='mix' without random lookup is implemented")
+        if pc.k_flatten_dim != 'causal_batch' or not pc.k_flatten:
+            raise SeaError("causal PerlinAttention needs k_flatten_dim='causal_batch' (perlin_opt.py:227-231)")
+        if float(pc.k_oversample) != 1.0:
+            raise SeaError('k_oversample != 1.0 is not implemented')
+
+        N, H, T, d = q.shape
+        assert attention_mask.shape == (N, 1, T, T), f'causal additive mask must be [N,1,T,T], got {tuple(attention_mask.shape)}'
+        assert k.shape == (N, H, T, d) and v.shape == (N, H, T, d)
+        if v_for_atten.data_ptr() != v.data_ptr() or v_for_atten.shape != v.shape:
+            raise SeaError('v_for_atten must alias v (LoRA-in-approximation, self_attention.py:104-120, is not implemented)')
+        P = pc.attention_predictor_length
+        if self.check_padding:
+            # dst_attention_mask = causal_attention_mask[:,:,:,:1] (attention.py:432); the reference reads the
+            # whole [N,1,T,T] mask and syncs (:434) -- only the first column matters.
+            if not bool((attention_mask[:, 0, :, 0] > -1).all()):
+                raise SeaError('padded query rows are not implemented yet (SURVEY 8f-3)')
+
+        w = self._weights_fp32()
+        S = self.attention_predictor_dec_row_splits
+        W = P // self.attention_predictor_dec_row_down_scale
+        k_per_row, z_alloc = self._shape_consts(H, P, T, T, q.device)
+
+        # a2+a3 (+ running mean for a13)
+        ctx, cumavg = ops.performer_causal(q_for_atten, k_for_atten, v, w['pos'], w['proj'])
+        # a4
+        cnn_in, scales, _ = ops.predictor_mlp(ctx, v, w, S, W)
+        # a5
+        y = ops.causal_conv3x3_dil2_relu(cnn_in, w['conv1_w'], w['conv1_b'])
+        y = ops.causal_conv3x3_dil2_relu(y, w['conv2_w'], w['conv2_b'])
+        # a5 tail + a6
+        probs, _ = ops.predictor_tail(y, w['conv3_w'], w['conv3_b'], w['out_ln_w'], w['out_ln_b'], P)
+        # a7
+        bits = ops.topk_mask_bits(probs, k_per_row.repeat(N) if N > 1 else k_per_row, 'causal_batch')
+        # a8 (int32 indices internally; no host sync: col is allocated at a shape-derived upper bound)
+        crow, col, Z = ops.csr_from_bits(bits, H, P, pc.k, T, is_causal=True, index_dtype=torch.int32, z_alloc=z_alloc)
+        # a9-a14
+        context, pvals = ops.sparse_attention(crow, col, q_for_score, k_for_score, v, scales, cumavg,
+                                              use_scaler=pc.partial_attention_scaler, want_probs=self.output_attentions)
+        partial_probs = partial_mask = None
+        if self.output_attentions:
+            size = (N, T, H * T)
+            partial_mask = torch.sparse_csr_tensor(crow, col, torch.ones((N, Z), dtype=torch.float32, device=q.device), size=size)
+            partial_probs = torch.sparse_csr_tensor(crow, col, pvals, size=size)
+        return PerlinAttentionOutput(
+            loss=0, context_layer=context, partial_attention_probs=partial_probs, partial_attention_mask=partial_mask,
+            estimated_attention_probs_m=probs, estimated_attention_probs=probs, dense_attention_probs=None,
+            key_for_score=k_for_score, state=None)

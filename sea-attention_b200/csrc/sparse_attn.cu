@@ -1,0 +1,241 @@
+// a9-a14 fused: flat_csr_masked_bmm -> flat_csr_softmax -> (* sigmoid(s0)) -> flat_csr_sdbmm ->
+// mix with the causal running mean -> [N, T, H*D]   (reference attention.py:1151-1173, 1237-1244, 1279-1282).
+//
+// CTA = one query row (n, t); its H head segments (entries are head-major, a8 emits them that way) are
+// located by H+1 parallel binary searches, then dealt to the CTA's warps.  Per segment: lane-per-entry
+// Q.K (K rows are 128-bit gathered, q is a shared-memory broadcast), warp-shuffle online softmax over
+// 32-entry chunks, and a lane-per-channel-pair P.V accumulation with coalesced V-row reads.
+// Nothing but the output row (and optionally the probabilities) is written: scores never touch HBM.
+#include "common.cuh"
+
+namespace sea {
+
+constexpr int kAttnWarps = 8;
+constexpr int kMaxPairs = 4;   // channel pairs per lane -> D <= 256
+
+template <typename T>
+__device__ __forceinline__ float dot_q(const float* __restrict__ qs, const T* __restrict__ krow, int D);
+
+template <>
+__device__ __forceinline__ float dot_q<float>(const float* __restrict__ qs, const float* __restrict__ krow, int D) {
+    float acc = 0.f;
+    const float4* k4 = reinterpret_cast<const float4*>(krow);
+    const float4* q4 = reinterpret_cast<const float4*>(qs);
+#pragma unroll 4
+    for (int c = 0; c < (D >> 2); ++c) {
+        const float4 kv = __ldg(k4 + c);
+        const float4 qv = q4[c];
+        acc = fmaf(qv.x, kv.x, acc); acc = fmaf(qv.y, kv.y, acc); acc = fmaf(qv.z, kv.z, acc); acc = fmaf(qv.w, kv.w, acc);
+    }
+    return acc;
+}
+
+template <typename T16>
+__device__ __forceinline__ void unpack2(uint32_t w, float& lo, float& hi);
+template <>
+__device__ __forceinline__ void unpack2<__nv_bfloat16>(uint32_t w, float& lo, float& hi) {
+    lo = __uint_as_float(w << 16);
+    hi = __uint_as_float(w & 0xffff0000u);
+}
+template <>
+__device__ __forceinline__ void unpack2<__half>(uint32_t w, float& lo, float& hi) {
+    const __half2 h2 = *reinterpret_cast<const __half2*>(&w);
+    lo = __low2float(h2);
+    hi = __high2float(h2);
+}
+
+template <typename T16>
+__device__ __forceinline__ float dot_q16(const float* __restrict__ qs, const T16* __restrict__ krow, int D) {
+    float acc = 0.f;
+    const uint4* k4 = reinterpret_cast<const uint4*>(krow);
+    const float4* q4 = reinterpret_cast<const float4*>(qs);
+#pragma unroll 2
+    for (int c = 0; c < (D >> 3); ++c) {
+        const uint4 kv = __ldg(k4 + c);
+        const float4 qa = q4[2 * c], qb = q4[2 * c + 1];
+        const uint32_t w[4] = {kv.x, kv.y, kv.z, kv.w};
+        const float qv[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float lo, hi;
+            unpack2<T16>(w[i], lo, hi);
+            acc = fmaf(qv[2 * i], lo, acc);
+            acc = fmaf(qv[2 * i + 1], hi, acc);
+        }
+    }
+    return acc;
+}
+template <>
+__device__ __forceinline__ float dot_q<__nv_bfloat16>(const float* __restrict__ qs, const __nv_bfloat16* __restrict__ krow, int D) {
+    return dot_q16<__nv_bfloat16>(qs, krow, D);
+}
+template <>
+__device__ __forceinline__ float dot_q<__half>(const float* __restrict__ qs, const __half* __restrict__ krow, int D) {
+    return dot_q16<__half>(qs, krow, D);
+}
+
+template <typename T>
+__device__ __forceinline__ float2 ld_pair(const T* p);
+template <>
+__device__ __forceinline__ float2 ld_pair<float>(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
+template <>
+__device__ __forceinline__ float2 ld_pair<__nv_bfloat16>(const __nv_bfloat16* p) {
+    const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(p));
+    return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+}
+template <>
+__device__ __forceinline__ float2 ld_pair<__half>(const __half* p) {
+    const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(p));
+    return __half22float2(*reinterpret_cast<const __half2*>(&w));
+}
+template <typename T>
+__device__ __forceinline__ void st_pair(T* p, float a, float b);
+template <>
+__device__ __forceinline__ void st_pair<float>(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
+template <>
+__device__ __forceinline__ void st_pair<__nv_bfloat16>(__nv_bfloat16* p, float a, float b) {
+    *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(a, b);
+}
+template <>
+__device__ __forceinline__ void st_pair<__half>(__half* p, float a, float b) { *reinterpret_cast<__half2*>(p) = __floats2half2_rn(a, b); }
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+template <typename T, typename IdxT>
+__global__ void __launch_bounds__(kAttnWarps * 32)
+sparse_attention_kernel(const IdxT* __restrict__ crow, const IdxT* __restrict__ col, int64_t Z,
+                        const T* __restrict__ q, int64_t q_sn, int64_t q_sh, int64_t q_st,
+                        const T* __restrict__ k, int64_t k_sn, int64_t k_sh, int64_t k_st,
+                        const T* __restrict__ v, int64_t v_sn, int64_t v_sh, int64_t v_st,
+                        const float* __restrict__ scales, const T* __restrict__ cumavg, int use_scaler,
+                        T* __restrict__ out, float* __restrict__ probs_values,
+                        int N, int H, int T_DST, int T_SRC, int D) {
+    extern __shared__ __align__(16) float smem[];
+    float* qs = smem;                                         // [H][D] fp32
+    int64_t* hp = reinterpret_cast<int64_t*>(qs + H * D);      // [H+1] absolute entry offsets
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int n = blockIdx.x / T_DST, t = blockIdx.x % T_DST;
+    const int tq = T_SRC - T_DST + t;                          // absolute position of the query row
+    const IdxT* colr = col + (int64_t) n * Z;
+    const int64_t rs = (int64_t) crow[(int64_t) n * (T_DST + 1) + t];
+    const int64_t re = (int64_t) crow[(int64_t) n * (T_DST + 1) + t + 1];
+    for (int idx = tid; idx < H * D; idx += kAttnWarps * 32) {
+        const int h = idx / D, c = idx % D;
+        qs[idx] = to_f32(q[(int64_t) n * q_sn + (int64_t) h * q_sh + (int64_t) t * q_st + c]);
+    }
+    for (int h = tid; h <= H; h += kAttnWarps * 32) {
+        // first entry whose column id >= h*T_SRC
+        const int64_t key = (int64_t) h * T_SRC;
+        int64_t lo = rs, hi = re;
+        while (lo < hi) {
+            const int64_t mid = (lo + hi) >> 1;
+            if ((int64_t) colr[mid] < key) lo = mid + 1; else hi = mid;
+        }
+        hp[h] = lo;
+    }
+    __syncthreads();
+    constexpr float kLog2e = 1.4426950408889634f;
+    for (int h = wid; h < H; h += kAttnWarps) {
+        const int64_t s0 = hp[h], s1 = hp[h + 1];
+        const float* qh = qs + h * D;
+        const T* kb = k + (int64_t) n * k_sn + (int64_t) h * k_sh;
+        const T* vb = v + (int64_t) n * v_sn + (int64_t) h * v_sh;
+        float m_run = -INFINITY, l_run = 0.f;
+        float acc[2 * kMaxPairs];
+#pragma unroll
+        for (int i = 0; i < 2 * kMaxPairs; ++i) acc[i] = 0.f;
+        for (int64_t base = s0; base < s1; base += 32) {
+            const int64_t z = base + lane;
+            const bool valid = z < s1;
+            int j = 0;
+            float sc = -INFINITY;
+            if (valid) {
+                j = (int) ((int64_t) colr[z] - (int64_t) h * T_SRC);
+                sc = dot_q<T>(qh, kb + (int64_t) j * k_st, D);
+                if (probs_values != nullptr) probs_values[(int64_t) n * Z + z] = sc;
+            }
+            const float m_new = fmaxf(m_run, warp_max(sc));
+            const float alpha = exp2f((m_run - m_new) * kLog2e);   // m_run = -inf -> 0
+            const float p = valid ? exp2f((sc - m_new) * kLog2e) : 0.f;
+            l_run = l_run * alpha + warp_sum(p);
+#pragma unroll
+            for (int i = 0; i < 2 * kMaxPairs; ++i) acc[i] *= alpha;
+            m_run = m_new;
+            const int nvalid = (int) min((int64_t) 32, s1 - base);
+            for (int e = 0; e < nvalid; ++e) {
+                const float pe = __shfl_sync(kFull, p, e);
+                const int je = __shfl_sync(kFull, j, e);
+                const T* vrow = vb + (int64_t) je * v_st;
+#pragma unroll
+                for (int i = 0; i < kMaxPairs; ++i) {
+                    const int d = 2 * lane + 64 * i;
+                    if (d < D) {
+                        const float2 vv = ld_pair<T>(vrow + d);
+                        acc[2 * i] = fmaf(pe, vv.x, acc[2 * i]);
+                        acc[2 * i + 1] = fmaf(pe, vv.y, acc[2 * i + 1]);
+                    }
+                }
+            }
+        }
+        const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
+        const float* sp = scales + ((((int64_t) n * H + h) * T_DST + t) << 1);
+        const float psc = use_scaler ? sigmoidf_(sp[0]) : 1.0f;
+        const float a = sigmoidf_(sp[1]);
+        T* orow = out + ((int64_t) n * T_DST + t) * ((int64_t) H * D) + (int64_t) h * D;
+        const T* arow = cumavg ? cumavg + (((int64_t) n * H + h) * T_DST + t) * D : nullptr;
+#pragma unroll
+        for (int i = 0; i < kMaxPairs; ++i) {
+            const int d = 2 * lane + 64 * i;
+            if (d < D) {
+                float c0 = acc[2 * i] * inv * psc, c1 = acc[2 * i + 1] * inv * psc;
+                if (arow) {
+                    const float2 av = ld_pair<T>(arow + d);
+                    c0 = c0 * a + (1.0f - a) * av.x;
+                    c1 = c1 * a + (1.0f - a) * av.y;
+                }
+                st_pair<T>(orow + d, c0, c1);
+            }
+        }
+        if (probs_values != nullptr) {
+            for (int64_t z = s0 + lane; z < s1; z += 32) {
+                float* pv = probs_values + (int64_t) n * Z + z;
+                *pv = exp2f((*pv - m_run) * kLog2e) * inv * psc;
+            }
+        }
+    }
+    (void) tq;
+}
+
+}  // namespace sea
+
+using namespace sea;
+
+extern "C" {
+
+int sea_sparse_attention_fwd(const void* crow, const void* col, int idx64, int64_t Z,
+                             const void* q, int64_t q_sn, int64_t q_sh, int64_t q_st,
+                             const void* k, int64_t k_sn, int64_t k_sh, int64_t k_st,
+                             const void* v, int64_t v_sn, int64_t v_sh, int64_t v_st,
+                             const float* scales, const void* cumavg, int use_scaler, int dtype, void* out,
+                             float* probs_values, int N, int H, int T_DST, int T_SRC, int D, void* stream) {
+    SEA_CHECK_ARG(crow && (col || Z == 0) && q && k && v && scales && out, "sea_sparse_attention_fwd: null pointer");
+    SEA_CHECK_ARG(N > 0 && H > 0 && T_DST > 0 && T_SRC >= T_DST && D > 0, "sea_sparse_attention_fwd: bad shape");
+    SEA_CHECK_ARG(D % 8 == 0 && D <= 64 * kMaxPairs, "sea_sparse_attention_fwd: head dim %d unsupported (multiple of 8, <= %d)", D, 64 * kMaxPairs);
+    SEA_CHECK_ARG((k_st % 8) == 0 && (k_sh % 8) == 0 && (k_sn % 8) == 0 && (v_st % 2) == 0 && (v_sh % 2) == 0 && (v_sn % 2) == 0,
+                  "sea_sparse_attention_fwd: k/v strides must keep rows 16-byte aligned");
+    SEA_CHECK_ARG((((uintptr_t) k) & 15) == 0 && (((uintptr_t) v) & 15) == 0 && (((uintptr_t) out) & 15) == 0, "sea_sparse_attention_fwd: k/v/out must be 16-byte aligned");
+    const size_t smem = (size_t) H * D * sizeof(float) + (size_t) (H + 1) * sizeof(int64_t) + 16;
+    SEA_CHECK_ARG(smem <= 227 * 1024, "sea_sparse_attention_fwd: H*D too large");
+    SEA_DISPATCH_DTYPE(dtype, T_, SEA_DISPATCH_IDX(idx64, I, {
+        auto kern = sparse_attention_kernel<T_, I>;
+        SEA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem), "smem attr");
+        kern<<<(unsigned) ((int64_t) N * T_DST), kAttnWarps * 32, smem, (cudaStream_t) stream>>>(
+            (const I*) crow, (const I*) col, Z, (const T_*) q, q_sn, q_sh, q_st, (const T_*) k, k_sn, k_sh, k_st,
+            (const T_*) v, v_sn, v_sh, v_st, scales, (const T_*) cumavg, use_scaler, (T_*) out, probs_values,
+            N, H, T_DST, T_SRC, D);
+        SEA_CHECK_LAUNCH("sparse_attention_kernel");
+    }));
+    return SEA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,311 @@
+"""Host-side mirror of the reference operator package `src/models/perlin_attention/ops/__init__.py:1-7`
+(same names, argument meaning and error behaviour), backed by the sm_100a kernels of libsea_b200.so.
+
+Every function takes CUDA tensors, allocates its outputs with torch (ownership convention of the
+reference: ops return fresh tensors, inputs are never mutated) and launches on torch's current stream.
+Nothing here computes on the CPU and there is no fallback: a missing library or a CPU tensor raises.
+"""
+import math
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import SeaError
+
+_DTYPES = {torch.float32: _lib.SEA_DTYPE_F32, torch.bfloat16: _lib.SEA_DTYPE_BF16, torch.float16: _lib.SEA_DTYPE_F16}
+
+
+def _dtype_code(t: torch.Tensor) -> int:
+    try:
+        return _DTYPES[t.dtype]
+    except KeyError:
+        raise SeaError(f'unsupported dtype {t.dtype}')
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise SeaError('sea-attention_b200 ops run on CUDA tensors only (no CPU fallback)')
+
+
+def _p(t: Optional[torch.Tensor]) -> int:
+    return 0 if t is None else t.data_ptr()
+
+
+def _inner_contig(t: torch.Tensor) -> torch.Tensor:
+    return t if t.stride(-1) == 1 else t.contiguous()
+
+
+def _idx64(crow: torch.Tensor, col: torch.Tensor) -> int:
+    if crow.dtype != col.dtype or crow.dtype not in (torch.int32, torch.int64):
+        raise SeaError('crow/col indices must both be int32 or both int64')
+    return 1 if crow.dtype == torch.int64 else 0
+
+
+# --------------------------------------------------------------------------------------------- masks
+def mask_to_bits(mask: torch.Tensor) -> torch.Tensor:
+    """0/1 float mask [N,H,T,P] -> u32 bit rows [N,T,ceil(H*P/32)] (bit h*P+m)."""
+    _cuda(mask)
+    N, H, T, P = mask.shape
+    m = _inner_contig(mask.float())
+    bits = torch.empty((N, T, (H * P + 31) // 32), dtype=torch.int32, device=mask.device)
+    _lib.call('sea_mask_float_to_bits', m.data_ptr(), m.stride(0), m.stride(1), m.stride(2), bits.data_ptr(), N, H, T, P, _stream())
+    return bits
+
+
+def bits_to_mask(bits: torch.Tensor, H: int, P: int) -> torch.Tensor:
+    _cuda(bits)
+    N, T, _ = bits.shape
+    out = torch.empty((N, H, T, P), dtype=torch.float32, device=bits.device)
+    _lib.call('sea_mask_bits_to_float', bits.data_ptr(), out.data_ptr(), N, H, T, P, _stream())
+    return out
+
+
+def topk_mask_bits(probs: torch.Tensor, k_per_group: torch.Tensor, group_mode: str = 'causal_batch',
+                   row_valid: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Grouped top-k (reference attention.py:774-947).  probs [N,H,T,P] fp32; k_per_group is the
+    reference's `per_item_top_k` ([N*T] for 'causal_batch', [N] for 'query')."""
+    _cuda(probs, k_per_group, row_valid)
+    N, H, T, P = probs.shape
+    pr = _inner_contig(probs.float())
+    kg = k_per_group.reshape(-1).float().contiguous()
+    mode = {'causal_batch': 0, 'query': 1}[group_mode]
+    if kg.numel() != (N * T if mode == 0 else N):
+        raise SeaError('k_per_group has the wrong number of groups')
+    rv = None if row_valid is None else row_valid.reshape(N, T).to(torch.uint8).contiguous()
+    bits = torch.empty((N, T, (H * P + 31) // 32), dtype=torch.int32, device=probs.device)
+    _lib.call('sea_topk_mask_bits', pr.data_ptr(), pr.stride(0), pr.stride(1), pr.stride(2), kg.data_ptr(), _p(rv),
+              bits.data_ptr(), N, H, T, P, mode, _stream())
+    return bits
+
+
+# --------------------------------------------------------------------------------------------- a8
+def csr_from_bits(bits: torch.Tensor, H: int, P: int, k: int, T_SRC: int, is_causal: bool = True,
+                  index_dtype=torch.int64, z_alloc: Optional[int] = None):
+    """bit mask -> (crow, col, Z).  z_alloc=None reads the exact nnz back (one host sync, like the
+    reference's `.item()` at causal_resize_m_to_t.py:667); an int skips the sync and over-allocates."""
+    N, T_DST, _ = bits.shape
+    idx64 = 1 if index_dtype == torch.int64 else 0
+    crow = torch.empty((N, T_DST + 1), dtype=index_dtype, device=bits.device)
+    _lib.call('sea_csr_count', bits.data_ptr(), crow.data_ptr(), idx64, N, H, T_DST, P, T_SRC, int(k), int(is_causal), _stream())
+    Z = int(crow[:, -1].max().item()) if z_alloc is None else int(z_alloc)
+    col = torch.empty((N, Z), dtype=index_dtype, device=bits.device)
+    _lib.call('sea_csr_fill', bits.data_ptr(), crow.data_ptr(), col.data_ptr(), idx64, Z, N, H, T_DST, P, T_SRC, int(k),
+              int(is_causal), _stream())
+    return crow, col, Z
+
+
+def resize_from_m_to_t_csr(x, masked_fill_value, k, target_width=None, training=False, need_assert=False, is_causal=True,
+                           max_col_z=None, benchmarking=False, oversampled=None):
+    """Mirror of ops/kernels/causal_resize_m_to_t.py:910-921.  x: 0/1 mask [N,H,T_DST,T_M] ->
+    batched torch.sparse_csr_tensor [N, T_DST, H*T_SRC] (int64 indices, values = ones of x.dtype)."""
+    assert not training
+    assert masked_fill_value == 0
+    _cuda(x)
+    N, H, T_DST, T_M = x.shape
+    T_SRC = target_width if target_width is not None else T_DST
+    bits = mask_to_bits(x)
+    crow, col, Z = csr_from_bits(bits, H, T_M, k, T_SRC, is_causal=is_causal, index_dtype=torch.int64)
+    values = torch.ones((N, Z), dtype=x.dtype, device=x.device)
+    return torch.sparse_csr_tensor(crow_indices=crow, col_indices=col, values=values, size=(N, T_DST, H * T_SRC))
+
+
+def flat_csr_to_dense(csr: torch.Tensor, T_SRC: int, H: int) -> torch.Tensor:
+    """Mirror of ops/kernels/flat_csr_to_dense.py:3 -> [N,H,T_DST,T_SRC]."""
+    assert csr.is_sparse_csr
+    N, T_DST, H_T = csr.shape
+    crow, col, values = csr.crow_indices(), csr.col_indices(), csr.values()
+    _cuda(crow)
+    out = torch.empty((N, H, T_DST, T_SRC), dtype=torch.float32, device=crow.device)
+    vals = values.float().contiguous()
+    _lib.call('sea_flat_csr_to_dense', crow.data_ptr(), col.data_ptr(), _idx64(crow, col), vals.data_ptr(), col.shape[-1],
+              out.data_ptr(), N, H, T_DST, T_SRC, _stream())
+    return out.to(values.dtype)
+
+
+# --------------------------------------------------------------------------------------------- a9-a12
+def _rebuild(csr, values):
+    return torch.sparse_csr_tensor(crow_indices=csr.crow_indices(), col_indices=csr.col_indices(), values=values, size=csr.shape)
+
+
+def flat_csr_masked_bmm(a: torch.Tensor, b: torch.Tensor, mask: torch.Tensor, max_z_per_row: int = None):
+    """Mirror of ops/kernels/flat_csr_masked_bmm.py:137."""
+    assert mask.is_sparse_csr
+    assert a.ndim == b.ndim
+    assert a.ndim == 4
+    N, H, T_DST, HID = a.shape
+    assert b.shape[:2] == (N, H)
+    _, _, T_SRC, HID = b.shape
+    assert mask.shape == (N, T_DST, H * T_SRC)
+    _cuda(a, b)
+    if a.dtype != b.dtype:
+        raise SeaError('a and b must share a dtype')
+    a, b = _inner_contig(a), _inner_contig(b)
+    crow, col = mask.crow_indices(), mask.col_indices()
+    Z = col.shape[-1]
+    out = torch.zeros((N, Z), dtype=torch.float32, device=a.device)
+    _lib.call('sea_flat_csr_masked_bmm', crow.data_ptr(), col.data_ptr(), _idx64(crow, col), Z,
+              a.data_ptr(), a.stride(0), a.stride(1), a.stride(2), b.data_ptr(), b.stride(0), b.stride(1), b.stride(2),
+              _dtype_code(a), out.data_ptr(), N, H, T_DST, T_SRC, HID, _stream())
+    return _rebuild(mask, out.to(mask.values().dtype))
+
+
+def flat_csr_softmax(scores: torch.Tensor, H: int, T_SRC: int, max_z_per_row: int = None):
+    """Mirror of ops/kernels/flat_csr_softmax.py:127."""
+    assert scores.is_sparse_csr
+    crow, col = scores.crow_indices(), scores.col_indices()
+    _cuda(crow)
+    vin = scores.values().float().contiguous()
+    N, R1 = crow.shape
+    out = torch.zeros_like(vin)
+    _lib.call('sea_flat_csr_softmax', crow.data_ptr(), col.data_ptr(), _idx64(crow, col), col.shape[-1], vin.data_ptr(),
+              out.data_ptr(), N, H, R1 - 1, T_SRC, _stream())
+    return _rebuild(scores, out.to(scores.values().dtype))
+
+
+def flat_csr_elmul(probs: torch.Tensor, dense: torch.Tensor, max_z_per_row: int = None):
+    """Mirror of ops/kernels/flat_csr_elmul.py:110 (dense may be a stride-0 expanded view)."""
+    assert probs.is_sparse_csr
+    N, T_DST, H_T = probs.shape
+    _N, H, _T_DST, T = dense.shape
+    assert T_DST == _T_DST
+    assert N == _N
+    assert H_T == H * T
+    crow, col = probs.crow_indices(), probs.col_indices()
+    _cuda(crow, dense)
+    vin = probs.values().float().contiguous()
+    d = dense if dense.dtype == torch.float32 else dense.float()
+    out = torch.zeros_like(vin)
+    _lib.call('sea_flat_csr_elmul', crow.data_ptr(), col.data_ptr(), _idx64(crow, col), col.shape[-1], vin.data_ptr(),
+              out.data_ptr(), d.data_ptr(), d.stride(0), d.stride(1), d.stride(2), d.stride(3), N, H, T_DST, T, _stream())
+    return _rebuild(probs, out.to(probs.values().dtype))
+
+
+def flat_csr_sdbmm(scores: torch.Tensor, value_layer: torch.Tensor, T_M: int, max_z_per_row: int = None, benchmarking: bool = False):
+    """Mirror of ops/kernels/flat_csr_sdbmm.py:323 -> dense fp32 [N,H,T_DST,HID]."""
+    assert scores.is_sparse_csr
+    crow, col = scores.crow_indices(), scores.col_indices()
+    _cuda(crow, value_layer)
+    N, R1 = crow.shape
+    _N, H, T_SRC, HID = value_layer.shape
+    assert N == _N
+    _N, T_DST, HT_SRC = scores.shape
+    assert HT_SRC == H * T_SRC
+    v = _inner_contig(value_layer)
+    vals = scores.values().float().contiguous()
+    out = torch.empty((N, H, T_DST, HID), dtype=torch.float32, device=v.device)
+    _lib.call('sea_flat_csr_sdbmm', crow.data_ptr(), col.data_ptr(), _idx64(crow, col), col.shape[-1], vals.data_ptr(),
+              v.data_ptr(), v.stride(0), v.stride(1), v.stride(2), _dtype_code(v), out.data_ptr(), N, H, T_DST, T_SRC, HID, _stream())
+    return out
+
+
+# --------------------------------------------------------------------------------------------- a16
+def resize_from_m_to_t(x: torch.Tensor, masked_fill_value: float, attention_mask: torch.Tensor, target_width: int = None,
+                       training=False, is_causal=True, k=None, oversampled=None):
+    """Mirror of ops/kernels/resize_m_to_t.py:6 (inference form: training=False, oversampled None/1.0)."""
+    assert masked_fill_value is not None
+    if training:
+        raise SeaError('resize_from_m_to_t: the training-time jitter (resize_m_to_t.py:40-45) is not part of the hot path')
+    if oversampled is not None and float(oversampled) != 1.0:
+        raise SeaError('resize_from_m_to_t: k_oversample != 1.0 is not supported')
+    _cuda(x, attention_mask)
+    N, H, T1, T_M = x.shape
+    _N, _H, _TQ, _TK = attention_mask.shape
+    assert _H == 1
+    T2 = target_width if target_width is not None else T1
+    if is_causal:
+        assert attention_mask.shape == (N, 1, T1, T2)
+    else:
+        assert attention_mask.shape == (N, 1, 1, T2), f"{attention_mask.shape} == {T2}"
+    am = _inner_contig(attention_mask.float())
+    xs = x.float().contiguous()
+    out = torch.empty((N, H, T1, T2), dtype=torch.float32, device=x.device)
+    _lib.call('sea_resize_m_to_t_dense', xs.data_ptr(), float(masked_fill_value), am.data_ptr(), am.stride(0),
+              am.stride(2) if is_causal else 0, out.data_ptr(), N, H, T1, T_M, T2, _stream())
+    return out.to(x.dtype)
+
+
+# --------------------------------------------------------------------------------------------- dense stages
+def performer_causal(q, k, v, pos_emb, proj, want_cumavg=True):
+    """a2+a3 (+ running mean of v).  q,k,v [N,H,T,D]; pos_emb fp32 [>=T, D]; proj fp32 [F, D]
+    -> ctx [N,H,T,2D], cumavg [N,H,T,D] (dtype of q)."""
+    _cuda(q, k, v, pos_emb, proj)
+    N, H, T, D = q.shape
+    F = proj.shape[0]
+    q, k, v = _inner_contig(q), _inner_contig(k), _inner_contig(v)
+    pos = pos_emb.reshape(-1, D).float().contiguous()
+    if pos.shape[0] < T:
+        raise SeaError(f'v_eye_learned_causal holds {pos.shape[0]} positions < T={T}')
+    pj = proj.float().contiguous()
+    ctx = torch.empty((N, H, T, 2 * D), dtype=q.dtype, device=q.device)
+    avg = torch.empty((N, H, T, D), dtype=q.dtype, device=q.device) if want_cumavg else None
+    ws = torch.empty((_lib.load().sea_performer_workspace_floats(N, H, T, D, F),), dtype=torch.float32, device=q.device)
+    _lib.call('sea_performer_causal_fwd', q.data_ptr(), q.stride(0), q.stride(1), q.stride(2),
+              k.data_ptr(), k.stride(0), k.stride(1), k.stride(2), v.data_ptr(), v.stride(0), v.stride(1), v.stride(2),
+              pos.data_ptr(), pj.data_ptr(), _dtype_code(q), ctx.data_ptr(), _p(avg), ws.data_ptr(), N, H, T, D, F, _stream())
+    return ctx, avg
+
+
+def predictor_mlp(ctx, v, w, S: int, W: int, want_t_pred=False):
+    """a4.  `w` = dict of fp32 contiguous weights (enc_w, enc_b, enc_ln_w, enc_ln_b, dec_w, dec_b, cnn_ln_w, cnn_ln_b,
+    scl_w, scl_b) -> cnn_in [N,T,W,H*S] channels-last, scales fp32 [N,H,T,2], t_pred or None."""
+    _cuda(ctx, v)
+    N, H, T, D2 = ctx.shape
+    D = D2 // 2
+    v = _inner_contig(v)
+    cnn_in = torch.empty((N, T, W, H * S), dtype=ctx.dtype, device=ctx.device)
+    scales = torch.empty((N, H, T, 2), dtype=torch.float32, device=ctx.device)
+    t_pred = torch.empty((N, H, T, D2), dtype=ctx.dtype, device=ctx.device) if want_t_pred else None
+    _lib.call('sea_predictor_mlp_fwd', ctx.data_ptr(), v.data_ptr(), v.stride(0), v.stride(1), v.stride(2), _dtype_code(ctx),
+              w['enc_w'].data_ptr(), w['enc_b'].data_ptr(), w['enc_ln_w'].data_ptr(), w['enc_ln_b'].data_ptr(),
+              w['dec_w'].data_ptr(), w['dec_b'].data_ptr(), w['cnn_ln_w'].data_ptr(), w['cnn_ln_b'].data_ptr(),
+              w['scl_w'].data_ptr(), w['scl_b'].data_ptr(), cnn_in.data_ptr(), scales.data_ptr(), _p(t_pred),
+              N, H, T, D, S, W, _stream())
+    return cnn_in, scales, t_pred
+
+
+def causal_conv3x3_dil2_relu(x, weight, bias):
+    """a5: one CausalConv2d(C,O,3,padding=2,dilation=2,causal)+ReLU on channels-last x [N,T,W,C];
+    weight fp32 in the reference layout [O,C,5,3]."""
+    _cuda(x, weight, bias)
+    N, T, W, C = x.shape
+    O = weight.shape[0]
+    y = torch.empty((N, T, W, O), dtype=x.dtype, device=x.device)
+    _lib.call('sea_causal_conv3x3_dil2_relu', x.data_ptr(), weight.data_ptr(), bias.data_ptr(), y.data_ptr(), _dtype_code(x),
+              N, T, W, C, O, _stream())
+    return y
+
+
+def predictor_tail(x, weight, bias, ln_w, ln_b, P: int, want_scores=False):
+    """a5 tail + a6 -> probs fp32 [N,H,T,P] (and the pre-softmax scores when asked)."""
+    _cuda(x, weight)
+    N, T, W, C = x.shape
+    H = weight.shape[0]
+    probs = torch.empty((N, H, T, P), dtype=torch.float32, device=x.device)
+    scores = torch.empty_like(probs) if want_scores else None
+    _lib.call('sea_predictor_tail_fwd', x.data_ptr(), _dtype_code(x), weight.data_ptr(), bias.data_ptr(), ln_w.data_ptr(),
+              ln_b.data_ptr(), probs.data_ptr(), _p(scores), N, H, T, W, C, P, _stream())
+    return probs, scores
+
+
+def sparse_attention(crow, col, q, k, v, scales, cumavg, use_scaler=True, want_probs=False):
+    """a9-a14 fused -> context [N,T_DST,H*D] (dtype of q) and, when asked, the probabilities [N,Z] fp32."""
+    _cuda(crow, col, q, k, v, scales, cumavg)
+    N, H, T_DST, D = q.shape
+    T_SRC = k.shape[2]
+    q, k, v = _inner_contig(q), _inner_contig(k), _inner_contig(v)
+    Z = col.shape[-1]
+    out = torch.empty((N, T_DST, H * D), dtype=q.dtype, device=q.device)
+    pv = torch.zeros((N, Z), dtype=torch.float32, device=q.device) if want_probs else None
+    sc = scales.float().contiguous()
+    ca = None if cumavg is None else cumavg.contiguous()
+    _lib.call('sea_sparse_attention_fwd', crow.data_ptr(), col.data_ptr(), _idx64(crow, col), Z,
+              q.data_ptr(), q.stride(0), q.stride(1), q.stride(2), k.data_ptr(), k.stride(0), k.stride(1), k.stride(2),
+              v.data_ptr(), v.stride(0), v.stride(1), v.stride(2), sc.data_ptr(), _p(ca), int(bool(use_scaler)), _dtype_code(q),
+              out.data_ptr(), _p(pv), N, H, T_DST, T_SRC, D, _stream())
+    return out, pv
