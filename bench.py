@@ -1,0 +1,321 @@
+"""Headline benchmark: SEA attention layer forward, tokens/s at the OPT-1.3B shape (32 heads, d=64,
+seq 4096, k=64, predictor length 256, nbf=8), bf16, 1..8 B200 (BASELINE.json `metric`).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One step = one PerlinAttention forward over one synthetic batch item per GPU (weak scaling: the path
+shards by batch with no collective).  Timing: CUDA events around every step on the launch
+stream, L2 flushed (256 MiB memset) between steps, barrier + synchronize on both sides, max over ranks.
+`value`  : inputs resident in HBM.            `e2e` : pinned-host q,k,v -> device, forward, context -> host.
+`roofline`: dominant kernel, algorithmic bytes (SURVEY 8d stage model) / its mean launch time.
+`cpu_baseline` / `--impl reference`: the reference's dense torch path restated in oracle/ (the reference
+is python and cannot travel to the GPU box), timed on the host cores on a bounded sample.
+"""
+import argparse
+import importlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = 'SEA attn fwd tokens/sec @OPT-1.3B 4k ctx'
+UNIT = 'tokens/s'
+NS = dict(H=32, d=64, T=4096, P=256, k=64, nbf=8)
+CPU_SAMPLE_T = 2048
+
+
+def _peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d['hbm_gbs'], d.get('bf16_tflops_sustained', d.get('bf16_tflops')), 'measured'
+    return 6650.0, 1590.0, 'fallback'
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index):
+        self.index, self.samples, self.stop_flag, self.thread = index, [], False, None
+
+    def _run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}', '--format=csv,noheader,nounits'],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(',')])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def start(self):
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+
+    def stop(self):
+        self.stop_flag = True
+        if self.thread:
+            self.thread.join(timeout=6)
+        sm = [int(s[0]) for s in self.samples if s[0].isdigit()]
+        mx = [int(s[1]) for s in self.samples if s[1].isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = sorted({names[i] for s in self.samples for i in range(4) if len(s) > 2 + i and s[2 + i].lower().startswith('active')})
+        return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': max(mx) if mx else None, 'reasons': reasons,
+                'samples': len(self.samples)}
+
+
+def stage_bytes(N, H, d, T, P, k, F, b, Z):
+    """ALGORITHMIC bytes per stage: every stage reads its inputs once and writes its outputs once."""
+    NHTd = N * H * T * d
+    NHT = N * H * T
+    return {
+        'performer': 3 * NHTd * b + 2 * NHTd * b + NHTd * b + F * d * 4 + T * d * 4,          # q,k,v in; ctx (2d) + cumavg out
+        'mlp': 2 * NHTd * b + NHTd * b + NHT * (P // 2) * b + NHT * 8,                         # ctx, v in; cnn_in, scales out
+        'conv': 2 * NHT * (P // 2) * b,                                                        # per conv: in + out
+        'tail': NHT * (P // 2) * b + NHT * P * 4,                                              # conv out in; probs fp32 out
+        'topk': NHT * P * 4 + N * T * H * P // 8,                                              # probs in; bitmask out
+        'csr': N * T * H * P // 8 * 2 + N * (T + 1) * 4 + Z * 4,                               # bitmask in (count+fill); crow, col (int32) out
+        'attn': 3 * NHTd * b + Z * 4 + NHT * 8 + NHTd * b + NHTd * b,                          # q,k,v, col, scales, cumavg in; ctx out
+    }
+
+
+def stage_flops(N, H, d, T, P, k, F, Z):
+    C = 2 * H
+    return {
+        'performer': 4 * N * H * T * d * F + 8 * N * H * T * F * d,
+        'mlp': 2 * N * H * T * (3 * d * 2 * d + 2 * d * (P // 2) + 2 * d * 2),
+        'conv': 2 * N * T * (P // 4) * C * C * 9,
+        'tail': 2 * N * T * (P // 4) * C * H,
+        'attn': 4 * Z * d,
+    }
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path.  /root/reference is python and absent
+    on the GPU box, so this times its restatement (oracle/sea_oracle.py, dense torch path = what the reference
+    itself runs on a CPU, attention.py benchmarking=False) with every host thread."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    from oracle import sea_oracle as so
+    import transformers
+    sea = importlib.import_module('sea-attention_b200')
+    torch.set_num_threads(os.cpu_count())
+    H, d, P, k, nbf = NS['H'], NS['d'], NS['P'], NS['k'], NS['nbf']
+    T = CPU_SAMPLE_T
+    torch.manual_seed(42)
+    cfg = transformers.BertConfig(hidden_size=H * d, num_attention_heads=H, max_position_embeddings=NS['T'])
+    mod = sea.PerlinAttention(cfg, sea.PerlinAttentionConfig(performer_nb_factor=nbf, k=k, attention_predictor_length=P, causal=True)).eval()
+    sd = {k_: v_.detach().float() for k_, v_ in mod.state_dict().items() if 'enc_per_layer' not in k_}
+    q = torch.randn(1, H, T, d) * d ** -0.5
+    kk = torch.randn(1, H, T, d)
+    v = torch.randn(1, H, T, d)
+    with torch.no_grad():
+        for _ in range(max(1, min(args.warmup, 2))):
+            so.perlin_forward_causal(sd, q, kk, v, k_top=k, P=P, sparse=False)
+        steps = max(1, min(args.steps, 10))
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            so.perlin_forward_causal(sd, q, kk, v, k_top=k, P=P, sparse=False)
+        dt = (time.perf_counter() - t0) / steps
+    val = T / dt
+    sample = f'first {T} of {NS["T"]} tokens of the north-star layer (causal prefix), fp32 dense torch path, {steps} steps'
+    line = {
+        'metric': METRIC, 'value': val, 'unit': UNIT, 'impl': 'reference', 'n_gpus': args.gpus, 'steps': steps, 'warmup': args.warmup,
+        'ms_per_step': dt * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'SEA attention layer fwd, OPT-1.3B shape: 32 heads d=64 seq 4096 k=64 predictor_length=256 nbf=8, causal, N=1/GPU',
+                   'sample': sample},
+        'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port', 'sample': sample},
+        'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='sea')
+    ap.add_argument('--dtype', default='bf16')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        return run_reference(args)
+
+    import transformers
+    sea = importlib.import_module('sea-attention_b200')
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    dev = torch.device('cuda', local_rank)
+    torch.cuda.set_device(dev)
+    dt = {'bf16': torch.bfloat16, 'fp32': torch.float32, 'fp16': torch.float16}[args.dtype]
+    H, d, T, P, k, nbf = (NS[x] for x in ('H', 'd', 'T', 'P', 'k', 'nbf'))
+    N = 1                                                     # batch items per GPU (weak scaling)
+    torch.manual_seed(42 + rank)
+    cfg = transformers.BertConfig(hidden_size=H * d, num_attention_heads=H, max_position_embeddings=T)
+    pc = sea.PerlinAttentionConfig(performer_nb_factor=nbf, k=k, attention_predictor_length=P, causal=True)
+    mod = sea.PerlinAttention(cfg, pc).eval().to(dev)
+    mod.benchmarking = True
+    mod.check_padding = False                                 # synthetic data has no padding; keeps the step free of host syncs
+    F = mod.performer_nb_features
+    gen = torch.Generator().manual_seed(42 + rank)
+    hq = (torch.randn(N, H, T, d, generator=gen) * d ** -0.5).to(dt).pin_memory()
+    hk = torch.randn(N, H, T, d, generator=gen).to(dt).pin_memory()
+    hv = torch.randn(N, H, T, d, generator=gen).to(dt).pin_memory()
+    hout = torch.empty(N, T, H * d, dtype=dt).pin_memory()
+    q, kk, v = hq.to(dev), hk.to(dev), hv.to(dev)
+    fp_min = torch.finfo(torch.float16).min / 2 if dt != torch.float32 else torch.finfo(torch.float32).min / 2
+    mask = ((torch.arange(T, device=dev).view(1, T) > torch.arange(T, device=dev).view(T, 1)) * fp_min).to(dt).view(1, 1, T, T).expand(N, 1, T, T)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step_device():
+        return mod(q, kk, v, q, kk, v, q, kk, mask, None, None)
+
+    dq, dk, dv = torch.empty_like(q), torch.empty_like(kk), torch.empty_like(v)
+
+    def step_e2e():
+        dq.copy_(hq, non_blocking=True)
+        dk.copy_(hk, non_blocking=True)
+        dv.copy_(hv, non_blocking=True)
+        out = mod(dq, dk, dv, dq, dk, dv, dq, dk, mask, None, None)
+        hout.copy_(out.context_layer, non_blocking=True)
+        return out
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        evs = []
+        for _ in range(steps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            evs.append((e0, e1))
+        barrier()
+        ms = sum(a.elapsed_time(b) for a, b in evs) / steps
+        if dist is not None:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    lib = sea._lib
+    warm = max(args.warmup, 3)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    lib.LAUNCH_COUNT = 0
+    if sampler:
+        sampler.start()
+    ms_dev = timed(step_device, args.steps, warm)
+    launches = getattr(lib, 'LAUNCH_COUNT', 0)
+    ms_e2e = timed(step_e2e, args.steps, warm)
+    clocks = sampler.stop() if sampler else None
+
+    # per-kernel breakdown (instrumented pass: events around every C-ABI call) -> dominant kernel + roofline
+    lib.TRACE = []
+    for _ in range(3):
+        flush.zero_()
+        step_device()
+    torch.cuda.synchronize()
+    per = {}
+    for name, e0, e1 in lib.TRACE:
+        per.setdefault(name, []).append(e0.elapsed_time(e1))
+    lib.TRACE = None
+    out = step_device()
+    torch.cuda.synchronize()
+
+    if rank == 0:
+        hbm, tf, which = _peaks()
+        crow = None
+        mod.output_attentions = True
+        o2 = step_device()
+        Z = int(o2.partial_attention_mask.crow_indices()[0, -1].item())
+        mod.output_attentions = False
+        b = 2 if dt != torch.float32 else 4
+        sb = stage_bytes(N, H, d, T, P, k, F, b, Z)
+        sf = stage_flops(N, H, d, T, P, k, F, Z)
+        entry_stage = {'sea_performer_causal_fwd': 'performer', 'sea_predictor_mlp_fwd': 'mlp', 'sea_causal_conv3x3_dil2_relu': 'conv',
+                       'sea_predictor_tail_fwd': 'tail', 'sea_topk_mask_bits': 'topk', 'sea_csr_count': 'csr', 'sea_csr_fill': 'csr',
+                       'sea_sparse_attention_fwd': 'attn'}
+        kernels = {}
+        for name, times in per.items():
+            st = entry_stage.get(name, name)
+            calls_per_step = len(times) / 3
+            kernels.setdefault(st, {'ms_per_step': 0.0, 'calls_per_step': 0})
+            kernels[st]['ms_per_step'] += sum(times) / 3
+            kernels[st]['calls_per_step'] += calls_per_step
+        dom = max(kernels, key=lambda s: kernels[s]['ms_per_step'])
+        dom_ms_launch = kernels[dom]['ms_per_step'] / max(1.0, kernels[dom]['calls_per_step'] if dom == 'conv' else 1.0)
+        tensor_bound = dom in ('conv', 'mlp')
+        if tensor_bound:
+            ach = sf[dom] / (dom_ms_launch * 1e-3) / 1e12
+            roof = {'kernel': dom, 'bound': 'tensor', 'achieved': ach, 'peak': tf, 'unit': 'TFLOP/s', 'frac': ach / tf, 'traffic': None,
+                    'peak_source': which + ' (sustained)'}
+        else:
+            ach = sb[dom] / (dom_ms_launch * 1e-3) / 1e9
+            roof = {'kernel': dom, 'bound': 'hbm', 'achieved': ach, 'peak': hbm, 'unit': 'GB/s', 'frac': ach / hbm, 'traffic': None,
+                    'peak_source': which}
+        total_bytes = sb['performer'] + sb['mlp'] + 2 * sb['conv'] + sb['tail'] + sb['topk'] + sb['csr'] + sb['attn']
+        tokens = N * T * world
+        line = {
+            'metric': METRIC, 'value': tokens / (ms_dev * 1e-3), 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': warm,
+            'ms_per_step': ms_dev, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': args.dtype, 'data': 'synthetic',
+            'config': {'workload': 'SEA attention layer fwd, OPT-1.3B shape: 32 heads d=64 seq 4096 k=64 predictor_length=256 nbf=8, causal, N=1/GPU',
+                       'sharding': 'batch (one item per GPU, no collective on the hot path)', 'l2': 'flushed between steps (256 MiB memset), per-step CUDA events',
+                       'weights': 'random-init (seed 42)', 'outputs': 'context_layer + estimated_attention_probs (output_attentions=False)', 'nnz': Z},
+            'e2e': {'value': tokens / (ms_e2e * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': 3 * q.numel() * q.element_size(),
+                    'd2h_bytes_per_step': hout.numel() * hout.element_size(), 'ms_per_step': ms_e2e,
+                    'note': 'causal additive mask is a shape constant kept on the device'},
+            'gpu_launches': launches,
+            'roofline': roof,
+            'layer_hbm': {'algorithmic_bytes': total_bytes, 'achieved_gbs': total_bytes / (ms_dev * 1e-3) / 1e9, 'peak_gbs': hbm,
+                          'frac': total_bytes / (ms_dev * 1e-3) / 1e9 / hbm},
+            'kernels_ms_per_step': {s: round(kv['ms_per_step'], 4) for s, kv in kernels.items()},
+            'clocks': clocks,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            from oracle import sea_oracle as so
+            torch.set_num_threads(os.cpu_count())
+            Ts = CPU_SAMPLE_T
+            sd = {k_: v_.detach().float().cpu() for k_, v_ in mod.state_dict().items() if 'enc_per_layer' not in k_}
+            cq, ck, cv = hq[:, :, :Ts].float(), hk[:, :, :Ts].float(), hv[:, :, :Ts].float()
+            with torch.no_grad():
+                so.perlin_forward_causal(sd, cq, ck, cv, k_top=k, P=P, sparse=False)
+                t0 = time.perf_counter()
+                reps = 3
+                for _ in range(reps):
+                    so.perlin_forward_causal(sd, cq, ck, cv, k_top=k, P=P, sparse=False)
+                cdt = (time.perf_counter() - t0) / reps
+            line['cpu_baseline'] = {'value': Ts / cdt, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',
+                                    'sample': f'first {Ts} of {T} tokens (causal prefix) of the same layer, fp32 dense torch path, {reps} steps'}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

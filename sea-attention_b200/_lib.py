@@ -75,10 +75,31 @@ def load():
     return lib
 
 
+# Kernel launches each entry enqueues (bench.py reports the sum as `gpu_launches`).
+KERNELS_PER_CALL = {
+    'sea_topk_mask_bits': 1, 'sea_mask_float_to_bits': 1, 'sea_mask_bits_to_float': 1, 'sea_csr_count': 2, 'sea_csr_fill': 1,
+    'sea_flat_csr_to_dense': 1, 'sea_flat_csr_masked_bmm': 1, 'sea_flat_csr_softmax': 1, 'sea_flat_csr_elmul': 1,
+    'sea_flat_csr_sdbmm': 1, 'sea_resize_m_to_t_dense': 1, 'sea_performer_causal_fwd': 3, 'sea_predictor_mlp_fwd': 1,
+    'sea_causal_conv3x3_dil2_relu': 1, 'sea_predictor_tail_fwd': 1, 'sea_sparse_attention_fwd': 1,
+}
+LAUNCH_COUNT = 0
+TRACE = None   # bench.py sets this to a list to get (entry, start_event, stop_event) per call
+
+
 def call(name, *args):
     """Calls an int-returning entry; raises SeaError with the library's message on failure."""
+    global LAUNCH_COUNT
     lib = load()
-    rc = getattr(lib, name)(*args)
+    LAUNCH_COUNT += KERNELS_PER_CALL.get(name, 1)
+    if TRACE is not None:
+        import torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(lib, name)(*args)
+        e1.record()
+        TRACE.append((name, e0, e1))
+    else:
+        rc = getattr(lib, name)(*args)
     if rc != 0:
         msg = lib.sea_last_error()
         raise SeaError(f'{name} failed (code {rc}): {msg.decode() if msg else ""}')

@@ -1,0 +1,185 @@
+"""GPU parity tests of the dense stages and of the whole PerlinAttention forward, through the drop-in
+module and the C ABI, against (a) the CPU oracle on the same seeded inputs and (b) the fixtures the
+unmodified reference produced (tests/golden, oracle/make_golden.py).
+
+Tolerances (north star): fp32 rtol 1e-3, bf16 rtol 2e-2; masks: bit-exact given identical probabilities,
+>= 99.9 % end to end."""
+import numpy as np
+import pytest
+import torch
+import transformers
+
+from conftest import golden_layer
+from oracle import sea_oracle as so
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+def _module(sea, m, sd, dtype=torch.float32):
+    cfg = transformers.BertConfig(hidden_size=m['H'] * m['d'], num_attention_heads=m['H'], max_position_embeddings=m['T'])
+    pc = sea.PerlinAttentionConfig(performer_nb_factor=m['nbf'], k=m['k'], attention_predictor_length=m['P'], causal=True)
+    mod = sea.PerlinAttention(cfg, pc).eval()
+    missing, unexpected = mod.load_state_dict(sd, strict=False)
+    assert not unexpected
+    mod = mod.to(DEV)
+    mod.benchmarking = True
+    return mod
+
+
+def _random_sd(sea, H, d, T, P, k, nbf, seed=0):
+    torch.manual_seed(seed)
+    cfg = transformers.BertConfig(hidden_size=H * d, num_attention_heads=H, max_position_embeddings=T)
+    pc = sea.PerlinAttentionConfig(performer_nb_factor=nbf, k=k, attention_predictor_length=P, causal=True)
+    mod = sea.PerlinAttention(cfg, pc).eval()
+    # make LayerNorm affine parameters non trivial
+    for n_, p_ in mod.named_parameters():
+        if ('.1.' in n_ or 'cnn.0' in n_ or 'cnn.2' in n_) and p_.ndim == 1:
+            p_.data.add_(0.1 * torch.randn_like(p_))
+    return mod, {k_: v_.detach().clone().float() for k_, v_ in mod.state_dict().items()}
+
+
+STAGE_CASES = [(1, 4, 64, 128, 32, 8, 8), (2, 3, 32, 100, 16, 6, 4), (1, 12, 64, 80, 64, 16, 8), (1, 2, 128, 48, 32, 8, 8)]
+
+
+@pytest.mark.parametrize('N,H,d,T,P,k,nbf', STAGE_CASES)
+def test_dense_stages_match_oracle_fp32(sea, N, H, d, T, P, k, nbf):
+    mod, sd = _random_sd(sea, H, d, T, P, k, nbf)
+    mod = mod.to(DEV)
+    g = torch.Generator().manual_seed(T + d)
+    q = torch.randn(N, H, T, d, generator=g) * d ** -0.5
+    kk = torch.randn(N, H, T, d, generator=g)
+    v = torch.randn(N, H, T, d, generator=g)
+    w = mod._weights_fp32()
+    # a2+a3 and the running mean
+    ctx, avg = sea.ops.performer_causal(q.to(DEV), kk.to(DEV), v.to(DEV), w['pos'], w['proj'])
+    pos = sd['v_eye_learned_causal'][:, :, :T, :].expand(N, H, T, d)
+    ctx_ref = so.performer_causal(q, kk, torch.cat([pos, v], -1), sd['performer.projection_matrix'])
+    torch.testing.assert_close(ctx.cpu(), ctx_ref, rtol=1e-3, atol=1e-4)
+    torch.testing.assert_close(avg.cpu(), v.cumsum(-2) / torch.arange(1, T + 1).view(1, 1, T, 1), rtol=1e-3, atol=1e-5)
+    # a4 (fed with the oracle's ctx so the stage is checked in isolation)
+    S, W = 2, P // 4
+    cnn_in, scales, t_pred = sea.ops.predictor_mlp(ctx_ref.to(DEV), v.to(DEV), w, S, W, want_t_pred=True)
+    t_ref = so.predictor_enc(torch.cat([ctx_ref, v], -1), sd)
+    torch.testing.assert_close(t_pred.cpu(), t_ref, rtol=1e-3, atol=1e-4)
+    torch.testing.assert_close(scales.cpu(), so.predictor_dec_scaler(t_ref, sd), rtol=1e-3, atol=1e-4)
+    dec = so.predictor_dec_row(t_ref, sd, S)                                         # [N, 2H, T, W]
+    x0 = so.layer_norm(dec, sd['attention_predictor_cnn.0.module.weight'], sd['attention_predictor_cnn.0.module.bias'])
+    torch.testing.assert_close(cnn_in.cpu().permute(0, 3, 1, 2), x0, rtol=1e-3, atol=2e-4)
+    # a5 convs, channels-last
+    p_ = 'attention_predictor_cnn.1.module.net.'
+    y_ref = x0
+    y = x0.permute(0, 2, 3, 1).contiguous().to(DEV)
+    for idx, wk in (('0', 'conv1'), ('2', 'conv2')):
+        y_ref = torch.relu(so.causal_conv2d(y_ref, sd[p_ + idx + '.module.weight'], sd[p_ + idx + '.module.weight_mask'],
+                                            sd[p_ + idx + '.module.bias'], 3, 2, 2))
+        y = sea.ops.causal_conv3x3_dil2_relu(y, w[wk + '_w'], w[wk + '_b'])
+        torch.testing.assert_close(y.cpu().permute(0, 3, 1, 2), y_ref, rtol=1e-3, atol=2e-4)
+    # tail + softmax
+    probs, scores = sea.ops.predictor_tail(y_ref.permute(0, 2, 3, 1).contiguous().to(DEV), w['conv3_w'], w['conv3_b'],
+                                           w['out_ln_w'], w['out_ln_b'], P, want_scores=True)
+    score_ref = so.predictor_cnn_causal(dec, sd)
+    torch.testing.assert_close(scores.cpu(), score_ref, rtol=1e-3, atol=5e-4)
+    torch.testing.assert_close(probs.cpu(), torch.softmax(score_ref, -1), rtol=2e-3, atol=1e-6)
+
+
+def _dense_mask_from_csr(crow, col, H, T):
+    return so.flat_csr_to_dense(crow.cpu().long(), col.cpu().long(), torch.ones(col.shape), T, H)
+
+
+@pytest.mark.parametrize('name', ['layer_causal_h4_t128', 'layer_causal_h3_t100'])
+def test_layer_forward_matches_reference_fixture_fp32(sea, name):
+    g, m, sd = golden_layer(name)
+    H, T, P, d = m['H'], m['T'], m['P'], m['d']
+    mod = _module(sea, m, sd)
+    mod.output_attentions = True
+    q, k, v = (torch.from_numpy(g[x]).to(DEV) for x in 'qkv')
+    mask = so.causal_additive_mask(T).to(DEV)
+    out = mod(q, k, v, q, k, v, q, k, mask, None, None)
+    assert out.loss == 0 and out.dense_attention_probs is None and out.state is None
+    assert tuple(out.context_layer.shape) == (1, T, H * d)
+    # estimated probabilities vs the reference's own
+    torch.testing.assert_close(out.estimated_attention_probs_m.cpu(), torch.from_numpy(g['sparse.estimated_attention_probs']),
+                               rtol=2e-3, atol=1e-6)
+    # mask agreement vs the reference's sparse (Triton) path, densified
+    pm = out.partial_attention_mask
+    assert pm.is_sparse_csr and tuple(pm.shape) == (1, T, H * T)
+    mine = _dense_mask_from_csr(pm.crow_indices(), pm.col_indices(), H, T).numpy()
+    ref = so.flat_csr_to_dense(torch.from_numpy(g['sparse.crow']), torch.from_numpy(g['sparse.col'].astype(np.int64)),
+                               torch.ones(1, g['sparse.col'].shape[-1]), T, H).numpy()
+    agreement = float((mine == ref).mean())
+    # ties inside the x4-upsampled predictor columns are implementation-defined in the reference (unstable
+    # sort); on these tiny shapes they are a visible fraction, at the benchmark shapes they are < 0.1 %.
+    assert agreement >= 0.99, agreement
+    # oracle (same tie rule as the kernels) must agree to >= 99.9 %
+    b = so.perlin_forward_causal(sd, q.cpu(), k.cpu(), v.cpu(), k_top=m['k'], P=P, sparse=True, keep_dense=True)
+    agree_oracle = float((mine == b['partial_attention_mask'].numpy()).mean())
+    assert agree_oracle >= 0.999, agree_oracle
+    rows_same = torch.from_numpy((mine == b['partial_attention_mask'].numpy()).all(axis=(0, 1, 3)))     # [T]
+    ctx = out.context_layer.cpu()
+    torch.testing.assert_close(ctx[:, rows_same], b['context_layer'][:, rows_same], rtol=1e-3, atol=2e-5)
+    assert rows_same.float().mean() > 0.95
+
+
+@pytest.mark.parametrize('N,H,d,T,P,k,nbf', [(2, 4, 64, 192, 32, 8, 8), (1, 12, 64, 256, 64, 16, 8)])
+def test_layer_forward_matches_oracle_fp32(sea, N, H, d, T, P, k, nbf):
+    mod, sd = _random_sd(sea, H, d, T, P, k, nbf, seed=1)
+    mod = mod.to(DEV)
+    mod.benchmarking = True
+    mod.output_attentions = True
+    g = torch.Generator().manual_seed(3)
+    q = torch.randn(N, H, T, d, generator=g) * d ** -0.5
+    kk = torch.randn(N, H, T, d, generator=g)
+    v = torch.randn(N, H, T, d, generator=g)
+    qd, kd, vd = q.to(DEV), kk.to(DEV), v.to(DEV)
+    out = mod(qd, kd, vd, qd, kd, vd, qd, kd, so.causal_additive_mask(T, torch.float32, N).to(DEV), None, None)
+    b = so.perlin_forward_causal(sd, q, kk, v, k_top=k, P=P, sparse=True, keep_dense=True)
+    torch.testing.assert_close(out.estimated_attention_probs.cpu(), b['estimated_attention_probs'], rtol=2e-3, atol=1e-6)
+    # bit-exact masks GIVEN IDENTICAL PROBABILITIES: feed the kernel's own probabilities to the oracle
+    kpr = torch.from_numpy(np.tile(so.per_item_top_k_causal(H, k, 1.0, P, T), N))
+    mask_m = so.topk_mask_causal_batch(out.estimated_attention_probs.cpu(), k)
+    crow_r, col_r, Z_r = so.resize_from_m_to_t_csr(mask_m, k, T, True)
+    pm = out.partial_attention_mask
+    assert torch.equal(pm.crow_indices().cpu().long(), crow_r)
+    assert torch.equal(pm.col_indices().cpu().long()[:, :Z_r], col_r)
+    # end-to-end agreement with the oracle's own pipeline
+    mine = _dense_mask_from_csr(pm.crow_indices(), pm.col_indices(), H, T).numpy()
+    assert float((mine == b['partial_attention_mask'].numpy()).mean()) >= 0.999
+    rows_same = torch.from_numpy((mine == b['partial_attention_mask'].numpy()).all(axis=(0, 1, 3)))
+    torch.testing.assert_close(out.context_layer.cpu()[:, rows_same], b['context_layer'][:, rows_same], rtol=1e-3, atol=2e-5)
+
+
+def test_layer_forward_bf16(sea):
+    N, H, d, T, P, k, nbf = 1, 12, 64, 256, 64, 16, 8
+    mod, sd = _random_sd(sea, H, d, T, P, k, nbf, seed=2)
+    mod = mod.to(DEV)
+    mod.benchmarking = True
+    mod.output_attentions = True
+    g = torch.Generator().manual_seed(4)
+    q = (torch.randn(N, H, T, d, generator=g) * d ** -0.5).bfloat16()
+    kk = torch.randn(N, H, T, d, generator=g).bfloat16()
+    v = torch.randn(N, H, T, d, generator=g).bfloat16()
+    qd, kd, vd = q.to(DEV), kk.to(DEV), v.to(DEV)
+    out = mod(qd, kd, vd, qd, kd, vd, qd, kd, so.causal_additive_mask(T, torch.bfloat16, N).to(DEV), None, None)
+    assert out.context_layer.dtype == torch.bfloat16
+    b = so.perlin_forward_causal(sd, q.float(), kk.float(), v.float(), k_top=k, P=P, sparse=True, keep_dense=True)
+    pm = out.partial_attention_mask
+    mine = _dense_mask_from_csr(pm.crow_indices(), pm.col_indices(), H, T).numpy()
+    agreement = float((mine == b['partial_attention_mask'].numpy()).mean())
+    assert agreement >= 0.98, agreement     # bf16 activations move near-ties of the top-k; reported in DESIGN.md
+    rows_same = torch.from_numpy((mine == b['partial_attention_mask'].numpy()).all(axis=(0, 1, 3)))
+    if rows_same.any():
+        torch.testing.assert_close(out.context_layer.float().cpu()[:, rows_same], b['context_layer'][:, rows_same], rtol=2e-2, atol=2e-2)
+
+
+def test_unsupported_modes_fail_loudly(sea):
+    mod, sd = _random_sd(sea, 2, 32, 16, 8, 4, 8)
+    mod = mod.to(DEV)
+    q = torch.zeros(1, 2, 16, 32, device=DEV)
+    mask = so.causal_additive_mask(16).to(DEV)
+    with pytest.raises(sea.SeaError):
+        mod(q, q, q, q, q, q, q, q, mask, torch.zeros(1, 2, 16, 16, device=DEV), None)      # teacher tensors -> training branch
+    padded = mask.clone()
+    padded[:, :, 10:, :] = so.fp_min_for(torch.float32)
+    with pytest.raises(sea.SeaError):
+        mod(q, q, q, q, q, q, q, q, padded, None, None)

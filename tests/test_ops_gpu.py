@@ -1,0 +1,209 @@
+"""GPU parity tests of the operator boundary (the 7 exports of the reference's ops/__init__.py plus the
+top-k), called through the C ABI (ops.py -> ctypes -> libsea_b200.so) and compared with the CPU oracle
+on the same seeded inputs.  Integer / index results: bit-exact.  Floating point: rtol 1e-3 (fp32)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_layer, load_golden
+from oracle import sea_oracle as so
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+def _rand_mask(N, H, T, P, k, seed, ties=False):
+    g = torch.Generator().manual_seed(seed)
+    probs = torch.softmax(torch.randn(N, H, T, P, generator=g), -1)
+    if ties:
+        probs = probs[..., : max(P // 4, 1)].repeat_interleave(4, dim=-1)[..., :P].contiguous()
+    return probs, so.topk_mask_causal_batch(probs, k)
+
+
+@pytest.mark.parametrize('N,H,T,P,k,ties', [
+    (2, 3, 50, 16, 4, False), (1, 4, 128, 32, 8, True), (1, 12, 64, 256, 64, True), (1, 32, 96, 256, 64, True),
+    (1, 1, 64, 8, 16, True), (2, 5, 33, 24, 3, False), (1, 64, 8, 256, 64, True),
+])
+def test_topk_bit_exact(sea, N, H, T, P, k, ties):
+    probs, ref = _rand_mask(N, H, T, P, k, seed=N * 1000 + H * 10 + T, ties=ties)
+    kpr = torch.from_numpy(np.tile(so.per_item_top_k_causal(H, k, 1.0, P, T), N))
+    bits = sea.ops.topk_mask_bits(probs.to(DEV), kpr.to(DEV), 'causal_batch')
+    got = sea.ops.bits_to_mask(bits, H, P).cpu()
+    assert torch.equal(got, ref)
+    # round trip float mask -> bits -> float mask
+    assert torch.equal(sea.ops.bits_to_mask(sea.ops.mask_to_bits(ref.to(DEV)), H, P).cpu(), ref)
+
+
+def test_topk_edge_cases(sea):
+    N, H, T, P = 1, 2, 4, 32
+    probs = torch.zeros(N, H, T, P)          # all keys equal (+0 and -0 mixed): lowest indices win
+    probs[0, 1, 1, :] = -0.0
+    for kval in (1.0, 5.0, 64.0, 1000.0):
+        kpr = torch.full((N * T,), kval)
+        got = sea.ops.bits_to_mask(sea.ops.topk_mask_bits(probs.to(DEV), kpr.to(DEV)), H, P).cpu()
+        alive = so.topk_alive_rows(probs.transpose(1, 2).reshape(N * T, H * P).numpy() + 0.0, kpr.numpy())
+        ref = torch.from_numpy(alive.reshape(N, T, H, P)).permute(0, 2, 1, 3).float()
+        assert torch.equal(got, ref), kval
+    # padded query rows are dead (attention.py:928-931)
+    rv = torch.tensor([[1, 0, 1, 0]], dtype=torch.uint8)
+    got = sea.ops.bits_to_mask(sea.ops.topk_mask_bits(probs.to(DEV), torch.full((4,), 3.0).to(DEV), row_valid=rv.to(DEV)), H, P).cpu()
+    assert got[0, :, 1].sum() == 0 and got[0, :, 3].sum() == 0 and got[0, :, 0].sum() == 3
+
+
+def test_topk_query_mode(sea):
+    N, H, T, P = 2, 3, 17, 24
+    g = torch.Generator().manual_seed(5)
+    probs = torch.softmax(torch.randn(N, H, T, P, generator=g), -1)
+    kq = torch.tensor([5.0, 9.0])
+    got = sea.ops.bits_to_mask(sea.ops.topk_mask_bits(probs.to(DEV), kq.to(DEV), 'query'), H, P).cpu()
+    alive = so.topk_alive_rows(probs.reshape(N * H * T, P).numpy(), kq.view(N, 1).expand(N, H * T).reshape(-1).numpy())
+    assert torch.equal(got, torch.from_numpy(alive.reshape(N, H, T, P)).float())
+
+
+CSR_CASES = [
+    # N, H, T_DST, T_SRC, P, k, causal
+    (1, 1, 64, 64, 8, 16, True), (2, 3, 100, 100, 16, 8, True), (1, 4, 257, 257, 32, 16, True),
+    (1, 2, 1024, 1024, 8, 16, True),      # T/P > k: clamp + sub-sampling branch
+    (1, 3, 100, 100, 16, 6, True),        # clamp active on late rows only
+    (1, 4, 40, 128, 32, 8, True),         # T_DST < T_SRC (last rows of a longer context)
+    (2, 4, 64, 64, 32, 8, False),         # non causal
+    (1, 12, 96, 96, 24, 5, True),         # P not a power of two
+]
+
+
+@pytest.mark.parametrize('N,H,T_DST,T_SRC,P,k,causal', CSR_CASES)
+@pytest.mark.parametrize('idx_dtype', [torch.int64, torch.int32])
+def test_csr_interpolation_bit_exact(sea, N, H, T_DST, T_SRC, P, k, causal, idx_dtype):
+    g = torch.Generator().manual_seed(T_DST + P)
+    mask = (torch.rand(N, H, T_DST, P, generator=g) < min(1.0, 1.5 * k / P)).float()
+    mask[0, :, 0, :] = 0           # an empty row
+    crow_r, col_r, Z_r = so.resize_from_m_to_t_csr(mask, k, T_SRC, causal)
+    bits = sea.ops.mask_to_bits(mask.to(DEV))
+    crow, col, Z = sea.ops.csr_from_bits(bits, H, P, k, T_SRC, is_causal=causal, index_dtype=idx_dtype)
+    assert Z == Z_r
+    assert torch.equal(crow.cpu().long(), crow_r)
+    assert torch.equal(col.cpu().long(), col_r)
+    # over-allocated (sync-free) variant: same prefix, zero tail
+    crow2, col2, Z2 = sea.ops.csr_from_bits(bits, H, P, k, T_SRC, is_causal=causal, index_dtype=idx_dtype, z_alloc=Z_r + 77)
+    assert torch.equal(col2.cpu().long()[:, :Z_r], col_r) and int(col2[:, Z_r:].abs().sum()) == 0
+
+
+def test_resize_csr_op_matches_reference_fixture(sea):
+    """resize_from_m_to_t_csr (the op, torch CSR in/out) against the reference's own (Triton-interpreted) output."""
+    g = load_golden('kat_causal_resize')
+    N, H, T, P, K = g['meta'].tolist()
+    csr = sea.resize_from_m_to_t_csr(torch.from_numpy(g['compressed_mask']).to(DEV), 0, K, target_width=T)
+    assert csr.is_sparse_csr and tuple(csr.shape) == (N, T, H * T)
+    assert np.array_equal(csr.crow_indices().cpu().numpy(), g['crow'])
+    assert np.array_equal(csr.col_indices().cpu().numpy(), g['col'])
+    assert np.diff(csr.crow_indices().cpu().numpy()[0]).tolist() == g['nnz_per_row_notebook'].tolist()
+    dense = sea.flat_csr_to_dense(csr, T, H)
+    assert np.array_equal(dense.cpu().numpy().astype(np.uint8), g['dense'])
+    for name in ('layer_causal_h4_t128', 'layer_causal_h3_t100'):
+        g, m, _ = golden_layer(name)
+        H, T, P = m['H'], m['T'], m['P']
+        mm = np.unpackbits(g['sparse.mask_before_interp'])[:H * T * P].reshape(1, H, T, P).astype(np.float32)
+        csr = sea.resize_from_m_to_t_csr(torch.from_numpy(mm).to(DEV), 0, m['k'], target_width=T)
+        assert np.array_equal(csr.crow_indices().cpu().numpy(), g['sparse.crow'])
+        assert np.array_equal(csr.col_indices().cpu().numpy(), g['sparse.col'].astype(np.int64))
+
+
+def _csr_case(N, H, T, P, k, d, seed, dtype=torch.float32):
+    g = torch.Generator().manual_seed(seed)
+    probs, mask = _rand_mask(N, H, T, P, k, seed)
+    crow, col, Z = so.resize_from_m_to_t_csr(mask, k, T, True)
+    q = (torch.randn(N, H, T, d, generator=g) * d ** -0.5).to(dtype)
+    kk = torch.randn(N, H, T, d, generator=g).to(dtype)
+    v = torch.randn(N, H, T, d, generator=g).to(dtype)
+    return crow, col, Z, q, kk, v
+
+
+def _mk_csr(crow, col, vals, shape):
+    return torch.sparse_csr_tensor(crow.to(DEV), col.to(DEV), vals.to(DEV), size=shape)
+
+
+@pytest.mark.parametrize('N,H,T,P,k,d', [(2, 3, 100, 16, 8, 32), (1, 4, 128, 32, 8, 64), (1, 2, 96, 32, 8, 80), (1, 2, 64, 16, 8, 128)])
+def test_flat_csr_ops_match_oracle(sea, N, H, T, P, k, d):
+    crow, col, Z, q, kk, v = _csr_case(N, H, T, P, k, d, seed=d + T)
+    shape = (N, T, H * T)
+    mask = _mk_csr(crow, col, torch.ones(N, Z), shape)
+    # a9
+    s = sea.flat_csr_masked_bmm(q.to(DEV), kk.to(DEV), mask)
+    s_ref = so.flat_csr_masked_bmm(q, kk, crow, col)
+    torch.testing.assert_close(s.values().cpu(), s_ref, rtol=1e-3, atol=1e-5)
+    # a10
+    p = sea.flat_csr_softmax(s, H, T)
+    p_ref = so.flat_csr_softmax(s_ref, crow, col, H, T)
+    torch.testing.assert_close(p.values().cpu(), p_ref, rtol=1e-3, atol=1e-6)
+    # a11 with the stride-0 row scaler of attention.py:1170
+    rs = torch.sigmoid(torch.randn(N, H, T, generator=torch.Generator().manual_seed(3)))
+    p2 = sea.flat_csr_elmul(p, rs.to(DEV).view(N, H, T, 1).expand(N, H, T, T))
+    p2_ref = so.flat_csr_elmul_rowscale(p_ref, crow, col, rs, T)
+    torch.testing.assert_close(p2.values().cpu(), p2_ref, rtol=1e-3, atol=1e-6)
+    # a12
+    o = sea.flat_csr_sdbmm(p2, v.to(DEV), P)
+    o_ref = so.flat_csr_sdbmm(p2_ref, crow, col, v, H)
+    assert o.dtype == torch.float32 and tuple(o.shape) == (N, H, T, d)
+    torch.testing.assert_close(o.cpu(), o_ref, rtol=1e-3, atol=1e-5)
+    # to_dense
+    dn = sea.flat_csr_to_dense(p2, T, H)
+    torch.testing.assert_close(dn.cpu(), so.flat_csr_to_dense(crow, col, p2.values().cpu(), T, H), rtol=0, atol=0)
+
+
+def test_flat_csr_ops_empty_and_ragged(sea):
+    """Empty rows, an empty batch item next to a full one, rows whose heads are absent."""
+    N, H, T, d = 2, 3, 8, 32
+    crow = torch.zeros(N, T + 1, dtype=torch.int64)
+    cols0 = []
+    for t in range(T):
+        if t % 3 == 0:
+            continue                      # empty row
+        cols0 += [0 * T + j for j in range(t + 1)] + [2 * T + t]      # head 1 absent everywhere
+        crow[0, t + 1:] = len(cols0)
+    Z = len(cols0)
+    col = torch.zeros(N, Z, dtype=torch.int64)
+    col[0] = torch.tensor(cols0)
+    g = torch.Generator().manual_seed(0)
+    q, kk, v = (torch.randn(N, H, T, d, generator=g) for _ in range(3))
+    mask = _mk_csr(crow, col, torch.ones(N, Z), (N, T, H * T))
+    s = sea.flat_csr_masked_bmm(q.to(DEV), kk.to(DEV), mask)
+    p = sea.flat_csr_softmax(s, H, T)
+    o = sea.flat_csr_sdbmm(p, v.to(DEV), 4)
+    s_ref = so.flat_csr_masked_bmm(q, kk, crow, col)
+    p_ref = so.flat_csr_softmax(s_ref, crow, col, H, T)
+    torch.testing.assert_close(p.values().cpu()[0], p_ref[0], rtol=1e-3, atol=1e-6)
+    torch.testing.assert_close(o.cpu(), so.flat_csr_sdbmm(p_ref, crow, col, v, H), rtol=1e-3, atol=1e-5)
+    assert float(o[1].abs().sum()) == 0.0 and float(o[0, 1].abs().sum()) == 0.0
+
+
+@pytest.mark.parametrize('causal', [True, False])
+def test_dense_resize_matches_oracle(sea, causal):
+    N, H, T, P, k = 2, 3, 70, 16, 8
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(N, H, T, P, generator=g)
+    if causal:
+        am = so.causal_additive_mask(T, torch.float32, N)
+    else:
+        am = torch.zeros(N, 1, 1, T)
+        am[1, 0, 0, 50:] = so.fp_min_for(torch.float32)         # padded tail on item 1
+    ref = so.resize_from_m_to_t_dense(x, -7.0, am, T, causal, k, None)
+    got = sea.resize_from_m_to_t(x.to(DEV), -7.0, am.to(DEV), target_width=T, is_causal=causal, k=k)
+    assert torch.equal(got.cpu(), ref)
+
+
+def test_fused_sparse_attention_matches_unfused_ops(sea):
+    N, H, T, P, k, d = 1, 4, 128, 32, 8, 64
+    crow, col, Z, q, kk, v = _csr_case(N, H, T, P, k, d, seed=77)
+    g = torch.Generator().manual_seed(9)
+    scales = torch.randn(N, H, T, 2, generator=g)
+    avg = v.cumsum(-2) / torch.arange(1, T + 1).view(1, 1, T, 1)
+    s_ref = so.flat_csr_masked_bmm(q, kk, crow, col)
+    p_ref = so.flat_csr_elmul_rowscale(so.flat_csr_softmax(s_ref, crow, col, H, T), crow, col, torch.sigmoid(scales[..., 0]), T)
+    ctx = so.flat_csr_sdbmm(p_ref, crow, col, v, H)
+    a = torch.sigmoid(scales[..., 1:2])
+    ref = (ctx * a + (1 - a) * avg).permute(0, 2, 1, 3).reshape(N, T, H * d)
+    for idt in (torch.int64, torch.int32):
+        out, pv = sea.ops.sparse_attention(crow.to(DEV).to(idt), col.to(DEV).to(idt), q.to(DEV), kk.to(DEV), v.to(DEV),
+                                           scales.to(DEV), avg.to(DEV), use_scaler=True, want_probs=True)
+        torch.testing.assert_close(out.cpu(), ref, rtol=1e-3, atol=2e-5)
+        torch.testing.assert_close(pv.cpu(), p_ref, rtol=1e-3, atol=1e-6)
