@@ -159,6 +159,18 @@ SEA_API int sea_predictor_mlp_fwd(const void* ctx, const void* v, int64_t v_sn, 
                           void* cnn_in, float* scales, void* t_pred,
                           int N, int H, int T, int D, int S, int W, void* stream);
 
+/* a4 on the tensor cores (bf16 only; csrc/umma_mlp.cu): same computation as sea_predictor_mlp_fwd with both Linear
+ * layers as chained tcgen05 GEMMs per 128-token tile (intermediates stay in TMEM / shared memory).  Shapes: D = 64,
+ * S = 2, H | 128, W in {16,32,64}; ctx contiguous [N,H,T,2D] bf16; cnn_in bf16 [N,T,W,2H]; no t_pred output.
+ * workspace: >= sea_predictor_mlp_umma_workspace_bytes() bytes, 128-byte aligned. */
+SEA_API int sea_predictor_mlp_umma_supported(int dtype, int H, int D, int S, int W);
+SEA_API int64_t sea_predictor_mlp_umma_workspace_bytes(void);
+SEA_API int sea_predictor_mlp_umma_fwd(const void* ctx, const void* v, int64_t v_sn, int64_t v_sh, int64_t v_st,
+                                       const float* enc_w, const float* enc_b, const float* enc_ln_w, const float* enc_ln_b,
+                                       const float* dec_w, const float* dec_b, const float* cnn_ln_w, const float* cnn_ln_b,
+                                       const float* scl_w, const float* scl_b, void* cnn_in, float* scales, void* workspace,
+                                       int N, int H, int T, int D, int S, int W, void* stream);
+
 /* a5  one CausalConv2d(C,C,3,padding=2,dilation=2,causal) + ReLU (modules.py:96-192;
  *     attention.py:271-274) on channels-last activations [N,T,W,C]:
  *   y[t,w,o] = relu(b[o] + sum_{i,j<3} sum_c Wt[o,c,i,j] x[t-4+2i, w-2+2j, c])   (zero outside)
@@ -166,12 +178,31 @@ SEA_API int sea_predictor_mlp_fwd(const void* ctx, const void* v, int64_t v_sn, 
 SEA_API int sea_causal_conv3x3_dil2_relu(const void* x, const float* weight, const float* bias, void* y, int dtype,
                                  int N, int T, int W, int C, int O, void* stream);
 
+/* a5 on the tensor cores (bf16 only): the same CausalConv2d + ReLU as an implicit GEMM with tcgen05.mma / TMEM /
+ * TMA (csrc/umma_conv.cu).  Shapes: C = O = 64, W a divisor of 128; sea_conv_umma_supported() tells.
+ * workspace: >= sea_conv_umma_workspace_bytes(C, O) bytes, 128-byte aligned (bf16 re-packed weights).
+ * sea_conv1x1_umma: the 1x1 CausalConv2d(C=64 -> O=32) of attention.py:276 evaluated BEFORE the nearest x4
+ * upsample (they commute): y [N,T,W,O] fp32 = x . Wt^T + b. */
+SEA_API int sea_conv_umma_supported(int dtype, int W, int C, int O);
+SEA_API int64_t sea_conv_umma_workspace_bytes(int C, int O);
+SEA_API int sea_causal_conv3x3_dil2_relu_umma(const void* x, const float* weight, const float* bias, void* y, void* workspace,
+                                              int N, int T, int W, int C, int O, void* stream);
+SEA_API int sea_conv1x1_umma(const void* x, const float* weight, const float* bias, float* y, void* workspace,
+                             int N, int T, int W, int C, int O, void* stream);
+
 /* a5 tail + a6  (attention.py:275-280, 670-673): nearest x4 along W, CausalConv2d(C,H,1,padding=1)
  * (width P+2, the two pad columns equal the bias), area-resize to P, LayerNorm(P), softmax(P).
  * x channels-last [N,T,W,C]; weight fp32 [H, C]; probs out fp32 [N,H,T,P]; scores out nullable. */
 SEA_API int sea_predictor_tail_fwd(const void* x, int dtype, const float* weight, const float* bias,
                            const float* ln_w, const float* ln_b, float* probs, float* scores,
                            int N, int H, int T, int W, int C, int P, void* stream);
+
+/* a5 tail + a6 + a7 fused (bf16 path): y3 fp32 [N,T,W,H] = output of sea_conv1x1_umma -> upsample, pad, area resize,
+ * LayerNorm(P), softmax(P) (attention.py:275-280, 670-673) -> probs fp32 [N,H,T,P] (nullable) and the 'causal_batch'
+ * top-k bit mask [N,T,H*P/32] (nullable; k_per_row [N*T] as in sea_topk_mask_bits).  P in {32,...,1024}, W | P. */
+SEA_API int sea_predictor_tail_topk_fwd(const float* y3, const float* bias, const float* ln_w, const float* ln_b,
+                                        const float* k_per_row, float* probs, uint32_t* mask_bits,
+                                        int N, int H, int T, int W, int P, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * a9-a14 fused sparse attention of the benchmarking branch (attention.py:1151-1173, 1237-1244,

@@ -279,13 +279,17 @@ class PerlinAttention(nn.Module):
         ctx, cumavg = ops.performer_causal(q_for_atten, k_for_atten, v, w['pos'], w['proj'])
         # a4
         cnn_in, scales, _ = ops.predictor_mlp(ctx, v, w, S, W)
-        # a5
+        # a5 .. a7
+        kpr = k_per_row.repeat(N) if N > 1 else k_per_row
         y = ops.causal_conv3x3_dil2_relu(cnn_in, w['conv1_w'], w['conv1_b'])
         y = ops.causal_conv3x3_dil2_relu(y, w['conv2_w'], w['conv2_b'])
-        # a5 tail + a6
-        probs, _ = ops.predictor_tail(y, w['conv3_w'], w['conv3_b'], w['out_ln_w'], w['out_ln_b'], P)
-        # a7
-        bits = ops.topk_mask_bits(probs, k_per_row.repeat(N) if N > 1 else k_per_row, 'causal_batch')
+        if q.dtype == torch.bfloat16 and ops.conv_umma_supported(q.dtype, W, S * H, H) and P % 32 == 0:
+            # tensor-core path: 1x1 conv before the upsample (tcgen05), then tail + softmax + top-k in one kernel
+            y3 = ops.conv1x1_umma(y, w['conv3_w'], w['conv3_b'])
+            probs, bits = ops.predictor_tail_topk(y3, w['conv3_b'], w['out_ln_w'], w['out_ln_b'], kpr, P)
+        else:
+            probs, _ = ops.predictor_tail(y, w['conv3_w'], w['conv3_b'], w['out_ln_w'], w['out_ln_b'], P)
+            bits = ops.topk_mask_bits(probs, kpr, 'causal_batch')
         # a8 (int32 indices internally; no host sync: col is allocated at a shape-derived upper bound)
         crow, col, Z = ops.csr_from_bits(bits, H, P, pc.k, T, is_causal=True, index_dtype=torch.int32, z_alloc=z_alloc)
         # a9-a14

@@ -5,6 +5,7 @@
 // All of these are HBM/L2-bound gather or bit work: warp-per-row kernels, shuffle scans, 128-bit loads
 // where rows are contiguous.  No tensor cores on purpose.
 #include "common.cuh"
+#include "topk.cuh"
 
 #include <stdarg.h>
 
@@ -16,118 +17,6 @@ void set_error(const char* fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
-}
-
-// ------------------------------------------------------------------------------------------------
-// a7 top-k: one CTA per group; keys staged once in shared memory as order-preserving u32; 4-pass
-// 8-bit radix select finds the K-th largest key; ties at the threshold are resolved in index order
-// with a block scan so that the LOWER flat index wins.
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t orderable(float f) {
-    uint32_t u = __float_as_uint(f);
-    if ((u << 1) == 0) return 0x80000000u;  // +-0 compare equal
-    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-}
-
-constexpr int kTopkThreads = 256;
-
-__device__ __forceinline__ int block_excl_scan(int v, int* warp_sums, int& total) {
-    // exclusive scan of one int per thread over a 256-thread CTA; `total` = sum over the CTA
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    int incl = warp_scan_incl_i(v, lane);
-    if (lane == 31) warp_sums[wid] = incl;
-    __syncthreads();
-    int wprefix = 0, tot = 0;
-#pragma unroll
-    for (int w = 0; w < kTopkThreads / 32; ++w) {
-        int s = warp_sums[w];
-        if (w < wid) wprefix += s;
-        tot += s;
-    }
-    __syncthreads();
-    total = tot;
-    return wprefix + incl - v;
-}
-
-// Select over `G` orderable keys resident in shared memory; writes ceil(G/32) words of alive bits.
-__device__ void topk_select_to_bits(const uint32_t* skeys, int G, int K, uint32_t* out_bits,
-                                    int* hist /*256*/, int* scratch /*16*/) {
-    const int tid = threadIdx.x;
-    const int nwords = (G + 31) >> 5;
-    if (K >= G) {
-        for (int w = tid; w < nwords; w += kTopkThreads) {
-            int rem = G - (w << 5);
-            out_bits[w] = rem >= 32 ? 0xffffffffu : ((1u << rem) - 1u);
-        }
-        return;
-    }
-    if (K <= 0) {
-        for (int w = tid; w < nwords; w += kTopkThreads) out_bits[w] = 0u;
-        return;
-    }
-    uint32_t prefix = 0, mask = 0;
-    int remaining = K;
-    for (int pass = 0; pass < 4; ++pass) {
-        const int shift = 24 - 8 * pass;
-        hist[tid] = 0;
-        __syncthreads();
-        for (int i = tid; i < G; i += kTopkThreads) {
-            uint32_t u = skeys[i];
-            if ((u & mask) == prefix) atomicAdd(&hist[(u >> shift) & 255], 1);
-        }
-        __syncthreads();
-        // suffix sums over digits: thread d gets count of keys with digit > d (within the prefix class)
-        int mine = hist[255 - tid];  // reversed so that an exclusive scan gives "strictly greater"
-        int tot;
-        int above = block_excl_scan(mine, scratch, tot);
-        // digit d = 255 - tid is the pivot digit iff above < remaining <= above + mine
-        if (above < remaining && remaining <= above + mine) {
-            scratch[8] = 255 - tid;
-            scratch[9] = remaining - above;
-        }
-        __syncthreads();
-        prefix |= (uint32_t) scratch[8] << shift;
-        mask |= 0xffu << shift;
-        remaining = scratch[9];
-        __syncthreads();
-    }
-    const uint32_t thr = prefix;  // K-th largest key; `remaining` of the keys equal to thr are alive
-    int carry = 0;
-    for (int w0 = 0; w0 < nwords; w0 += kTopkThreads) {
-        const int w = w0 + tid;
-        uint32_t gt = 0, eq = 0;
-        if (w < nwords) {
-            const int base = w << 5;
-            const int lim = min(32, G - base);
-            // thread = word, so a plain b-loop would be a 32-way bank conflict: rotate by tid
-            for (int r = 0; r < 32; ++r) {
-                const int b = (r + tid) & 31;
-                if (b < lim) {
-                    uint32_t u = skeys[base + b];
-                    gt |= (u > thr ? 1u : 0u) << b;
-                    eq |= (u == thr ? 1u : 0u) << b;
-                }
-            }
-        }
-        int neq = __popc(eq);
-        int tot;
-        int before = carry + block_excl_scan(neq, scratch, tot);
-        carry += tot;
-        if (w < nwords) {
-            int take = remaining - before;  // how many of my equal keys (in index order) are alive
-            uint32_t sel = 0;
-            if (take >= neq) sel = eq;
-            else if (take > 0) {
-                uint32_t e = eq;
-                for (int c = 0; c < take; ++c) {
-                    uint32_t low = e & (~e + 1u);
-                    sel |= low;
-                    e ^= low;
-                }
-            }
-            out_bits[w] = gt | sel;
-        }
-    }
 }
 
 __global__ void __launch_bounds__(kTopkThreads)
@@ -332,10 +221,10 @@ csr_fill_kernel(const uint32_t* __restrict__ bits, const IdxT* __restrict__ crow
             p += wd;
         }
     }
-    // zero the tail of the last row's batch item (reference allocates col with torch.zeros, :669)
-    if (t == T_DST - 1) {
-        for (int64_t z = pos + lane; z < Z; z += 32) out[z] = 0;
-    }
+    // zero the tail [crow[n, T_DST], Z) (the reference allocates col with torch.zeros, :669); every warp of the batch
+    // item takes a strided slice so that an over-allocated col costs one coalesced pass, not one warp's serial loop
+    const int64_t tail_begin = (int64_t) crow[(int64_t) n * (T_DST + 1) + T_DST];
+    for (int64_t z = tail_begin + (int64_t) t * 32 + lane; z < Z; z += (int64_t) T_DST * 32) out[z] = 0;
 }
 
 template <typename IdxT>

@@ -1,0 +1,299 @@
+// a5 on the 5th-generation tensor cores: the predictor's CausalConv2d(3x3, dilation 2) + ReLU and its 1x1
+// output conv as IMPLICIT GEMM with tcgen05.mma (bf16 in, fp32 accumulate in TMEM), operands staged by TMA.
+//
+//   activations channels-last [N, T, W, C=64] bf16  ->  one pixel = one 128-byte row = one SWIZZLE_128B K-atom
+//   output tile  = 128 pixels (TR = 128/W rows of t) x kNOut channels, accumulator [128 lanes x kNOut cols] in TMEM
+//   K loop       = 9 taps x 64 channels: tap (i, j) is the SAME 4-D TMA box shifted by (dt, dw) = (2i-4, 2j-2);
+//                  out-of-range rows/columns (the conv's zero padding, incl. the causal top padding) are zero-filled
+//                  by TMA, so no im2col buffer and no boundary code exists anywhere.
+//   weights      = 9 x [kNOut x 64] bf16 K-major tiles, resident in shared memory for the whole persistent CTA
+//   warp roles   = warp 0: TMA producer, warp 1: MMA issuer (one elected lane) + TMEM allocator,
+//                  warps 2-5: epilogue (tcgen05.ld -> +bias, ReLU -> bf16 -> swizzled smem -> coalesced 16B stores)
+//   pipelines    = kStages-deep smem ring (full/empty mbarriers), 2 TMEM accumulators (tmem_full/empty mbarriers)
+// Reference: modules.py:96-192 (CausalConv2d), attention.py:271-276.
+#include "common.cuh"
+#include "umma.cuh"
+
+#include <mutex>
+
+namespace sea {
+
+PFN_encodeTiled get_encode_tiled() {
+    static PFN_encodeTiled fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(p);
+    });
+    return fn;
+}
+
+int make_tmap_bf16_sw128(CUtensorMap* out, void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box) {
+    PFN_encodeTiled enc = get_encode_tiled();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled is not available (driver entry point lookup failed)");
+        return SEA_ERR_CUDA;
+    }
+    cuuint64_t d[5], s[4];
+    cuuint32_t b[5], e[5];
+    for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; e[i] = 1; }
+    for (int i = 0; i + 1 < rank; ++i) s[i] = strides_bytes[i];
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t) rank, base, d, s, b, e, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int) r);
+        return SEA_ERR_CUDA;
+    }
+    return SEA_OK;
+}
+
+namespace {
+
+constexpr int kStages = 6;
+constexpr int kATileBytes = 128 * 128;     // 128 pixels x 64 bf16
+constexpr int kConvThreads = 192;
+
+template <int kTaps, int kNOut>
+struct ConvSmem {
+    static constexpr int kWBytes = kTaps * kNOut * 128;
+    static constexpr int kStageOff = kWBytes;
+    static constexpr int kOutOff = kStageOff + kStages * kATileBytes;
+    static constexpr int kOutBytes = 128 * 128;                      // 128 rows x 128 B (64 bf16 or 32 fp32)
+    static constexpr int kBarOff = kOutOff + kOutBytes;
+    static constexpr int kTotal = kBarOff + 256 + 1024;              // + barriers + alignment slack
+};
+
+__global__ void pack_conv_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int O, int C, int taps) {
+    // reference layout [O][C][2k-1][k] (k = 3 -> 5x3, k = 1 -> 1x1)  ->  [tap][o][c] bf16
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= taps * O * C) return;
+    const int c = idx % C, o = (idx / C) % O, tap = idx / (C * O);
+    float val;
+    if (taps == 9) val = w[(((int64_t) o * C + c) * 5 + tap / 3) * 3 + tap % 3];
+    else val = w[(int64_t) o * C + c];
+    out[idx] = __float2bfloat16_rn(val);
+}
+
+template <int kTaps, int kNOut, bool kRelu, typename OutT>
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+                 const float* __restrict__ bias, OutT* __restrict__ y, int N, int T, int W, int TR, int tblocks, int num_tiles) {
+    using SM = ConvSmem<kTaps, kNOut>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* wsm = smem;
+    uint8_t* asm_ = smem + SM::kStageOff;
+    uint8_t* osm = smem + SM::kOutOff;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + SM::kBarOff);
+    uint64_t* empty = full + kStages;
+    uint64_t* tmem_full = empty + kStages;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint64_t* wbar = tmem_empty + 2;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(wbar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        umma::prefetch_tensormap(&tmap_x);
+        umma::prefetch_tensormap(&tmap_w);
+        for (int s = 0; s < kStages; ++s) { umma::mbar_init(&full[s], 1); umma::mbar_init(&empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { umma::mbar_init(&tmem_full[a], 1); umma::mbar_init(&tmem_empty[a], 128); }
+        umma::mbar_init(wbar, 1);
+        umma::fence_barrier_init();
+    }
+    if (warp == 1) umma::tmem_alloc(tmem_ptr, 2 * kNOut);
+    umma::tc_fence_before();
+    __syncthreads();
+    umma::tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            umma::mbar_arrive_expect_tx(wbar, SM::kWBytes);
+            for (int tap = 0; tap < kTaps; ++tap) umma::tma_load_2d(wsm + tap * kNOut * 128, &tmap_w, wbar, 0, tap * kNOut);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int n = tile / tblocks, t0 = (tile % tblocks) * TR;
+                for (int tap = 0; tap < kTaps; ++tap) {
+                    umma::mbar_wait(&empty[stage], phase ^ 1);
+                    umma::mbar_arrive_expect_tx(&full[stage], kATileBytes);
+                    const int dt = kTaps == 9 ? (tap / 3) * 2 - 4 : 0;
+                    const int dw = kTaps == 9 ? (tap % 3) * 2 - 2 : 0;
+                    umma::tma_load_4d(asm_ + stage * kATileBytes, &tmap_x, &full[stage], 0, dw, t0 + dt, n);
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma::make_idesc_bf16(128, kNOut);
+            umma::mbar_wait(wbar, 0);
+            int stage = 0, acc = 0;
+            uint32_t phase = 0, acc_phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                umma::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                umma::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t) (acc * kNOut);
+                for (int tap = 0; tap < kTaps; ++tap) {
+                    umma::mbar_wait(&full[stage], phase);
+                    umma::tc_fence_after();
+                    const uint32_t a_addr = umma::smem_u32(asm_ + stage * kATileBytes);
+                    const uint32_t b_addr = umma::smem_u32(wsm + tap * kNOut * 128);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma::mma_bf16_ss(d_tmem, umma::make_desc_k_sw128(a_addr + k * 32), umma::make_desc_k_sw128(b_addr + k * 32),
+                                          idesc, (uint32_t) ((tap | k) != 0));
+                    umma::mma_commit(&empty[stage]);
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+                umma::mma_commit(&tmem_full[acc]);
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1;
+            }
+        }
+    } else {
+        const int q = warp & 3;                       // TMEM lane quarter this warp may read
+        const int row = q * 32 + lane;                // pixel row inside the tile
+        const int et = threadIdx.x - 64;              // 0..127 among the epilogue threads
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int n = tile / tblocks, t0 = (tile % tblocks) * TR;
+            umma::mbar_wait(&tmem_full[acc], acc_phase);
+            umma::tc_fence_after();
+#pragma unroll
+            for (int c0 = 0; c0 < kNOut; c0 += 32) {
+                uint32_t r[32];
+                umma::tmem_ld_32x32(tmem_base + ((uint32_t) (q * 32) << 16) + (uint32_t) (acc * kNOut + c0), r);
+                umma::tmem_ld_wait();
+                float f[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    float val = __uint_as_float(r[i]) + __ldg(bias + c0 + i);
+                    f[i] = kRelu ? fmaxf(val, 0.f) : val;
+                }
+                if (sizeof(OutT) == 2) {
+                    // 32 channels -> 64 bytes = chunks (c0/8) .. (c0/8 + 3) of the 128-byte row
+#pragma unroll
+                    for (int ch = 0; ch < 4; ++ch) {
+                        uint4 pk;
+                        __nv_bfloat162 p0 = __floats2bfloat162_rn(f[ch * 8 + 0], f[ch * 8 + 1]);
+                        __nv_bfloat162 p1 = __floats2bfloat162_rn(f[ch * 8 + 2], f[ch * 8 + 3]);
+                        __nv_bfloat162 p2 = __floats2bfloat162_rn(f[ch * 8 + 4], f[ch * 8 + 5]);
+                        __nv_bfloat162 p3 = __floats2bfloat162_rn(f[ch * 8 + 6], f[ch * 8 + 7]);
+                        pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
+                        pk.z = *reinterpret_cast<uint32_t*>(&p2); pk.w = *reinterpret_cast<uint32_t*>(&p3);
+                        const int chunk = (c0 >> 3) + ch;
+                        *reinterpret_cast<uint4*>(osm + row * 128 + ((chunk ^ (row & 7)) << 4)) = pk;
+                    }
+                } else {
+                    // fp32 out: 32 channels = the whole 128-byte row (kNOut == 32)
+#pragma unroll
+                    for (int ch = 0; ch < 8; ++ch) {
+                        const float4 pk = make_float4(f[ch * 4 + 0], f[ch * 4 + 1], f[ch * 4 + 2], f[ch * 4 + 3]);
+                        *reinterpret_cast<float4*>(osm + row * 128 + ((ch ^ (row & 7)) << 4)) = pk;
+                    }
+                }
+            }
+            umma::tc_fence_before();
+            umma::mbar_arrive(&tmem_empty[acc]);
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            // 128 rows x 128 B are contiguous in global memory: pixel (t0 + r / W, r % W)
+            const int valid_rows = min(TR, T - t0) * W;
+            uint8_t* gout = reinterpret_cast<uint8_t*>(y) + (((int64_t) n * T + t0) * W) * (int64_t) (kNOut * sizeof(OutT));
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int g = i * 128 + et;
+                const int rr = g >> 3, ch = g & 7;
+                if (rr < valid_rows)
+                    *reinterpret_cast<uint4*>(gout + (int64_t) g * 16) = *reinterpret_cast<const uint4*>(osm + rr * 128 + ((ch ^ (rr & 7)) << 4));
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
+        }
+    }
+    umma::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        umma::tc_fence_after();
+        umma::tmem_dealloc(tmem_base, 2 * kNOut);
+    }
+}
+
+template <int kTaps, int kNOut, bool kRelu, typename OutT>
+int launch_conv_umma(const void* x, const float* weight, const float* bias, void* y, void* ws, int N, int T, int W, int C, cudaStream_t s) {
+    using SM = ConvSmem<kTaps, kNOut>;
+    __nv_bfloat16* wpack = reinterpret_cast<__nv_bfloat16*>(ws);
+    const int nel = kTaps * kNOut * C;
+    pack_conv_weights_kernel<<<(nel + 255) / 256, 256, 0, s>>>(weight, wpack, kNOut, C, kTaps);
+    SEA_CHECK_LAUNCH("pack_conv_weights_kernel");
+    const int TR = 128 / W;
+    CUtensorMap tx, tw;
+    {
+        const uint64_t dims[4] = {(uint64_t) C, (uint64_t) W, (uint64_t) T, (uint64_t) N};
+        const uint64_t strides[3] = {(uint64_t) C * 2, (uint64_t) W * C * 2, (uint64_t) T * W * C * 2};
+        const uint32_t box[4] = {64, (uint32_t) W, (uint32_t) TR, 1};
+        int rc = make_tmap_bf16_sw128(&tx, const_cast<void*>(x), 4, dims, strides, box);
+        if (rc) return rc;
+    }
+    {
+        const uint64_t dims[2] = {(uint64_t) C, (uint64_t) kTaps * kNOut};
+        const uint64_t strides[1] = {(uint64_t) C * 2};
+        const uint32_t box[2] = {64, (uint32_t) kNOut};
+        int rc = make_tmap_bf16_sw128(&tw, wpack, 2, dims, strides, box);
+        if (rc) return rc;
+    }
+    const int tblocks = (T + TR - 1) / TR;
+    const int num_tiles = N * tblocks;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    auto kern = conv_umma_kernel<kTaps, kNOut, kRelu, OutT>;
+    SEA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kTotal), "smem attr");
+    const int grid = num_tiles < sms ? num_tiles : sms;
+    kern<<<grid, kConvThreads, SM::kTotal, s>>>(tx, tw, bias, reinterpret_cast<OutT*>(y), N, T, W, TR, tblocks, num_tiles);
+    SEA_CHECK_LAUNCH("conv_umma_kernel");
+    return SEA_OK;
+}
+
+}  // namespace
+}  // namespace sea
+
+using namespace sea;
+
+extern "C" {
+
+int sea_conv_umma_supported(int dtype, int W, int C, int O) {
+    return dtype == SEA_DTYPE_BF16 && C == 64 && (O == 64 || O == 32) && W >= 1 && W <= 128 && (128 % W) == 0;
+}
+
+int64_t sea_conv_umma_workspace_bytes(int C, int O) { return (int64_t) 9 * O * C * 2 + 1024; }
+
+int sea_causal_conv3x3_dil2_relu_umma(const void* x, const float* weight, const float* bias, void* y, void* workspace,
+                                      int N, int T, int W, int C, int O, void* stream) {
+    SEA_CHECK_ARG(x && weight && bias && y && workspace, "sea_causal_conv3x3_dil2_relu_umma: null pointer");
+    SEA_CHECK_ARG(N > 0 && T > 0, "sea_causal_conv3x3_dil2_relu_umma: bad shape");
+    if (!sea_conv_umma_supported(SEA_DTYPE_BF16, W, C, O) || O != 64) {
+        set_error("sea_causal_conv3x3_dil2_relu_umma: unsupported shape W=%d C=%d O=%d (need C=O=64, W | 128)", W, C, O);
+        return SEA_ERR_UNSUPPORTED;
+    }
+    SEA_CHECK_ARG((((uintptr_t) x) & 127) == 0 && (((uintptr_t) y) & 15) == 0 && (((uintptr_t) workspace) & 127) == 0,
+                  "sea_causal_conv3x3_dil2_relu_umma: misaligned pointer");
+    return launch_conv_umma<9, 64, true, __nv_bfloat16>(x, weight, bias, y, workspace, N, T, W, C, (cudaStream_t) stream);
+}
+
+int sea_conv1x1_umma(const void* x, const float* weight, const float* bias, float* y, void* workspace,
+                     int N, int T, int W, int C, int O, void* stream) {
+    SEA_CHECK_ARG(x && weight && bias && y && workspace, "sea_conv1x1_umma: null pointer");
+    if (!sea_conv_umma_supported(SEA_DTYPE_BF16, W, C, O) || O != 32) {
+        set_error("sea_conv1x1_umma: unsupported shape W=%d C=%d O=%d (need C=64, O=32, W | 128)", W, C, O);
+        return SEA_ERR_UNSUPPORTED;
+    }
+    SEA_CHECK_ARG((((uintptr_t) x) & 127) == 0 && (((uintptr_t) y) & 15) == 0 && (((uintptr_t) workspace) & 127) == 0, "sea_conv1x1_umma: misaligned pointer");
+    return launch_conv_umma<1, 32, false, float>(x, weight, bias, y, workspace, N, T, W, C, (cudaStream_t) stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,342 @@
+// a4 on the tensor cores (bf16): the predictor MLP as two chained tcgen05 GEMMs per 128-token tile, with every
+// intermediate kept on chip.
+//   tile   = 128 tokens = TT = 128/H consecutive query rows t x all H heads (row r = h*TT + tl), so that the tile's
+//            slice of the channels-last CNN input [N,T,W,C=2H] is one contiguous block of global memory
+//   GEMM1  : [128 x 3D] (ctx[2D] | v[D], three 64-wide K atoms fetched by three TMA boxes -- the torch.cat of
+//            attention.py:577-590 never exists) x enc_w^T [3D x 2D]        -> TMEM acc1 [128 x 128]
+//   epi 1  : + bias, LayerNorm(2D), GELU(erf)  (thread = token, fully thread-local)  -> bf16 A2 tile in smem,
+//            written directly in the SWIZZLE_128B K-major layout tcgen05 reads
+//   GEMM2  : A2 [128 x 2D] x [dec_row weight ; scaler weight ; 0-pad]^T [2D x (S*W + 16)]     -> TMEM acc2
+//   epi 2  : + bias, ChannelSplit, first CNN LayerNorm(W) (thread-local per split), scales -> global fp32,
+//            CNN input -> bf16 staged in smem as [tl][w][c = 2h+s] and copied out with coalesced 16-byte stores
+// Reference: attention.py:190-196, 242-245, 267, 289-291, 599-625.   Shapes: D = 64, S = 2, H | 128, S*W in {32,64,128}.
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace sea {
+namespace {
+
+constexpr int kMlpTcThreads = 192;
+constexpr int kD = 64, kD2 = 128, kD3 = 192;
+constexpr int kTile = 128 * 128;   // one K atom of 128 rows (bytes)
+
+struct MlpSmem {
+    static constexpr int kW1 = 0;                          // 3 atoms x [128 x 128 B]
+    static constexpr int kW2 = kW1 + 3 * kTile;            // 2 atoms x [N2max=144 x 128 B]
+    static constexpr int kW2Atom = 144 * 128;
+    static constexpr int kA1 = kW2 + 2 * kW2Atom;          // 2 buffers x 3 atoms
+    static constexpr int kA2 = kA1 + 2 * 3 * kTile;        // 2 atoms; aliased by the output staging (32 KB)
+    static constexpr int kPar = kA2 + 2 * kTile;           // fp32 parameters
+    static constexpr int kParFloats = 3 * 128 + 144 + 2 * 128;
+    static constexpr int kBar = kPar + kParFloats * 4;
+    static constexpr int kTotal = kBar + 128 + 1024;
+};
+
+__global__ void pack_mlp_weights_kernel(const float* __restrict__ enc_w, const float* __restrict__ dec_w, const float* __restrict__ scl_w,
+                                        __nv_bfloat16* __restrict__ w1, __nv_bfloat16* __restrict__ w2, int SW) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < kD2 * kD3) w1[idx] = __float2bfloat16_rn(enc_w[idx]);
+    if (idx < 144 * kD2) {
+        const int o = idx / kD2, c = idx % kD2;
+        float val = 0.f;
+        if (o < SW) val = dec_w[o * kD2 + c];
+        else if (o < SW + 2) val = scl_w[(o - SW) * kD2 + c];
+        w2[idx] = __float2bfloat16_rn(val);
+    }
+}
+
+__device__ __forceinline__ float gelu_erf_(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+__global__ void __launch_bounds__(kMlpTcThreads, 1)
+mlp_umma_kernel(const __grid_constant__ CUtensorMap tmap_ctx, const __grid_constant__ CUtensorMap tmap_v,
+                const __grid_constant__ CUtensorMap tmap_w1, const __grid_constant__ CUtensorMap tmap_w2,
+                const float* __restrict__ enc_b, const float* __restrict__ enc_ln_w, const float* __restrict__ enc_ln_b,
+                const float* __restrict__ dec_b, const float* __restrict__ scl_b,
+                const float* __restrict__ cnn_ln_w, const float* __restrict__ cnn_ln_b,
+                __nv_bfloat16* __restrict__ cnn_in, float* __restrict__ scales,
+                int N, int H, int T, int W, int TT, int tblocks, int num_tiles) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    float* par = reinterpret_cast<float*>(smem + MlpSmem::kPar);
+    float* s_enc_b = par, *s_ln_w = par + 128, *s_ln_b = par + 256, *s_dec_b = par + 384, *s_cw = par + 528, *s_cb = par + 656;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + MlpSmem::kBar);
+    uint64_t* full1 = bars;          // [2]
+    uint64_t* empty1 = bars + 2;     // [2]
+    uint64_t* acc1_full = bars + 4;
+    uint64_t* a2_full = bars + 5;
+    uint64_t* acc2_full = bars + 6;
+    uint64_t* wbar = bars + 7;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
+
+    const int SW = 2 * W, C = 2 * H;
+    const int N2 = SW + 16;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < 128; i += kMlpTcThreads) { s_enc_b[i] = enc_b[i]; s_ln_w[i] = enc_ln_w[i]; s_ln_b[i] = enc_ln_b[i]; }
+    for (int i = threadIdx.x; i < 144; i += kMlpTcThreads) s_dec_b[i] = i < SW ? dec_b[i] : (i < SW + 2 ? scl_b[i - SW] : 0.f);
+    for (int i = threadIdx.x; i < W; i += kMlpTcThreads) { s_cw[i] = cnn_ln_w[i]; s_cb[i] = cnn_ln_b[i]; }
+    if (threadIdx.x == 0) {
+        umma::prefetch_tensormap(&tmap_ctx); umma::prefetch_tensormap(&tmap_v);
+        umma::prefetch_tensormap(&tmap_w1); umma::prefetch_tensormap(&tmap_w2);
+        for (int b = 0; b < 2; ++b) { umma::mbar_init(&full1[b], 1); umma::mbar_init(&empty1[b], 1); }
+        umma::mbar_init(acc1_full, 1); umma::mbar_init(a2_full, 128); umma::mbar_init(acc2_full, 1); umma::mbar_init(wbar, 1);
+        umma::fence_barrier_init();
+    }
+    if (warp == 1) umma::tmem_alloc(tmem_ptr, 512);
+    umma::tc_fence_before();
+    __syncthreads();
+    umma::tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+    const uint32_t acc1 = tmem_base, acc2 = tmem_base + 128;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            umma::mbar_arrive_expect_tx(wbar, 3 * kTile + 2 * N2 * 128);
+            for (int a = 0; a < 3; ++a) umma::tma_load_2d(smem + MlpSmem::kW1 + a * kTile, &tmap_w1, wbar, a * 64, 0);
+            for (int a = 0; a < 2; ++a) umma::tma_load_2d(smem + MlpSmem::kW2 + a * MlpSmem::kW2Atom, &tmap_w2, wbar, a * 64, 0);
+            int buf = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int n = tile / tblocks, t0 = (tile % tblocks) * TT;
+                umma::mbar_wait(&empty1[buf], phase ^ 1);
+                umma::mbar_arrive_expect_tx(&full1[buf], 3 * kTile);
+                uint8_t* dst = smem + MlpSmem::kA1 + buf * 3 * kTile;
+                umma::tma_load_4d(dst, &tmap_ctx, &full1[buf], 0, t0, 0, n);
+                umma::tma_load_4d(dst + kTile, &tmap_ctx, &full1[buf], 64, t0, 0, n);
+                umma::tma_load_4d(dst + 2 * kTile, &tmap_v, &full1[buf], 0, t0, 0, n);
+                if (++buf == 2) { buf = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc1 = umma::make_idesc_bf16(128, 128);
+            const uint32_t idesc2 = umma::make_idesc_bf16(128, (uint32_t) N2);
+            umma::mbar_wait(wbar, 0);
+            int buf = 0;
+            uint32_t phase = 0, tphase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                umma::mbar_wait(&full1[buf], phase);
+                umma::tc_fence_after();
+                const uint32_t a1 = umma::smem_u32(smem + MlpSmem::kA1 + buf * 3 * kTile);
+                const uint32_t w1 = umma::smem_u32(smem + MlpSmem::kW1);
+#pragma unroll
+                for (int a = 0; a < 3; ++a)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma::mma_bf16_ss(acc1, umma::make_desc_k_sw128(a1 + a * kTile + k * 32), umma::make_desc_k_sw128(w1 + a * kTile + k * 32),
+                                          idesc1, (uint32_t) ((a | k) != 0));
+                umma::mma_commit(&empty1[buf]);
+                umma::mma_commit(acc1_full);
+                umma::mbar_wait(a2_full, tphase);
+                umma::tc_fence_after();
+                const uint32_t a2 = umma::smem_u32(smem + MlpSmem::kA2);
+                const uint32_t w2 = umma::smem_u32(smem + MlpSmem::kW2);
+#pragma unroll
+                for (int a = 0; a < 2; ++a)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma::mma_bf16_ss(acc2, umma::make_desc_k_sw128(a2 + a * kTile + k * 32),
+                                          umma::make_desc_k_sw128(w2 + a * MlpSmem::kW2Atom + k * 32), idesc2, (uint32_t) ((a | k) != 0));
+                umma::mma_commit(acc2_full);
+                tphase ^= 1;
+                if (++buf == 2) { buf = 0; phase ^= 1; }
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const int row = q * 32 + lane;           // token row r = h*TT + tl
+        const int h = row / TT, tl = row % TT;
+        const int et = threadIdx.x - 64;
+        uint8_t* a2s = smem + MlpSmem::kA2;
+        uint32_t tphase = 0;
+        const uint32_t lane_addr = (uint32_t) (q * 32) << 16;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int n = tile / tblocks, t0 = (tile % tblocks) * TT;
+            // ---------------- epilogue 1: bias + LayerNorm(128) + GELU -> A2 (bf16, swizzled K-major) ----------------
+            umma::mbar_wait(acc1_full, tphase);
+            umma::tc_fence_after();
+            float x[128];
+#pragma unroll
+            for (int c0 = 0; c0 < 128; c0 += 32) {
+                uint32_t r[32];
+                umma::tmem_ld_32x32(acc1 + lane_addr + (uint32_t) c0, r);
+                umma::tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) x[c0 + i] = __uint_as_float(r[i]) + s_enc_b[c0 + i];
+            }
+            float s = 0.f;
+#pragma unroll
+            for (int i = 0; i < 128; ++i) s += x[i];
+            const float mean = s * (1.0f / 128.0f);
+            float vq = 0.f;
+#pragma unroll
+            for (int i = 0; i < 128; ++i) { const float dlt = x[i] - mean; vq = fmaf(dlt, dlt, vq); }
+            const float rstd = rsqrtf(vq * (1.0f / 128.0f) + 1e-5f);
+#pragma unroll
+            for (int ch = 0; ch < 16; ++ch) {
+                float g[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int c = ch * 8 + i;
+                    g[i] = gelu_erf_((x[c] - mean) * rstd * s_ln_w[c] + s_ln_b[c]);
+                }
+                uint4 pk;
+                __nv_bfloat162 p0 = __floats2bfloat162_rn(g[0], g[1]), p1 = __floats2bfloat162_rn(g[2], g[3]);
+                __nv_bfloat162 p2 = __floats2bfloat162_rn(g[4], g[5]), p3 = __floats2bfloat162_rn(g[6], g[7]);
+                pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
+                pk.z = *reinterpret_cast<uint32_t*>(&p2); pk.w = *reinterpret_cast<uint32_t*>(&p3);
+                const int atom = ch >> 3, cc = ch & 7;
+                *reinterpret_cast<uint4*>(a2s + atom * kTile + row * 128 + ((cc ^ (row & 7)) << 4)) = pk;
+            }
+            umma::fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
+            umma::tc_fence_before();
+            umma::mbar_arrive(a2_full);
+            // ---------------- epilogue 2: dec_row bias, LayerNorm(W) per split, scales, channels-last store ----------------
+            umma::mbar_wait(acc2_full, tphase);
+            umma::tc_fence_after();
+            const int t = t0 + tl;
+            {   // scales: columns SW, SW+1
+                uint32_t r[32];
+                umma::tmem_ld_32x32(acc2 + lane_addr + (uint32_t) SW, r);     // columns SW .. SW+31 (allocated, only 2 used)
+                umma::tmem_ld_wait();
+                if (t < T) {
+                    float2 sc = make_float2(__uint_as_float(r[0]) + s_dec_b[SW], __uint_as_float(r[1]) + s_dec_b[SW + 1]);
+                    *reinterpret_cast<float2*>(scales + ((((int64_t) n * H + h) * T + t) << 1)) = sc;
+                }
+            }
+            // staging [tl][w][c] bf16 aliases A2: GEMM2 has completed (acc2_full), so A2 is free
+            __nv_bfloat16* stg = reinterpret_cast<__nv_bfloat16*>(a2s);
+            float sp[2][2];   // per split: mean, rstd
+            // pass 1: statistics of both splits
+#pragma unroll
+            for (int sidx = 0; sidx < 2; ++sidx) {
+                float sm = 0.f, sq = 0.f;
+                for (int c0 = 0; c0 < W; c0 += 32) {
+                    uint32_t r[32];
+                    umma::tmem_ld_32x32(acc2 + lane_addr + (uint32_t) (sidx * W + c0), r);
+                    umma::tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        if (c0 + i < W) {
+                            const float val = __uint_as_float(r[i]) + s_dec_b[sidx * W + c0 + i];
+                            sm += val;
+                            sq = fmaf(val, val, sq);
+                        }
+                    }
+                }
+                const float mu = sm / (float) W;
+                sp[sidx][0] = mu;
+                sp[sidx][1] = rsqrtf(fmaxf(sq / (float) W - mu * mu, 0.f) + 1e-5f);
+            }
+            // pass 2: normalise and stage; channel pair (2h, 2h+1) = (split 0, split 1) of this head
+            for (int c0 = 0; c0 < W; c0 += 32) {
+                uint32_t r0[32], r1[32];
+                umma::tmem_ld_32x32(acc2 + lane_addr + (uint32_t) c0, r0);
+                umma::tmem_ld_32x32(acc2 + lane_addr + (uint32_t) (W + c0), r1);
+                umma::tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const int w = c0 + i;
+                    if (w < W) {
+                        const float v0 = (__uint_as_float(r0[i]) + s_dec_b[w] - sp[0][0]) * sp[0][1] * s_cw[w] + s_cb[w];
+                        const float v1 = (__uint_as_float(r1[i]) + s_dec_b[W + w] - sp[1][0]) * sp[1][1] * s_cw[w] + s_cb[w];
+                        *reinterpret_cast<__nv_bfloat162*>(stg + ((size_t) (tl * W + w) * C + 2 * h)) = __floats2bfloat162_rn(v0, v1);
+                    }
+                }
+            }
+            umma::tc_fence_before();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            const int valid_t = min(TT, T - t0);
+            const int nchunks = (valid_t * W * C * 2) >> 4;       // 16-byte chunks of the contiguous block
+            uint8_t* gout = reinterpret_cast<uint8_t*>(cnn_in) + (((int64_t) n * T + t0) * W * C) * 2;
+            for (int g = et; g < nchunks; g += 128)
+                *reinterpret_cast<uint4*>(gout + (int64_t) g * 16) = *reinterpret_cast<const uint4*>(a2s + (size_t) g * 16);
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            tphase ^= 1;
+        }
+    }
+    umma::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        umma::tc_fence_after();
+        umma::tmem_dealloc(tmem_base, 512);
+    }
+}
+
+}  // namespace
+}  // namespace sea
+
+using namespace sea;
+
+extern "C" {
+
+int sea_predictor_mlp_umma_supported(int dtype, int H, int D, int S, int W) {
+    return dtype == SEA_DTYPE_BF16 && D == 64 && S == 2 && H >= 1 && H <= 128 && (128 % H) == 0 && (W == 16 || W == 32 || W == 64);
+}
+
+int64_t sea_predictor_mlp_umma_workspace_bytes(void) { return (int64_t) (kD2 * kD3 + 144 * kD2) * 2 + 1024; }
+
+int sea_predictor_mlp_umma_fwd(const void* ctx, const void* v, int64_t v_sn, int64_t v_sh, int64_t v_st,
+                               const float* enc_w, const float* enc_b, const float* enc_ln_w, const float* enc_ln_b,
+                               const float* dec_w, const float* dec_b, const float* cnn_ln_w, const float* cnn_ln_b,
+                               const float* scl_w, const float* scl_b, void* cnn_in, float* scales, void* workspace,
+                               int N, int H, int T, int D, int S, int W, void* stream) {
+    SEA_CHECK_ARG(ctx && v && enc_w && enc_b && enc_ln_w && enc_ln_b && dec_w && dec_b && cnn_ln_w && cnn_ln_b && scl_w && scl_b &&
+                  cnn_in && scales && workspace, "sea_predictor_mlp_umma_fwd: null pointer");
+    if (!sea_predictor_mlp_umma_supported(SEA_DTYPE_BF16, H, D, S, W)) {
+        set_error("sea_predictor_mlp_umma_fwd: unsupported shape H=%d D=%d S=%d W=%d", H, D, S, W);
+        return SEA_ERR_UNSUPPORTED;
+    }
+    SEA_CHECK_ARG(N > 0 && T > 0, "sea_predictor_mlp_umma_fwd: bad shape");
+    SEA_CHECK_ARG((((uintptr_t) ctx) & 127) == 0 && (((uintptr_t) v) & 15) == 0 && (((uintptr_t) cnn_in) & 15) == 0 && (((uintptr_t) workspace) & 127) == 0 &&
+                  (v_sn % 8) == 0 && (v_sh % 8) == 0 && (v_st % 8) == 0, "sea_predictor_mlp_umma_fwd: misaligned pointer or stride");
+    cudaStream_t s = (cudaStream_t) stream;
+    __nv_bfloat16* w1 = reinterpret_cast<__nv_bfloat16*>(workspace);
+    __nv_bfloat16* w2 = w1 + kD2 * kD3;
+    const int SW = S * W;
+    pack_mlp_weights_kernel<<<(kD2 * kD3 + 255) / 256, 256, 0, s>>>(enc_w, dec_w, scl_w, w1, w2, SW);
+    SEA_CHECK_LAUNCH("pack_mlp_weights_kernel");
+    const int TT = 128 / H;
+    CUtensorMap t_ctx, t_v, t_w1, t_w2;
+    {
+        const uint64_t dims[4] = {(uint64_t) kD2, (uint64_t) T, (uint64_t) H, (uint64_t) N};
+        const uint64_t str[3] = {(uint64_t) kD2 * 2, (uint64_t) T * kD2 * 2, (uint64_t) H * T * kD2 * 2};
+        const uint32_t box[4] = {64, (uint32_t) TT, (uint32_t) H, 1};
+        int rc = make_tmap_bf16_sw128(&t_ctx, const_cast<void*>(ctx), 4, dims, str, box);
+        if (rc) return rc;
+    }
+    {
+        const uint64_t dims[4] = {(uint64_t) kD, (uint64_t) T, (uint64_t) H, (uint64_t) N};
+        const uint64_t str[3] = {(uint64_t) v_st * 2, (uint64_t) v_sh * 2, (uint64_t) v_sn * 2};
+        const uint32_t box[4] = {64, (uint32_t) TT, (uint32_t) H, 1};
+        int rc = make_tmap_bf16_sw128(&t_v, const_cast<void*>(v), 4, dims, str, box);
+        if (rc) return rc;
+    }
+    {
+        const uint64_t dims[2] = {(uint64_t) kD3, (uint64_t) kD2};
+        const uint64_t str[1] = {(uint64_t) kD3 * 2};
+        const uint32_t box[2] = {64, 128};
+        int rc = make_tmap_bf16_sw128(&t_w1, w1, 2, dims, str, box);
+        if (rc) return rc;
+    }
+    {
+        const uint64_t dims[2] = {(uint64_t) kD2, 144};
+        const uint64_t str[1] = {(uint64_t) kD2 * 2};
+        const uint32_t box[2] = {64, (uint32_t) (SW + 16)};
+        int rc = make_tmap_bf16_sw128(&t_w2, w2, 2, dims, str, box);
+        if (rc) return rc;
+    }
+    const int tblocks = (T + TT - 1) / TT;
+    const int num_tiles = N * tblocks;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    SEA_CUDA_TRY(cudaFuncSetAttribute(mlp_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MlpSmem::kTotal), "smem attr");
+    const int grid = num_tiles < sms ? num_tiles : sms;
+    mlp_umma_kernel<<<grid, kMlpTcThreads, MlpSmem::kTotal, s>>>(t_ctx, t_v, t_w1, t_w2, enc_b, enc_ln_w, enc_ln_b, dec_b, scl_b, cnn_ln_w,
+                                                                 cnn_ln_b, reinterpret_cast<__nv_bfloat16*>(cnn_in), scales, N, H, T, W, TT,
+                                                                 tblocks, num_tiles);
+    SEA_CHECK_LAUNCH("mlp_umma_kernel");
+    return SEA_OK;
+}
+
+}  // extern "C"

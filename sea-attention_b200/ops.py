@@ -251,7 +251,7 @@ def performer_causal(q, k, v, pos_emb, proj, want_cumavg=True):
     return ctx, avg
 
 
-def predictor_mlp(ctx, v, w, S: int, W: int, want_t_pred=False):
+def predictor_mlp(ctx, v, w, S: int, W: int, want_t_pred=False, force_simt=False):
     """a4.  `w` = dict of fp32 contiguous weights (enc_w, enc_b, enc_ln_w, enc_ln_b, dec_w, dec_b, cnn_ln_w, cnn_ln_b,
     scl_w, scl_b) -> cnn_in [N,T,W,H*S] channels-last, scales fp32 [N,H,T,2], t_pred or None."""
     _cuda(ctx, v)
@@ -260,6 +260,17 @@ def predictor_mlp(ctx, v, w, S: int, W: int, want_t_pred=False):
     v = _inner_contig(v)
     cnn_in = torch.empty((N, T, W, H * S), dtype=ctx.dtype, device=ctx.device)
     scales = torch.empty((N, H, T, 2), dtype=torch.float32, device=ctx.device)
+    lib = _lib.load()
+    if (not want_t_pred and not force_simt and ctx.is_contiguous()
+            and lib.sea_predictor_mlp_umma_supported(_DTYPES.get(ctx.dtype, -1), H, D, S, W)
+            and v.stride(0) % 8 == 0 and v.stride(1) % 8 == 0 and v.stride(2) % 8 == 0):
+        ws = torch.empty((lib.sea_predictor_mlp_umma_workspace_bytes(),), dtype=torch.uint8, device=ctx.device)
+        _lib.call('sea_predictor_mlp_umma_fwd', ctx.data_ptr(), v.data_ptr(), v.stride(0), v.stride(1), v.stride(2),
+                  w['enc_w'].data_ptr(), w['enc_b'].data_ptr(), w['enc_ln_w'].data_ptr(), w['enc_ln_b'].data_ptr(),
+                  w['dec_w'].data_ptr(), w['dec_b'].data_ptr(), w['cnn_ln_w'].data_ptr(), w['cnn_ln_b'].data_ptr(),
+                  w['scl_w'].data_ptr(), w['scl_b'].data_ptr(), cnn_in.data_ptr(), scales.data_ptr(), ws.data_ptr(),
+                  N, H, T, D, S, W, _stream())
+        return cnn_in, scales, None
     t_pred = torch.empty((N, H, T, D2), dtype=ctx.dtype, device=ctx.device) if want_t_pred else None
     _lib.call('sea_predictor_mlp_fwd', ctx.data_ptr(), v.data_ptr(), v.stride(0), v.stride(1), v.stride(2), _dtype_code(ctx),
               w['enc_w'].data_ptr(), w['enc_b'].data_ptr(), w['enc_ln_w'].data_ptr(), w['enc_ln_b'].data_ptr(),
@@ -269,16 +280,53 @@ def predictor_mlp(ctx, v, w, S: int, W: int, want_t_pred=False):
     return cnn_in, scales, t_pred
 
 
-def causal_conv3x3_dil2_relu(x, weight, bias):
+def conv_umma_supported(dtype, W, C, O) -> bool:
+    return bool(_lib.load().sea_conv_umma_supported(_DTYPES.get(dtype, -1), W, C, O))
+
+
+def _conv_ws(C, O, device):
+    return torch.empty((_lib.load().sea_conv_umma_workspace_bytes(C, O),), dtype=torch.uint8, device=device)
+
+
+def causal_conv3x3_dil2_relu(x, weight, bias, force_simt=False):
     """a5: one CausalConv2d(C,O,3,padding=2,dilation=2,causal)+ReLU on channels-last x [N,T,W,C];
-    weight fp32 in the reference layout [O,C,5,3]."""
+    weight fp32 in the reference layout [O,C,5,3].  bf16 with C=O=64 runs the tcgen05 implicit-GEMM kernel,
+    everything else the fp32 SIMT kernel."""
     _cuda(x, weight, bias)
     N, T, W, C = x.shape
     O = weight.shape[0]
     y = torch.empty((N, T, W, O), dtype=x.dtype, device=x.device)
+    if not force_simt and O == 64 and conv_umma_supported(x.dtype, W, C, O):
+        ws = _conv_ws(C, O, x.device)
+        _lib.call('sea_causal_conv3x3_dil2_relu_umma', x.data_ptr(), weight.data_ptr(), bias.data_ptr(), y.data_ptr(), ws.data_ptr(),
+                  N, T, W, C, O, _stream())
+        return y
     _lib.call('sea_causal_conv3x3_dil2_relu', x.data_ptr(), weight.data_ptr(), bias.data_ptr(), y.data_ptr(), _dtype_code(x),
               N, T, W, C, O, _stream())
     return y
+
+
+def conv1x1_umma(x, weight, bias):
+    """1x1 CausalConv2d(64 -> 32) before the upsample, tcgen05: x bf16 [N,T,W,64] -> y fp32 [N,T,W,32]."""
+    _cuda(x, weight, bias)
+    N, T, W, C = x.shape
+    O = weight.shape[0]
+    y = torch.empty((N, T, W, O), dtype=torch.float32, device=x.device)
+    ws = _conv_ws(C, O, x.device)
+    _lib.call('sea_conv1x1_umma', x.data_ptr(), weight.data_ptr(), bias.data_ptr(), y.data_ptr(), ws.data_ptr(), N, T, W, C, O, _stream())
+    return y
+
+
+def predictor_tail_topk(y3, bias, ln_w, ln_b, k_per_row, P: int, want_probs=True, want_bits=True):
+    """a5 tail + a6 + a7 fused: y3 fp32 [N,T,W,H] (conv1x1_umma) -> probs fp32 [N,H,T,P], top-k bit mask [N,T,H*P/32]."""
+    _cuda(y3, bias, ln_w, ln_b, k_per_row)
+    N, T, W, H = y3.shape
+    probs = torch.empty((N, H, T, P), dtype=torch.float32, device=y3.device) if want_probs else None
+    bits = torch.empty((N, T, (H * P) // 32), dtype=torch.int32, device=y3.device) if want_bits else None
+    kpr = None if k_per_row is None else k_per_row.reshape(-1).float().contiguous()
+    _lib.call('sea_predictor_tail_topk_fwd', y3.data_ptr(), bias.data_ptr(), ln_w.data_ptr(), ln_b.data_ptr(), _p(kpr), _p(probs),
+              _p(bits), N, H, T, W, P, _stream())
+    return probs, bits
 
 
 def predictor_tail(x, weight, bias, ln_w, ln_b, P: int, want_scores=False):

@@ -1,0 +1,96 @@
+"""GPU: the tcgen05/TMA implicit-GEMM kernels (bf16) against the fp32 SIMT kernels / the oracle."""
+import pytest
+import torch
+
+from oracle import sea_oracle as so
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+def _conv_ref(x_cl, weight, bias):
+    """x_cl [N,T,W,C] float -> oracle conv (NCHW) -> channels-last"""
+    x = x_cl.permute(0, 3, 1, 2).float()
+    wm = torch.zeros_like(weight)
+    wm[:, :, :3, :] = 1
+    y = torch.relu(so.causal_conv2d(x, weight, wm, bias, 3, 2, 2))
+    return y.permute(0, 2, 3, 1).contiguous()
+
+
+@pytest.mark.parametrize('N,T,W', [(1, 8, 64), (2, 37, 64), (1, 130, 32), (1, 64, 16), (1, 5, 128)])
+def test_conv3x3_umma_matches_oracle(sea, N, T, W):
+    C = O = 64
+    g = torch.Generator().manual_seed(T * 7 + W)
+    x = torch.randn(N, T, W, C, generator=g).bfloat16()
+    weight = torch.zeros(O, C, 5, 3)
+    weight[:, :, :3, :] = torch.randn(O, C, 3, 3, generator=g) * 0.05
+    bias = torch.randn(O, generator=g) * 0.1
+    assert sea.ops.conv_umma_supported(torch.bfloat16, W, C, O)
+    y = sea.ops.causal_conv3x3_dil2_relu(x.to(DEV), weight.to(DEV), bias.to(DEV))
+    torch.cuda.synchronize()
+    # reference on the bf16-rounded operands (the kernel multiplies bf16 x bf16 exactly, accumulates in fp32)
+    ref = _conv_ref(x.float(), weight.bfloat16().float(), bias)
+    torch.testing.assert_close(y.float().cpu(), ref, rtol=2e-2, atol=2e-2)
+    # and against the fp32 SIMT kernel fed the same bf16 input
+    y2 = sea.ops.causal_conv3x3_dil2_relu(x.to(DEV), weight.to(DEV), bias.to(DEV), force_simt=True)
+    torch.testing.assert_close(y.float().cpu(), y2.float().cpu(), rtol=2e-2, atol=2e-2)
+
+
+@pytest.mark.parametrize('N,T,W', [(1, 8, 64), (2, 37, 64), (1, 130, 32)])
+def test_conv1x1_umma_matches_oracle(sea, N, T, W):
+    C, O = 64, 32
+    g = torch.Generator().manual_seed(T + W)
+    x = torch.randn(N, T, W, C, generator=g).bfloat16()
+    weight = torch.randn(O, C, generator=g) * 0.1
+    bias = torch.randn(O, generator=g)
+    y = sea.ops.conv1x1_umma(x.to(DEV), weight.to(DEV), bias.to(DEV))
+    ref = x.float() @ weight.bfloat16().float().t() + bias
+    torch.testing.assert_close(y.cpu(), ref, rtol=1e-2, atol=1e-2)
+
+
+@pytest.mark.parametrize('N,H,T,W,P,k', [(1, 32, 40, 64, 256, 64), (2, 8, 33, 16, 64, 8), (1, 4, 20, 8, 32, 4), (1, 32, 12, 32, 128, 16)])
+def test_tail_topk_fused_matches_oracle(sea, N, H, T, W, P, k):
+    import numpy as np
+    g = torch.Generator().manual_seed(P + T)
+    y3 = torch.randn(N, T, W, H, generator=g)
+    bias = torch.randn(H, generator=g)
+    ln_w = 1 + 0.1 * torch.randn(P, generator=g)
+    ln_b = 0.1 * torch.randn(P, generator=g)
+    kpr = torch.from_numpy(np.tile(so.per_item_top_k_causal(H, k, 1.0, P, T), N))
+    probs, bits = sea.ops.predictor_tail_topk(y3.to(DEV), bias.to(DEV), ln_w.to(DEV), ln_b.to(DEV), kpr.to(DEV), P)
+    # oracle: [N,H,T,W] -> nearest x(P/W) -> bias pad columns -> area resize -> LN -> softmax
+    y = y3.permute(0, 3, 1, 2)
+    u = y.repeat_interleave(P // W, dim=-1)
+    pad = bias.view(1, H, 1, 1).expand(N, H, T, 1)
+    u = so.area_resize_width(torch.cat([pad, u, pad], dim=-1), P)
+    ref = torch.softmax(so.layer_norm(u, ln_w, ln_b), dim=-1)
+    torch.testing.assert_close(probs.cpu(), ref, rtol=1e-4, atol=1e-7)
+    # top-k bit-exact given the kernel's own probabilities
+    mask_ref = so.topk_mask_causal_batch(probs.cpu(), k)
+    assert torch.equal(sea.ops.bits_to_mask(bits, H, P).cpu(), mask_ref)
+    # and equal to the standalone top-k kernel
+    bits2 = sea.ops.topk_mask_bits(probs, kpr.to(DEV), 'causal_batch')
+    assert torch.equal(bits.cpu(), bits2.cpu())
+
+
+@pytest.mark.parametrize('N,H,T,P', [(1, 32, 64, 256), (2, 32, 37, 256), (1, 16, 50, 128), (1, 64, 9, 64), (1, 4, 70, 256)])
+def test_mlp_umma_matches_simt(sea, N, H, T, P):
+    import transformers
+    d, S, W = 64, 2, P // 4
+    torch.manual_seed(P + H)
+    cfg = transformers.BertConfig(hidden_size=H * d, num_attention_heads=H, max_position_embeddings=T)
+    pc = sea.PerlinAttentionConfig(performer_nb_factor=8, k=8, attention_predictor_length=P, causal=True)
+    mod = sea.PerlinAttention(cfg, pc).eval().to(DEV)
+    for n_, p_ in mod.named_parameters():
+        if p_.ndim == 1:
+            p_.data.add_(0.1 * torch.randn_like(p_))
+    w = mod._weights_fp32()
+    ctx = torch.randn(N, H, T, 2 * d, device=DEV).bfloat16()
+    v = torch.randn(N, H, T, d, device=DEV).bfloat16()
+    assert sea._lib.load().sea_predictor_mlp_umma_supported(1, H, d, S, W)
+    a_in, a_sc, _ = sea.ops.predictor_mlp(ctx, v, w, S, W)
+    b_in, b_sc, _ = sea.ops.predictor_mlp(ctx, v, w, S, W, force_simt=True)
+    torch.cuda.synchronize()
+    # bf16 operands (weights and the GELU output are rounded to bf16 before each GEMM): 2e-2-class tolerance
+    torch.testing.assert_close(a_sc.cpu(), b_sc.cpu(), rtol=3e-2, atol=3e-2)
+    torch.testing.assert_close(a_in.float().cpu(), b_in.float().cpu(), rtol=5e-2, atol=5e-2)
