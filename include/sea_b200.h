@@ -142,6 +142,17 @@ SEA_API int sea_performer_causal_fwd(const void* q, int64_t q_sn, int64_t q_sh, 
                              void* ctx, void* cumavg, float* workspace,
                              int N, int H, int T, int D, int F, void* stream);
 
+/* a2+a3 on the tensor cores (bf16, D = 64, F <= 63; csrc/performer_mma.cu): same contract as
+ * sea_performer_causal_fwd, chunk-parallel GEMMs chained through registers.  workspace: fp32,
+ * >= sea_performer_mma_workspace_floats(...) elements. */
+SEA_API int sea_performer_mma_supported(int dtype, int D, int F);
+SEA_API int64_t sea_performer_mma_workspace_floats(int N, int H, int T, int D, int F);
+SEA_API int sea_performer_causal_mma_fwd(const void* q, int64_t q_sn, int64_t q_sh, int64_t q_st,
+                                         const void* k, int64_t k_sn, int64_t k_sh, int64_t k_st,
+                                         const void* v, int64_t v_sn, int64_t v_sh, int64_t v_st,
+                                         const float* pos_emb, const float* proj, void* ctx, void* cumavg, float* workspace,
+                                         int N, int H, int T, int D, int F, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * a4  predictor MLP (attention.py:190-196,242-245,289-291,577-625) for the causal predictor:
  *   x = cat(ctx[2D], v[D]) -> Linear(3D,2D) -> LayerNorm -> GELU = t_pred

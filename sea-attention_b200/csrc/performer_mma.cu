@@ -1,0 +1,436 @@
+// a2 + a3 (+ a13 running mean) for bf16, D = 64: the causal Performer estimate as chunk-parallel tensor-core GEMMs.
+//
+// Everything the stage needs per 128-row chunk is a small GEMM, chained through REGISTERS (accumulator fragments are
+// re-packed as the next MMA's A fragments, flash-attention style), so nothing but q, k, v is read and nothing but
+// ctx / cumavg is written:
+//   phi(k) = relu(d^-1/4 K P^T)+1e-3, phi(q) likewise                [128 x 64] x [64 x Fp]
+//   pass A : S_c = phi_ext(k)^T V2ext                                [Fp x 128] x [128 x 144]   per chunk -> workspace
+//   prefix : exclusive prefix of S_c over the chunks of one (n, h)   (performer.cu: performer_prefix_kernel)
+//   pass C : O = tril(phi(q) phi(k)^T) V2ext + phi(q) S_prev         [128 x 128] x [128 x 144] + [128 x Fp] x [Fp x 144]
+//            ctx = O[:, :128] / O[:, 128] ;  cumavg = (tril(1) V + vsum_prev) / (t+1)
+// with V2ext = [pos_emb | v | 1 | 0-pad] (the `1` column carries the denominator: O[:,128] = sum_j A_ij + phi(q).z) and
+// phi_ext(k) = [phi(k) | 1 | 0-pad] (the `1` feature makes row F of S the column sums of V2ext = running sum of v).
+// Warp-level mma.sync.m16n8k16 (bf16 in, fp32 accumulate) + ldmatrix: the FLOPs here are ~13 GF per layer, the stage is
+// bound by HBM and launch latency, not by the tensor pipe; tcgen05 would not change the roofline.
+// Reference: performer_pytorch.FastAttention call sites attention.py:159-164, 504-508, 527-534; running mean :1237-1241.
+#include "common.cuh"
+
+namespace sea {
+namespace {
+
+constexpr int kCh = 128;            // rows per chunk
+constexpr int kThreads = 256;       // 8 warps x 16 rows
+constexpr int kDm = 64;             // head dim
+constexpr int kE = 128;             // v2 width
+constexpr int kEx = 144;            // v2ext width (ones column at 128)
+constexpr int kLdQ = kDm + 8;       // smem row strides (elements); +8 keeps ldmatrix rows on distinct banks
+constexpr int kLdV = kEx + 8;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+    __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&p);
+}
+
+template <int kFp>
+struct PerfSmem {
+    static constexpr int kP = 0;                                // [kFp][kLdQ]
+    static constexpr int kQ = kP + kFp * kLdQ;                  // [kCh][kLdQ]
+    static constexpr int kK = kQ + kCh * kLdQ;                  // [kCh][kLdQ]
+    static constexpr int kPhiK = kK + kCh * kLdQ;               // [kCh][kFp + 8]
+    static constexpr int kV = kPhiK + kCh * (kFp + 8);          // [kCh][kLdV]
+    static constexpr int kS = kV + kCh * kLdV;                  // [kFp][kLdV]
+    static constexpr int kElems = kS + kFp * kLdV;
+    static constexpr int kBytes = kElems * 2 + 64 * 4;          // + vsum_prev fp32 [64]
+};
+
+// ---- cooperative loads -------------------------------------------------------------------------------------------
+template <int kFp>
+__device__ __forceinline__ void load_proj(__nv_bfloat16* Ps, const float* __restrict__ proj, int F) {
+    for (int idx = threadIdx.x; idx < kFp * kDm; idx += kThreads) {
+        const int f = idx / kDm, c = idx % kDm;
+        Ps[f * kLdQ + c] = __float2bfloat16_rn(f < F ? proj[f * kDm + c] : 0.f);
+    }
+}
+__device__ __forceinline__ void load_rows_bf16(__nv_bfloat16* dst, int ld, const __nv_bfloat16* __restrict__ src, int64_t row_stride,
+                                               int r0, int nvalid) {
+    // 128 rows x 64 bf16, 16-byte vectors; rows beyond nvalid are zero
+    for (int idx = threadIdx.x; idx < kCh * (kDm / 8); idx += kThreads) {
+        const int r = idx >> 3, c8 = idx & 7;
+        uint4 val = make_uint4(0, 0, 0, 0);
+        if (r < nvalid) val = __ldg(reinterpret_cast<const uint4*>(src + (int64_t) (r0 + r) * row_stride) + c8);
+        *reinterpret_cast<uint4*>(dst + r * ld + c8 * 8) = val;
+    }
+}
+__device__ __forceinline__ void load_v2ext(__nv_bfloat16* Vs, const __nv_bfloat16* __restrict__ v, int64_t v_st, const float* __restrict__ pos,
+                                           int r0, int nvalid) {
+    for (int idx = threadIdx.x; idx < kCh * (kDm / 8); idx += kThreads) {     // v -> cols 64..127
+        const int r = idx >> 3, c8 = idx & 7;
+        uint4 val = make_uint4(0, 0, 0, 0);
+        if (r < nvalid) val = __ldg(reinterpret_cast<const uint4*>(v + (int64_t) (r0 + r) * v_st) + c8);
+        *reinterpret_cast<uint4*>(Vs + r * kLdV + kDm + c8 * 8) = val;
+    }
+    for (int idx = threadIdx.x; idx < kCh * (kDm / 4); idx += kThreads) {     // pos_emb (fp32) -> cols 0..63
+        const int r = idx >> 4, c4 = idx & 15;
+        float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < nvalid) p = __ldg(reinterpret_cast<const float4*>(pos + (int64_t) (r0 + r) * kDm) + c4);
+        uint2 pk = make_uint2(pack_bf16(p.x, p.y), pack_bf16(p.z, p.w));
+        *reinterpret_cast<uint2*>(Vs + r * kLdV + c4 * 4) = pk;
+    }
+    for (int idx = threadIdx.x; idx < kCh * 3; idx += kThreads) {             // cols 128..151: ones column then zeros
+        const int r = idx / 3, part = idx % 3;
+        uint4 val = make_uint4(0, 0, 0, 0);
+        if (part == 0 && r < nvalid) val.x = 0x00003F80u;                      // bf16(1.0) at column 128
+        *reinterpret_cast<uint4*>(Vs + r * kLdV + kE + part * 8) = val;
+    }
+}
+
+// phi of this warp's 16 rows: acc[kFp/8][4] = X[16 x 64] . P^T, then relu(norm * acc) + 1e-3 on the valid features
+template <int kFp>
+__device__ __forceinline__ void phi_rows(float (&acc)[kFp / 8][4], const __nv_bfloat16* Xs, const __nv_bfloat16* Ps, int warp, int lane) {
+#pragma unroll
+    for (int nt = 0; nt < kFp / 8; ++nt)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[nt][i] = 0.f;
+    const int arow = 16 * warp + (lane & 7) + 8 * ((lane >> 3) & 1), acol = 8 * (lane >> 4);
+    const int brow = (lane & 7) + 8 * (lane >> 4), bcol = 8 * ((lane >> 3) & 1);       // B from [n][k] storage
+#pragma unroll
+    for (int ks = 0; ks < kDm / 16; ++ks) {
+        uint32_t a[4];
+        ldsm_x4(a, smem_u32(Xs + arow * kLdQ + ks * 16 + acol));
+#pragma unroll
+        for (int np = 0; np < kFp / 16; ++np) {
+            uint32_t b[4];      // b[0],b[1]: n-tile 2np ; b[2],b[3]: n-tile 2np+1
+            ldsm_x4(b, smem_u32(Ps + (np * 16 + brow) * kLdQ + ks * 16 + bcol));
+            mma16816(acc[2 * np], a, b[0], b[1]);
+            mma16816(acc[2 * np + 1], a, b[2], b[3]);
+        }
+    }
+}
+
+// ---- pass A: per-chunk state sums -----------------------------------------------------------------------------
+template <int kFp>
+__global__ void __launch_bounds__(kThreads)
+performer_sums_mma_kernel(const __nv_bfloat16* __restrict__ k, int64_t k_sn, int64_t k_sh, int64_t k_st,
+                          const __nv_bfloat16* __restrict__ v, int64_t v_sn, int64_t v_sh, int64_t v_st,
+                          const float* __restrict__ pos_emb, const float* __restrict__ proj, float* __restrict__ ws,
+                          int H, int T, int F, int nchunks) {
+    using SM = PerfSmem<kFp>;
+    extern __shared__ __align__(16) __nv_bfloat16 sm[];
+    __nv_bfloat16 *Ps = sm + SM::kP, *Ks = sm + SM::kK, *PhiK = sm + SM::kPhiK, *Vs = sm + SM::kV;
+    const int chunk = blockIdx.x, nh = blockIdx.y, n = nh / H, h = nh % H;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tq = lane & 3;
+    const int r0 = chunk * kCh, nvalid = min(kCh, T - r0);
+    load_proj<kFp>(Ps, proj, F);
+    load_rows_bf16(Ks, kLdQ, k + (int64_t) n * k_sn + (int64_t) h * k_sh, k_st, r0, nvalid);
+    load_v2ext(Vs, v + (int64_t) n * v_sn + (int64_t) h * v_sh, v_st, pos_emb, r0, nvalid);
+    __syncthreads();
+    const float norm = rsqrtf(sqrtf((float) kDm));
+    {
+        float acc[kFp / 8][4];
+        phi_rows<kFp>(acc, Ks, Ps, warp, lane);
+#pragma unroll
+        for (int nt = 0; nt < kFp / 8; ++nt) {
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int row = 16 * warp + g + 8 * half;
+                float o[2];
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int f = nt * 8 + 2 * tq + e;
+                    float val = 0.f;
+                    if (row < nvalid) val = f < F ? fmaxf(acc[nt][2 * half + e] * norm, 0.f) + 1e-3f : (f == F ? 1.0f : 0.f);
+                    o[e] = val;
+                }
+                *reinterpret_cast<uint32_t*>(PhiK + row * (kFp + 8) + nt * 8 + 2 * tq) = pack_bf16(o[0], o[1]);
+            }
+        }
+    }
+    __syncthreads();
+    // S_c[f][e] = sum_r PhiK[r][f] * V2ext[r][e]: warp w owns n-tiles {w, w+8, w+16}
+    constexpr int kMT = kFp / 16;
+    float acc[kMT][3][4];
+#pragma unroll
+    for (int mt = 0; mt < kMT; ++mt)
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[mt][j][i] = 0.f;
+    const int ar = (lane & 7) + 8 * (lane >> 4), af = 8 * ((lane >> 3) & 1);        // A^T from [r][f] storage (trans)
+    const int br = (lane & 7) + 8 * ((lane >> 3) & 1);                               // B from [k][n] storage (trans), x2 per n-tile
+#pragma unroll
+    for (int ks = 0; ks < kCh / 16; ++ks) {
+        uint32_t a[kMT][4];
+#pragma unroll
+        for (int mt = 0; mt < kMT; ++mt) ldsm_x4_t(a[mt], smem_u32(PhiK + (ks * 16 + ar) * (kFp + 8) + mt * 16 + af));
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const int nt = warp + 8 * j;
+            if (nt < kEx / 8) {
+                uint32_t b[4];
+                // x4.trans: matrices (k 0-7, n 0-7), (k 8-15, n 0-7), and the same for the next 8 columns (unused half ok)
+                ldsm_x4_t(b, smem_u32(Vs + (ks * 16 + br) * kLdV + nt * 8 + 8 * (lane >> 4)));
+#pragma unroll
+                for (int mt = 0; mt < kMT; ++mt) mma16816(acc[mt][j], a[mt], b[0], b[1]);
+            }
+        }
+    }
+    float* slot = ws + ((int64_t) nh * nchunks + chunk) * (kFp * kEx);
+#pragma unroll
+    for (int mt = 0; mt < kMT; ++mt)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const int nt = warp + 8 * j;
+            if (nt < kEx / 8) {
+                const int f0 = mt * 16 + g, e0 = nt * 8 + 2 * tq;
+                *reinterpret_cast<float2*>(slot + f0 * kEx + e0) = make_float2(acc[mt][j][0], acc[mt][j][1]);
+                *reinterpret_cast<float2*>(slot + (f0 + 8) * kEx + e0) = make_float2(acc[mt][j][2], acc[mt][j][3]);
+            }
+        }
+}
+
+// ---- pass C: outputs ------------------------------------------------------------------------------------------
+template <int kFp>
+__global__ void __launch_bounds__(kThreads, 1)
+performer_out_mma_kernel(const __nv_bfloat16* __restrict__ q, int64_t q_sn, int64_t q_sh, int64_t q_st,
+                         const __nv_bfloat16* __restrict__ k, int64_t k_sn, int64_t k_sh, int64_t k_st,
+                         const __nv_bfloat16* __restrict__ v, int64_t v_sn, int64_t v_sh, int64_t v_st,
+                         const float* __restrict__ pos_emb, const float* __restrict__ proj, const float* __restrict__ ws,
+                         __nv_bfloat16* __restrict__ ctx, __nv_bfloat16* __restrict__ cumavg, int H, int T, int F, int nchunks) {
+    using SM = PerfSmem<kFp>;
+    extern __shared__ __align__(16) __nv_bfloat16 sm[];
+    __nv_bfloat16 *Ps = sm + SM::kP, *Qs = sm + SM::kQ, *Ks = sm + SM::kK, *PhiK = sm + SM::kPhiK, *Vs = sm + SM::kV, *Ss = sm + SM::kS;
+    float* vsum_prev = reinterpret_cast<float*>(sm + SM::kElems);
+    const int chunk = blockIdx.x, nh = blockIdx.y, n = nh / H, h = nh % H;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tq = lane & 3;
+    const int r0 = chunk * kCh, nvalid = min(kCh, T - r0);
+    load_proj<kFp>(Ps, proj, F);
+    load_rows_bf16(Qs, kLdQ, q + (int64_t) n * q_sn + (int64_t) h * q_sh, q_st, r0, nvalid);
+    load_rows_bf16(Ks, kLdQ, k + (int64_t) n * k_sn + (int64_t) h * k_sh, k_st, r0, nvalid);
+    load_v2ext(Vs, v + (int64_t) n * v_sn + (int64_t) h * v_sh, v_st, pos_emb, r0, nvalid);
+    {   // S_prev (exclusive prefix, fp32) -> bf16; the z column gets the +1e-6 of the reference's denominator
+        const float* slot = ws + ((int64_t) nh * nchunks + chunk) * (kFp * kEx);
+        for (int idx = threadIdx.x; idx < kFp * (kEx / 2); idx += kThreads) {
+            const int f = idx / (kEx / 2), e = (idx % (kEx / 2)) * 2;
+            float2 s2 = *reinterpret_cast<const float2*>(slot + f * kEx + e);
+            if (e == kE && f < F) s2.x += 1e-6f;
+            *reinterpret_cast<uint32_t*>(Ss + f * kLdV + e) = pack_bf16(s2.x, s2.y);
+        }
+        for (int idx = threadIdx.x; idx < kFp; idx += kThreads) *reinterpret_cast<uint4*>(Ss + idx * kLdV + kEx) = make_uint4(0, 0, 0, 0);
+        for (int c = threadIdx.x; c < kDm; c += kThreads) vsum_prev[c] = slot[F * kEx + kDm + c];
+    }
+    __syncthreads();
+    const float norm = rsqrtf(sqrtf((float) kDm));
+    uint32_t aq[kFp / 16][4];     // phi(q) of this warp's rows as A fragments
+    {
+        float acc[kFp / 8][4];
+        phi_rows<kFp>(acc, Ks, Ps, warp, lane);
+#pragma unroll
+        for (int nt = 0; nt < kFp / 8; ++nt)
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int row = 16 * warp + g + 8 * half;
+                float o[2];
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int f = nt * 8 + 2 * tq + e;
+                    o[e] = (row < nvalid && f < F) ? fmaxf(acc[nt][2 * half + e] * norm, 0.f) + 1e-3f : 0.f;
+                }
+                *reinterpret_cast<uint32_t*>(PhiK + row * (kFp + 8) + nt * 8 + 2 * tq) = pack_bf16(o[0], o[1]);
+            }
+        phi_rows<kFp>(acc, Qs, Ps, warp, lane);
+#pragma unroll
+        for (int ks = 0; ks < kFp / 16; ++ks) {
+            float o[2][4];
+#pragma unroll
+            for (int t2 = 0; t2 < 2; ++t2)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int f = (2 * ks + t2) * 8 + 2 * tq + (i & 1);
+                    o[t2][i] = f < F ? fmaxf(acc[2 * ks + t2][i] * norm, 0.f) + 1e-3f : 0.f;
+                }
+            aq[ks][0] = pack_bf16(o[0][0], o[0][1]);
+            aq[ks][1] = pack_bf16(o[0][2], o[0][3]);
+            aq[ks][2] = pack_bf16(o[1][0], o[1][1]);
+            aq[ks][3] = pack_bf16(o[1][2], o[1][3]);
+        }
+    }
+    __syncthreads();
+    float O[kEx / 8][4];        // [16 x 144]
+    float A2[kDm / 8][4];       // running-sum GEMM: tril(1) . v   [16 x 64]
+#pragma unroll
+    for (int nt = 0; nt < kEx / 8; ++nt)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) O[nt][i] = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < kDm / 8; ++nt)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) A2[nt][i] = 0.f;
+    const int brow = (lane & 7) + 8 * (lane >> 4), bcol = 8 * ((lane >> 3) & 1);    // B from [n][k] storage (PhiK)
+    const int vr = (lane & 7) + 8 * ((lane >> 3) & 1), vc = 8 * (lane >> 4);        // B from [k][n] storage (Vs, Ss), trans
+    for (int jt = 0; jt <= warp; ++jt) {
+        // P tile [16 x 16] = phi(q) . phi(k_j)^T for source rows 16jt .. 16jt+15
+        float p[2][4];
+#pragma unroll
+        for (int t2 = 0; t2 < 2; ++t2)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) p[t2][i] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < kFp / 16; ++ks) {
+            uint32_t b[4];
+            ldsm_x4(b, smem_u32(PhiK + (jt * 16 + brow) * (kFp + 8) + ks * 16 + bcol));
+            mma16816(p[0], aq[ks], b[0], b[1]);
+            mma16816(p[1], aq[ks], b[2], b[3]);
+        }
+        uint32_t pa[4], la[4];
+        if (jt == warp) {       // diagonal tile: keep source j <= query i
+#pragma unroll
+            for (int t2 = 0; t2 < 2; ++t2)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int col = t2 * 8 + 2 * tq + (i & 1), row = g + 8 * (i >> 1);
+                    if (col > row) p[t2][i] = 0.f;
+                }
+            const uint32_t lo = (2 * tq <= g) ? 0x3F80u : 0u, hi = (2 * tq + 1 <= g) ? 0x3F800000u : 0u;
+            la[0] = lo | hi; la[1] = 0x3F803F80u; la[2] = 0u; la[3] = lo | hi;
+        } else {
+            la[0] = la[1] = la[2] = la[3] = 0x3F803F80u;
+        }
+        pa[0] = pack_bf16(p[0][0], p[0][1]); pa[1] = pack_bf16(p[0][2], p[0][3]);
+        pa[2] = pack_bf16(p[1][0], p[1][1]); pa[3] = pack_bf16(p[1][2], p[1][3]);
+#pragma unroll
+        for (int np = 0; np < kEx / 16; ++np) {
+            uint32_t b[4];
+            ldsm_x4_t(b, smem_u32(Vs + (jt * 16 + vr) * kLdV + np * 16 + vc));
+            mma16816(O[2 * np], pa, b[0], b[1]);
+            mma16816(O[2 * np + 1], pa, b[2], b[3]);
+            if (np >= 4 && np < 8) {        // columns 64..127 = v: running sum with the triangular ones tile
+                mma16816(A2[2 * (np - 4)], la, b[0], b[1]);
+                mma16816(A2[2 * (np - 4) + 1], la, b[2], b[3]);
+            }
+        }
+    }
+    // + phi(q) . S_prev
+#pragma unroll
+    for (int ks = 0; ks < kFp / 16; ++ks)
+#pragma unroll
+        for (int np = 0; np < kEx / 16; ++np) {
+            uint32_t b[4];
+            ldsm_x4_t(b, smem_u32(Ss + (ks * 16 + vr) * kLdV + np * 16 + vc));
+            mma16816(O[2 * np], aq[ks], b[0], b[1]);
+            mma16816(O[2 * np + 1], aq[ks], b[2], b[3]);
+        }
+    // denominators live in column 128 (n-tile 16, element 0 of the quad leader)
+    const float den_lo = __shfl_sync(kFull, O[kE / 8][0], lane & ~3);
+    const float den_hi = __shfl_sync(kFull, O[kE / 8][2], lane & ~3);
+    const float inv_lo = 1.0f / den_lo, inv_hi = 1.0f / den_hi;
+    const int row_lo = 16 * warp + g, row_hi = row_lo + 8;
+    __nv_bfloat16* cb = ctx + (((int64_t) n * H + h) * T + r0) * kE;
+#pragma unroll
+    for (int nt = 0; nt < kE / 8; ++nt) {
+        const int e0 = nt * 8 + 2 * tq;
+        if (row_lo < nvalid) *reinterpret_cast<uint32_t*>(cb + (int64_t) row_lo * kE + e0) = pack_bf16(O[nt][0] * inv_lo, O[nt][1] * inv_lo);
+        if (row_hi < nvalid) *reinterpret_cast<uint32_t*>(cb + (int64_t) row_hi * kE + e0) = pack_bf16(O[nt][2] * inv_hi, O[nt][3] * inv_hi);
+    }
+    if (cumavg != nullptr) {
+        __nv_bfloat16* ab = cumavg + (((int64_t) n * H + h) * T + r0) * kDm;
+        const float il = 1.0f / (float) (r0 + row_lo + 1), ih = 1.0f / (float) (r0 + row_hi + 1);
+#pragma unroll
+        for (int nt = 0; nt < kDm / 8; ++nt) {
+            const int c0 = nt * 8 + 2 * tq;
+            const float s0 = vsum_prev[c0], s1 = vsum_prev[c0 + 1];
+            if (row_lo < nvalid) *reinterpret_cast<uint32_t*>(ab + (int64_t) row_lo * kDm + c0) = pack_bf16((A2[nt][0] + s0) * il, (A2[nt][1] + s1) * il);
+            if (row_hi < nvalid) *reinterpret_cast<uint32_t*>(ab + (int64_t) row_hi * kDm + c0) = pack_bf16((A2[nt][2] + s0) * ih, (A2[nt][3] + s1) * ih);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+prefix_chunks_kernel(float* __restrict__ ws, int nchunks, int64_t stride) {
+    float* base = ws + (int64_t) blockIdx.y * nchunks * stride;
+    for (int64_t idx = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; idx < stride; idx += (int64_t) gridDim.x * blockDim.x) {
+        float run = 0.f;
+        for (int c = 0; c < nchunks; ++c) {
+            const float cur = base[c * stride + idx];
+            base[c * stride + idx] = run;
+            run += cur;
+        }
+    }
+}
+
+template <int kFp>
+int launch_performer_mma(const void* q, int64_t q_sn, int64_t q_sh, int64_t q_st, const void* k, int64_t k_sn, int64_t k_sh, int64_t k_st,
+                         const void* v, int64_t v_sn, int64_t v_sh, int64_t v_st, const float* pos_emb, const float* proj,
+                         void* ctx, void* cumavg, float* ws, int N, int H, int T, int F, cudaStream_t s) {
+    using SM = PerfSmem<kFp>;
+    const int nchunks = (T + kCh - 1) / kCh;
+    dim3 grid(nchunks, N * H);
+    auto ka = performer_sums_mma_kernel<kFp>;
+    auto kc = performer_out_mma_kernel<kFp>;
+    SEA_CUDA_TRY(cudaFuncSetAttribute(ka, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kBytes), "smem attr");
+    SEA_CUDA_TRY(cudaFuncSetAttribute(kc, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kBytes), "smem attr");
+    using B = __nv_bfloat16;
+    ka<<<grid, kThreads, SM::kBytes, s>>>((const B*) k, k_sn, k_sh, k_st, (const B*) v, v_sn, v_sh, v_st, pos_emb, proj, ws, H, T, F, nchunks);
+    SEA_CHECK_LAUNCH("performer_sums_mma_kernel");
+    const int64_t stride = (int64_t) kFp * kEx;
+    prefix_chunks_kernel<<<dim3((unsigned) ((stride + 255) / 256), N * H), 256, 0, s>>>(ws, nchunks, stride);
+    SEA_CHECK_LAUNCH("prefix_chunks_kernel");
+    kc<<<grid, kThreads, SM::kBytes, s>>>((const B*) q, q_sn, q_sh, q_st, (const B*) k, k_sn, k_sh, k_st, (const B*) v, v_sn, v_sh, v_st,
+                                          pos_emb, proj, ws, (B*) ctx, (B*) cumavg, H, T, F, nchunks);
+    SEA_CHECK_LAUNCH("performer_out_mma_kernel");
+    return SEA_OK;
+}
+
+}  // namespace
+}  // namespace sea
+
+using namespace sea;
+
+extern "C" {
+
+int sea_performer_mma_supported(int dtype, int D, int F) { return dtype == SEA_DTYPE_BF16 && D == 64 && F >= 1 && F <= 63; }
+
+int64_t sea_performer_mma_workspace_floats(int N, int H, int T, int D, int F) {
+    if (N <= 0 || H <= 0 || T <= 0 || F <= 0) return 0;
+    const int Fp = ((F + 1) + 15) & ~15;
+    return (int64_t) N * H * ((T + kCh - 1) / kCh) * Fp * kEx;
+}
+
+int sea_performer_causal_mma_fwd(const void* q, int64_t q_sn, int64_t q_sh, int64_t q_st,
+                                 const void* k, int64_t k_sn, int64_t k_sh, int64_t k_st,
+                                 const void* v, int64_t v_sn, int64_t v_sh, int64_t v_st,
+                                 const float* pos_emb, const float* proj, void* ctx, void* cumavg, float* workspace,
+                                 int N, int H, int T, int D, int F, void* stream) {
+    SEA_CHECK_ARG(q && k && v && pos_emb && proj && ctx && workspace, "sea_performer_causal_mma_fwd: null pointer");
+    if (!sea_performer_mma_supported(SEA_DTYPE_BF16, D, F)) {
+        set_error("sea_performer_causal_mma_fwd: unsupported shape D=%d F=%d (need D=64, F<=63)", D, F);
+        return SEA_ERR_UNSUPPORTED;
+    }
+    SEA_CHECK_ARG(N > 0 && H > 0 && T > 0 && (int64_t) N * H <= 65535, "sea_performer_causal_mma_fwd: bad shape");
+    SEA_CHECK_ARG(((q_sn | q_sh | q_st | k_sn | k_sh | k_st | v_sn | v_sh | v_st) % 8) == 0 &&
+                  ((((uintptr_t) q) | ((uintptr_t) k) | ((uintptr_t) v) | ((uintptr_t) pos_emb) | ((uintptr_t) ctx)) & 15) == 0,
+                  "sea_performer_causal_mma_fwd: q/k/v rows must be 16-byte aligned");
+    cudaStream_t s = (cudaStream_t) stream;
+    const int Fp = ((F + 1) + 15) & ~15;
+    switch (Fp) {
+        case 16: return launch_performer_mma<16>(q, q_sn, q_sh, q_st, k, k_sn, k_sh, k_st, v, v_sn, v_sh, v_st, pos_emb, proj, ctx, cumavg, workspace, N, H, T, F, s);
+        case 32: return launch_performer_mma<32>(q, q_sn, q_sh, q_st, k, k_sn, k_sh, k_st, v, v_sn, v_sh, v_st, pos_emb, proj, ctx, cumavg, workspace, N, H, T, F, s);
+        case 48: return launch_performer_mma<48>(q, q_sn, q_sh, q_st, k, k_sn, k_sh, k_st, v, v_sn, v_sh, v_st, pos_emb, proj, ctx, cumavg, workspace, N, H, T, F, s);
+        case 64: return launch_performer_mma<64>(q, q_sn, q_sh, q_st, k, k_sn, k_sh, k_st, v, v_sn, v_sh, v_st, pos_emb, proj, ctx, cumavg, workspace, N, H, T, F, s);
+    }
+    set_error("sea_performer_causal_mma_fwd: unsupported padded feature count %d", Fp);
+    return SEA_ERR_UNSUPPORTED;
+}
+
+}  // extern "C"

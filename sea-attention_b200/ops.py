@@ -231,7 +231,7 @@ def resize_from_m_to_t(x: torch.Tensor, masked_fill_value: float, attention_mask
 
 
 # --------------------------------------------------------------------------------------------- dense stages
-def performer_causal(q, k, v, pos_emb, proj, want_cumavg=True):
+def performer_causal(q, k, v, pos_emb, proj, want_cumavg=True, force_simt=False):
     """a2+a3 (+ running mean of v).  q,k,v [N,H,T,D]; pos_emb fp32 [>=T, D]; proj fp32 [F, D]
     -> ctx [N,H,T,2D], cumavg [N,H,T,D] (dtype of q)."""
     _cuda(q, k, v, pos_emb, proj)
@@ -244,7 +244,15 @@ def performer_causal(q, k, v, pos_emb, proj, want_cumavg=True):
     pj = proj.float().contiguous()
     ctx = torch.empty((N, H, T, 2 * D), dtype=q.dtype, device=q.device)
     avg = torch.empty((N, H, T, D), dtype=q.dtype, device=q.device) if want_cumavg else None
-    ws = torch.empty((_lib.load().sea_performer_workspace_floats(N, H, T, D, F),), dtype=torch.float32, device=q.device)
+    lib = _lib.load()
+    if not force_simt and lib.sea_performer_mma_supported(_DTYPES.get(q.dtype, -1), D, F) and all(
+            t.stride(i) % 8 == 0 for t in (q, k, v) for i in range(3)):
+        ws = torch.empty((lib.sea_performer_mma_workspace_floats(N, H, T, D, F),), dtype=torch.float32, device=q.device)
+        _lib.call('sea_performer_causal_mma_fwd', q.data_ptr(), q.stride(0), q.stride(1), q.stride(2),
+                  k.data_ptr(), k.stride(0), k.stride(1), k.stride(2), v.data_ptr(), v.stride(0), v.stride(1), v.stride(2),
+                  pos.data_ptr(), pj.data_ptr(), ctx.data_ptr(), _p(avg), ws.data_ptr(), N, H, T, D, F, _stream())
+        return ctx, avg
+    ws = torch.empty((lib.sea_performer_workspace_floats(N, H, T, D, F),), dtype=torch.float32, device=q.device)
     _lib.call('sea_performer_causal_fwd', q.data_ptr(), q.stride(0), q.stride(1), q.stride(2),
               k.data_ptr(), k.stride(0), k.stride(1), k.stride(2), v.data_ptr(), v.stride(0), v.stride(1), v.stride(2),
               pos.data_ptr(), pj.data_ptr(), _dtype_code(q), ctx.data_ptr(), _p(avg), ws.data_ptr(), N, H, T, D, F, _stream())

@@ -94,3 +94,27 @@ def test_mlp_umma_matches_simt(sea, N, H, T, P):
     # bf16 operands (weights and the GELU output are rounded to bf16 before each GEMM): 2e-2-class tolerance
     torch.testing.assert_close(a_sc.cpu(), b_sc.cpu(), rtol=3e-2, atol=3e-2)
     torch.testing.assert_close(a_in.float().cpu(), b_in.float().cpu(), rtol=5e-2, atol=5e-2)
+
+
+@pytest.mark.parametrize('N,H,T,nbf', [(1, 2, 128, 8), (2, 3, 200, 8), (1, 4, 515, 8), (1, 2, 96, 5), (1, 1, 300, 16), (1, 1, 40, 32)])
+def test_performer_mma_matches_oracle(sea, N, H, T, nbf):
+    import math
+    d = 64
+    F = int(d * math.log(d) / nbf)
+    g = torch.Generator().manual_seed(T + nbf)
+    q = (torch.randn(N, H, T, d, generator=g) * d ** -0.5).bfloat16()
+    k = torch.randn(N, H, T, d, generator=g).bfloat16()
+    v = torch.randn(N, H, T, d, generator=g).bfloat16()
+    pos = torch.randn(T + 3, d, generator=g)
+    proj = torch.randn(F, d, generator=g)
+    assert sea._lib.load().sea_performer_mma_supported(1, d, F)
+    ctx, avg = sea.ops.performer_causal(q.to(DEV), k.to(DEV), v.to(DEV), pos.to(DEV), proj.to(DEV))
+    torch.cuda.synchronize()
+    v2 = torch.cat([pos[:T].view(1, 1, T, d).expand(N, H, T, d), v.float()], -1)
+    ref = so.performer_causal(q.float(), k.float(), v2, proj)
+    torch.testing.assert_close(ctx.float().cpu(), ref, rtol=2e-2, atol=2e-2)
+    avg_ref = v.float().cumsum(-2) / torch.arange(1, T + 1).view(1, 1, T, 1)
+    torch.testing.assert_close(avg.float().cpu(), avg_ref, rtol=2e-2, atol=1e-2)
+    # cross-check against the fp32 SIMT kernel on the same bf16 inputs
+    ctx2, avg2 = sea.ops.performer_causal(q.to(DEV), k.to(DEV), v.to(DEV), pos.to(DEV), proj.to(DEV), force_simt=True)
+    torch.testing.assert_close(ctx.float().cpu(), ctx2.float().cpu(), rtol=2e-2, atol=2e-2)
