@@ -79,7 +79,9 @@ SEA_API int sea_mask_bits_to_float(const uint32_t* mask_bits, float* mask, int N
  */
 SEA_API int sea_csr_count(const uint32_t* mask_bits, void* crow, int idx64,
                   int N, int H, int T_DST, int P, int T_SRC, int k, int is_causal, void* stream);
-SEA_API int sea_csr_fill(const uint32_t* mask_bits, const void* crow, void* col, int idx64, int64_t Z,
+/* head_ptr (nullable, int32 [N, T_DST, H+1], needs P % 32 == 0): absolute entry offset (inside batch item n) at which
+ * head h starts in row t, head_ptr[..., H] = end of the row; an auxiliary index for sea_sparse_attention_fwd. */
+SEA_API int sea_csr_fill(const uint32_t* mask_bits, const void* crow, void* col, int idx64, int64_t Z, int32_t* head_ptr,
                  int N, int H, int T_DST, int P, int T_SRC, int k, int is_causal, void* stream);
 
 /* flat_csr_to_dense (ops/kernels/flat_csr_to_dense.py:3-36): out [N,H,T_DST,T_SRC] fp32, zero filled
@@ -222,13 +224,16 @@ SEA_API int sea_predictor_tail_topk_fwd(const float* y3, const float* bias, cons
  * probs_values (nullable, fp32 [N,Z]) receives the scaled probabilities (the reference's
  * partial_attention_probs.values()).  Requires head-major entries inside a row (what a8 emits).
  * cumavg nullable (then out = ctx, layout still [N,T_DST,H*D]).
+ * head_ptr (nullable): the index sea_csr_fill emits; with it and 16-bit activations (D in {32,64,128}) the call runs the
+ * warp-per-(row, head) kernel with batched 128-bit gathers, otherwise a CTA-per-row kernel that finds the head
+ * segments by binary search.
  */
 SEA_API int sea_sparse_attention_fwd(const void* crow, const void* col, int idx64, int64_t Z,
                              const void* q, int64_t q_sn, int64_t q_sh, int64_t q_st,
                              const void* k, int64_t k_sn, int64_t k_sh, int64_t k_st,
                              const void* v, int64_t v_sn, int64_t v_sh, int64_t v_st,
                              const float* scales, const void* cumavg, int use_scaler, int dtype,
-                             void* out, float* probs_values,
+                             void* out, float* probs_values, const int32_t* head_ptr,
                              int N, int H, int T_DST, int T_SRC, int D, void* stream);
 
 #ifdef __cplusplus

@@ -38,7 +38,7 @@ _SIGNATURES = {
     'sea_mask_float_to_bits': (_I, [_P, _L, _L, _L, _P, _I, _I, _I, _I, _P]),
     'sea_mask_bits_to_float': (_I, [_P, _P, _I, _I, _I, _I, _P]),
     'sea_csr_count': (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
-    'sea_csr_fill': (_I, [_P, _P, _P, _I, _L, _I, _I, _I, _I, _I, _I, _I, _P]),
+    'sea_csr_fill': (_I, [_P, _P, _P, _I, _L, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     'sea_flat_csr_to_dense': (_I, [_P, _P, _I, _P, _L, _P, _I, _I, _I, _I, _P]),
     'sea_flat_csr_masked_bmm': (_I, [_P, _P, _I, _L, _P, _L, _L, _L, _P, _L, _L, _L, _I, _P, _I, _I, _I, _I, _I, _P]),
     'sea_flat_csr_softmax': (_I, [_P, _P, _I, _L, _P, _P, _I, _I, _I, _I, _P]),
@@ -61,7 +61,7 @@ _SIGNATURES = {
     'sea_conv1x1_umma': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     'sea_predictor_tail_topk_fwd': (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     'sea_predictor_tail_fwd': (_I, [_P, _I, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
-    'sea_sparse_attention_fwd': (_I, [_P, _P, _I, _L, _P, _L, _L, _L, _P, _L, _L, _L, _P, _L, _L, _L, _P, _P, _I, _I, _P, _P,
+    'sea_sparse_attention_fwd': (_I, [_P, _P, _I, _L, _P, _L, _L, _L, _P, _L, _L, _L, _P, _L, _L, _L, _P, _P, _I, _I, _P, _P, _P,
                                       _I, _I, _I, _I, _I, _P]),
 }
 

@@ -291,10 +291,12 @@ class PerlinAttention(nn.Module):
             probs, _ = ops.predictor_tail(y, w['conv3_w'], w['conv3_b'], w['out_ln_w'], w['out_ln_b'], P)
             bits = ops.topk_mask_bits(probs, kpr, 'causal_batch')
         # a8 (int32 indices internally; no host sync: col is allocated at a shape-derived upper bound)
-        crow, col, Z = ops.csr_from_bits(bits, H, P, pc.k, T, is_causal=True, index_dtype=torch.int32, z_alloc=z_alloc)
+        crow, col, Z, head_ptr = ops.csr_from_bits(bits, H, P, pc.k, T, is_causal=True, index_dtype=torch.int32, z_alloc=z_alloc,
+                                                   want_head_ptr=True)
         # a9-a14
         context, pvals = ops.sparse_attention(crow, col, q_for_score, k_for_score, v, scales, cumavg,
-                                              use_scaler=pc.partial_attention_scaler, want_probs=self.output_attentions)
+                                              use_scaler=pc.partial_attention_scaler, want_probs=self.output_attentions,
+                                              head_ptr=head_ptr)
         partial_probs = partial_mask = None
         if self.output_attentions:
             size = (N, T, H * T)

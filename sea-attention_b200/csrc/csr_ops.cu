@@ -115,31 +115,36 @@ __device__ __forceinline__ int pixel_width(float s, int m, int k) {
 }
 
 constexpr int kCsrWarps = 8;
+constexpr int kCsrThreads = 256;
 
+__device__ __forceinline__ int word_width_sum(uint32_t word, int w, int P, float s, int k) {
+    int acc = 0;
+    for (uint32_t x = word; x; x &= x - 1) acc += pixel_width(s, ((w << 5) + __ffs(x) - 1) % P, k);
+    return acc;
+}
+
+// CTA per query row, thread per 32-pixel word: the early causal rows keep all H*P pixels alive, so a warp-per-row
+// mapping leaves one warp with thousands of serial pixels on the critical path.
 template <typename IdxT>
-__global__ void __launch_bounds__(kCsrWarps * 32)
+__global__ void __launch_bounds__(kCsrThreads)
 csr_count_kernel(const uint32_t* __restrict__ bits, IdxT* __restrict__ crow,
                  int N, int H, int T_DST, int P, int T_SRC, int k, int is_causal, int words_per_row) {
-    const int lane = threadIdx.x & 31;
-    const int64_t row = (int64_t) blockIdx.x * kCsrWarps + (threadIdx.x >> 5);
-    if (row >= (int64_t) N * T_DST) return;
+    __shared__ int wsum[kCsrThreads / 32];
+    const int64_t row = blockIdx.x;
     const int n = (int) (row / T_DST), t = (int) (row % T_DST);
     const int L = is_causal ? (T_SRC - T_DST + t + 1) : T_SRC;
     const float s = __fdiv_rn((float) L, (float) P);
     const uint32_t* rb = bits + row * words_per_row;
     int cnt = 0;
-    for (int w = lane; w < words_per_row; w += 32) {
-        uint32_t word = rb[w];
-        while (word) {
-            int b = __ffs(word) - 1;
-            word &= word - 1;
-            int m = ((w << 5) + b) % P;
-            cnt += pixel_width(s, m, k);
-        }
-    }
+    for (int w = threadIdx.x; w < words_per_row; w += kCsrThreads) cnt += word_width_sum(rb[w], w, P, s, k);
     cnt = warp_sum_i(cnt);
-    if (lane == 0) {
-        crow[(int64_t) n * (T_DST + 1) + t + 1] = (IdxT) cnt;
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int tot = 0;
+#pragma unroll
+        for (int i = 0; i < kCsrThreads / 32; ++i) tot += wsum[i];
+        crow[(int64_t) n * (T_DST + 1) + t + 1] = (IdxT) tot;
         if (t == 0) crow[(int64_t) n * (T_DST + 1)] = 0;
     }
 }
@@ -179,27 +184,40 @@ crow_scan_kernel(IdxT* __restrict__ crow, int T_DST) {
     }
 }
 
+// CTA per query row: block-wide exclusive scan of the per-word entry counts gives every thread the offset of its
+// word's first entry.  Optionally emits head_ptr[n, t, 0..H] (absolute entry offset where head h starts in the row),
+// which the fused attention kernel uses instead of binary searches (only when P % 32 == 0: a head starts on a word).
 template <typename IdxT>
-__global__ void __launch_bounds__(kCsrWarps * 32)
+__global__ void __launch_bounds__(kCsrThreads)
 csr_fill_kernel(const uint32_t* __restrict__ bits, const IdxT* __restrict__ crow, IdxT* __restrict__ col, int64_t Z,
-                int N, int H, int T_DST, int P, int T_SRC, int k, int is_causal, int words_per_row) {
-    const int lane = threadIdx.x & 31;
-    const int64_t row = (int64_t) blockIdx.x * kCsrWarps + (threadIdx.x >> 5);
-    if (row >= (int64_t) N * T_DST) return;
+                int32_t* __restrict__ head_ptr, int N, int H, int T_DST, int P, int T_SRC, int k, int is_causal, int words_per_row) {
+    __shared__ int wsum[kCsrThreads / 32];
+    __shared__ int carry_s;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int64_t row = blockIdx.x;
     const int n = (int) (row / T_DST), t = (int) (row % T_DST);
     const int L = is_causal ? (T_SRC - T_DST + t + 1) : T_SRC;
     const float s = __fdiv_rn((float) L, (float) P);
     const uint32_t* rb = bits + row * words_per_row;
     IdxT* out = col + (int64_t) n * Z;
-    int64_t pos = (int64_t) crow[(int64_t) n * (T_DST + 1) + t];
-    for (int w0 = 0; w0 < words_per_row; w0 += 32) {
-        const int w = w0 + lane;
-        uint32_t word = w < words_per_row ? rb[w] : 0u;
-        int mine = 0;
-        for (uint32_t x = word; x; x &= x - 1) mine += pixel_width(s, ((w << 5) + __ffs(x) - 1) % P, k);
-        int incl = warp_scan_incl_i(mine, lane);
-        int64_t p = pos + incl - mine;
-        pos += __shfl_sync(kFull, incl, 31);
+    const int64_t row_start = (int64_t) crow[(int64_t) n * (T_DST + 1) + t];
+    const int words_per_head = P >> 5;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (int w0 = 0; w0 < words_per_row; w0 += kCsrThreads) {
+        const int w = w0 + threadIdx.x;
+        const uint32_t word = w < words_per_row ? rb[w] : 0u;
+        const int mine = word_width_sum(word, w, P, s, k);
+        const int incl = warp_scan_incl_i(mine, lane);
+        if (lane == 31) wsum[wid] = incl;
+        __syncthreads();
+        int wprefix = 0, tot = 0;
+#pragma unroll
+        for (int i = 0; i < kCsrThreads / 32; ++i) { const int sw = wsum[i]; if (i < wid) wprefix += sw; tot += sw; }
+        const int carry = carry_s;
+        int64_t p = row_start + carry + wprefix + incl - mine;
+        if (head_ptr != nullptr && w < words_per_row && (w % words_per_head) == 0)
+            head_ptr[row * (H + 1) + w / words_per_head] = (int32_t) p;
         for (uint32_t x = word; x; x &= x - 1) {
             const int i = (w << 5) + __ffs(x) - 1;
             const int h = i / P, m = i % P;
@@ -220,11 +238,15 @@ csr_fill_kernel(const uint32_t* __restrict__ bits, const IdxT* __restrict__ crow
             }
             p += wd;
         }
+        __syncthreads();
+        if (threadIdx.x == 0) carry_s = carry + tot;
+        __syncthreads();
     }
-    // zero the tail [crow[n, T_DST], Z) (the reference allocates col with torch.zeros, :669); every warp of the batch
-    // item takes a strided slice so that an over-allocated col costs one coalesced pass, not one warp's serial loop
+    if (head_ptr != nullptr && threadIdx.x == 0) head_ptr[row * (H + 1) + H] = (int32_t) (row_start + carry_s);
+    // zero the tail [crow[n, T_DST], Z) (the reference allocates col with torch.zeros, :669); every CTA of the batch
+    // item takes a strided slice so that an over-allocated col costs one coalesced pass
     const int64_t tail_begin = (int64_t) crow[(int64_t) n * (T_DST + 1) + T_DST];
-    for (int64_t z = tail_begin + (int64_t) t * 32 + lane; z < Z; z += (int64_t) T_DST * 32) out[z] = 0;
+    for (int64_t z = tail_begin + (int64_t) t * kCsrThreads + threadIdx.x; z < Z; z += (int64_t) T_DST * kCsrThreads) out[z] = 0;
 }
 
 template <typename IdxT>
@@ -521,7 +543,7 @@ int sea_csr_count(const uint32_t* mask_bits, void* crow, int idx64, int N, int H
     const int64_t rows = (int64_t) N * T_DST;
     cudaStream_t s = (cudaStream_t) stream;
     SEA_DISPATCH_IDX(idx64, I, {
-        csr_count_kernel<I><<<cdiv(rows, kCsrWarps), kCsrWarps * 32, 0, s>>>(mask_bits, (I*) crow, N, H, T_DST, P, T_SRC, k, is_causal, wpr);
+        csr_count_kernel<I><<<(unsigned) rows, kCsrThreads, 0, s>>>(mask_bits, (I*) crow, N, H, T_DST, P, T_SRC, k, is_causal, wpr);
         SEA_CHECK_LAUNCH("csr_count_kernel");
         crow_scan_kernel<I><<<N, 1024, 0, s>>>((I*) crow, T_DST);
         SEA_CHECK_LAUNCH("crow_scan_kernel");
@@ -529,15 +551,16 @@ int sea_csr_count(const uint32_t* mask_bits, void* crow, int idx64, int N, int H
     return SEA_OK;
 }
 
-int sea_csr_fill(const uint32_t* mask_bits, const void* crow, void* col, int idx64, int64_t Z, int N, int H, int T_DST,
+int sea_csr_fill(const uint32_t* mask_bits, const void* crow, void* col, int idx64, int64_t Z, int32_t* head_ptr, int N, int H, int T_DST,
                  int P, int T_SRC, int k, int is_causal, void* stream) {
     SEA_CHECK_ARG(mask_bits && crow && (col || Z == 0), "sea_csr_fill: null pointer");
     SEA_CHECK_ARG(N > 0 && H > 0 && T_DST > 0 && P > 0 && T_SRC >= T_DST && k > 0 && Z >= 0, "sea_csr_fill: bad shape");
+    SEA_CHECK_ARG(head_ptr == nullptr || (P % 32) == 0, "sea_csr_fill: head_ptr needs P %% 32 == 0");
     const int wpr = (H * P + 31) >> 5;
     const int64_t rows = (int64_t) N * T_DST;
     SEA_DISPATCH_IDX(idx64, I, {
-        csr_fill_kernel<I><<<cdiv(rows, kCsrWarps), kCsrWarps * 32, 0, (cudaStream_t) stream>>>(
-            mask_bits, (const I*) crow, (I*) col, Z, N, H, T_DST, P, T_SRC, k, is_causal, wpr);
+        csr_fill_kernel<I><<<(unsigned) rows, kCsrThreads, 0, (cudaStream_t) stream>>>(
+            mask_bits, (const I*) crow, (I*) col, Z, head_ptr, N, H, T_DST, P, T_SRC, k, is_causal, wpr);
         SEA_CHECK_LAUNCH("csr_fill_kernel");
     });
     return SEA_OK;

@@ -206,6 +206,162 @@ sparse_attention_kernel(const IdxT* __restrict__ crow, const IdxT* __restrict__ 
     (void) tq;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// v2 (16-bit activations, D in {32, 64, 128}, head_ptr available): warp per (row, head) segment, no shared memory.
+// A K / V row (D x 2 bytes) is covered by LPR = D/8 lanes with ONE 16-byte load each, so a warp-wide load instruction
+// fetches EPI = 32/LPR whole rows; the 32/EPI loads of a 32-entry chunk -- for K and for V -- are all issued before any
+// is consumed (16 independent 128-bit loads in flight per lane), which is what hides the L2 gather latency.
+// Scores are reduced across the LPR lanes with shuffles; every lane of a group then already holds the probability of
+// the entries whose V slices it accumulates, so P.V needs no further communication until the final cross-group sum.
+// ------------------------------------------------------------------------------------------------
+template <typename T16>
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+    unpack2<T16>(u.x, f[0], f[1]);
+    unpack2<T16>(u.y, f[2], f[3]);
+    unpack2<T16>(u.z, f[4], f[5]);
+    unpack2<T16>(u.w, f[6], f[7]);
+}
+template <typename T16>
+__device__ __forceinline__ uint32_t pack2(float a, float b);
+template <>
+__device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float a, float b) {
+    __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&p);
+}
+template <>
+__device__ __forceinline__ uint32_t pack2<__half>(float a, float b) {
+    __half2 p = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&p);
+}
+
+template <typename T16, typename IdxT, int D>
+__global__ void __launch_bounds__(kAttnWarps * 32)
+sparse_attention_v2_kernel(const IdxT* __restrict__ col, int64_t Z, const int32_t* __restrict__ head_ptr,
+                           const T16* __restrict__ q, int64_t q_sn, int64_t q_sh, int64_t q_st,
+                           const T16* __restrict__ k, int64_t k_sn, int64_t k_sh, int64_t k_st,
+                           const T16* __restrict__ v, int64_t v_sn, int64_t v_sh, int64_t v_st,
+                           const float* __restrict__ scales, const T16* __restrict__ cumavg, int use_scaler,
+                           T16* __restrict__ out, float* __restrict__ probs_values,
+                           int N, int H, int T_DST, int T_SRC) {
+    constexpr int LPR = D / 8;          // lanes per K/V row
+    constexpr int EPI = 32 / LPR;       // entries per warp-wide load
+    constexpr int NI = 32 / EPI;        // loads per 32-entry chunk (= LPR)
+    const int lane = threadIdx.x & 31;
+    const int64_t task = (int64_t) blockIdx.x * kAttnWarps + (threadIdx.x >> 5);      // (n, t, h)
+    if (task >= (int64_t) N * T_DST * H) return;
+    const int h = (int) (task % H);
+    const int64_t row = task / H;
+    const int n = (int) (row / T_DST), t = (int) (row % T_DST);
+    const int sub = lane % LPR;         // which 8-channel slice of the row this lane owns
+    const int grp = lane / LPR;         // which entry of a load instruction this lane serves
+    const int32_t* hp = head_ptr + row * (H + 1) + h;
+    const int64_t s0 = hp[0], s1 = hp[1];
+    const IdxT* colr = col + (int64_t) n * Z;
+    const T16* kb = k + (int64_t) n * k_sn + (int64_t) h * k_sh + sub * 8;
+    const T16* vb = v + (int64_t) n * v_sn + (int64_t) h * v_sh + sub * 8;
+    float qf[8];
+    {
+        const uint4 qu = __ldg(reinterpret_cast<const uint4*>(q + (int64_t) n * q_sn + (int64_t) h * q_sh + (int64_t) t * q_st + sub * 8));
+        unpack8<T16>(qu, qf);
+    }
+    constexpr float kLog2e = 1.4426950408889634f;
+    float m_run = -INFINITY, l_run = 0.f;
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    const int64_t hbase = (int64_t) h * T_SRC;
+    for (int64_t base = s0; base < s1; base += 32) {
+        const int cnt = (int) min((int64_t) 32, s1 - base);
+        int jmine = 0;
+        if (lane < cnt) jmine = (int) ((int64_t) colr[base + lane] - hbase);
+        uint4 ku[NI], vu[NI];
+#pragma unroll
+        for (int i = 0; i < NI; ++i) {
+            const int e = i * EPI + grp;
+            const int j = __shfl_sync(kFull, jmine, e);
+            ku[i] = make_uint4(0, 0, 0, 0);
+            vu[i] = make_uint4(0, 0, 0, 0);
+            if (e < cnt) {
+                ku[i] = __ldg(reinterpret_cast<const uint4*>(kb + (int64_t) j * k_st));
+                vu[i] = __ldg(reinterpret_cast<const uint4*>(vb + (int64_t) j * v_st));
+            }
+        }
+        float sc[NI];
+        float cmax = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < NI; ++i) {
+            float kf[8];
+            unpack8<T16>(ku[i], kf);
+            float d = 0.f;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) d = fmaf(qf[c], kf[c], d);
+#pragma unroll
+            for (int o = LPR / 2; o > 0; o >>= 1) d += __shfl_xor_sync(kFull, d, o);
+            const bool valid = i * EPI + grp < cnt;
+            sc[i] = valid ? d : -INFINITY;
+            cmax = fmaxf(cmax, sc[i]);
+        }
+#pragma unroll
+        for (int o = LPR; o < 32; o <<= 1) cmax = fmaxf(cmax, __shfl_xor_sync(kFull, cmax, o));
+        if (probs_values != nullptr && sub == 0) {
+#pragma unroll
+            for (int i = 0; i < NI; ++i)
+                if (i * EPI + grp < cnt) probs_values[(int64_t) n * Z + base + i * EPI + grp] = sc[i];
+        }
+        const float m_new = fmaxf(m_run, cmax);
+        const float alpha = exp2f((m_run - m_new) * kLog2e);
+        float psum = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] *= alpha;
+#pragma unroll
+        for (int i = 0; i < NI; ++i) {
+            const float p = exp2f((sc[i] - m_new) * kLog2e);      // -inf -> 0 for the padding entries
+            psum += p;
+            float vf[8];
+            unpack8<T16>(vu[i], vf);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) acc[c] = fmaf(p, vf[c], acc[c]);
+        }
+        // every lane of a group holds the same p's: sum over groups only
+#pragma unroll
+        for (int o = LPR; o < 32; o <<= 1) psum += __shfl_xor_sync(kFull, psum, o);
+        l_run = l_run * alpha + psum;
+        m_run = m_new;
+    }
+#pragma unroll
+    for (int o = LPR; o < 32; o <<= 1) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[c] += __shfl_xor_sync(kFull, acc[c], o);
+    }
+    const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
+    const float* sp = scales + ((((int64_t) n * H + h) * T_DST + t) << 1);
+    const float psc = use_scaler ? sigmoidf_(sp[0]) : 1.0f;
+    if (grp == 0) {
+        const float a = sigmoidf_(sp[1]);
+        float o8[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) o8[c] = acc[c] * inv * psc;
+        if (cumavg != nullptr) {
+            const uint4 au = __ldg(reinterpret_cast<const uint4*>(cumavg + (((int64_t) n * H + h) * T_DST + t) * D + sub * 8));
+            float af[8];
+            unpack8<T16>(au, af);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) o8[c] = o8[c] * a + (1.0f - a) * af[c];
+        }
+        uint4 ou;
+        ou.x = pack2<T16>(o8[0], o8[1]); ou.y = pack2<T16>(o8[2], o8[3]);
+        ou.z = pack2<T16>(o8[4], o8[5]); ou.w = pack2<T16>(o8[6], o8[7]);
+        *reinterpret_cast<uint4*>(out + ((int64_t) n * T_DST + t) * ((int64_t) H * D) + (int64_t) h * D + sub * 8) = ou;
+    }
+    if (probs_values != nullptr) {
+        for (int64_t z = s0 + lane; z < s1; z += 32) {
+            float* pv = probs_values + (int64_t) n * Z + z;
+            *pv = exp2f((*pv - m_run) * kLog2e) * inv * psc;
+        }
+    }
+}
+
 }  // namespace sea
 
 using namespace sea;
@@ -217,13 +373,36 @@ int sea_sparse_attention_fwd(const void* crow, const void* col, int idx64, int64
                              const void* k, int64_t k_sn, int64_t k_sh, int64_t k_st,
                              const void* v, int64_t v_sn, int64_t v_sh, int64_t v_st,
                              const float* scales, const void* cumavg, int use_scaler, int dtype, void* out,
-                             float* probs_values, int N, int H, int T_DST, int T_SRC, int D, void* stream) {
+                             float* probs_values, const int32_t* head_ptr, int N, int H, int T_DST, int T_SRC, int D, void* stream) {
     SEA_CHECK_ARG(crow && (col || Z == 0) && q && k && v && scales && out, "sea_sparse_attention_fwd: null pointer");
     SEA_CHECK_ARG(N > 0 && H > 0 && T_DST > 0 && T_SRC >= T_DST && D > 0, "sea_sparse_attention_fwd: bad shape");
     SEA_CHECK_ARG(D % 8 == 0 && D <= 64 * kMaxPairs, "sea_sparse_attention_fwd: head dim %d unsupported (multiple of 8, <= %d)", D, 64 * kMaxPairs);
     SEA_CHECK_ARG((k_st % 8) == 0 && (k_sh % 8) == 0 && (k_sn % 8) == 0 && (v_st % 2) == 0 && (v_sh % 2) == 0 && (v_sn % 2) == 0,
                   "sea_sparse_attention_fwd: k/v strides must keep rows 16-byte aligned");
     SEA_CHECK_ARG((((uintptr_t) k) & 15) == 0 && (((uintptr_t) v) & 15) == 0 && (((uintptr_t) out) & 15) == 0, "sea_sparse_attention_fwd: k/v/out must be 16-byte aligned");
+    if (head_ptr != nullptr && dtype != SEA_DTYPE_F32 && (D == 32 || D == 64 || D == 128) &&
+        (q_st % 8) == 0 && (q_sh % 8) == 0 && (q_sn % 8) == 0 && (((uintptr_t) q) & 15) == 0 &&
+        (cumavg == nullptr || (((uintptr_t) cumavg) & 15) == 0)) {
+        const int64_t tasks = (int64_t) N * T_DST * H;
+        const unsigned grid = (unsigned) ((tasks + kAttnWarps - 1) / kAttnWarps);
+        cudaStream_t s = (cudaStream_t) stream;
+#define SEA_ATTN_V2(TT, II, DD)                                                                                              \
+        sparse_attention_v2_kernel<TT, II, DD><<<grid, kAttnWarps * 32, 0, s>>>(                                             \
+            (const II*) col, Z, head_ptr, (const TT*) q, q_sn, q_sh, q_st, (const TT*) k, k_sn, k_sh, k_st, (const TT*) v, v_sn, \
+            v_sh, v_st, scales, (const TT*) cumavg, use_scaler, (TT*) out, probs_values, N, H, T_DST, T_SRC)
+#define SEA_ATTN_V2_D(TT, II)                                                  \
+        do {                                                                   \
+            if (D == 32) SEA_ATTN_V2(TT, II, 32);                              \
+            else if (D == 64) SEA_ATTN_V2(TT, II, 64);                         \
+            else SEA_ATTN_V2(TT, II, 128);                                     \
+        } while (0)
+        if (dtype == SEA_DTYPE_BF16) { if (idx64) SEA_ATTN_V2_D(__nv_bfloat16, int64_t); else SEA_ATTN_V2_D(__nv_bfloat16, int32_t); }
+        else { if (idx64) SEA_ATTN_V2_D(__half, int64_t); else SEA_ATTN_V2_D(__half, int32_t); }
+#undef SEA_ATTN_V2_D
+#undef SEA_ATTN_V2
+        SEA_CHECK_LAUNCH("sparse_attention_v2_kernel");
+        return SEA_OK;
+    }
     const size_t smem = (size_t) H * D * sizeof(float) + (size_t) (H + 1) * sizeof(int64_t) + 16;
     SEA_CHECK_ARG(smem <= 227 * 1024, "sea_sparse_attention_fwd: H*D too large");
     SEA_DISPATCH_DTYPE(dtype, T_, SEA_DISPATCH_IDX(idx64, I, {

@@ -86,7 +86,7 @@ def topk_mask_bits(probs: torch.Tensor, k_per_group: torch.Tensor, group_mode: s
 
 # --------------------------------------------------------------------------------------------- a8
 def csr_from_bits(bits: torch.Tensor, H: int, P: int, k: int, T_SRC: int, is_causal: bool = True,
-                  index_dtype=torch.int64, z_alloc: Optional[int] = None):
+                  index_dtype=torch.int64, z_alloc: Optional[int] = None, want_head_ptr: bool = False):
     """bit mask -> (crow, col, Z).  z_alloc=None reads the exact nnz back (one host sync, like the
     reference's `.item()` at causal_resize_m_to_t.py:667); an int skips the sync and over-allocates."""
     N, T_DST, _ = bits.shape
@@ -95,8 +95,11 @@ def csr_from_bits(bits: torch.Tensor, H: int, P: int, k: int, T_SRC: int, is_cau
     _lib.call('sea_csr_count', bits.data_ptr(), crow.data_ptr(), idx64, N, H, T_DST, P, T_SRC, int(k), int(is_causal), _stream())
     Z = int(crow[:, -1].max().item()) if z_alloc is None else int(z_alloc)
     col = torch.empty((N, Z), dtype=index_dtype, device=bits.device)
-    _lib.call('sea_csr_fill', bits.data_ptr(), crow.data_ptr(), col.data_ptr(), idx64, Z, N, H, T_DST, P, T_SRC, int(k),
+    hp = torch.empty((N, T_DST, H + 1), dtype=torch.int32, device=bits.device) if (want_head_ptr and P % 32 == 0) else None
+    _lib.call('sea_csr_fill', bits.data_ptr(), crow.data_ptr(), col.data_ptr(), idx64, Z, _p(hp), N, H, T_DST, P, T_SRC, int(k),
               int(is_causal), _stream())
+    if want_head_ptr:
+        return crow, col, Z, hp
     return crow, col, Z
 
 
@@ -349,7 +352,7 @@ def predictor_tail(x, weight, bias, ln_w, ln_b, P: int, want_scores=False):
     return probs, scores
 
 
-def sparse_attention(crow, col, q, k, v, scales, cumavg, use_scaler=True, want_probs=False):
+def sparse_attention(crow, col, q, k, v, scales, cumavg, use_scaler=True, want_probs=False, head_ptr=None):
     """a9-a14 fused -> context [N,T_DST,H*D] (dtype of q) and, when asked, the probabilities [N,Z] fp32."""
     _cuda(crow, col, q, k, v, scales, cumavg)
     N, H, T_DST, D = q.shape
@@ -363,5 +366,5 @@ def sparse_attention(crow, col, q, k, v, scales, cumavg, use_scaler=True, want_p
     _lib.call('sea_sparse_attention_fwd', crow.data_ptr(), col.data_ptr(), _idx64(crow, col), Z,
               q.data_ptr(), q.stride(0), q.stride(1), q.stride(2), k.data_ptr(), k.stride(0), k.stride(1), k.stride(2),
               v.data_ptr(), v.stride(0), v.stride(1), v.stride(2), sc.data_ptr(), _p(ca), int(bool(use_scaler)), _dtype_code(q),
-              out.data_ptr(), _p(pv), N, H, T_DST, T_SRC, D, _stream())
+              out.data_ptr(), _p(pv), _p(head_ptr), N, H, T_DST, T_SRC, D, _stream())
     return out, pv

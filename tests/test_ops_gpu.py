@@ -207,3 +207,40 @@ def test_fused_sparse_attention_matches_unfused_ops(sea):
                                            scales.to(DEV), avg.to(DEV), use_scaler=True, want_probs=True)
         torch.testing.assert_close(out.cpu(), ref, rtol=1e-3, atol=2e-5)
         torch.testing.assert_close(pv.cpu(), p_ref, rtol=1e-3, atol=1e-6)
+
+
+@pytest.mark.parametrize('d,idt', [(64, torch.int32), (128, torch.int32), (32, torch.int64), (64, torch.int64)])
+def test_fused_sparse_attention_v2_bf16_with_head_ptr(sea, d, idt):
+    """16-bit warp-per-(row, head) kernel driven by the head_ptr index that sea_csr_fill emits."""
+    N, H, T, P, k = 2, 4, 160, 32, 8
+    g = torch.Generator().manual_seed(d)
+    probs, mask = _rand_mask(N, H, T, P, k, seed=d + 1)
+    mask[1, 2] = 0                  # a head with no entries at all in item 1
+    bits = sea.ops.mask_to_bits(mask.to(DEV))
+    crow, col, Z, hp = sea.ops.csr_from_bits(bits, H, P, k, T, True, idt, want_head_ptr=True)
+    crow_r, col_r, Z_r = so.resize_from_m_to_t_csr(mask, k, T, True)
+    assert torch.equal(col.cpu().long(), col_r)
+    # head_ptr is the lower bound of h*T inside each row
+    hp_c, crow_c = hp.cpu().long(), crow.cpu().long()
+    assert torch.equal(hp_c[:, :, 0], crow_c[:, :-1]) and torch.equal(hp_c[:, :, H], crow_c[:, 1:])
+    for n in range(N):
+        for t in (0, 7, T - 1):
+            row = col_r[n, crow_r[n, t]:crow_r[n, t + 1]]
+            for h in range(H + 1):
+                assert int(hp_c[n, t, h]) == int(crow_r[n, t]) + int((row < h * T).sum())
+    q = (torch.randn(N, H, T, d, generator=g) * d ** -0.5).bfloat16()
+    kk = torch.randn(N, H, T, d, generator=g).bfloat16()
+    v = torch.randn(N, H, T, d, generator=g).bfloat16()
+    scales = torch.randn(N, H, T, 2, generator=g)
+    avg = (v.float().cumsum(-2) / torch.arange(1, T + 1).view(1, 1, T, 1)).bfloat16()
+    s_ref = so.flat_csr_masked_bmm(q.float(), kk.float(), crow_r, col_r)
+    p_ref = so.flat_csr_elmul_rowscale(so.flat_csr_softmax(s_ref, crow_r, col_r, H, T), crow_r, col_r, torch.sigmoid(scales[..., 0]), T)
+    ctx = so.flat_csr_sdbmm(p_ref, crow_r, col_r, v.float(), H)
+    a = torch.sigmoid(scales[..., 1:2])
+    ref = (ctx * a + (1 - a) * avg.float()).permute(0, 2, 1, 3).reshape(N, T, H * d)
+    out, pv = sea.ops.sparse_attention(crow, col, q.to(DEV), kk.to(DEV), v.to(DEV), scales.to(DEV), avg.to(DEV), True, True, head_ptr=hp)
+    torch.testing.assert_close(out.float().cpu(), ref, rtol=2e-2, atol=1e-2)
+    torch.testing.assert_close(pv.cpu(), p_ref, rtol=1e-3, atol=1e-6)
+    # the binary-search kernel (no head_ptr) must agree
+    out2, pv2 = sea.ops.sparse_attention(crow, col, q.to(DEV), kk.to(DEV), v.to(DEV), scales.to(DEV), avg.to(DEV), True, True)
+    torch.testing.assert_close(out.float().cpu(), out2.float().cpu(), rtol=2e-2, atol=1e-2)
