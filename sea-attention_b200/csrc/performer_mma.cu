@@ -66,27 +66,51 @@ __device__ __forceinline__ void load_proj(__nv_bfloat16* Ps, const float* __rest
 __device__ __forceinline__ void load_rows_bf16(__nv_bfloat16* dst, int ld, const __nv_bfloat16* __restrict__ src, int64_t row_stride,
                                                int r0, int nvalid) {
     // 128 rows x 64 bf16, 16-byte vectors; rows beyond nvalid are zero
-    for (int idx = threadIdx.x; idx < kCh * (kDm / 8); idx += kThreads) {
-        const int r = idx >> 3, c8 = idx & 7;
-        uint4 val = make_uint4(0, 0, 0, 0);
-        if (r < nvalid) val = __ldg(reinterpret_cast<const uint4*>(src + (int64_t) (r0 + r) * row_stride) + c8);
-        *reinterpret_cast<uint4*>(dst + r * ld + c8 * 8) = val;
+    constexpr int kIt = kCh * (kDm / 8) / kThreads;     // 4: all loads of a thread are issued before the first store
+    uint4 val[kIt];
+#pragma unroll
+    for (int it = 0; it < kIt; ++it) {
+        const int idx = threadIdx.x + it * kThreads, r = idx >> 3, c8 = idx & 7;
+        val[it] = make_uint4(0, 0, 0, 0);
+        if (r < nvalid) val[it] = __ldg(reinterpret_cast<const uint4*>(src + (int64_t) (r0 + r) * row_stride) + c8);
+    }
+#pragma unroll
+    for (int it = 0; it < kIt; ++it) {
+        const int idx = threadIdx.x + it * kThreads, r = idx >> 3, c8 = idx & 7;
+        *reinterpret_cast<uint4*>(dst + r * ld + c8 * 8) = val[it];
     }
 }
 __device__ __forceinline__ void load_v2ext(__nv_bfloat16* Vs, const __nv_bfloat16* __restrict__ v, int64_t v_st, const float* __restrict__ pos,
                                            int r0, int nvalid) {
-    for (int idx = threadIdx.x; idx < kCh * (kDm / 8); idx += kThreads) {     // v -> cols 64..127
-        const int r = idx >> 3, c8 = idx & 7;
-        uint4 val = make_uint4(0, 0, 0, 0);
-        if (r < nvalid) val = __ldg(reinterpret_cast<const uint4*>(v + (int64_t) (r0 + r) * v_st) + c8);
-        *reinterpret_cast<uint4*>(Vs + r * kLdV + kDm + c8 * 8) = val;
+    {   // v -> cols 64..127
+        constexpr int kIt = kCh * (kDm / 8) / kThreads;
+        uint4 val[kIt];
+#pragma unroll
+        for (int it = 0; it < kIt; ++it) {
+            const int idx = threadIdx.x + it * kThreads, r = idx >> 3, c8 = idx & 7;
+            val[it] = make_uint4(0, 0, 0, 0);
+            if (r < nvalid) val[it] = __ldg(reinterpret_cast<const uint4*>(v + (int64_t) (r0 + r) * v_st) + c8);
+        }
+#pragma unroll
+        for (int it = 0; it < kIt; ++it) {
+            const int idx = threadIdx.x + it * kThreads, r = idx >> 3, c8 = idx & 7;
+            *reinterpret_cast<uint4*>(Vs + r * kLdV + kDm + c8 * 8) = val[it];
+        }
     }
-    for (int idx = threadIdx.x; idx < kCh * (kDm / 4); idx += kThreads) {     // pos_emb (fp32) -> cols 0..63
-        const int r = idx >> 4, c4 = idx & 15;
-        float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (r < nvalid) p = __ldg(reinterpret_cast<const float4*>(pos + (int64_t) (r0 + r) * kDm) + c4);
-        uint2 pk = make_uint2(pack_bf16(p.x, p.y), pack_bf16(p.z, p.w));
-        *reinterpret_cast<uint2*>(Vs + r * kLdV + c4 * 4) = pk;
+    {   // pos_emb (fp32) -> cols 0..63
+        constexpr int kIt = kCh * (kDm / 4) / kThreads;
+        float4 p[kIt];
+#pragma unroll
+        for (int it = 0; it < kIt; ++it) {
+            const int idx = threadIdx.x + it * kThreads, r = idx >> 4, c4 = idx & 15;
+            p[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r < nvalid) p[it] = __ldg(reinterpret_cast<const float4*>(pos + (int64_t) (r0 + r) * kDm) + c4);
+        }
+#pragma unroll
+        for (int it = 0; it < kIt; ++it) {
+            const int idx = threadIdx.x + it * kThreads, r = idx >> 4, c4 = idx & 15;
+            *reinterpret_cast<uint2*>(Vs + r * kLdV + c4 * 4) = make_uint2(pack_bf16(p[it].x, p[it].y), pack_bf16(p[it].z, p[it].w));
+        }
     }
     for (int idx = threadIdx.x; idx < kCh * 3; idx += kThreads) {             // cols 128..151: ones column then zeros
         const int r = idx / 3, part = idx % 3;
