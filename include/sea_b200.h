@@ -215,7 +215,12 @@ SEA_API int sea_predictor_tail_fwd(const void* x, int dtype, const float* weight
  * top-k bit mask [N,T,H*P/32] (nullable; k_per_row [N*T] as in sea_topk_mask_bits).  P in {32,...,1024}, W | P. */
 SEA_API int sea_predictor_tail_topk_fwd(const float* y3, const float* bias, const float* ln_w, const float* ln_b,
                                         const float* k_per_row, float* probs, uint32_t* mask_bits,
+                                        int32_t* crow_counts, int k_clamp,
                                         int N, int H, int T, int W, int P, void* stream);
+/* crow_counts (nullable, int32 [N, T+1]): when given, the kernel also performs pass 1 of a8 for the causal prefill
+ * (T_DST = T_SRC = T): crow_counts[n, t+1] = entries of row t, crow_counts[n, 0] = 0; sea_crow_scan() then turns the
+ * counts into row offsets in place (the second half of sea_csr_count). */
+SEA_API int sea_crow_scan(void* crow, int idx64, int N, int T_DST, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * a9-a14 fused sparse attention of the benchmarking branch (attention.py:1151-1173, 1237-1244,

@@ -6,6 +6,7 @@
 // where rows are contiguous.  No tensor cores on purpose.
 #include "common.cuh"
 #include "topk.cuh"
+#include "csr_common.cuh"
 
 #include <stdarg.h>
 
@@ -100,28 +101,8 @@ __global__ void mask_bits_to_float_kernel(const uint32_t* __restrict__ bits, flo
     mask[idx] = (float) ((word >> (i & 31)) & 1u);
 }
 
-// ------------------------------------------------------------------------------------------------
-// a8 CSR interpolation.  Pixel m of a row whose (causal) source length is L covers source tokens
-// [roundf(m*s), roundf((m+1)*s)),  s = fp32(L)/fp32(P)   (un-fused IEEE ops, roundf = half away).
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void pixel_bounds(float s, int m, float& vs, float& ve) {
-    vs = roundf(__fmul_rn((float) m, s));
-    ve = roundf(__fmul_rn((float) (m + 1), s));
-}
-__device__ __forceinline__ int pixel_width(float s, int m, int k) {
-    float vs, ve;
-    pixel_bounds(s, m, vs, ve);
-    return min((int) __fsub_rn(ve, vs), k);
-}
-
 constexpr int kCsrWarps = 8;
 constexpr int kCsrThreads = 256;
-
-__device__ __forceinline__ int word_width_sum(uint32_t word, int w, int P, float s, int k) {
-    int acc = 0;
-    for (uint32_t x = word; x; x &= x - 1) acc += pixel_width(s, ((w << 5) + __ffs(x) - 1) % P, k);
-    return acc;
-}
 
 // CTA per query row, thread per 32-pixel word: the early causal rows keep all H*P pixels alive, so a warp-per-row
 // mapping leaves one warp with thousands of serial pixels on the critical path.
@@ -220,7 +201,7 @@ csr_fill_kernel(const uint32_t* __restrict__ bits, const IdxT* __restrict__ crow
             head_ptr[row * (H + 1) + w / words_per_head] = (int32_t) p;
         for (uint32_t x = word; x; x &= x - 1) {
             const int i = (w << 5) + __ffs(x) - 1;
-            const int h = i / P, m = i % P;
+            const int h = pix_h(i, P), m = pix_m(i, P);
             float vs, ve;
             pixel_bounds(s, m, vs, ve);
             const float span = __fsub_rn(ve, vs);
@@ -546,6 +527,15 @@ int sea_csr_count(const uint32_t* mask_bits, void* crow, int idx64, int N, int H
         csr_count_kernel<I><<<(unsigned) rows, kCsrThreads, 0, s>>>(mask_bits, (I*) crow, N, H, T_DST, P, T_SRC, k, is_causal, wpr);
         SEA_CHECK_LAUNCH("csr_count_kernel");
         crow_scan_kernel<I><<<N, 1024, 0, s>>>((I*) crow, T_DST);
+        SEA_CHECK_LAUNCH("crow_scan_kernel");
+    });
+    return SEA_OK;
+}
+
+int sea_crow_scan(void* crow, int idx64, int N, int T_DST, void* stream) {
+    SEA_CHECK_ARG(crow && N > 0 && T_DST > 0, "sea_crow_scan: bad argument");
+    SEA_DISPATCH_IDX(idx64, I, {
+        crow_scan_kernel<I><<<N, 1024, 0, (cudaStream_t) stream>>>((I*) crow, T_DST);
         SEA_CHECK_LAUNCH("crow_scan_kernel");
     });
     return SEA_OK;

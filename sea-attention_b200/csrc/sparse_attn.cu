@@ -235,8 +235,14 @@ __device__ __forceinline__ uint32_t pack2<__half>(float a, float b) {
     return *reinterpret_cast<uint32_t*>(&p);
 }
 
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 template <typename T16, typename IdxT, int D>
-__global__ void __launch_bounds__(kAttnWarps * 32)
+__global__ void __launch_bounds__(kAttnWarps * 32, 3)
 sparse_attention_v2_kernel(const IdxT* __restrict__ col, int64_t Z, const int32_t* __restrict__ head_ptr,
                            const T16* __restrict__ q, int64_t q_sn, int64_t q_sh, int64_t q_st,
                            const T16* __restrict__ k, int64_t k_sn, int64_t k_sh, int64_t k_st,
@@ -256,35 +262,39 @@ sparse_attention_v2_kernel(const IdxT* __restrict__ col, int64_t Z, const int32_
     const int sub = lane % LPR;         // which 8-channel slice of the row this lane owns
     const int grp = lane / LPR;         // which entry of a load instruction this lane serves
     const int32_t* hp = head_ptr + row * (H + 1) + h;
-    const int64_t s0 = hp[0], s1 = hp[1];
+    const int s0 = hp[0], s1 = hp[1];
     const IdxT* colr = col + (int64_t) n * Z;
-    const T16* kb = k + (int64_t) n * k_sn + (int64_t) h * k_sh + sub * 8;
-    const T16* vb = v + (int64_t) n * v_sn + (int64_t) h * v_sh + sub * 8;
+    // 16-byte-vector views; row strides in vectors fit 32 bits (strides are multiples of 8 elements)
+    const uint4* kb = reinterpret_cast<const uint4*>(k + (int64_t) n * k_sn + (int64_t) h * k_sh) + sub;
+    const uint4* vb = reinterpret_cast<const uint4*>(v + (int64_t) n * v_sn + (int64_t) h * v_sh) + sub;
+    const uint32_t k_sv = (uint32_t) (k_st >> 3), v_sv = (uint32_t) (v_st >> 3);
+    constexpr float kLog2e = 1.4426950408889634f;
     float qf[8];
     {
-        const uint4 qu = __ldg(reinterpret_cast<const uint4*>(q + (int64_t) n * q_sn + (int64_t) h * q_sh + (int64_t) t * q_st + sub * 8));
+        const uint4 qu = __ldg(reinterpret_cast<const uint4*>(q + (int64_t) n * q_sn + (int64_t) h * q_sh + (int64_t) t * q_st) + sub);
         unpack8<T16>(qu, qf);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) qf[c] *= kLog2e;      // scores live in the log2 domain: softmax = 2^(s - m) / sum
     }
-    constexpr float kLog2e = 1.4426950408889634f;
     float m_run = -INFINITY, l_run = 0.f;
     float acc[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-    const int64_t hbase = (int64_t) h * T_SRC;
-    for (int64_t base = s0; base < s1; base += 32) {
-        const int cnt = (int) min((int64_t) 32, s1 - base);
+    const int hbase = h * T_SRC;
+    for (int base = s0; base < s1; base += 32) {
+        const int cnt = min(32, s1 - base);
         int jmine = 0;
-        if (lane < cnt) jmine = (int) ((int64_t) colr[base + lane] - hbase);
+        if (lane < cnt) jmine = (int) colr[base + lane] - hbase;
         uint4 ku[NI], vu[NI];
 #pragma unroll
         for (int i = 0; i < NI; ++i) {
             const int e = i * EPI + grp;
-            const int j = __shfl_sync(kFull, jmine, e);
+            const uint32_t j = (uint32_t) __shfl_sync(kFull, jmine, e);
             ku[i] = make_uint4(0, 0, 0, 0);
             vu[i] = make_uint4(0, 0, 0, 0);
             if (e < cnt) {
-                ku[i] = __ldg(reinterpret_cast<const uint4*>(kb + (int64_t) j * k_st));
-                vu[i] = __ldg(reinterpret_cast<const uint4*>(vb + (int64_t) j * v_st));
+                ku[i] = __ldg(kb + j * k_sv);
+                vu[i] = __ldg(vb + j * v_sv);
             }
         }
         float sc[NI];
@@ -298,8 +308,7 @@ sparse_attention_v2_kernel(const IdxT* __restrict__ col, int64_t Z, const int32_
             for (int c = 0; c < 8; ++c) d = fmaf(qf[c], kf[c], d);
 #pragma unroll
             for (int o = LPR / 2; o > 0; o >>= 1) d += __shfl_xor_sync(kFull, d, o);
-            const bool valid = i * EPI + grp < cnt;
-            sc[i] = valid ? d : -INFINITY;
+            sc[i] = (i * EPI + grp < cnt) ? d : -INFINITY;
             cmax = fmaxf(cmax, sc[i]);
         }
 #pragma unroll
@@ -310,13 +319,13 @@ sparse_attention_v2_kernel(const IdxT* __restrict__ col, int64_t Z, const int32_
                 if (i * EPI + grp < cnt) probs_values[(int64_t) n * Z + base + i * EPI + grp] = sc[i];
         }
         const float m_new = fmaxf(m_run, cmax);
-        const float alpha = exp2f((m_run - m_new) * kLog2e);
+        const float alpha = ex2_approx(m_run - m_new);
         float psum = 0.f;
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[i] *= alpha;
 #pragma unroll
         for (int i = 0; i < NI; ++i) {
-            const float p = exp2f((sc[i] - m_new) * kLog2e);      // -inf -> 0 for the padding entries
+            const float p = ex2_approx(sc[i] - m_new);            // -inf -> 0 for the padding entries
             psum += p;
             float vf[8];
             unpack8<T16>(vu[i], vf);
@@ -343,7 +352,7 @@ sparse_attention_v2_kernel(const IdxT* __restrict__ col, int64_t Z, const int32_
 #pragma unroll
         for (int c = 0; c < 8; ++c) o8[c] = acc[c] * inv * psc;
         if (cumavg != nullptr) {
-            const uint4 au = __ldg(reinterpret_cast<const uint4*>(cumavg + (((int64_t) n * H + h) * T_DST + t) * D + sub * 8));
+            const uint4 au = __ldg(reinterpret_cast<const uint4*>(cumavg + (((int64_t) n * H + h) * T_DST + t) * D) + sub);
             float af[8];
             unpack8<T16>(au, af);
 #pragma unroll
@@ -352,12 +361,12 @@ sparse_attention_v2_kernel(const IdxT* __restrict__ col, int64_t Z, const int32_
         uint4 ou;
         ou.x = pack2<T16>(o8[0], o8[1]); ou.y = pack2<T16>(o8[2], o8[3]);
         ou.z = pack2<T16>(o8[4], o8[5]); ou.w = pack2<T16>(o8[6], o8[7]);
-        *reinterpret_cast<uint4*>(out + ((int64_t) n * T_DST + t) * ((int64_t) H * D) + (int64_t) h * D + sub * 8) = ou;
+        *(reinterpret_cast<uint4*>(out + ((int64_t) n * T_DST + t) * ((int64_t) H * D) + (int64_t) h * D) + sub) = ou;
     }
     if (probs_values != nullptr) {
-        for (int64_t z = s0 + lane; z < s1; z += 32) {
+        for (int z = s0 + lane; z < s1; z += 32) {
             float* pv = probs_values + (int64_t) n * Z + z;
-            *pv = exp2f((*pv - m_run) * kLog2e) * inv * psc;
+            *pv = ex2_approx(*pv - m_run) * inv * psc;
         }
     }
 }

@@ -86,13 +86,19 @@ def topk_mask_bits(probs: torch.Tensor, k_per_group: torch.Tensor, group_mode: s
 
 # --------------------------------------------------------------------------------------------- a8
 def csr_from_bits(bits: torch.Tensor, H: int, P: int, k: int, T_SRC: int, is_causal: bool = True,
-                  index_dtype=torch.int64, z_alloc: Optional[int] = None, want_head_ptr: bool = False):
+                  index_dtype=torch.int64, z_alloc: Optional[int] = None, want_head_ptr: bool = False, crow_counts=None):
     """bit mask -> (crow, col, Z).  z_alloc=None reads the exact nnz back (one host sync, like the
     reference's `.item()` at causal_resize_m_to_t.py:667); an int skips the sync and over-allocates."""
     N, T_DST, _ = bits.shape
     idx64 = 1 if index_dtype == torch.int64 else 0
-    crow = torch.empty((N, T_DST + 1), dtype=index_dtype, device=bits.device)
-    _lib.call('sea_csr_count', bits.data_ptr(), crow.data_ptr(), idx64, N, H, T_DST, P, T_SRC, int(k), int(is_causal), _stream())
+    if crow_counts is not None:      # per-row counts already produced by the fused predictor tail: only scan them
+        crow = crow_counts
+        if crow.dtype != index_dtype:
+            raise SeaError('crow_counts dtype must equal index_dtype')
+        _lib.call('sea_crow_scan', crow.data_ptr(), idx64, N, T_DST, _stream())
+    else:
+        crow = torch.empty((N, T_DST + 1), dtype=index_dtype, device=bits.device)
+        _lib.call('sea_csr_count', bits.data_ptr(), crow.data_ptr(), idx64, N, H, T_DST, P, T_SRC, int(k), int(is_causal), _stream())
     Z = int(crow[:, -1].max().item()) if z_alloc is None else int(z_alloc)
     col = torch.empty((N, Z), dtype=index_dtype, device=bits.device)
     hp = torch.empty((N, T_DST, H + 1), dtype=torch.int32, device=bits.device) if (want_head_ptr and P % 32 == 0) else None
@@ -328,15 +334,19 @@ def conv1x1_umma(x, weight, bias):
     return y
 
 
-def predictor_tail_topk(y3, bias, ln_w, ln_b, k_per_row, P: int, want_probs=True, want_bits=True):
-    """a5 tail + a6 + a7 fused: y3 fp32 [N,T,W,H] (conv1x1_umma) -> probs fp32 [N,H,T,P], top-k bit mask [N,T,H*P/32]."""
+def predictor_tail_topk(y3, bias, ln_w, ln_b, k_per_row, P: int, want_probs=True, want_bits=True, count_k: int = 0):
+    """a5 tail + a6 + a7 fused: y3 fp32 [N,T,W,H] (conv1x1_umma) -> probs fp32 [N,H,T,P], top-k bit mask [N,T,H*P/32].
+    count_k > 0 additionally fuses pass 1 of a8 (causal prefill): returns int32 crow [N,T+1] holding per-row counts."""
     _cuda(y3, bias, ln_w, ln_b, k_per_row)
     N, T, W, H = y3.shape
     probs = torch.empty((N, H, T, P), dtype=torch.float32, device=y3.device) if want_probs else None
     bits = torch.empty((N, T, (H * P) // 32), dtype=torch.int32, device=y3.device) if want_bits else None
+    crow = torch.empty((N, T + 1), dtype=torch.int32, device=y3.device) if count_k > 0 else None
     kpr = None if k_per_row is None else k_per_row.reshape(-1).float().contiguous()
     _lib.call('sea_predictor_tail_topk_fwd', y3.data_ptr(), bias.data_ptr(), ln_w.data_ptr(), ln_b.data_ptr(), _p(kpr), _p(probs),
-              _p(bits), N, H, T, W, P, _stream())
+              _p(bits), _p(crow), int(count_k), N, H, T, W, P, _stream())
+    if count_k > 0:
+        return probs, bits, crow
     return probs, bits
 
 

@@ -118,3 +118,21 @@ def test_performer_mma_matches_oracle(sea, N, H, T, nbf):
     # cross-check against the fp32 SIMT kernel on the same bf16 inputs
     ctx2, avg2 = sea.ops.performer_causal(q.to(DEV), k.to(DEV), v.to(DEV), pos.to(DEV), proj.to(DEV), force_simt=True)
     torch.testing.assert_close(ctx.float().cpu(), ctx2.float().cpu(), rtol=2e-2, atol=2e-2)
+
+
+def test_tail_topk_fused_row_counts(sea):
+    """The fused tail also emits pass 1 of the CSR interpolation (per-row entry counts)."""
+    import numpy as np
+    N, H, T, W, P, k = 2, 8, 70, 16, 64, 8
+    g = torch.Generator().manual_seed(1)
+    y3 = torch.randn(N, T, W, H, generator=g)
+    bias = torch.randn(H, generator=g)
+    ln_w, ln_b = torch.ones(P), torch.zeros(P)
+    kpr = torch.from_numpy(np.tile(so.per_item_top_k_causal(H, k, 1.0, P, T), N))
+    probs, bits, crow = sea.ops.predictor_tail_topk(y3.to(DEV), bias.to(DEV), ln_w.to(DEV), ln_b.to(DEV), kpr.to(DEV), P, count_k=k)
+    crow2, col2, Z2 = sea.ops.csr_from_bits(bits, H, P, k, T, True, torch.int32)          # unfused count
+    crow3, col3, Z3, hp = sea.ops.csr_from_bits(bits, H, P, k, T, True, torch.int32, z_alloc=Z2, want_head_ptr=True, crow_counts=crow)
+    assert torch.equal(crow3.cpu(), crow2.cpu()) and torch.equal(col3.cpu(), col2.cpu())
+    mask = sea.ops.bits_to_mask(bits, H, P).cpu()
+    crow_r, col_r, Z_r = so.resize_from_m_to_t_csr(mask, k, T, True)
+    assert torch.equal(crow3.cpu().long(), crow_r) and torch.equal(col3.cpu().long(), col_r)
