@@ -1,0 +1,51 @@
+"""Multi-GPU plumbing for the SEA attention hot path.
+
+The path shards with NO exchange step: every stage is independent across batch items, and -- for long contexts --
+across query blocks given replicated K/V.  One process per GPU; `torch.distributed` (NCCL over NVLink/NVSwitch on the
+GPU box, gloo in the CPU tests) is used only (a) for barriers / max-over-ranks timing and (b) when a caller asks for
+the full context tensor on every rank (`all_gather_context`).  Nothing here launches a collective on the hot path.
+"""
+from typing import List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(total: int, world_size: int, rank: int) -> Tuple[int, int]:
+    """Contiguous, balanced [begin, end) slice of `total` units (batch items or query rows) owned by `rank`;
+    the first `total % world_size` ranks get one extra unit."""
+    if world_size <= 0 or not (0 <= rank < world_size):
+        raise ValueError(f'bad rank {rank} / world size {world_size}')
+    base, rem = divmod(total, world_size)
+    begin = rank * base + min(rank, rem)
+    return begin, begin + base + (1 if rank < rem else 0)
+
+
+def shard_batch(tensors, world_size: int, rank: int):
+    """Batch sharding: slices dim 0 of every tensor (q, k, v, masks ...) to this rank's items."""
+    n = tensors[0].shape[0]
+    b, e = shard_bounds(n, world_size, rank)
+    return [t[b:e] for t in tensors]
+
+
+def all_gather_context(ctx_local: torch.Tensor, total_batch: int, group: Optional[dist.ProcessGroup] = None) -> torch.Tensor:
+    """Assembles the full context_layer [N, T, H*d] on every rank from batch shards of possibly unequal size.
+    The only collective the path ever needs, and only on request (NCCL all-gather over NVLink on the GPU box)."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    sizes = [shard_bounds(total_batch, world, r) for r in range(world)]
+    max_n = max(e - b for b, e in sizes)
+    pad = torch.zeros((max_n,) + tuple(ctx_local.shape[1:]), dtype=ctx_local.dtype, device=ctx_local.device)
+    pad[: ctx_local.shape[0]] = ctx_local
+    bufs: List[torch.Tensor] = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(bufs, pad, group=group)
+    return torch.cat([bufs[r][: sizes[r][1] - sizes[r][0]] for r in range(world)], dim=0)
+
+
+def max_over_ranks(value: float, device, group: Optional[dist.ProcessGroup] = None) -> float:
+    """Device-side timing reduction used by bench.py: the slowest rank defines the step time."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return value
+    t = torch.tensor([value], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return float(t.item())
