@@ -185,12 +185,18 @@ performer_chunk_kernel(const T* __restrict__ q, int64_t q_sn, int64_t q_sh, int6
 __global__ void __launch_bounds__(256)
 performer_prefix_kernel(float* __restrict__ ws, int nchunks, int64_t ws_stride) {
     float* base = ws + (int64_t) blockIdx.y * nchunks * ws_stride;
+    constexpr int kBatch = 16;      // independent loads issued together, then the serial prefix
     for (int64_t idx = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; idx < ws_stride; idx += (int64_t) gridDim.x * blockDim.x) {
         float run = 0.f;
-        for (int c = 0; c < nchunks; ++c) {
-            float cur = base[c * ws_stride + idx];
-            base[c * ws_stride + idx] = run;
-            run += cur;
+        for (int c0 = 0; c0 < nchunks; c0 += kBatch) {
+            float cur[kBatch];
+#pragma unroll
+            for (int i = 0; i < kBatch; ++i) cur[i] = (c0 + i < nchunks) ? __ldcg(base + (int64_t) (c0 + i) * ws_stride + idx) : 0.f;
+#pragma unroll
+            for (int i = 0; i < kBatch; ++i) {
+                if (c0 + i < nchunks) __stcg(base + (int64_t) (c0 + i) * ws_stride + idx, run);
+                run += cur[i];
+            }
         }
     }
 }

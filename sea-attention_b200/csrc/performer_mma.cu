@@ -63,40 +63,27 @@ __device__ __forceinline__ void load_proj(__nv_bfloat16* Ps, const float* __rest
         Ps[f * kLdQ + c] = __float2bfloat16_rn(f < F ? proj[f * kDm + c] : 0.f);
     }
 }
+// 16-byte asynchronous global->shared copy (LDGSTS); src_bytes = 0 zero-fills the destination
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 __device__ __forceinline__ void load_rows_bf16(__nv_bfloat16* dst, int ld, const __nv_bfloat16* __restrict__ src, int64_t row_stride,
                                                int r0, int nvalid) {
-    // 128 rows x 64 bf16, 16-byte vectors; rows beyond nvalid are zero
-    constexpr int kIt = kCh * (kDm / 8) / kThreads;     // 4: all loads of a thread are issued before the first store
-    uint4 val[kIt];
+    // 128 rows x 64 bf16 as 16-byte async copies: no registers are held while the data is in flight, so the q, k and v
+    // tiles of a chunk are all requested at once; rows beyond nvalid are zero-filled
+    constexpr int kIt = kCh * (kDm / 8) / kThreads;
 #pragma unroll
     for (int it = 0; it < kIt; ++it) {
         const int idx = threadIdx.x + it * kThreads, r = idx >> 3, c8 = idx & 7;
-        val[it] = make_uint4(0, 0, 0, 0);
-        if (r < nvalid) val[it] = __ldg(reinterpret_cast<const uint4*>(src + (int64_t) (r0 + r) * row_stride) + c8);
-    }
-#pragma unroll
-    for (int it = 0; it < kIt; ++it) {
-        const int idx = threadIdx.x + it * kThreads, r = idx >> 3, c8 = idx & 7;
-        *reinterpret_cast<uint4*>(dst + r * ld + c8 * 8) = val[it];
+        const bool ok = r < nvalid;
+        cp_async16(dst + r * ld + c8 * 8, src + (int64_t) (r0 + (ok ? r : 0)) * row_stride + c8 * 8, ok ? 16 : 0);
     }
 }
 __device__ __forceinline__ void load_v2ext(__nv_bfloat16* Vs, const __nv_bfloat16* __restrict__ v, int64_t v_st, const float* __restrict__ pos,
                                            int r0, int nvalid) {
-    {   // v -> cols 64..127
-        constexpr int kIt = kCh * (kDm / 8) / kThreads;
-        uint4 val[kIt];
-#pragma unroll
-        for (int it = 0; it < kIt; ++it) {
-            const int idx = threadIdx.x + it * kThreads, r = idx >> 3, c8 = idx & 7;
-            val[it] = make_uint4(0, 0, 0, 0);
-            if (r < nvalid) val[it] = __ldg(reinterpret_cast<const uint4*>(v + (int64_t) (r0 + r) * v_st) + c8);
-        }
-#pragma unroll
-        for (int it = 0; it < kIt; ++it) {
-            const int idx = threadIdx.x + it * kThreads, r = idx >> 3, c8 = idx & 7;
-            *reinterpret_cast<uint4*>(Vs + r * kLdV + kDm + c8 * 8) = val[it];
-        }
-    }
+    load_rows_bf16(Vs + kDm, kLdV, v, v_st, r0, nvalid);      // v -> cols 64..127 (async)
     {   // pos_emb (fp32) -> cols 0..63
         constexpr int kIt = kCh * (kDm / 4) / kThreads;
         float4 p[kIt];
@@ -159,6 +146,7 @@ performer_sums_mma_kernel(const __nv_bfloat16* __restrict__ k, int64_t k_sn, int
     load_proj<kFp>(Ps, proj, F);
     load_rows_bf16(Ks, kLdQ, k + (int64_t) n * k_sn + (int64_t) h * k_sh, k_st, r0, nvalid);
     load_v2ext(Vs, v + (int64_t) n * v_sn + (int64_t) h * v_sh, v_st, pos_emb, r0, nvalid);
+    cp_async_wait_all();
     __syncthreads();
     const float norm = rsqrtf(sqrtf((float) kDm));
     {
@@ -226,7 +214,7 @@ performer_sums_mma_kernel(const __nv_bfloat16* __restrict__ k, int64_t k_sn, int
 
 // ---- pass C: outputs ------------------------------------------------------------------------------------------
 template <int kFp>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 2)
 performer_out_mma_kernel(const __nv_bfloat16* __restrict__ q, int64_t q_sn, int64_t q_sh, int64_t q_st,
                          const __nv_bfloat16* __restrict__ k, int64_t k_sn, int64_t k_sh, int64_t k_st,
                          const __nv_bfloat16* __restrict__ v, int64_t v_sn, int64_t v_sh, int64_t v_st,
@@ -235,7 +223,6 @@ performer_out_mma_kernel(const __nv_bfloat16* __restrict__ q, int64_t q_sn, int6
     using SM = PerfSmem<kFp>;
     extern __shared__ __align__(16) __nv_bfloat16 sm[];
     __nv_bfloat16 *Ps = sm + SM::kP, *Qs = sm + SM::kQ, *Ks = sm + SM::kK, *PhiK = sm + SM::kPhiK, *Vs = sm + SM::kV, *Ss = sm + SM::kS;
-    float* vsum_prev = reinterpret_cast<float*>(sm + SM::kElems);
     const int chunk = blockIdx.x, nh = blockIdx.y, n = nh / H, h = nh % H;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tq = lane & 3;
     const int r0 = chunk * kCh, nvalid = min(kCh, T - r0);
@@ -252,8 +239,8 @@ performer_out_mma_kernel(const __nv_bfloat16* __restrict__ q, int64_t q_sn, int6
             *reinterpret_cast<uint32_t*>(Ss + f * kLdV + e) = pack_bf16(s2.x, s2.y);
         }
         for (int idx = threadIdx.x; idx < kFp; idx += kThreads) *reinterpret_cast<uint4*>(Ss + idx * kLdV + kEx) = make_uint4(0, 0, 0, 0);
-        for (int c = threadIdx.x; c < kDm; c += kThreads) vsum_prev[c] = slot[F * kEx + kDm + c];
     }
+    cp_async_wait_all();
     __syncthreads();
     const float norm = rsqrtf(sqrtf((float) kDm));
     uint32_t aq[kFp / 16][4];     // phi(q) of this warp's rows as A fragments
@@ -292,15 +279,10 @@ performer_out_mma_kernel(const __nv_bfloat16* __restrict__ q, int64_t q_sn, int6
     }
     __syncthreads();
     float O[kEx / 8][4];        // [16 x 144]
-    float A2[kDm / 8][4];       // running-sum GEMM: tril(1) . v   [16 x 64]
 #pragma unroll
     for (int nt = 0; nt < kEx / 8; ++nt)
 #pragma unroll
         for (int i = 0; i < 4; ++i) O[nt][i] = 0.f;
-#pragma unroll
-    for (int nt = 0; nt < kDm / 8; ++nt)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) A2[nt][i] = 0.f;
     const int brow = (lane & 7) + 8 * (lane >> 4), bcol = 8 * ((lane >> 3) & 1);    // B from [n][k] storage (PhiK)
     const int vr = (lane & 7) + 8 * ((lane >> 3) & 1), vc = 8 * (lane >> 4);        // B from [k][n] storage (Vs, Ss), trans
     for (int jt = 0; jt <= warp; ++jt) {
@@ -317,7 +299,7 @@ performer_out_mma_kernel(const __nv_bfloat16* __restrict__ q, int64_t q_sn, int6
             mma16816(p[0], aq[ks], b[0], b[1]);
             mma16816(p[1], aq[ks], b[2], b[3]);
         }
-        uint32_t pa[4], la[4];
+        uint32_t pa[4];
         if (jt == warp) {       // diagonal tile: keep source j <= query i
 #pragma unroll
             for (int t2 = 0; t2 < 2; ++t2)
@@ -326,10 +308,6 @@ performer_out_mma_kernel(const __nv_bfloat16* __restrict__ q, int64_t q_sn, int6
                     const int col = t2 * 8 + 2 * tq + (i & 1), row = g + 8 * (i >> 1);
                     if (col > row) p[t2][i] = 0.f;
                 }
-            const uint32_t lo = (2 * tq <= g) ? 0x3F80u : 0u, hi = (2 * tq + 1 <= g) ? 0x3F800000u : 0u;
-            la[0] = lo | hi; la[1] = 0x3F803F80u; la[2] = 0u; la[3] = lo | hi;
-        } else {
-            la[0] = la[1] = la[2] = la[3] = 0x3F803F80u;
         }
         pa[0] = pack_bf16(p[0][0], p[0][1]); pa[1] = pack_bf16(p[0][2], p[0][3]);
         pa[2] = pack_bf16(p[1][0], p[1][1]); pa[3] = pack_bf16(p[1][2], p[1][3]);
@@ -339,10 +317,6 @@ performer_out_mma_kernel(const __nv_bfloat16* __restrict__ q, int64_t q_sn, int6
             ldsm_x4_t(b, smem_u32(Vs + (jt * 16 + vr) * kLdV + np * 16 + vc));
             mma16816(O[2 * np], pa, b[0], b[1]);
             mma16816(O[2 * np + 1], pa, b[2], b[3]);
-            if (np >= 4 && np < 8) {        // columns 64..127 = v: running sum with the triangular ones tile
-                mma16816(A2[2 * (np - 4)], la, b[0], b[1]);
-                mma16816(A2[2 * (np - 4) + 1], la, b[2], b[3]);
-            }
         }
     }
     // + phi(q) . S_prev
@@ -367,28 +341,58 @@ performer_out_mma_kernel(const __nv_bfloat16* __restrict__ q, int64_t q_sn, int6
         if (row_lo < nvalid) *reinterpret_cast<uint32_t*>(cb + (int64_t) row_lo * kE + e0) = pack_bf16(O[nt][0] * inv_lo, O[nt][1] * inv_lo);
         if (row_hi < nvalid) *reinterpret_cast<uint32_t*>(cb + (int64_t) row_hi * kE + e0) = pack_bf16(O[nt][2] * inv_hi, O[nt][3] * inv_hi);
     }
-    if (cumavg != nullptr) {
-        __nv_bfloat16* ab = cumavg + (((int64_t) n * H + h) * T + r0) * kDm;
-        const float il = 1.0f / (float) (r0 + row_lo + 1), ih = 1.0f / (float) (r0 + row_hi + 1);
+}
+
+// a13 running mean of v (attention.py:1237-1241): cumavg[t] = (vsum_prev(chunk) + sum_{j<=t in chunk} v_j) / (t+1).
+// vsum_prev is row F (the ones feature) of the prefixed state, columns 64..127.  Thread = (8-row group, channel);
+// group partial sums are combined through shared memory, then each thread walks its 8 rows.
+template <int kFp>
+__global__ void __launch_bounds__(1024)
+cumavg_kernel(const __nv_bfloat16* __restrict__ v, int64_t v_sn, int64_t v_sh, int64_t v_st, const float* __restrict__ ws,
+              __nv_bfloat16* __restrict__ cumavg, int H, int T, int F, int nchunks) {
+    __shared__ float part[16][kDm];
+    const int chunk = blockIdx.x, nh = blockIdx.y, n = nh / H, h = nh % H;
+    const int c = threadIdx.x & 63, grp = threadIdx.x >> 6;      // 16 groups x 8 rows
+    const int r0 = chunk * kCh;
+    const __nv_bfloat16* vb = v + (int64_t) n * v_sn + (int64_t) h * v_sh;
+    float x[8];
+    float s = 0.f;
 #pragma unroll
-        for (int nt = 0; nt < kDm / 8; ++nt) {
-            const int c0 = nt * 8 + 2 * tq;
-            const float s0 = vsum_prev[c0], s1 = vsum_prev[c0 + 1];
-            if (row_lo < nvalid) *reinterpret_cast<uint32_t*>(ab + (int64_t) row_lo * kDm + c0) = pack_bf16((A2[nt][0] + s0) * il, (A2[nt][1] + s1) * il);
-            if (row_hi < nvalid) *reinterpret_cast<uint32_t*>(ab + (int64_t) row_hi * kDm + c0) = pack_bf16((A2[nt][2] + s0) * ih, (A2[nt][3] + s1) * ih);
-        }
+    for (int i = 0; i < 8; ++i) {
+        const int t = r0 + grp * 8 + i;
+        x[i] = t < T ? __bfloat162float(vb[(int64_t) t * v_st + c]) : 0.f;
+        s += x[i];
+    }
+    part[grp][c] = s;
+    __syncthreads();
+    float run = ws[((int64_t) nh * nchunks + chunk) * (kFp * kEx) + F * kEx + kDm + c];
+    for (int gidx = 0; gidx < grp; ++gidx) run += part[gidx][c];
+    __nv_bfloat16* ab = cumavg + (((int64_t) n * H + h) * T) * kDm;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int t = r0 + grp * 8 + i;
+        run += x[i];
+        if (t < T) ab[(int64_t) t * kDm + c] = __float2bfloat16_rn(__fdividef(run, (float) (t + 1)));
     }
 }
 
+// exclusive prefix over the chunk slots of one (n, h).  The loads of a batch of chunks are issued together (they are
+// independent; a naive load/store loop serialises on aliasing and costs one L2 round trip per chunk).
 __global__ void __launch_bounds__(256)
 prefix_chunks_kernel(float* __restrict__ ws, int nchunks, int64_t stride) {
     float* base = ws + (int64_t) blockIdx.y * nchunks * stride;
+    constexpr int kBatch = 16;
     for (int64_t idx = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; idx < stride; idx += (int64_t) gridDim.x * blockDim.x) {
         float run = 0.f;
-        for (int c = 0; c < nchunks; ++c) {
-            const float cur = base[c * stride + idx];
-            base[c * stride + idx] = run;
-            run += cur;
+        for (int c0 = 0; c0 < nchunks; c0 += kBatch) {
+            float cur[kBatch];
+#pragma unroll
+            for (int i = 0; i < kBatch; ++i) cur[i] = (c0 + i < nchunks) ? __ldcg(base + (int64_t) (c0 + i) * stride + idx) : 0.f;
+#pragma unroll
+            for (int i = 0; i < kBatch; ++i) {
+                if (c0 + i < nchunks) __stcg(base + (int64_t) (c0 + i) * stride + idx, run);
+                run += cur[i];
+            }
         }
     }
 }
@@ -413,6 +417,10 @@ int launch_performer_mma(const void* q, int64_t q_sn, int64_t q_sh, int64_t q_st
     kc<<<grid, kThreads, SM::kBytes, s>>>((const B*) q, q_sn, q_sh, q_st, (const B*) k, k_sn, k_sh, k_st, (const B*) v, v_sn, v_sh, v_st,
                                           pos_emb, proj, ws, (B*) ctx, (B*) cumavg, H, T, F, nchunks);
     SEA_CHECK_LAUNCH("performer_out_mma_kernel");
+    if (cumavg != nullptr) {
+        cumavg_kernel<kFp><<<grid, 1024, 0, s>>>((const B*) v, v_sn, v_sh, v_st, ws, (B*) cumavg, H, T, F, nchunks);
+        SEA_CHECK_LAUNCH("cumavg_kernel");
+    }
     return SEA_OK;
 }
 

@@ -254,11 +254,14 @@ sparse_attention_v2_kernel(const IdxT* __restrict__ col, int64_t Z, const int32_
     constexpr int EPI = 32 / LPR;       // entries per warp-wide load
     constexpr int NI = 32 / EPI;        // loads per 32-entry chunk (= LPR)
     const int lane = threadIdx.x & 31;
-    const int64_t task = (int64_t) blockIdx.x * kAttnWarps + (threadIdx.x >> 5);      // (n, t, h)
+    // task order (n, h, t) with t fastest: the warps of a CTA work on CONSECUTIVE query rows of ONE head, whose pixel
+    // runs overlap, so part of the K/V gathers hits the SM's L1 instead of going to L2 again
+    const int64_t task = (int64_t) blockIdx.x * kAttnWarps + (threadIdx.x >> 5);
     if (task >= (int64_t) N * T_DST * H) return;
-    const int h = (int) (task % H);
-    const int64_t row = task / H;
-    const int n = (int) (row / T_DST), t = (int) (row % T_DST);
+    const int t = (int) (task % T_DST);
+    const int h = (int) ((task / T_DST) % H);
+    const int n = (int) (task / ((int64_t) T_DST * H));
+    const int64_t row = (int64_t) n * T_DST + t;
     const int sub = lane % LPR;         // which 8-channel slice of the row this lane owns
     const int grp = lane / LPR;         // which entry of a load instruction this lane serves
     const int32_t* hp = head_ptr + row * (H + 1) + h;

@@ -51,7 +51,7 @@ int make_tmap_bf16_sw128(CUtensorMap* out, void* base, int rank, const uint64_t*
 
 namespace {
 
-constexpr int kStages = 6;
+constexpr int kStages = 8;
 constexpr int kATileBytes = 128 * 128;     // 128 pixels x 64 bf16
 constexpr int kConvThreads = 192;
 
