@@ -241,6 +241,16 @@ SEA_API int sea_sparse_attention_fwd(const void* crow, const void* col, int idx6
                              void* out, float* probs_values, const int32_t* head_ptr,
                              int N, int H, int T_DST, int T_SRC, int D, void* stream);
 
+/* a8 + a9-a14 fused: the same attention as sea_sparse_attention_fwd, driven directly by the top-k bit mask (the CSR
+ * column list is a pure function of it, sea_csr_fill); used when the caller does not need the CSR tensors.
+ * 16-bit activations, D in {32,64,128}, P % 32 == 0, P <= 1024.  k_clamp = pconfig.k (pixel width clamp of a8). */
+SEA_API int sea_sparse_attention_bits_fwd(const uint32_t* mask_bits,
+                                          const void* q, int64_t q_sn, int64_t q_sh, int64_t q_st,
+                                          const void* k, int64_t k_sn, int64_t k_sh, int64_t k_st,
+                                          const void* v, int64_t v_sn, int64_t v_sh, int64_t v_st,
+                                          const float* scales, const void* cumavg, int use_scaler, int dtype, void* out,
+                                          int N, int H, int T_DST, int T_SRC, int D, int P, int k_clamp, int is_causal, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

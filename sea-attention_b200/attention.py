@@ -286,18 +286,27 @@ class PerlinAttention(nn.Module):
         if q.dtype == torch.bfloat16 and ops.conv_umma_supported(q.dtype, W, S * H, H) and P % 32 == 0:
             # tensor-core path: 1x1 conv before the upsample (tcgen05), then tail + softmax + top-k in one kernel
             y3 = ops.conv1x1_umma(y, w['conv3_w'], w['conv3_b'])
-            probs, bits, crow_counts = ops.predictor_tail_topk(y3, w['conv3_b'], w['out_ln_w'], w['out_ln_b'], kpr, P, count_k=pc.k)
+            res = ops.predictor_tail_topk(y3, w['conv3_b'], w['out_ln_w'], w['out_ln_b'], kpr, P, count_k=pc.k if self.output_attentions else 0)
+            probs, bits, crow_counts = res if len(res) == 3 else (res[0], res[1], None)
         else:
             probs, _ = ops.predictor_tail(y, w['conv3_w'], w['conv3_b'], w['out_ln_w'], w['out_ln_b'], P)
             bits = ops.topk_mask_bits(probs, kpr, 'causal_batch')
             crow_counts = None
-        # a8 (int32 indices internally; no host sync: col is allocated at a shape-derived upper bound)
-        crow, col, Z, head_ptr = ops.csr_from_bits(bits, H, P, pc.k, T, is_causal=True, index_dtype=torch.int32, z_alloc=z_alloc,
-                                                   want_head_ptr=True, crow_counts=crow_counts)
-        # a9-a14
-        context, pvals = ops.sparse_attention(crow, col, q_for_score, k_for_score, v, scales, cumavg,
-                                              use_scaler=pc.partial_attention_scaler, want_probs=self.output_attentions,
-                                              head_ptr=head_ptr)
+        if not self.output_attentions and ops.attention_bits_supported(q.dtype, d, P):
+            # a8 + a9-a14 in one kernel: the CSR column list is a pure function of the bit mask, so it is only
+            # materialised when the caller asks for the CSR tensors (output_attentions)
+            context = ops.sparse_attention_from_bits(bits, q_for_score, k_for_score, v, scales, cumavg, P, pc.k,
+                                                     use_scaler=pc.partial_attention_scaler, is_causal=True)
+            pvals = crow = col = None
+            Z = 0
+        else:
+            # a8 (int32 indices internally; no host sync: col is allocated at a shape-derived upper bound)
+            crow, col, Z, head_ptr = ops.csr_from_bits(bits, H, P, pc.k, T, is_causal=True, index_dtype=torch.int32, z_alloc=z_alloc,
+                                                       want_head_ptr=True, crow_counts=crow_counts)
+            # a9-a14
+            context, pvals = ops.sparse_attention(crow, col, q_for_score, k_for_score, v, scales, cumavg,
+                                                  use_scaler=pc.partial_attention_scaler, want_probs=self.output_attentions,
+                                                  head_ptr=head_ptr)
         partial_probs = partial_mask = None
         if self.output_attentions:
             size = (N, T, H * T)

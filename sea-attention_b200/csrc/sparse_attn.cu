@@ -7,6 +7,9 @@
 // 32-entry chunks, and a lane-per-channel-pair P.V accumulation with coalesced V-row reads.
 // Nothing but the output row (and optionally the probabilities) is written: scores never touch HBM.
 #include "common.cuh"
+#include "csr_common.cuh"
+
+#include <stdlib.h>
 
 namespace sea {
 
@@ -374,6 +377,418 @@ sparse_attention_v2_kernel(const IdxT* __restrict__ col, int64_t Z, const int32_
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// v3: attention straight from the top-k BIT MASK.  The flat-CSR column list is a pure function of the bit mask
+// (a8), so when the caller does not ask for the CSR tensors the entries are enumerated on the fly, per (row, head),
+// with the same pixel arithmetic (csr_common.cuh) -- the count / scan / fill kernels and the 4 bytes per entry of
+// column ids leave the hot path.  Entry order inside a (row, head) segment equals the CSR order (pixels ascending,
+// tokens descending inside a pixel), so results match the CSR kernels up to fp32 summation order.
+// ------------------------------------------------------------------------------------------------
+template <typename T16, int D>
+__global__ void __launch_bounds__(kAttnWarps * 32, 3)
+sparse_attention_bits_kernel(const uint32_t* __restrict__ mask_bits,
+                             const T16* __restrict__ q, int64_t q_sn, int64_t q_sh, int64_t q_st,
+                             const T16* __restrict__ k, int64_t k_sn, int64_t k_sh, int64_t k_st,
+                             const T16* __restrict__ v, int64_t v_sn, int64_t v_sh, int64_t v_st,
+                             const float* __restrict__ scales, const T16* __restrict__ cumavg, int use_scaler,
+                             T16* __restrict__ out, int N, int H, int T_DST, int T_SRC, int P, int k_clamp, int is_causal) {
+    constexpr int LPR = D / 8, EPI = 32 / LPR, NI = 32 / EPI;
+    const int lane = threadIdx.x & 31;
+    const int64_t task = (int64_t) blockIdx.x * kAttnWarps + (threadIdx.x >> 5);
+    if (task >= (int64_t) N * T_DST * H) return;
+    const int t = (int) (task % T_DST);
+    const int h = (int) ((task / T_DST) % H);
+    const int n = (int) (task / ((int64_t) T_DST * H));
+    const int64_t row = (int64_t) n * T_DST + t;
+    const int sub = lane % LPR, grp = lane / LPR;
+    const uint4* kb = reinterpret_cast<const uint4*>(k + (int64_t) n * k_sn + (int64_t) h * k_sh) + sub;
+    const uint4* vb = reinterpret_cast<const uint4*>(v + (int64_t) n * v_sn + (int64_t) h * v_sh) + sub;
+    const uint32_t k_sv = (uint32_t) (k_st >> 3), v_sv = (uint32_t) (v_st >> 3);
+    constexpr float kLog2e = 1.4426950408889634f;
+    float qf[8];
+    {
+        const uint4 qu = __ldg(reinterpret_cast<const uint4*>(q + (int64_t) n * q_sn + (int64_t) h * q_sh + (int64_t) t * q_st) + sub);
+        unpack8<T16>(qu, qf);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) qf[c] *= kLog2e;
+    }
+    float m_run = -INFINITY, l_run = 0.f;
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+
+    // this head's P mask bits: lane w holds word w (P/32 <= 32 words)
+    const int nw = P >> 5;
+    const int L = is_causal ? (T_SRC - T_DST + t + 1) : T_SRC;
+    const float s_scale = __fdiv_rn((float) L, (float) P);
+    const uint32_t word = lane < nw ? mask_bits[row * ((int64_t) H * nw) + (int64_t) h * nw + lane] : 0u;
+    const int pc = __popc(word);
+    const int pc_incl = warp_scan_incl_i(pc, lane);
+    const int n_alive = __shfl_sync(kFull, pc_incl, 31);
+    for (int r0 = 0; r0 < n_alive; r0 += 32) {
+        // lane takes the (r0 + lane)-th alive pixel of the head
+        const int slot = r0 + lane;
+        int wi = 0;
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1) {
+            const int vv = __shfl_sync(kFull, pc_incl, wi + step - 1);
+            if (vv <= slot) wi += step;
+        }
+        wi = min(wi, 31);
+        const uint32_t wsel = __shfl_sync(kFull, word, wi);
+        const int before = __shfl_sync(kFull, pc_incl - pc, wi);
+        int wd = 0, ve_i = 0, span_i = 0;
+        if (slot < n_alive) {
+            const int bit = __fns(wsel, 0, slot - before + 1);
+            float vs, ve;
+            pixel_bounds(s_scale, (wi << 5) + bit, vs, ve);
+            span_i = (int) __fsub_rn(ve, vs);
+            ve_i = (int) ve;
+            wd = min(span_i, k_clamp);
+        }
+        const int incl = warp_scan_incl_i(wd, lane);
+        const int excl = incl - wd;
+        const int total = __shfl_sync(kFull, incl, 31);
+        for (int e0 = 0; e0 < total; e0 += 32) {
+            const int cnt = min(32, total - e0);
+            const int e = e0 + lane;
+            int pl = 0;
+#pragma unroll
+            for (int step = 16; step > 0; step >>= 1) {
+                const int vv = __shfl_sync(kFull, incl, pl + step - 1);
+                if (vv <= e) pl += step;
+            }
+            pl = min(pl, 31);
+            const int p_excl = __shfl_sync(kFull, excl, pl);
+            const int p_ve = __shfl_sync(kFull, ve_i, pl);
+            const int p_wd = __shfl_sync(kFull, wd, pl);
+            const int p_span = __shfl_sync(kFull, span_i, pl);
+            int jmine = 0;
+            if (lane < cnt) {
+                const int i = e - p_excl;
+                jmine = p_wd == p_span ? p_ve - 1 - i
+                                       : p_ve - 1 - (int) __fmul_rn((float) i, __fdiv_rn((float) p_span, (float) p_wd));
+            }
+            uint4 ku[NI], vu[NI];
+#pragma unroll
+            for (int i = 0; i < NI; ++i) {
+                const int ee = i * EPI + grp;
+                const uint32_t j = (uint32_t) __shfl_sync(kFull, jmine, ee);
+                ku[i] = make_uint4(0, 0, 0, 0);
+                vu[i] = make_uint4(0, 0, 0, 0);
+                if (ee < cnt) {
+                    ku[i] = __ldg(kb + j * k_sv);
+                    vu[i] = __ldg(vb + j * v_sv);
+                }
+            }
+            float sc[NI];
+            float cmax = -INFINITY;
+#pragma unroll
+            for (int i = 0; i < NI; ++i) {
+                float kf[8];
+                unpack8<T16>(ku[i], kf);
+                float d = 0.f;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) d = fmaf(qf[c], kf[c], d);
+#pragma unroll
+                for (int o = LPR / 2; o > 0; o >>= 1) d += __shfl_xor_sync(kFull, d, o);
+                sc[i] = (i * EPI + grp < cnt) ? d : -INFINITY;
+                cmax = fmaxf(cmax, sc[i]);
+            }
+#pragma unroll
+            for (int o = LPR; o < 32; o <<= 1) cmax = fmaxf(cmax, __shfl_xor_sync(kFull, cmax, o));
+            const float m_new = fmaxf(m_run, cmax);
+            const float alpha = ex2_approx(m_run - m_new);
+            float psum = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] *= alpha;
+#pragma unroll
+            for (int i = 0; i < NI; ++i) {
+                const float p = ex2_approx(sc[i] - m_new);
+                psum += p;
+                float vf[8];
+                unpack8<T16>(vu[i], vf);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) acc[c] = fmaf(p, vf[c], acc[c]);
+            }
+#pragma unroll
+            for (int o = LPR; o < 32; o <<= 1) psum += __shfl_xor_sync(kFull, psum, o);
+            l_run = l_run * alpha + psum;
+            m_run = m_new;
+        }
+    }
+#pragma unroll
+    for (int o = LPR; o < 32; o <<= 1) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[c] += __shfl_xor_sync(kFull, acc[c], o);
+    }
+    if (grp == 0) {
+        const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
+        const float* sp = scales + ((((int64_t) n * H + h) * T_DST + t) << 1);
+        const float psc = use_scaler ? sigmoidf_(sp[0]) : 1.0f;
+        const float a = sigmoidf_(sp[1]);
+        float o8[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) o8[c] = acc[c] * inv * psc;
+        if (cumavg != nullptr) {
+            const uint4 au = __ldg(reinterpret_cast<const uint4*>(cumavg + (((int64_t) n * H + h) * T_DST + t) * D) + sub);
+            float af[8];
+            unpack8<T16>(au, af);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) o8[c] = o8[c] * a + (1.0f - a) * af[c];
+        }
+        uint4 ou;
+        ou.x = pack2<T16>(o8[0], o8[1]); ou.y = pack2<T16>(o8[2], o8[3]);
+        ou.z = pack2<T16>(o8[4], o8[5]); ou.w = pack2<T16>(o8[6], o8[7]);
+        *(reinterpret_cast<uint4*>(out + ((int64_t) n * T_DST + t) * ((int64_t) H * D) + (int64_t) h * D) + sub) = ou;
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// v4: the per-(row, head) segment on the TENSOR CORES.  A single query row is a degenerate GEMM, but the CUDA-core
+// version of v2/v3 spends ~800 instructions per 32 entries on bf16 unpacking, FMAs and shuffle reductions, and is
+// issue-bound.  Here the 32 gathered K rows and V rows of a chunk are copied global -> shared with 16-byte cp.async
+// (no register staging), and
+//   scores  = K_tile [32 x D] . q          as  m16n8k16 MMAs with q in column 0 of the B operand
+//   out    += p [1 x 32] . V_tile [32 x D]  as  m16n8k16 MMAs with p in row 0 of the A operand (V via ldmatrix.trans)
+// 15/16 of every MMA is padding -- irrelevant: the tensor pipe is idle otherwise, and the instruction count per chunk
+// drops ~4x.  fp32 accumulation, fp32 online softmax in the log2 domain; q, K, V, p enter the MMAs as bf16/fp16.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gsrc, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t) __cvta_generic_to_shared(smem_dst)), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void ldsm4(uint32_t (&r)[4], const void* p) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"((uint32_t) __cvta_generic_to_shared(p)));
+}
+__device__ __forceinline__ void ldsm4_t(uint32_t (&r)[4], const void* p) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"((uint32_t) __cvta_generic_to_shared(p)));
+}
+template <typename T16>
+__device__ __forceinline__ void mma_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1);
+template <>
+__device__ __forceinline__ void mma_16816<__nv_bfloat16>(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+template <>
+__device__ __forceinline__ void mma_16816<__half>(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <int D>
+struct AttnMmaCfg {
+    static constexpr int kLd = D + 8;                       // padded row (elements): ldmatrix rows hit distinct banks
+    static constexpr int kWarpElems = 2 * 32 * kLd;         // K tile + V tile per warp
+    static constexpr int kSmemBytes = kAttnWarps * kWarpElems * 2;
+};
+
+// One 32-entry chunk: gathers K/V rows `jmine` (lane e holds the source token of entry e; cnt valid entries) and folds
+// them into the running (m, l, acc) online-softmax state of this warp's (row, head).
+template <typename T16, int D>
+__device__ __forceinline__ void attn_chunk_mma(T16* __restrict__ Ks, T16* __restrict__ Vs, const uint4* __restrict__ kb, const uint4* __restrict__ vb,
+                                               uint32_t k_sv, uint32_t v_sv, int jmine, int cnt, const uint32_t (&qb)[D / 16][2],
+                                               float& m_run, float& l_run, float (&acc)[D / 8][4], int lane) {
+    constexpr int LPR = D / 8, EPI = 32 / LPR, NI = LPR, kLd = AttnMmaCfg<D>::kLd;
+    constexpr float kLog2e = 1.4426950408889634f;
+    const int sub = lane % LPR, grp = lane / LPR;
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+        const int e = i * EPI + grp;
+        const uint32_t j = (uint32_t) __shfl_sync(kFull, jmine, e);
+        const bool ok = e < cnt;
+        cp_async16_zfill(Ks + e * kLd + sub * 8, kb + (ok ? j * k_sv : 0u), ok ? 16 : 0);
+        cp_async16_zfill(Vs + e * kLd + sub * 8, vb + (ok ? j * v_sv : 0u), ok ? 16 : 0);
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncwarp();
+    const int g = lane >> 2, tq = lane & 3;
+    // scores: two m16 tiles of entries; only column 0 of the n8 tile is real
+    float sc[2][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) sc[mt][i] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < D / 16; ++ks) {
+            uint32_t a[4];
+            ldsm4(a, Ks + (mt * 16 + (lane & 7) + 8 * ((lane >> 3) & 1)) * kLd + ks * 16 + 8 * (lane >> 4));
+            mma_16816<T16>(sc[mt], a, qb[ks][0], qb[ks][1]);
+        }
+    }
+    // lanes with tq == 0 hold entries g, g+8, 16+g, 24+g in (sc[0][0], sc[0][2], sc[1][0], sc[1][2])
+    float s4[4] = {sc[0][0] * kLog2e, sc[0][2] * kLog2e, sc[1][0] * kLog2e, sc[1][2] * kLog2e};
+    const int e4[4] = {g, g + 8, 16 + g, 24 + g};
+    float cmax = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if (e4[i] >= cnt) s4[i] = -INFINITY;
+        cmax = fmaxf(cmax, s4[i]);
+    }
+#pragma unroll
+    for (int o = 4; o < 32; o <<= 1) cmax = fmaxf(cmax, __shfl_xor_sync(kFull, cmax, o));
+    cmax = __shfl_sync(kFull, cmax, lane & ~3);              // take the tq == 0 lane's value (others hold padding columns)
+    const float m_new = fmaxf(m_run, cmax);
+    const float alpha = ex2_approx(m_run - m_new);
+    float p4[4], psum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { p4[i] = ex2_approx(s4[i] - m_new); psum += p4[i]; }
+    if (tq != 0) psum = 0.f;
+#pragma unroll
+    for (int o = 4; o < 32; o <<= 1) psum += __shfl_xor_sync(kFull, psum, o);
+    psum = __shfl_sync(kFull, psum, lane & ~3);
+    l_run = l_run * alpha + psum;
+    m_run = m_new;
+#pragma unroll
+    for (int nt = 0; nt < D / 8; ++nt) { acc[nt][0] *= alpha; acc[nt][1] *= alpha; }
+    // p as the A operand (row 0 only): lane (g == 0, tq) needs entries 16ks+2tq, +1, 16ks+8+2tq, +1
+    uint32_t pa[2][4];
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+        const float lo0 = __shfl_sync(kFull, p4[2 * ks], 8 * tq);          // entry 16ks + 2tq      (holder lane 4*(2tq), slot c0)
+        const float lo1 = __shfl_sync(kFull, p4[2 * ks], 8 * tq + 4);      // entry 16ks + 2tq + 1
+        const float hi0 = __shfl_sync(kFull, p4[2 * ks + 1], 8 * tq);      // entry 16ks + 8 + 2tq  (slot c2)
+        const float hi1 = __shfl_sync(kFull, p4[2 * ks + 1], 8 * tq + 4);
+        const bool row0 = g == 0;
+        pa[ks][0] = row0 ? pack2<T16>(lo0, lo1) : 0u;
+        pa[ks][1] = 0u;
+        pa[ks][2] = row0 ? pack2<T16>(hi0, hi1) : 0u;
+        pa[ks][3] = 0u;
+    }
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+#pragma unroll
+        for (int np = 0; np < D / 16; ++np) {
+            uint32_t b[4];
+            ldsm4_t(b, Vs + (ks * 16 + (lane & 7) + 8 * ((lane >> 3) & 1)) * kLd + np * 16 + 8 * (lane >> 4));
+            mma_16816<T16>(acc[2 * np], pa[ks], b[0], b[1]);
+            mma_16816<T16>(acc[2 * np + 1], pa[ks], b[2], b[3]);
+        }
+    }
+    __syncwarp();       // every lane is done reading the tiles before the next chunk overwrites them
+}
+
+template <typename T16, int D>
+__global__ void __launch_bounds__(kAttnWarps * 32, 3)
+sparse_attention_bits_mma_kernel(const uint32_t* __restrict__ mask_bits,
+                                 const T16* __restrict__ q, int64_t q_sn, int64_t q_sh, int64_t q_st,
+                                 const T16* __restrict__ k, int64_t k_sn, int64_t k_sh, int64_t k_st,
+                                 const T16* __restrict__ v, int64_t v_sn, int64_t v_sh, int64_t v_st,
+                                 const float* __restrict__ scales, const T16* __restrict__ cumavg, int use_scaler,
+                                 T16* __restrict__ out, int N, int H, int T_DST, int T_SRC, int P, int k_clamp, int is_causal) {
+    extern __shared__ __align__(16) uint8_t attn_smem[];
+    constexpr int LPR = D / 8;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    T16* Ks = reinterpret_cast<T16*>(attn_smem) + warp * AttnMmaCfg<D>::kWarpElems;
+    T16* Vs = Ks + 32 * AttnMmaCfg<D>::kLd;
+    const int64_t task = (int64_t) blockIdx.x * kAttnWarps + warp;
+    if (task >= (int64_t) N * T_DST * H) return;
+    const int t = (int) (task % T_DST);
+    const int h = (int) ((task / T_DST) % H);
+    const int n = (int) (task / ((int64_t) T_DST * H));
+    const int64_t row = (int64_t) n * T_DST + t;
+    const int sub = lane % LPR;
+    const int g = lane >> 2, tq = lane & 3;
+    const uint4* kb = reinterpret_cast<const uint4*>(k + (int64_t) n * k_sn + (int64_t) h * k_sh) + sub;
+    const uint4* vb = reinterpret_cast<const uint4*>(v + (int64_t) n * v_sn + (int64_t) h * v_sh) + sub;
+    const uint32_t k_sv = (uint32_t) (k_st >> 3), v_sv = (uint32_t) (v_st >> 3);
+    // q as the B operand: column 0 of every n8 tile -> only lanes with g == 0 carry data
+    uint32_t qb[D / 16][2];
+    {
+        const uint32_t* qw = reinterpret_cast<const uint32_t*>(q + (int64_t) n * q_sn + (int64_t) h * q_sh + (int64_t) t * q_st);
+#pragma unroll
+        for (int ks = 0; ks < D / 16; ++ks) {
+            qb[ks][0] = g == 0 ? __ldg(qw + ks * 8 + tq) : 0u;           // dims 16ks + 2tq, +1
+            qb[ks][1] = g == 0 ? __ldg(qw + ks * 8 + 4 + tq) : 0u;       // dims 16ks + 8 + 2tq, +1
+        }
+    }
+    float m_run = -INFINITY, l_run = 0.f;
+    float acc[D / 8][4];
+#pragma unroll
+    for (int nt = 0; nt < D / 8; ++nt)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[nt][i] = 0.f;
+
+    const int nw = P >> 5;
+    const int L = is_causal ? (T_SRC - T_DST + t + 1) : T_SRC;
+    const float s_scale = __fdiv_rn((float) L, (float) P);
+    const uint32_t word = lane < nw ? mask_bits[row * ((int64_t) H * nw) + (int64_t) h * nw + lane] : 0u;
+    const int pc = __popc(word);
+    const int pc_incl = warp_scan_incl_i(pc, lane);
+    const int n_alive = __shfl_sync(kFull, pc_incl, 31);
+    for (int r0 = 0; r0 < n_alive; r0 += 32) {
+        const int slot = r0 + lane;
+        int wi = 0;
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1) {
+            const int vv = __shfl_sync(kFull, pc_incl, wi + step - 1);
+            if (vv <= slot) wi += step;
+        }
+        wi = min(wi, 31);
+        const uint32_t wsel = __shfl_sync(kFull, word, wi);
+        const int before = __shfl_sync(kFull, pc_incl - pc, wi);
+        int wd = 0, ve_i = 0, span_i = 0;
+        if (slot < n_alive) {
+            const int bit = __fns(wsel, 0, slot - before + 1);
+            float vs, ve;
+            pixel_bounds(s_scale, (wi << 5) + bit, vs, ve);
+            span_i = (int) __fsub_rn(ve, vs);
+            ve_i = (int) ve;
+            wd = min(span_i, k_clamp);
+        }
+        const int incl = warp_scan_incl_i(wd, lane);
+        const int excl = incl - wd;
+        const int total = __shfl_sync(kFull, incl, 31);
+        for (int e0 = 0; e0 < total; e0 += 32) {
+            const int cnt = min(32, total - e0);
+            const int e = e0 + lane;
+            int pl = 0;
+#pragma unroll
+            for (int step = 16; step > 0; step >>= 1) {
+                const int vv = __shfl_sync(kFull, incl, pl + step - 1);
+                if (vv <= e) pl += step;
+            }
+            pl = min(pl, 31);
+            const int p_excl = __shfl_sync(kFull, excl, pl);
+            const int p_ve = __shfl_sync(kFull, ve_i, pl);
+            const int p_wd = __shfl_sync(kFull, wd, pl);
+            const int p_span = __shfl_sync(kFull, span_i, pl);
+            int jmine = 0;
+            if (lane < cnt) {
+                const int i = e - p_excl;
+                jmine = p_wd == p_span ? p_ve - 1 - i
+                                       : p_ve - 1 - (int) __fmul_rn((float) i, __fdiv_rn((float) p_span, (float) p_wd));
+            }
+            attn_chunk_mma<T16, D>(Ks, Vs, kb, vb, k_sv, v_sv, jmine, cnt, qb, m_run, l_run, acc, lane);
+        }
+    }
+    // row 0 of the accumulator tiles lives in lanes g == 0: dims 8nt + 2tq, +1
+    if (g == 0) {
+        const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
+        const float* sp = scales + ((((int64_t) n * H + h) * T_DST + t) << 1);
+        const float psc = use_scaler ? sigmoidf_(sp[0]) : 1.0f;
+        const float a = sigmoidf_(sp[1]);
+        T16* orow = out + ((int64_t) n * T_DST + t) * ((int64_t) H * D) + (int64_t) h * D;
+        const T16* arow = cumavg ? cumavg + (((int64_t) n * H + h) * T_DST + t) * D : nullptr;
+#pragma unroll
+        for (int nt = 0; nt < D / 8; ++nt) {
+            const int dd = nt * 8 + 2 * tq;
+            float c0 = acc[nt][0] * inv * psc, c1 = acc[nt][1] * inv * psc;
+            if (arow) {
+                float a0, a1;
+                unpack2<T16>(__ldg(reinterpret_cast<const uint32_t*>(arow + dd)), a0, a1);
+                c0 = c0 * a + (1.0f - a) * a0;
+                c1 = c1 * a + (1.0f - a) * a1;
+            }
+            *reinterpret_cast<uint32_t*>(orow + dd) = pack2<T16>(c0, c1);
+        }
+    }
+}
+
 }  // namespace sea
 
 using namespace sea;
@@ -430,3 +845,44 @@ int sea_sparse_attention_fwd(const void* crow, const void* col, int idx64, int64
 }
 
 }  // extern "C"
+
+extern "C" int sea_sparse_attention_bits_fwd(const uint32_t* mask_bits,
+                                             const void* q, int64_t q_sn, int64_t q_sh, int64_t q_st,
+                                             const void* k, int64_t k_sn, int64_t k_sh, int64_t k_st,
+                                             const void* v, int64_t v_sn, int64_t v_sh, int64_t v_st,
+                                             const float* scales, const void* cumavg, int use_scaler, int dtype, void* out,
+                                             int N, int H, int T_DST, int T_SRC, int D, int P, int k_clamp, int is_causal, void* stream) {
+    SEA_CHECK_ARG(mask_bits && q && k && v && scales && out, "sea_sparse_attention_bits_fwd: null pointer");
+    SEA_CHECK_ARG(N > 0 && H > 0 && T_DST > 0 && T_SRC >= T_DST && k_clamp > 0, "sea_sparse_attention_bits_fwd: bad shape");
+    if (dtype == SEA_DTYPE_F32 || !(D == 32 || D == 64 || D == 128) || (P % 32) != 0 || P > 1024) {
+        set_error("sea_sparse_attention_bits_fwd: unsupported (needs 16-bit activations, D in {32,64,128}, P %% 32 == 0, P <= 1024)");
+        return SEA_ERR_UNSUPPORTED;
+    }
+    SEA_CHECK_ARG(((q_sn | q_sh | q_st | k_sn | k_sh | k_st | v_sn | v_sh | v_st) % 8) == 0 &&
+                  ((((uintptr_t) q) | ((uintptr_t) k) | ((uintptr_t) v) | ((uintptr_t) out) | ((uintptr_t) cumavg)) & 15) == 0,
+                  "sea_sparse_attention_bits_fwd: rows must be 16-byte aligned");
+    const int64_t tasks = (int64_t) N * T_DST * H;
+    const unsigned grid = (unsigned) ((tasks + kAttnWarps - 1) / kAttnWarps);
+    cudaStream_t s = (cudaStream_t) stream;
+    static const bool use_mma = getenv("SEA_ATTN_NO_MMA") == nullptr;     // development switch: CUDA-core variant for A/B timing
+#define SEA_ATTN_BITS(TT, DD)                                                                                                   \
+    do {                                                                                                                        \
+        if (use_mma) {                                                                                                          \
+            auto kern = sparse_attention_bits_mma_kernel<TT, DD>;                                                               \
+            SEA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnMmaCfg<DD>::kSmemBytes), "smem attr"); \
+            kern<<<grid, kAttnWarps * 32, AttnMmaCfg<DD>::kSmemBytes, s>>>(mask_bits, (const TT*) q, q_sn, q_sh, q_st, (const TT*) k, k_sn,  \
+                k_sh, k_st, (const TT*) v, v_sn, v_sh, v_st, scales, (const TT*) cumavg, use_scaler, (TT*) out, N, H, T_DST, T_SRC, P, k_clamp, is_causal); \
+        } else {                                                                                                                \
+            sparse_attention_bits_kernel<TT, DD><<<grid, kAttnWarps * 32, 0, s>>>(mask_bits, (const TT*) q, q_sn, q_sh, q_st, (const TT*) k, k_sn, \
+                k_sh, k_st, (const TT*) v, v_sn, v_sh, v_st, scales, (const TT*) cumavg, use_scaler, (TT*) out, N, H, T_DST, T_SRC, P, k_clamp, is_causal); \
+        }                                                                                                                       \
+    } while (0)
+    if (dtype == SEA_DTYPE_BF16) {
+        if (D == 32) SEA_ATTN_BITS(__nv_bfloat16, 32); else if (D == 64) SEA_ATTN_BITS(__nv_bfloat16, 64); else SEA_ATTN_BITS(__nv_bfloat16, 128);
+    } else {
+        if (D == 32) SEA_ATTN_BITS(__half, 32); else if (D == 64) SEA_ATTN_BITS(__half, 64); else SEA_ATTN_BITS(__half, 128);
+    }
+#undef SEA_ATTN_BITS
+    SEA_CHECK_LAUNCH("sparse_attention_bits_kernel");
+    return SEA_OK;
+}

@@ -378,3 +378,23 @@ def sparse_attention(crow, col, q, k, v, scales, cumavg, use_scaler=True, want_p
               v.data_ptr(), v.stride(0), v.stride(1), v.stride(2), sc.data_ptr(), _p(ca), int(bool(use_scaler)), _dtype_code(q),
               out.data_ptr(), _p(pv), _p(head_ptr), N, H, T_DST, T_SRC, D, _stream())
     return out, pv
+
+
+def sparse_attention_from_bits(bits, q, k, v, scales, cumavg, P: int, k_clamp: int, use_scaler=True, is_causal=True):
+    """a8 + a9-a14 fused: attention driven directly by the top-k bit mask (no CSR tensors are materialised)."""
+    _cuda(bits, q, k, v, scales, cumavg)
+    N, H, T_DST, D = q.shape
+    T_SRC = k.shape[2]
+    q, k, v = _inner_contig(q), _inner_contig(k), _inner_contig(v)
+    out = torch.empty((N, T_DST, H * D), dtype=q.dtype, device=q.device)
+    sc = scales.float().contiguous()
+    ca = None if cumavg is None else cumavg.contiguous()
+    _lib.call('sea_sparse_attention_bits_fwd', bits.data_ptr(), q.data_ptr(), q.stride(0), q.stride(1), q.stride(2),
+              k.data_ptr(), k.stride(0), k.stride(1), k.stride(2), v.data_ptr(), v.stride(0), v.stride(1), v.stride(2),
+              sc.data_ptr(), _p(ca), int(bool(use_scaler)), _dtype_code(q), out.data_ptr(), N, H, T_DST, T_SRC, D, int(P), int(k_clamp),
+              int(bool(is_causal)), _stream())
+    return out
+
+
+def attention_bits_supported(dtype, D: int, P: int) -> bool:
+    return dtype in (torch.bfloat16, torch.float16) and D in (32, 64, 128) and P % 32 == 0 and P <= 1024

@@ -170,6 +170,11 @@ def test_layer_forward_bf16(sea):
     rows_same = torch.from_numpy((mine == b['partial_attention_mask'].numpy()).all(axis=(0, 1, 3)))
     if rows_same.any():
         torch.testing.assert_close(out.context_layer.float().cpu()[:, rows_same], b['context_layer'][:, rows_same], rtol=2e-2, atol=2e-2)
+    # default mode (output_attentions=False): attention runs straight from the bit mask, no CSR tensors
+    mod.output_attentions = False
+    out2 = mod(qd, kd, vd, qd, kd, vd, qd, kd, so.causal_additive_mask(T, torch.bfloat16, N).to(DEV), None, None)
+    assert out2.partial_attention_mask is None and out2.partial_attention_probs is None
+    torch.testing.assert_close(out2.context_layer.float().cpu(), out.context_layer.float().cpu(), rtol=2e-2, atol=2e-2)
 
 
 def test_unsupported_modes_fail_loudly(sea):

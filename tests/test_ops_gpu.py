@@ -244,3 +244,26 @@ def test_fused_sparse_attention_v2_bf16_with_head_ptr(sea, d, idt):
     # the binary-search kernel (no head_ptr) must agree
     out2, pv2 = sea.ops.sparse_attention(crow, col, q.to(DEV), kk.to(DEV), v.to(DEV), scales.to(DEV), avg.to(DEV), True, True)
     torch.testing.assert_close(out.float().cpu(), out2.float().cpu(), rtol=2e-2, atol=1e-2)
+
+
+@pytest.mark.parametrize('N,H,T_DST,T_SRC,P,k,d,causal', [
+    (2, 4, 160, 160, 32, 8, 64, True), (1, 2, 1024, 1024, 32, 4, 64, True),     # second: T/P > k -> clamped, sub-sampled pixels
+    (1, 3, 40, 128, 64, 8, 128, True), (2, 4, 64, 64, 32, 8, 32, False), (1, 32, 70, 70, 256, 64, 64, True),
+])
+def test_attention_from_bits_equals_csr_path(sea, N, H, T_DST, T_SRC, P, k, d, causal):
+    """The bit-mask driven kernel enumerates exactly the entries sea_csr_fill would emit."""
+    g = torch.Generator().manual_seed(P + d)
+    mask = (torch.rand(N, H, T_DST, P, generator=g) < min(1.0, 2.0 * k / P)).float()
+    mask[0, 1, 3] = 0
+    mask[0, 0, 5] = 1               # a head with every pixel alive
+    bits = sea.ops.mask_to_bits(mask.to(DEV))
+    crow, col, Z, hp = sea.ops.csr_from_bits(bits, H, P, k, T_SRC, causal, torch.int32, want_head_ptr=True)
+    q = (torch.randn(N, H, T_DST, d, generator=g) * d ** -0.5).bfloat16().to(DEV)
+    kk = torch.randn(N, H, T_SRC, d, generator=g).bfloat16().to(DEV)
+    v = torch.randn(N, H, T_SRC, d, generator=g).bfloat16().to(DEV)
+    scales = torch.randn(N, H, T_DST, 2, generator=g).to(DEV)
+    avg = torch.randn(N, H, T_DST, d, generator=g).bfloat16().to(DEV)
+    ref, _ = sea.ops.sparse_attention(crow, col, q, kk, v, scales, avg, True, False, head_ptr=hp)
+    out = sea.ops.sparse_attention_from_bits(bits, q, kk, v, scales, avg, P, k, True, causal)
+    torch.testing.assert_close(out.float().cpu(), ref.float().cpu(), rtol=1e-2, atol=1e-2)
+    assert float((out.float() - ref.float()).abs().mean()) < 1e-3
