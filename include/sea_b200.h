@@ -228,7 +228,8 @@ SEA_API int sea_crow_scan(void* crow, int idx64, int N, int T_DST, void* stream)
  * sum p V -> out = ctx*sigmoid(scales[...,1]) + (1-sigmoid(.))*cumavg -> [N, T_DST, H*D].
  * probs_values (nullable, fp32 [N,Z]) receives the scaled probabilities (the reference's
  * partial_attention_probs.values()).  Requires head-major entries inside a row (what a8 emits).
- * cumavg nullable (then out = ctx, layout still [N,T_DST,H*D]).
+ * cumavg nullable (then out = ctx, layout still [N,T_DST,H*D]); its element strides are (avg_sh per (n,h), avg_st per row):
+ * causal running mean [N,H,T_DST,D] -> (T_DST*D, D); the BERT probability-weighted mean [N,H,1,D] -> (D, 0).
  * head_ptr (nullable): the index sea_csr_fill emits; with it and 16-bit activations (D in {32,64,128}) the call runs the
  * warp-per-(row, head) kernel with batched 128-bit gathers, otherwise a CTA-per-row kernel that finds the head
  * segments by binary search.
@@ -237,7 +238,7 @@ SEA_API int sea_sparse_attention_fwd(const void* crow, const void* col, int idx6
                              const void* q, int64_t q_sn, int64_t q_sh, int64_t q_st,
                              const void* k, int64_t k_sn, int64_t k_sh, int64_t k_st,
                              const void* v, int64_t v_sn, int64_t v_sh, int64_t v_st,
-                             const float* scales, const void* cumavg, int use_scaler, int dtype,
+                             const float* scales, const void* cumavg, int64_t avg_sh, int64_t avg_st, int use_scaler, int dtype,
                              void* out, float* probs_values, const int32_t* head_ptr,
                              int N, int H, int T_DST, int T_SRC, int D, void* stream);
 
@@ -248,8 +249,33 @@ SEA_API int sea_sparse_attention_bits_fwd(const uint32_t* mask_bits,
                                           const void* q, int64_t q_sn, int64_t q_sh, int64_t q_st,
                                           const void* k, int64_t k_sn, int64_t k_sh, int64_t k_st,
                                           const void* v, int64_t v_sn, int64_t v_sh, int64_t v_st,
-                                          const float* scales, const void* cumavg, int use_scaler, int dtype, void* out,
+                                          const float* scales, const void* cumavg, int64_t avg_sh, int64_t avg_st, int use_scaler, int dtype, void* out,
                                           int N, int H, int T_DST, int T_SRC, int D, int P, int k_clamp, int is_causal, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Non-causal (BERT) variant, csrc/noncausal.cu.  No padding.
+ * sea_performer_noncausal_fwd: v_for_atten = cat(grid-sampled identity, v) (attention.py:462-502) and the FAVOR+
+ *   softmax-feature Performer with un-prefixed sums (performer-pytorch softmax_kernel / linear_attention):
+ *   ctx [N,H,T,2D] (`dtype`); workspace fp32 >= sea_performer_noncausal_workspace_floats().
+ * sea_conv3x3_cl: Conv2d(C,O,3,padding=1, stride (stride_t,1)) on channels-last [N,Tin,W,C] -> [N,Tout,W,O], input rows
+ *   nearest-upsampled by `up` first (attention.py:209-215); weight fp32 [O,C,3,3].
+ * sea_bert_tail_fwd: bilinear (align_corners=False) resize of [N,Tin,Win,H] to (T,P) (KeepRes, modules.py:42-55) +
+ *   softmax(P) -> probs fp32 [N,H,T,P].
+ * sea_topk_mask_bits_batch: k_flatten_dim='batch' (attention.py:833-837): one top-k group per item over H*T*P keys in
+ *   view(N, H*T*P) order; k_per_item [N] fp32; ties to the lower flat index; bit layout as sea_topk_mask_bits.
+ * sea_bert_avg_fwd: probability-weighted mean of v (attention.py:1209-1219) -> avg [N,H,D] (`dtype`). */
+SEA_API int64_t sea_performer_noncausal_workspace_floats(int N, int H, int T, int D, int F);
+SEA_API int sea_performer_noncausal_fwd(const void* q, int64_t q_sn, int64_t q_sh, int64_t q_st,
+                                        const void* k, int64_t k_sn, int64_t k_sh, int64_t k_st,
+                                        const void* v, int64_t v_sn, int64_t v_sh, int64_t v_st,
+                                        const float* proj, int dtype, void* ctx, float* workspace,
+                                        int N, int H, int T, int D, int F, void* stream);
+SEA_API int sea_conv3x3_cl(const void* x, const float* weight, const float* bias, void* y, int dtype,
+                           int N, int Tin, int Tout, int W, int C, int O, int stride_t, int up, int relu, void* stream);
+SEA_API int sea_bert_tail_fwd(const void* y, int dtype, float* probs, float* scores, int N, int H, int Tin, int Win, int T, int P, void* stream);
+SEA_API int sea_topk_mask_bits_batch(const float* keys, const float* k_per_item, uint32_t* mask_bits, int N, int H, int T, int P, void* stream);
+SEA_API int sea_bert_avg_fwd(const float* probs, const void* v, int64_t v_sn, int64_t v_sh, int64_t v_st, int dtype, void* avg,
+                             int N, int H, int T, int P, int D, void* stream);
 
 #ifdef __cplusplus
 }

@@ -518,3 +518,76 @@ def perlin_forward_causal(sd: Dict[str, torch.Tensor], q, k, v, *, k_top: int, P
     # a14 (:1279-1282)
     buf['context_layer'] = out.permute(0, 2, 1, 3).reshape(N, T, H * d).contiguous()
     return buf
+
+
+# ----------------------------------------------------------------------------- non-causal (BERT) layer
+def v_identity_grid(N: int, H: int, T: int, d: int, valid: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """attention.py:462-495: bilinear grid_sample (align_corners=True) of the d x d identity at x = channel c,
+    y = (rank of the token among the valid tokens) / (count - 1) * (d - 1)  ->  [N,H,T,d]; in closed form the sample
+    is the hat function max(0, 1 - |y - c|)."""
+    if valid is None:
+        valid = torch.ones(N, T)
+    cs = valid.float().cumsum(-1)
+    tot = valid.float().sum(-1, keepdim=True)
+    y_norm = (cs - 1.0) / ((tot - 1.0) + 1e-8) * 2 - 1
+    ypix = (y_norm + 1) / 2 * (d - 1)                                   # align_corners=True un-normalisation
+    c = torch.arange(d, dtype=torch.float32).view(1, 1, d)
+    w = torch.clamp(1.0 - (ypix.view(N, T, 1) - c).abs(), min=0.0)
+    inside = ((ypix >= 0) & (ypix <= d - 1)).view(N, T, 1)             # zero padding outside the grid
+    return (w * inside).view(N, 1, T, d).expand(N, H, T, d).contiguous()
+
+
+def perlin_forward_noncausal(sd: Dict[str, torch.Tensor], q, k, v, *, k_top: int, P: int, k_flatten_dim: str = 'batch',
+                             k_oversample: float = 1.0, partial_attention_scaler: bool = True, sparse: bool = True,
+                             keep_dense: bool = False) -> Dict[str, torch.Tensor]:
+    """attention.py:333-1359 with `causal=False` (BERT), no padding, context_output_method='mix'."""
+    q, k, v = q.float(), k.float(), v.float()
+    N, H, T, d = q.shape
+    buf: Dict[str, torch.Tensor] = {}
+    v_for_atten = torch.cat([v_identity_grid(N, H, T, d), v], dim=-1)                           # :462-502
+    pcl = performer_noncausal(q, k, v_for_atten, sd['performer.projection_matrix'])              # :527-534
+    buf['performer_context_layer'] = pcl
+    t_pred = predictor_enc(torch.cat([pcl, v], dim=-1), sd)                                      # :577-620
+    buf['t_attention_predictor'] = t_pred
+    dec = predictor_dec_row(t_pred, sd, splits=4)                                                # :203-206
+    score = predictor_cnn_bert(dec, sd, P)                                                       # :207-218
+    buf['estimated_attention_score'] = score
+    probs = torch.softmax(score, dim=-1)                                                         # :670-673
+    buf['estimated_attention_probs'] = probs
+    token_length = torch.full((N,), T, dtype=torch.long)
+    mask_m = topk_mask_noncausal(probs, k_top, k_oversample, token_length, k_flatten_dim)        # :833-947
+    buf['partial_attention_mask_before_interp'] = mask_m
+    scales = predictor_dec_scaler(t_pred, sd)
+    buf['estimated_scales'] = scales
+    if sparse:
+        crow, col, Z = resize_from_m_to_t_csr(mask_m, k_top, target_width=T, is_causal=False)    # :1025-1027
+        buf['crow_indices'], buf['col_indices'] = crow, col
+        s = flat_csr_masked_bmm(q, k, crow, col)
+        p = flat_csr_softmax(s, crow, col, H, T)
+        if partial_attention_scaler:
+            p = flat_csr_elmul_rowscale(p, crow, col, torch.sigmoid(scales[..., 0]), T)
+        buf['partial_attention_probs_values'] = p
+        ctx = flat_csr_sdbmm(p, crow, col, v, H)
+        if keep_dense:
+            buf['partial_attention_mask'] = flat_csr_to_dense(crow, col, torch.ones_like(p), T, H)
+    else:
+        fmin = fp_min_for(torch.float32)
+        amask = torch.zeros(N, 1, 1, T)
+        pm = resize_from_m_to_t_dense((1.0 - mask_m) * fmin, fmin, amask, target_width=T, is_causal=False, k=k_top, oversampled=k_oversample)
+        if keep_dense:
+            buf['partial_attention_mask'] = (pm > -1).float()
+        s = q @ k.transpose(-1, -2) + pm
+        p = torch.softmax(s, dim=-1).masked_fill(pm < -1, 0)
+        if partial_attention_scaler:
+            p = p * torch.sigmoid(scales[..., 0:1])
+        ctx = p @ v
+    buf['partial_context_layer_1'] = ctx
+    # :1209-1219: probability-weighted mean of v
+    amask = torch.zeros(N, 1, 1, T)
+    wts = resize_from_m_to_t_dense(probs.mean(-2, keepdim=True), 0.0, amask, target_width=T, is_causal=False)   # [N,H,1,T]
+    avg = (v * wts.transpose(-1, -2)).sum(-2, keepdim=True)
+    buf['average_context_layer'] = avg
+    a = torch.sigmoid(scales[..., 1:2])
+    out = ctx * a + (1 - a) * avg
+    buf['context_layer'] = out.permute(0, 2, 1, 3).reshape(N, T, H * d).contiguous()
+    return buf

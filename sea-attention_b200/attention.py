@@ -211,17 +211,26 @@ class PerlinAttention(nn.Module):
     def _weights_fp32(self):
         f = lambda t: t.detach().float().contiguous()
         enc, dec, scl, cnn = self.attention_predictor_enc, self.attention_predictor_dec_row, self.attention_predictor_dec_scaler, self.attention_predictor_cnn
-        net = cnn[1].module.net
-        return {
+        w = {
             'enc_w': f(enc[0].weight), 'enc_b': f(enc[0].bias), 'enc_ln_w': f(enc[1].weight), 'enc_ln_b': f(enc[1].bias),
             'dec_w': f(dec[0].weight), 'dec_b': f(dec[0].bias), 'scl_w': f(scl[0].weight), 'scl_b': f(scl[0].bias),
-            'cnn_ln_w': f(cnn[0].module.weight), 'cnn_ln_b': f(cnn[0].module.bias),
-            'conv1_w': f(net[0].module.weight), 'conv1_b': f(net[0].module.bias),
-            'conv2_w': f(net[2].module.weight), 'conv2_b': f(net[2].module.bias),
-            'conv3_w': f(net[5].module.weight).reshape(net[5].module.weight.shape[0], -1), 'conv3_b': f(net[5].module.bias),
-            'out_ln_w': f(cnn[2].module.weight), 'out_ln_b': f(cnn[2].module.bias),
-            'proj': f(self.performer.projection_matrix), 'pos': f(self.v_eye_learned_causal).reshape(-1, self.attention_head_size),
+            'proj': f(self.performer.projection_matrix),
         }
+        if self.pconfig.causal:
+            net = cnn[1].module.net
+            w.update({
+                'cnn_ln_w': f(cnn[0].module.weight), 'cnn_ln_b': f(cnn[0].module.bias),
+                'conv1_w': f(net[0].module.weight), 'conv1_b': f(net[0].module.bias),
+                'conv2_w': f(net[2].module.weight), 'conv2_b': f(net[2].module.bias),
+                'conv3_w': f(net[5].module.weight).reshape(net[5].module.weight.shape[0], -1), 'conv3_b': f(net[5].module.bias),
+                'out_ln_w': f(cnn[2].module.weight), 'out_ln_b': f(cnn[2].module.bias),
+                'pos': f(self.v_eye_learned_causal).reshape(-1, self.attention_head_size),
+            })
+        else:
+            net = cnn[0].net
+            w.update({'conv1_w': f(net[0].weight), 'conv1_b': f(net[0].bias), 'conv2_w': f(net[2].weight), 'conv2_b': f(net[2].bias),
+                      'conv3_w': f(net[5].weight), 'conv3_b': f(net[5].bias)})
+        return w
 
     def _shape_consts(self, H, P, T_SRC, T_DST, device):
         key = (H, P, T_SRC, T_DST, self.pconfig.k, self.pconfig.k_oversample, str(device))
@@ -242,8 +251,6 @@ class PerlinAttention(nn.Module):
             raise SeaError('QUERY_SKIPS > 1 (attention.py:598) is not implemented')
         if not q.is_cuda:
             raise SeaError('PerlinAttention (sea-attention_b200) runs on CUDA tensors only; there is no CPU path')
-        if not pc.causal:
-            raise SeaError('non-causal (BERT) PerlinAttention is not implemented yet (SURVEY 8f-3)')
         if pc.use_cache or last_state is not None:
             raise SeaError('use_cache / PerlinAttentionState decoding is not implemented yet (SURVEY 8f-2)')
         if self.training or attention_scores_truth is not None or context_layer_truth is not None:
@@ -253,10 +260,12 @@ class PerlinAttention(nn.Module):
             raise SeaError('only the mlp predictor with the performer backend is implemented')
         if pc.context_output_method != 'mix' or pc.random_lookup or pc.out_add_performer_context:
             raise SeaError("only context_output_method='mix' without random lookup is implemented")
-        if pc.k_flatten_dim != 'causal_batch' or not pc.k_flatten:
-            raise SeaError("causal PerlinAttention needs k_flatten_dim='causal_batch' (perlin_opt.py:227-231)")
         if float(pc.k_oversample) != 1.0:
             raise SeaError('k_oversample != 1.0 is not implemented')
+        if not pc.causal:
+            return self._forward_noncausal(q, k, v, q_for_atten, k_for_atten, v_for_atten, q_for_score, k_for_score, attention_mask)
+        if pc.k_flatten_dim != 'causal_batch' or not pc.k_flatten:
+            raise SeaError("causal PerlinAttention needs k_flatten_dim='causal_batch' (perlin_opt.py:227-231)")
 
         N, H, T, d = q.shape
         assert attention_mask.shape == (N, 1, T, T), f'causal additive mask must be [N,1,T,T], got {tuple(attention_mask.shape)}'
@@ -312,6 +321,59 @@ class PerlinAttention(nn.Module):
             size = (N, T, H * T)
             partial_mask = torch.sparse_csr_tensor(crow, col, torch.ones((N, Z), dtype=torch.float32, device=q.device), size=size)
             partial_probs = torch.sparse_csr_tensor(crow, col, pvals, size=size)
+        return PerlinAttentionOutput(
+            loss=0, context_layer=context, partial_attention_probs=partial_probs, partial_attention_mask=partial_mask,
+            estimated_attention_probs_m=probs, estimated_attention_probs=probs, dense_attention_probs=None,
+            key_for_score=k_for_score, state=None)
+
+    # ------------------------------------------------------------------------------------------------
+    def _forward_noncausal(self, q, k, v, q_for_atten, k_for_atten, v_for_atten, q_for_score, k_for_score, attention_mask):
+        """BERT variant (attention.py with causal=False): eye-grid v_for_atten, FAVOR+ Performer, strided CNN + bilinear
+        resize, 'batch' / 'query' / 'causal_batch' top-k, non-causal CSR, sparse attention, probability-weighted mean mix."""
+        pc = self.pconfig
+        N, H, T, d = q.shape
+        assert attention_mask.shape == (N, 1, 1, T), f'non-causal additive mask must be [N,1,1,T], got {tuple(attention_mask.shape)}'
+        if v_for_atten.data_ptr() != v.data_ptr():
+            raise SeaError('v_for_atten must alias v (LoRA-in-approximation is not implemented)')
+        if self.check_padding and not bool((attention_mask > -1).all()):
+            raise SeaError('padded batches are not implemented yet (SURVEY 8f-3)')
+        P = pc.attention_predictor_length
+        w = self._weights_fp32()
+        S, W = self.attention_predictor_dec_row_splits, P // self.attention_predictor_dec_row_down_scale
+        ctx = ops.performer_noncausal(q_for_atten, k_for_atten, v, w['proj'])
+        cnn_in, scales, _ = ops.predictor_mlp(ctx, v, w, S, W)                      # [N,T,W,4H], no leading LayerNorm
+        y = ops.conv3x3_cl(cnn_in, w['conv1_w'], w['conv1_b'], stride_t=2, relu=True)
+        y = ops.conv3x3_cl(y, w['conv2_w'], w['conv2_b'], relu=True)
+        y = ops.conv3x3_cl(y, w['conv3_w'], w['conv3_b'], up=2, relu=False)       # nearest (2,1) upsample folded into the conv
+        probs, _ = ops.bert_tail(y, T, P)
+        kf = float(pc.k) * float(pc.k_oversample) * P
+        tl_ = torch.full((N,), T, dtype=torch.long, device=q.device)
+        mode = pc.k_flatten_dim if pc.k_flatten else 'query'
+        if mode == 'batch':
+            kpi = torch.clamp_min(torch.round(tl_ * H * (kf / tl_)), 1)                                         # attention.py:837,856,866
+            bits = ops.topk_mask_bits_batch(probs, kpi)
+        elif mode == 'query':
+            kpi = torch.clamp_min(torch.round(kf / tl_), 1)                                                      # :853
+            bits = ops.topk_mask_bits(probs, kpi, 'query')
+        elif mode == 'causal_batch':
+            kpi = torch.clamp_min(torch.round(H * (kf / tl_)), 1).view(N, 1).expand(N, T).reshape(-1)             # :846
+            bits = ops.topk_mask_bits(probs, kpi, 'causal_batch')
+        else:
+            raise SeaError(f"k_flatten_dim='{mode}' is not implemented")
+        avg = ops.bert_avg(probs, v)
+        partial_probs = partial_mask = None
+        if not self.output_attentions and ops.attention_bits_supported(q.dtype, d, P):
+            context = ops.sparse_attention_from_bits(bits, q_for_score, k_for_score, v, scales, avg, P, pc.k,
+                                                     use_scaler=pc.partial_attention_scaler, is_causal=False)
+        else:
+            # exact-size CSR (one host read of the nnz, like the reference's own .item(), causal_resize_m_to_t.py:667)
+            crow, col, Z, head_ptr = ops.csr_from_bits(bits, H, P, pc.k, T, is_causal=False, index_dtype=torch.int32, want_head_ptr=True)
+            context, pvals = ops.sparse_attention(crow, col, q_for_score, k_for_score, v, scales, avg,
+                                                  use_scaler=pc.partial_attention_scaler, want_probs=self.output_attentions, head_ptr=head_ptr)
+            if self.output_attentions:
+                size = (N, T, H * T)
+                partial_mask = torch.sparse_csr_tensor(crow, col, torch.ones((N, Z), dtype=torch.float32, device=q.device), size=size)
+                partial_probs = torch.sparse_csr_tensor(crow, col, pvals, size=size)
         return PerlinAttentionOutput(
             loss=0, context_layer=context, partial_attention_probs=partial_probs, partial_attention_mask=partial_mask,
             estimated_attention_probs_m=probs, estimated_attention_probs=probs, dense_attention_probs=None,

@@ -154,8 +154,8 @@ predictor_mlp_kernel(const T* __restrict__ ctx, const T* __restrict__ v, int64_t
         }
     }
     __syncthreads();
-    // first CNN LayerNorm over W for every (tok, s) row; in place
-    {
+    // first CNN LayerNorm over W for every (tok, s) row; in place (the BERT predictor has none: null weights skip it)
+    if (cnn_ln_w != nullptr) {
         const int lane = tid & 31, wid = tid >> 5;
         for (int row = wid; row < TOK * S; row += kMlpThreads / 32) {
             float* r = ds + (row / S) * ldd + (row % S) * W;
@@ -362,7 +362,7 @@ int sea_predictor_mlp_fwd(const void* ctx, const void* v, int64_t v_sn, int64_t 
                           const float* dec_w, const float* dec_b, const float* cnn_ln_w, const float* cnn_ln_b,
                           const float* scl_w, const float* scl_b, void* cnn_in, float* scales, void* t_pred,
                           int N, int H, int T, int D, int S, int W, void* stream) {
-    SEA_CHECK_ARG(ctx && v && enc_w && enc_b && enc_ln_w && enc_ln_b && dec_w && dec_b && cnn_ln_w && cnn_ln_b && scl_w && scl_b && cnn_in && scales,
+    SEA_CHECK_ARG(ctx && v && enc_w && enc_b && enc_ln_w && enc_ln_b && dec_w && dec_b && scl_w && scl_b && cnn_in && scales && (!cnn_ln_w == !cnn_ln_b),
                   "sea_predictor_mlp_fwd: null pointer");
     SEA_CHECK_ARG(N > 0 && H > 0 && T > 0 && D > 0 && S > 0 && W > 0, "sea_predictor_mlp_fwd: bad shape");
     MlpDims dm;

@@ -110,7 +110,7 @@ sparse_attention_kernel(const IdxT* __restrict__ crow, const IdxT* __restrict__ 
                         const T* __restrict__ q, int64_t q_sn, int64_t q_sh, int64_t q_st,
                         const T* __restrict__ k, int64_t k_sn, int64_t k_sh, int64_t k_st,
                         const T* __restrict__ v, int64_t v_sn, int64_t v_sh, int64_t v_st,
-                        const float* __restrict__ scales, const T* __restrict__ cumavg, int use_scaler,
+                        const float* __restrict__ scales, const T* __restrict__ cumavg, int64_t avg_sh, int64_t avg_st, int use_scaler,
                         T* __restrict__ out, float* __restrict__ probs_values,
                         int N, int H, int T_DST, int T_SRC, int D) {
     extern __shared__ __align__(16) float smem[];
@@ -185,7 +185,7 @@ sparse_attention_kernel(const IdxT* __restrict__ crow, const IdxT* __restrict__ 
         const float psc = use_scaler ? sigmoidf_(sp[0]) : 1.0f;
         const float a = sigmoidf_(sp[1]);
         T* orow = out + ((int64_t) n * T_DST + t) * ((int64_t) H * D) + (int64_t) h * D;
-        const T* arow = cumavg ? cumavg + (((int64_t) n * H + h) * T_DST + t) * D : nullptr;
+        const T* arow = cumavg ? cumavg + ((int64_t) n * H + h) * avg_sh + (int64_t) t * avg_st : nullptr;
 #pragma unroll
         for (int i = 0; i < kMaxPairs; ++i) {
             const int d = 2 * lane + 64 * i;
@@ -250,7 +250,7 @@ sparse_attention_v2_kernel(const IdxT* __restrict__ col, int64_t Z, const int32_
                            const T16* __restrict__ q, int64_t q_sn, int64_t q_sh, int64_t q_st,
                            const T16* __restrict__ k, int64_t k_sn, int64_t k_sh, int64_t k_st,
                            const T16* __restrict__ v, int64_t v_sn, int64_t v_sh, int64_t v_st,
-                           const float* __restrict__ scales, const T16* __restrict__ cumavg, int use_scaler,
+                           const float* __restrict__ scales, const T16* __restrict__ cumavg, int64_t avg_sh, int64_t avg_st, int use_scaler,
                            T16* __restrict__ out, float* __restrict__ probs_values,
                            int N, int H, int T_DST, int T_SRC) {
     constexpr int LPR = D / 8;          // lanes per K/V row
@@ -358,7 +358,7 @@ sparse_attention_v2_kernel(const IdxT* __restrict__ col, int64_t Z, const int32_
 #pragma unroll
         for (int c = 0; c < 8; ++c) o8[c] = acc[c] * inv * psc;
         if (cumavg != nullptr) {
-            const uint4 au = __ldg(reinterpret_cast<const uint4*>(cumavg + (((int64_t) n * H + h) * T_DST + t) * D) + sub);
+            const uint4 au = __ldg(reinterpret_cast<const uint4*>(cumavg + ((int64_t) n * H + h) * avg_sh + (int64_t) t * avg_st) + sub);
             float af[8];
             unpack8<T16>(au, af);
 #pragma unroll
@@ -391,7 +391,7 @@ sparse_attention_bits_kernel(const uint32_t* __restrict__ mask_bits,
                              const T16* __restrict__ q, int64_t q_sn, int64_t q_sh, int64_t q_st,
                              const T16* __restrict__ k, int64_t k_sn, int64_t k_sh, int64_t k_st,
                              const T16* __restrict__ v, int64_t v_sn, int64_t v_sh, int64_t v_st,
-                             const float* __restrict__ scales, const T16* __restrict__ cumavg, int use_scaler,
+                             const float* __restrict__ scales, const T16* __restrict__ cumavg, int64_t avg_sh, int64_t avg_st, int use_scaler,
                              T16* __restrict__ out, int N, int H, int T_DST, int T_SRC, int P, int k_clamp, int is_causal) {
     constexpr int LPR = D / 8, EPI = 32 / LPR, NI = 32 / EPI;
     const int lane = threadIdx.x & 31;
@@ -532,7 +532,7 @@ sparse_attention_bits_kernel(const uint32_t* __restrict__ mask_bits,
 #pragma unroll
         for (int c = 0; c < 8; ++c) o8[c] = acc[c] * inv * psc;
         if (cumavg != nullptr) {
-            const uint4 au = __ldg(reinterpret_cast<const uint4*>(cumavg + (((int64_t) n * H + h) * T_DST + t) * D) + sub);
+            const uint4 au = __ldg(reinterpret_cast<const uint4*>(cumavg + ((int64_t) n * H + h) * avg_sh + (int64_t) t * avg_st) + sub);
             float af[8];
             unpack8<T16>(au, af);
 #pragma unroll
@@ -678,7 +678,7 @@ sparse_attention_bits_mma_kernel(const uint32_t* __restrict__ mask_bits,
                                  const T16* __restrict__ q, int64_t q_sn, int64_t q_sh, int64_t q_st,
                                  const T16* __restrict__ k, int64_t k_sn, int64_t k_sh, int64_t k_st,
                                  const T16* __restrict__ v, int64_t v_sn, int64_t v_sh, int64_t v_st,
-                                 const float* __restrict__ scales, const T16* __restrict__ cumavg, int use_scaler,
+                                 const float* __restrict__ scales, const T16* __restrict__ cumavg, int64_t avg_sh, int64_t avg_st, int use_scaler,
                                  T16* __restrict__ out, int N, int H, int T_DST, int T_SRC, int P, int k_clamp, int is_causal) {
     extern __shared__ __align__(16) uint8_t attn_smem[];
     constexpr int LPR = D / 8;
@@ -773,7 +773,7 @@ sparse_attention_bits_mma_kernel(const uint32_t* __restrict__ mask_bits,
         const float psc = use_scaler ? sigmoidf_(sp[0]) : 1.0f;
         const float a = sigmoidf_(sp[1]);
         T16* orow = out + ((int64_t) n * T_DST + t) * ((int64_t) H * D) + (int64_t) h * D;
-        const T16* arow = cumavg ? cumavg + (((int64_t) n * H + h) * T_DST + t) * D : nullptr;
+        const T16* arow = cumavg ? cumavg + ((int64_t) n * H + h) * avg_sh + (int64_t) t * avg_st : nullptr;
 #pragma unroll
         for (int nt = 0; nt < D / 8; ++nt) {
             const int dd = nt * 8 + 2 * tq;
@@ -799,7 +799,7 @@ int sea_sparse_attention_fwd(const void* crow, const void* col, int idx64, int64
                              const void* q, int64_t q_sn, int64_t q_sh, int64_t q_st,
                              const void* k, int64_t k_sn, int64_t k_sh, int64_t k_st,
                              const void* v, int64_t v_sn, int64_t v_sh, int64_t v_st,
-                             const float* scales, const void* cumavg, int use_scaler, int dtype, void* out,
+                             const float* scales, const void* cumavg, int64_t avg_sh, int64_t avg_st, int use_scaler, int dtype, void* out,
                              float* probs_values, const int32_t* head_ptr, int N, int H, int T_DST, int T_SRC, int D, void* stream) {
     SEA_CHECK_ARG(crow && (col || Z == 0) && q && k && v && scales && out, "sea_sparse_attention_fwd: null pointer");
     SEA_CHECK_ARG(N > 0 && H > 0 && T_DST > 0 && T_SRC >= T_DST && D > 0, "sea_sparse_attention_fwd: bad shape");
@@ -816,7 +816,7 @@ int sea_sparse_attention_fwd(const void* crow, const void* col, int idx64, int64
 #define SEA_ATTN_V2(TT, II, DD)                                                                                              \
         sparse_attention_v2_kernel<TT, II, DD><<<grid, kAttnWarps * 32, 0, s>>>(                                             \
             (const II*) col, Z, head_ptr, (const TT*) q, q_sn, q_sh, q_st, (const TT*) k, k_sn, k_sh, k_st, (const TT*) v, v_sn, \
-            v_sh, v_st, scales, (const TT*) cumavg, use_scaler, (TT*) out, probs_values, N, H, T_DST, T_SRC)
+            v_sh, v_st, scales, (const TT*) cumavg, avg_sh, avg_st, use_scaler, (TT*) out, probs_values, N, H, T_DST, T_SRC)
 #define SEA_ATTN_V2_D(TT, II)                                                  \
         do {                                                                   \
             if (D == 32) SEA_ATTN_V2(TT, II, 32);                              \
@@ -837,7 +837,7 @@ int sea_sparse_attention_fwd(const void* crow, const void* col, int idx64, int64
         SEA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem), "smem attr");
         kern<<<(unsigned) ((int64_t) N * T_DST), kAttnWarps * 32, smem, (cudaStream_t) stream>>>(
             (const I*) crow, (const I*) col, Z, (const T_*) q, q_sn, q_sh, q_st, (const T_*) k, k_sn, k_sh, k_st,
-            (const T_*) v, v_sn, v_sh, v_st, scales, (const T_*) cumavg, use_scaler, (T_*) out, probs_values,
+            (const T_*) v, v_sn, v_sh, v_st, scales, (const T_*) cumavg, avg_sh, avg_st, use_scaler, (T_*) out, probs_values,
             N, H, T_DST, T_SRC, D);
         SEA_CHECK_LAUNCH("sparse_attention_kernel");
     }));
@@ -850,7 +850,7 @@ extern "C" int sea_sparse_attention_bits_fwd(const uint32_t* mask_bits,
                                              const void* q, int64_t q_sn, int64_t q_sh, int64_t q_st,
                                              const void* k, int64_t k_sn, int64_t k_sh, int64_t k_st,
                                              const void* v, int64_t v_sn, int64_t v_sh, int64_t v_st,
-                                             const float* scales, const void* cumavg, int use_scaler, int dtype, void* out,
+                                             const float* scales, const void* cumavg, int64_t avg_sh, int64_t avg_st, int use_scaler, int dtype, void* out,
                                              int N, int H, int T_DST, int T_SRC, int D, int P, int k_clamp, int is_causal, void* stream) {
     SEA_CHECK_ARG(mask_bits && q && k && v && scales && out, "sea_sparse_attention_bits_fwd: null pointer");
     SEA_CHECK_ARG(N > 0 && H > 0 && T_DST > 0 && T_SRC >= T_DST && k_clamp > 0, "sea_sparse_attention_bits_fwd: bad shape");
@@ -871,10 +871,10 @@ extern "C" int sea_sparse_attention_bits_fwd(const uint32_t* mask_bits,
             auto kern = sparse_attention_bits_mma_kernel<TT, DD>;                                                               \
             SEA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnMmaCfg<DD>::kSmemBytes), "smem attr"); \
             kern<<<grid, kAttnWarps * 32, AttnMmaCfg<DD>::kSmemBytes, s>>>(mask_bits, (const TT*) q, q_sn, q_sh, q_st, (const TT*) k, k_sn,  \
-                k_sh, k_st, (const TT*) v, v_sn, v_sh, v_st, scales, (const TT*) cumavg, use_scaler, (TT*) out, N, H, T_DST, T_SRC, P, k_clamp, is_causal); \
+                k_sh, k_st, (const TT*) v, v_sn, v_sh, v_st, scales, (const TT*) cumavg, avg_sh, avg_st, use_scaler, (TT*) out, N, H, T_DST, T_SRC, P, k_clamp, is_causal); \
         } else {                                                                                                                \
             sparse_attention_bits_kernel<TT, DD><<<grid, kAttnWarps * 32, 0, s>>>(mask_bits, (const TT*) q, q_sn, q_sh, q_st, (const TT*) k, k_sn, \
-                k_sh, k_st, (const TT*) v, v_sn, v_sh, v_st, scales, (const TT*) cumavg, use_scaler, (TT*) out, N, H, T_DST, T_SRC, P, k_clamp, is_causal); \
+                k_sh, k_st, (const TT*) v, v_sn, v_sh, v_st, scales, (const TT*) cumavg, avg_sh, avg_st, use_scaler, (TT*) out, N, H, T_DST, T_SRC, P, k_clamp, is_causal); \
         }                                                                                                                       \
     } while (0)
     if (dtype == SEA_DTYPE_BF16) {

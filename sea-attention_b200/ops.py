@@ -278,7 +278,7 @@ def predictor_mlp(ctx, v, w, S: int, W: int, want_t_pred=False, force_simt=False
     cnn_in = torch.empty((N, T, W, H * S), dtype=ctx.dtype, device=ctx.device)
     scales = torch.empty((N, H, T, 2), dtype=torch.float32, device=ctx.device)
     lib = _lib.load()
-    if (not want_t_pred and not force_simt and ctx.is_contiguous()
+    if (not want_t_pred and not force_simt and ctx.is_contiguous() and w.get('cnn_ln_w') is not None
             and lib.sea_predictor_mlp_umma_supported(_DTYPES.get(ctx.dtype, -1), H, D, S, W)
             and v.stride(0) % 8 == 0 and v.stride(1) % 8 == 0 and v.stride(2) % 8 == 0):
         ws = torch.empty((lib.sea_predictor_mlp_umma_workspace_bytes(),), dtype=torch.uint8, device=ctx.device)
@@ -291,7 +291,7 @@ def predictor_mlp(ctx, v, w, S: int, W: int, want_t_pred=False, force_simt=False
     t_pred = torch.empty((N, H, T, D2), dtype=ctx.dtype, device=ctx.device) if want_t_pred else None
     _lib.call('sea_predictor_mlp_fwd', ctx.data_ptr(), v.data_ptr(), v.stride(0), v.stride(1), v.stride(2), _dtype_code(ctx),
               w['enc_w'].data_ptr(), w['enc_b'].data_ptr(), w['enc_ln_w'].data_ptr(), w['enc_ln_b'].data_ptr(),
-              w['dec_w'].data_ptr(), w['dec_b'].data_ptr(), w['cnn_ln_w'].data_ptr(), w['cnn_ln_b'].data_ptr(),
+              w['dec_w'].data_ptr(), w['dec_b'].data_ptr(), _p(w.get('cnn_ln_w')), _p(w.get('cnn_ln_b')),
               w['scl_w'].data_ptr(), w['scl_b'].data_ptr(), cnn_in.data_ptr(), scales.data_ptr(), _p(t_pred),
               N, H, T, D, S, W, _stream())
     return cnn_in, scales, t_pred
@@ -362,6 +362,18 @@ def predictor_tail(x, weight, bias, ln_w, ln_b, P: int, want_scores=False):
     return probs, scores
 
 
+def _avg_arg(avg, N, H, T_DST, D):
+    """The mix-in average: per-row causal running mean [N,H,T_DST,D] or the BERT per-head mean [N,H,1,D] / [N,H,D]."""
+    if avg is None:
+        return None, 0, 0
+    a = avg.contiguous()
+    if a.numel() == N * H * T_DST * D and T_DST > 1:
+        return a, T_DST * D, D
+    if a.numel() == N * H * D:
+        return a, D, 0
+    raise SeaError(f'average context has unexpected shape {tuple(avg.shape)}')
+
+
 def sparse_attention(crow, col, q, k, v, scales, cumavg, use_scaler=True, want_probs=False, head_ptr=None):
     """a9-a14 fused -> context [N,T_DST,H*D] (dtype of q) and, when asked, the probabilities [N,Z] fp32."""
     _cuda(crow, col, q, k, v, scales, cumavg)
@@ -372,10 +384,10 @@ def sparse_attention(crow, col, q, k, v, scales, cumavg, use_scaler=True, want_p
     out = torch.empty((N, T_DST, H * D), dtype=q.dtype, device=q.device)
     pv = torch.zeros((N, Z), dtype=torch.float32, device=q.device) if want_probs else None
     sc = scales.float().contiguous()
-    ca = None if cumavg is None else cumavg.contiguous()
+    ca, avg_sh, avg_st = _avg_arg(cumavg, N, H, T_DST, D)
     _lib.call('sea_sparse_attention_fwd', crow.data_ptr(), col.data_ptr(), _idx64(crow, col), Z,
               q.data_ptr(), q.stride(0), q.stride(1), q.stride(2), k.data_ptr(), k.stride(0), k.stride(1), k.stride(2),
-              v.data_ptr(), v.stride(0), v.stride(1), v.stride(2), sc.data_ptr(), _p(ca), int(bool(use_scaler)), _dtype_code(q),
+              v.data_ptr(), v.stride(0), v.stride(1), v.stride(2), sc.data_ptr(), _p(ca), avg_sh, avg_st, int(bool(use_scaler)), _dtype_code(q),
               out.data_ptr(), _p(pv), _p(head_ptr), N, H, T_DST, T_SRC, D, _stream())
     return out, pv
 
@@ -388,13 +400,74 @@ def sparse_attention_from_bits(bits, q, k, v, scales, cumavg, P: int, k_clamp: i
     q, k, v = _inner_contig(q), _inner_contig(k), _inner_contig(v)
     out = torch.empty((N, T_DST, H * D), dtype=q.dtype, device=q.device)
     sc = scales.float().contiguous()
-    ca = None if cumavg is None else cumavg.contiguous()
+    ca, avg_sh, avg_st = _avg_arg(cumavg, N, H, T_DST, D)
     _lib.call('sea_sparse_attention_bits_fwd', bits.data_ptr(), q.data_ptr(), q.stride(0), q.stride(1), q.stride(2),
               k.data_ptr(), k.stride(0), k.stride(1), k.stride(2), v.data_ptr(), v.stride(0), v.stride(1), v.stride(2),
-              sc.data_ptr(), _p(ca), int(bool(use_scaler)), _dtype_code(q), out.data_ptr(), N, H, T_DST, T_SRC, D, int(P), int(k_clamp),
+              sc.data_ptr(), _p(ca), avg_sh, avg_st, int(bool(use_scaler)), _dtype_code(q), out.data_ptr(), N, H, T_DST, T_SRC, D, int(P), int(k_clamp),
               int(bool(is_causal)), _stream())
     return out
 
 
 def attention_bits_supported(dtype, D: int, P: int) -> bool:
     return dtype in (torch.bfloat16, torch.float16) and D in (32, 64, 128) and P % 32 == 0 and P <= 1024
+
+
+# --------------------------------------------------------------------------------------------- non-causal (BERT)
+def performer_noncausal(q, k, v, proj):
+    """a2'+a3': cat(grid-sampled identity, v) + FAVOR+ Performer -> ctx [N,H,T,2D]."""
+    _cuda(q, k, v, proj)
+    N, H, T, D = q.shape
+    F = proj.shape[0]
+    q, k, v = _inner_contig(q), _inner_contig(k), _inner_contig(v)
+    pj = proj.float().contiguous()
+    ctx = torch.empty((N, H, T, 2 * D), dtype=q.dtype, device=q.device)
+    ws = torch.empty((_lib.load().sea_performer_noncausal_workspace_floats(N, H, T, D, F),), dtype=torch.float32, device=q.device)
+    _lib.call('sea_performer_noncausal_fwd', q.data_ptr(), q.stride(0), q.stride(1), q.stride(2), k.data_ptr(), k.stride(0), k.stride(1),
+              k.stride(2), v.data_ptr(), v.stride(0), v.stride(1), v.stride(2), pj.data_ptr(), _dtype_code(q), ctx.data_ptr(), ws.data_ptr(),
+              N, H, T, D, F, _stream())
+    return ctx
+
+
+def conv3x3_cl(x, weight, bias, stride_t=1, up=1, relu=True):
+    """Conv2d(C,O,3,padding=1,stride=(stride_t,1)) on channels-last x [N,Tin,W,C] (rows nearest-upsampled by `up` first)."""
+    _cuda(x, weight, bias)
+    N, Tin, W, C = x.shape
+    O = weight.shape[0]
+    Tout = (Tin * up + 2 - 3) // stride_t + 1
+    y = torch.empty((N, Tout, W, O), dtype=x.dtype, device=x.device)
+    _lib.call('sea_conv3x3_cl', x.data_ptr(), weight.data_ptr(), bias.data_ptr(), y.data_ptr(), _dtype_code(x), N, Tin, Tout, W, C, O,
+              int(stride_t), int(up), int(bool(relu)), _stream())
+    return y
+
+
+def bert_tail(y, T: int, P: int, want_scores=False):
+    """bilinear resize of channels-last y [N,Tin,Win,H] to (T,P) + softmax(P) -> probs fp32 [N,H,T,P]."""
+    _cuda(y)
+    N, Tin, Win, H = y.shape
+    probs = torch.empty((N, H, T, P), dtype=torch.float32, device=y.device)
+    scores = torch.empty_like(probs) if want_scores else None
+    _lib.call('sea_bert_tail_fwd', y.data_ptr(), _dtype_code(y), probs.data_ptr(), _p(scores), N, H, Tin, Win, T, P, _stream())
+    return probs, scores
+
+
+def topk_mask_bits_batch(probs, k_per_item):
+    """k_flatten_dim='batch' top-k: one group per item over the H*T*P keys (flat order of view(N, H*T*P))."""
+    _cuda(probs, k_per_item)
+    N, H, T, P = probs.shape
+    pr = probs.float().contiguous()
+    kp = k_per_item.reshape(-1).float().contiguous()
+    bits = torch.empty((N, T, (H * P + 31) // 32), dtype=torch.int32, device=probs.device)
+    _lib.call('sea_topk_mask_bits_batch', pr.data_ptr(), kp.data_ptr(), bits.data_ptr(), N, H, T, P, _stream())
+    return bits
+
+
+def bert_avg(probs, v):
+    """a13': probability-weighted mean of v -> [N,H,1,D] (dtype of v)."""
+    _cuda(probs, v)
+    N, H, T, P = probs.shape
+    D = v.shape[-1]
+    v = _inner_contig(v)
+    avg = torch.empty((N, H, 1, D), dtype=v.dtype, device=v.device)
+    _lib.call('sea_bert_avg_fwd', probs.contiguous().data_ptr(), v.data_ptr(), v.stride(0), v.stride(1), v.stride(2), _dtype_code(v), avg.data_ptr(),
+              N, H, T, P, D, _stream())
+    return avg

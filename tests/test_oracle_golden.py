@@ -99,3 +99,24 @@ def test_dense_resize_matches_reference():
     pm = so.resize_from_m_to_t_dense((1 - alive) * fmin, fmin, cm, T, True, m['k'], 1.0).masked_fill(cm < -1, fmin)
     ref = _bits(g, 'dense.partial_attention_mask_alive', (1, H, T, T))
     assert np.array_equal((pm > -1).numpy().astype(np.uint8), ref)
+
+
+def test_bert_layer_oracle_matches_reference():
+    """Non-causal (BERT, k_flatten_dim='batch') oracle forward vs the reference's dense and Triton paths."""
+    g, m, sd = golden_layer('layer_bert_h4_t64')
+    H, T, P, d = m['H'], m['T'], m['P'], m['d']
+    q, k, v = (torch.from_numpy(g[x]) for x in 'qkv')
+    for sparse in (False, True):
+        b = so.perlin_forward_noncausal(sd, q, k, v, k_top=m['k'], P=P, sparse=sparse, keep_dense=True)
+        for key in ['performer_context_layer', 't_attention_predictor', 'estimated_attention_score', 'estimated_attention_probs',
+                    'estimated_scales', 'average_context_layer', 'partial_context_layer_1']:
+            torch.testing.assert_close(b[key], torch.from_numpy(g['dense.' + key]), rtol=1e-3, atol=2e-5, msg=key)
+        alive = _bits(g, 'dense.mask_before_interp_alive', (1, H, T, P))
+        assert np.array_equal(alive, b['partial_attention_mask_before_interp'].numpy().astype(np.uint8))
+        if sparse:
+            assert np.array_equal(g['sparse.crow'], b['crow_indices'].numpy())
+            assert np.array_equal(g['sparse.col'].astype(np.int64), b['col_indices'].numpy())
+            torch.testing.assert_close(b['context_layer'], torch.from_numpy(g['sparse.context_layer']), rtol=1e-3, atol=2e-5)
+        else:
+            assert np.array_equal(_bits(g, 'dense.partial_attention_mask_alive', (1, H, T, T)), b['partial_attention_mask'].numpy().astype(np.uint8))
+            torch.testing.assert_close(b['context_layer'], torch.from_numpy(g['dense.partial_context_layer']), rtol=1e-3, atol=2e-5)
