@@ -4,10 +4,11 @@
 //            slice of the channels-last CNN input [N,T,W,C=2H] is one contiguous block of global memory
 //   GEMM1  : [128 x 3D] (ctx[2D] | v[D], three 64-wide K atoms fetched by three TMA boxes -- the torch.cat of
 //            attention.py:577-590 never exists) x enc_w^T [3D x 2D]        -> TMEM acc1 [128 x 128]
-//   epi 1  : + bias, LayerNorm(2D), GELU(erf)  (thread = token, fully thread-local)  -> bf16 A2 tile in smem,
+//   epi 1  : + bias, LayerNorm(2D), GELU(erf)  (16 warps: 4 threads per token, 32 columns each, statistics combined
+//            through shared memory)  -> bf16 A2 tile in smem,
 //            written directly in the SWIZZLE_128B K-major layout tcgen05 reads
 //   GEMM2  : A2 [128 x 2D] x [dec_row weight ; scaler weight ; 0-pad]^T [2D x (S*W + 16)]     -> TMEM acc2
-//   epi 2  : + bias, ChannelSplit, first CNN LayerNorm(W) (thread-local per split), scales -> global fp32,
+//   epi 2  : + bias, ChannelSplit, first CNN LayerNorm(W) per split (4 threads per token), scales -> global fp32,
 //            CNN input -> bf16 staged in smem as [tl][w][c = 2h+s] and copied out with coalesced 16-byte stores
 // Reference: attention.py:190-196, 242-245, 267, 289-291, 599-625.   Shapes: D = 64, S = 2, H | 128, S*W in {32,64,128}.
 #include "common.cuh"
@@ -16,7 +17,9 @@
 namespace sea {
 namespace {
 
-constexpr int kMlpTcThreads = 192;
+constexpr int kMlpEpiWarps = 16;                          // 4 TMEM lane quarters x 4 column parts
+constexpr int kMlpEpiThreads = kMlpEpiWarps * 32;
+constexpr int kMlpTcThreads = 64 + kMlpEpiThreads;
 constexpr int kD = 64, kD2 = 128, kD3 = 192;
 constexpr int kTile = 128 * 128;   // one K atom of 128 rows (bytes)
 
@@ -28,7 +31,8 @@ struct MlpSmem {
     static constexpr int kA2 = kA1 + 2 * 3 * kTile;        // 2 atoms; aliased by the output staging (32 KB)
     static constexpr int kPar = kA2 + 2 * kTile;           // fp32 parameters
     static constexpr int kParFloats = 3 * 128 + 144 + 2 * 128;
-    static constexpr int kBar = kPar + kParFloats * 4;
+    static constexpr int kRed = kPar + kParFloats * 4;     // cross-warp LayerNorm partials: [4 parts][128 rows] float4
+    static constexpr int kBar = kRed + 4 * 128 * 16;
     static constexpr int kTotal = kBar + 128 + 1024;
 };
 
@@ -47,7 +51,7 @@ __global__ void pack_mlp_weights_kernel(const float* __restrict__ enc_w, const f
 
 __device__ __forceinline__ float gelu_erf_(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
-__global__ void __launch_bounds__(kMlpTcThreads, 1)
+__global__ void __maxnreg__(96)
 mlp_umma_kernel(const __grid_constant__ CUtensorMap tmap_ctx, const __grid_constant__ CUtensorMap tmap_v,
                 const __grid_constant__ CUtensorMap tmap_w1, const __grid_constant__ CUtensorMap tmap_w2,
                 const float* __restrict__ enc_b, const float* __restrict__ enc_ln_w, const float* __restrict__ enc_ln_b,
@@ -78,7 +82,7 @@ mlp_umma_kernel(const __grid_constant__ CUtensorMap tmap_ctx, const __grid_const
         umma::prefetch_tensormap(&tmap_ctx); umma::prefetch_tensormap(&tmap_v);
         umma::prefetch_tensormap(&tmap_w1); umma::prefetch_tensormap(&tmap_w2);
         for (int b = 0; b < 2; ++b) { umma::mbar_init(&full1[b], 1); umma::mbar_init(&empty1[b], 1); }
-        umma::mbar_init(acc1_full, 1); umma::mbar_init(a2_full, 128); umma::mbar_init(acc2_full, 1); umma::mbar_init(wbar, 1);
+        umma::mbar_init(acc1_full, 1); umma::mbar_init(a2_full, kMlpEpiThreads); umma::mbar_init(acc2_full, 1); umma::mbar_init(wbar, 1);
         umma::fence_barrier_init();
     }
     if (warp == 1) umma::tmem_alloc(tmem_ptr, 512);
@@ -142,49 +146,56 @@ mlp_umma_kernel(const __grid_constant__ CUtensorMap tmap_ctx, const __grid_const
             }
         }
     } else {
-        const int q = warp & 3;
+        // 16 epilogue warps: warp id % 4 fixes the TMEM lane quarter the hardware lets a warp read; the four warps of a
+        // quarter split the columns, and the LayerNorm statistics of a token are combined through shared memory.
+        const int q = warp & 3, cp = (warp - 2) >> 2;
         const int row = q * 32 + lane;           // token row r = h*TT + tl
         const int h = row / TT, tl = row % TT;
         const int et = threadIdx.x - 64;
         uint8_t* a2s = smem + MlpSmem::kA2;
+        float4* red = reinterpret_cast<float4*>(smem + MlpSmem::kRed);
         uint32_t tphase = 0;
         const uint32_t lane_addr = (uint32_t) (q * 32) << 16;
+        const int W4 = W >> 2;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int n = tile / tblocks, t0 = (tile % tblocks) * TT;
             // ---------------- epilogue 1: bias + LayerNorm(128) + GELU -> A2 (bf16, swizzled K-major) ----------------
             umma::mbar_wait(acc1_full, tphase);
             umma::tc_fence_after();
-            float x[128];
-#pragma unroll
-            for (int c0 = 0; c0 < 128; c0 += 32) {
+            float x[32];
+            {
                 uint32_t r[32];
-                umma::tmem_ld_32x32(acc1 + lane_addr + (uint32_t) c0, r);
+                umma::tmem_ld_32x32(acc1 + lane_addr + (uint32_t) (cp * 32), r);
                 umma::tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 32; ++i) x[c0 + i] = __uint_as_float(r[i]) + s_enc_b[c0 + i];
+                for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(r[i]) + s_enc_b[cp * 32 + i];
             }
             float s = 0.f;
 #pragma unroll
-            for (int i = 0; i < 128; ++i) s += x[i];
-            const float mean = s * (1.0f / 128.0f);
+            for (int i = 0; i < 32; ++i) s += x[i];
+            red[cp * 128 + row].x = s;
+            asm volatile("bar.sync 1, 512;" ::: "memory");
+            const float mean = (red[row].x + red[128 + row].x + red[256 + row].x + red[384 + row].x) * (1.0f / 128.0f);
             float vq = 0.f;
 #pragma unroll
-            for (int i = 0; i < 128; ++i) { const float dlt = x[i] - mean; vq = fmaf(dlt, dlt, vq); }
-            const float rstd = rsqrtf(vq * (1.0f / 128.0f) + 1e-5f);
+            for (int i = 0; i < 32; ++i) { const float dlt = x[i] - mean; vq = fmaf(dlt, dlt, vq); }
+            red[cp * 128 + row].y = vq;
+            asm volatile("bar.sync 1, 512;" ::: "memory");
+            const float rstd = rsqrtf((red[row].y + red[128 + row].y + red[256 + row].y + red[384 + row].y) * (1.0f / 128.0f) + 1e-5f);
 #pragma unroll
-            for (int ch = 0; ch < 16; ++ch) {
+            for (int c4 = 0; c4 < 4; ++c4) {
                 float g[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    const int c = ch * 8 + i;
-                    g[i] = gelu_erf_((x[c] - mean) * rstd * s_ln_w[c] + s_ln_b[c]);
+                    const int c = cp * 32 + c4 * 8 + i;
+                    g[i] = gelu_erf_((x[c4 * 8 + i] - mean) * rstd * s_ln_w[c] + s_ln_b[c]);
                 }
                 uint4 pk;
                 __nv_bfloat162 p0 = __floats2bfloat162_rn(g[0], g[1]), p1 = __floats2bfloat162_rn(g[2], g[3]);
                 __nv_bfloat162 p2 = __floats2bfloat162_rn(g[4], g[5]), p3 = __floats2bfloat162_rn(g[6], g[7]);
                 pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
                 pk.z = *reinterpret_cast<uint32_t*>(&p2); pk.w = *reinterpret_cast<uint32_t*>(&p3);
-                const int atom = ch >> 3, cc = ch & 7;
+                const int ch = cp * 4 + c4, atom = ch >> 3, cc = ch & 7;
                 *reinterpret_cast<uint4*>(a2s + atom * kTile + row * 128 + ((cc ^ (row & 7)) << 4)) = pk;
             }
             umma::fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
@@ -194,63 +205,64 @@ mlp_umma_kernel(const __grid_constant__ CUtensorMap tmap_ctx, const __grid_const
             umma::mbar_wait(acc2_full, tphase);
             umma::tc_fence_after();
             const int t = t0 + tl;
-            {   // scales: columns SW, SW+1
-                uint32_t r[32];
-                umma::tmem_ld_32x32(acc2 + lane_addr + (uint32_t) SW, r);     // columns SW .. SW+31 (allocated, only 2 used)
+            if (cp == 0) {   // scales: columns SW, SW+1
+                uint32_t r[2];
+                umma::tmem_ld_32x2(acc2 + lane_addr + (uint32_t) SW, r);
                 umma::tmem_ld_wait();
                 if (t < T) {
                     float2 sc = make_float2(__uint_as_float(r[0]) + s_dec_b[SW], __uint_as_float(r[1]) + s_dec_b[SW + 1]);
                     *reinterpret_cast<float2*>(scales + ((((int64_t) n * H + h) * T + t) << 1)) = sc;
                 }
             }
-            // staging [tl][w][c] bf16 aliases A2: GEMM2 has completed (acc2_full), so A2 is free
-            __nv_bfloat16* stg = reinterpret_cast<__nv_bfloat16*>(a2s);
-            float sp[2][2];   // per split: mean, rstd
-            // pass 1: statistics of both splits
+            // this thread: w in [cp*W/4, (cp+1)*W/4) of both splits (16-column loads; only the first W/4 are used)
+            float y0[16], y1[16];
+            {
+                uint32_t r0[16], r1[16];
+                umma::tmem_ld_32x16(acc2 + lane_addr + (uint32_t) (cp * W4), r0);
+                umma::tmem_ld_32x16(acc2 + lane_addr + (uint32_t) (W + cp * W4), r1);
+                umma::tmem_ld_wait();
+                float4 part = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-            for (int sidx = 0; sidx < 2; ++sidx) {
-                float sm = 0.f, sq = 0.f;
-                for (int c0 = 0; c0 < W; c0 += 32) {
-                    uint32_t r[32];
-                    umma::tmem_ld_32x32(acc2 + lane_addr + (uint32_t) (sidx * W + c0), r);
-                    umma::tmem_ld_wait();
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        if (c0 + i < W) {
-                            const float val = __uint_as_float(r[i]) + s_dec_b[sidx * W + c0 + i];
-                            sm += val;
-                            sq = fmaf(val, val, sq);
-                        }
+                for (int i = 0; i < 16; ++i) {
+                    if (i < W4) {
+                        y0[i] = __uint_as_float(r0[i]) + s_dec_b[cp * W4 + i];
+                        y1[i] = __uint_as_float(r1[i]) + s_dec_b[W + cp * W4 + i];
+                        part.x += y0[i]; part.y = fmaf(y0[i], y0[i], part.y);
+                        part.z += y1[i]; part.w = fmaf(y1[i], y1[i], part.w);
                     }
                 }
-                const float mu = sm / (float) W;
-                sp[sidx][0] = mu;
-                sp[sidx][1] = rsqrtf(fmaxf(sq / (float) W - mu * mu, 0.f) + 1e-5f);
+                red[cp * 128 + row] = part;
             }
-            // pass 2: normalise and stage; channel pair (2h, 2h+1) = (split 0, split 1) of this head
-            for (int c0 = 0; c0 < W; c0 += 32) {
-                uint32_t r0[32], r1[32];
-                umma::tmem_ld_32x32(acc2 + lane_addr + (uint32_t) c0, r0);
-                umma::tmem_ld_32x32(acc2 + lane_addr + (uint32_t) (W + c0), r1);
-                umma::tmem_ld_wait();
+            asm volatile("bar.sync 1, 512;" ::: "memory");
+            float mu0, rs0, mu1, rs1;
+            {
+                const float4 a = red[row], b = red[128 + row], c = red[256 + row], d = red[384 + row];
+                const float invw = 1.0f / (float) W;
+                mu0 = (a.x + b.x + c.x + d.x) * invw;
+                rs0 = rsqrtf(fmaxf((a.y + b.y + c.y + d.y) * invw - mu0 * mu0, 0.f) + 1e-5f);
+                mu1 = (a.z + b.z + c.z + d.z) * invw;
+                rs1 = rsqrtf(fmaxf((a.w + b.w + c.w + d.w) * invw - mu1 * mu1, 0.f) + 1e-5f);
+            }
+            // staging [tl][w][c] bf16 aliases A2: GEMM2 has completed (acc2_full), so A2 is free.
+            // channel pair (2h, 2h+1) = (split 0, split 1) of this head
+            __nv_bfloat16* stg = reinterpret_cast<__nv_bfloat16*>(a2s);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const int w = c0 + i;
-                    if (w < W) {
-                        const float v0 = (__uint_as_float(r0[i]) + s_dec_b[w] - sp[0][0]) * sp[0][1] * s_cw[w] + s_cb[w];
-                        const float v1 = (__uint_as_float(r1[i]) + s_dec_b[W + w] - sp[1][0]) * sp[1][1] * s_cw[w] + s_cb[w];
-                        *reinterpret_cast<__nv_bfloat162*>(stg + ((size_t) (tl * W + w) * C + 2 * h)) = __floats2bfloat162_rn(v0, v1);
-                    }
+            for (int i = 0; i < 16; ++i) {
+                if (i < W4) {
+                    const int w = cp * W4 + i;
+                    const float v0 = (y0[i] - mu0) * rs0 * s_cw[w] + s_cb[w];
+                    const float v1 = (y1[i] - mu1) * rs1 * s_cw[w] + s_cb[w];
+                    *reinterpret_cast<__nv_bfloat162*>(stg + ((size_t) (tl * W + w) * C + 2 * h)) = __floats2bfloat162_rn(v0, v1);
                 }
             }
             umma::tc_fence_before();
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 1, 512;" ::: "memory");
             const int valid_t = min(TT, T - t0);
             const int nchunks = (valid_t * W * C * 2) >> 4;       // 16-byte chunks of the contiguous block
             uint8_t* gout = reinterpret_cast<uint8_t*>(cnn_in) + (((int64_t) n * T + t0) * W * C) * 2;
-            for (int g = et; g < nchunks; g += 128)
+            for (int g = et; g < nchunks; g += kMlpEpiThreads)
                 *reinterpret_cast<uint4*>(gout + (int64_t) g * 16) = *reinterpret_cast<const uint4*>(a2s + (size_t) g * 16);
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 1, 512;" ::: "memory");
             tphase ^= 1;
         }
     }
