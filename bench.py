@@ -323,7 +323,7 @@ def main():
         mod.output_attentions = False
         b = 2 if dt != torch.float32 else 4
         sb = stage_bytes(N, H, d, T, P, k, F, b, Z)
-        if 'sea_sparse_attention_bits_fwd' in per:
+        if 'sea_sparse_attention_bits_fwd' in per or 'sea_block_attention_fwd' in per:
             # attention driven by the bit mask: no CSR tensors on the hot path (a8 is folded into the attention kernel)
             sb['csr'] = 0
             sb['attn'] = sb['attn'] - Z * 4 + N * T * H * P // 8
@@ -332,7 +332,7 @@ def main():
                        'sea_causal_conv3x3_dil2_relu_umma': 'conv', 'sea_conv1x1_umma': 'tail', 'sea_predictor_tail_topk_fwd': 'tail',
                        'sea_predictor_mlp_umma_fwd': 'mlp', 'sea_performer_causal_mma_fwd': 'performer',
                        'sea_predictor_tail_fwd': 'tail', 'sea_topk_mask_bits': 'topk', 'sea_csr_count': 'csr', 'sea_csr_fill': 'csr', 'sea_crow_scan': 'csr',
-                       'sea_sparse_attention_fwd': 'attn', 'sea_sparse_attention_bits_fwd': 'attn'}
+                       'sea_sparse_attention_fwd': 'attn', 'sea_sparse_attention_bits_fwd': 'attn', 'sea_block_attention_fwd': 'attn'}
         kernels = {}
         for name, times in per.items():
             st = entry_stage.get(name, name)

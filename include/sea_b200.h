@@ -252,6 +252,23 @@ SEA_API int sea_sparse_attention_bits_fwd(const uint32_t* mask_bits,
                                           const float* scales, const void* cumavg, int64_t avg_sh, int64_t avg_st, int use_scaler, int dtype, void* out,
                                           int N, int H, int T_DST, int T_SRC, int D, int P, int k_clamp, int is_causal, void* stream);
 
+/* a8 + a9-a14 fused, short-context form (csrc/block_attn.cu): the same result as sea_sparse_attention_bits_fwd, computed as a
+ * tile-skipping, element-masked flash attention: the top-k bit mask is first expanded to the dense bit-packed
+ * partial_attention_mask (one u64 per head / query row / 64-token tile, in `workspace`), then 128-row query blocks share
+ * TMA-staged K/V tiles.  Replaces flat_csr_masked_bmm -> flat_csr_softmax -> flat_csr_elmul -> flat_csr_sdbmm
+ * (reference attention.py:1159-1173) when the caller does not need the CSR tensors.
+ * Supported iff sea_block_attention_workspace_bytes(...) > 0: 16-bit activations, D == 64, P % 32 == 0, P <= 1024,
+ * no clamped pixel (ceil(T_SRC / P) + 1 <= k_clamp) and T_SRC <= 8192 (work is O(T^2) in the worst case).
+ * `workspace` must be 16-byte aligned; it is overwritten. */
+SEA_API int64_t sea_block_attention_workspace_bytes(int N, int H, int T_DST, int T_SRC, int D, int P, int k_clamp, int dtype);
+SEA_API int sea_block_attention_fwd(const uint32_t* mask_bits,
+                                    const void* q, int64_t q_sn, int64_t q_sh, int64_t q_st,
+                                    const void* k, int64_t k_sn, int64_t k_sh, int64_t k_st,
+                                    const void* v, int64_t v_sn, int64_t v_sh, int64_t v_st,
+                                    const float* scales, const void* cumavg, int64_t avg_sh, int64_t avg_st, int use_scaler, int dtype, void* out,
+                                    int N, int H, int T_DST, int T_SRC, int D, int P, int k_clamp, int is_causal,
+                                    void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Non-causal (BERT) variant, csrc/noncausal.cu.  No padding.
  * sea_performer_noncausal_fwd: v_for_atten = cat(grid-sampled identity, v) (attention.py:462-502) and the FAVOR+

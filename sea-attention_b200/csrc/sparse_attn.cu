@@ -861,9 +861,9 @@ extern "C" int sea_sparse_attention_bits_fwd(const uint32_t* mask_bits,
     SEA_CHECK_ARG(((q_sn | q_sh | q_st | k_sn | k_sh | k_st | v_sn | v_sh | v_st) % 8) == 0 &&
                   ((((uintptr_t) q) | ((uintptr_t) k) | ((uintptr_t) v) | ((uintptr_t) out) | ((uintptr_t) cumavg)) & 15) == 0,
                   "sea_sparse_attention_bits_fwd: rows must be 16-byte aligned");
+    cudaStream_t s = (cudaStream_t) stream;
     const int64_t tasks = (int64_t) N * T_DST * H;
     const unsigned grid = (unsigned) ((tasks + kAttnWarps - 1) / kAttnWarps);
-    cudaStream_t s = (cudaStream_t) stream;
     static const bool use_mma = getenv("SEA_ATTN_NO_MMA") == nullptr;     // development switch: CUDA-core variant for A/B timing
 #define SEA_ATTN_BITS(TT, DD)                                                                                                   \
     do {                                                                                                                        \

@@ -6,6 +6,7 @@ reference: ops return fresh tensors, inputs are never mutated) and launches on t
 Nothing here computes on the CPU and there is no fallback: a missing library or a CPU tensor raises.
 """
 import math
+import os
 from typing import Optional
 
 import torch
@@ -392,8 +393,11 @@ def sparse_attention(crow, col, q, k, v, scales, cumavg, use_scaler=True, want_p
     return out, pv
 
 
-def sparse_attention_from_bits(bits, q, k, v, scales, cumavg, P: int, k_clamp: int, use_scaler=True, is_causal=True):
-    """a8 + a9-a14 fused: attention driven directly by the top-k bit mask (no CSR tensors are materialised)."""
+def sparse_attention_from_bits(bits, q, k, v, scales, cumavg, P: int, k_clamp: int, use_scaler=True, is_causal=True, kernel: str = 'auto'):
+    """a8 + a9-a14 fused: attention driven directly by the top-k bit mask (no CSR tensors are materialised).
+
+    kernel = 'auto' picks the tile-skipping block kernel (sea_block_attention_fwd) where the library supports the shape
+    (d = 64, no clamped pixel, T_SRC <= 8192) and the per-(row, head) gather kernel otherwise; 'gather' / 'block' force one."""
     _cuda(bits, q, k, v, scales, cumavg)
     N, H, T_DST, D = q.shape
     T_SRC = k.shape[2]
@@ -401,6 +405,22 @@ def sparse_attention_from_bits(bits, q, k, v, scales, cumavg, P: int, k_clamp: i
     out = torch.empty((N, T_DST, H * D), dtype=q.dtype, device=q.device)
     sc = scales.float().contiguous()
     ca, avg_sh, avg_st = _avg_arg(cumavg, N, H, T_DST, D)
+    if kernel not in ('auto', 'gather', 'block'):
+        raise SeaError(f'unknown attention kernel {kernel!r}')
+    if kernel == 'auto' and os.environ.get('SEA_ATTN_GATHER'):
+        kernel = 'gather'             # development switch for A/B timing
+    ws_bytes = 0
+    if kernel != 'gather':
+        ws_bytes = int(_lib.load().sea_block_attention_workspace_bytes(N, H, T_DST, T_SRC, D, int(P), int(k_clamp), _dtype_code(q)))
+        if ws_bytes == 0 and kernel == 'block':
+            raise SeaError('sparse_attention_from_bits: the block kernel does not support this shape')
+    if ws_bytes > 0:
+        ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=q.device)
+        _lib.call('sea_block_attention_fwd', bits.data_ptr(), q.data_ptr(), q.stride(0), q.stride(1), q.stride(2),
+                  k.data_ptr(), k.stride(0), k.stride(1), k.stride(2), v.data_ptr(), v.stride(0), v.stride(1), v.stride(2),
+                  sc.data_ptr(), _p(ca), avg_sh, avg_st, int(bool(use_scaler)), _dtype_code(q), out.data_ptr(), N, H, T_DST, T_SRC, D, int(P),
+                  int(k_clamp), int(bool(is_causal)), ws.data_ptr(), ws_bytes, _stream())
+        return out
     _lib.call('sea_sparse_attention_bits_fwd', bits.data_ptr(), q.data_ptr(), q.stride(0), q.stride(1), q.stride(2),
               k.data_ptr(), k.stride(0), k.stride(1), k.stride(2), v.data_ptr(), v.stride(0), v.stride(1), v.stride(2),
               sc.data_ptr(), _p(ca), avg_sh, avg_st, int(bool(use_scaler)), _dtype_code(q), out.data_ptr(), N, H, T_DST, T_SRC, D, int(P), int(k_clamp),

@@ -249,6 +249,9 @@ def test_fused_sparse_attention_v2_bf16_with_head_ptr(sea, d, idt):
 @pytest.mark.parametrize('N,H,T_DST,T_SRC,P,k,d,causal', [
     (2, 4, 160, 160, 32, 8, 64, True), (1, 2, 1024, 1024, 32, 4, 64, True),     # second: T/P > k -> clamped, sub-sampled pixels
     (1, 3, 40, 128, 64, 8, 128, True), (2, 4, 64, 64, 32, 8, 32, False), (1, 32, 70, 70, 256, 64, 64, True),
+    # d = 64 and no clamped pixel -> the tile-skipping block kernel (block_attn.cu): ragged row blocks, T_DST < T_SRC, non-causal
+    (1, 2, 1000, 1000, 64, 32, 64, True), (1, 3, 40, 128, 64, 8, 64, True), (2, 4, 200, 200, 32, 8, 64, False),
+    (1, 2, 2048, 2048, 256, 64, 64, True),
 ])
 def test_attention_from_bits_equals_csr_path(sea, N, H, T_DST, T_SRC, P, k, d, causal):
     """The bit-mask driven kernel enumerates exactly the entries sea_csr_fill would emit."""
@@ -267,3 +270,13 @@ def test_attention_from_bits_equals_csr_path(sea, N, H, T_DST, T_SRC, P, k, d, c
     out = sea.ops.sparse_attention_from_bits(bits, q, kk, v, scales, avg, P, k, True, causal)
     torch.testing.assert_close(out.float().cpu(), ref.float().cpu(), rtol=1e-2, atol=1e-2)
     assert float((out.float() - ref.float()).abs().mean()) < 1e-3
+    # both kernels behind the op: the per-(row, head) gather kernel and (where the shape allows) the block kernel
+    out_g = sea.ops.sparse_attention_from_bits(bits, q, kk, v, scales, avg, P, k, True, causal, kernel='gather')
+    torch.testing.assert_close(out_g.float().cpu(), ref.float().cpu(), rtol=1e-2, atol=1e-2)
+    if sea._lib.load().sea_block_attention_workspace_bytes(N, H, T_DST, T_SRC, d, P, k, sea._lib.SEA_DTYPE_BF16) > 0:
+        out_b = sea.ops.sparse_attention_from_bits(bits, q, kk, v, scales, avg, P, k, True, causal, kernel='block')
+        torch.testing.assert_close(out_b.float().cpu(), ref.float().cpu(), rtol=1e-2, atol=1e-2)
+        out_h = sea.ops.sparse_attention_from_bits(bits, q.half(), kk.half(), v.half(), scales, avg.half(), P, k, True, causal, kernel='block')
+        torch.testing.assert_close(out_h.float().cpu(), ref.float().cpu(), rtol=2e-2, atol=2e-2)
+    else:
+        assert d != 64 or (T_SRC + P - 1) // P + 1 > k
