@@ -9,6 +9,8 @@
 #include "topk.cuh"
 #include "csr_common.cuh"
 
+#include <stdlib.h>
+
 namespace sea {
 
 template <int kPerLane, int kUp>
@@ -124,6 +126,299 @@ tail_topk_kernel(const float* __restrict__ y3, const float* __restrict__ bias, c
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Register-resident variant (H % 8 == 0, (H/8) * (P/32) <= 32 keys per thread) -- the production path at the OPT shapes.
+// The kernel above streams the H*P keys of a row through shared memory five times (or/and, 4 radix passes, bit build) and
+// is issue-bound (ncu: 79 % issue-active, ~45 k warp instructions per row).  Here warp w owns heads w, w+8, ...; a lane
+// owns P/32 CONSECUTIVE pixels of each of them, so the keys never leave registers:
+//   * LayerNorm / softmax per head with warp reductions, probabilities stored as 16-byte vectors,
+//   * radix select with 8-bit digits that START at the highest bit in which the row's keys differ (all digits carry
+//     entropy -> no serialised shared-memory atomics on a constant exponent byte),
+//   * alive bits assembled with shuffles inside 32/(P/32)-lane groups; ties at the threshold are cut in flat-index order
+//     (lower h*P+m wins) with one warp scan per head.
+// ------------------------------------------------------------------------------------------------
+constexpr int kMaxCand = 1024;
+
+template <int kPerLane, int kHPW, int kUp>
+__global__ void __launch_bounds__(kTopkThreads, 3)
+tail_topk_reg_kernel(const float* __restrict__ y3, const float* __restrict__ bias, const float* __restrict__ ln_w,
+                     const float* __restrict__ ln_b, const float* __restrict__ k_per_row, float* __restrict__ probs,
+                     uint32_t* __restrict__ mask_bits, int32_t* __restrict__ crow_counts, int k_clamp,
+                     int N, int Tn, int W) {
+    constexpr int P = 32 * kPerLane, H = 8 * kHPW, G = H * P;
+    constexpr int kLanesPerWord = 32 / kPerLane > 0 ? 32 / kPerLane : 1;     // lanes that share one 32-pixel word (kPerLane <= 32)
+    extern __shared__ __align__(16) uint32_t smem_u[];
+    __shared__ int hist[256];
+    __shared__ int scratch[16];
+    __shared__ int head_eq[H];
+    __shared__ uint32_t cand[kMaxCand];
+    __shared__ int4 stap[P];
+    float* ys = reinterpret_cast<float*>(smem_u);               // [H][W+2]: W conv outputs, then the bias (pad columns), then 0
+    uint32_t* sbits = smem_u + H * (W + 3);                     // [G/32] (only for the fused row counts)
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int n = blockIdx.x / Tn, t = blockIdx.x % Tn;
+    const int ldy = (W + 2) | 1;
+    const float* yr = y3 + ((int64_t) n * Tn + t) * W * H;
+    for (int base = 0; base < W * H; base += 8 * kTopkThreads) {
+        // 8 independent loads in flight per thread before the first (transposing) shared-memory store
+        float tmp[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int idx = base + u * kTopkThreads + tid;
+            tmp[u] = idx < W * H ? __ldg(yr + idx) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int idx = base + u * kTopkThreads + tid;
+            if (idx < W * H) ys[(idx % H) * ldy + idx / H] = tmp[u];
+        }
+    }
+    for (int h = tid; h < H; h += kTopkThreads) { ys[h * ldy + W] = bias[h]; ys[h * ldy + W + 1] = 0.f; }
+    __syncthreads();
+    constexpr int PW = P + 2;
+    const int up = kUp > 0 ? kUp : P / W;
+    // area-resize window of every output column, resolved once per CTA (thread = column) into three slots of the per-head
+    // vector: a conv output w, the bias slot W (the zero-padded columns of the 1x1 conv) or the zero slot W+1
+    for (int j = tid; j < P; j += kTopkThreads) {
+        const int st = (j * PW) / P;
+        const int cnt = ((j + 1) * PW + P - 1) / P - st;
+        int tp[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const int pcol = st + c;
+            tp[c] = c >= cnt ? W + 1 : ((pcol == 0 || pcol == PW - 1) ? W : (pcol - 1) / up);
+        }
+        stap[(j % kPerLane) * 32 + j / kPerLane] = make_int4(tp[0], tp[1], tp[2], __float_as_int(1.0f / (float) cnt));   // [i][lane]: conflict-free reads
+    }
+    __syncthreads();
+    int tap[kPerLane][3];
+    float rc[kPerLane], lw[kPerLane], lb[kPerLane];
+#pragma unroll
+    for (int i = 0; i < kPerLane; ++i) {
+        const int j = lane * kPerLane + i;
+        const int4 tp = stap[i * 32 + lane];
+        tap[i][0] = tp.x; tap[i][1] = tp.y; tap[i][2] = tp.z;
+        rc[i] = __int_as_float(tp.w);
+        lw[i] = ln_w[j];
+        lb[i] = ln_b[j];
+    }
+    constexpr float invP = 1.0f / (float) P;
+    uint32_t key[kHPW][kPerLane];
+#pragma unroll
+    for (int hh = 0; hh < kHPW; ++hh) {
+        const int h = wid + 8 * hh;
+        const float* yh = ys + h * ldy;
+        float val[kPerLane];
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < kPerLane; ++i) {
+            val[i] = (yh[tap[i][0]] + yh[tap[i][1]] + yh[tap[i][2]]) * rc[i];
+            s += val[i];
+        }
+        const float mean = warp_sum(s) * invP;
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < kPerLane; ++i) { const float d = val[i] - mean; q = fmaf(d, d, q); }
+        const float rstd = rsqrtf(warp_sum(q) * invP + 1e-5f);
+        float mx = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < kPerLane; ++i) { val[i] = (val[i] - mean) * rstd * lw[i] + lb[i]; mx = fmaxf(mx, val[i]); }
+        mx = warp_max(mx);
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < kPerLane; ++i) { val[i] = __expf(val[i] - mx); sum += val[i]; }
+        const float inv = 1.0f / warp_sum(sum);
+#pragma unroll
+        for (int i = 0; i < kPerLane; ++i) { val[i] *= inv; key[hh][i] = __float_as_uint(val[i]) | 0x80000000u; }   // == orderable(): val >= +0
+        if (probs) {
+            float* prow = probs + (((int64_t) n * H + h) * Tn + t) * P + lane * kPerLane;
+            if constexpr (kPerLane % 4 == 0) {
+#pragma unroll
+                for (int i = 0; i < kPerLane; i += 4) *reinterpret_cast<float4*>(prow + i) = make_float4(val[i], val[i + 1], val[i + 2], val[i + 3]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < kPerLane; ++i) prow[i] = val[i];
+            }
+        }
+    }
+    if (mask_bits == nullptr) return;
+    const float kf = k_per_row[blockIdx.x];
+    const int K = (int) fminf(ceilf(kf), (float) G);
+
+    // ---- K-th largest key: or/and -> highest differing bit -> 8-bit radix passes from there ------------------------
+    uint32_t thr = 0u;
+    int remaining = K, eq_total = G;
+    bool all_alive = K >= G;
+    if (!all_alive) {
+        uint32_t k_or = 0u, k_and = 0xffffffffu;
+#pragma unroll
+        for (int hh = 0; hh < kHPW; ++hh)
+#pragma unroll
+            for (int i = 0; i < kPerLane; ++i) { k_or |= key[hh][i]; k_and &= key[hh][i]; }
+        k_or = __reduce_or_sync(kFull, k_or);
+        k_and = __reduce_and_sync(kFull, k_and);
+        if (lane == 0) { hist[wid] = (int) k_or; hist[8 + wid] = (int) k_and; }
+        __syncthreads();
+#pragma unroll
+        for (int w = 0; w < kTopkThreads / 32; ++w) { k_or |= (uint32_t) hist[w]; k_and &= (uint32_t) hist[8 + w]; }
+        __syncthreads();
+        const uint32_t diff = k_or ^ k_and;
+        thr = k_and;                                             // bits above the first difference are common
+        if (diff != 0u) {
+            int top = 32 - __clz(diff);                          // bits [0, top) still unresolved
+            thr &= top >= 32 ? 0u : (0xffffffffu << top);
+            bool first = true;
+            while (top > 0) {
+                const int wd = min(8, top), sh = top - wd;
+                const uint32_t hi_mask = top >= 32 ? 0u : (0xffffffffu << top);
+                const uint32_t dmask = (1u << wd) - 1u;
+                hist[tid] = 0;
+                __syncthreads();
+                if (first) {                                     // every key carries the common prefix
+#pragma unroll
+                    for (int hh = 0; hh < kHPW; ++hh)
+#pragma unroll
+                        for (int i = 0; i < kPerLane; ++i) atomicAdd(&hist[(key[hh][i] >> sh) & dmask], 1);
+                } else {
+#pragma unroll
+                    for (int hh = 0; hh < kHPW; ++hh)
+#pragma unroll
+                        for (int i = 0; i < kPerLane; ++i) {
+                            const uint32_t u = key[hh][i];
+                            if ((u & hi_mask) == thr) atomicAdd(&hist[(u >> sh) & dmask], 1);
+                        }
+                }
+                __syncthreads();
+                if (wid == 0) {
+                    // pivot digit by one warp: lane l owns digits 255-8l .. 248-8l (descending), suffix counts by warp scan
+                    int c[8], loc = 0;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { c[j] = hist[255 - 8 * lane - j]; loc += c[j]; }
+                    int above = warp_scan_incl_i(loc, lane) - loc;          // keys with a digit above this lane's range
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        if (above < remaining && remaining <= above + c[j]) {
+                            scratch[8] = 255 - 8 * lane - j;
+                            scratch[9] = remaining - above;
+                            scratch[10] = c[j];
+                        }
+                        above += c[j];
+                    }
+                    if (lane == 0) scratch[11] = 0;                         // candidate counter
+                }
+                __syncthreads();
+                thr |= (uint32_t) scratch[8] << sh;
+                remaining = scratch[9];
+                eq_total = scratch[10];
+                top = sh;
+                if (first && top > 0 && eq_total <= kMaxCand) {
+                    // few keys share the pivot digit: list them and rank them directly instead of more radix passes
+                    const uint32_t pd = (uint32_t) scratch[8];
+#pragma unroll
+                    for (int hh = 0; hh < kHPW; ++hh)
+#pragma unroll
+                        for (int i = 0; i < kPerLane; ++i) {
+                            const uint32_t u = key[hh][i];
+                            if (((u >> sh) & dmask) == pd) cand[atomicAdd(&scratch[11], 1)] = u;
+                        }
+                    __syncthreads();
+                    const int nc = eq_total;
+                    for (int ci = tid; ci < nc; ci += kTopkThreads) {
+                        const uint32_t mine_k = cand[ci];
+                        int gt = 0, eq = 0;
+                        for (int j = 0; j < nc; ++j) { const uint32_t o = cand[j]; gt += o > mine_k ? 1 : 0; eq += o == mine_k ? 1 : 0; }
+                        if (gt < remaining && remaining <= gt + eq) {       // every thread holding the threshold value writes the same triple
+                            scratch[12] = (int) mine_k;
+                            scratch[13] = remaining - gt;
+                            scratch[14] = eq;
+                        }
+                    }
+                    __syncthreads();
+                    thr = (uint32_t) scratch[12];
+                    remaining = scratch[13];
+                    eq_total = scratch[14];
+                    top = 0;
+                }
+                first = false;
+                __syncthreads();
+            }
+        }
+    }
+    // ---- alive bits: key > thr, plus the first `remaining` keys == thr in flat-index order ---------------------------
+    const bool cut_ties = !all_alive && remaining < eq_total;
+    uint32_t alive[kHPW];
+#pragma unroll
+    for (int hh = 0; hh < kHPW; ++hh) {
+        uint32_t a = 0u;
+#pragma unroll
+        for (int i = 0; i < kPerLane; ++i) a |= ((all_alive || key[hh][i] >= thr) ? 1u : 0u) << i;
+        alive[hh] = a;
+    }
+    if (cut_ties) {                                              // CTA-uniform branch
+        int eqc[kHPW], lane_before[kHPW];
+#pragma unroll
+        for (int hh = 0; hh < kHPW; ++hh) {
+            int c = 0;
+#pragma unroll
+            for (int i = 0; i < kPerLane; ++i) c += key[hh][i] == thr ? 1 : 0;
+            eqc[hh] = c;
+            const int incl = warp_scan_incl_i(c, lane);
+            lane_before[hh] = incl - c;
+            if (lane == 31) head_eq[wid + 8 * hh] = incl;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int hh = 0; hh < kHPW; ++hh) {
+            const int h = wid + 8 * hh;
+            int before = lane_before[hh];
+            for (int h2 = 0; h2 < h; ++h2) before += head_eq[h2];
+            int take = remaining - before;                       // how many of my equal keys (in index order) stay alive
+            if (take < eqc[hh]) {
+                uint32_t a = alive[hh];
+#pragma unroll
+                for (int i = 0; i < kPerLane; ++i)
+                    if (key[hh][i] == thr) {
+                        if (take <= 0) a &= ~(1u << i);
+                        --take;
+                    }
+                alive[hh] = a;
+            }
+        }
+    }
+    // ---- words: kLanesPerWord lanes share one 32-pixel word ---------------------------------------------------------
+    uint32_t* out_row = mask_bits + (int64_t) blockIdx.x * (G >> 5);
+#pragma unroll
+    for (int hh = 0; hh < kHPW; ++hh) {
+        const int h = wid + 8 * hh;
+        uint32_t word = kPerLane >= 32 ? alive[hh] : (alive[hh] << (kPerLane * (lane % kLanesPerWord)));
+#pragma unroll
+        for (int o = 1; o < kLanesPerWord; o <<= 1) word |= __shfl_xor_sync(kFull, word, o);
+        if ((lane % kLanesPerWord) == 0) {
+            const int w = h * (P >> 5) + lane / kLanesPerWord;
+            out_row[w] = word;
+            if (crow_counts != nullptr) sbits[w] = word;
+        }
+    }
+    if (crow_counts != nullptr) {
+        // a8 pass 1 fused: crow[n, t+1] = entries of this row (sea_crow_scan turns the counts into offsets)
+        __syncthreads();
+        int cnt = 0;
+        const float sc = __fdiv_rn((float) (t + 1), (float) P);
+        for (int w = tid; w < (G >> 5); w += kTopkThreads) cnt += word_width_sum(sbits[w], w, P, sc, k_clamp);
+        cnt = warp_sum_i(cnt);
+        if (lane == 0) scratch[wid] = cnt;
+        __syncthreads();
+        if (tid == 0) {
+            int tot = 0;
+#pragma unroll
+            for (int i = 0; i < kTopkThreads / 32; ++i) tot += scratch[i];
+            crow_counts[(int64_t) n * (Tn + 1) + t + 1] = tot;
+            if (t == 0) crow_counts[(int64_t) n * (Tn + 1)] = 0;
+        }
+    }
+}
+
 }  // namespace sea
 
 using namespace sea;
@@ -142,10 +437,42 @@ int sea_predictor_tail_topk_fwd(const float* y3, const float* bias, const float*
         return SEA_ERR_UNSUPPORTED;
     }
     const int G = H * P;
-    const size_t smem = ((size_t) G + (G >> 5)) * 4 + (size_t) H * (W + 2) * 4 + 16;
-    SEA_CHECK_ARG(smem <= 220 * 1024, "sea_predictor_tail_topk_fwd: H*P=%d keys do not fit shared memory", G);
     cudaStream_t s = (cudaStream_t) stream;
     const unsigned grid = (unsigned) ((int64_t) N * T);
+    static const bool no_reg = getenv("SEA_TAIL_SMEM") != nullptr;        // development switch for A/B timing
+    if (!no_reg && H % 8 == 0 && (H / 8) * (P / 32) <= 32 && P <= 1024 && H <= 64) {
+        const size_t smem_r = (size_t) H * (W + 3) * 4 + (size_t) (G >> 5) * 4 + 16;
+        bool launched = true;
+#define SEA_TAILR(PL, HP)                                                                                                  \
+        {                                                                                                                  \
+            if (P / W == 4) {                                                                                              \
+                auto kern = tail_topk_reg_kernel<PL, HP, 4>;                                                               \
+                SEA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_r), "smem attr"); \
+                kern<<<grid, kTopkThreads, smem_r, s>>>(y3, bias, ln_w, ln_b, k_per_row, probs, mask_bits, crow_counts, k_clamp, N, T, W); \
+            } else {                                                                                                       \
+                auto kern = tail_topk_reg_kernel<PL, HP, 0>;                                                               \
+                SEA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_r), "smem attr"); \
+                kern<<<grid, kTopkThreads, smem_r, s>>>(y3, bias, ln_w, ln_b, k_per_row, probs, mask_bits, crow_counts, k_clamp, N, T, W); \
+            }                                                                                                              \
+        }
+        const int pl = P / 32, hp = H / 8;
+        if (pl == 8 && hp == 4) SEA_TAILR(8, 4)
+        else if (pl == 8 && hp == 2) SEA_TAILR(8, 2)
+        else if (pl == 8 && hp == 1) SEA_TAILR(8, 1)
+        else if (pl == 4 && hp == 4) SEA_TAILR(4, 4)
+        else if (pl == 4 && hp == 2) SEA_TAILR(4, 2)
+        else if (pl == 2 && hp == 1) SEA_TAILR(2, 1)
+        else if (pl == 16 && hp == 2) SEA_TAILR(16, 2)
+        else if (pl == 16 && hp == 1) SEA_TAILR(16, 1)
+        else launched = false;
+#undef SEA_TAILR
+        if (launched) {
+            SEA_CHECK_LAUNCH("tail_topk_reg_kernel");
+            return SEA_OK;
+        }
+    }
+    const size_t smem = ((size_t) G + (G >> 5)) * 4 + (size_t) H * (W + 2) * 4 + 16;
+    SEA_CHECK_ARG(smem <= 220 * 1024, "sea_predictor_tail_topk_fwd: H*P=%d keys do not fit shared memory", G);
 #define SEA_TAIL_LAUNCH(PL, UP)                                                                                       \
     {                                                                                                                \
         auto kern = tail_topk_kernel<PL, UP>;                                                                        \

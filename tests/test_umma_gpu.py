@@ -48,14 +48,18 @@ def test_conv1x1_umma_matches_oracle(sea, N, T, W):
     torch.testing.assert_close(y.cpu(), ref, rtol=1e-2, atol=1e-2)
 
 
-@pytest.mark.parametrize('N,H,T,W,P,k', [(1, 32, 40, 64, 256, 64), (2, 8, 33, 16, 64, 8), (1, 4, 20, 8, 32, 4), (1, 32, 12, 32, 128, 16)])
-def test_tail_topk_fused_matches_oracle(sea, N, H, T, W, P, k):
+@pytest.mark.parametrize('ties', [False, True])
+@pytest.mark.parametrize('N,H,T,W,P,k', [(1, 32, 40, 64, 256, 64), (2, 8, 33, 16, 64, 8), (1, 4, 20, 8, 32, 4), (1, 32, 12, 32, 128, 16),
+                                        (1, 32, 300, 64, 256, 8), (1, 16, 90, 64, 256, 16), (1, 12, 50, 64, 256, 64)])
+def test_tail_topk_fused_matches_oracle(sea, N, H, T, W, P, k, ties):
     import numpy as np
     g = torch.Generator().manual_seed(P + T)
     y3 = torch.randn(N, T, W, H, generator=g)
     bias = torch.randn(H, generator=g)
     ln_w = 1 + 0.1 * torch.randn(P, generator=g)
     ln_b = 0.1 * torch.randn(P, generator=g)
+    if ties:        # freshly initialised LayerNorm: the x(P/W) upsample makes runs of exactly equal probabilities
+        ln_w, ln_b = torch.ones(P), torch.zeros(P)
     kpr = torch.from_numpy(np.tile(so.per_item_top_k_causal(H, k, 1.0, P, T), N))
     probs, bits = sea.ops.predictor_tail_topk(y3.to(DEV), bias.to(DEV), ln_w.to(DEV), ln_b.to(DEV), kpr.to(DEV), P)
     # oracle: [N,H,T,W] -> nearest x(P/W) -> bias pad columns -> area resize -> LN -> softmax
