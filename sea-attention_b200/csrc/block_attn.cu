@@ -18,7 +18,8 @@
 //                       of the block is alive are skipped;  mma.sync m16n8k16 fed by ldmatrix from the swizzled tiles.
 // Work is O(active tiles), i.e. O(T^2) in the worst case: callers keep the gather kernel (O(T k)) for long contexts.
 //
-// Softmax: fp32, log2 domain, online (running max / sum per row, accumulator rescaled only when a max moves);
+// Softmax: fp32, online, exponent fused as ex2(s * log2e - m * log2e); the per-row reference maximum moves lazily
+// (only when a tile exceeds it by more than 2^8), so the accumulator is almost never rescaled;
 // epilogue = * sigmoid(s0), mix with the causal running mean, permuted store [N, T, H*D]
 // (reference attention.py:1151-1173, 1237-1244, 1279-1282).
 #include "common.cuh"
@@ -35,9 +36,11 @@ constexpr int kBWarps = kBM / 16;
 constexpr int kBThreads = kBWarps * 32;
 constexpr int kStages = 4;
 constexpr int kTileBytes = kBN * kBD * 2;      // 8 KB
+constexpr int kMaskBytes = kBM * 16;            // per stage: 128 rows x 2 u64 (the element masks of an aligned tile pair)
+constexpr int kStageBytes = 2 * kTileBytes + kMaskBytes;
 constexpr int kMaxTileWords = 64;  // activity bitmap words -> T_SRC <= 64 * 32 * 64 = 131072
 #ifndef SEA_BLOCK_DENSE_GROUPS
-#define SEA_BLOCK_DENSE_GROUPS 1
+#define SEA_BLOCK_DENSE_GROUPS 0
 #endif
 template <typename T16>
 __device__ __forceinline__ uint32_t pack2b(float a, float b);
@@ -106,12 +109,13 @@ __global__ void __launch_bounds__(kBThreads, 2)
 block_attention_bits_kernel(const unsigned long long* __restrict__ dmask, int W64,
                             const T16* __restrict__ q, int64_t q_sn, int64_t q_sh, int64_t q_st,
                             const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_v,
+                            const __grid_constant__ CUtensorMap tmap_m,
                             const float* __restrict__ scales, const T16* __restrict__ cumavg, int64_t avg_sh, int64_t avg_st, int use_scaler,
                             T16* __restrict__ out, int N, int H, int T_DST, int T_SRC, int is_causal, int n_row_blocks, int max_tiles) {
     extern __shared__ uint8_t bsm_raw[];
     uint8_t* bsm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(bsm_raw) + 1023) & ~(uintptr_t) 1023);   // swizzle atoms are 1 KB
-    uint8_t* kv = bsm;                                                               // [stages][K 8 KB | V 8 KB]
-    uint32_t* sact = reinterpret_cast<uint32_t*>(kv + kStages * 2 * kTileBytes);     // [kMaxTileWords]
+    uint8_t* kv = bsm;                                                               // [stages][K 8 KB | V 8 KB | masks 2 KB]
+    uint32_t* sact = reinterpret_cast<uint32_t*>(kv + kStages * kStageBytes);     // [kMaxTileWords]
     uint64_t* full = reinterpret_cast<uint64_t*>(sact + kMaxTileWords);              // [stages]
     int* rel_cnt = reinterpret_cast<int*>(full + kStages);                           // [stages] warps that released the stage
     uint16_t* slist = reinterpret_cast<uint16_t*>(rel_cnt + kStages);                // [max_tiles]
@@ -128,7 +132,7 @@ block_attention_bits_kernel(const unsigned long long* __restrict__ dmask, int W6
     // ---- set-up: barriers, tile activity = OR over the 128 rows of their element-mask words -------------------------------
     if (tid < kMaxTileWords) sact[tid] = 0u;
     if (tid == 0) {
-        umma::prefetch_tensormap(&tmap_k); umma::prefetch_tensormap(&tmap_v);
+        umma::prefetch_tensormap(&tmap_k); umma::prefetch_tensormap(&tmap_v); umma::prefetch_tensormap(&tmap_m);
         for (int s = 0; s < kStages; ++s) { umma::mbar_init(&full[s], 1); rel_cnt[s] = 0; }
         umma::fence_barrier_init();
     }
@@ -166,11 +170,12 @@ block_attention_bits_kernel(const unsigned long long* __restrict__ dmask, int W6
     // K / V tile of 64 source tokens -> one stage, by TMA (rows past T_SRC are zero-filled by the box)
     auto issue_tile = [&](int j) {
         const int s = j % kStages;
-        uint8_t* dst = kv + s * 2 * kTileBytes;
-        const int c0 = (int) slist[j] * kBN;
-        umma::mbar_arrive_expect_tx(&full[s], 2 * kTileBytes);
-        umma::tma_load_4d(dst, &tmap_k, &full[s], 0, c0, h, n);
-        umma::tma_load_4d(dst + kTileBytes, &tmap_v, &full[s], 0, c0, h, n);
+        uint8_t* dst = kv + s * kStageBytes;
+        const int tile = (int) slist[j];
+        umma::mbar_arrive_expect_tx(&full[s], kStageBytes);
+        umma::tma_load_4d(dst, &tmap_k, &full[s], 0, tile * kBN, h, n);
+        umma::tma_load_4d(dst + kTileBytes, &tmap_v, &full[s], 0, tile * kBN, h, n);
+        umma::tma_load_3d(dst + 2 * kTileBytes, &tmap_m, &full[s], (tile & ~1) * 2, r0, n * H + h);    // u32 columns of the tile pair
     };
     if (tid == 0)
         for (int j = 0; j < kStages && j < nact; ++j) issue_tile(j);
@@ -191,37 +196,43 @@ block_attention_bits_kernel(const unsigned long long* __restrict__ dmask, int W6
             qa[ks][3] = t1 < T_DST ? __ldg(q1 + ks * 8 + 4 + tq) : 0u;
         }
     }
-    float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+    float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f}, nms[2] = {0.f, 0.f};     // nms = -m_run * log2(e)
     float acc[kBD / 8][4];
 #pragma unroll
     for (int nt = 0; nt < kBD / 8; ++nt)
 #pragma unroll
         for (int i = 0; i < 4; ++i) acc[nt][i] = 0.f;
     constexpr float kLog2e = 1.4426950408889634f;
+    constexpr float kLazy = 8.0f / kLog2e;          // 2^8 in raw score units
     const uint32_t kv_base = umma::smem_u32(kv);
     // ldmatrix lane offsets inside a swizzled [64 x 128 B] tile: row * 128 + ((chunk ^ (row & 7)) << 4); row & 7 == lane & 7
     const uint32_t k_row_off = (uint32_t) ((lane & 7) + 8 * (lane >> 4)) * 128u, k_chunk = (uint32_t) ((lane >> 3) & 1);
     const uint32_t v_row_off = (uint32_t) ((lane & 7) + 8 * ((lane >> 3) & 1)) * 128u, v_chunk = (uint32_t) (lane >> 4);
     const uint32_t swz = (uint32_t) (lane & 7);
 
-    // element-mask words of this thread's rows g, g + 8 (one u64 per 64-token tile), prefetched one tile ahead
-    const int tr0 = min(r0 + warp * 16 + g, T_DST - 1), tr1 = min(r0 + warp * 16 + g + 8, T_DST - 1);
-    const unsigned long long* dm0 = dmask + (((int64_t) n * H + h) * T_DST + tr0) * W64;
-    const unsigned long long* dm1 = dmask + (((int64_t) n * H + h) * T_DST + tr1) * W64;
-    const bool ok0 = r0 + warp * 16 + g < T_DST, ok1 = r0 + warp * 16 + g + 8 < T_DST;
-    unsigned long long nmk0 = 0ull, nmk1 = 0ull;
-    if (nact > 0) { const int t0_ = slist[0]; nmk0 = ok0 ? __ldg(dm0 + t0_) : 0ull; nmk1 = ok1 ? __ldg(dm1 + t0_) : 0ull; }
+    const uint32_t full_addr = umma::smem_u32(full);
+    const uint32_t mrow_off = (uint32_t) (warp * 16 + g) * 16u;      // this thread's rows g, g + 8 inside a stage's mask block
+    int old_pending = -1, pending_it = 0;                            // deferred "was I the last releaser" check (lane 0)
 
     for (int it = 0; it < nact; ++it) {
         const int stage = it % kStages;
-        const uint32_t ks_addr = kv_base + (uint32_t) stage * 2u * kTileBytes;
+        const int tile = slist[it];
+        const uint8_t* st_ptr = kv + stage * kStageBytes;
+        const uint32_t ks_addr = kv_base + (uint32_t) stage * (uint32_t) kStageBytes;
         const uint32_t vs_addr = ks_addr + kTileBytes;
-        const unsigned long long mk0 = nmk0, mk1 = nmk1;
-        if (it + 1 < nact) { const int tn = slist[it + 1]; nmk0 = ok0 ? __ldg(dm0 + tn) : 0ull; nmk1 = ok1 ? __ldg(dm1 + tn) : 0ull; }
+        if (lane == 0 && old_pending == kBWarps - 1) {
+            // I was the last of the 8 warps to release the stage of tile pending_it: refill it (no warp ever waits to produce)
+            rel_cnt[pending_it % kStages] = 0;
+            __threadfence_block();
+            if (pending_it + kStages < nact) issue_tile(pending_it + kStages);
+        }
+        old_pending = -1;
+        umma::mbar_wait_addr(full_addr + 8u * (uint32_t) stage, (uint32_t) ((it / kStages) & 1));
+        const unsigned long long mk0 = *reinterpret_cast<const unsigned long long*>(st_ptr + 2 * kTileBytes + mrow_off + (tile & 1) * 8);
+        const unsigned long long mk1 = *reinterpret_cast<const unsigned long long*>(st_ptr + 2 * kTileBytes + mrow_off + 128 + (tile & 1) * 8);
         const uint32_t mlo0 = (uint32_t) mk0, mhi0 = (uint32_t) (mk0 >> 32), mlo1 = (uint32_t) mk1, mhi1 = (uint32_t) (mk1 >> 32);
         const uint32_t anyl = mlo0 | mlo1, anyh = mhi0 | mhi1;
         const uint32_t act = __reduce_or_sync(kFull, ((anyl & 0xffffu) ? 1u : 0u) | ((anyl >> 16) ? 2u : 0u) | ((anyh & 0xffffu) ? 4u : 0u) | ((anyh >> 16) ? 8u : 0u));
-        umma::mbar_wait(&full[stage], (uint32_t) ((it / kStages) & 1));
         if (act != 0u) {
             float sc[kBN / 8][4];
 #pragma unroll
@@ -239,20 +250,23 @@ block_attention_bits_kernel(const unsigned long long* __restrict__ dmask, int W6
                     }
                 }
             }
-            // masked scores (log2 domain) and the tile's row maxima
+            // masked raw scores and the tile's row maxima; the words are pre-shifted so that every test uses an immediate
+            const uint32_t sh2 = 2u * (uint32_t) tq;
+            const uint32_t r0lo = mlo0 >> sh2, r0hi = mhi0 >> sh2, r1lo = mlo1 >> sh2, r1hi = mhi1 >> sh2;
             float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
             for (int cg = 0; cg < 4; ++cg) {
                 if (SEA_BLOCK_DENSE_GROUPS || (act & (1u << cg))) {
-                    const uint32_t w0 = cg < 2 ? mlo0 : mhi0, w1 = cg < 2 ? mlo1 : mhi1;
+                    const uint32_t w0 = cg < 2 ? r0lo : r0hi, w1 = cg < 2 ? r1lo : r1hi;
 #pragma unroll
                     for (int j = 0; j < 2; ++j) {
                         const int nt = 2 * cg + j;
-                        const int bit = (nt & 3) * 8 + 2 * tq;
-                        sc[nt][0] = (w0 >> bit) & 1u ? sc[nt][0] * kLog2e : -INFINITY;
-                        sc[nt][1] = (w0 >> (bit + 1)) & 1u ? sc[nt][1] * kLog2e : -INFINITY;
-                        sc[nt][2] = (w1 >> bit) & 1u ? sc[nt][2] * kLog2e : -INFINITY;
-                        sc[nt][3] = (w1 >> (bit + 1)) & 1u ? sc[nt][3] * kLog2e : -INFINITY;
+                        constexpr uint32_t one = 1u;
+                        const uint32_t b0 = one << ((nt & 3) * 8), b1 = b0 << 1;
+                        sc[nt][0] = (w0 & b0) ? sc[nt][0] : -INFINITY;
+                        sc[nt][1] = (w0 & b1) ? sc[nt][1] : -INFINITY;
+                        sc[nt][2] = (w1 & b0) ? sc[nt][2] : -INFINITY;
+                        sc[nt][3] = (w1 & b1) ? sc[nt][3] : -INFINITY;
                         mx0 = fmaxf(mx0, fmaxf(sc[nt][0], sc[nt][1]));
                         mx1 = fmaxf(mx1, fmaxf(sc[nt][2], sc[nt][3]));
                     }
@@ -260,11 +274,16 @@ block_attention_bits_kernel(const unsigned long long* __restrict__ dmask, int W6
             }
             mx0 = fmaxf(mx0, __shfl_xor_sync(kFull, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(kFull, mx0, 2));
             mx1 = fmaxf(mx1, __shfl_xor_sync(kFull, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(kFull, mx1, 2));
-            const float mn0 = fmaxf(m_run[0], mx0), mn1 = fmaxf(m_run[1], mx1);
-            const float ms0 = mn0 == -INFINITY ? 0.f : mn0, ms1 = mn1 == -INFINITY ? 0.f : mn1;
-            const float al0 = ex2f(m_run[0] - ms0), al1 = ex2f(m_run[1] - ms1);     // m_run = -inf -> 0
-            m_run[0] = mn0; m_run[1] = mn1;
-            if (__any_sync(kFull, al0 != 1.0f || al1 != 1.0f)) {
+            // lazy rescaling: the reference maximum of a row only moves when the tile exceeds it by more than 2^8
+            // (probabilities stay <= 256, exact after the final normalisation because the same reference is used throughout)
+            if (__any_sync(kFull, mx0 > m_run[0] + kLazy || mx1 > m_run[1] + kLazy)) {
+                const float mn0 = mx0 > m_run[0] + kLazy ? mx0 : m_run[0], mn1 = mx1 > m_run[1] + kLazy ? mx1 : m_run[1];
+                const float al0 = mn0 == -INFINITY ? 1.f : ex2f((m_run[0] - mn0) * kLog2e);       // m_run = -inf -> 0
+                const float al1 = mn1 == -INFINITY ? 1.f : ex2f((m_run[1] - mn1) * kLog2e);
+                m_run[0] = mn0; m_run[1] = mn1;
+                nms[0] = mn0 == -INFINITY ? 0.f : -mn0 * kLog2e;
+                nms[1] = mn1 == -INFINITY ? 0.f : -mn1 * kLog2e;
+                l_run[0] *= al0; l_run[1] *= al1;
 #pragma unroll
                 for (int nt = 0; nt < kBD / 8; ++nt) { acc[nt][0] *= al0; acc[nt][1] *= al0; acc[nt][2] *= al1; acc[nt][3] *= al1; }
             }
@@ -274,10 +293,10 @@ block_attention_bits_kernel(const unsigned long long* __restrict__ dmask, int W6
                 if (SEA_BLOCK_DENSE_GROUPS || (act & (1u << cg))) {
                     uint32_t pa[4];
                     {
-                        const float p00 = ex2f(sc[2 * cg][0] - ms0), p01 = ex2f(sc[2 * cg][1] - ms0);
-                        const float p02 = ex2f(sc[2 * cg][2] - ms1), p03 = ex2f(sc[2 * cg][3] - ms1);
-                        const float p10 = ex2f(sc[2 * cg + 1][0] - ms0), p11 = ex2f(sc[2 * cg + 1][1] - ms0);
-                        const float p12 = ex2f(sc[2 * cg + 1][2] - ms1), p13 = ex2f(sc[2 * cg + 1][3] - ms1);
+                        const float p00 = ex2f(fmaf(sc[2 * cg][0], kLog2e, nms[0])), p01 = ex2f(fmaf(sc[2 * cg][1], kLog2e, nms[0]));
+                        const float p02 = ex2f(fmaf(sc[2 * cg][2], kLog2e, nms[1])), p03 = ex2f(fmaf(sc[2 * cg][3], kLog2e, nms[1]));
+                        const float p10 = ex2f(fmaf(sc[2 * cg + 1][0], kLog2e, nms[0])), p11 = ex2f(fmaf(sc[2 * cg + 1][1], kLog2e, nms[0]));
+                        const float p12 = ex2f(fmaf(sc[2 * cg + 1][2], kLog2e, nms[1])), p13 = ex2f(fmaf(sc[2 * cg + 1][3], kLog2e, nms[1]));
                         ps0 += (p00 + p01) + (p10 + p11);
                         ps1 += (p02 + p03) + (p12 + p13);
                         pa[0] = pack2b<T16>(p00, p01); pa[1] = pack2b<T16>(p02, p03);
@@ -292,21 +311,17 @@ block_attention_bits_kernel(const unsigned long long* __restrict__ dmask, int W6
                     }
                 }
             }
-            l_run[0] = l_run[0] * al0 + ps0;
-            l_run[1] = l_run[1] * al1 + ps1;
+            l_run[0] += ps0;
+            l_run[1] += ps1;
         }
         __syncwarp();                                   // every lane is done reading the stage
         if (lane == 0) {
-            // the last of the 8 warps to release a stage refills it with tile it + kStages: no warp ever waits to produce
             __threadfence_block();
-            const int old = atomicAdd(&rel_cnt[stage], 1);
-            if (old == kBWarps - 1) {
-                rel_cnt[stage] = 0;
-                __threadfence_block();
-                if (it + kStages < nact) issue_tile(it + kStages);
-            }
+            old_pending = atomicAdd(&rel_cnt[stage], 1);      // consumed at the top of the next iteration: the round trip is hidden
+            pending_it = it;
         }
     }
+    if (lane == 0 && old_pending == kBWarps - 1) rel_cnt[pending_it % kStages] = 0;
 
     // ---- epilogue: normalise, * sigmoid(s0), mix with the running mean, permuted store ----------------------------------
     l_run[0] += __shfl_xor_sync(kFull, l_run[0], 1); l_run[0] += __shfl_xor_sync(kFull, l_run[0], 2);
@@ -442,13 +457,21 @@ int sea_block_attention_fwd(const uint32_t* mask_bits,
         rc = make_tmap_bf16_sw128(&t_v, const_cast<void*>(v), 4, dims, vs, box);
         if (rc) return rc;
     }
-    const size_t smem = 1024 + (size_t) kStages * 2 * kTileBytes + kMaxTileWords * 4 + kStages * 8 + kStages * 4 + (size_t) ((max_tiles + 7) & ~7) * 2;
+    CUtensorMap t_m;
+    {
+        const uint64_t dims[3] = {(uint64_t) W64 * 2, (uint64_t) T_DST, (uint64_t) N * H};
+        const uint64_t str[2] = {(uint64_t) W64 * 8, (uint64_t) T_DST * W64 * 8};
+        const uint32_t box[3] = {4, (uint32_t) kBM, 1};
+        int rc = make_tmap_u32_plain(&t_m, dmask, 3, dims, str, box);
+        if (rc) return rc;
+    }
+    const size_t smem = 1024 + (size_t) kStages * kStageBytes + kMaxTileWords * 4 + kStages * 8 + kStages * 4 + (size_t) ((max_tiles + 7) & ~7) * 2;
     const unsigned grid = (unsigned) ((int64_t) n_row_blocks * N * H);
 #define SEA_BLOCK_ATTN(TT)                                                                                                       \
     do {                                                                                                                         \
         auto kern = block_attention_bits_kernel<TT>;                                                                             \
         SEA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem), "smem attr");          \
-        kern<<<grid, kBThreads, smem, s>>>(dmask, W64, (const TT*) q, q_sn, q_sh, q_st, t_k, t_v, scales, (const TT*) cumavg,    \
+        kern<<<grid, kBThreads, smem, s>>>(dmask, W64, (const TT*) q, q_sn, q_sh, q_st, t_k, t_v, t_m, scales, (const TT*) cumavg,    \
             avg_sh, avg_st, use_scaler, (TT*) out, N, H, T_DST, T_SRC, is_causal, n_row_blocks, max_tiles);                      \
     } while (0)
     if (dtype == SEA_DTYPE_BF16) SEA_BLOCK_ATTN(__nv_bfloat16); else SEA_BLOCK_ATTN(__half);

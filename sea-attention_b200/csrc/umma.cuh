@@ -40,6 +40,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {
     }
 }
+// same, on a precomputed shared-window address (keeps the generic->shared conversion out of hot loops)
+__device__ __forceinline__ void mbar_wait_addr(uint32_t bar_addr, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t}"
+        ::"r"(bar_addr), "r"(parity)
+        : "memory");
+}
 
 // ---------------------------------------------------------------- TMA
 __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* m) {
@@ -141,5 +153,8 @@ PFN_encodeTiled get_encode_tiled();
 // bf16 tensor map with 128B swizzle; dims/strides innermost first (strides in BYTES for dims 1..rank-1)
 int make_tmap_bf16_sw128(CUtensorMap* out, void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                          const uint32_t* box);
+// uint32 tensor map, no swizzle (plain row-major box in shared memory)
+int make_tmap_u32_plain(CUtensorMap* out, void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                        const uint32_t* box);
 
 }  // namespace sea

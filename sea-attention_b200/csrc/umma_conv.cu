@@ -49,6 +49,25 @@ int make_tmap_bf16_sw128(CUtensorMap* out, void* base, int rank, const uint64_t*
     return SEA_OK;
 }
 
+int make_tmap_u32_plain(CUtensorMap* out, void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box) {
+    PFN_encodeTiled enc = get_encode_tiled();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled is not available (driver entry point lookup failed)");
+        return SEA_ERR_CUDA;
+    }
+    cuuint64_t d[5], s[4];
+    cuuint32_t b[5], e[5];
+    for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; e[i] = 1; }
+    for (int i = 0; i + 1 < rank; ++i) s[i] = strides_bytes[i];
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_UINT32, (cuuint32_t) rank, base, d, s, b, e, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled (u32) failed with CUresult %d", (int) r);
+        return SEA_ERR_CUDA;
+    }
+    return SEA_OK;
+}
+
 namespace {
 
 constexpr int kStages = 8;
