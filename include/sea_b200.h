@@ -175,7 +175,8 @@ SEA_API int sea_predictor_mlp_fwd(const void* ctx, const void* v, int64_t v_sn, 
 /* a4 on the tensor cores (bf16 only; csrc/umma_mlp.cu): same computation as sea_predictor_mlp_fwd with both Linear
  * layers as chained tcgen05 GEMMs per 128-token tile (intermediates stay in TMEM / shared memory).  Shapes: D = 64,
  * S = 2, H | 128, W in {16,32,64}; ctx contiguous [N,H,T,2D] bf16; cnn_in bf16 [N,T,W,2H]; no t_pred output.
- * workspace: >= sea_predictor_mlp_umma_workspace_bytes() bytes, 128-byte aligned. */
+ * workspace: >= sea_predictor_mlp_umma_workspace_bytes() bytes, 128-byte aligned.  The call re-packs enc_w / dec_w / scl_w
+ * into it; passing all three as NULL reuses the packing a previous call left in `workspace` (inference: weights are constant). */
 SEA_API int sea_predictor_mlp_umma_supported(int dtype, int H, int D, int S, int W);
 SEA_API int64_t sea_predictor_mlp_umma_workspace_bytes(void);
 SEA_API int sea_predictor_mlp_umma_fwd(const void* ctx, const void* v, int64_t v_sn, int64_t v_sh, int64_t v_st,
@@ -193,7 +194,8 @@ SEA_API int sea_causal_conv3x3_dil2_relu(const void* x, const float* weight, con
 
 /* a5 on the tensor cores (bf16 only): the same CausalConv2d + ReLU as an implicit GEMM with tcgen05.mma / TMEM /
  * TMA (csrc/umma_conv.cu).  Shapes: C = O = 64, W a divisor of 128; sea_conv_umma_supported() tells.
- * workspace: >= sea_conv_umma_workspace_bytes(C, O) bytes, 128-byte aligned (bf16 re-packed weights).
+ * workspace: >= sea_conv_umma_workspace_bytes(C, O) bytes, 128-byte aligned (bf16 re-packed weights); weight == NULL
+ * reuses the packing a previous call with the same weights left in `workspace`.
  * sea_conv1x1_umma: the 1x1 CausalConv2d(C=64 -> O=32) of attention.py:276 evaluated BEFORE the nearest x4
  * upsample (they commute): y [N,T,W,O] fp32 = x . Wt^T + b. */
 SEA_API int sea_conv_umma_supported(int dtype, int W, int C, int O);

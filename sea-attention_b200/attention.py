@@ -206,6 +206,7 @@ class PerlinAttention(nn.Module):
         max_pos = config.max_position_embeddings if hasattr(config, 'max_position_embeddings') else 2048
         self.v_eye_learned_causal = nn.Parameter(torch.randn((1, 1, max_pos, d)))
         self._shape_cache = {}
+        self._packed = ops.PackedWeights()
 
     # ------------------------------------------------------------------------------------------------
     def _weights_fp32(self):
@@ -287,14 +288,19 @@ class PerlinAttention(nn.Module):
         # a2+a3 (+ running mean for a13)
         ctx, cumavg = ops.performer_causal(q_for_atten, k_for_atten, v, w['pos'], w['proj'])
         # a4
-        cnn_in, scales, _ = ops.predictor_mlp(ctx, v, w, S, W)
+        # (weight packings of the tensor-core kernels are cached per module and re-made only when a parameter changes)
+        pk = self._packed
+        enc, dec, scl = self.attention_predictor_enc, self.attention_predictor_dec_row, self.attention_predictor_dec_scaler
+        net = self.attention_predictor_cnn[1].module.net
+        w['_src_mlp'] = (enc[0].weight, dec[0].weight, scl[0].weight)
+        cnn_in, scales, _ = ops.predictor_mlp(ctx, v, w, S, W, packed=pk)
         # a5 .. a7
         kpr = k_per_row.repeat(N) if N > 1 else k_per_row
-        y = ops.causal_conv3x3_dil2_relu(cnn_in, w['conv1_w'], w['conv1_b'])
-        y = ops.causal_conv3x3_dil2_relu(y, w['conv2_w'], w['conv2_b'])
+        y = ops.causal_conv3x3_dil2_relu(cnn_in, w['conv1_w'], w['conv1_b'], packed=pk, slot='conv1', src=net[0].module.weight)
+        y = ops.causal_conv3x3_dil2_relu(y, w['conv2_w'], w['conv2_b'], packed=pk, slot='conv2', src=net[2].module.weight)
         if q.dtype == torch.bfloat16 and ops.conv_umma_supported(q.dtype, W, S * H, H) and P % 32 == 0:
             # tensor-core path: 1x1 conv before the upsample (tcgen05), then tail + softmax + top-k in one kernel
-            y3 = ops.conv1x1_umma(y, w['conv3_w'], w['conv3_b'])
+            y3 = ops.conv1x1_umma(y, w['conv3_w'], w['conv3_b'], packed=pk, slot='conv3', src=net[5].module.weight)
             res = ops.predictor_tail_topk(y3, w['conv3_b'], w['out_ln_w'], w['out_ln_b'], kpr, P, count_k=pc.k if self.output_attentions else 0)
             probs, bits, crow_counts = res if len(res) == 3 else (res[0], res[1], None)
         else:

@@ -247,7 +247,8 @@ int launch_conv_umma(const void* x, const float* weight, const float* bias, void
     using SM = ConvSmem<kTaps, kNOut>;
     __nv_bfloat16* wpack = reinterpret_cast<__nv_bfloat16*>(ws);
     const int nel = kTaps * kNOut * C;
-    pack_conv_weights_kernel<<<(nel + 255) / 256, 256, 0, s>>>(weight, wpack, kNOut, C, kTaps);
+    if (weight != nullptr)          // nullptr: `workspace` still holds the packing of an earlier call with the same weights
+        pack_conv_weights_kernel<<<(nel + 255) / 256, 256, 0, s>>>(weight, wpack, kNOut, C, kTaps);
     SEA_CHECK_LAUNCH("pack_conv_weights_kernel");
     const int TR = 128 / W;
     CUtensorMap tx, tw;
@@ -293,7 +294,7 @@ int64_t sea_conv_umma_workspace_bytes(int C, int O) { return (int64_t) 9 * O * C
 
 int sea_causal_conv3x3_dil2_relu_umma(const void* x, const float* weight, const float* bias, void* y, void* workspace,
                                       int N, int T, int W, int C, int O, void* stream) {
-    SEA_CHECK_ARG(x && weight && bias && y && workspace, "sea_causal_conv3x3_dil2_relu_umma: null pointer");
+    SEA_CHECK_ARG(x && bias && y && workspace, "sea_causal_conv3x3_dil2_relu_umma: null pointer");
     SEA_CHECK_ARG(N > 0 && T > 0, "sea_causal_conv3x3_dil2_relu_umma: bad shape");
     if (!sea_conv_umma_supported(SEA_DTYPE_BF16, W, C, O) || O != 64) {
         set_error("sea_causal_conv3x3_dil2_relu_umma: unsupported shape W=%d C=%d O=%d (need C=O=64, W | 128)", W, C, O);
@@ -306,7 +307,7 @@ int sea_causal_conv3x3_dil2_relu_umma(const void* x, const float* weight, const 
 
 int sea_conv1x1_umma(const void* x, const float* weight, const float* bias, float* y, void* workspace,
                      int N, int T, int W, int C, int O, void* stream) {
-    SEA_CHECK_ARG(x && weight && bias && y && workspace, "sea_conv1x1_umma: null pointer");
+    SEA_CHECK_ARG(x && bias && y && workspace, "sea_conv1x1_umma: null pointer");
     if (!sea_conv_umma_supported(SEA_DTYPE_BF16, W, C, O) || O != 32) {
         set_error("sea_conv1x1_umma: unsupported shape W=%d C=%d O=%d (need C=64, O=32, W | 128)", W, C, O);
         return SEA_ERR_UNSUPPORTED;

@@ -292,7 +292,7 @@ int sea_predictor_mlp_umma_fwd(const void* ctx, const void* v, int64_t v_sn, int
                                const float* dec_w, const float* dec_b, const float* cnn_ln_w, const float* cnn_ln_b,
                                const float* scl_w, const float* scl_b, void* cnn_in, float* scales, void* workspace,
                                int N, int H, int T, int D, int S, int W, void* stream) {
-    SEA_CHECK_ARG(ctx && v && enc_w && enc_b && enc_ln_w && enc_ln_b && dec_w && dec_b && cnn_ln_w && cnn_ln_b && scl_w && scl_b &&
+    SEA_CHECK_ARG(ctx && v && enc_b && enc_ln_w && enc_ln_b && dec_b && cnn_ln_w && cnn_ln_b && scl_b && ((enc_w && dec_w && scl_w) || (!enc_w && !dec_w && !scl_w)) &&
                   cnn_in && scales && workspace, "sea_predictor_mlp_umma_fwd: null pointer");
     if (!sea_predictor_mlp_umma_supported(SEA_DTYPE_BF16, H, D, S, W)) {
         set_error("sea_predictor_mlp_umma_fwd: unsupported shape H=%d D=%d S=%d W=%d", H, D, S, W);
@@ -305,7 +305,8 @@ int sea_predictor_mlp_umma_fwd(const void* ctx, const void* v, int64_t v_sn, int
     __nv_bfloat16* w1 = reinterpret_cast<__nv_bfloat16*>(workspace);
     __nv_bfloat16* w2 = w1 + kD2 * kD3;
     const int SW = S * W;
-    pack_mlp_weights_kernel<<<(kD2 * kD3 + 255) / 256, 256, 0, s>>>(enc_w, dec_w, scl_w, w1, w2, SW);
+    if (enc_w != nullptr)           // all three weights nullptr: `workspace` still holds the packing of an earlier call
+        pack_mlp_weights_kernel<<<(kD2 * kD3 + 255) / 256, 256, 0, s>>>(enc_w, dec_w, scl_w, w1, w2, SW);
     SEA_CHECK_LAUNCH("pack_mlp_weights_kernel");
     const int TT = 128 / H;
     CUtensorMap t_ctx, t_v, t_w1, t_w2;

@@ -269,7 +269,25 @@ def performer_causal(q, k, v, pos_emb, proj, want_cumavg=True, force_simt=False)
     return ctx, avg
 
 
-def predictor_mlp(ctx, v, w, S: int, W: int, want_t_pred=False, force_simt=False):
+class PackedWeights:
+    """Per-module cache of the bf16 weight packings the tensor-core kernels keep in their workspace: a packing is reused
+    (weight pointer NULL in the C call) as long as the source tensors' (data_ptr, _version) are unchanged."""
+
+    def __init__(self):
+        self._slots = {}
+
+    def get(self, slot, sources, nbytes, device):
+        """-> (workspace tensor, fresh): fresh = the caller must let the kernel re-pack."""
+        stamp = tuple((int(t.data_ptr()), int(t._version)) for t in sources) + (str(device), int(nbytes))
+        hit = self._slots.get(slot)
+        if hit is not None and hit[0] == stamp:
+            return hit[1], False
+        ws = torch.empty((nbytes,), dtype=torch.uint8, device=device)
+        self._slots[slot] = (stamp, ws)
+        return ws, True
+
+
+def predictor_mlp(ctx, v, w, S: int, W: int, want_t_pred=False, force_simt=False, packed: 'PackedWeights' = None):
     """a4.  `w` = dict of fp32 contiguous weights (enc_w, enc_b, enc_ln_w, enc_ln_b, dec_w, dec_b, cnn_ln_w, cnn_ln_b,
     scl_w, scl_b) -> cnn_in [N,T,W,H*S] channels-last, scales fp32 [N,H,T,2], t_pred or None."""
     _cuda(ctx, v)
@@ -282,11 +300,16 @@ def predictor_mlp(ctx, v, w, S: int, W: int, want_t_pred=False, force_simt=False
     if (not want_t_pred and not force_simt and ctx.is_contiguous() and w.get('cnn_ln_w') is not None
             and lib.sea_predictor_mlp_umma_supported(_DTYPES.get(ctx.dtype, -1), H, D, S, W)
             and v.stride(0) % 8 == 0 and v.stride(1) % 8 == 0 and v.stride(2) % 8 == 0):
-        ws = torch.empty((lib.sea_predictor_mlp_umma_workspace_bytes(),), dtype=torch.uint8, device=ctx.device)
+        nbytes = lib.sea_predictor_mlp_umma_workspace_bytes()
+        if packed is not None:
+            ws, fresh = packed.get('mlp', w.get('_src_mlp', (w['enc_w'], w['dec_w'], w['scl_w'])), nbytes, ctx.device)
+        else:
+            ws, fresh = torch.empty((nbytes,), dtype=torch.uint8, device=ctx.device), True
+        wp = (lambda t: t.data_ptr()) if fresh else (lambda t: None)
         _lib.call('sea_predictor_mlp_umma_fwd', ctx.data_ptr(), v.data_ptr(), v.stride(0), v.stride(1), v.stride(2),
-                  w['enc_w'].data_ptr(), w['enc_b'].data_ptr(), w['enc_ln_w'].data_ptr(), w['enc_ln_b'].data_ptr(),
-                  w['dec_w'].data_ptr(), w['dec_b'].data_ptr(), w['cnn_ln_w'].data_ptr(), w['cnn_ln_b'].data_ptr(),
-                  w['scl_w'].data_ptr(), w['scl_b'].data_ptr(), cnn_in.data_ptr(), scales.data_ptr(), ws.data_ptr(),
+                  wp(w['enc_w']), w['enc_b'].data_ptr(), w['enc_ln_w'].data_ptr(), w['enc_ln_b'].data_ptr(),
+                  wp(w['dec_w']), w['dec_b'].data_ptr(), w['cnn_ln_w'].data_ptr(), w['cnn_ln_b'].data_ptr(),
+                  wp(w['scl_w']), w['scl_b'].data_ptr(), cnn_in.data_ptr(), scales.data_ptr(), ws.data_ptr(),
                   N, H, T, D, S, W, _stream())
         return cnn_in, scales, None
     t_pred = torch.empty((N, H, T, D2), dtype=ctx.dtype, device=ctx.device) if want_t_pred else None
@@ -306,7 +329,15 @@ def _conv_ws(C, O, device):
     return torch.empty((_lib.load().sea_conv_umma_workspace_bytes(C, O),), dtype=torch.uint8, device=device)
 
 
-def causal_conv3x3_dil2_relu(x, weight, bias, force_simt=False):
+def _packed_conv_ws(packed, slot, weight, src, C, O, device):
+    nbytes = _lib.load().sea_conv_umma_workspace_bytes(C, O)
+    if packed is None:
+        return torch.empty((nbytes,), dtype=torch.uint8, device=device), weight.data_ptr()
+    ws, fresh = packed.get(slot, (src if src is not None else weight,), nbytes, device)
+    return ws, (weight.data_ptr() if fresh else None)
+
+
+def causal_conv3x3_dil2_relu(x, weight, bias, force_simt=False, packed: 'PackedWeights' = None, slot: str = 'conv', src=None):
     """a5: one CausalConv2d(C,O,3,padding=2,dilation=2,causal)+ReLU on channels-last x [N,T,W,C];
     weight fp32 in the reference layout [O,C,5,3].  bf16 with C=O=64 runs the tcgen05 implicit-GEMM kernel,
     everything else the fp32 SIMT kernel."""
@@ -315,8 +346,8 @@ def causal_conv3x3_dil2_relu(x, weight, bias, force_simt=False):
     O = weight.shape[0]
     y = torch.empty((N, T, W, O), dtype=x.dtype, device=x.device)
     if not force_simt and O == 64 and conv_umma_supported(x.dtype, W, C, O):
-        ws = _conv_ws(C, O, x.device)
-        _lib.call('sea_causal_conv3x3_dil2_relu_umma', x.data_ptr(), weight.data_ptr(), bias.data_ptr(), y.data_ptr(), ws.data_ptr(),
+        ws, wptr = _packed_conv_ws(packed, slot, weight, src, C, O, x.device)
+        _lib.call('sea_causal_conv3x3_dil2_relu_umma', x.data_ptr(), wptr, bias.data_ptr(), y.data_ptr(), ws.data_ptr(),
                   N, T, W, C, O, _stream())
         return y
     _lib.call('sea_causal_conv3x3_dil2_relu', x.data_ptr(), weight.data_ptr(), bias.data_ptr(), y.data_ptr(), _dtype_code(x),
@@ -324,14 +355,14 @@ def causal_conv3x3_dil2_relu(x, weight, bias, force_simt=False):
     return y
 
 
-def conv1x1_umma(x, weight, bias):
+def conv1x1_umma(x, weight, bias, packed: 'PackedWeights' = None, slot: str = 'conv1x1', src=None):
     """1x1 CausalConv2d(64 -> 32) before the upsample, tcgen05: x bf16 [N,T,W,64] -> y fp32 [N,T,W,32]."""
     _cuda(x, weight, bias)
     N, T, W, C = x.shape
     O = weight.shape[0]
     y = torch.empty((N, T, W, O), dtype=torch.float32, device=x.device)
-    ws = _conv_ws(C, O, x.device)
-    _lib.call('sea_conv1x1_umma', x.data_ptr(), weight.data_ptr(), bias.data_ptr(), y.data_ptr(), ws.data_ptr(), N, T, W, C, O, _stream())
+    ws, wptr = _packed_conv_ws(packed, slot, weight, src, C, O, x.device)
+    _lib.call('sea_conv1x1_umma', x.data_ptr(), wptr, bias.data_ptr(), y.data_ptr(), ws.data_ptr(), N, T, W, C, O, _stream())
     return y
 
 

@@ -177,6 +177,29 @@ def test_layer_forward_bf16(sea):
     torch.testing.assert_close(out2.context_layer.float().cpu(), out.context_layer.float().cpu(), rtol=2e-2, atol=2e-2)
 
 
+def test_packed_weight_cache_follows_parameter_updates(sea):
+    """The tensor-core kernels keep bf16 weight packings per module; an in-place parameter update must invalidate them."""
+    import copy
+    N, H, d, T, P, k, nbf = 1, 32, 64, 128, 64, 16, 8          # H | 128, W = 16: tcgen05 MLP + conv path
+    mod, _ = _random_sd(sea, H, d, T, P, k, nbf, seed=5)
+    mod = mod.to(DEV)
+    g = torch.Generator().manual_seed(6)
+    mk = lambda s: (torch.randn(N, H, T, d, generator=g) * s).bfloat16().to(DEV)
+    q, kk, v = mk(d ** -0.5), mk(1.0), mk(1.0)
+    am = so.causal_additive_mask(T, torch.bfloat16, N).to(DEV)
+    run = lambda m: m(q, kk, v, q, kk, v, q, kk, am, None, None).estimated_attention_probs.float().cpu()
+    p0 = run(mod)
+    torch.testing.assert_close(run(mod), p0, rtol=0, atol=0)                       # second call: cached packings, same result
+    with torch.no_grad():
+        mod.attention_predictor_cnn[1].module.net[0].module.weight.mul_(1.7)
+        mod.attention_predictor_enc[0].weight.mul_(0.6)
+    p1 = run(mod)
+    fresh = copy.deepcopy(mod)
+    fresh._packed = sea.ops.PackedWeights()
+    torch.testing.assert_close(p1, run(fresh), rtol=0, atol=0)
+    assert float((p1 - p0).abs().max()) > 0
+
+
 def test_unsupported_modes_fail_loudly(sea):
     mod, sd = _random_sd(sea, 2, 32, 16, 8, 4, 8)
     mod = mod.to(DEV)
