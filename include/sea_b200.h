@@ -271,6 +271,21 @@ SEA_API int sea_block_attention_fwd(const uint32_t* mask_bits,
                                     int N, int H, int T_DST, int T_SRC, int D, int P, int k_clamp, int is_causal,
                                     void* workspace, int64_t workspace_bytes, void* stream);
 
+/* Backward of sea_sparse_attention_bits_fwd / sea_block_attention_fwd (csrc/sparse_attn_bwd.cu).  The reference has
+ * no sparse backward kernel: its training path lets autograd differentiate the dense masked attention
+ * (attention.py:1066-1133); this entry returns that gradient restricted to the alive (row, source token) pairs of the bit mask.
+ *   dout [N,T_DST,H*D] (`dtype`) = grad of the forward output;  dq [N,H,T_DST,D], dk, dv [N,H,T_SRC,D] fp32 contiguous
+ *   (dk / dv are zeroed here and accumulated with atomics);  dscales fp32 [N,H,T_DST,2] (nullable) = grad of the two scaler
+ *   logits (attention.py:1166-1171, 1242-1244).  cumavg non-NULL adds the running-mean branch (causal prefill only).
+ * The top-k mask is piecewise constant: no gradient flows through it.  D % 8 == 0, D <= 128, P % 32 == 0, P <= 1024. */
+SEA_API int sea_sparse_attention_bits_bwd(const uint32_t* mask_bits,
+                                          const void* q, int64_t q_sn, int64_t q_sh, int64_t q_st,
+                                          const void* k, int64_t k_sn, int64_t k_sh, int64_t k_st,
+                                          const void* v, int64_t v_sn, int64_t v_sh, int64_t v_st,
+                                          const float* scales, const void* cumavg, int64_t avg_sh, int64_t avg_st, int use_scaler, int dtype,
+                                          const void* dout, float* dq, float* dk, float* dv, float* dscales,
+                                          int N, int H, int T_DST, int T_SRC, int D, int P, int k_clamp, int is_causal, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Non-causal (BERT) variant, csrc/noncausal.cu.  No padding.
  * sea_performer_noncausal_fwd: v_for_atten = cat(grid-sampled identity, v) (attention.py:462-502) and the FAVOR+

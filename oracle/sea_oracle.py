@@ -591,3 +591,27 @@ def perlin_forward_noncausal(sd: Dict[str, torch.Tensor], q, k, v, *, k_top: int
     out = ctx * a + (1 - a) * avg
     buf['context_layer'] = out.permute(0, 2, 1, 3).reshape(N, T, H * d).contiguous()
     return buf
+
+
+def sparse_attention_grads(alive: torch.Tensor, q, k, v, scales, dout, use_scaler: bool = True, with_avg: bool = True):
+    """Gradient of the masked attention + scaler + running-mean mix w.r.t. (q, k, v, scales), by autograd in fp64.
+    alive: bool [N,H,T_DST,T_SRC] (densified partial_attention_mask).  Follows the reference's dense training expression
+    (attention.py:1066-1133 masked softmax, :1166-1171 scaler, :1237-1244 running mean) restricted to the mask -- the
+    parity target of sea_sparse_attention_bits_bwd.  dout: [N,T_DST,H*D].  Returns (out, dq, dk, dv, dscales)."""
+    N, H, T_DST, D = q.shape
+    T_SRC = k.shape[2]
+    q_, k_, v_, s_ = (t.detach().double().requires_grad_(True) for t in (q, k, v, scales))
+    scores = torch.einsum('nhtd,nhsd->nhts', q_, k_).masked_fill(~alive, float('-inf'))
+    has_any = alive.any(-1, keepdim=True)
+    probs = torch.softmax(scores.masked_fill(~has_any, 0.0), dim=-1) * alive
+    ctx = torch.einsum('nhts,nhsd->nhtd', probs, v_)
+    if use_scaler:
+        ctx = ctx * torch.sigmoid(s_[..., 0:1])
+    if with_avg:
+        assert T_SRC == T_DST
+        avg = torch.cumsum(v_, dim=2) / torch.arange(1, T_SRC + 1, dtype=torch.float64).view(1, 1, -1, 1)
+        a = torch.sigmoid(s_[..., 1:2])
+        ctx = ctx * a + (1 - a) * avg
+    out = ctx.permute(0, 2, 1, 3).reshape(N, T_DST, H * D)
+    out.backward(dout.double())
+    return out.detach().float(), q_.grad.float(), k_.grad.float(), v_.grad.float(), s_.grad.float()

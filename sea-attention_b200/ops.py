@@ -459,6 +459,53 @@ def sparse_attention_from_bits(bits, q, k, v, scales, cumavg, P: int, k_clamp: i
     return out
 
 
+def sparse_attention_from_bits_backward(bits, q, k, v, scales, cumavg, dout, P: int, k_clamp: int, use_scaler=True, is_causal=True):
+    """Gradient of sparse_attention_from_bits w.r.t. (q, k, v, scales), restricted to the alive pairs of the bit mask
+    (SURVEY 8f-1).  Returns fp32 (dq [N,H,T_DST,D], dk, dv [N,H,T_SRC,D], dscales [N,H,T_DST,2]).  The running-mean branch
+    (cumavg) contributes to dv; the mask itself carries no gradient."""
+    _cuda(bits, q, k, v, scales, dout)
+    N, H, T_DST, D = q.shape
+    T_SRC = k.shape[2]
+    q, k, v = _inner_contig(q), _inner_contig(k), _inner_contig(v)
+    dout = dout.to(q.dtype).contiguous()
+    sc = scales.float().contiguous()
+    ca, avg_sh, avg_st = _avg_arg(cumavg, N, H, T_DST, D)
+    dq = torch.empty((N, H, T_DST, D), dtype=torch.float32, device=q.device)
+    dk = torch.empty((N, H, T_SRC, D), dtype=torch.float32, device=q.device)
+    dv = torch.empty((N, H, T_SRC, D), dtype=torch.float32, device=q.device)
+    dsc = torch.empty((N, H, T_DST, 2), dtype=torch.float32, device=q.device)
+    _lib.call('sea_sparse_attention_bits_bwd', bits.data_ptr(), q.data_ptr(), q.stride(0), q.stride(1), q.stride(2),
+              k.data_ptr(), k.stride(0), k.stride(1), k.stride(2), v.data_ptr(), v.stride(0), v.stride(1), v.stride(2),
+              sc.data_ptr(), _p(ca), avg_sh, avg_st, int(bool(use_scaler)), _dtype_code(q), dout.data_ptr(), dq.data_ptr(), dk.data_ptr(),
+              dv.data_ptr(), dsc.data_ptr(), N, H, T_DST, T_SRC, D, int(P), int(k_clamp), int(bool(is_causal)), _stream())
+    return dq, dk, dv, dsc
+
+
+class SparseAttentionFromBits(torch.autograd.Function):
+    """autograd wrapper: forward = sparse_attention_from_bits, backward = sea_sparse_attention_bits_bwd.  `cumavg` is
+    recomputed as the running mean of v inside the graph by the caller when it must receive gradient; here it is treated
+    as the forward's own function of v (the kernel adds its dv term)."""
+
+    @staticmethod
+    def forward(ctx, bits, q, k, v, scales, cumavg, P, k_clamp, use_scaler, is_causal):
+        out = sparse_attention_from_bits(bits, q, k, v, scales, cumavg, P, k_clamp, use_scaler, is_causal)
+        ctx.save_for_backward(bits, q, k, v, scales, cumavg)
+        ctx.cfg = (P, k_clamp, use_scaler, is_causal)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        bits, q, k, v, scales, cumavg = ctx.saved_tensors
+        P, k_clamp, use_scaler, is_causal = ctx.cfg
+        dq, dk, dv, dsc = sparse_attention_from_bits_backward(bits, q, k, v, scales, cumavg, dout, P, k_clamp, use_scaler, is_causal)
+        return None, dq.to(q.dtype), dk.to(k.dtype), dv.to(v.dtype), dsc.to(scales.dtype), None, None, None, None, None
+
+
+def sparse_attention_from_bits_autograd(bits, q, k, v, scales, cumavg, P: int, k_clamp: int, use_scaler=True, is_causal=True):
+    """Differentiable form of sparse_attention_from_bits (q, k, v, scales receive gradient)."""
+    return SparseAttentionFromBits.apply(bits, q, k, v, scales, cumavg, int(P), int(k_clamp), bool(use_scaler), bool(is_causal))
+
+
 def attention_bits_supported(dtype, D: int, P: int) -> bool:
     return dtype in (torch.bfloat16, torch.float16) and D in (32, 64, 128) and P % 32 == 0 and P <= 1024
 

@@ -120,3 +120,24 @@ def test_bert_layer_oracle_matches_reference():
         else:
             assert np.array_equal(_bits(g, 'dense.partial_attention_mask_alive', (1, H, T, T)), b['partial_attention_mask'].numpy().astype(np.uint8))
             torch.testing.assert_close(b['context_layer'], torch.from_numpy(g['dense.partial_context_layer']), rtol=1e-3, atol=2e-5)
+
+
+@pytest.mark.parametrize('name', LAYERS)
+def test_backward_oracle_forward_matches_reference_dense_path(name):
+    """Pins the expression oracle.sparse_attention_grads differentiates to the reference: on the reference's own
+    mask, q, k, v and estimated_scales its forward value equals the reference dense path's partial_context_layer."""
+    g, meta, sd = golden_layer(name)
+    q, k, v = (torch.from_numpy(g[x]) for x in ('q', 'k', 'v'))
+    N, H, T, d = q.shape
+    alive = torch.from_numpy(_bits(g, 'dense.partial_attention_mask_alive', (N, H, T, T)).astype(bool))
+    scales = torch.from_numpy(g['dense.estimated_scales'])
+    dout = torch.ones(N, T, H * d)
+    out, dq, dk, dv, ds = so.sparse_attention_grads(alive, q, k, v, scales, dout, use_scaler=True, with_avg=True)
+    torch.testing.assert_close(out, torch.from_numpy(g['dense.partial_context_layer']), rtol=1e-4, atol=1e-5)
+    # finite-difference spot check of the gradient itself (fp64 autograd vs central differences on one coordinate)
+    eps = 1e-3
+    qp, qm = q.clone(), q.clone()
+    qp[0, 1, 7, 3] += eps; qm[0, 1, 7, 3] -= eps
+    fp = so.sparse_attention_grads(alive, qp, k, v, scales, dout)[0].double().sum()
+    fm = so.sparse_attention_grads(alive, qm, k, v, scales, dout)[0].double().sum()
+    assert abs(float((fp - fm) / (2 * eps)) - float(dq[0, 1, 7, 3])) < 5e-3 * max(1.0, abs(float(dq[0, 1, 7, 3])))
