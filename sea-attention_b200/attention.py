@@ -310,8 +310,15 @@ class PerlinAttention(nn.Module):
         if not self.output_attentions and ops.attention_bits_supported(q.dtype, d, P):
             # a8 + a9-a14 in one kernel: the CSR column list is a pure function of the bit mask, so it is only
             # materialised when the caller asks for the CSR tensors (output_attentions)
-            context = ops.sparse_attention_from_bits(bits, q_for_score, k_for_score, v, scales, cumavg, P, pc.k,
-                                                     use_scaler=pc.partial_attention_scaler, is_causal=True)
+            if torch.is_grad_enabled() and any(t.requires_grad for t in (q_for_score, k_for_score, v)):
+                # training through the sparse path: q, k, v receive the gradient of the masked attention, the
+                # scaler and the running-mean mix; the predictor (Performer / MLP / CNN -> mask, scales) is not differentiated
+                # here -- in the reference it learns from its own distillation losses (attention.py:707-765), not built yet
+                context = ops.sparse_attention_from_bits_autograd(bits, q_for_score, k_for_score, v, scales, cumavg, P, pc.k,
+                                                                  use_scaler=pc.partial_attention_scaler, is_causal=True)
+            else:
+                context = ops.sparse_attention_from_bits(bits, q_for_score, k_for_score, v, scales, cumavg, P, pc.k,
+                                                         use_scaler=pc.partial_attention_scaler, is_causal=True)
             pvals = crow = col = None
             Z = 0
         else:

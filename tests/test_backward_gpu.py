@@ -71,3 +71,33 @@ def test_sparse_attention_autograd_bf16(sea, N, H, T, P, k, d):
     for mine, ref in ((qd.grad, dq_r), (kd.grad, dk_r), (vd.grad, dv_r), (sd.grad, ds_r)):
         assert mine is not None
         torch.testing.assert_close(mine.float().cpu(), ref, rtol=2e-2, atol=2e-2)
+
+
+def test_module_forward_backward_through_sparse_path(sea):
+    """PerlinAttention.forward with inputs that require grad: context_layer backpropagates into q, k, v through the
+    sparse attention (mask and scales are treated as constants of the step)."""
+    import transformers
+    N, H, d, T, P, k, nbf = 1, 4, 64, 192, 32, 8, 8
+    torch.manual_seed(11)
+    cfg = transformers.BertConfig(hidden_size=H * d, num_attention_heads=H, max_position_embeddings=T)
+    mod = sea.PerlinAttention(cfg, sea.PerlinAttentionConfig(performer_nb_factor=nbf, k=k, attention_predictor_length=P, causal=True)).eval().to(DEV)
+    mk = lambda s: (torch.randn(N, H, T, d, device=DEV) * s).bfloat16().requires_grad_(True)
+    q, kk, v = mk(d ** -0.5), mk(1.0), mk(1.0)
+    am = so.causal_additive_mask(T, torch.bfloat16, N).to(DEV)
+    out = mod(q, kk, v, q, kk, v, q, kk, am, None, None)
+    dout = torch.randn_like(out.context_layer)
+    out.context_layer.backward(dout)
+    for t in (q, kk, v):
+        assert t.grad is not None and torch.isfinite(t.grad.float()).all() and float(t.grad.float().abs().sum()) > 0
+    # the same numbers as the operator called by hand on the step's own mask / scales
+    with torch.no_grad():
+        mod.output_attentions = False
+        w = mod._weights_fp32()
+        ctx, cumavg = sea.ops.performer_causal(q, kk, v, w['pos'], w['proj'])
+        cnn_in, scales, _ = sea.ops.predictor_mlp(ctx, v, w, mod.attention_predictor_dec_row_splits, P // mod.attention_predictor_dec_row_down_scale)
+    probs = out.estimated_attention_probs
+    kpr, _ = mod._shape_consts(H, P, T, T, q.device)
+    bits = sea.ops.topk_mask_bits(probs, kpr, 'causal_batch')
+    dq, dk, dv, _ = sea.ops.sparse_attention_from_bits_backward(bits, q.detach(), kk.detach(), v.detach(), scales, cumavg, dout, P, k, True, True)
+    torch.testing.assert_close(q.grad.float(), dq.bfloat16().float(), rtol=1e-2, atol=1e-3)
+    torch.testing.assert_close(v.grad.float(), dv.bfloat16().float(), rtol=1e-2, atol=1e-3)
