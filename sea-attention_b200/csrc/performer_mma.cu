@@ -58,9 +58,19 @@ struct PerfSmem {
 // ---- cooperative loads -------------------------------------------------------------------------------------------
 template <int kFp>
 __device__ __forceinline__ void load_proj(__nv_bfloat16* Ps, const float* __restrict__ proj, int F) {
-    for (int idx = threadIdx.x; idx < kFp * kDm; idx += kThreads) {
-        const int f = idx / kDm, c = idx % kDm;
-        Ps[f * kLdQ + c] = __float2bfloat16_rn(f < F ? proj[f * kDm + c] : 0.f);
+    // [F x 64] fp32 -> bf16 [kFp x kLdQ]; all of a thread's 16-byte loads are issued before the first conversion
+    constexpr int kVec = kFp * kDm / 4, kIt = (kVec + kThreads - 1) / kThreads;
+    float4 p[kIt];
+#pragma unroll
+    for (int it = 0; it < kIt; ++it) {
+        const int idx = threadIdx.x + it * kThreads, f = idx / (kDm / 4);
+        p[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (idx < kVec && f < F) p[it] = __ldg(reinterpret_cast<const float4*>(proj) + idx);
+    }
+#pragma unroll
+    for (int it = 0; it < kIt; ++it) {
+        const int idx = threadIdx.x + it * kThreads, f = idx / (kDm / 4), c4 = idx % (kDm / 4);
+        if (idx < kVec) *reinterpret_cast<uint2*>(Ps + f * kLdQ + c4 * 4) = make_uint2(pack_bf16(p[it].x, p[it].y), pack_bf16(p[it].z, p[it].w));
     }
 }
 // 16-byte asynchronous global->shared copy (LDGSTS); src_bytes = 0 zero-fills the destination
@@ -232,11 +242,21 @@ performer_out_mma_kernel(const __nv_bfloat16* __restrict__ q, int64_t q_sn, int6
     load_v2ext(Vs, v + (int64_t) n * v_sn + (int64_t) h * v_sh, v_st, pos_emb, r0, nvalid);
     {   // S_prev (exclusive prefix, fp32) -> bf16; the z column gets the +1e-6 of the reference's denominator
         const float* slot = ws + ((int64_t) nh * nchunks + chunk) * (kFp * kEx);
-        for (int idx = threadIdx.x; idx < kFp * (kEx / 2); idx += kThreads) {
-            const int f = idx / (kEx / 2), e = (idx % (kEx / 2)) * 2;
-            float2 s2 = *reinterpret_cast<const float2*>(slot + f * kEx + e);
-            if (e == kE && f < F) s2.x += 1e-6f;
-            *reinterpret_cast<uint32_t*>(Ss + f * kLdV + e) = pack_bf16(s2.x, s2.y);
+        constexpr int kVec = kFp * kEx / 4, kIt = (kVec + kThreads - 1) / kThreads;      // kEx % 4 == 0: a float4 never straddles rows
+        float4 sv[kIt];
+#pragma unroll
+        for (int it = 0; it < kIt; ++it) {
+            const int idx = threadIdx.x + it * kThreads;
+            sv[it] = idx < kVec ? __ldcg(reinterpret_cast<const float4*>(slot) + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int it = 0; it < kIt; ++it) {
+            const int idx = threadIdx.x + it * kThreads;
+            if (idx < kVec) {
+                const int f = idx / (kEx / 4), e = (idx % (kEx / 4)) * 4;
+                if (e == kE && f < F) sv[it].x += 1e-6f;
+                *reinterpret_cast<uint2*>(Ss + f * kLdV + e) = make_uint2(pack_bf16(sv[it].x, sv[it].y), pack_bf16(sv[it].z, sv[it].w));
+            }
         }
         for (int idx = threadIdx.x; idx < kFp; idx += kThreads) *reinterpret_cast<uint4*>(Ss + idx * kLdV + kEx) = make_uint4(0, 0, 0, 0);
     }
@@ -451,7 +471,7 @@ int sea_performer_causal_mma_fwd(const void* q, int64_t q_sn, int64_t q_sh, int6
     }
     SEA_CHECK_ARG(N > 0 && H > 0 && T > 0 && (int64_t) N * H <= 65535, "sea_performer_causal_mma_fwd: bad shape");
     SEA_CHECK_ARG(((q_sn | q_sh | q_st | k_sn | k_sh | k_st | v_sn | v_sh | v_st) % 8) == 0 &&
-                  ((((uintptr_t) q) | ((uintptr_t) k) | ((uintptr_t) v) | ((uintptr_t) pos_emb) | ((uintptr_t) ctx)) & 15) == 0,
+                  ((((uintptr_t) q) | ((uintptr_t) k) | ((uintptr_t) v) | ((uintptr_t) pos_emb) | ((uintptr_t) ctx) | ((uintptr_t) proj) | ((uintptr_t) workspace)) & 15) == 0,
                   "sea_performer_causal_mma_fwd: q/k/v rows must be 16-byte aligned");
     cudaStream_t s = (cudaStream_t) stream;
     const int Fp = ((F + 1) + 15) & ~15;

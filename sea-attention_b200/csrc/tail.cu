@@ -204,41 +204,77 @@ tail_topk_reg_kernel(const float* __restrict__ y3, const float* __restrict__ bia
         lb[i] = ln_b[j];
     }
     constexpr float invP = 1.0f / (float) P;
+    // The kHPW heads of this warp advance through LayerNorm / softmax stage by stage, so that the kHPW warp reductions of a
+    // stage are independent shuffle chains in flight together (a head-by-head loop exposes 4 x 5 dependent shuffles per head).
+    float val[kHPW][kPerLane];
+    float red[kHPW];
+#pragma unroll
+    for (int hh = 0; hh < kHPW; ++hh) {
+        const float* yh = ys + (wid + 8 * hh) * ldy;
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < kPerLane; ++i) {
+            val[hh][i] = (yh[tap[i][0]] + yh[tap[i][1]] + yh[tap[i][2]]) * rc[i];
+            s += val[hh][i];
+        }
+        red[hh] = s;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int hh = 0; hh < kHPW; ++hh) red[hh] += __shfl_xor_sync(kFull, red[hh], o);
+    float mean[kHPW];
+#pragma unroll
+    for (int hh = 0; hh < kHPW; ++hh) {
+        mean[hh] = red[hh] * invP;
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < kPerLane; ++i) { const float d = val[hh][i] - mean[hh]; q = fmaf(d, d, q); }
+        red[hh] = q;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int hh = 0; hh < kHPW; ++hh) red[hh] += __shfl_xor_sync(kFull, red[hh], o);
+#pragma unroll
+    for (int hh = 0; hh < kHPW; ++hh) {
+        const float rstd = rsqrtf(red[hh] * invP + 1e-5f);
+        float mx = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < kPerLane; ++i) { val[hh][i] = (val[hh][i] - mean[hh]) * rstd * lw[i] + lb[i]; mx = fmaxf(mx, val[hh][i]); }
+        red[hh] = mx;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int hh = 0; hh < kHPW; ++hh) red[hh] = fmaxf(red[hh], __shfl_xor_sync(kFull, red[hh], o));
+#pragma unroll
+    for (int hh = 0; hh < kHPW; ++hh) {
+        const float mx = red[hh];
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < kPerLane; ++i) { val[hh][i] = __expf(val[hh][i] - mx); sum += val[hh][i]; }
+        red[hh] = sum;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int hh = 0; hh < kHPW; ++hh) red[hh] += __shfl_xor_sync(kFull, red[hh], o);
     uint32_t key[kHPW][kPerLane];
 #pragma unroll
     for (int hh = 0; hh < kHPW; ++hh) {
         const int h = wid + 8 * hh;
-        const float* yh = ys + h * ldy;
-        float val[kPerLane];
-        float s = 0.f;
+        const float inv = 1.0f / red[hh];
 #pragma unroll
-        for (int i = 0; i < kPerLane; ++i) {
-            val[i] = (yh[tap[i][0]] + yh[tap[i][1]] + yh[tap[i][2]]) * rc[i];
-            s += val[i];
-        }
-        const float mean = warp_sum(s) * invP;
-        float q = 0.f;
-#pragma unroll
-        for (int i = 0; i < kPerLane; ++i) { const float d = val[i] - mean; q = fmaf(d, d, q); }
-        const float rstd = rsqrtf(warp_sum(q) * invP + 1e-5f);
-        float mx = -INFINITY;
-#pragma unroll
-        for (int i = 0; i < kPerLane; ++i) { val[i] = (val[i] - mean) * rstd * lw[i] + lb[i]; mx = fmaxf(mx, val[i]); }
-        mx = warp_max(mx);
-        float sum = 0.f;
-#pragma unroll
-        for (int i = 0; i < kPerLane; ++i) { val[i] = __expf(val[i] - mx); sum += val[i]; }
-        const float inv = 1.0f / warp_sum(sum);
-#pragma unroll
-        for (int i = 0; i < kPerLane; ++i) { val[i] *= inv; key[hh][i] = __float_as_uint(val[i]) | 0x80000000u; }   // == orderable(): val >= +0
+        for (int i = 0; i < kPerLane; ++i) { val[hh][i] *= inv; key[hh][i] = __float_as_uint(val[hh][i]) | 0x80000000u; }   // == orderable(): val >= +0
         if (probs) {
             float* prow = probs + (((int64_t) n * H + h) * Tn + t) * P + lane * kPerLane;
             if constexpr (kPerLane % 4 == 0) {
 #pragma unroll
-                for (int i = 0; i < kPerLane; i += 4) *reinterpret_cast<float4*>(prow + i) = make_float4(val[i], val[i + 1], val[i + 2], val[i + 3]);
+                for (int i = 0; i < kPerLane; i += 4) *reinterpret_cast<float4*>(prow + i) = make_float4(val[hh][i], val[hh][i + 1], val[hh][i + 2], val[hh][i + 3]);
             } else {
 #pragma unroll
-                for (int i = 0; i < kPerLane; ++i) prow[i] = val[i];
+                for (int i = 0; i < kPerLane; ++i) prow[i] = val[hh][i];
             }
         }
     }
