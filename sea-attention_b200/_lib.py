@@ -112,11 +112,12 @@ LAUNCH_COUNT = 0
 TRACE = None   # bench.py sets this to a list to get (entry, start_event, stop_event) per call
 
 
-def call(name, *args):
-    """Calls an int-returning entry; raises SeaError with the library's message on failure."""
+def call(name, *args, kernels=None):
+    """Calls an int-returning entry; raises SeaError with the library's message on failure.
+    `kernels` overrides the entry's default launch count (e.g. a call that reuses a cached weight packing)."""
     global LAUNCH_COUNT
     lib = load()
-    LAUNCH_COUNT += KERNELS_PER_CALL.get(name, 1)
+    LAUNCH_COUNT += KERNELS_PER_CALL.get(name, 1) if kernels is None else kernels
     if TRACE is not None:
         import torch
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

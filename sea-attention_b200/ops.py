@@ -310,7 +310,7 @@ def predictor_mlp(ctx, v, w, S: int, W: int, want_t_pred=False, force_simt=False
                   wp(w['enc_w']), w['enc_b'].data_ptr(), w['enc_ln_w'].data_ptr(), w['enc_ln_b'].data_ptr(),
                   wp(w['dec_w']), w['dec_b'].data_ptr(), w['cnn_ln_w'].data_ptr(), w['cnn_ln_b'].data_ptr(),
                   wp(w['scl_w']), w['scl_b'].data_ptr(), cnn_in.data_ptr(), scales.data_ptr(), ws.data_ptr(),
-                  N, H, T, D, S, W, _stream())
+                  N, H, T, D, S, W, _stream(), kernels=2 if fresh else 1)
         return cnn_in, scales, None
     t_pred = torch.empty((N, H, T, D2), dtype=ctx.dtype, device=ctx.device) if want_t_pred else None
     _lib.call('sea_predictor_mlp_fwd', ctx.data_ptr(), v.data_ptr(), v.stride(0), v.stride(1), v.stride(2), _dtype_code(ctx),
@@ -348,7 +348,7 @@ def causal_conv3x3_dil2_relu(x, weight, bias, force_simt=False, packed: 'PackedW
     if not force_simt and O == 64 and conv_umma_supported(x.dtype, W, C, O):
         ws, wptr = _packed_conv_ws(packed, slot, weight, src, C, O, x.device)
         _lib.call('sea_causal_conv3x3_dil2_relu_umma', x.data_ptr(), wptr, bias.data_ptr(), y.data_ptr(), ws.data_ptr(),
-                  N, T, W, C, O, _stream())
+                  N, T, W, C, O, _stream(), kernels=2 if wptr is not None else 1)
         return y
     _lib.call('sea_causal_conv3x3_dil2_relu', x.data_ptr(), weight.data_ptr(), bias.data_ptr(), y.data_ptr(), _dtype_code(x),
               N, T, W, C, O, _stream())
@@ -362,7 +362,8 @@ def conv1x1_umma(x, weight, bias, packed: 'PackedWeights' = None, slot: str = 'c
     O = weight.shape[0]
     y = torch.empty((N, T, W, O), dtype=torch.float32, device=x.device)
     ws, wptr = _packed_conv_ws(packed, slot, weight, src, C, O, x.device)
-    _lib.call('sea_conv1x1_umma', x.data_ptr(), wptr, bias.data_ptr(), y.data_ptr(), ws.data_ptr(), N, T, W, C, O, _stream())
+    _lib.call('sea_conv1x1_umma', x.data_ptr(), wptr, bias.data_ptr(), y.data_ptr(), ws.data_ptr(), N, T, W, C, O, _stream(),
+              kernels=2 if wptr is not None else 1)
     return y
 
 
