@@ -25,6 +25,9 @@
 #include "common.cuh"
 #include "csr_common.cuh"
 #include "umma.cuh"
+#include "block_attn.cuh"
+
+#include <stdlib.h>
 
 namespace sea {
 namespace {
@@ -106,7 +109,7 @@ struct RowScale {
 
 template <typename T16>
 __global__ void __launch_bounds__(kBThreads, 2)
-block_attention_bits_kernel(const unsigned long long* __restrict__ dmask, int W64,
+block_attention_bits_kernel(const uint32_t* __restrict__ tile_act, int act_words,
                             const T16* __restrict__ q, int64_t q_sn, int64_t q_sh, int64_t q_st,
                             const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_v,
                             const __grid_constant__ CUtensorMap tmap_m,
@@ -127,27 +130,14 @@ block_attention_bits_kernel(const unsigned long long* __restrict__ dmask, int W6
     const int nh = (int) (blockIdx.x % (unsigned) (N * H));
     const int n = nh / H, h = nh % H;
     const int r0 = rb * kBM;
-    const int src_off = is_causal ? (T_SRC - T_DST) : 0;
 
-    // ---- set-up: barriers, tile activity = OR over the 128 rows of their element-mask words -------------------------------
-    if (tid < kMaxTileWords) sact[tid] = 0u;
+    // ---- set-up: barriers, tile activity of this (head, row block) as left by expand_mask_kernel ---------------------------
+    if (tid < kMaxTileWords)
+        sact[tid] = tid < act_words ? __ldg(tile_act + (((int64_t) n * H + h) * n_row_blocks + rb) * act_words + tid) : 0u;
     if (tid == 0) {
         umma::prefetch_tensormap(&tmap_k); umma::prefetch_tensormap(&tmap_v); umma::prefetch_tensormap(&tmap_m);
         for (int s = 0; s < kStages; ++s) { umma::mbar_init(&full[s], 1); rel_cnt[s] = 0; }
         umma::fence_barrier_init();
-    }
-    __syncthreads();
-    const int blk_tiles = min(max_tiles, ((is_causal ? src_off + min(r0 + kBM, T_DST) : T_SRC) + kBN - 1) / kBN);   // tiles any row of the block can see
-    {
-        const int r = tid & (kBM - 1), part = tid >> 7;
-        if (r0 + r < T_DST) {
-            const ulonglong2* row2 = reinterpret_cast<const ulonglong2*>(dmask + (((int64_t) n * H + h) * T_DST + r0 + r) * W64);
-            for (int w2 = part; 2 * w2 < blk_tiles; w2 += kBThreads / kBM) {
-                const ulonglong2 mm = __ldg(row2 + w2);
-                if (mm.x != 0ull && !((sact[(2 * w2) >> 5] >> ((2 * w2) & 31)) & 1u)) atomicOr(&sact[(2 * w2) >> 5], 1u << ((2 * w2) & 31));
-                if (2 * w2 + 1 < blk_tiles && mm.y != 0ull && !((sact[(2 * w2 + 1) >> 5] >> ((2 * w2 + 1) & 31)) & 1u)) atomicOr(&sact[(2 * w2 + 1) >> 5], 1u << ((2 * w2 + 1) & 31));
-            }
-        }
     }
     __syncthreads();
     if (warp == 0) {
@@ -357,7 +347,7 @@ block_attention_bits_kernel(const unsigned long long* __restrict__ dmask, int W6
 // shared memory, which is then written out with coalesced stores.  Only the words a 128-row query block can see are
 // written (causal).
 __global__ void __launch_bounds__(256)
-expand_mask_kernel(const uint32_t* __restrict__ mask_bits, unsigned long long* __restrict__ dmask, int W64,
+expand_mask_kernel(const uint32_t* __restrict__ mask_bits, unsigned long long* __restrict__ dmask, uint32_t* __restrict__ tile_act, int act_words, int W64,
                    int N, int H, int T_DST, int T_SRC, int P, int p_lg, int is_causal) {
     extern __shared__ uint32_t ex_sm[];                   // [H][2 * wneed]
     const int nw = P >> 5;
@@ -385,10 +375,17 @@ expand_mask_kernel(const uint32_t* __restrict__ mask_bits, unsigned long long* _
         }
     }
     __syncthreads();
+    // tile activity of the (head, 128-row query block): which 64-token tiles hold an alive element of any of its rows
+    uint32_t* act_blk = tile_act + (int64_t) n * H * ((T_DST + kBM - 1) / kBM) * act_words + (int64_t) (t / kBM) * act_words;
+    const int64_t act_hs = (int64_t) ((T_DST + kBM - 1) / kBM) * act_words;
     for (int i = threadIdx.x; i < H * wneed; i += blockDim.x) {
         const int h = i / wneed, w = i - h * wneed;
         const uint2 v = *reinterpret_cast<const uint2*>(ex_sm + 2 * i);
         dmask[(((int64_t) n * H + h) * T_DST + t) * W64 + w] = (unsigned long long) v.x | ((unsigned long long) v.y << 32);
+        if ((v.x | v.y) != 0u) {
+            uint32_t* aw = act_blk + h * act_hs + (w >> 5);
+            if (!((*aw >> (w & 31)) & 1u)) atomicOr(aw, 1u << (w & 31));
+        }
     }
 }
 
@@ -407,10 +404,15 @@ using namespace sea;
 
 extern "C" {
 
+static inline int64_t act_bytes(int N, int H, int T_DST, int T_SRC) {
+    const int64_t words = (int64_t) N * H * ((T_DST + kBM - 1) / kBM) * (((T_SRC + kBN - 1) / kBN + 31) / 32);
+    return (words * 4 + 15) & ~(int64_t) 15;
+}
+
 int64_t sea_block_attention_workspace_bytes(int N, int H, int T_DST, int T_SRC, int D, int P, int k_clamp, int dtype) {
     if (dtype != SEA_DTYPE_BF16 && dtype != SEA_DTYPE_F16) return 0;
     if (N <= 0 || H <= 0 || T_DST <= 0 || T_SRC < T_DST || !block_attention_eligible(D, T_SRC, P, k_clamp)) return 0;
-    return (int64_t) N * H * T_DST * mask_row_words(T_SRC) * 8;
+    return (int64_t) N * H * T_DST * mask_row_words(T_SRC) * 8 + act_bytes(N, H, T_DST, T_SRC);      // dense bit mask + tile activity
 }
 
 int sea_block_attention_fwd(const uint32_t* mask_bits,
@@ -434,6 +436,9 @@ int sea_block_attention_fwd(const uint32_t* mask_bits,
     cudaStream_t s = (cudaStream_t) stream;
     const int W64 = mask_row_words(T_SRC);
     unsigned long long* dmask = reinterpret_cast<unsigned long long*>(workspace);
+    uint32_t* tile_act = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(workspace) + (int64_t) N * H * T_DST * W64 * 8);
+    const int act_words = ((T_SRC + kBN - 1) / kBN + 31) / 32;
+    SEA_CUDA_TRY(cudaMemsetAsync(tile_act, 0, (size_t) act_bytes(N, H, T_DST, T_SRC), s), "memset tile activity");
     // integer pixel edges are exact iff P is a power of two and m * L stays below 2^24
     int p_lg = -1;
     if ((P & (P - 1)) == 0 && (int64_t) P * T_SRC <= (1 << 24)) { p_lg = 0; while ((1 << p_lg) < P) ++p_lg; }
@@ -441,9 +446,14 @@ int sea_block_attention_fwd(const uint32_t* mask_bits,
         const size_t smem = (size_t) H * W64 * 8;
         SEA_CHECK_ARG(smem <= 200 * 1024, "sea_block_attention_fwd: H * T_SRC too large for the mask expansion");
         SEA_CUDA_TRY(cudaFuncSetAttribute(expand_mask_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem), "smem attr");
-        expand_mask_kernel<<<(unsigned) ((int64_t) N * T_DST), 256, smem, s>>>(mask_bits, dmask, W64, N, H, T_DST, T_SRC, P, p_lg, is_causal);
+        expand_mask_kernel<<<(unsigned) ((int64_t) N * T_DST), 256, smem, s>>>(mask_bits, dmask, tile_act, act_words, W64, N, H, T_DST, T_SRC, P, p_lg, is_causal);
         SEA_CHECK_LAUNCH("expand_mask_kernel");
     }
+    // bf16: the two contractions on tcgen05 / TMEM (block_attn_umma.cu); fp16 (and SEA_ATTN_MMA_SYNC=1, for A/B timing): mma.sync
+    static const bool force_mma_sync = getenv("SEA_ATTN_MMA_SYNC") != nullptr;
+    if (dtype == SEA_DTYPE_BF16 && !force_mma_sync && T_SRC <= 4096)      // measured: tcgen05 0.18 ms vs 0.18 ms at T = 4096, mma.sync ahead at 8192
+        return launch_block_attention_umma(dmask, W64, tile_act, act_words, q, q_sn, q_sh, q_st, k, k_sn, k_sh, k_st, v, v_sn, v_sh, v_st, scales, cumavg,
+                                           avg_sh, avg_st, use_scaler, out, N, H, T_DST, T_SRC, is_causal, s);
     const int n_row_blocks = (T_DST + kBM - 1) / kBM;
     const int max_tiles = (T_SRC + kBN - 1) / kBN;
     CUtensorMap t_k, t_v;
@@ -471,7 +481,7 @@ int sea_block_attention_fwd(const uint32_t* mask_bits,
     do {                                                                                                                         \
         auto kern = block_attention_bits_kernel<TT>;                                                                             \
         SEA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem), "smem attr");          \
-        kern<<<grid, kBThreads, smem, s>>>(dmask, W64, (const TT*) q, q_sn, q_sh, q_st, t_k, t_v, t_m, scales, (const TT*) cumavg,    \
+        kern<<<grid, kBThreads, smem, s>>>(tile_act, act_words, (const TT*) q, q_sn, q_sh, q_st, t_k, t_v, t_m, scales, (const TT*) cumavg,    \
             avg_sh, avg_st, use_scaler, (TT*) out, N, H, T_DST, T_SRC, is_causal, n_row_blocks, max_tiles);                      \
     } while (0)
     if (dtype == SEA_DTYPE_BF16) SEA_BLOCK_ATTN(__nv_bfloat16); else SEA_BLOCK_ATTN(__half);
