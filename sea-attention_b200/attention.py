@@ -207,6 +207,7 @@ class PerlinAttention(nn.Module):
         self.v_eye_learned_causal = nn.Parameter(torch.randn((1, 1, max_pos, d)))
         self._shape_cache = {}
         self._packed = ops.PackedWeights()
+        self.fuse_mask_expansion = False
 
     # ------------------------------------------------------------------------------------------------
     def _weights_fp32(self):
@@ -298,10 +299,18 @@ class PerlinAttention(nn.Module):
         kpr = k_per_row.repeat(N) if N > 1 else k_per_row
         y = ops.causal_conv3x3_dil2_relu(cnn_in, w['conv1_w'], w['conv1_b'], packed=pk, slot='conv1', src=net[0].module.weight)
         y = ops.causal_conv3x3_dil2_relu(y, w['conv2_w'], w['conv2_b'], packed=pk, slot='conv2', src=net[2].module.weight)
+        expanded_ws = None
         if q.dtype == torch.bfloat16 and ops.conv_umma_supported(q.dtype, W, S * H, H) and P % 32 == 0:
             # tensor-core path: 1x1 conv before the upsample (tcgen05), then tail + softmax + top-k in one kernel
             y3 = ops.conv1x1_umma(y, w['conv3_w'], w['conv3_b'], packed=pk, slot='conv3', src=net[5].module.weight)
-            res = ops.predictor_tail_topk(y3, w['conv3_b'], w['out_ln_w'], w['out_ln_b'], kpr, P, count_k=pc.k if self.output_attentions else 0)
+            needs_grad = torch.is_grad_enabled() and any(t_.requires_grad for t_ in (q_for_score, k_for_score, v))
+            if (self.fuse_mask_expansion and not self.output_attentions and not needs_grad and ops.attention_bits_supported(q.dtype, d, P)
+                    and ops.tail_expand_supported(H, P)):
+                # optional: the dense bit-packed mask the block attention consumes is written by the top-k kernel itself (measured
+                # slower than the separate expansion kernel at the north-star shape: 0.616 vs 0.581 ms/step, so off by default)
+                expanded_ws = ops.block_attention_workspace(N, H, T, T, d, P, pc.k, q.dtype, q.device)
+            res = ops.predictor_tail_topk(y3, w['conv3_b'], w['out_ln_w'], w['out_ln_b'], kpr, P, count_k=pc.k if self.output_attentions else 0,
+                                          expand=None if expanded_ws is None else (expanded_ws, d, pc.k, q.dtype))
             probs, bits, crow_counts = res if len(res) == 3 else (res[0], res[1], None)
         else:
             probs, _ = ops.predictor_tail(y, w['conv3_w'], w['conv3_b'], w['out_ln_w'], w['out_ln_b'], P)
@@ -318,7 +327,7 @@ class PerlinAttention(nn.Module):
                                                                   use_scaler=pc.partial_attention_scaler, is_causal=True)
             else:
                 context = ops.sparse_attention_from_bits(bits, q_for_score, k_for_score, v, scales, cumavg, P, pc.k,
-                                                         use_scaler=pc.partial_attention_scaler, is_causal=True)
+                                                         use_scaler=pc.partial_attention_scaler, is_causal=True, expanded=expanded_ws)
             pvals = crow = col = None
             Z = 0
         else:

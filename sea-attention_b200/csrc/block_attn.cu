@@ -97,16 +97,6 @@ __device__ __forceinline__ void mma16816<__half>(float (&c)[4], const uint32_t (
                  : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-// First source token of pixel m for a row of source length L (a8: roundf(fp32(m) * (fp32(L) / fp32(P))), un-fused).
-// When P = 2^lg and m * L < 2^24 every intermediate is exact, so roundf(m * L / P) == (m * L + P/2) >> lg: integer path.
-struct RowScale {
-    int L, lg, halfP;
-    float s;
-    __device__ __forceinline__ int edge(int m) const {
-        return lg >= 0 ? (m * L + halfP) >> lg : (int) roundf(__fmul_rn((float) m, s));
-    }
-};
-
 template <typename T16>
 __global__ void __launch_bounds__(kBThreads, 2)
 block_attention_bits_kernel(const uint32_t* __restrict__ tile_act, int act_words,
@@ -396,7 +386,7 @@ bool block_attention_eligible(int D, int T_SRC, int P, int k_clamp) {
     return D == kBD && (P % 32) == 0 && P <= 1024 && (T_SRC + P - 1) / P + 1 <= k_clamp && T_SRC <= 8192;
 }
 
-static inline int mask_row_words(int T_SRC) { return (((T_SRC + kBN - 1) / kBN) + 1) & ~1; }      // u64 words, 16-byte rows
+static_assert(kBM == kMaskRowBlock && kBN == kMaskTile, "mask layout constants");
 
 }  // namespace sea
 
@@ -404,15 +394,10 @@ using namespace sea;
 
 extern "C" {
 
-static inline int64_t act_bytes(int N, int H, int T_DST, int T_SRC) {
-    const int64_t words = (int64_t) N * H * ((T_DST + kBM - 1) / kBM) * (((T_SRC + kBN - 1) / kBN + 31) / 32);
-    return (words * 4 + 15) & ~(int64_t) 15;
-}
-
 int64_t sea_block_attention_workspace_bytes(int N, int H, int T_DST, int T_SRC, int D, int P, int k_clamp, int dtype) {
     if (dtype != SEA_DTYPE_BF16 && dtype != SEA_DTYPE_F16) return 0;
     if (N <= 0 || H <= 0 || T_DST <= 0 || T_SRC < T_DST || !block_attention_eligible(D, T_SRC, P, k_clamp)) return 0;
-    return (int64_t) N * H * T_DST * mask_row_words(T_SRC) * 8 + act_bytes(N, H, T_DST, T_SRC);      // dense bit mask + tile activity
+    return (int64_t) N * H * T_DST * mask_row_words(T_SRC) * 8 + mask_act_bytes(N, H, T_DST, T_SRC);      // dense bit mask + tile activity
 }
 
 int sea_block_attention_fwd(const uint32_t* mask_bits,
@@ -422,7 +407,7 @@ int sea_block_attention_fwd(const uint32_t* mask_bits,
                             const float* scales, const void* cumavg, int64_t avg_sh, int64_t avg_st, int use_scaler, int dtype, void* out,
                             int N, int H, int T_DST, int T_SRC, int D, int P, int k_clamp, int is_causal,
                             void* workspace, int64_t workspace_bytes, void* stream) {
-    SEA_CHECK_ARG(mask_bits && q && k && v && scales && out && workspace, "sea_block_attention_fwd: null pointer");
+    SEA_CHECK_ARG(q && k && v && scales && out && workspace, "sea_block_attention_fwd: null pointer");
     const int64_t need = sea_block_attention_workspace_bytes(N, H, T_DST, T_SRC, D, P, k_clamp, dtype);
     if (need == 0) {
         set_error("sea_block_attention_fwd: unsupported shape (needs 16-bit activations, D = 64, P %% 32 == 0, no clamped pixel: "
@@ -437,12 +422,10 @@ int sea_block_attention_fwd(const uint32_t* mask_bits,
     const int W64 = mask_row_words(T_SRC);
     unsigned long long* dmask = reinterpret_cast<unsigned long long*>(workspace);
     uint32_t* tile_act = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(workspace) + (int64_t) N * H * T_DST * W64 * 8);
-    const int act_words = ((T_SRC + kBN - 1) / kBN + 31) / 32;
-    SEA_CUDA_TRY(cudaMemsetAsync(tile_act, 0, (size_t) act_bytes(N, H, T_DST, T_SRC), s), "memset tile activity");
-    // integer pixel edges are exact iff P is a power of two and m * L stays below 2^24
-    int p_lg = -1;
-    if ((P & (P - 1)) == 0 && (int64_t) P * T_SRC <= (1 << 24)) { p_lg = 0; while ((1 << p_lg) < P) ++p_lg; }
-    {
+    const int act_words = mask_act_words(T_SRC);
+    const int p_lg = exact_edge_shift(P, T_SRC);      // integer pixel edges are exact iff P is a power of two and m * L stays below 2^24
+    if (mask_bits != nullptr) {      // nullptr: `workspace` was filled by sea_predictor_tail_topk_expand_fwd (mask expansion fused into the top-k)
+        SEA_CUDA_TRY(cudaMemsetAsync(tile_act, 0, (size_t) mask_act_bytes(N, H, T_DST, T_SRC), s), "memset tile activity");
         const size_t smem = (size_t) H * W64 * 8;
         SEA_CHECK_ARG(smem <= 200 * 1024, "sea_block_attention_fwd: H * T_SRC too large for the mask expansion");
         SEA_CUDA_TRY(cudaFuncSetAttribute(expand_mask_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem), "smem attr");

@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(kTopkThreads, 3)
 tail_topk_reg_kernel(const float* __restrict__ y3, const float* __restrict__ bias, const float* __restrict__ ln_w,
                      const float* __restrict__ ln_b, const float* __restrict__ k_per_row, float* __restrict__ probs,
                      uint32_t* __restrict__ mask_bits, int32_t* __restrict__ crow_counts, int k_clamp,
-                     int N, int Tn, int W) {
+                     int N, int Tn, int W, MaskExpandArgs ex) {
     constexpr int P = 32 * kPerLane, H = 8 * kHPW, G = H * P;
     constexpr int kLanesPerWord = 32 / kPerLane > 0 ? 32 / kPerLane : 1;     // lanes that share one 32-pixel word (kPerLane <= 32)
     extern __shared__ __align__(16) uint32_t smem_u[];
@@ -156,8 +156,14 @@ tail_topk_reg_kernel(const float* __restrict__ y3, const float* __restrict__ bia
     __shared__ int4 stap[P];
     float* ys = reinterpret_cast<float*>(smem_u);               // [H][W+2]: W conv outputs, then the bias (pad columns), then 0
     uint32_t* sbits = smem_u + H * (W + 3);                     // [G/32] (only for the fused row counts)
+    uint32_t* img = sbits + (G >> 5);                           // [H][2 * wneed] dense element mask of this row (fused a8 expansion)
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int n = blockIdx.x / Tn, t = blockIdx.x % Tn;
+    // fused a8 expansion (short-context attention path, block_attn.cu): words a kMaskRowBlock-row query block can see
+    const int ex_src_off = ex.is_causal ? (ex.T_SRC - Tn) : 0;
+    const int ex_blk_end = ex.is_causal ? ex_src_off + min((t / kMaskRowBlock + 1) * kMaskRowBlock, Tn) : ex.T_SRC;
+    const int wneed = ex.dmask != nullptr ? min(ex.W64, (ex_blk_end + 63) >> 6) : 0;
+    for (int i = tid; i < H * 2 * wneed; i += kTopkThreads) img[i] = 0u;
     const int ldy = (W + 2) | 1;
     const float* yr = y3 + ((int64_t) n * Tn + t) * W * H;
     for (int base = 0; base < W * H; base += 8 * kTopkThreads) {
@@ -436,6 +442,38 @@ tail_topk_reg_kernel(const float* __restrict__ y3, const float* __restrict__ bia
             if (crow_counts != nullptr) sbits[w] = word;
         }
     }
+    if (ex.dmask != nullptr) {
+        // every alive pixel ORs its token run into the row image; then coalesced stores + the query block's tile activity
+        RowScale rs;
+        rs.L = ex.is_causal ? (ex_src_off + t + 1) : ex.T_SRC; rs.lg = ex.p_lg; rs.halfP = P >> 1;
+        rs.s = __fdiv_rn((float) rs.L, (float) P);
+#pragma unroll
+        for (int hh = 0; hh < kHPW; ++hh) {
+            uint32_t* himg = img + (wid + 8 * hh) * 2 * wneed;
+            for (uint32_t x = alive[hh]; x; x &= x - 1) {
+                const int m = lane * kPerLane + __ffs(x) - 1;
+                const int a = rs.edge(m), b = rs.edge(m + 1);
+                if (b > a)
+                    for (int wd = a >> 5; wd <= ((b - 1) >> 5); ++wd) {
+                        const int lo = max(a - (wd << 5), 0), hi = min(b - (wd << 5), 32);
+                        atomicOr(himg + wd, (hi - lo >= 32 ? 0xffffffffu : ((1u << (hi - lo)) - 1u)) << lo);
+                    }
+            }
+        }
+        __syncthreads();
+        const int nrb = (Tn + kMaskRowBlock - 1) / kMaskRowBlock;
+        uint32_t* act_blk = ex.tile_act + (int64_t) n * H * nrb * ex.act_words + (int64_t) (t / kMaskRowBlock) * ex.act_words;
+        const int64_t act_hs = (int64_t) nrb * ex.act_words;
+        for (int i = tid; i < H * wneed; i += kTopkThreads) {
+            const int h = i / wneed, w = i - h * wneed;
+            const uint2 v = *reinterpret_cast<const uint2*>(img + 2 * i);
+            ex.dmask[(((int64_t) n * H + h) * Tn + t) * ex.W64 + w] = (unsigned long long) v.x | ((unsigned long long) v.y << 32);
+            if ((v.x | v.y) != 0u) {
+                uint32_t* aw = act_blk + h * act_hs + (w >> 5);
+                if (!((*aw >> (w & 31)) & 1u)) atomicOr(aw, 1u << (w & 31));
+            }
+        }
+    }
     if (crow_counts != nullptr) {
         // a8 pass 1 fused: crow[n, t+1] = entries of this row (sea_crow_scan turns the counts into offsets)
         __syncthreads();
@@ -459,11 +497,9 @@ tail_topk_reg_kernel(const float* __restrict__ y3, const float* __restrict__ bia
 
 using namespace sea;
 
-extern "C" {
-
-int sea_predictor_tail_topk_fwd(const float* y3, const float* bias, const float* ln_w, const float* ln_b,
-                                const float* k_per_row, float* probs, uint32_t* mask_bits, int32_t* crow_counts, int k_clamp,
-                                int N, int H, int T, int W, int P, void* stream) {
+static int tail_topk_impl(const float* y3, const float* bias, const float* ln_w, const float* ln_b,
+                          const float* k_per_row, float* probs, uint32_t* mask_bits, int32_t* crow_counts, int k_clamp,
+                          int N, int H, int T, int W, int P, void* stream, const MaskExpandArgs& ex) {
     SEA_CHECK_ARG(y3 && bias && ln_w && ln_b && (probs || mask_bits), "sea_predictor_tail_topk_fwd: null pointer");
     SEA_CHECK_ARG(mask_bits == nullptr || k_per_row != nullptr, "sea_predictor_tail_topk_fwd: k_per_row is required for the top-k");
     SEA_CHECK_ARG(N > 0 && H > 0 && T > 0 && W > 0 && P > 0, "sea_predictor_tail_topk_fwd: bad shape");
@@ -477,18 +513,19 @@ int sea_predictor_tail_topk_fwd(const float* y3, const float* bias, const float*
     const unsigned grid = (unsigned) ((int64_t) N * T);
     static const bool no_reg = getenv("SEA_TAIL_SMEM") != nullptr;        // development switch for A/B timing
     if (!no_reg && H % 8 == 0 && (H / 8) * (P / 32) <= 32 && P <= 1024 && H <= 64) {
-        const size_t smem_r = (size_t) H * (W + 3) * 4 + (size_t) (G >> 5) * 4 + 16;
+        const size_t smem_r = (size_t) H * (W + 3) * 4 + (size_t) (G >> 5) * 4 + 16 + (ex.dmask ? (size_t) H * ex.W64 * 8 : 0);
+        SEA_CHECK_ARG(smem_r <= 72 * 1024, "sea_predictor_tail_topk: row image too large for the fused mask expansion");
         bool launched = true;
 #define SEA_TAILR(PL, HP)                                                                                                  \
         {                                                                                                                  \
             if (P / W == 4) {                                                                                              \
                 auto kern = tail_topk_reg_kernel<PL, HP, 4>;                                                               \
                 SEA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_r), "smem attr"); \
-                kern<<<grid, kTopkThreads, smem_r, s>>>(y3, bias, ln_w, ln_b, k_per_row, probs, mask_bits, crow_counts, k_clamp, N, T, W); \
+                kern<<<grid, kTopkThreads, smem_r, s>>>(y3, bias, ln_w, ln_b, k_per_row, probs, mask_bits, crow_counts, k_clamp, N, T, W, ex); \
             } else {                                                                                                       \
                 auto kern = tail_topk_reg_kernel<PL, HP, 0>;                                                               \
                 SEA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_r), "smem attr"); \
-                kern<<<grid, kTopkThreads, smem_r, s>>>(y3, bias, ln_w, ln_b, k_per_row, probs, mask_bits, crow_counts, k_clamp, N, T, W); \
+                kern<<<grid, kTopkThreads, smem_r, s>>>(y3, bias, ln_w, ln_b, k_per_row, probs, mask_bits, crow_counts, k_clamp, N, T, W, ex); \
             }                                                                                                              \
         }
         const int pl = P / 32, hp = H / 8;
@@ -500,12 +537,19 @@ int sea_predictor_tail_topk_fwd(const float* y3, const float* bias, const float*
         else if (pl == 2 && hp == 1) SEA_TAILR(2, 1)
         else if (pl == 16 && hp == 2) SEA_TAILR(16, 2)
         else if (pl == 16 && hp == 1) SEA_TAILR(16, 1)
+        else if (pl == 2 && hp == 4) SEA_TAILR(2, 4)
+        else if (pl == 2 && hp == 2) SEA_TAILR(2, 2)
+        else if (pl == 4 && hp == 1) SEA_TAILR(4, 1)
         else launched = false;
 #undef SEA_TAILR
         if (launched) {
             SEA_CHECK_LAUNCH("tail_topk_reg_kernel");
             return SEA_OK;
         }
+    }
+    if (ex.dmask != nullptr) {
+        set_error("sea_predictor_tail_topk_expand_fwd: needs the register-resident top-k (H %% 8 == 0, (H/8) * (P/32) <= 32)");
+        return SEA_ERR_UNSUPPORTED;
     }
     const size_t smem = ((size_t) G + (G >> 5)) * 4 + (size_t) H * (W + 2) * 4 + 16;
     SEA_CHECK_ARG(smem <= 220 * 1024, "sea_predictor_tail_topk_fwd: H*P=%d keys do not fit shared memory", G);
@@ -530,6 +574,46 @@ int sea_predictor_tail_topk_fwd(const float* y3, const float* bias, const float*
 #undef SEA_TAIL_LAUNCH
     SEA_CHECK_LAUNCH("tail_topk_kernel");
     return SEA_OK;
+}
+
+extern "C" {
+
+int sea_predictor_tail_topk_fwd(const float* y3, const float* bias, const float* ln_w, const float* ln_b,
+                                const float* k_per_row, float* probs, uint32_t* mask_bits, int32_t* crow_counts, int k_clamp,
+                                int N, int H, int T, int W, int P, void* stream) {
+    MaskExpandArgs ex = {nullptr, nullptr, 0, 0, 0, -1, 0};
+    return tail_topk_impl(y3, bias, ln_w, ln_b, k_per_row, probs, mask_bits, crow_counts, k_clamp, N, H, T, W, P, stream, ex);
+}
+
+int64_t sea_block_attention_workspace_bytes(int N, int H, int T_DST, int T_SRC, int D, int P, int k_clamp, int dtype);
+
+int sea_predictor_tail_expand_supported(int H, int P) {
+    if (H % 8 != 0 || P % 32 != 0) return 0;
+    const int pl = P / 32, hp = H / 8;
+    return (pl == 8 && (hp == 4 || hp == 2 || hp == 1)) || (pl == 4 && (hp == 4 || hp == 2 || hp == 1)) || (pl == 2 && (hp == 4 || hp == 2 || hp == 1)) ||
+           (pl == 16 && (hp == 2 || hp == 1));
+}
+
+int sea_predictor_tail_topk_expand_fwd(const float* y3, const float* bias, const float* ln_w, const float* ln_b,
+                                       const float* k_per_row, float* probs, uint32_t* mask_bits, int k_clamp,
+                                       int N, int H, int T, int W, int P, int D, int dtype, void* workspace, int64_t workspace_bytes, void* stream) {
+    SEA_CHECK_ARG(mask_bits && workspace, "sea_predictor_tail_topk_expand_fwd: null pointer");
+    const int64_t need = sea_block_attention_workspace_bytes(N, H, T, T, D, P, k_clamp, dtype);
+    if (need == 0) {
+        set_error("sea_predictor_tail_topk_expand_fwd: the block attention does not support this shape");
+        return SEA_ERR_UNSUPPORTED;
+    }
+    SEA_CHECK_ARG(workspace_bytes >= need && (((uintptr_t) workspace) & 15) == 0, "sea_predictor_tail_topk_expand_fwd: workspace too small or misaligned");
+    MaskExpandArgs ex;
+    ex.W64 = mask_row_words(T);
+    ex.dmask = reinterpret_cast<unsigned long long*>(workspace);
+    ex.tile_act = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(workspace) + (int64_t) N * H * T * ex.W64 * 8);
+    ex.act_words = mask_act_words(T);
+    ex.T_SRC = T;
+    ex.p_lg = exact_edge_shift(P, T);
+    ex.is_causal = 1;
+    SEA_CUDA_TRY(cudaMemsetAsync(ex.tile_act, 0, (size_t) mask_act_bytes(N, H, T, T), (cudaStream_t) stream), "memset tile activity");
+    return tail_topk_impl(y3, bias, ln_w, ln_b, k_per_row, probs, mask_bits, nullptr, k_clamp, N, H, T, W, P, stream, ex);
 }
 
 }  // extern "C"
