@@ -287,7 +287,7 @@ SEA_API int sea_block_attention_fwd(const uint32_t* mask_bits,
  *   dout [N,T_DST,H*D] (`dtype`) = grad of the forward output;  dq [N,H,T_DST,D], dk, dv [N,H,T_SRC,D] fp32 contiguous
  *   (dk / dv are zeroed here and accumulated with atomics);  dscales fp32 [N,H,T_DST,2] (nullable) = grad of the two scaler
  *   logits (attention.py:1166-1171, 1242-1244).  cumavg non-NULL adds the running-mean branch (causal prefill only).
- * The top-k mask is piecewise constant: no gradient flows through it.  D % 8 == 0, D <= 128, P % 32 == 0, P <= 1024. */
+ * The top-k mask is piecewise constant: no gradient flows through it.  D in {32, 64, 128}, P % 32 == 0, P <= 1024. */
 SEA_API int sea_sparse_attention_bits_bwd(const uint32_t* mask_bits,
                                           const void* q, int64_t q_sn, int64_t q_sh, int64_t q_st,
                                           const void* k, int64_t k_sn, int64_t k_sh, int64_t k_st,

@@ -116,7 +116,7 @@ sparse_attention_bits_bwd_kernel(const uint32_t* __restrict__ mask_bits,
                                  const float* __restrict__ scales, const T* __restrict__ cumavg, int64_t avg_sh, int64_t avg_st, int use_scaler,
                                  const T* __restrict__ dout, float* __restrict__ dq, float* __restrict__ dk, float* __restrict__ dv,
                                  float* __restrict__ dscales, int N, int H, int T_DST, int T_SRC, int D, int P, int k_clamp, int is_causal) {
-    extern __shared__ float bw_sm[];                       // per warp: q[D] | dout[D]
+    extern __shared__ __align__(16) float bw_sm[];                       // per warp: q[D] | dout[D]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float* qs = bw_sm + warp * 2 * D;
     float* gs = qs + D;
@@ -174,8 +174,13 @@ sparse_attention_bits_bwd_kernel(const uint32_t* __restrict__ mask_bits,
     }
 
     // ---- sweep B: dS_z = a psc P_z (g_z - E);  dq += dS k;  dk_z += dS q;  dv_z += a psc P_z dout --------------------
+    // vector updates: D/4 lanes cover one row with 4 channels each, so 32/(D/4) entries are processed per step and every
+    // dk / dv update is ONE 16-byte vector reduction (red.global.add.v4.f32) instead of four scalar atomics
     const float w_ctx = a * psc;
-    float dq_acc[4] = {0.f, 0.f, 0.f, 0.f};                 // channels lane, lane + 32, ... (D <= 128)
+    const int lpr = D >> 2, epi = 32 / lpr;                  // lanes per row, entries per step
+    const int sub = lane % lpr, grp = lane / lpr;
+    float4 dq_acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 q4 = *reinterpret_cast<const float4*>(qs + 4 * sub), g4 = *reinterpret_cast<const float4*>(gs + 4 * sub);
     float* dkb = dk + (((int64_t) n * H + h) * T_SRC) * D;
     float* dvb = dv + (((int64_t) n * H + h) * T_SRC) * D;
     for_each_entry_chunk(word, lane, s_scale, k_clamp, [&](int jmine, int cnt) {
@@ -187,28 +192,26 @@ sparse_attention_bits_bwd_kernel(const uint32_t* __restrict__ mask_bits,
             pv = w_ctx * p;
             ds = pv * (g - E);
         }
-        for (int e = 0; e < cnt; ++e) {
-            const int j = __shfl_sync(kFull, jmine, e);
-            const float ds_e = __shfl_sync(kFull, ds, e);
-            const float pv_e = __shfl_sync(kFull, pv, e);
-            const T* krow = kb + (int64_t) j * k_st;
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int c = lane + 32 * u;
-                if (c < D) {
-                    dq_acc[u] = fmaf(ds_e, ldf(krow + c), dq_acc[u]);
-                    atomicAdd(dkb + (int64_t) j * D + c, ds_e * qs[c]);
-                    atomicAdd(dvb + (int64_t) j * D + c, pv_e * gs[c]);
-                }
+        for (int e0 = 0; e0 < cnt; e0 += epi) {
+            const int e = e0 + grp;
+            const int j = __shfl_sync(kFull, jmine, e & 31);
+            const float ds_e = __shfl_sync(kFull, ds, e & 31);
+            const float pv_e = __shfl_sync(kFull, pv, e & 31);
+            if (e < cnt) {
+                const T* krow = kb + (int64_t) j * k_st + 4 * sub;
+                dq_acc.x = fmaf(ds_e, ldf(krow), dq_acc.x); dq_acc.y = fmaf(ds_e, ldf(krow + 1), dq_acc.y);
+                dq_acc.z = fmaf(ds_e, ldf(krow + 2), dq_acc.z); dq_acc.w = fmaf(ds_e, ldf(krow + 3), dq_acc.w);
+                atomicAdd(reinterpret_cast<float4*>(dkb + (int64_t) j * D) + sub, make_float4(ds_e * q4.x, ds_e * q4.y, ds_e * q4.z, ds_e * q4.w));
+                atomicAdd(reinterpret_cast<float4*>(dvb + (int64_t) j * D) + sub, make_float4(pv_e * g4.x, pv_e * g4.y, pv_e * g4.z, pv_e * g4.w));
             }
         }
     });
-    float* dqrow = dq + (((int64_t) n * H + h) * T_DST + t) * D;
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-        const int c = lane + 32 * u;
-        if (c < D) dqrow[c] = dq_acc[u];
+    // combine the entry groups (lanes sub, sub + lpr, ...) and store dq
+    for (int o = lpr; o < 32; o <<= 1) {
+        dq_acc.x += __shfl_xor_sync(kFull, dq_acc.x, o); dq_acc.y += __shfl_xor_sync(kFull, dq_acc.y, o);
+        dq_acc.z += __shfl_xor_sync(kFull, dq_acc.z, o); dq_acc.w += __shfl_xor_sync(kFull, dq_acc.w, o);
     }
+    if (grp == 0) *(reinterpret_cast<float4*>(dq + (((int64_t) n * H + h) * T_DST + t) * D) + sub) = dq_acc;
 }
 
 // dv_j += sum_{r >= j} (1 - a_r) dout_r / (r + 1): reverse running sum down the query rows, one thread per (n, h, channel).
@@ -243,7 +246,8 @@ extern "C" int sea_sparse_attention_bits_bwd(const uint32_t* mask_bits,
                                              int N, int H, int T_DST, int T_SRC, int D, int P, int k_clamp, int is_causal, void* stream) {
     SEA_CHECK_ARG(mask_bits && q && k && v && scales && dout && dq && dk && dv, "sea_sparse_attention_bits_bwd: null pointer");
     SEA_CHECK_ARG(N > 0 && H > 0 && T_DST > 0 && T_SRC >= T_DST && k_clamp > 0, "sea_sparse_attention_bits_bwd: bad shape");
-    SEA_CHECK_ARG(D > 0 && D <= 128 && D % 8 == 0 && (P % 32) == 0 && P <= 1024, "sea_sparse_attention_bits_bwd: needs D %% 8 == 0, D <= 128, P %% 32 == 0, P <= 1024");
+    SEA_CHECK_ARG((D == 32 || D == 64 || D == 128) && (P % 32) == 0 && P <= 1024, "sea_sparse_attention_bits_bwd: needs D in {32, 64, 128}, P %% 32 == 0, P <= 1024");
+    SEA_CHECK_ARG(((((uintptr_t) dq) | ((uintptr_t) dk) | ((uintptr_t) dv)) & 15) == 0, "sea_sparse_attention_bits_bwd: dq / dk / dv must be 16-byte aligned");
     SEA_CHECK_ARG(cumavg == nullptr || (is_causal && T_SRC == T_DST), "sea_sparse_attention_bits_bwd: the running-mean branch needs causal prefill (T_SRC == T_DST)");
     SEA_CHECK_ARG(((k_sn | k_sh | k_st | v_sn | v_sh | v_st) % 8) == 0 && ((((uintptr_t) k) | ((uintptr_t) v)) & 15) == 0,
                   "sea_sparse_attention_bits_bwd: k / v rows must be 16-byte aligned");
