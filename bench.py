@@ -352,6 +352,13 @@ def main():
             ach = sb[dom] / (dom_ms_launch * 1e-3) / 1e9
             roof = {'kernel': dom, 'bound': 'hbm', 'achieved': ach, 'peak': hbm, 'unit': 'GB/s', 'frac': ach / hbm, 'traffic': None,
                     'peak_source': which}
+        try:        # dram bytes per launch of the dominant kernel, from the committed ncu --set full capture (profiles/)
+            tr = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json'))).get(dom)
+            if tr:
+                roof['traffic'] = tr['dram_bytes_per_launch']
+                roof['traffic_source'] = tr['source']
+        except Exception:
+            pass
         total_bytes = sb['performer'] + sb['mlp'] + 2 * sb['conv'] + sb['tail'] + sb['topk'] + sb['csr'] + sb['attn']
         tokens = N * T * world
         line = {
