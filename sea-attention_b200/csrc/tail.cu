@@ -138,6 +138,12 @@ tail_topk_kernel(const float* __restrict__ y3, const float* __restrict__ bias, c
 //   * alive bits assembled with shuffles inside 32/(P/32)-lane groups; ties at the threshold are cut in flat-index order
 //     (lower h*P+m wins) with one warp scan per head.
 // ------------------------------------------------------------------------------------------------
+constexpr float kLog2eT = 1.4426950408889634f;
+__device__ __forceinline__ float ex2_fast(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 constexpr int kMaxCand = 1024;
 
 template <int kPerLane, int kHPW, int kUp>
@@ -153,6 +159,7 @@ tail_topk_reg_kernel(const float* __restrict__ y3, const float* __restrict__ bia
     __shared__ int scratch[16];
     __shared__ int head_eq[H];
     __shared__ uint32_t cand[kMaxCand];
+    __shared__ uint32_t s_orand[2];
     __shared__ int4 stap[P];
     float* ys = reinterpret_cast<float*>(smem_u);               // [H][W+2]: W conv outputs, then the bias (pad columns), then 0
     uint32_t* sbits = smem_u + H * (W + 3);                     // [G/32] (only for the fused row counts)
@@ -164,7 +171,9 @@ tail_topk_reg_kernel(const float* __restrict__ y3, const float* __restrict__ bia
     const int ex_blk_end = ex.is_causal ? ex_src_off + min((t / kMaskRowBlock + 1) * kMaskRowBlock, Tn) : ex.T_SRC;
     const int wneed = ex.dmask != nullptr ? min(ex.W64, (ex_blk_end + 63) >> 6) : 0;
     for (int i = tid; i < H * 2 * wneed; i += kTopkThreads) img[i] = 0u;
-    const int ldy = (W + 2) | 1;
+    hist[tid] = 0;
+    if (tid == 0) { s_orand[0] = 0u; s_orand[1] = 0xffffffffu; }
+    const int ldy = kUp > 0 ? ((P / (kUp > 0 ? kUp : 1) + 2) | 1) : ((W + 2) | 1);        // compile-time when the upsample factor is (W == P / kUp)
     const float* yr = y3 + ((int64_t) n * Tn + t) * W * H;
     for (int base = 0; base < W * H; base += 8 * kTopkThreads) {
         // 8 independent loads in flight per thread before the first (transposing) shared-memory store
@@ -206,8 +215,8 @@ tail_topk_reg_kernel(const float* __restrict__ y3, const float* __restrict__ bia
         const int4 tp = stap[i * 32 + lane];
         tap[i][0] = tp.x; tap[i][1] = tp.y; tap[i][2] = tp.z;
         rc[i] = __int_as_float(tp.w);
-        lw[i] = ln_w[j];
-        lb[i] = ln_b[j];
+        lw[i] = ln_w[j] * kLog2eT;          // softmax in the log2 domain: exp(x - max) == exp2(x * log2e - max * log2e)
+        lb[i] = ln_b[j] * kLog2eT;
     }
     constexpr float invP = 1.0f / (float) P;
     // The kHPW heads of this warp advance through LayerNorm / softmax stage by stage, so that the kHPW warp reductions of a
@@ -245,9 +254,10 @@ tail_topk_reg_kernel(const float* __restrict__ y3, const float* __restrict__ bia
 #pragma unroll
     for (int hh = 0; hh < kHPW; ++hh) {
         const float rstd = rsqrtf(red[hh] * invP + 1e-5f);
+        const float nmr = -mean[hh] * rstd;
         float mx = -INFINITY;
 #pragma unroll
-        for (int i = 0; i < kPerLane; ++i) { val[hh][i] = (val[hh][i] - mean[hh]) * rstd * lw[i] + lb[i]; mx = fmaxf(mx, val[hh][i]); }
+        for (int i = 0; i < kPerLane; ++i) { val[hh][i] = fmaf(fmaf(val[hh][i], rstd, nmr), lw[i], lb[i]); mx = fmaxf(mx, val[hh][i]); }
         red[hh] = mx;
     }
 #pragma unroll
@@ -259,7 +269,7 @@ tail_topk_reg_kernel(const float* __restrict__ y3, const float* __restrict__ bia
         const float mx = red[hh];
         float sum = 0.f;
 #pragma unroll
-        for (int i = 0; i < kPerLane; ++i) { val[hh][i] = __expf(val[hh][i] - mx); sum += val[hh][i]; }
+        for (int i = 0; i < kPerLane; ++i) { val[hh][i] = ex2_fast(val[hh][i] - mx); sum += val[hh][i]; }
         red[hh] = sum;
     }
 #pragma unroll
@@ -277,7 +287,8 @@ tail_topk_reg_kernel(const float* __restrict__ y3, const float* __restrict__ bia
             float* prow = probs + (((int64_t) n * H + h) * Tn + t) * P + lane * kPerLane;
             if constexpr (kPerLane % 4 == 0) {
 #pragma unroll
-                for (int i = 0; i < kPerLane; i += 4) *reinterpret_cast<float4*>(prow + i) = make_float4(val[hh][i], val[hh][i + 1], val[hh][i + 2], val[hh][i + 3]);
+                for (int i = 0; i < kPerLane; i += 4)       // streaming store: nothing on the hot path reads the probabilities back, keep them from evicting q / k / v
+                    __stcs(reinterpret_cast<float4*>(prow + i), make_float4(val[hh][i], val[hh][i + 1], val[hh][i + 2], val[hh][i + 3]));
             } else {
 #pragma unroll
                 for (int i = 0; i < kPerLane; ++i) prow[i] = val[hh][i];
@@ -300,11 +311,9 @@ tail_topk_reg_kernel(const float* __restrict__ y3, const float* __restrict__ bia
             for (int i = 0; i < kPerLane; ++i) { k_or |= key[hh][i]; k_and &= key[hh][i]; }
         k_or = __reduce_or_sync(kFull, k_or);
         k_and = __reduce_and_sync(kFull, k_and);
-        if (lane == 0) { hist[wid] = (int) k_or; hist[8 + wid] = (int) k_and; }
+        if (lane == 0) { atomicOr(&s_orand[0], k_or); atomicAnd(&s_orand[1], k_and); }       // initialised before the first barrier
         __syncthreads();
-#pragma unroll
-        for (int w = 0; w < kTopkThreads / 32; ++w) { k_or |= (uint32_t) hist[w]; k_and &= (uint32_t) hist[8 + w]; }
-        __syncthreads();
+        k_or = s_orand[0]; k_and = s_orand[1];
         const uint32_t diff = k_or ^ k_and;
         thr = k_and;                                             // bits above the first difference are common
         if (diff != 0u) {
@@ -315,8 +324,10 @@ tail_topk_reg_kernel(const float* __restrict__ y3, const float* __restrict__ bia
                 const int wd = min(8, top), sh = top - wd;
                 const uint32_t hi_mask = top >= 32 ? 0u : (0xffffffffu << top);
                 const uint32_t dmask = (1u << wd) - 1u;
-                hist[tid] = 0;
-                __syncthreads();
+                if (!first) {                                    // (zeroed at kernel start for the first pass)
+                    hist[tid] = 0;
+                    __syncthreads();
+                }
                 if (first) {                                     // every key carries the common prefix
 #pragma unroll
                     for (int hh = 0; hh < kHPW; ++hh)
@@ -356,13 +367,13 @@ tail_topk_reg_kernel(const float* __restrict__ y3, const float* __restrict__ bia
                 top = sh;
                 if (first && top > 0 && eq_total <= kMaxCand) {
                     // few keys share the pivot digit: list them and rank them directly instead of more radix passes
-                    const uint32_t pd = (uint32_t) scratch[8];
+                    const uint32_t dsel = dmask << sh, pdsel = (uint32_t) scratch[8] << sh;
 #pragma unroll
                     for (int hh = 0; hh < kHPW; ++hh)
 #pragma unroll
                         for (int i = 0; i < kPerLane; ++i) {
                             const uint32_t u = key[hh][i];
-                            if (((u >> sh) & dmask) == pd) cand[atomicAdd(&scratch[11], 1)] = u;
+                            if ((u & dsel) == pdsel) cand[atomicAdd(&scratch[11], 1)] = u;
                         }
                     __syncthreads();
                     const int nc = eq_total;
@@ -383,7 +394,7 @@ tail_topk_reg_kernel(const float* __restrict__ y3, const float* __restrict__ bia
                     top = 0;
                 }
                 first = false;
-                __syncthreads();
+                if (top > 0) __syncthreads();                    // scratch / hist are reused by the next pass
             }
         }
     }
