@@ -174,7 +174,7 @@ SEA_API int sea_predictor_mlp_fwd(const void* ctx, const void* v, int64_t v_sn, 
 
 /* a4 on the tensor cores (bf16 only; csrc/umma_mlp.cu): same computation as sea_predictor_mlp_fwd with both Linear
  * layers as chained tcgen05 GEMMs per 128-token tile (intermediates stay in TMEM / shared memory).  Shapes: D = 64,
- * S = 2, H | 128, W in {16,32,64}; ctx contiguous [N,H,T,2D] bf16; cnn_in bf16 [N,T,W,2H]; no t_pred output.
+ * S = 2, H <= 128, W in {16,32,64}; ctx contiguous [N,H,T,2D] bf16; cnn_in bf16 [N,T,W,2H]; no t_pred output.
  * workspace: >= sea_predictor_mlp_umma_workspace_bytes() bytes, 128-byte aligned.  The call re-packs enc_w / dec_w / scl_w
  * into it; passing all three as NULL reuses the packing a previous call left in `workspace` (inference: weights are constant). */
 SEA_API int sea_predictor_mlp_umma_supported(int dtype, int H, int D, int S, int W);
@@ -184,6 +184,13 @@ SEA_API int sea_predictor_mlp_umma_fwd(const void* ctx, const void* v, int64_t v
                                        const float* dec_w, const float* dec_b, const float* cnn_ln_w, const float* cnn_ln_b,
                                        const float* scl_w, const float* scl_b, void* cnn_in, float* scales, void* workspace,
                                        int N, int H, int T, int D, int S, int W, void* stream);
+/* Same with a padded output: cnn_in is [N,T,W,Cout], Cout >= 2H (channels 2H.. are written as zeros), so that models whose 2H != 64
+ * (e.g. OPT-125m, H = 12) can feed the 64-channel tcgen05 convolutions.  H need not divide 128. */
+SEA_API int sea_predictor_mlp_umma_fwd_ex(const void* ctx, const void* v, int64_t v_sn, int64_t v_sh, int64_t v_st,
+                                       const float* enc_w, const float* enc_b, const float* enc_ln_w, const float* enc_ln_b,
+                                       const float* dec_w, const float* dec_b, const float* cnn_ln_w, const float* cnn_ln_b,
+                                       const float* scl_w, const float* scl_b, void* cnn_in, float* scales, void* workspace,
+                                       int N, int H, int T, int D, int S, int W, int Cout, void* stream);
 
 /* a5  one CausalConv2d(C,C,3,padding=2,dilation=2,causal) + ReLU (modules.py:96-192;
  *     attention.py:271-274) on channels-last activations [N,T,W,C]:

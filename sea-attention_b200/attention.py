@@ -208,6 +208,7 @@ class PerlinAttention(nn.Module):
         self._shape_cache = {}
         self._packed = ops.PackedWeights()
         self.fuse_mask_expansion = False
+        self._padded_cache = None
 
     # ------------------------------------------------------------------------------------------------
     def _weights_fp32(self):
@@ -233,6 +234,31 @@ class PerlinAttention(nn.Module):
             w.update({'conv1_w': f(net[0].weight), 'conv1_b': f(net[0].bias), 'conv2_w': f(net[2].weight), 'conv2_b': f(net[2].bias),
                       'conv3_w': f(net[5].weight), 'conv3_b': f(net[5].bias)})
         return w
+
+    def _padded_conv_weights(self, w, C, H):
+        """Zero-padded copies of the CNN weights for the 64-channel tcgen05 kernels (conv 3x3: [C,C,5,3] -> [64,64,5,3]; 1x1:
+        [H,C] -> [32,64]); cached until a source parameter changes."""
+        net = self.attention_predictor_cnn[1].module.net
+        src = (net[0].module.weight, net[0].module.bias, net[2].module.weight, net[2].module.bias, net[5].module.weight, net[5].module.bias)
+        stamp = tuple((int(t.data_ptr()), int(t._version)) for t in src)
+        hit = self._padded_cache
+        if hit is not None and hit[0] == stamp:
+            return hit[1]
+        dev = w['conv1_w'].device
+        out = {}
+        for name in ('conv1', 'conv2'):
+            wt = torch.zeros((64, 64, 5, 3), dtype=torch.float32, device=dev)
+            wt[:C, :C] = w[name + '_w']
+            b = torch.zeros((64,), dtype=torch.float32, device=dev)
+            b[:C] = w[name + '_b']
+            out[name + '_w'], out[name + '_b'] = wt, b
+        w3 = torch.zeros((32, 64), dtype=torch.float32, device=dev)
+        w3[:H, :C] = w['conv3_w']
+        b3 = torch.zeros((32,), dtype=torch.float32, device=dev)
+        b3[:H] = w['conv3_b']
+        out['conv3_w'], out['conv3_b'] = w3, b3
+        self._padded_cache = (stamp, out)
+        return out
 
     def _shape_consts(self, H, P, T_SRC, T_DST, device):
         key = (H, P, T_SRC, T_DST, self.pconfig.k, self.pconfig.k_oversample, str(device))
@@ -294,15 +320,28 @@ class PerlinAttention(nn.Module):
         enc, dec, scl = self.attention_predictor_enc, self.attention_predictor_dec_row, self.attention_predictor_dec_scaler
         net = self.attention_predictor_cnn[1].module.net
         w['_src_mlp'] = (enc[0].weight, dec[0].weight, scl[0].weight)
-        cnn_in, scales, _ = ops.predictor_mlp(ctx, v, w, S, W, packed=pk)
+        # models whose 2H != 64 (e.g. OPT-125m, H = 12): run the 64-channel tcgen05 MLP / conv kernels on zero-padded channels
+        pad_c = (q.dtype == torch.bfloat16 and d == 64 and S * H < 64 and H <= 32 and P % 32 == 0 and W in (16, 32, 64)
+                 and ops.conv_umma_supported(q.dtype, W, 64, 64) and ctx.is_contiguous())
+        if pad_c:
+            wp = self._padded_conv_weights(w, S * H, H)
+            cnn_in, scales, _ = ops.predictor_mlp(ctx, v, w, S, W, packed=pk, c_out=64)
+            y = ops.causal_conv3x3_dil2_relu(cnn_in, wp['conv1_w'], wp['conv1_b'], packed=pk, slot='conv1', src=net[0].module.weight)
+            y = ops.causal_conv3x3_dil2_relu(y, wp['conv2_w'], wp['conv2_b'], packed=pk, slot='conv2', src=net[2].module.weight)
+        else:
+            cnn_in, scales, _ = ops.predictor_mlp(ctx, v, w, S, W, packed=pk)
+            y = ops.causal_conv3x3_dil2_relu(cnn_in, w['conv1_w'], w['conv1_b'], packed=pk, slot='conv1', src=net[0].module.weight)
+            y = ops.causal_conv3x3_dil2_relu(y, w['conv2_w'], w['conv2_b'], packed=pk, slot='conv2', src=net[2].module.weight)
         # a5 .. a7
         kpr = k_per_row.repeat(N) if N > 1 else k_per_row
-        y = ops.causal_conv3x3_dil2_relu(cnn_in, w['conv1_w'], w['conv1_b'], packed=pk, slot='conv1', src=net[0].module.weight)
-        y = ops.causal_conv3x3_dil2_relu(y, w['conv2_w'], w['conv2_b'], packed=pk, slot='conv2', src=net[2].module.weight)
         expanded_ws = None
-        if q.dtype == torch.bfloat16 and ops.conv_umma_supported(q.dtype, W, S * H, H) and P % 32 == 0:
+        if pad_c or (q.dtype == torch.bfloat16 and ops.conv_umma_supported(q.dtype, W, S * H, H) and P % 32 == 0):
             # tensor-core path: 1x1 conv before the upsample (tcgen05), then tail + softmax + top-k in one kernel
-            y3 = ops.conv1x1_umma(y, w['conv3_w'], w['conv3_b'], packed=pk, slot='conv3', src=net[5].module.weight)
+            if pad_c:
+                y3 = ops.conv1x1_umma(y, wp['conv3_w'], wp['conv3_b'], packed=pk, slot='conv3', src=net[5].module.weight)
+                y3 = y3[..., :H].contiguous()
+            else:
+                y3 = ops.conv1x1_umma(y, w['conv3_w'], w['conv3_b'], packed=pk, slot='conv3', src=net[5].module.weight)
             needs_grad = torch.is_grad_enabled() and any(t_.requires_grad for t_ in (q_for_score, k_for_score, v))
             if (self.fuse_mask_expansion and not self.output_attentions and not needs_grad and ops.attention_bits_supported(q.dtype, d, P)
                     and ops.tail_expand_supported(H, P)):

@@ -58,7 +58,7 @@ mlp_umma_kernel(const __grid_constant__ CUtensorMap tmap_ctx, const __grid_const
                 const float* __restrict__ dec_b, const float* __restrict__ scl_b,
                 const float* __restrict__ cnn_ln_w, const float* __restrict__ cnn_ln_b,
                 __nv_bfloat16* __restrict__ cnn_in, float* __restrict__ scales,
-                int N, int H, int T, int W, int TT, int tblocks, int num_tiles) {
+                int N, int H, int T, int W, int TT, int tblocks, int num_tiles, int Cout) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     float* par = reinterpret_cast<float*>(smem + MlpSmem::kPar);
@@ -72,7 +72,9 @@ mlp_umma_kernel(const __grid_constant__ CUtensorMap tmap_ctx, const __grid_const
     uint64_t* wbar = bars + 7;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
 
-    const int SW = 2 * W, C = 2 * H;
+    const int SW = 2 * W, C = Cout;                 // channels of the channels-last output (>= 2H; channels 2H.. are zero padding)
+    const int rows_used = TT * H;                   // rows of the 128-row tile that carry tokens (H need not divide 128)
+    const uint32_t atom_bytes = (uint32_t) rows_used * 128u;     // bytes one TMA box delivers
     const int N2 = SW + 16;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int i = threadIdx.x; i < 128; i += kMlpTcThreads) { s_enc_b[i] = enc_b[i]; s_ln_w[i] = enc_ln_w[i]; s_ln_b[i] = enc_ln_b[i]; }
@@ -102,7 +104,7 @@ mlp_umma_kernel(const __grid_constant__ CUtensorMap tmap_ctx, const __grid_const
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const int n = tile / tblocks, t0 = (tile % tblocks) * TT;
                 umma::mbar_wait(&empty1[buf], phase ^ 1);
-                umma::mbar_arrive_expect_tx(&full1[buf], 3 * kTile);
+                umma::mbar_arrive_expect_tx(&full1[buf], 3 * atom_bytes);
                 uint8_t* dst = smem + MlpSmem::kA1 + buf * 3 * kTile;
                 umma::tma_load_4d(dst, &tmap_ctx, &full1[buf], 0, t0, 0, n);
                 umma::tma_load_4d(dst + kTile, &tmap_ctx, &full1[buf], 64, t0, 0, n);
@@ -209,7 +211,7 @@ mlp_umma_kernel(const __grid_constant__ CUtensorMap tmap_ctx, const __grid_const
                 uint32_t r[2];
                 umma::tmem_ld_32x2(acc2 + lane_addr + (uint32_t) SW, r);
                 umma::tmem_ld_wait();
-                if (t < T) {
+                if (t < T && row < rows_used) {
                     float2 sc = make_float2(__uint_as_float(r[0]) + s_dec_b[SW], __uint_as_float(r[1]) + s_dec_b[SW + 1]);
                     *reinterpret_cast<float2*>(scales + ((((int64_t) n * H + h) * T + t) << 1)) = sc;
                 }
@@ -246,9 +248,14 @@ mlp_umma_kernel(const __grid_constant__ CUtensorMap tmap_ctx, const __grid_const
             // staging [tl][w][c] bf16 aliases A2: GEMM2 has completed (acc2_full), so A2 is free.
             // channel pair (2h, 2h+1) = (split 0, split 1) of this head
             __nv_bfloat16* stg = reinterpret_cast<__nv_bfloat16*>(a2s);
+            if (C > 2 * H) {                     // zero padding channels (the tcgen05 conv wants 64 channels): clear the block first
+                const int zchunks = (TT * W * C * 2) >> 4;
+                for (int g = et; g < zchunks; g += kMlpEpiThreads) *reinterpret_cast<uint4*>(a2s + (size_t) g * 16) = make_uint4(0, 0, 0, 0);
+                asm volatile("bar.sync 1, 512;" ::: "memory");
+            }
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-                if (i < W4) {
+                if (i < W4 && row < rows_used) {
                     const int w = cp * W4 + i;
                     const float v0 = (y0[i] - mu0) * rs0 * s_cw[w] + s_cb[w];
                     const float v1 = (y1[i] - mu1) * rs1 * s_cw[w] + s_cb[w];
@@ -282,16 +289,31 @@ using namespace sea;
 extern "C" {
 
 int sea_predictor_mlp_umma_supported(int dtype, int H, int D, int S, int W) {
-    return dtype == SEA_DTYPE_BF16 && D == 64 && S == 2 && H >= 1 && H <= 128 && (128 % H) == 0 && (W == 16 || W == 32 || W == 64);
+    return dtype == SEA_DTYPE_BF16 && D == 64 && S == 2 && H >= 1 && H <= 128 && (W == 16 || W == 32 || W == 64);
 }
 
 int64_t sea_predictor_mlp_umma_workspace_bytes(void) { return (int64_t) (kD2 * kD3 + 144 * kD2) * 2 + 1024; }
+
+int sea_predictor_mlp_umma_fwd_ex(const void* ctx, const void* v, int64_t v_sn, int64_t v_sh, int64_t v_st,
+                                  const float* enc_w, const float* enc_b, const float* enc_ln_w, const float* enc_ln_b,
+                                  const float* dec_w, const float* dec_b, const float* cnn_ln_w, const float* cnn_ln_b,
+                                  const float* scl_w, const float* scl_b, void* cnn_in, float* scales, void* workspace,
+                                  int N, int H, int T, int D, int S, int W, int Cout, void* stream);
 
 int sea_predictor_mlp_umma_fwd(const void* ctx, const void* v, int64_t v_sn, int64_t v_sh, int64_t v_st,
                                const float* enc_w, const float* enc_b, const float* enc_ln_w, const float* enc_ln_b,
                                const float* dec_w, const float* dec_b, const float* cnn_ln_w, const float* cnn_ln_b,
                                const float* scl_w, const float* scl_b, void* cnn_in, float* scales, void* workspace,
                                int N, int H, int T, int D, int S, int W, void* stream) {
+    return sea_predictor_mlp_umma_fwd_ex(ctx, v, v_sn, v_sh, v_st, enc_w, enc_b, enc_ln_w, enc_ln_b, dec_w, dec_b, cnn_ln_w, cnn_ln_b, scl_w, scl_b,
+                                         cnn_in, scales, workspace, N, H, T, D, S, W, S * H, stream);
+}
+
+int sea_predictor_mlp_umma_fwd_ex(const void* ctx, const void* v, int64_t v_sn, int64_t v_sh, int64_t v_st,
+                                  const float* enc_w, const float* enc_b, const float* enc_ln_w, const float* enc_ln_b,
+                                  const float* dec_w, const float* dec_b, const float* cnn_ln_w, const float* cnn_ln_b,
+                                  const float* scl_w, const float* scl_b, void* cnn_in, float* scales, void* workspace,
+                                  int N, int H, int T, int D, int S, int W, int Cout, void* stream) {
     SEA_CHECK_ARG(ctx && v && enc_b && enc_ln_w && enc_ln_b && dec_b && cnn_ln_w && cnn_ln_b && scl_b && ((enc_w && dec_w && scl_w) || (!enc_w && !dec_w && !scl_w)) &&
                   cnn_in && scales && workspace, "sea_predictor_mlp_umma_fwd: null pointer");
     if (!sea_predictor_mlp_umma_supported(SEA_DTYPE_BF16, H, D, S, W)) {
@@ -308,7 +330,10 @@ int sea_predictor_mlp_umma_fwd(const void* ctx, const void* v, int64_t v_sn, int
     if (enc_w != nullptr)           // all three weights nullptr: `workspace` still holds the packing of an earlier call
         pack_mlp_weights_kernel<<<(kD2 * kD3 + 255) / 256, 256, 0, s>>>(enc_w, dec_w, scl_w, w1, w2, SW);
     SEA_CHECK_LAUNCH("pack_mlp_weights_kernel");
-    const int TT = 128 / H;
+    SEA_CHECK_ARG(Cout >= S * H && Cout % 8 == 0 && W * Cout * 2 <= 32 * 1024, "sea_predictor_mlp_umma_fwd: Cout must be >= 2H, a multiple of 8, and one token's [W, Cout] block must fit 32 KB");
+    // tokens per tile: all H heads of TT consecutive tokens fill (up to) 128 rows, and the [TT, W, Cout] output block must fit the 32 KB staging area
+    int TT = 128 / H;
+    while (TT > 1 && TT * W * Cout * 2 > 32 * 1024) --TT;
     CUtensorMap t_ctx, t_v, t_w1, t_w2;
     {
         const uint64_t dims[4] = {(uint64_t) kD2, (uint64_t) T, (uint64_t) H, (uint64_t) N};
@@ -347,7 +372,7 @@ int sea_predictor_mlp_umma_fwd(const void* ctx, const void* v, int64_t v_sn, int
     const int grid = num_tiles < sms ? num_tiles : sms;
     mlp_umma_kernel<<<grid, kMlpTcThreads, MlpSmem::kTotal, s>>>(t_ctx, t_v, t_w1, t_w2, enc_b, enc_ln_w, enc_ln_b, dec_b, scl_b, cnn_ln_w,
                                                                  cnn_ln_b, reinterpret_cast<__nv_bfloat16*>(cnn_in), scales, N, H, T, W, TT,
-                                                                 tblocks, num_tiles);
+                                                                 tblocks, num_tiles, Cout);
     SEA_CHECK_LAUNCH("mlp_umma_kernel");
     return SEA_OK;
 }

@@ -287,14 +287,15 @@ class PackedWeights:
         return ws, True
 
 
-def predictor_mlp(ctx, v, w, S: int, W: int, want_t_pred=False, force_simt=False, packed: 'PackedWeights' = None):
+def predictor_mlp(ctx, v, w, S: int, W: int, want_t_pred=False, force_simt=False, packed: 'PackedWeights' = None, c_out: int = None):
     """a4.  `w` = dict of fp32 contiguous weights (enc_w, enc_b, enc_ln_w, enc_ln_b, dec_w, dec_b, cnn_ln_w, cnn_ln_b,
     scl_w, scl_b) -> cnn_in [N,T,W,H*S] channels-last, scales fp32 [N,H,T,2], t_pred or None."""
     _cuda(ctx, v)
     N, H, T, D2 = ctx.shape
     D = D2 // 2
     v = _inner_contig(v)
-    cnn_in = torch.empty((N, T, W, H * S), dtype=ctx.dtype, device=ctx.device)
+    c_out = H * S if c_out is None else int(c_out)      # > H*S: zero-padded channels (tensor-core path only)
+    cnn_in = torch.empty((N, T, W, c_out), dtype=ctx.dtype, device=ctx.device)
     scales = torch.empty((N, H, T, 2), dtype=torch.float32, device=ctx.device)
     lib = _lib.load()
     if (not want_t_pred and not force_simt and ctx.is_contiguous() and w.get('cnn_ln_w') is not None
@@ -306,12 +307,14 @@ def predictor_mlp(ctx, v, w, S: int, W: int, want_t_pred=False, force_simt=False
         else:
             ws, fresh = torch.empty((nbytes,), dtype=torch.uint8, device=ctx.device), True
         wp = (lambda t: t.data_ptr()) if fresh else (lambda t: None)
-        _lib.call('sea_predictor_mlp_umma_fwd', ctx.data_ptr(), v.data_ptr(), v.stride(0), v.stride(1), v.stride(2),
+        _lib.call('sea_predictor_mlp_umma_fwd_ex', ctx.data_ptr(), v.data_ptr(), v.stride(0), v.stride(1), v.stride(2),
                   wp(w['enc_w']), w['enc_b'].data_ptr(), w['enc_ln_w'].data_ptr(), w['enc_ln_b'].data_ptr(),
                   wp(w['dec_w']), w['dec_b'].data_ptr(), w['cnn_ln_w'].data_ptr(), w['cnn_ln_b'].data_ptr(),
                   wp(w['scl_w']), w['scl_b'].data_ptr(), cnn_in.data_ptr(), scales.data_ptr(), ws.data_ptr(),
-                  N, H, T, D, S, W, _stream(), kernels=2 if fresh else 1)
+                  N, H, T, D, S, W, c_out, _stream(), kernels=2 if fresh else 1)
         return cnn_in, scales, None
+    if c_out != H * S:
+        raise SeaError('predictor_mlp: padded output channels need the tensor-core kernel (bf16, D = 64, contiguous ctx)')
     t_pred = torch.empty((N, H, T, D2), dtype=ctx.dtype, device=ctx.device) if want_t_pred else None
     _lib.call('sea_predictor_mlp_fwd', ctx.data_ptr(), v.data_ptr(), v.stride(0), v.stride(1), v.stride(2), _dtype_code(ctx),
               w['enc_w'].data_ptr(), w['enc_b'].data_ptr(), w['enc_ln_w'].data_ptr(), w['enc_ln_b'].data_ptr(),

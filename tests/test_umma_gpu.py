@@ -77,7 +77,8 @@ def test_tail_topk_fused_matches_oracle(sea, N, H, T, W, P, k, ties):
     assert torch.equal(bits.cpu(), bits2.cpu())
 
 
-@pytest.mark.parametrize('N,H,T,P', [(1, 32, 64, 256), (2, 32, 37, 256), (1, 16, 50, 128), (1, 64, 9, 64), (1, 4, 70, 256)])
+@pytest.mark.parametrize('N,H,T,P', [(1, 32, 64, 256), (2, 32, 37, 256), (1, 16, 50, 128), (1, 64, 9, 64), (1, 4, 70, 256),
+                                     (1, 12, 45, 256), (2, 12, 33, 64), (1, 20, 19, 128)])        # H need not divide 128
 def test_mlp_umma_matches_simt(sea, N, H, T, P):
     import transformers
     d, S, W = 64, 2, P // 4
@@ -98,6 +99,11 @@ def test_mlp_umma_matches_simt(sea, N, H, T, P):
     # bf16 operands (weights and the GELU output are rounded to bf16 before each GEMM): 2e-2-class tolerance
     torch.testing.assert_close(a_sc.cpu(), b_sc.cpu(), rtol=3e-2, atol=3e-2)
     torch.testing.assert_close(a_in.float().cpu(), b_in.float().cpu(), rtol=5e-2, atol=5e-2)
+    if 2 * H < 64:      # zero-padded channels for the 64-channel tcgen05 convolutions (OPT-125m: H = 12)
+        p_in, p_sc, _ = sea.ops.predictor_mlp(ctx, v, w, S, W, c_out=64)
+        assert p_in.shape == (N, T, W, 64)
+        assert torch.equal(p_in[..., :2 * H], a_in) and torch.equal(p_sc, a_sc)
+        assert float(p_in[..., 2 * H:].float().abs().max()) == 0.0
 
 
 @pytest.mark.parametrize('N,H,T,nbf', [(1, 2, 128, 8), (2, 3, 200, 8), (1, 4, 515, 8), (1, 2, 96, 5), (1, 1, 300, 16), (1, 1, 40, 32)])
