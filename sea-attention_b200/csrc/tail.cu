@@ -146,18 +146,21 @@ __device__ __forceinline__ float ex2_fast(float x) {
 }
 constexpr int kMaxCand = 1024;
 
-template <int kPerLane, int kHPW, int kUp>
+template <int kPerLane, int kHPW, int kUp, bool kExactH>
 __global__ void __launch_bounds__(kTopkThreads, 3)
 tail_topk_reg_kernel(const float* __restrict__ y3, const float* __restrict__ bias, const float* __restrict__ ln_w,
                      const float* __restrict__ ln_b, const float* __restrict__ k_per_row, float* __restrict__ probs,
                      uint32_t* __restrict__ mask_bits, int32_t* __restrict__ crow_counts, int k_clamp,
-                     int N, int Tn, int W, MaskExpandArgs ex) {
-    constexpr int P = 32 * kPerLane, H = 8 * kHPW, G = H * P;
+                     int N, int Tn, int W, int Hr, MaskExpandArgs ex) {
+    // Hmax = 8 * kHPW head slots; Hr <= Hmax real heads (kExactH: Hr == Hmax, everything below folds to constants).  The slots
+    // h >= Hr hold no keys: they are skipped in every key loop and their alive bits stay 0.
+    constexpr int P = 32 * kPerLane, Hmax = 8 * kHPW;
+    const int H = kExactH ? Hmax : Hr, G = H * P;
     constexpr int kLanesPerWord = 32 / kPerLane > 0 ? 32 / kPerLane : 1;     // lanes that share one 32-pixel word (kPerLane <= 32)
     extern __shared__ __align__(16) uint32_t smem_u[];
     __shared__ int hist[256];
     __shared__ int scratch[16];
-    __shared__ int head_eq[H];
+    __shared__ int head_eq[Hmax];
     __shared__ uint32_t cand[kMaxCand];
     __shared__ uint32_t s_orand[2];
     __shared__ int4 stap[P];
@@ -225,7 +228,8 @@ tail_topk_reg_kernel(const float* __restrict__ y3, const float* __restrict__ bia
     float red[kHPW];
 #pragma unroll
     for (int hh = 0; hh < kHPW; ++hh) {
-        const float* yh = ys + (wid + 8 * hh) * ldy;
+        const bool hv = kExactH || wid + 8 * hh < H;                // warp-uniform
+        const float* yh = ys + (hv ? wid + 8 * hh : 0) * ldy;
         float s = 0.f;
 #pragma unroll
         for (int i = 0; i < kPerLane; ++i) {
@@ -282,8 +286,10 @@ tail_topk_reg_kernel(const float* __restrict__ y3, const float* __restrict__ bia
         const int h = wid + 8 * hh;
         const float inv = 1.0f / red[hh];
 #pragma unroll
-        for (int i = 0; i < kPerLane; ++i) { val[hh][i] *= inv; key[hh][i] = __float_as_uint(val[hh][i]) | 0x80000000u; }   // == orderable(): val >= +0
-        if (probs) {
+        const bool hv = kExactH || h < H;
+#pragma unroll
+        for (int i = 0; i < kPerLane; ++i) { val[hh][i] *= inv; key[hh][i] = hv ? (__float_as_uint(val[hh][i]) | 0x80000000u) : 0u; }   // == orderable(): val >= +0
+        if (probs && hv) {
             float* prow = probs + (((int64_t) n * H + h) * Tn + t) * P + lane * kPerLane;
             if constexpr (kPerLane % 4 == 0) {
 #pragma unroll
@@ -307,8 +313,10 @@ tail_topk_reg_kernel(const float* __restrict__ y3, const float* __restrict__ bia
         uint32_t k_or = 0u, k_and = 0xffffffffu;
 #pragma unroll
         for (int hh = 0; hh < kHPW; ++hh)
+            if (kExactH || wid + 8 * hh < H) {
 #pragma unroll
-            for (int i = 0; i < kPerLane; ++i) { k_or |= key[hh][i]; k_and &= key[hh][i]; }
+                for (int i = 0; i < kPerLane; ++i) { k_or |= key[hh][i]; k_and &= key[hh][i]; }
+            }
         k_or = __reduce_or_sync(kFull, k_or);
         k_and = __reduce_and_sync(kFull, k_and);
         if (lane == 0) { atomicOr(&s_orand[0], k_or); atomicAnd(&s_orand[1], k_and); }       // initialised before the first barrier
@@ -331,8 +339,10 @@ tail_topk_reg_kernel(const float* __restrict__ y3, const float* __restrict__ bia
                 if (first) {                                     // every key carries the common prefix
 #pragma unroll
                     for (int hh = 0; hh < kHPW; ++hh)
+                        if (kExactH || wid + 8 * hh < H) {
 #pragma unroll
-                        for (int i = 0; i < kPerLane; ++i) atomicAdd(&hist[(key[hh][i] >> sh) & dmask], 1);
+                            for (int i = 0; i < kPerLane; ++i) atomicAdd(&hist[(key[hh][i] >> sh) & dmask], 1);
+                        }
                 } else {
 #pragma unroll
                     for (int hh = 0; hh < kHPW; ++hh)
@@ -370,10 +380,12 @@ tail_topk_reg_kernel(const float* __restrict__ y3, const float* __restrict__ bia
                     const uint32_t dsel = dmask << sh, pdsel = (uint32_t) scratch[8] << sh;
 #pragma unroll
                     for (int hh = 0; hh < kHPW; ++hh)
+                        if (kExactH || wid + 8 * hh < H) {
 #pragma unroll
-                        for (int i = 0; i < kPerLane; ++i) {
-                            const uint32_t u = key[hh][i];
-                            if ((u & dsel) == pdsel) cand[atomicAdd(&scratch[11], 1)] = u;
+                            for (int i = 0; i < kPerLane; ++i) {
+                                const uint32_t u = key[hh][i];
+                                if ((u & dsel) == pdsel) cand[atomicAdd(&scratch[11], 1)] = u;
+                            }
                         }
                     __syncthreads();
                     const int nc = eq_total;
@@ -406,7 +418,7 @@ tail_topk_reg_kernel(const float* __restrict__ y3, const float* __restrict__ bia
         uint32_t a = 0u;
 #pragma unroll
         for (int i = 0; i < kPerLane; ++i) a |= ((all_alive || key[hh][i] >= thr) ? 1u : 0u) << i;
-        alive[hh] = a;
+        alive[hh] = (kExactH || wid + 8 * hh < H) ? a : 0u;
     }
     if (cut_ties) {                                              // CTA-uniform branch
         int eqc[kHPW], lane_before[kHPW];
@@ -447,7 +459,7 @@ tail_topk_reg_kernel(const float* __restrict__ y3, const float* __restrict__ bia
         uint32_t word = kPerLane >= 32 ? alive[hh] : (alive[hh] << (kPerLane * (lane % kLanesPerWord)));
 #pragma unroll
         for (int o = 1; o < kLanesPerWord; o <<= 1) word |= __shfl_xor_sync(kFull, word, o);
-        if ((lane % kLanesPerWord) == 0) {
+        if ((lane % kLanesPerWord) == 0 && (kExactH || h < H)) {
             const int w = h * (P >> 5) + lane / kLanesPerWord;
             out_row[w] = word;
             if (crow_counts != nullptr) sbits[w] = word;
@@ -461,7 +473,7 @@ tail_topk_reg_kernel(const float* __restrict__ y3, const float* __restrict__ bia
 #pragma unroll
         for (int hh = 0; hh < kHPW; ++hh) {
             uint32_t* himg = img + (wid + 8 * hh) * 2 * wneed;
-            for (uint32_t x = alive[hh]; x; x &= x - 1) {
+            for (uint32_t x = (kExactH || wid + 8 * hh < H) ? alive[hh] : 0u; x; x &= x - 1) {
                 const int m = lane * kPerLane + __ffs(x) - 1;
                 const int a = rs.edge(m), b = rs.edge(m + 1);
                 if (b > a)
@@ -523,36 +535,50 @@ static int tail_topk_impl(const float* y3, const float* bias, const float* ln_w,
     cudaStream_t s = (cudaStream_t) stream;
     const unsigned grid = (unsigned) ((int64_t) N * T);
     static const bool no_reg = getenv("SEA_TAIL_SMEM") != nullptr;        // development switch for A/B timing
-    if (!no_reg && H % 8 == 0 && (H / 8) * (P / 32) <= 32 && P <= 1024 && H <= 64) {
+    const int hp_slots = (H + 7) / 8;
+    if (!no_reg && hp_slots * (P / 32) <= 32 && P <= 1024 && H <= 64) {
         const size_t smem_r = (size_t) H * (W + 3) * 4 + (size_t) (G >> 5) * 4 + 16 + (ex.dmask ? (size_t) H * ex.W64 * 8 : 0);
         SEA_CHECK_ARG(smem_r <= 72 * 1024, "sea_predictor_tail_topk: row image too large for the fused mask expansion");
         bool launched = true;
+#define SEA_TAILR_L(PL, HP, UP, EX)                                                                                        \
+        {                                                                                                                  \
+            auto kern = tail_topk_reg_kernel<PL, HP, UP, EX>;                                                              \
+            SEA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_r), "smem attr"); \
+            kern<<<grid, kTopkThreads, smem_r, s>>>(y3, bias, ln_w, ln_b, k_per_row, probs, mask_bits, crow_counts, k_clamp, N, T, W, H, ex); \
+        }
 #define SEA_TAILR(PL, HP)                                                                                                  \
         {                                                                                                                  \
-            if (P / W == 4) {                                                                                              \
-                auto kern = tail_topk_reg_kernel<PL, HP, 4>;                                                               \
-                SEA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_r), "smem attr"); \
-                kern<<<grid, kTopkThreads, smem_r, s>>>(y3, bias, ln_w, ln_b, k_per_row, probs, mask_bits, crow_counts, k_clamp, N, T, W, ex); \
-            } else {                                                                                                       \
-                auto kern = tail_topk_reg_kernel<PL, HP, 0>;                                                               \
-                SEA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_r), "smem attr"); \
-                kern<<<grid, kTopkThreads, smem_r, s>>>(y3, bias, ln_w, ln_b, k_per_row, probs, mask_bits, crow_counts, k_clamp, N, T, W, ex); \
-            }                                                                                                              \
+            if (P / W == 4) SEA_TAILR_L(PL, HP, 4, true) else SEA_TAILR_L(PL, HP, 0, true)                                 \
         }
-        const int pl = P / 32, hp = H / 8;
-        if (pl == 8 && hp == 4) SEA_TAILR(8, 4)
-        else if (pl == 8 && hp == 2) SEA_TAILR(8, 2)
-        else if (pl == 8 && hp == 1) SEA_TAILR(8, 1)
-        else if (pl == 4 && hp == 4) SEA_TAILR(4, 4)
-        else if (pl == 4 && hp == 2) SEA_TAILR(4, 2)
-        else if (pl == 2 && hp == 1) SEA_TAILR(2, 1)
-        else if (pl == 16 && hp == 2) SEA_TAILR(16, 2)
-        else if (pl == 16 && hp == 1) SEA_TAILR(16, 1)
-        else if (pl == 2 && hp == 4) SEA_TAILR(2, 4)
-        else if (pl == 2 && hp == 2) SEA_TAILR(2, 2)
-        else if (pl == 4 && hp == 1) SEA_TAILR(4, 1)
-        else launched = false;
+#define SEA_TAILR_PART(PL, HP)            /* H < 8 * HP: some head slots are empty */                                      \
+        {                                                                                                                  \
+            if (P / W == 4) SEA_TAILR_L(PL, HP, 4, false) else SEA_TAILR_L(PL, HP, 0, false)                               \
+        }
+        const int pl = P / 32, hp = hp_slots;
+        if (H % 8 == 0) {
+            if (pl == 8 && hp == 4) SEA_TAILR(8, 4)
+            else if (pl == 8 && hp == 2) SEA_TAILR(8, 2)
+            else if (pl == 8 && hp == 1) SEA_TAILR(8, 1)
+            else if (pl == 4 && hp == 4) SEA_TAILR(4, 4)
+            else if (pl == 4 && hp == 2) SEA_TAILR(4, 2)
+            else if (pl == 2 && hp == 1) SEA_TAILR(2, 1)
+            else if (pl == 16 && hp == 2) SEA_TAILR(16, 2)
+            else if (pl == 16 && hp == 1) SEA_TAILR(16, 1)
+            else if (pl == 2 && hp == 4) SEA_TAILR(2, 4)
+            else if (pl == 2 && hp == 2) SEA_TAILR(2, 2)
+            else if (pl == 4 && hp == 1) SEA_TAILR(4, 1)
+            else launched = false;
+        } else {
+            if (pl == 8 && hp == 2) SEA_TAILR_PART(8, 2)          // e.g. OPT-125m: H = 12, P = 256
+            else if (pl == 4 && hp == 2) SEA_TAILR_PART(4, 2)
+            else if (pl == 2 && hp == 2) SEA_TAILR_PART(2, 2)
+            else if (pl == 8 && hp == 1) SEA_TAILR_PART(8, 1)
+            else if (pl == 2 && hp == 1) SEA_TAILR_PART(2, 1)
+            else launched = false;
+        }
+#undef SEA_TAILR_PART
 #undef SEA_TAILR
+#undef SEA_TAILR_L
         if (launched) {
             SEA_CHECK_LAUNCH("tail_topk_reg_kernel");
             return SEA_OK;
