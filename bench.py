@@ -250,13 +250,15 @@ def main():
     if use_graph:
         e2e_graphs = [capture(lambda b=b: mod(dbuf[b][0], dbuf[b][1], dbuf[b][2], dbuf[b][0], dbuf[b][1], dbuf[b][2], dbuf[b][0], dbuf[b][1], mask, None, None))
                       for b in range(2)]
-    s_h2d, s_d2h = torch.cuda.Stream(), torch.cuda.Stream()
+    s_h2d, s_d2h, s_h2d2 = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
+    split_h2d = os.environ.get('SEA_BENCH_SPLIT_H2D', '0') == '1'
 
     def timed_e2e(steps, warmup):
         main = torch.cuda.current_stream()
         comp_done = [torch.cuda.Event() for _ in range(2)]
         d2h_done = [torch.cuda.Event() for _ in range(2)]
         copied = [torch.cuda.Event() for _ in range(2)]
+        copied2 = [torch.cuda.Event() for _ in range(2)]
         outs = [None, None]
 
         def one(i):
@@ -264,9 +266,17 @@ def main():
             with torch.cuda.stream(s_h2d):
                 s_h2d.wait_event(comp_done[b])          # the forward that last read this buffer set has finished
                 dbuf[b][0].copy_(hq, non_blocking=True)
-                dbuf[b][1].copy_(hk, non_blocking=True)
-                dbuf[b][2].copy_(hv, non_blocking=True)
+                dbuf[b][1][:, : H // 2].copy_(hk[:, : H // 2], non_blocking=True) if split_h2d else dbuf[b][1].copy_(hk, non_blocking=True)
+                if not split_h2d:
+                    dbuf[b][2].copy_(hv, non_blocking=True)
                 copied[b].record(s_h2d)
+            if split_h2d:                               # second copy stream: keeps two DMA engines busy on the host->device direction
+                with torch.cuda.stream(s_h2d2):
+                    s_h2d2.wait_event(comp_done[b])
+                    dbuf[b][1][:, H // 2:].copy_(hk[:, H // 2:], non_blocking=True)
+                    dbuf[b][2].copy_(hv, non_blocking=True)
+                    copied2[b].record(s_h2d2)
+                main.wait_event(copied2[b])
             main.wait_event(copied[b])
             main.wait_event(d2h_done[b])                # the result buffer of this set has been drained
             if use_graph:
@@ -288,6 +298,7 @@ def main():
         for i in range(steps):
             one(i)
         main.wait_stream(s_h2d)
+        main.wait_stream(s_h2d2)
         main.wait_stream(s_d2h)
         e1.record()
         barrier()

@@ -303,6 +303,23 @@ SEA_API int sea_sparse_attention_bits_bwd(const uint32_t* mask_bits,
                                           const void* dout, float* dq, float* dk, float* dv, float* dscales,
                                           int N, int H, int T_DST, int T_SRC, int D, int P, int k_clamp, int is_causal, void* stream);
 
+/* Decode / use_cache form of a2 + a3 + a13 (csrc/performer_state.cu): replaces the reference's StatefulCausalPerformer /
+ * StatefulCumAvg (attention_state.py:43-98, 205-224).  `state` holds per (n, h) the fp32 running sums S [F][2D] | z [F] | vsum [D]
+ * (sea_performer_state_floats() floats, zero-initialised by the caller before the first token); the call advances it with the
+ * T_new tokens at positions t0 .. t0+T_new-1 (q, k, v [N,H,T_new,D] strided like the other entries, pos_emb rows indexed by the
+ * absolute position) and writes ctx [N,H,T_new,2D] and cumavg [N,H,T_new,D] (nullable) in `dtype`. */
+SEA_API int64_t sea_performer_state_floats(int N, int H, int D, int F);
+/* state += the sums of a whole prompt (tokens 0 .. T-1), chunk-parallel with fp32 atomics: what the prefill leaves for the decode. */
+SEA_API int sea_performer_state_build(const void* k, int64_t k_sn, int64_t k_sh, int64_t k_st,
+                                      const void* v, int64_t v_sn, int64_t v_sh, int64_t v_st,
+                                      const float* pos_emb, const float* proj, int dtype, float* state,
+                                      int N, int H, int T, int D, int F, void* stream);
+SEA_API int sea_performer_causal_state_fwd(const void* q, int64_t q_sn, int64_t q_sh, int64_t q_st,
+                                           const void* k, int64_t k_sn, int64_t k_sh, int64_t k_st,
+                                           const void* v, int64_t v_sn, int64_t v_sh, int64_t v_st,
+                                           const float* pos_emb, const float* proj, int dtype, float* state, void* ctx, void* cumavg,
+                                           int N, int H, int T_new, int t0, int D, int F, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Non-causal (BERT) variant, csrc/noncausal.cu.  No padding.
  * sea_performer_noncausal_fwd: v_for_atten = cat(grid-sampled identity, v) (attention.py:462-502) and the FAVOR+

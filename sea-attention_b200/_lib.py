@@ -72,6 +72,9 @@ _SIGNATURES = {
                                      _I, _I, _I, _I, _I, _I, _I, _I, _P, _L, _P]),
     'sea_sparse_attention_bits_bwd': (_I, [_P, _P, _L, _L, _L, _P, _L, _L, _L, _P, _L, _L, _L, _P, _P, _L, _L, _I, _I,
                                            _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    'sea_performer_state_floats': (_L, [_I, _I, _I, _I]),
+    'sea_performer_state_build': (_I, [_P, _L, _L, _L, _P, _L, _L, _L, _P, _P, _I, _P, _I, _I, _I, _I, _I, _P]),
+    'sea_performer_causal_state_fwd': (_I, [_P, _L, _L, _L, _P, _L, _L, _L, _P, _L, _L, _L, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     'sea_performer_noncausal_workspace_floats': (_L, [_I, _I, _I, _I, _I]),
     'sea_performer_noncausal_fwd': (_I, [_P, _L, _L, _L, _P, _L, _L, _L, _P, _L, _L, _L, _P, _I, _P, _P, _I, _I, _I, _I, _I, _P]),
     'sea_conv3x3_cl': (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),

@@ -20,6 +20,7 @@ import torch
 from torch import nn
 
 from . import ops
+from .attention_state import PerlinAttentionState
 from ._lib import SeaError
 from .config import PerlinAttentionConfig, get_default_config
 
@@ -279,8 +280,8 @@ class PerlinAttention(nn.Module):
             raise SeaError('QUERY_SKIPS > 1 (attention.py:598) is not implemented')
         if not q.is_cuda:
             raise SeaError('PerlinAttention (sea-attention_b200) runs on CUDA tensors only; there is no CPU path')
-        if pc.use_cache or last_state is not None:
-            raise SeaError('use_cache / PerlinAttentionState decoding is not implemented yet (SURVEY 8f-2)')
+        if (pc.use_cache or last_state is not None) and not pc.causal:
+            raise SeaError('use_cache / PerlinAttentionState is only defined for the causal model (attention_state.py)')
         if self.training or attention_scores_truth is not None or context_layer_truth is not None:
             raise SeaError('the training branch (dense path + KD losses, attention.py:707-765, 1066-1133) is not implemented yet '
                            '(SURVEY 8f-1); call under eval() without teacher tensors')
@@ -295,6 +296,14 @@ class PerlinAttention(nn.Module):
         if pc.k_flatten_dim != 'causal_batch' or not pc.k_flatten:
             raise SeaError("causal PerlinAttention needs k_flatten_dim='causal_batch' (perlin_opt.py:227-231)")
 
+        if pc.use_cache or last_state is not None:
+            return self._forward_causal_stateful(q, k, v, q_for_atten, k_for_atten, v_for_atten, q_for_score, k_for_score, attention_mask, last_state)
+        return self._forward_causal_prefill(q, k, v, q_for_atten, k_for_atten, v_for_atten, q_for_score, k_for_score, attention_mask)
+
+    # ------------------------------------------------------------------------------------------------
+    def _forward_causal_prefill(self, q, k, v, q_for_atten, k_for_atten, v_for_atten, q_for_score, k_for_score, attention_mask, capture=None):
+        """Causal prefill (T_DST == T_SRC).  `capture` (dict) receives the CNN intermediates the decode state is built from."""
+        pc = self.pconfig
         N, H, T, d = q.shape
         assert attention_mask.shape == (N, 1, T, T), f'causal additive mask must be [N,1,T,T], got {tuple(attention_mask.shape)}'
         assert k.shape == (N, H, T, d) and v.shape == (N, H, T, d)
@@ -326,12 +335,14 @@ class PerlinAttention(nn.Module):
         if pad_c:
             wp = self._padded_conv_weights(w, S * H, H)
             cnn_in, scales, _ = ops.predictor_mlp(ctx, v, w, S, W, packed=pk, c_out=64)
-            y = ops.causal_conv3x3_dil2_relu(cnn_in, wp['conv1_w'], wp['conv1_b'], packed=pk, slot='conv1', src=net[0].module.weight)
-            y = ops.causal_conv3x3_dil2_relu(y, wp['conv2_w'], wp['conv2_b'], packed=pk, slot='conv2', src=net[2].module.weight)
+            y1 = ops.causal_conv3x3_dil2_relu(cnn_in, wp['conv1_w'], wp['conv1_b'], packed=pk, slot='conv1', src=net[0].module.weight)
+            y = ops.causal_conv3x3_dil2_relu(y1, wp['conv2_w'], wp['conv2_b'], packed=pk, slot='conv2', src=net[2].module.weight)
         else:
             cnn_in, scales, _ = ops.predictor_mlp(ctx, v, w, S, W, packed=pk)
-            y = ops.causal_conv3x3_dil2_relu(cnn_in, w['conv1_w'], w['conv1_b'], packed=pk, slot='conv1', src=net[0].module.weight)
-            y = ops.causal_conv3x3_dil2_relu(y, w['conv2_w'], w['conv2_b'], packed=pk, slot='conv2', src=net[2].module.weight)
+            y1 = ops.causal_conv3x3_dil2_relu(cnn_in, w['conv1_w'], w['conv1_b'], packed=pk, slot='conv1', src=net[0].module.weight)
+            y = ops.causal_conv3x3_dil2_relu(y1, w['conv2_w'], w['conv2_b'], packed=pk, slot='conv2', src=net[2].module.weight)
+        if capture is not None:
+            capture['cnn_in'], capture['conv1'] = cnn_in, y1
         # a5 .. a7
         kpr = k_per_row.repeat(N) if N > 1 else k_per_row
         expanded_ws = None
@@ -386,6 +397,83 @@ class PerlinAttention(nn.Module):
             loss=0, context_layer=context, partial_attention_probs=partial_probs, partial_attention_mask=partial_mask,
             estimated_attention_probs_m=probs, estimated_attention_probs=probs, dense_attention_probs=None,
             key_for_score=k_for_score, state=None)
+
+    # ------------------------------------------------------------------------------------------------
+    def _forward_causal_stateful(self, q, k, v, q_for_atten, k_for_atten, v_for_atten, q_for_score, k_for_score, attention_mask, last_state):
+        """use_cache / decode path (reference attention_state.py + attention.py:559-572, 627-639, 1222-1236).
+        q holds the T_new NEW query tokens, k / v all T_SRC tokens seen so far (the caller's KV cache).
+          * last_state is None: prompt prefill through the normal kernels + construction of the state;
+          * otherwise: the new tokens are advanced one by one -- incremental Performer / running mean, the predictor MLP on one
+            token, the two dilated causal convs on a 5-row window, top-k of one row, sparse attention of one query row.
+        Row t of a decode equals row t of a prefill (the reference checks the same property in test_perlin_opt_cache.py)."""
+        pc = self.pconfig
+        N, H, T_new, d = q.shape
+        T_SRC = k.shape[2]
+        P = pc.attention_predictor_length
+        S = self.attention_predictor_dec_row_splits
+        W = P // self.attention_predictor_dec_row_down_scale
+        w = self._weights_fp32()
+        F = w['proj'].shape[0]
+        if last_state is None:
+            if T_new != T_SRC:
+                raise SeaError('use_cache without a state: the first call must be the prompt prefill (T_DST == T_SRC)')
+            cap = {}
+            out = self._forward_causal_prefill(q, k, v, q_for_atten, k_for_atten, v_for_atten, q_for_score, k_for_score, attention_mask, capture=cap)
+            st = PerlinAttentionState(t=T_SRC, performer=ops.performer_state_new(N, H, d, F, q.device))
+            ops.performer_state_build(k_for_atten, v, w['pos'], w['proj'], st.performer)
+
+            def last_rows(x):            # last 4 rows, zero-padded at the front for prompts shorter than 4 tokens
+                win = torch.zeros((N, 4) + tuple(x.shape[2:]), dtype=x.dtype, device=x.device)
+                n_ = min(4, x.shape[1])
+                win[:, 4 - n_:] = x[:, x.shape[1] - n_:]
+                return win
+            st.cnn_in_win, st.conv1_win = last_rows(cap['cnn_in']), last_rows(cap['conv1'])
+            return out._replace(state=st)
+
+        if v_for_atten.data_ptr() != v.data_ptr():
+            raise SeaError('v_for_atten must alias v (LoRA-in-approximation is not implemented)')
+        st = last_state.clone()
+        if st.t + T_new != T_SRC:
+            raise SeaError(f'state has consumed {st.t} tokens, got {T_new} new queries but {T_SRC} keys')
+        pk = self._packed
+        net = self.attention_predictor_cnn[1].module.net
+        enc, dec, scl = self.attention_predictor_enc, self.attention_predictor_dec_row, self.attention_predictor_dec_scaler
+        w['_src_mlp'] = (enc[0].weight, dec[0].weight, scl[0].weight)
+        C_win = st.cnn_in_win.shape[-1]
+        pad_c = C_win != S * H                       # the state was built on the zero-padded 64-channel path
+        wp = self._padded_conv_weights(w, S * H, H) if pad_c else w
+        contexts, prob_rows = [], []
+        for i in range(T_new):
+            t = st.t
+            qa, ka, v1 = q_for_atten[:, :, i:i + 1], k_for_atten[:, :, t:t + 1], v[:, :, t:t + 1]
+            ctx, cumavg = ops.performer_causal_state(qa, ka, v1, w['pos'], w['proj'], st.performer, t)
+            cnn_row, scales, _ = ops.predictor_mlp(ctx, v1, w, S, W, packed=pk, c_out=C_win if pad_c else None)      # [N,1,W,C]
+            x_win = torch.cat([st.cnn_in_win, cnn_row], dim=1)                                                       # rows t-4 .. t
+            y1 = ops.causal_conv3x3_dil2_relu(x_win, wp['conv1_w'], wp['conv1_b'], packed=pk, slot='conv1', src=net[0].module.weight)[:, 4:5]
+            y1_win = torch.cat([st.conv1_win, y1], dim=1)
+            y2 = ops.causal_conv3x3_dil2_relu(y1_win, wp['conv2_w'], wp['conv2_b'], packed=pk, slot='conv2', src=net[2].module.weight)[:, 4:5]
+            st.cnn_in_win, st.conv1_win = x_win[:, 1:].contiguous(), y1_win[:, 1:].contiguous()
+            y2 = y2[..., :S * H].contiguous()
+            probs, _ = ops.predictor_tail(y2, w['conv3_w'], w['conv3_b'], w['out_ln_w'], w['out_ln_b'], P)             # [N,H,1,P]
+            kpr = _k_per_row_causal(H, pc.k, pc.k_oversample, P, t + 1, 1, q.device)
+            bits = ops.topk_mask_bits(probs, kpr.repeat(N) if N > 1 else kpr, 'causal_batch')
+            qs, ks, vs = q_for_score[:, :, i:i + 1], k_for_score[:, :, :t + 1], v[:, :, :t + 1]
+            if ops.attention_bits_supported(q.dtype, d, P):
+                context = ops.sparse_attention_from_bits(bits, qs, ks, vs, scales, cumavg, P, pc.k, use_scaler=pc.partial_attention_scaler,
+                                                         is_causal=True, kernel='gather')
+            else:
+                crow, col, Z, head_ptr = ops.csr_from_bits(bits, H, P, pc.k, t + 1, is_causal=True, index_dtype=torch.int32, want_head_ptr=True)
+                context, _ = ops.sparse_attention(crow, col, qs, ks, vs, scales, cumavg, use_scaler=pc.partial_attention_scaler, want_probs=False,
+                                                  head_ptr=head_ptr)
+            contexts.append(context)
+            prob_rows.append(probs)
+            st.t = t + 1
+        context = contexts[0] if T_new == 1 else torch.cat(contexts, dim=1)
+        probs = prob_rows[0] if T_new == 1 else torch.cat(prob_rows, dim=2)
+        return PerlinAttentionOutput(
+            loss=0, context_layer=context, partial_attention_probs=None, partial_attention_mask=None,
+            estimated_attention_probs_m=probs, estimated_attention_probs=probs, dense_attention_probs=None,
+            key_for_score=k_for_score, state=st)
 
     # ------------------------------------------------------------------------------------------------
     def _forward_noncausal(self, q, k, v, q_for_atten, k_for_atten, v_for_atten, q_for_score, k_for_score, attention_mask):

@@ -370,6 +370,36 @@ def conv1x1_umma(x, weight, bias, packed: 'PackedWeights' = None, slot: str = 'c
     return y
 
 
+def performer_state_new(N: int, H: int, D: int, F: int, device) -> torch.Tensor:
+    """Zeroed decode state of the causal Performer + running mean (fp32; S | z | vsum per (n, h))."""
+    return torch.zeros((int(_lib.load().sea_performer_state_floats(N, H, D, F)),), dtype=torch.float32, device=device)
+
+
+def performer_state_build(k, v, pos_emb, proj, state: torch.Tensor):
+    """Adds the running sums of a whole prompt (k, v [N,H,T,D]) to `state` (in place): the state a prefill leaves for the decode."""
+    _cuda(k, v, pos_emb, proj, state)
+    N, H, T, D = k.shape
+    k, v = _inner_contig(k), _inner_contig(v)
+    _lib.call('sea_performer_state_build', k.data_ptr(), k.stride(0), k.stride(1), k.stride(2), v.data_ptr(), v.stride(0), v.stride(1), v.stride(2),
+              pos_emb.data_ptr(), proj.data_ptr(), _dtype_code(k), state.data_ptr(), N, H, T, D, proj.shape[0], _stream())
+    return state
+
+
+def performer_causal_state(q, k, v, pos_emb, proj, state: torch.Tensor, t0: int, want_cumavg=True):
+    """a2 + a3 + a13 advanced token by token from `state` (in place): q, k, v [N,H,T_new,D] are the NEW tokens at positions
+    t0 .. t0+T_new-1.  Returns ctx [N,H,T_new,2D], cumavg [N,H,T_new,D]."""
+    _cuda(q, k, v, pos_emb, proj, state)
+    N, H, T_new, D = q.shape
+    F = proj.shape[0]
+    q, k, v = _inner_contig(q), _inner_contig(k), _inner_contig(v)
+    ctx = torch.empty((N, H, T_new, 2 * D), dtype=q.dtype, device=q.device)
+    avg = torch.empty((N, H, T_new, D), dtype=q.dtype, device=q.device) if want_cumavg else None
+    _lib.call('sea_performer_causal_state_fwd', q.data_ptr(), q.stride(0), q.stride(1), q.stride(2), k.data_ptr(), k.stride(0), k.stride(1), k.stride(2),
+              v.data_ptr(), v.stride(0), v.stride(1), v.stride(2), pos_emb.data_ptr(), proj.data_ptr(), _dtype_code(q), state.data_ptr(),
+              ctx.data_ptr(), _p(avg), N, H, T_new, int(t0), D, F, _stream())
+    return ctx, avg
+
+
 def block_attention_workspace(N, H, T_DST, T_SRC, D, P, k_clamp, dtype, device):
     """Workspace of the short-context block attention (dense bit-packed mask + tile activity), or None when the library does
     not support the shape (the gather kernel is used then)."""

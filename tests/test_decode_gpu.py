@@ -1,0 +1,102 @@
+"""GPU tests of the use_cache / decode path.  The reference checks its stateful ops against the stateless
+forward (test_perlin_opt_cache.py: cache vs no-cache consistency); the same property is the parity target here: row t of a
+token-by-token decode equals row t of the prefill, whose parity with the reference is established in test_layer_gpu.py."""
+import pytest
+import torch
+
+from oracle import sea_oracle as so
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+def _module(sea, H, d, T, P, k, nbf, seed):
+    import transformers
+    torch.manual_seed(seed)
+    cfg = transformers.BertConfig(hidden_size=H * d, num_attention_heads=H, max_position_embeddings=T)
+    mod = sea.PerlinAttention(cfg, sea.PerlinAttentionConfig(performer_nb_factor=nbf, k=k, attention_predictor_length=P, causal=True)).eval().to(DEV)
+    for n_, p_ in mod.named_parameters():
+        if p_.ndim == 1:
+            p_.data.add_(0.1 * torch.randn_like(p_))
+    return mod
+
+
+def _close_rows(a, b, rtol, atol):
+    """fraction of rows (dim 1) of two [N,T,C] tensors that agree within tolerance"""
+    ok = ((a - b).abs() <= atol + rtol * b.abs()).all(dim=-1).all(dim=0)
+    return float(ok.float().mean())
+
+
+@pytest.mark.parametrize('N,H,d,T,T0,P,k', [(1, 4, 64, 48, 29, 32, 8), (2, 3, 32, 40, 2, 32, 8)])
+def test_decode_matches_prefill_fp32(sea, N, H, d, T, T0, P, k):
+    mod = _module(sea, H, d, T, P, k, 8, seed=T + H)
+    g = torch.Generator().manual_seed(7)
+    q = (torch.randn(N, H, T, d, generator=g) * d ** -0.5).to(DEV)
+    kk = torch.randn(N, H, T, d, generator=g).to(DEV)
+    v = torch.randn(N, H, T, d, generator=g).to(DEV)
+    full = mod(q, kk, v, q, kk, v, q, kk, so.causal_additive_mask(T, torch.float32, N).to(DEV), None, None)
+    assert full.state is None
+    mod.pconfig.use_cache = True
+    s = lambda x, a, b: x[:, :, a:b]
+    out0 = mod(s(q, 0, T0), s(kk, 0, T0), s(v, 0, T0), s(q, 0, T0), s(kk, 0, T0), s(v, 0, T0), s(q, 0, T0), s(kk, 0, T0),
+               so.causal_additive_mask(T0, torch.float32, N).to(DEV), None, None)
+    assert out0.state is not None and out0.state.t == T0
+    torch.testing.assert_close(out0.context_layer, full.context_layer[:, :T0], rtol=1e-4, atol=1e-5)
+    state = out0.state
+    ctx_rows, prob_rows = [], []
+    t = T0
+    for step in (1, 1, 3, 1):                      # single tokens and a 3-token chunk
+        while t + step <= T and (step == 3 or len(ctx_rows) < 100):
+            dummy = torch.zeros(N, 1, step, t + step, device=DEV)
+            o = mod(s(q, t, t + step), s(kk, 0, t + step), s(v, 0, t + step), s(q, t, t + step), s(kk, 0, t + step), s(v, 0, t + step),
+                    s(q, t, t + step), s(kk, 0, t + step), dummy, None, None, last_state=state)
+            assert o.state.t == t + step and state.t == t          # functional update: the caller's state is untouched
+            state = o.state
+            ctx_rows.append(o.context_layer)
+            prob_rows.append(o.estimated_attention_probs)
+            t += step
+            if step == 3:
+                break
+        if t >= T:
+            break
+    while t < T:
+        dummy = torch.zeros(N, 1, 1, t + 1, device=DEV)
+        o = mod(s(q, t, t + 1), s(kk, 0, t + 1), s(v, 0, t + 1), s(q, t, t + 1), s(kk, 0, t + 1), s(v, 0, t + 1), s(q, t, t + 1), s(kk, 0, t + 1),
+                dummy, None, None, last_state=state)
+        state = o.state
+        ctx_rows.append(o.context_layer)
+        prob_rows.append(o.estimated_attention_probs)
+        t += 1
+    ctx = torch.cat(ctx_rows, dim=1)
+    probs = torch.cat(prob_rows, dim=2)
+    torch.testing.assert_close(probs, full.estimated_attention_probs[:, :, T0:], rtol=1e-3, atol=1e-6)
+    # a near-tie of the top-k may flip under the (1e-6-level) different summation order of the incremental Performer
+    assert _close_rows(ctx, full.context_layer[:, T0:], 1e-3, 1e-4) >= 0.9
+
+
+def test_decode_bf16_tensor_core_shape(sea):
+    """OPT-1.3B-like head count (tcgen05 MLP / conv kernels in the step): probabilities track the prefill within bf16 tolerance."""
+    N, H, d, T, T0, P, k = 1, 32, 64, 80, 64, 64, 16
+    mod = _module(sea, H, d, T, P, k, 8, seed=3)
+    g = torch.Generator().manual_seed(8)
+    q = (torch.randn(N, H, T, d, generator=g) * d ** -0.5).bfloat16().to(DEV)
+    kk = torch.randn(N, H, T, d, generator=g).bfloat16().to(DEV)
+    v = torch.randn(N, H, T, d, generator=g).bfloat16().to(DEV)
+    full = mod(q, kk, v, q, kk, v, q, kk, so.causal_additive_mask(T, torch.bfloat16, N).to(DEV), None, None)
+    mod.pconfig.use_cache = True
+    s = lambda x, a, b: x[:, :, a:b]
+    o = mod(s(q, 0, T0), s(kk, 0, T0), s(v, 0, T0), s(q, 0, T0), s(kk, 0, T0), s(v, 0, T0), s(q, 0, T0), s(kk, 0, T0),
+            so.causal_additive_mask(T0, torch.bfloat16, N).to(DEV), None, None)
+    state = o.state
+    rows, prows = [], []
+    for t in range(T0, T):
+        o = mod(s(q, t, t + 1), s(kk, 0, t + 1), s(v, 0, t + 1), s(q, t, t + 1), s(kk, 0, t + 1), s(v, 0, t + 1), s(q, t, t + 1), s(kk, 0, t + 1),
+                torch.zeros(N, 1, 1, t + 1, device=DEV, dtype=torch.bfloat16), None, None, last_state=state)
+        state = o.state
+        rows.append(o.context_layer)
+        prows.append(o.estimated_attention_probs)
+    probs = torch.cat(prows, dim=2)
+    torch.testing.assert_close(probs, full.estimated_attention_probs[:, :, T0:], rtol=1e-1, atol=2e-3)
+    ctx = torch.cat(rows, dim=1).float()
+    assert torch.isfinite(ctx).all()
+    assert _close_rows(ctx, full.context_layer[:, T0:].float(), 5e-2, 5e-2) >= 0.5
