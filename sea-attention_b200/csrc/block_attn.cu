@@ -365,16 +365,25 @@ expand_mask_kernel(const uint32_t* __restrict__ mask_bits, unsigned long long* _
         }
     }
     __syncthreads();
-    // tile activity of the (head, 128-row query block): which 64-token tiles hold an alive element of any of its rows
-    uint32_t* act_blk = tile_act + (int64_t) n * H * ((T_DST + kBM - 1) / kBM) * act_words + (int64_t) (t / kBM) * act_words;
-    const int64_t act_hs = (int64_t) ((T_DST + kBM - 1) / kBM) * act_words;
+    // tile activity of the (head, 128-row query block): which 64-token tiles hold an alive element of any of its rows.
+    // Collected per CTA in shared memory first, so that a row issues at most H * act_words global atomics.
+    uint32_t* act_sm = ex_sm + H * 2 * W64;                                   // [H][act_words]
+    for (int i = threadIdx.x; i < H * act_words; i += blockDim.x) act_sm[i] = 0u;
+    __syncthreads();
     for (int i = threadIdx.x; i < H * wneed; i += blockDim.x) {
         const int h = i / wneed, w = i - h * wneed;
-        const uint2 v = *reinterpret_cast<const uint2*>(ex_sm + 2 * i);
+        const uint2 v = *reinterpret_cast<const uint2*>(ex_sm + 2 * (h * wneed + w));
         dmask[(((int64_t) n * H + h) * T_DST + t) * W64 + w] = (unsigned long long) v.x | ((unsigned long long) v.y << 32);
-        if ((v.x | v.y) != 0u) {
-            uint32_t* aw = act_blk + h * act_hs + (w >> 5);
-            if (!((*aw >> (w & 31)) & 1u)) atomicOr(aw, 1u << (w & 31));
+        if ((v.x | v.y) != 0u) atomicOr(act_sm + h * act_words + (w >> 5), 1u << (w & 31));
+    }
+    __syncthreads();
+    uint32_t* act_blk = tile_act + (int64_t) n * H * ((T_DST + kBM - 1) / kBM) * act_words + (int64_t) (t / kBM) * act_words;
+    const int64_t act_hs = (int64_t) ((T_DST + kBM - 1) / kBM) * act_words;
+    for (int i = threadIdx.x; i < H * act_words; i += blockDim.x) {
+        const uint32_t bits = act_sm[i];
+        if (bits != 0u) {
+            uint32_t* aw = act_blk + (i / act_words) * act_hs + (i % act_words);
+            if ((__ldcg(aw) & bits) != bits) atomicOr(aw, bits);
         }
     }
 }
@@ -426,7 +435,7 @@ int sea_block_attention_fwd(const uint32_t* mask_bits,
     const int p_lg = exact_edge_shift(P, T_SRC);      // integer pixel edges are exact iff P is a power of two and m * L stays below 2^24
     if (mask_bits != nullptr) {      // nullptr: `workspace` was filled by sea_predictor_tail_topk_expand_fwd (mask expansion fused into the top-k)
         SEA_CUDA_TRY(cudaMemsetAsync(tile_act, 0, (size_t) mask_act_bytes(N, H, T_DST, T_SRC), s), "memset tile activity");
-        const size_t smem = (size_t) H * W64 * 8;
+        const size_t smem = (size_t) H * W64 * 8 + (size_t) H * act_words * 4;
         SEA_CHECK_ARG(smem <= 200 * 1024, "sea_block_attention_fwd: H * T_SRC too large for the mask expansion");
         SEA_CUDA_TRY(cudaFuncSetAttribute(expand_mask_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem), "smem attr");
         expand_mask_kernel<<<(unsigned) ((int64_t) N * T_DST), 256, smem, s>>>(mask_bits, dmask, tile_act, act_words, W64, N, H, T_DST, T_SRC, P, p_lg, is_causal);
