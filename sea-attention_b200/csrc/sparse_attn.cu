@@ -379,173 +379,13 @@ sparse_attention_v2_kernel(const IdxT* __restrict__ col, int64_t Z, const int32_
 
 
 // ------------------------------------------------------------------------------------------------
-// v3: attention straight from the top-k BIT MASK.  The flat-CSR column list is a pure function of the bit mask
-// (a8), so when the caller does not ask for the CSR tensors the entries are enumerated on the fly, per (row, head),
-// with the same pixel arithmetic (csr_common.cuh) -- the count / scan / fill kernels and the 4 bytes per entry of
-// column ids leave the hot path.  Entry order inside a (row, head) segment equals the CSR order (pixels ascending,
-// tokens descending inside a pixel), so results match the CSR kernels up to fp32 summation order.
+// Attention straight from the top-k BIT MASK.  The flat-CSR column list is a pure function of the bit mask (a8), so when the
+// caller does not ask for the CSR tensors the entries are enumerated on the fly, per (row, head), with the same pixel
+// arithmetic (csr_common.cuh) -- the count / scan / fill kernels and the 4 bytes per entry of column ids leave the hot path.
+// Entry order inside a (row, head) segment equals the CSR order (pixels ascending, tokens descending inside a pixel), so results
+// match the CSR kernels up to fp32 summation order.  (A CUDA-core version of this kernel measured no faster than the CSR path
+// and was removed; the tensor-core version below is the one in use.)
 // ------------------------------------------------------------------------------------------------
-template <typename T16, int D>
-__global__ void __launch_bounds__(kAttnWarps * 32, 3)
-sparse_attention_bits_kernel(const uint32_t* __restrict__ mask_bits,
-                             const T16* __restrict__ q, int64_t q_sn, int64_t q_sh, int64_t q_st,
-                             const T16* __restrict__ k, int64_t k_sn, int64_t k_sh, int64_t k_st,
-                             const T16* __restrict__ v, int64_t v_sn, int64_t v_sh, int64_t v_st,
-                             const float* __restrict__ scales, const T16* __restrict__ cumavg, int64_t avg_sh, int64_t avg_st, int use_scaler,
-                             T16* __restrict__ out, int N, int H, int T_DST, int T_SRC, int P, int k_clamp, int is_causal) {
-    constexpr int LPR = D / 8, EPI = 32 / LPR, NI = 32 / EPI;
-    const int lane = threadIdx.x & 31;
-    const int64_t task = (int64_t) blockIdx.x * kAttnWarps + (threadIdx.x >> 5);
-    if (task >= (int64_t) N * T_DST * H) return;
-    const int t = (int) (task % T_DST);
-    const int h = (int) ((task / T_DST) % H);
-    const int n = (int) (task / ((int64_t) T_DST * H));
-    const int64_t row = (int64_t) n * T_DST + t;
-    const int sub = lane % LPR, grp = lane / LPR;
-    const uint4* kb = reinterpret_cast<const uint4*>(k + (int64_t) n * k_sn + (int64_t) h * k_sh) + sub;
-    const uint4* vb = reinterpret_cast<const uint4*>(v + (int64_t) n * v_sn + (int64_t) h * v_sh) + sub;
-    const uint32_t k_sv = (uint32_t) (k_st >> 3), v_sv = (uint32_t) (v_st >> 3);
-    constexpr float kLog2e = 1.4426950408889634f;
-    float qf[8];
-    {
-        const uint4 qu = __ldg(reinterpret_cast<const uint4*>(q + (int64_t) n * q_sn + (int64_t) h * q_sh + (int64_t) t * q_st) + sub);
-        unpack8<T16>(qu, qf);
-#pragma unroll
-        for (int c = 0; c < 8; ++c) qf[c] *= kLog2e;
-    }
-    float m_run = -INFINITY, l_run = 0.f;
-    float acc[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-
-    // this head's P mask bits: lane w holds word w (P/32 <= 32 words)
-    const int nw = P >> 5;
-    const int L = is_causal ? (T_SRC - T_DST + t + 1) : T_SRC;
-    const float s_scale = __fdiv_rn((float) L, (float) P);
-    const uint32_t word = lane < nw ? mask_bits[row * ((int64_t) H * nw) + (int64_t) h * nw + lane] : 0u;
-    const int pc = __popc(word);
-    const int pc_incl = warp_scan_incl_i(pc, lane);
-    const int n_alive = __shfl_sync(kFull, pc_incl, 31);
-    for (int r0 = 0; r0 < n_alive; r0 += 32) {
-        // lane takes the (r0 + lane)-th alive pixel of the head
-        const int slot = r0 + lane;
-        int wi = 0;
-#pragma unroll
-        for (int step = 16; step > 0; step >>= 1) {
-            const int vv = __shfl_sync(kFull, pc_incl, wi + step - 1);
-            if (vv <= slot) wi += step;
-        }
-        wi = min(wi, 31);
-        const uint32_t wsel = __shfl_sync(kFull, word, wi);
-        const int before = __shfl_sync(kFull, pc_incl - pc, wi);
-        int wd = 0, ve_i = 0, span_i = 0;
-        if (slot < n_alive) {
-            const int bit = __fns(wsel, 0, slot - before + 1);
-            float vs, ve;
-            pixel_bounds(s_scale, (wi << 5) + bit, vs, ve);
-            span_i = (int) __fsub_rn(ve, vs);
-            ve_i = (int) ve;
-            wd = min(span_i, k_clamp);
-        }
-        const int incl = warp_scan_incl_i(wd, lane);
-        const int excl = incl - wd;
-        const int total = __shfl_sync(kFull, incl, 31);
-        for (int e0 = 0; e0 < total; e0 += 32) {
-            const int cnt = min(32, total - e0);
-            const int e = e0 + lane;
-            int pl = 0;
-#pragma unroll
-            for (int step = 16; step > 0; step >>= 1) {
-                const int vv = __shfl_sync(kFull, incl, pl + step - 1);
-                if (vv <= e) pl += step;
-            }
-            pl = min(pl, 31);
-            const int p_excl = __shfl_sync(kFull, excl, pl);
-            const int p_ve = __shfl_sync(kFull, ve_i, pl);
-            const int p_wd = __shfl_sync(kFull, wd, pl);
-            const int p_span = __shfl_sync(kFull, span_i, pl);
-            int jmine = 0;
-            if (lane < cnt) {
-                const int i = e - p_excl;
-                jmine = p_wd == p_span ? p_ve - 1 - i
-                                       : p_ve - 1 - (int) __fmul_rn((float) i, __fdiv_rn((float) p_span, (float) p_wd));
-            }
-            uint4 ku[NI], vu[NI];
-#pragma unroll
-            for (int i = 0; i < NI; ++i) {
-                const int ee = i * EPI + grp;
-                const uint32_t j = (uint32_t) __shfl_sync(kFull, jmine, ee);
-                ku[i] = make_uint4(0, 0, 0, 0);
-                vu[i] = make_uint4(0, 0, 0, 0);
-                if (ee < cnt) {
-                    ku[i] = __ldg(kb + j * k_sv);
-                    vu[i] = __ldg(vb + j * v_sv);
-                }
-            }
-            float sc[NI];
-            float cmax = -INFINITY;
-#pragma unroll
-            for (int i = 0; i < NI; ++i) {
-                float kf[8];
-                unpack8<T16>(ku[i], kf);
-                float d = 0.f;
-#pragma unroll
-                for (int c = 0; c < 8; ++c) d = fmaf(qf[c], kf[c], d);
-#pragma unroll
-                for (int o = LPR / 2; o > 0; o >>= 1) d += __shfl_xor_sync(kFull, d, o);
-                sc[i] = (i * EPI + grp < cnt) ? d : -INFINITY;
-                cmax = fmaxf(cmax, sc[i]);
-            }
-#pragma unroll
-            for (int o = LPR; o < 32; o <<= 1) cmax = fmaxf(cmax, __shfl_xor_sync(kFull, cmax, o));
-            const float m_new = fmaxf(m_run, cmax);
-            const float alpha = ex2_approx(m_run - m_new);
-            float psum = 0.f;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) acc[i] *= alpha;
-#pragma unroll
-            for (int i = 0; i < NI; ++i) {
-                const float p = ex2_approx(sc[i] - m_new);
-                psum += p;
-                float vf[8];
-                unpack8<T16>(vu[i], vf);
-#pragma unroll
-                for (int c = 0; c < 8; ++c) acc[c] = fmaf(p, vf[c], acc[c]);
-            }
-#pragma unroll
-            for (int o = LPR; o < 32; o <<= 1) psum += __shfl_xor_sync(kFull, psum, o);
-            l_run = l_run * alpha + psum;
-            m_run = m_new;
-        }
-    }
-#pragma unroll
-    for (int o = LPR; o < 32; o <<= 1) {
-#pragma unroll
-        for (int c = 0; c < 8; ++c) acc[c] += __shfl_xor_sync(kFull, acc[c], o);
-    }
-    if (grp == 0) {
-        const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
-        const float* sp = scales + ((((int64_t) n * H + h) * T_DST + t) << 1);
-        const float psc = use_scaler ? sigmoidf_(sp[0]) : 1.0f;
-        const float a = sigmoidf_(sp[1]);
-        float o8[8];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) o8[c] = acc[c] * inv * psc;
-        if (cumavg != nullptr) {
-            const uint4 au = __ldg(reinterpret_cast<const uint4*>(cumavg + ((int64_t) n * H + h) * avg_sh + (int64_t) t * avg_st) + sub);
-            float af[8];
-            unpack8<T16>(au, af);
-#pragma unroll
-            for (int c = 0; c < 8; ++c) o8[c] = o8[c] * a + (1.0f - a) * af[c];
-        }
-        uint4 ou;
-        ou.x = pack2<T16>(o8[0], o8[1]); ou.y = pack2<T16>(o8[2], o8[3]);
-        ou.z = pack2<T16>(o8[4], o8[5]); ou.w = pack2<T16>(o8[6], o8[7]);
-        *(reinterpret_cast<uint4*>(out + ((int64_t) n * T_DST + t) * ((int64_t) H * D) + (int64_t) h * D) + sub) = ou;
-    }
-}
-
-
 // ------------------------------------------------------------------------------------------------
 // v4: the per-(row, head) segment on the TENSOR CORES.  A single query row is a degenerate GEMM, but the CUDA-core
 // version of v2/v3 spends ~800 instructions per 32 entries on bf16 unpacking, FMAs and shuffle reductions, and is
@@ -864,18 +704,12 @@ extern "C" int sea_sparse_attention_bits_fwd(const uint32_t* mask_bits,
     cudaStream_t s = (cudaStream_t) stream;
     const int64_t tasks = (int64_t) N * T_DST * H;
     const unsigned grid = (unsigned) ((tasks + kAttnWarps - 1) / kAttnWarps);
-    static const bool use_mma = getenv("SEA_ATTN_NO_MMA") == nullptr;     // development switch: CUDA-core variant for A/B timing
 #define SEA_ATTN_BITS(TT, DD)                                                                                                   \
     do {                                                                                                                        \
-        if (use_mma) {                                                                                                          \
-            auto kern = sparse_attention_bits_mma_kernel<TT, DD>;                                                               \
-            SEA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnMmaCfg<DD>::kSmemBytes), "smem attr"); \
-            kern<<<grid, kAttnWarps * 32, AttnMmaCfg<DD>::kSmemBytes, s>>>(mask_bits, (const TT*) q, q_sn, q_sh, q_st, (const TT*) k, k_sn,  \
-                k_sh, k_st, (const TT*) v, v_sn, v_sh, v_st, scales, (const TT*) cumavg, avg_sh, avg_st, use_scaler, (TT*) out, N, H, T_DST, T_SRC, P, k_clamp, is_causal); \
-        } else {                                                                                                                \
-            sparse_attention_bits_kernel<TT, DD><<<grid, kAttnWarps * 32, 0, s>>>(mask_bits, (const TT*) q, q_sn, q_sh, q_st, (const TT*) k, k_sn, \
-                k_sh, k_st, (const TT*) v, v_sn, v_sh, v_st, scales, (const TT*) cumavg, avg_sh, avg_st, use_scaler, (TT*) out, N, H, T_DST, T_SRC, P, k_clamp, is_causal); \
-        }                                                                                                                       \
+        auto kern = sparse_attention_bits_mma_kernel<TT, DD>;                                                                   \
+        SEA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnMmaCfg<DD>::kSmemBytes), "smem attr"); \
+        kern<<<grid, kAttnWarps * 32, AttnMmaCfg<DD>::kSmemBytes, s>>>(mask_bits, (const TT*) q, q_sn, q_sh, q_st, (const TT*) k, k_sn,  \
+            k_sh, k_st, (const TT*) v, v_sn, v_sh, v_st, scales, (const TT*) cumavg, avg_sh, avg_st, use_scaler, (TT*) out, N, H, T_DST, T_SRC, P, k_clamp, is_causal); \
     } while (0)
     if (dtype == SEA_DTYPE_BF16) {
         if (D == 32) SEA_ATTN_BITS(__nv_bfloat16, 32); else if (D == 64) SEA_ATTN_BITS(__nv_bfloat16, 64); else SEA_ATTN_BITS(__nv_bfloat16, 128);
@@ -883,6 +717,6 @@ extern "C" int sea_sparse_attention_bits_fwd(const uint32_t* mask_bits,
         if (D == 32) SEA_ATTN_BITS(__half, 32); else if (D == 64) SEA_ATTN_BITS(__half, 64); else SEA_ATTN_BITS(__half, 128);
     }
 #undef SEA_ATTN_BITS
-    SEA_CHECK_LAUNCH("sparse_attention_bits_kernel");
+    SEA_CHECK_LAUNCH("sparse_attention_bits_mma_kernel");
     return SEA_OK;
 }

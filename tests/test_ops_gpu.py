@@ -252,6 +252,7 @@ def test_fused_sparse_attention_v2_bf16_with_head_ptr(sea, d, idt):
     # d = 64 and no clamped pixel -> the tile-skipping block kernel (block_attn.cu): ragged row blocks, T_DST < T_SRC, non-causal
     (1, 2, 1000, 1000, 64, 32, 64, True), (1, 3, 40, 128, 64, 8, 64, True), (2, 4, 200, 200, 32, 8, 64, False),
     (1, 2, 2048, 2048, 256, 64, 64, True),
+    (1, 2, 300, 300, 96, 16, 64, True),           # P not a power of two: the float pixel-edge path of the mask expansion
 ])
 def test_attention_from_bits_equals_csr_path(sea, N, H, T_DST, T_SRC, P, k, d, causal):
     """The bit-mask driven kernel enumerates exactly the entries sea_csr_fill would emit."""
@@ -259,6 +260,8 @@ def test_attention_from_bits_equals_csr_path(sea, N, H, T_DST, T_SRC, P, k, d, c
     mask = (torch.rand(N, H, T_DST, P, generator=g) < min(1.0, 2.0 * k / P)).float()
     mask[0, 1, 3] = 0
     mask[0, 0, 5] = 1               # a head with every pixel alive
+    if T_DST >= 256:
+        mask[0, 0, 128:256] = 0     # a whole 128-row query block of one head without any alive pixel (no active tile)
     bits = sea.ops.mask_to_bits(mask.to(DEV))
     crow, col, Z, hp = sea.ops.csr_from_bits(bits, H, P, k, T_SRC, causal, torch.int32, want_head_ptr=True)
     q = (torch.randn(N, H, T_DST, d, generator=g) * d ** -0.5).bfloat16().to(DEV)
