@@ -351,6 +351,174 @@ topk_batch_kernel(const float* __restrict__ keys, const float* __restrict__ k_pe
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Multi-CTA form of the 'batch' top-k (one CTA per item above leaves 147 SMs idle for ~2 ms at BERT-base).  The same radix
+// select, spread over ceil(G / 4096) CTAs per item and a handful of small launches; per-item scratch in a caller workspace:
+//   u32 hist[4][256] | u32 state[8] = {prefix, mask, remaining, eq_total, ...} | u32 eq_cnt[chunks]
+//   tkb_hist_kernel (x4)   keys matching the prefix found so far -> 8-bit digit histogram (shared memory, then global atomics)
+//   tkb_pivot_kernel (x4)  one CTA per item: pivot digit of the pass, remaining count
+//   tkb_count_kernel       keys == threshold per chunk;  tkb_scan_kernel: exclusive scan over the chunks of an item
+//   tkb_bits_kernel        alive = key > thr, or key == thr and fewer than `remaining` equal keys precede it in flat index order;
+//                          a warp owns 32 consecutive keys = one word of the bit mask when P % 32 == 0
+// ------------------------------------------------------------------------------------------------
+constexpr int kTkbChunk = 4096, kTkbThreads = 256, kTkbPer = kTkbChunk / kTkbThreads;
+__host__ __device__ inline int64_t tkb_item_words(int64_t G) { return 4 * 256 + 8 + (G + kTkbChunk - 1) / kTkbChunk; }
+
+__global__ void __launch_bounds__(kTkbThreads)
+tkb_hist_kernel(const float* __restrict__ keys, uint32_t* __restrict__ ws, int64_t G, int pass) {
+    __shared__ int hist[256];
+    const int n = blockIdx.y, tid = threadIdx.x;
+    uint32_t* wsn = ws + (int64_t) n * tkb_item_words(G);
+    const uint32_t prefix = wsn[1024], mask = wsn[1025];
+    if (wsn[1028] != 0u) return;                        // every key is alive: nothing to select
+    hist[tid] = 0;
+    __syncthreads();
+    const int shift = 24 - 8 * pass;
+    const float* kb = keys + (int64_t) n * G;
+    const int64_t base = (int64_t) blockIdx.x * kTkbChunk;
+#pragma unroll
+    for (int u = 0; u < kTkbPer; ++u) {
+        const int64_t i = base + u * kTkbThreads + tid;
+        if (i < G) {
+            const uint32_t key = orderable(__ldg(kb + i));
+            if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255], 1);
+        }
+    }
+    __syncthreads();
+    if (hist[tid] != 0) atomicAdd(&wsn[pass * 256 + tid], (uint32_t) hist[tid]);
+}
+
+__global__ void tkb_init_kernel(const float* __restrict__ k_per_item, uint32_t* __restrict__ ws, int64_t G, int N) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    uint32_t* wsn = ws + (int64_t) n * tkb_item_words(G);
+    const int64_t K = (int64_t) fminf(ceilf(k_per_item[n]), (float) G);
+    wsn[1026] = (uint32_t) K;                           // remaining
+    wsn[1028] = K >= G ? 1u : 0u;                       // every key alive
+}
+
+__global__ void __launch_bounds__(256)
+tkb_pivot_kernel(uint32_t* __restrict__ ws, int64_t G, int pass) {
+    __shared__ int wsum[8];
+    __shared__ int piv[3];
+    const int n = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    uint32_t* wsn = ws + (int64_t) n * tkb_item_words(G);
+    if (wsn[1028] != 0u) return;
+    const int remaining = (int) wsn[1026];
+    const int mine = (int) wsn[pass * 256 + (255 - tid)];          // reversed: exclusive scan = keys with a larger digit
+    int incl = warp_scan_incl_i(mine, lane);
+    if (lane == 31) wsum[wid] = incl;
+    __syncthreads();
+    int above = incl - mine;
+    for (int w = 0; w < wid; ++w) above += wsum[w];
+    if (above < remaining && remaining <= above + mine) { piv[0] = 255 - tid; piv[1] = remaining - above; piv[2] = mine; }
+    __syncthreads();
+    if (tid == 0) {
+        const int shift = 24 - 8 * pass;
+        wsn[1024] |= (uint32_t) piv[0] << shift;
+        wsn[1025] |= 0xffu << shift;
+        wsn[1026] = (uint32_t) piv[1];
+        wsn[1027] = (uint32_t) piv[2];                  // keys equal to the threshold (after the last pass)
+    }
+}
+
+__global__ void __launch_bounds__(kTkbThreads)
+tkb_count_kernel(const float* __restrict__ keys, uint32_t* __restrict__ ws, int64_t G) {
+    __shared__ int wsum[kTkbThreads / 32];
+    const int n = blockIdx.y, tid = threadIdx.x;
+    uint32_t* wsn = ws + (int64_t) n * tkb_item_words(G);
+    if (wsn[1028] != 0u) return;
+    const uint32_t thr = wsn[1024];
+    const float* kb = keys + (int64_t) n * G;
+    const int64_t base = (int64_t) blockIdx.x * kTkbChunk;
+    int c = 0;
+#pragma unroll
+    for (int u = 0; u < kTkbPer; ++u) {
+        const int64_t i = base + u * kTkbThreads + tid;
+        if (i < G && orderable(__ldg(kb + i)) == thr) ++c;
+    }
+    c = warp_sum_i(c);
+    if ((tid & 31) == 0) wsum[tid >> 5] = c;
+    __syncthreads();
+    if (tid == 0) {
+        int tot = 0;
+        for (int w = 0; w < kTkbThreads / 32; ++w) tot += wsum[w];
+        wsn[1032 + blockIdx.x] = (uint32_t) tot;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+tkb_scan_kernel(uint32_t* __restrict__ ws, int64_t G, int chunks) {
+    __shared__ int wsum[8];
+    __shared__ int carry_s;
+    const int n = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    uint32_t* wsn = ws + (int64_t) n * tkb_item_words(G);
+    if (wsn[1028] != 0u) return;
+    if (tid == 0) carry_s = 0;
+    __syncthreads();
+    for (int c0 = 0; c0 < chunks; c0 += 256) {
+        const int c = c0 + tid;
+        const int v = c < chunks ? (int) wsn[1032 + c] : 0;
+        const int incl = warp_scan_incl_i(v, lane);
+        if (lane == 31) wsum[wid] = incl;
+        __syncthreads();
+        int before = carry_s + incl - v;
+        for (int w = 0; w < wid; ++w) before += wsum[w];
+        if (c < chunks) wsn[1032 + c] = (uint32_t) before;
+        __syncthreads();
+        if (tid == 255) carry_s = before + v;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(kTkbThreads)
+tkb_bits_kernel(const float* __restrict__ keys, const uint32_t* __restrict__ ws, uint32_t* __restrict__ mask_bits, int64_t G, int H, int T, int P) {
+    __shared__ int wsum[kTkbThreads / 32];
+    __shared__ int carry_s;
+    const int n = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint32_t* wsn = ws + (int64_t) n * tkb_item_words(G);
+    const bool all_alive = wsn[1028] != 0u;
+    const uint32_t thr = wsn[1024];
+    const int remaining = (int) wsn[1026];
+    const float* kb = keys + (int64_t) n * G;
+    const int wpr = (H * P + 31) >> 5;
+    uint32_t* bits = mask_bits + (int64_t) n * T * wpr;
+    const int64_t base = (int64_t) blockIdx.x * kTkbChunk;
+    if (tid == 0) carry_s = all_alive ? 0 : (int) wsn[1032 + blockIdx.x];
+    __syncthreads();
+    for (int u = 0; u < kTkbPer; ++u) {                 // consecutive keys per step so that the flat index order is the scan order
+        const int64_t i = base + u * kTkbThreads + tid;
+        bool gt = false, eq = false;
+        if (i < G) {
+            if (all_alive) gt = true;
+            else { const uint32_t key = orderable(__ldg(kb + i)); gt = key > thr; eq = key == thr; }
+        }
+        const uint32_t eqb = __ballot_sync(kFull, eq);
+        if (lane == 0) wsum[wid] = __popc(eqb);
+        __syncthreads();
+        int before = carry_s + __popc(eqb & ((1u << lane) - 1u));
+        int tot = 0;
+        for (int w = 0; w < kTkbThreads / 32; ++w) { const int sct = wsum[w]; if (w < wid) before += sct; tot += sct; }
+        const bool alive = i < G && (gt || (eq && before < remaining));
+        if ((P & 31) == 0) {
+            // 32 consecutive keys of one (h, t) row = one word of the mask
+            const uint32_t word = __ballot_sync(kFull, alive);
+            const int64_t i0 = i - lane;
+            if (lane == 0 && i0 < G) {
+                const int m0 = (int) (i0 % P), t = (int) ((i0 / P) % T), h = (int) (i0 / ((int64_t) P * T));
+                bits[(int64_t) t * wpr + ((h * P + m0) >> 5)] = word;
+            }
+        } else if (alive) {
+            const int m = (int) (i % P), t = (int) ((i / P) % T), h = (int) (i / ((int64_t) P * T));
+            const int b = h * P + m;
+            atomicOr(&bits[(int64_t) t * wpr + (b >> 5)], 1u << (b & 31));
+        }
+        __syncthreads();
+        if (tid == 0) carry_s += tot;
+        __syncthreads();
+    }
+}
+
 // a13': avg[n,h,:] = sum_j w_j v[n,h,j,:],  w = dense resize of mean_t probs[n,h,t,:] to T (no padding)
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -478,6 +646,36 @@ int sea_topk_mask_bits_batch(const float* keys, const float* k_per_item, uint32_
     SEA_CHECK_ARG((int64_t) H * T * P < (1ll << 31), "sea_topk_mask_bits_batch: group too large");
     topk_batch_kernel<<<N, kBatchThreads, 0, (cudaStream_t) stream>>>(keys, k_per_item, mask_bits, H, T, P);
     SEA_CHECK_LAUNCH("topk_batch_kernel");
+    return SEA_OK;
+}
+
+int64_t sea_topk_batch_workspace_bytes(int N, int H, int T, int P) {
+    if (N <= 0 || H <= 0 || T <= 0 || P <= 0) return 0;
+    return (int64_t) N * tkb_item_words((int64_t) H * T * P) * 4;
+}
+
+int sea_topk_mask_bits_batch_ws(const float* keys, const float* k_per_item, uint32_t* mask_bits, void* workspace, int64_t workspace_bytes,
+                                int N, int H, int T, int P, void* stream) {
+    SEA_CHECK_ARG(keys && k_per_item && mask_bits && workspace && N > 0 && H > 0 && T > 0 && P > 0, "sea_topk_mask_bits_batch_ws: bad argument");
+    const int64_t G = (int64_t) H * T * P;
+    SEA_CHECK_ARG(G < (1ll << 31) && N <= 65535, "sea_topk_mask_bits_batch_ws: group too large");
+    SEA_CHECK_ARG(workspace_bytes >= sea_topk_batch_workspace_bytes(N, H, T, P), "sea_topk_mask_bits_batch_ws: workspace too small");
+    cudaStream_t s = (cudaStream_t) stream;
+    uint32_t* ws = reinterpret_cast<uint32_t*>(workspace);
+    const int chunks = (int) ((G + kTkbChunk - 1) / kTkbChunk);
+    const int wpr = (H * P + 31) >> 5;
+    SEA_CUDA_TRY(cudaMemsetAsync(ws, 0, (size_t) sea_topk_batch_workspace_bytes(N, H, T, P), s), "memset workspace");
+    if ((P & 31) != 0) SEA_CUDA_TRY(cudaMemsetAsync(mask_bits, 0, (size_t) N * T * wpr * 4, s), "memset bits");
+    const dim3 grid((unsigned) chunks, (unsigned) N);
+    tkb_init_kernel<<<(N + 127) / 128, 128, 0, s>>>(k_per_item, ws, G, N);
+    for (int pass = 0; pass < 4; ++pass) {
+        tkb_hist_kernel<<<grid, kTkbThreads, 0, s>>>(keys, ws, G, pass);
+        tkb_pivot_kernel<<<N, 256, 0, s>>>(ws, G, pass);
+    }
+    tkb_count_kernel<<<grid, kTkbThreads, 0, s>>>(keys, ws, G);
+    tkb_scan_kernel<<<N, 256, 0, s>>>(ws, G, chunks);
+    tkb_bits_kernel<<<grid, kTkbThreads, 0, s>>>(keys, ws, mask_bits, G, H, T, P);
+    SEA_CHECK_LAUNCH("tkb kernels");
     return SEA_OK;
 }
 

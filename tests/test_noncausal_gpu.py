@@ -62,7 +62,8 @@ def test_bert_tail_matches_torch(sea):
     torch.testing.assert_close(probs.cpu(), torch.softmax(ref, -1), rtol=1e-4, atol=1e-7)
 
 
-@pytest.mark.parametrize('N,H,T,P,k,ties', [(2, 3, 40, 16, 4, False), (1, 4, 64, 32, 8, True), (1, 12, 30, 128, 64, True)])
+@pytest.mark.parametrize('N,H,T,P,k,ties', [(2, 3, 40, 16, 4, False), (1, 4, 64, 32, 8, True), (1, 12, 30, 128, 64, True),
+                                           (2, 12, 130, 128, 64, True), (1, 12, 512, 128, 64, False), (1, 2, 9, 32, 64, False)])
 def test_topk_batch_bit_exact(sea, N, H, T, P, k, ties):
     g = torch.Generator().manual_seed(P + T)
     probs = torch.softmax(torch.randn(N, H, T, P, generator=g), -1)
@@ -71,8 +72,10 @@ def test_topk_batch_bit_exact(sea, N, H, T, P, k, ties):
     tl_ = torch.full((N,), T, dtype=torch.long)
     ref = so.topk_mask_noncausal(probs, k, 1.0, tl_, 'batch')
     kpi = torch.clamp_min(torch.round(tl_ * H * (k * 1.0 * P / tl_)), 1)
-    bits = sea.ops.topk_mask_bits_batch(probs.to(DEV), kpi.to(DEV))
+    bits = sea.ops.topk_mask_bits_batch(probs.to(DEV), kpi.to(DEV))                      # multi-CTA selection
     assert torch.equal(sea.ops.bits_to_mask(bits, H, P).cpu(), ref)
+    bits1 = sea.ops.topk_mask_bits_batch(probs.to(DEV), kpi.to(DEV), single_cta=True)     # one CTA per item
+    assert torch.equal(bits1.cpu(), bits.cpu())
 
 
 def test_bert_avg_matches_oracle(sea):
