@@ -226,6 +226,62 @@ conv3x3_cl_kernel(const T* __restrict__ x, const float* __restrict__ weight, con
         }
 }
 
+// The same convolution with the weights staged once per CTA in shared memory as [tap][c][o] (zero-padded to a multiple of kOT
+// output channels): a thread owns one output pixel and kOT output channels, so each input value it loads feeds kOT FMAs whose
+// weights arrive as broadcast 16-byte shared-memory loads -- the kernel above issues one global weight load per FMA.
+template <typename T, int kOT>
+__global__ void __launch_bounds__(256)
+conv3x3_cl_smem_kernel(const T* __restrict__ x, const float* __restrict__ weight, const float* __restrict__ bias, T* __restrict__ y,
+                       int N, int Tin, int Tout, int W, int C, int O, int stride_t, int up, int relu) {
+    extern __shared__ __align__(16) float cw_sm[];            // [9][C][Opad]
+    const int OG = (O + kOT - 1) / kOT, Opad = OG * kOT;
+    for (int i = threadIdx.x; i < 9 * C * Opad; i += 256) {
+        const int o = i % Opad, c = (i / Opad) % C, tap = i / (Opad * C);
+        cw_sm[i] = o < O ? __ldg(weight + ((int64_t) o * C + c) * 9 + tap) : 0.f;
+    }
+    __syncthreads();
+    const int ppc = 256 / OG;                                 // pixels per CTA
+    const int og = threadIdx.x % OG, pl = threadIdx.x / OG;
+    const int64_t pix = (int64_t) blockIdx.x * ppc + pl;
+    if (pl >= ppc || pix >= (int64_t) N * Tout * W) return;
+    const int w = (int) (pix % W);
+    const int t = (int) ((pix / W) % Tout);
+    const int n = (int) (pix / ((int64_t) W * Tout));
+    const int Tvirt = Tin * up;
+    float acc[kOT];
+#pragma unroll
+    for (int u = 0; u < kOT; ++u) acc[u] = 0.f;
+    for (int i = 0; i < 3; ++i) {
+        const int tv = t * stride_t - 1 + i;
+        if (tv < 0 || tv >= Tvirt) continue;
+        const int ti = tv / up;
+        for (int j = 0; j < 3; ++j) {
+            const int wc = w - 1 + j;
+            if (wc < 0 || wc >= W) continue;
+            const T* xp = x + (((int64_t) n * Tin + ti) * W + wc) * C;
+            const float* wp = cw_sm + (size_t) ((i * 3 + j) * C) * Opad + og * kOT;
+            for (int c = 0; c < C; ++c) {
+                const float xv = to_f32(xp[c]);
+#pragma unroll
+                for (int u4 = 0; u4 < kOT / 4; ++u4) {
+                    const float4 w4 = *reinterpret_cast<const float4*>(wp + (size_t) c * Opad + 4 * u4);
+                    acc[4 * u4] = fmaf(xv, w4.x, acc[4 * u4]); acc[4 * u4 + 1] = fmaf(xv, w4.y, acc[4 * u4 + 1]);
+                    acc[4 * u4 + 2] = fmaf(xv, w4.z, acc[4 * u4 + 2]); acc[4 * u4 + 3] = fmaf(xv, w4.w, acc[4 * u4 + 3]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < kOT; ++u) {
+        const int o = og * kOT + u;
+        if (o < O) {
+            float r = acc[u] + bias[o];
+            if (relu) r = fmaxf(r, 0.f);
+            y[pix * O + o] = from_f32<T>(r);
+        }
+    }
+}
+
 // bilinear resize (align_corners=False) of [N, Tin, Win, H] (channels-last) to (T, P), then softmax over P.
 // warp per (n, h, t).
 template <typename T>
@@ -621,6 +677,27 @@ int sea_conv3x3_cl(const void* x, const float* weight, const float* bias, void* 
                    int N, int Tin, int Tout, int W, int C, int O, int stride_t, int up, int relu, void* stream) {
     SEA_CHECK_ARG(x && weight && bias && y, "sea_conv3x3_cl: null pointer");
     SEA_CHECK_ARG(N > 0 && Tin > 0 && Tout > 0 && W > 0 && C > 0 && O > 0 && stride_t >= 1 && up >= 1, "sea_conv3x3_cl: bad shape");
+    // weights in shared memory when they fit (BERT-base: 9 x 48 x 48 fp32 = 83 KB); kOT = 12 output channels per thread when O allows
+    const int ot = (O % 12 == 0) ? 12 : 4;
+    const int OG = (O + ot - 1) / ot;
+    const size_t wsm = (size_t) 9 * C * OG * ot * sizeof(float);
+    if (wsm <= 160 * 1024 && OG <= 256) {
+        const int ppc = 256 / OG;
+        const int64_t pixels = (int64_t) N * Tout * W;
+        SEA_DISPATCH_DTYPE(dtype, T_, {
+            if (ot == 12) {
+                auto kern = conv3x3_cl_smem_kernel<T_, 12>;
+                SEA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) wsm), "smem attr");
+                kern<<<cdiv(pixels, ppc), 256, wsm, (cudaStream_t) stream>>>((const T_*) x, weight, bias, (T_*) y, N, Tin, Tout, W, C, O, stride_t, up, relu);
+            } else {
+                auto kern = conv3x3_cl_smem_kernel<T_, 4>;
+                SEA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) wsm), "smem attr");
+                kern<<<cdiv(pixels, ppc), 256, wsm, (cudaStream_t) stream>>>((const T_*) x, weight, bias, (T_*) y, N, Tin, Tout, W, C, O, stride_t, up, relu);
+            }
+            SEA_CHECK_LAUNCH("conv3x3_cl_smem_kernel");
+        });
+        return SEA_OK;
+    }
     const int64_t total = (int64_t) N * Tout * W * ((O + 3) / 4);
     SEA_DISPATCH_DTYPE(dtype, T_, {
         conv3x3_cl_kernel<T_><<<cdiv(total, 256), 256, 0, (cudaStream_t) stream>>>((const T_*) x, weight, bias, (T_*) y, N, Tin, Tout, W, C, O,
