@@ -42,13 +42,42 @@ def _peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock / throttle reasons sampled DURING the timed region: NVML polled every ~2 ms (the timed loops last tens of
+    milliseconds), nvidia-smi as the fallback when pynvml is unavailable."""
     Q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+    NAMES = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
 
     def __init__(self, index):
-        self.index, self.samples, self.stop_flag, self.thread = index, [], False, None
+        self.index, self.samples, self.stop_flag, self.thread, self.how = index, [], False, None, 'nvidia-smi'
+
+    def _run_nvml(self):
+        import pynvml
+        pynvml.nvmlInit()
+        # CUDA_VISIBLE_DEVICES may renumber devices: resolve through the PCI bus id of the torch device
+        try:
+            bus = torch.cuda.get_device_properties(self.index).pci_bus_id
+            dom = torch.cuda.get_device_properties(self.index).pci_domain_id
+            dev = torch.cuda.get_device_properties(self.index).pci_device_id
+            h = pynvml.nvmlDeviceGetHandleByPciBusId(f'{dom:08x}:{bus:02x}:{dev:02x}.0')
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+        mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+        bits = [(getattr(pynvml, 'nvmlClocksThrottleReasonHwSlowdown', 0x8), 0), (getattr(pynvml, 'nvmlClocksThrottleReasonHwThermalSlowdown', 0x40), 1),
+                (getattr(pynvml, 'nvmlClocksThrottleReasonSwThermalSlowdown', 0x20), 2), (getattr(pynvml, 'nvmlClocksThrottleReasonSwPowerCap', 0x4), 3)]
+        self.how = 'nvml'
+        while not self.stop_flag:
+            sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+            r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+            row = [str(sm), str(mx)] + ['Active' if r & b else 'Not Active' for b, _ in bits]
+            self.samples.append(row)
+            time.sleep(0.002)
 
     def _run(self):
+        try:
+            self._run_nvml()
+            return
+        except Exception:
+            self.how = 'nvidia-smi'
         while not self.stop_flag:
             try:
                 out = subprocess.run(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}', '--format=csv,noheader,nounits'],
@@ -69,10 +98,9 @@ class ClockSampler:
             self.thread.join(timeout=6)
         sm = [int(s[0]) for s in self.samples if s[0].isdigit()]
         mx = [int(s[1]) for s in self.samples if s[1].isdigit()]
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        reasons = sorted({names[i] for s in self.samples for i in range(4) if len(s) > 2 + i and s[2 + i].lower().startswith('active')})
+        reasons = sorted({self.NAMES[i] for s in self.samples for i in range(4) if len(s) > 2 + i and s[2 + i].lower().startswith('active')})
         return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': max(mx) if mx else None, 'reasons': reasons,
-                'samples': len(self.samples)}
+                'samples': len(self.samples), 'source': self.how}
 
 
 def stage_bytes(N, H, d, T, P, k, F, b, Z):
