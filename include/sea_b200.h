@@ -342,10 +342,12 @@ SEA_API int sea_conv3x3_cl(const void* x, const float* weight, const float* bias
                            int N, int Tin, int Tout, int W, int C, int O, int stride_t, int up, int relu, void* stream);
 SEA_API int sea_bert_tail_fwd(const void* y, int dtype, float* probs, float* scores, int N, int H, int Tin, int Win, int T, int P, void* stream);
 SEA_API int sea_topk_mask_bits_batch(const float* keys, const float* k_per_item, uint32_t* mask_bits, int N, int H, int T, int P, void* stream);
-/* the same selection spread over ceil(H*T*P / 4096) CTAs per item (a dozen small launches); scratch in `workspace` */
-SEA_API int64_t sea_topk_batch_workspace_bytes(int N, int H, int T, int P);
-SEA_API int sea_topk_mask_bits_batch_ws(const float* keys, const float* k_per_item, uint32_t* mask_bits, void* workspace, int64_t workspace_bytes,
-                                        int N, int H, int T, int P, void* stream);
+/* the same selection spread over ceil(keys / 4096) CTAs per group (a dozen small launches); scratch in `workspace`.
+ * group_heads = H: k_flatten_dim='batch' (one group per item); group_heads = 1: k_flatten_dim='head' (attention.py:838-842, one group per
+ * (item, head) over its T*P keys); k_per_group has N * H / group_heads entries. */
+SEA_API int64_t sea_topk_batch_workspace_bytes(int N, int H, int T, int P, int group_heads);
+SEA_API int sea_topk_mask_bits_batch_ws(const float* keys, const float* k_per_group, uint32_t* mask_bits, void* workspace, int64_t workspace_bytes,
+                                        int N, int H, int T, int P, int group_heads, void* stream);
 SEA_API int sea_bert_avg_fwd(const float* probs, const void* v, int64_t v_sn, int64_t v_sh, int64_t v_st, int dtype, void* avg,
                              int N, int H, int T, int P, int D, void* stream);
 

@@ -80,8 +80,8 @@ _SIGNATURES = {
     'sea_conv3x3_cl': (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     'sea_bert_tail_fwd': (_I, [_P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     'sea_topk_mask_bits_batch': (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
-    'sea_topk_batch_workspace_bytes': (_L, [_I, _I, _I, _I]),
-    'sea_topk_mask_bits_batch_ws': (_I, [_P, _P, _P, _P, _L, _I, _I, _I, _I, _P]),
+    'sea_topk_batch_workspace_bytes': (_L, [_I, _I, _I, _I, _I]),
+    'sea_topk_mask_bits_batch_ws': (_I, [_P, _P, _P, _P, _L, _I, _I, _I, _I, _I, _P]),
     'sea_bert_avg_fwd': (_I, [_P, _P, _L, _L, _L, _I, _P, _I, _I, _I, _I, _I, _P]),
     'sea_sparse_attention_fwd': (_I, [_P, _P, _I, _L, _P, _L, _L, _L, _P, _L, _L, _L, _P, _L, _L, _L, _P, _P, _L, _L, _I, _I, _P, _P, _P,
                                       _I, _I, _I, _I, _I, _P]),

@@ -501,6 +501,9 @@ class PerlinAttention(nn.Module):
         if mode == 'batch':
             kpi = torch.clamp_min(torch.round(tl_ * H * (kf / tl_)), 1)                                         # attention.py:837,856,866
             bits = ops.topk_mask_bits_batch(probs, kpi)
+        elif mode == 'head':
+            kpi = torch.clamp_min(torch.round(tl_ * (kf / tl_)), 1).view(N, 1).expand(N, H).reshape(-1)          # :838-842
+            bits = ops.topk_mask_bits_batch(probs, kpi, group_heads=1)
         elif mode == 'query':
             kpi = torch.clamp_min(torch.round(kf / tl_), 1)                                                      # :853
             bits = ops.topk_mask_bits(probs, kpi, 'query')

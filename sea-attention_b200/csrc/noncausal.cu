@@ -528,7 +528,8 @@ tkb_scan_kernel(uint32_t* __restrict__ ws, int64_t G, int chunks) {
 }
 
 __global__ void __launch_bounds__(kTkbThreads)
-tkb_bits_kernel(const float* __restrict__ keys, const uint32_t* __restrict__ ws, uint32_t* __restrict__ mask_bits, int64_t G, int H, int T, int P) {
+tkb_bits_kernel(const float* __restrict__ keys, const uint32_t* __restrict__ ws, uint32_t* __restrict__ mask_bits, int64_t G, int H, int T, int P,
+                int group_heads) {
     __shared__ int wsum[kTkbThreads / 32];
     __shared__ int carry_s;
     const int n = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -536,9 +537,11 @@ tkb_bits_kernel(const float* __restrict__ keys, const uint32_t* __restrict__ ws,
     const bool all_alive = wsn[1028] != 0u;
     const uint32_t thr = wsn[1024];
     const int remaining = (int) wsn[1026];
-    const float* kb = keys + (int64_t) n * G;
+    const float* kb = keys + (int64_t) n * G;                  // group n = (item, head group): its group_heads * T * P keys are contiguous
     const int wpr = (H * P + 31) >> 5;
-    uint32_t* bits = mask_bits + (int64_t) n * T * wpr;
+    const int gpi = H / group_heads;                           // groups per item
+    const int hb = (n % gpi) * group_heads;                    // first head of the group
+    uint32_t* bits = mask_bits + (int64_t) (n / gpi) * T * wpr;
     const int64_t base = (int64_t) blockIdx.x * kTkbChunk;
     if (tid == 0) carry_s = all_alive ? 0 : (int) wsn[1032 + blockIdx.x];
     __syncthreads();
@@ -561,11 +564,11 @@ tkb_bits_kernel(const float* __restrict__ keys, const uint32_t* __restrict__ ws,
             const uint32_t word = __ballot_sync(kFull, alive);
             const int64_t i0 = i - lane;
             if (lane == 0 && i0 < G) {
-                const int m0 = (int) (i0 % P), t = (int) ((i0 / P) % T), h = (int) (i0 / ((int64_t) P * T));
+                const int m0 = (int) (i0 % P), t = (int) ((i0 / P) % T), h = hb + (int) (i0 / ((int64_t) P * T));
                 bits[(int64_t) t * wpr + ((h * P + m0) >> 5)] = word;
             }
         } else if (alive) {
-            const int m = (int) (i % P), t = (int) ((i / P) % T), h = (int) (i / ((int64_t) P * T));
+            const int m = (int) (i % P), t = (int) ((i / P) % T), h = hb + (int) (i / ((int64_t) P * T));
             const int b = h * P + m;
             atomicOr(&bits[(int64_t) t * wpr + (b >> 5)], 1u << (b & 31));
         }
@@ -726,32 +729,34 @@ int sea_topk_mask_bits_batch(const float* keys, const float* k_per_item, uint32_
     return SEA_OK;
 }
 
-int64_t sea_topk_batch_workspace_bytes(int N, int H, int T, int P) {
-    if (N <= 0 || H <= 0 || T <= 0 || P <= 0) return 0;
-    return (int64_t) N * tkb_item_words((int64_t) H * T * P) * 4;
+int64_t sea_topk_batch_workspace_bytes(int N, int H, int T, int P, int group_heads) {
+    if (N <= 0 || H <= 0 || T <= 0 || P <= 0 || group_heads <= 0 || H % group_heads != 0) return 0;
+    return (int64_t) N * (H / group_heads) * tkb_item_words((int64_t) group_heads * T * P) * 4;
 }
 
-int sea_topk_mask_bits_batch_ws(const float* keys, const float* k_per_item, uint32_t* mask_bits, void* workspace, int64_t workspace_bytes,
-                                int N, int H, int T, int P, void* stream) {
-    SEA_CHECK_ARG(keys && k_per_item && mask_bits && workspace && N > 0 && H > 0 && T > 0 && P > 0, "sea_topk_mask_bits_batch_ws: bad argument");
-    const int64_t G = (int64_t) H * T * P;
-    SEA_CHECK_ARG(G < (1ll << 31) && N <= 65535, "sea_topk_mask_bits_batch_ws: group too large");
-    SEA_CHECK_ARG(workspace_bytes >= sea_topk_batch_workspace_bytes(N, H, T, P), "sea_topk_mask_bits_batch_ws: workspace too small");
+int sea_topk_mask_bits_batch_ws(const float* keys, const float* k_per_group, uint32_t* mask_bits, void* workspace, int64_t workspace_bytes,
+                                int N, int H, int T, int P, int group_heads, void* stream) {
+    SEA_CHECK_ARG(keys && k_per_group && mask_bits && workspace && N > 0 && H > 0 && T > 0 && P > 0, "sea_topk_mask_bits_batch_ws: bad argument");
+    SEA_CHECK_ARG(group_heads > 0 && H % group_heads == 0, "sea_topk_mask_bits_batch_ws: group_heads must divide H");
+    const int64_t G = (int64_t) group_heads * T * P;           // keys per group
+    const int groups = N * (H / group_heads);
+    SEA_CHECK_ARG(G < (1ll << 31) && groups <= 65535, "sea_topk_mask_bits_batch_ws: group too large");
+    SEA_CHECK_ARG(workspace_bytes >= sea_topk_batch_workspace_bytes(N, H, T, P, group_heads), "sea_topk_mask_bits_batch_ws: workspace too small");
     cudaStream_t s = (cudaStream_t) stream;
     uint32_t* ws = reinterpret_cast<uint32_t*>(workspace);
     const int chunks = (int) ((G + kTkbChunk - 1) / kTkbChunk);
     const int wpr = (H * P + 31) >> 5;
-    SEA_CUDA_TRY(cudaMemsetAsync(ws, 0, (size_t) sea_topk_batch_workspace_bytes(N, H, T, P), s), "memset workspace");
+    SEA_CUDA_TRY(cudaMemsetAsync(ws, 0, (size_t) sea_topk_batch_workspace_bytes(N, H, T, P, group_heads), s), "memset workspace");
     if ((P & 31) != 0) SEA_CUDA_TRY(cudaMemsetAsync(mask_bits, 0, (size_t) N * T * wpr * 4, s), "memset bits");
-    const dim3 grid((unsigned) chunks, (unsigned) N);
-    tkb_init_kernel<<<(N + 127) / 128, 128, 0, s>>>(k_per_item, ws, G, N);
+    const dim3 grid((unsigned) chunks, (unsigned) groups);
+    tkb_init_kernel<<<(groups + 127) / 128, 128, 0, s>>>(k_per_group, ws, G, groups);
     for (int pass = 0; pass < 4; ++pass) {
         tkb_hist_kernel<<<grid, kTkbThreads, 0, s>>>(keys, ws, G, pass);
-        tkb_pivot_kernel<<<N, 256, 0, s>>>(ws, G, pass);
+        tkb_pivot_kernel<<<groups, 256, 0, s>>>(ws, G, pass);
     }
     tkb_count_kernel<<<grid, kTkbThreads, 0, s>>>(keys, ws, G);
-    tkb_scan_kernel<<<N, 256, 0, s>>>(ws, G, chunks);
-    tkb_bits_kernel<<<grid, kTkbThreads, 0, s>>>(keys, ws, mask_bits, G, H, T, P);
+    tkb_scan_kernel<<<groups, 256, 0, s>>>(ws, G, chunks);
+    tkb_bits_kernel<<<grid, kTkbThreads, 0, s>>>(keys, ws, mask_bits, G, H, T, P, group_heads);
     SEA_CHECK_LAUNCH("tkb kernels");
     return SEA_OK;
 }

@@ -610,19 +610,23 @@ def bert_tail(y, T: int, P: int, want_scores=False):
     return probs, scores
 
 
-def topk_mask_bits_batch(probs, k_per_item, single_cta: bool = False):
-    """k_flatten_dim='batch' top-k: one group per item over the H*T*P keys (flat order of view(N, H*T*P))."""
+def topk_mask_bits_batch(probs, k_per_item, single_cta: bool = False, group_heads: int = None):
+    """k_flatten_dim='batch' top-k: one group per item over the H*T*P keys (flat order of view(N, H*T*P)).
+    group_heads=1: k_flatten_dim='head' (one group per (item, head), k_per_item has N*H entries)."""
     _cuda(probs, k_per_item)
     N, H, T, P = probs.shape
     pr = probs.float().contiguous()
     kp = k_per_item.reshape(-1).float().contiguous()
     bits = torch.empty((N, T, (H * P + 31) // 32), dtype=torch.int32, device=probs.device)
+    gh = H if group_heads is None else int(group_heads)
     if single_cta:
+        if gh != H:
+            raise SeaError('the single-CTA top-k only implements the per-item group')
         _lib.call('sea_topk_mask_bits_batch', pr.data_ptr(), kp.data_ptr(), bits.data_ptr(), N, H, T, P, _stream())
         return bits
-    nbytes = int(_lib.load().sea_topk_batch_workspace_bytes(N, H, T, P))
+    nbytes = int(_lib.load().sea_topk_batch_workspace_bytes(N, H, T, P, gh))
     ws = torch.empty((nbytes,), dtype=torch.uint8, device=probs.device)
-    _lib.call('sea_topk_mask_bits_batch_ws', pr.data_ptr(), kp.data_ptr(), bits.data_ptr(), ws.data_ptr(), nbytes, N, H, T, P, _stream())
+    _lib.call('sea_topk_mask_bits_batch_ws', pr.data_ptr(), kp.data_ptr(), bits.data_ptr(), ws.data_ptr(), nbytes, N, H, T, P, gh, _stream())
     return bits
 
 

@@ -78,6 +78,20 @@ def test_topk_batch_bit_exact(sea, N, H, T, P, k, ties):
     assert torch.equal(bits1.cpu(), bits.cpu())
 
 
+@pytest.mark.parametrize('N,H,T,P,k,ties', [(2, 3, 40, 16, 4, False), (1, 12, 130, 128, 64, True), (2, 4, 64, 32, 8, True)])
+def test_topk_head_mode_bit_exact(sea, N, H, T, P, k, ties):
+    """k_flatten_dim='head' (attention.py:838-842): one top-k group per (item, head) over its T*P keys."""
+    g = torch.Generator().manual_seed(P + T + 1)
+    probs = torch.softmax(torch.randn(N, H, T, P, generator=g), -1)
+    if ties:
+        probs = probs[..., : P // 4].repeat_interleave(4, dim=-1).contiguous()
+    tl_ = torch.full((N,), T, dtype=torch.long)
+    ref = so.topk_mask_noncausal(probs, k, 1.0, tl_, 'head')
+    kpi = torch.clamp_min(torch.round(tl_ * (k * 1.0 * P / tl_)), 1).view(N, 1).expand(N, H).reshape(-1)
+    bits = sea.ops.topk_mask_bits_batch(probs.to(DEV), kpi.to(DEV), group_heads=1)
+    assert torch.equal(sea.ops.bits_to_mask(bits, H, P).cpu(), ref)
+
+
 def test_bert_avg_matches_oracle(sea):
     N, H, T, P, d = 2, 3, 50, 16, 32
     g = torch.Generator().manual_seed(4)
