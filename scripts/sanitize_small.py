@@ -1,0 +1,39 @@
+"""Small end-to-end exercise of the new kernels for compute-sanitizer (memcheck): bf16 prefill (tcgen05 path, block attention in
+both variants), backward, decode steps, BERT layer."""
+import importlib, sys, os, torch, transformers
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sea = importlib.import_module('sea-attention_b200')
+DEV = 'cuda:0'
+torch.manual_seed(0)
+N, H, d, T, P, k, nbf = 1, 32, 64, 200, 64, 16, 8
+cfg = transformers.BertConfig(hidden_size=H * d, num_attention_heads=H, max_position_embeddings=T + 8)
+mod = sea.PerlinAttention(cfg, sea.PerlinAttentionConfig(performer_nb_factor=nbf, k=k, attention_predictor_length=P, causal=True)).eval().to(DEV)
+mk = lambda t, s=1.0: (torch.randn(N, H, t, d, device=DEV) * s).bfloat16()
+q, kk, v = mk(T + 4, d ** -0.5), mk(T + 4), mk(T + 4)
+sl = lambda x, a, b: x[:, :, a:b]
+am = torch.zeros(N, 1, T, T, device=DEV, dtype=torch.bfloat16)
+o = mod(sl(q, 0, T), sl(kk, 0, T), sl(v, 0, T), sl(q, 0, T), sl(kk, 0, T), sl(v, 0, T), sl(q, 0, T), sl(kk, 0, T), am, None, None)
+os.environ['SEA_ATTN_MMA_SYNC'] = '1'
+qh = sl(q, 0, T).half(); kh = sl(kk, 0, T).half(); vh = sl(v, 0, T).half()
+o2 = mod(qh, kh, vh, qh, kh, vh, qh, kh, am.half(), None, None)          # fp16 -> mma.sync block kernel
+qg = sl(q, 0, T).clone().requires_grad_(True); kg = sl(kk, 0, T).clone().requires_grad_(True); vg = sl(v, 0, T).clone().requires_grad_(True)
+o3 = mod(qg, kg, vg, qg, kg, vg, qg, kg, am, None, None)
+o3.context_layer.float().sum().backward()
+mod.pconfig.use_cache = True
+o4 = mod(sl(q, 0, T), sl(kk, 0, T), sl(v, 0, T), sl(q, 0, T), sl(kk, 0, T), sl(v, 0, T), sl(q, 0, T), sl(kk, 0, T), am, None, None)
+st = o4.state
+for t in range(T, T + 3):
+    o5 = mod(sl(q, t, t + 1), sl(kk, 0, t + 1), sl(v, 0, t + 1), sl(q, t, t + 1), sl(kk, 0, t + 1), sl(v, 0, t + 1), sl(q, t, t + 1), sl(kk, 0, t + 1),
+             torch.zeros(N, 1, 1, 1, device=DEV, dtype=torch.bfloat16), None, None, last_state=st)
+    st = o5.state
+# OPT-125m-like head count (padded channels, partial head slots)
+H2 = 12
+cfg2 = transformers.BertConfig(hidden_size=H2 * d, num_attention_heads=H2, max_position_embeddings=T)
+mod2 = sea.PerlinAttention(cfg2, sea.PerlinAttentionConfig(performer_nb_factor=nbf, k=k, attention_predictor_length=P, causal=True)).eval().to(DEV)
+q2 = (torch.randn(N, H2, T, d, device=DEV) * d ** -0.5).bfloat16(); k2 = torch.randn(N, H2, T, d, device=DEV).bfloat16(); v2 = torch.randn(N, H2, T, d, device=DEV).bfloat16()
+o6 = mod2(q2, k2, v2, q2, k2, v2, q2, k2, am, None, None)
+# BERT layer
+mod3 = sea.PerlinAttention(cfg2, sea.PerlinAttentionConfig(performer_nb_factor=1, k=k, attention_predictor_length=P, causal=False, k_flatten_dim='batch')).eval().to(DEV)
+o7 = mod3(q2, k2, v2, q2, k2, v2, q2, k2, torch.zeros(N, 1, 1, T, device=DEV, dtype=torch.bfloat16), None, None)
+torch.cuda.synchronize()
+print('ok', [float(x.context_layer.float().abs().mean()) for x in (o, o2, o3, o5, o6, o7)])

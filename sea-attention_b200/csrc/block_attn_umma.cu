@@ -139,7 +139,7 @@ block_attention_umma_kernel(const uint32_t* __restrict__ tile_act, int act_words
 
     if (warp == 0) {
         // ---------------------------------------------------------------- TMA producer
-        if (lane == 0) {
+        if (lane == 0 && nact > 0) {        // (no active tile: nothing may be left in flight when the CTA exits)
             umma::mbar_arrive_expect_tx(q_full, kUQ);
             umma::tma_load_4d(sm + USmem::kQ, &tmap_q, q_full, 0, r0, h, n);
             for (int j = 0; j < nact; ++j) {
