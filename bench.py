@@ -129,6 +129,24 @@ def stage_flops(N, H, d, T, P, k, F, Z):
     }
 
 
+_STDOUT_FD = None
+
+
+def _claim_stdout():
+    """Library chatter (NCCL's version banner is a bare printf) must not share stdout with the ONE JSON line: everything written
+    to fd 1 from here on goes to stderr, the JSON line is written to the saved descriptor."""
+    global _STDOUT_FD
+    if _STDOUT_FD is None:
+        sys.stdout.flush()
+        _STDOUT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(line):
+    sys.stdout.flush()
+    os.write(_STDOUT_FD if _STDOUT_FD is not None else 1, (json.dumps(line) + '\n').encode())
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path.  /root/reference is python and absent
     on the GPU box, so this times its restatement (oracle/sea_oracle.py, dense torch path = what the reference
@@ -167,7 +185,7 @@ def run_reference(args):
         'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port', 'sample': sample},
         'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 def main():
@@ -180,6 +198,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='launch the kernels eagerly instead of replaying one CUDA graph per step')
     args = ap.parse_args()
+    _claim_stdout()
     if args.impl == 'reference':
         return run_reference(args)
 
@@ -191,7 +210,6 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
-        os.environ['NCCL_DEBUG'] = 'WARN'          # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     dev = torch.device('cuda', local_rank)
     torch.cuda.set_device(dev)
@@ -433,7 +451,7 @@ def main():
                 cdt = (time.perf_counter() - t0) / reps
             line['cpu_baseline'] = {'value': Ts / cdt, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',
                                     'sample': f'first {Ts} of {T} tokens (causal prefix) of the same layer, fp32 dense torch path, {reps} steps'}
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
