@@ -283,3 +283,22 @@ def test_attention_from_bits_equals_csr_path(sea, N, H, T_DST, T_SRC, P, k, d, c
         torch.testing.assert_close(out_h.float().cpu(), ref.float().cpu(), rtol=2e-2, atol=2e-2)
     else:
         assert d != 64 or (T_SRC + P - 1) // P + 1 > k
+
+
+def test_attention_from_bits_strided_inputs(sea):
+    """q / k / v as transposed views of [N,T,H,d] buffers (what a caller gets from .view(...).transpose(1, 2)): the TMA tensor
+    maps and the gather kernels take the strides as they are."""
+    N, H, T, P, k, d = 2, 4, 300, 32, 16, 64
+    g = torch.Generator().manual_seed(5)
+    mask = (torch.rand(N, H, T, P, generator=g) < 0.4).float()
+    bits = sea.ops.mask_to_bits(mask.to(DEV))
+    mk = lambda s: (torch.randn(N, T, H, d, generator=g) * s).bfloat16().to(DEV)
+    qt, kt, vt = mk(d ** -0.5), mk(1.0), mk(1.0)
+    q, kk, v = qt.transpose(1, 2), kt.transpose(1, 2), vt.transpose(1, 2)
+    assert not q.is_contiguous()
+    scales = torch.randn(N, H, T, 2, generator=g).to(DEV)
+    avg = torch.randn(N, H, T, d, generator=g).bfloat16().to(DEV)
+    for kern in ('block', 'gather'):
+        ref = sea.ops.sparse_attention_from_bits(bits, q.contiguous(), kk.contiguous(), v.contiguous(), scales, avg, P, k, True, True, kernel=kern)
+        out = sea.ops.sparse_attention_from_bits(bits, q, kk, v, scales, avg, P, k, True, True, kernel=kern)
+        assert torch.equal(out, ref), kern
