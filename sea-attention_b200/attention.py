@@ -432,9 +432,12 @@ class PerlinAttention(nn.Module):
 
         if v_for_atten.data_ptr() != v.data_ptr():
             raise SeaError('v_for_atten must alias v (LoRA-in-approximation is not implemented)')
-        st = last_state.clone()
-        if st.t + T_new != T_SRC:
-            raise SeaError(f'state has consumed {st.t} tokens, got {T_new} new queries but {T_SRC} keys')
+        if last_state.t + T_new != T_SRC:
+            raise SeaError(f'state has consumed {last_state.t} tokens, got {T_new} new queries but {T_SRC} keys')
+        # functional update like the reference: the caller's state object is left untouched.  Only the Performer sums are advanced in
+        # place by the kernel, so only they are copied; the CNN windows are rebuilt (torch.cat) every step anyway.
+        st = PerlinAttentionState(t=last_state.t, performer=last_state.performer.clone(), cnn_in_win=last_state.cnn_in_win,
+                                  conv1_win=last_state.conv1_win)
         pk = self._packed
         net = self.attention_predictor_cnn[1].module.net
         enc, dec, scl = self.attention_predictor_enc, self.attention_predictor_dec_row, self.attention_predictor_dec_scaler
@@ -442,6 +445,13 @@ class PerlinAttention(nn.Module):
         C_win = st.cnn_in_win.shape[-1]
         pad_c = C_win != S * H                       # the state was built on the zero-padded 64-channel path
         wp = self._padded_conv_weights(w, S * H, H) if pad_c else w
+        # per_item_top_k of every position up to max_position_embeddings, computed once (it depends on shapes only)
+        max_pos = self.v_eye_learned_causal.shape[2]
+        key = ('decode_kpr', H, P, pc.k, pc.k_oversample, max_pos, str(q.device))
+        kpr_all = self._shape_cache.get(key)
+        if kpr_all is None:
+            kpr_all = _k_per_row_causal(H, pc.k, pc.k_oversample, P, max_pos, max_pos, q.device)
+            self._shape_cache[key] = kpr_all
         contexts, prob_rows = [], []
         for i in range(T_new):
             t = st.t
@@ -452,10 +462,10 @@ class PerlinAttention(nn.Module):
             y1 = ops.causal_conv3x3_dil2_relu(x_win, wp['conv1_w'], wp['conv1_b'], packed=pk, slot='conv1', src=net[0].module.weight)[:, 4:5]
             y1_win = torch.cat([st.conv1_win, y1], dim=1)
             y2 = ops.causal_conv3x3_dil2_relu(y1_win, wp['conv2_w'], wp['conv2_b'], packed=pk, slot='conv2', src=net[2].module.weight)[:, 4:5]
-            st.cnn_in_win, st.conv1_win = x_win[:, 1:].contiguous(), y1_win[:, 1:].contiguous()
-            y2 = y2[..., :S * H].contiguous()
+            st.cnn_in_win, st.conv1_win = x_win[:, 1:], y1_win[:, 1:]            # views of fresh tensors: the next cat copies them
+            y2 = (y2[..., :S * H] if pad_c else y2).contiguous()          # [:, 4:5] is a strided view when N > 1
             probs, _ = ops.predictor_tail(y2, w['conv3_w'], w['conv3_b'], w['out_ln_w'], w['out_ln_b'], P)             # [N,H,1,P]
-            kpr = _k_per_row_causal(H, pc.k, pc.k_oversample, P, t + 1, 1, q.device)
+            kpr = kpr_all[t:t + 1]
             bits = ops.topk_mask_bits(probs, kpr.repeat(N) if N > 1 else kpr, 'causal_batch')
             qs, ks, vs = q_for_score[:, :, i:i + 1], k_for_score[:, :, :t + 1], v[:, :, :t + 1]
             if ops.attention_bits_supported(q.dtype, d, P):
