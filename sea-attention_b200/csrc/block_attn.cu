@@ -42,9 +42,6 @@ constexpr int kTileBytes = kBN * kBD * 2;      // 8 KB
 constexpr int kMaskBytes = kBM * 16;            // per stage: 128 rows x 2 u64 (the element masks of an aligned tile pair)
 constexpr int kStageBytes = 2 * kTileBytes + kMaskBytes;
 constexpr int kMaxTileWords = 64;  // activity bitmap words -> T_SRC <= 64 * 32 * 64 = 131072
-#ifndef SEA_BLOCK_DENSE_GROUPS
-#define SEA_BLOCK_DENSE_GROUPS 0
-#endif
 template <typename T16>
 __device__ __forceinline__ uint32_t pack2b(float a, float b);
 template <>
@@ -217,7 +214,7 @@ block_attention_bits_kernel(const uint32_t* __restrict__ tile_act, int act_words
             float sc[kBN / 8][4];
 #pragma unroll
             for (int cg = 0; cg < 4; ++cg) {
-                if (SEA_BLOCK_DENSE_GROUPS || (act & (1u << cg))) {
+                if (act & (1u << cg)) {
 #pragma unroll
                     for (int i = 0; i < 4; ++i) { sc[2 * cg][i] = 0.f; sc[2 * cg + 1][i] = 0.f; }
 #pragma unroll
@@ -236,7 +233,7 @@ block_attention_bits_kernel(const uint32_t* __restrict__ tile_act, int act_words
             float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
             for (int cg = 0; cg < 4; ++cg) {
-                if (SEA_BLOCK_DENSE_GROUPS || (act & (1u << cg))) {
+                if (act & (1u << cg)) {
                     const uint32_t w0 = cg < 2 ? r0lo : r0hi, w1 = cg < 2 ? r1lo : r1hi;
 #pragma unroll
                     for (int j = 0; j < 2; ++j) {
@@ -270,7 +267,7 @@ block_attention_bits_kernel(const uint32_t* __restrict__ tile_act, int act_words
             float ps0 = 0.f, ps1 = 0.f;
 #pragma unroll
             for (int cg = 0; cg < 4; ++cg) {
-                if (SEA_BLOCK_DENSE_GROUPS || (act & (1u << cg))) {
+                if (act & (1u << cg)) {
                     uint32_t pa[4];
                     {
                         const float p00 = ex2f(fmaf(sc[2 * cg][0], kLog2e, nms[0])), p01 = ex2f(fmaf(sc[2 * cg][1], kLog2e, nms[0]));
