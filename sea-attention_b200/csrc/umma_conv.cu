@@ -15,6 +15,7 @@
 #include "umma.cuh"
 
 #include <mutex>
+#include <stdlib.h>
 
 namespace sea {
 
@@ -242,6 +243,185 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Row-pair ring version of the 3x3 / dilation-2 causal convolution for W = 64 (a tile = 2 time rows x 64 columns).
+// The kernel above fetches nine shifted 16 KB windows per tile and is bound by that TMA traffic (ncu: tensor pipe 21 %, 144 KB
+// per 1.2 MFLOP tile).  With dilation 2 and 2-row tiles the three time shifts of tile k are exactly the row pairs k-2, k-1, k,
+// so a CTA that walks consecutive tiles keeps a ring of three row pairs (x three column shifts -2, 0, +2) in shared memory
+// and loads only the NEW pair per tile: 48 KB instead of 144 KB.  Taps are issued oldest pair first; the slot of pair k-2 is
+// released right after its taps (tcgen05.commit), and refilled with pair k+1 while the taps of pairs k-1 and k run.
+// No output staging buffer: every epilogue thread owns one pixel row = 128 contiguous bytes of the channels-last output.
+// ------------------------------------------------------------------------------------------------
+constexpr int kRingPos = 3;
+struct RingSmem {
+    static constexpr int kWBytes = 9 * 64 * 128;
+    static constexpr int kRingOff = kWBytes;
+    static constexpr int kBarOff = kRingOff + kRingPos * 3 * kATileBytes;
+    static constexpr int kTotal = kBarOff + 256 + 1024;
+};
+
+template <bool kRelu>
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv_ring_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+                      const float* __restrict__ bias, __nv_bfloat16* __restrict__ y, int N, int T, int PT, int pairs_per_cta) {
+    constexpr int kNOut = 64, W = 64;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* wsm = smem;
+    uint8_t* ring = smem + RingSmem::kRingOff;                     // [pos][shift][128 rows x 128 B]
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + RingSmem::kBarOff);     // [pos]
+    uint64_t* empty = full + kRingPos;                             // [pos]
+    uint64_t* tmem_full = empty + kRingPos;                        // [2]
+    uint64_t* tmem_empty = tmem_full + 2;                          // [2]
+    uint64_t* wbar = tmem_empty + 2;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(wbar + 1);
+    // the shuffle makes the warp index provably warp-uniform, so the role branches below stay in the uniform datapath
+    const int warp = __shfl_sync(0xffffffffu, (int) (threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+    const int G = N * PT;
+    const int g_begin = blockIdx.x * pairs_per_cta, g_end = min(G, g_begin + pairs_per_cta);
+    if (threadIdx.x == 0) {
+        umma::prefetch_tensormap(&tmap_x);
+        umma::prefetch_tensormap(&tmap_w);
+        for (int p = 0; p < kRingPos; ++p) { umma::mbar_init(&full[p], 1); umma::mbar_init(&empty[p], 1); }
+        for (int a = 0; a < 2; ++a) { umma::mbar_init(&tmem_full[a], 1); umma::mbar_init(&tmem_empty[a], 128); }
+        umma::mbar_init(wbar, 1);
+        umma::fence_barrier_init();
+    }
+    if (warp == 1) umma::tmem_alloc(tmem_ptr, 2 * kNOut);
+    umma::tc_fence_before();
+    __syncthreads();
+    umma::tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        if (lane == 0 && g_begin < g_end) {
+            umma::mbar_arrive_expect_tx(wbar, RingSmem::kWBytes);
+            for (int tap = 0; tap < 9; ++tap) umma::tma_load_2d(wsm + tap * kNOut * 128, &tmap_w, wbar, 0, tap * kNOut);
+            uint32_t filled = 0, fill_par = 0;           // bit pos: position has been filled before / parity of its next release
+            bool run_start = true;
+            int pos0 = ((g_begin % PT) + 1) % 3;
+            for (int g = g_begin; g < g_end; ++g) {
+                const int n = g / PT, k = g % PT;
+                if (k == 0) { run_start = true; pos0 = 1; }
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    if (!(run_start || i == 2)) continue;  // pairs k-2 and k-1 are already resident inside a run
+                    const int pk = k - 2 + i;              // row pair (may be < 0: all zeros, the causal padding)
+                    int pos = pos0 + i;
+                    pos = pos >= 3 ? pos - 3 : pos;
+                    if ((filled >> pos) & 1u) {
+                        umma::mbar_wait(&empty[pos], (fill_par >> pos) & 1u);
+                        fill_par ^= 1u << pos;
+                    }
+                    filled |= 1u << pos;
+                    umma::mbar_arrive_expect_tx(&full[pos], 3 * kATileBytes);
+#pragma unroll
+                    for (int j = 0; j < 3; ++j)
+                        umma::tma_load_4d(ring + (pos * 3 + j) * kATileBytes, &tmap_x, &full[pos], 0, 2 * j - 2, 2 * pk, n);
+                }
+                run_start = false;
+                pos0 = pos0 == 2 ? 0 : pos0 + 1;
+            }
+        }
+    } else if (warp == 1) {
+        if (g_begin < g_end) {
+            // The whole warp walks this loop (warp-uniform control flow and operands); elect.sync inside the helpers picks the
+            // issuing lane.  Descriptors are base + constant offsets in units of 16 B: ring slot 1024, weight tap 512, k-step 2.
+            constexpr uint32_t idesc = umma::make_idesc_bf16(128, kNOut);
+            const uint64_t a_base = umma::make_desc_k_sw128(umma::smem_u32(ring));
+            const uint64_t b_base = umma::make_desc_k_sw128(umma::smem_u32(wsm));
+            umma::mbar_wait(wbar, 0);
+            uint32_t fill_par = 0;                        // bit pos: parity of the next fill of that ring position
+            bool run_start = true;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            int pos0 = ((g_begin % PT) + 1) % 3;          // ring position of pair k-2
+            for (int g = g_begin; g < g_end; ++g) {
+                const int k = g % PT;
+                if (k == 0) { run_start = true; pos0 = 1; }
+                const bool run_end = (g + 1 == g_end) || (k + 1 == PT);       // the next tile does not continue this run of rows
+                umma::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                umma::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t) (acc * kNOut);
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    int pos = pos0 + i;
+                    pos = pos >= 3 ? pos - 3 : pos;
+                    if (run_start || i == 2) {             // a fresh fill of this position: wait for its three windows
+                        umma::mbar_wait(&full[pos], (fill_par >> pos) & 1u);
+                        umma::tc_fence_after();
+                        fill_par ^= 1u << pos;
+                    }
+                    const uint64_t a_pos = a_base + (uint64_t) (pos * 3 * (kATileBytes >> 4));
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) {
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk)
+                            umma::mma_bf16_ss_elect(d_tmem, a_pos + (uint64_t) (j * (kATileBytes >> 4) + kk * 2),
+                                                    b_base + (uint64_t) ((i * 3 + j) * (kNOut * 128 >> 4) + kk * 2), idesc,
+                                                    (uint32_t) ((i | j | kk) != 0));
+                    }
+                    if (i == 0 && !run_end) umma::mma_commit_elect(&empty[pos]);    // pair k-2 is not needed by any later tile
+                }
+                if (run_end) {
+#pragma unroll
+                    for (int p = 0; p < kRingPos; ++p) umma::mma_commit_elect(&empty[p]);
+                }
+                umma::mma_commit_elect(&tmem_full[acc]);
+                run_start = false;
+                pos0 = pos0 == 2 ? 0 : pos0 + 1;
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1;
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const int row = q * 32 + lane;                // pixel row inside the tile: (t0 + row / 64, row % 64)
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int g = g_begin; g < g_end; ++g) {
+            const int n = g / PT, t0 = (g % PT) * 2;
+            umma::mbar_wait(&tmem_full[acc], acc_phase);
+            umma::tc_fence_after();
+            const bool ok = t0 + row / W < T;
+            uint8_t* gout = reinterpret_cast<uint8_t*>(y) + ((((int64_t) n * T + t0) * W) + row) * (int64_t) (kNOut * 2);
+#pragma unroll
+            for (int c0 = 0; c0 < kNOut; c0 += 32) {
+                uint32_t r[32];
+                umma::tmem_ld_32x32(tmem_base + ((uint32_t) (q * 32) << 16) + (uint32_t) (acc * kNOut + c0), r);
+                umma::tmem_ld_wait();
+                float f[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const float val = __uint_as_float(r[i]) + __ldg(bias + c0 + i);
+                    f[i] = kRelu ? fmaxf(val, 0.f) : val;
+                }
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch) {
+                    uint4 pk;
+                    __nv_bfloat162 p0 = __floats2bfloat162_rn(f[ch * 8 + 0], f[ch * 8 + 1]);
+                    __nv_bfloat162 p1 = __floats2bfloat162_rn(f[ch * 8 + 2], f[ch * 8 + 3]);
+                    __nv_bfloat162 p2 = __floats2bfloat162_rn(f[ch * 8 + 4], f[ch * 8 + 5]);
+                    __nv_bfloat162 p3 = __floats2bfloat162_rn(f[ch * 8 + 6], f[ch * 8 + 7]);
+                    pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
+                    pk.z = *reinterpret_cast<uint32_t*>(&p2); pk.w = *reinterpret_cast<uint32_t*>(&p3);
+                    if (ok) *reinterpret_cast<uint4*>(gout + c0 * 2 + ch * 16) = pk;
+                }
+            }
+            umma::tc_fence_before();
+            umma::mbar_arrive(&tmem_empty[acc]);
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
+        }
+    }
+    umma::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        umma::tc_fence_after();
+        umma::tmem_dealloc(tmem_base, 2 * kNOut);
+    }
+}
+
 template <int kTaps, int kNOut, bool kRelu, typename OutT>
 int launch_conv_umma(const void* x, const float* weight, const float* bias, void* y, void* ws, int N, int T, int W, int C, cudaStream_t s) {
     using SM = ConvSmem<kTaps, kNOut>;
@@ -271,6 +451,20 @@ int launch_conv_umma(const void* x, const float* weight, const float* bias, void
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if constexpr (kTaps == 9 && kNOut == 64 && sizeof(OutT) == 2) {
+        static const bool no_ring = getenv("SEA_CONV_NO_RING") != nullptr;       // development switch for A/B timing
+        if (W == 64 && !no_ring) {
+            // row-pair ring: CTAs walk runs of consecutive tiles; one run per CTA
+            const int grid_r = num_tiles < sms ? num_tiles : sms;
+            const int per = (num_tiles + grid_r - 1) / grid_r;
+            const int grid_used = (num_tiles + per - 1) / per;
+            auto kr = conv_ring_umma_kernel<kRelu>;
+            SEA_CUDA_TRY(cudaFuncSetAttribute(kr, cudaFuncAttributeMaxDynamicSharedMemorySize, RingSmem::kTotal), "smem attr");
+            kr<<<grid_used, kConvThreads, RingSmem::kTotal, s>>>(tx, tw, bias, reinterpret_cast<__nv_bfloat16*>(y), N, T, tblocks, per);
+            SEA_CHECK_LAUNCH("conv_ring_umma_kernel");
+            return SEA_OK;
+        }
+    }
     auto kern = conv_umma_kernel<kTaps, kNOut, kRelu, OutT>;
     SEA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kTotal), "smem attr");
     const int grid = num_tiles < sms ? num_tiles : sms;

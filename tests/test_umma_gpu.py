@@ -17,7 +17,7 @@ def _conv_ref(x_cl, weight, bias):
     return y.permute(0, 2, 3, 1).contiguous()
 
 
-@pytest.mark.parametrize('N,T,W', [(1, 8, 64), (2, 37, 64), (1, 130, 32), (1, 64, 16), (1, 5, 128)])
+@pytest.mark.parametrize('N,T,W', [(1, 8, 64), (2, 37, 64), (1, 130, 32), (1, 64, 16), (1, 5, 128), (3, 700, 64), (1, 601, 64)])
 def test_conv3x3_umma_matches_oracle(sea, N, T, W):
     C = O = 64
     g = torch.Generator().manual_seed(T * 7 + W)
