@@ -96,7 +96,8 @@ block_attention_umma_kernel(const uint32_t* __restrict__ tile_act, int act_words
     uint16_t* slist = reinterpret_cast<uint16_t*>(sm + USmem::kList);
     __shared__ int s_nact;
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // warp index (and below the tile count) through a shuffle: provably warp-uniform, which keeps the MMA issue loop in the uniform datapath
+    const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const int rb = n_row_blocks - 1 - (int) (blockIdx.x / (unsigned) (N * H));       // heavy (late) row blocks first
     const int nh = (int) (blockIdx.x % (unsigned) (N * H));
     const int n = nh / H, h = nh % H;
@@ -134,7 +135,7 @@ block_attention_umma_kernel(const uint32_t* __restrict__ tile_act, int act_words
         if (lane == 0) s_nact = base;
     }
     __syncthreads();
-    const int nact = s_nact;
+    const int nact = __shfl_sync(0xffffffffu, s_nact, 0);
     const uint32_t tS0 = tmem_base, tS1 = tmem_base + 64, tO = tmem_base + 128;
 
     if (warp == 0) {
@@ -155,7 +156,7 @@ block_attention_umma_kernel(const uint32_t* __restrict__ tile_act, int act_words
         }
     } else if (warp == 1) {
         // ---------------------------------------------------------------- MMA issuer
-        if (lane == 0 && nact > 0) {
+        if (nact > 0) {          // all 32 lanes walk the loop; elect.sync inside the *_elect helpers picks the issuing lane
             const uint32_t idesc_s = umma::make_idesc_bf16(kUM, kUN);          // A, B K-major
             const uint32_t idesc_o = idesc_bf16_b_mn(kUM, kUD);                // B = V, MN-major
             const uint32_t q_addr = umma::smem_u32(sm + USmem::kQ);
@@ -169,8 +170,8 @@ block_attention_umma_kernel(const uint32_t* __restrict__ tile_act, int act_words
                 const uint32_t ka = kv_addr + (uint32_t) s * kUStage;
 #pragma unroll
                 for (int k = 0; k < kUD / 16; ++k)
-                    umma::mma_bf16_ss(b ? tS1 : tS0, umma::make_desc_k_sw128(q_addr + k * 32), umma::make_desc_k_sw128(ka + k * 32), idesc_s, (uint32_t) (k != 0));
-                umma::mma_commit(&s_full[b]);
+                    umma::mma_bf16_ss_elect(b ? tS1 : tS0, umma::make_desc_k_sw128(q_addr + k * 32), umma::make_desc_k_sw128(ka + k * 32), idesc_s, (uint32_t) (k != 0));
+                umma::mma_commit_elect(&s_full[b]);
             };
             umma::mbar_wait(q_full, 0);
             issue_s(0);
@@ -183,9 +184,9 @@ block_attention_umma_kernel(const uint32_t* __restrict__ tile_act, int act_words
                 const uint32_t pa = p_addr + (uint32_t) b * kUP;
 #pragma unroll
                 for (int k = 0; k < kUN / 16; ++k)       // 16 source tokens per step: A advances 32 B inside the row, B two 8-token groups
-                    umma::mma_bf16_ss(tO, umma::make_desc_k_sw128(pa + k * 32), umma::make_desc_k_sw128(va + k * 2048), idesc_o, (uint32_t) ((j | k) != 0));
-                umma::mma_commit(&kv_empty[s]);
-                umma::mma_commit(&p_empty[b]);
+                    umma::mma_bf16_ss_elect(tO, umma::make_desc_k_sw128(pa + k * 32), umma::make_desc_k_sw128(va + k * 2048), idesc_o, (uint32_t) ((j | k) != 0));
+                umma::mma_commit_elect(&kv_empty[s]);
+                umma::mma_commit_elect(&p_empty[b]);
             }
         }
     } else {

@@ -113,7 +113,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     uint64_t* wbar = tmem_empty + 2;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(wbar + 1);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int) (threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform
     if (threadIdx.x == 0) {
         umma::prefetch_tensormap(&tmap_x);
         umma::prefetch_tensormap(&tmap_w);
@@ -147,7 +147,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {   // all 32 lanes walk the loop; elect.sync inside the *_elect helpers picks the issuing lane
             constexpr uint32_t idesc = umma::make_idesc_bf16(128, kNOut);
             umma::mbar_wait(wbar, 0);
             int stage = 0, acc = 0;
@@ -163,12 +163,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                     const uint32_t b_addr = umma::smem_u32(wsm + tap * kNOut * 128);
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
-                        umma::mma_bf16_ss(d_tmem, umma::make_desc_k_sw128(a_addr + k * 32), umma::make_desc_k_sw128(b_addr + k * 32),
+                        umma::mma_bf16_ss_elect(d_tmem, umma::make_desc_k_sw128(a_addr + k * 32), umma::make_desc_k_sw128(b_addr + k * 32),
                                           idesc, (uint32_t) ((tap | k) != 0));
-                    umma::mma_commit(&empty[stage]);
+                    umma::mma_commit_elect(&empty[stage]);
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
-                umma::mma_commit(&tmem_full[acc]);
+                umma::mma_commit_elect(&tmem_full[acc]);
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1;
             }

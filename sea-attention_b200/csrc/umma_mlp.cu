@@ -89,7 +89,8 @@ mlp_umma_kernel(const __grid_constant__ CUtensorMap tmap_ctx, const __grid_const
     const int rows_used = TT * H;                   // rows of the 128-row tile that carry tokens (H need not divide 128)
     const uint32_t atom_bytes = (uint32_t) rows_used * 128u;     // bytes one TMA box delivers
     const int N2 = SW + 16;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // warp index through a shuffle: provably warp-uniform, so the role branches and the MMA issue loop use the uniform datapath
+    const int warp = __shfl_sync(0xffffffffu, (int) (threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     for (int i = threadIdx.x; i < 128; i += kMlpTcThreads) { s_enc_b[i] = enc_b[i]; s_ln_w[i] = enc_ln_w[i]; s_ln_b[i] = enc_ln_b[i]; }
     for (int i = threadIdx.x; i < 144; i += kMlpTcThreads) s_dec_b[i] = i < SW ? dec_b[i] : (i < SW + 2 ? scl_b[i - SW] : 0.f);
     for (int i = threadIdx.x; i < W; i += kMlpTcThreads) { s_cw[i] = cnn_ln_w[i]; s_cb[i] = cnn_ln_b[i]; }
@@ -126,7 +127,7 @@ mlp_umma_kernel(const __grid_constant__ CUtensorMap tmap_ctx, const __grid_const
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {   // all 32 lanes walk the loop; elect.sync inside the *_elect helpers picks the issuing lane
             const uint32_t idesc1 = umma::make_idesc_bf16(128, 128);
             const uint32_t idesc2 = umma::make_idesc_bf16(128, (uint32_t) N2);
             umma::mbar_wait(wbar, 0);
@@ -141,10 +142,10 @@ mlp_umma_kernel(const __grid_constant__ CUtensorMap tmap_ctx, const __grid_const
                 for (int a = 0; a < 3; ++a)
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
-                        umma::mma_bf16_ss(acc1, umma::make_desc_k_sw128(a1 + a * kTile + k * 32), umma::make_desc_k_sw128(w1 + a * kTile + k * 32),
+                        umma::mma_bf16_ss_elect(acc1, umma::make_desc_k_sw128(a1 + a * kTile + k * 32), umma::make_desc_k_sw128(w1 + a * kTile + k * 32),
                                           idesc1, (uint32_t) ((a | k) != 0));
-                umma::mma_commit(&empty1[buf]);
-                umma::mma_commit(acc1_full);
+                umma::mma_commit_elect(&empty1[buf]);
+                umma::mma_commit_elect(acc1_full);
                 umma::mbar_wait(a2_full, tphase);
                 umma::tc_fence_after();
                 const uint32_t a2 = umma::smem_u32(smem + MlpSmem::kA2);
@@ -153,9 +154,9 @@ mlp_umma_kernel(const __grid_constant__ CUtensorMap tmap_ctx, const __grid_const
                 for (int a = 0; a < 2; ++a)
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
-                        umma::mma_bf16_ss(acc2, umma::make_desc_k_sw128(a2 + a * kTile + k * 32),
+                        umma::mma_bf16_ss_elect(acc2, umma::make_desc_k_sw128(a2 + a * kTile + k * 32),
                                           umma::make_desc_k_sw128(w2 + a * MlpSmem::kW2Atom + k * 32), idesc2, (uint32_t) ((a | k) != 0));
-                umma::mma_commit(acc2_full);
+                umma::mma_commit_elect(acc2_full);
                 tphase ^= 1;
                 if (++buf == 2) { buf = 0; phase ^= 1; }
             }
