@@ -247,21 +247,25 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 // Row-pair ring version of the 3x3 / dilation-2 causal convolution for W = 64 (a tile = 2 time rows x 64 columns).
 // The kernel above fetches nine shifted 16 KB windows per tile and is bound by that TMA traffic (ncu: tensor pipe 21 %, 144 KB
 // per 1.2 MFLOP tile).  With dilation 2 and 2-row tiles the three time shifts of tile k are exactly the row pairs k-2, k-1, k,
-// so a CTA that walks consecutive tiles keeps a ring of three row pairs (x three column shifts -2, 0, +2) in shared memory
-// and loads only the NEW pair per tile: 48 KB instead of 144 KB.  Taps are issued oldest pair first; the slot of pair k-2 is
-// released right after its taps (tcgen05.commit), and refilled with pair k+1 while the taps of pairs k-1 and k run.
+// so a CTA that walks consecutive tiles loads every row pair ONCE (x three column shifts -2, 0, +2 = 48 KB instead of 144 KB
+// per tile) into a ring of three positions.  The MMA order is pair-stationary: when pair p lands, its 36 MMAs go to three
+// TMEM accumulators -- the last taps of tile p (which completes it), the middle taps of tile p+1, the first taps of tile
+// p+2 -- and the position is released, so the producer always runs two pairs (72 MMAs) ahead of the tensor core.
+// Four accumulators of 64 columns: three in flight plus one being drained by the epilogue warps.
 // No output staging buffer: every epilogue thread owns one pixel row = 128 contiguous bytes of the channels-last output.
 // ------------------------------------------------------------------------------------------------
-constexpr int kRingPos = 3;
+constexpr int kRingPos = 3, kRingAcc = 4;
+constexpr int kRingEpiWarps = 8, kRingThreads = 64 + 32 * kRingEpiWarps;      // TMA warp, MMA warp, 8 epilogue warps
 struct RingSmem {
     static constexpr int kWBytes = 9 * 64 * 128;
     static constexpr int kRingOff = kWBytes;
     static constexpr int kBarOff = kRingOff + kRingPos * 3 * kATileBytes;
-    static constexpr int kTotal = kBarOff + 256 + 1024;
+    static constexpr int kBiasOff = kBarOff + 256;
+    static constexpr int kTotal = kBiasOff + 256 + 1024;
 };
 
 template <bool kRelu>
-__global__ void __launch_bounds__(kConvThreads, 1)
+__global__ void __launch_bounds__(kRingThreads, 1)
 conv_ring_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                       const float* __restrict__ bias, __nv_bfloat16* __restrict__ y, int N, int T, int PT, int pairs_per_cta) {
     constexpr int kNOut = 64, W = 64;
@@ -271,10 +275,12 @@ conv_ring_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
     uint8_t* ring = smem + RingSmem::kRingOff;                     // [pos][shift][128 rows x 128 B]
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + RingSmem::kBarOff);     // [pos]
     uint64_t* empty = full + kRingPos;                             // [pos]
-    uint64_t* tmem_full = empty + kRingPos;                        // [2]
-    uint64_t* tmem_empty = tmem_full + 2;                          // [2]
-    uint64_t* wbar = tmem_empty + 2;
+    uint64_t* tmem_full = empty + kRingPos;                        // [kRingAcc]
+    uint64_t* tmem_empty = tmem_full + kRingAcc;                   // [kRingAcc]
+    uint64_t* wbar = tmem_empty + kRingAcc;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(wbar + 1);
+    float* s_bias = reinterpret_cast<float*>(smem + RingSmem::kBiasOff);
+    if (threadIdx.x < kNOut) s_bias[threadIdx.x] = bias[threadIdx.x];
     // the shuffle makes the warp index provably warp-uniform, so the role branches below stay in the uniform datapath
     const int warp = __shfl_sync(0xffffffffu, (int) (threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const int G = N * PT;
@@ -283,11 +289,11 @@ conv_ring_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
         umma::prefetch_tensormap(&tmap_x);
         umma::prefetch_tensormap(&tmap_w);
         for (int p = 0; p < kRingPos; ++p) { umma::mbar_init(&full[p], 1); umma::mbar_init(&empty[p], 1); }
-        for (int a = 0; a < 2; ++a) { umma::mbar_init(&tmem_full[a], 1); umma::mbar_init(&tmem_empty[a], 128); }
+        for (int a = 0; a < kRingAcc; ++a) { umma::mbar_init(&tmem_full[a], 1); umma::mbar_init(&tmem_empty[a], 32 * kRingEpiWarps); }
         umma::mbar_init(wbar, 1);
         umma::fence_barrier_init();
     }
-    if (warp == 1) umma::tmem_alloc(tmem_ptr, 2 * kNOut);
+    if (warp == 1) umma::tmem_alloc(tmem_ptr, kRingAcc * kNOut);
     umma::tc_fence_before();
     __syncthreads();
     umma::tc_fence_after();
@@ -297,30 +303,19 @@ conv_ring_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
         if (lane == 0 && g_begin < g_end) {
             umma::mbar_arrive_expect_tx(wbar, RingSmem::kWBytes);
             for (int tap = 0; tap < 9; ++tap) umma::tma_load_2d(wsm + tap * kNOut * 128, &tmap_w, wbar, 0, tap * kNOut);
-            uint32_t filled = 0, fill_par = 0;           // bit pos: position has been filled before / parity of its next release
-            bool run_start = true;
-            int pos0 = ((g_begin % PT) + 1) % 3;
-            for (int g = g_begin; g < g_end; ++g) {
-                const int n = g / PT, k = g % PT;
-                if (k == 0) { run_start = true; pos0 = 1; }
-#pragma unroll
-                for (int i = 0; i < 3; ++i) {
-                    if (!(run_start || i == 2)) continue;  // pairs k-2 and k-1 are already resident inside a run
-                    const int pk = k - 2 + i;              // row pair (may be < 0: all zeros, the causal padding)
-                    int pos = pos0 + i;
-                    pos = pos >= 3 ? pos - 3 : pos;
-                    if ((filled >> pos) & 1u) {
-                        umma::mbar_wait(&empty[pos], (fill_par >> pos) & 1u);
-                        fill_par ^= 1u << pos;
-                    }
-                    filled |= 1u << pos;
+            int pos = 0, round = 0;                      // ring position / how many times the ring has wrapped
+            for (int g0 = g_begin; g0 < g_end;) {
+                const int n = g0 / PT, k0 = g0 % PT;     // one run: tiles [k0, k1) of batch item n
+                const int k1 = min(PT, k0 + (g_end - g0));
+                for (int pk = k0 - 2; pk < k1; ++pk) {   // row pairs of the run (pk < 0: all zeros, the causal padding)
+                    if (round > 0) umma::mbar_wait(&empty[pos], (uint32_t) ((round - 1) & 1));
                     umma::mbar_arrive_expect_tx(&full[pos], 3 * kATileBytes);
 #pragma unroll
                     for (int j = 0; j < 3; ++j)
                         umma::tma_load_4d(ring + (pos * 3 + j) * kATileBytes, &tmap_x, &full[pos], 0, 2 * j - 2, 2 * pk, n);
+                    if (++pos == kRingPos) { pos = 0; ++round; }
                 }
-                run_start = false;
-                pos0 = pos0 == 2 ? 0 : pos0 + 1;
+                g0 += k1 - k0;
             }
         }
     } else if (warp == 1) {
@@ -331,94 +326,89 @@ conv_ring_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
             const uint64_t a_base = umma::make_desc_k_sw128(umma::smem_u32(ring));
             const uint64_t b_base = umma::make_desc_k_sw128(umma::smem_u32(wsm));
             umma::mbar_wait(wbar, 0);
-            uint32_t fill_par = 0;                        // bit pos: parity of the next fill of that ring position
-            bool run_start = true;
-            int acc = 0;
-            uint32_t acc_phase = 0;
-            int pos0 = ((g_begin % PT) + 1) % 3;          // ring position of pair k-2
-            for (int g = g_begin; g < g_end; ++g) {
-                const int k = g % PT;
-                if (k == 0) { run_start = true; pos0 = 1; }
-                const bool run_end = (g + 1 == g_end) || (k + 1 == PT);       // the next tile does not continue this run of rows
-                umma::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
-                umma::tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t) (acc * kNOut);
-#pragma unroll
-                for (int i = 0; i < 3; ++i) {
-                    int pos = pos0 + i;
-                    pos = pos >= 3 ? pos - 3 : pos;
-                    if (run_start || i == 2) {             // a fresh fill of this position: wait for its three windows
-                        umma::mbar_wait(&full[pos], (fill_par >> pos) & 1u);
-                        umma::tc_fence_after();
-                        fill_par ^= 1u << pos;
-                    }
+            int pos = 0, round = 0, c_base = 0;           // c_base: tiles of this CTA that belong to earlier runs
+            for (int g0 = g_begin; g0 < g_end;) {
+                const int k0 = g0 % PT;
+                const int k1 = min(PT, k0 + (g_end - g0));
+                for (int pk = k0 - 2; pk < k1; ++pk) {
+                    umma::mbar_wait(&full[pos], (uint32_t) (round & 1));
+                    umma::tc_fence_after();
                     const uint64_t a_pos = a_base + (uint64_t) (pos * 3 * (kATileBytes >> 4));
 #pragma unroll
-                    for (int j = 0; j < 3; ++j) {
+                    for (int ii = 0; ii < 3; ++ii) {      // oldest tile first: tile pk takes this pair with its last taps (i = 2)
+                        const int i = 2 - ii;
+                        const int t = pk + ii;
+                        if (t >= k0 && t < k1) {
+                            const int c = c_base + (t - k0);
+                            const int slot = c & (kRingAcc - 1);
+                            if (i == 0) {                  // first taps of tile t: its accumulator must have been drained
+                                umma::mbar_wait(&tmem_empty[slot], (uint32_t) (((c / kRingAcc) & 1) ^ 1));
+                                umma::tc_fence_after();
+                            }
+                            const uint32_t d_tmem = tmem_base + (uint32_t) (slot * kNOut);
 #pragma unroll
-                        for (int kk = 0; kk < 4; ++kk)
-                            umma::mma_bf16_ss_elect(d_tmem, a_pos + (uint64_t) (j * (kATileBytes >> 4) + kk * 2),
-                                                    b_base + (uint64_t) ((i * 3 + j) * (kNOut * 128 >> 4) + kk * 2), idesc,
-                                                    (uint32_t) ((i | j | kk) != 0));
+                            for (int j = 0; j < 3; ++j) {
+#pragma unroll
+                                for (int kk = 0; kk < 4; ++kk)
+                                    umma::mma_bf16_ss_elect(d_tmem, a_pos + (uint64_t) (j * (kATileBytes >> 4) + kk * 2),
+                                                            b_base + (uint64_t) ((i * 3 + j) * (kNOut * 128 >> 4) + kk * 2), idesc,
+                                                            (uint32_t) ((i | j | kk) != 0));
+                            }
+                            if (i == 2) umma::mma_commit_elect(&tmem_full[slot]);
+                        }
                     }
-                    if (i == 0 && !run_end) umma::mma_commit_elect(&empty[pos]);    // pair k-2 is not needed by any later tile
+                    umma::mma_commit_elect(&empty[pos]);
+                    if (++pos == kRingPos) { pos = 0; ++round; }
                 }
-                if (run_end) {
-#pragma unroll
-                    for (int p = 0; p < kRingPos; ++p) umma::mma_commit_elect(&empty[p]);
-                }
-                umma::mma_commit_elect(&tmem_full[acc]);
-                run_start = false;
-                pos0 = pos0 == 2 ? 0 : pos0 + 1;
-                acc ^= 1;
-                if (acc == 0) acc_phase ^= 1;
+                c_base += k1 - k0;
+                g0 += k1 - k0;
             }
         }
     } else {
-        const int q = warp & 3;
+        // Eight epilogue warps: warp % 4 is the TMEM lane quarter the hardware lets a warp read, (warp - 2) / 4 the column
+        // half.  Every thread owns 32 channels of one pixel = 64 contiguous bytes of the channels-last output, written with
+        // two 256-bit stores (full 32-byte sectors).  Bias comes from shared memory as broadcast float4 reads.
+        const int q = warp & 3, half = (warp - 2) >> 2;
         const int row = q * 32 + lane;                // pixel row inside the tile: (t0 + row / 64, row % 64)
-        int acc = 0;
-        uint32_t acc_phase = 0;
+        const int c0 = half * 32;
+        const float4* b4 = reinterpret_cast<const float4*>(s_bias + c0);
         for (int g = g_begin; g < g_end; ++g) {
             const int n = g / PT, t0 = (g % PT) * 2;
-            umma::mbar_wait(&tmem_full[acc], acc_phase);
+            const int c = g - g_begin, acc = c & (kRingAcc - 1);
+            umma::mbar_wait(&tmem_full[acc], (uint32_t) ((c / kRingAcc) & 1));
             umma::tc_fence_after();
             const bool ok = t0 + row / W < T;
-            uint8_t* gout = reinterpret_cast<uint8_t*>(y) + ((((int64_t) n * T + t0) * W) + row) * (int64_t) (kNOut * 2);
-#pragma unroll
-            for (int c0 = 0; c0 < kNOut; c0 += 32) {
-                uint32_t r[32];
-                umma::tmem_ld_32x32(tmem_base + ((uint32_t) (q * 32) << 16) + (uint32_t) (acc * kNOut + c0), r);
-                umma::tmem_ld_wait();
-                float f[32];
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const float val = __uint_as_float(r[i]) + __ldg(bias + c0 + i);
-                    f[i] = kRelu ? fmaxf(val, 0.f) : val;
-                }
-#pragma unroll
-                for (int ch = 0; ch < 4; ++ch) {
-                    uint4 pk;
-                    __nv_bfloat162 p0 = __floats2bfloat162_rn(f[ch * 8 + 0], f[ch * 8 + 1]);
-                    __nv_bfloat162 p1 = __floats2bfloat162_rn(f[ch * 8 + 2], f[ch * 8 + 3]);
-                    __nv_bfloat162 p2 = __floats2bfloat162_rn(f[ch * 8 + 4], f[ch * 8 + 5]);
-                    __nv_bfloat162 p3 = __floats2bfloat162_rn(f[ch * 8 + 6], f[ch * 8 + 7]);
-                    pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
-                    pk.z = *reinterpret_cast<uint32_t*>(&p2); pk.w = *reinterpret_cast<uint32_t*>(&p3);
-                    if (ok) *reinterpret_cast<uint4*>(gout + c0 * 2 + ch * 16) = pk;
-                }
-            }
+            uint8_t* gout = reinterpret_cast<uint8_t*>(y) + ((((int64_t) n * T + t0) * W) + row) * (int64_t) (kNOut * 2) + c0 * 2;
+            uint32_t r[32];
+            umma::tmem_ld_32x32(tmem_base + ((uint32_t) (q * 32) << 16) + (uint32_t) (acc * kNOut + c0), r);
+            umma::tmem_ld_wait();
             umma::tc_fence_before();
-            umma::mbar_arrive(&tmem_empty[acc]);
-            acc ^= 1;
-            if (acc == 0) acc_phase ^= 1;
+            umma::mbar_arrive(&tmem_empty[acc]);       // the accumulator is in registers: hand it back before the stores
+            uint32_t o[16];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float4 b = b4[i];
+                float v0 = __uint_as_float(r[4 * i + 0]) + b.x, v1 = __uint_as_float(r[4 * i + 1]) + b.y;
+                float v2 = __uint_as_float(r[4 * i + 2]) + b.z, v3 = __uint_as_float(r[4 * i + 3]) + b.w;
+                if (kRelu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
+                __nv_bfloat162 p0 = __floats2bfloat162_rn(v0, v1), p1 = __floats2bfloat162_rn(v2, v3);
+                o[2 * i] = *reinterpret_cast<uint32_t*>(&p0);
+                o[2 * i + 1] = *reinterpret_cast<uint32_t*>(&p1);
+            }
+            if (ok) {
+#pragma unroll
+                for (int hv = 0; hv < 2; ++hv)
+                    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(gout + hv * 32), "r"(o[8 * hv]), "r"(o[8 * hv + 1]),
+                                 "r"(o[8 * hv + 2]), "r"(o[8 * hv + 3]), "r"(o[8 * hv + 4]), "r"(o[8 * hv + 5]), "r"(o[8 * hv + 6]), "r"(o[8 * hv + 7])
+                                 : "memory");
+            }
         }
     }
     umma::tc_fence_before();
     __syncthreads();
     if (warp == 1) {
         umma::tc_fence_after();
-        umma::tmem_dealloc(tmem_base, 2 * kNOut);
+        umma::tmem_dealloc(tmem_base, kRingAcc * kNOut);
     }
 }
 
@@ -460,7 +450,7 @@ int launch_conv_umma(const void* x, const float* weight, const float* bias, void
             const int grid_used = (num_tiles + per - 1) / per;
             auto kr = conv_ring_umma_kernel<kRelu>;
             SEA_CUDA_TRY(cudaFuncSetAttribute(kr, cudaFuncAttributeMaxDynamicSharedMemorySize, RingSmem::kTotal), "smem attr");
-            kr<<<grid_used, kConvThreads, RingSmem::kTotal, s>>>(tx, tw, bias, reinterpret_cast<__nv_bfloat16*>(y), N, T, tblocks, per);
+            kr<<<grid_used, kRingThreads, RingSmem::kTotal, s>>>(tx, tw, bias, reinterpret_cast<__nv_bfloat16*>(y), N, T, tblocks, per);
             SEA_CHECK_LAUNCH("conv_ring_umma_kernel");
             return SEA_OK;
         }
