@@ -245,21 +245,29 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 
 // ------------------------------------------------------------------------------------------------
 // Row-pair ring version of the 3x3 / dilation-2 causal convolution for W = 64 (a tile = 2 time rows x 64 columns).
-// The kernel above fetches nine shifted 16 KB windows per tile and is bound by that TMA traffic (ncu: tensor pipe 21 %, 144 KB
-// per 1.2 MFLOP tile).  With dilation 2 and 2-row tiles the three time shifts of tile k are exactly the row pairs k-2, k-1, k,
-// so a CTA that walks consecutive tiles loads every row pair ONCE (x three column shifts -2, 0, +2 = 48 KB instead of 144 KB
-// per tile) into a ring of three positions.  The MMA order is pair-stationary: when pair p lands, its 36 MMAs go to three
-// TMEM accumulators -- the last taps of tile p (which completes it), the middle taps of tile p+1, the first taps of tile
-// p+2 -- and the position is released, so the producer always runs two pairs (72 MMAs) ahead of the tensor core.
-// Four accumulators of 64 columns: three in flight plus one being drained by the epilogue warps.
-// No output staging buffer: every epilogue thread owns one pixel row = 128 contiguous bytes of the channels-last output.
+// The kernel above fetches nine shifted 16 KB windows per tile and is bound by that L2 -> SM traffic (ncu: tensor pipe 21 %).
+// Here every input row pair is fetched ONCE, 17 KB instead of 144 KB per tile:
+//  * time shifts: with dilation 2 and 2-row tiles the three time taps of tile k are exactly the row pairs k-2, k-1, k, so a
+//    CTA walks consecutive tiles and keeps the pairs in a ring;
+//  * column shifts: the pair is stored column-major interleaved with a zero halo -- shared-memory row r = 2 * (w + 2) + tt for
+//    w = -2 .. 65 (one TMA box through a tensor map whose W and T dimensions are swapped; the halo is TMA's out-of-bounds
+//    zero fill = the convolution's zero padding).  A shift by 2 columns is then a shift by 4 rows = 512 B of the operand
+//    start address, i.e. the three column taps are three UMMA descriptors into the same buffer (start offsets 0 / 512 /
+//    1024 B; measured on B200: the 128B swizzle is applied to absolute shared-memory address bits, so the tap that starts
+//    half-way into a 1024-B atom needs no descriptor base-offset -- setting it gives wrong results).
+// The MMA order is pair-stationary: when pair p lands, its 36 MMAs go to three TMEM accumulators -- the last taps of tile p
+// (which completes it), the middle taps of tile p+1, the first taps of tile p+2 -- and the ring position is released.
+// Four accumulators of 64 columns: three in flight plus one being drained by the epilogue warps.  TMEM lane r of a tile is
+// pixel (t0 + (r & 1), r >> 1).
+// No output staging buffer: every epilogue thread owns 32 channels of one pixel = 64 contiguous bytes of the output.
 // ------------------------------------------------------------------------------------------------
-constexpr int kRingPos = 3, kRingAcc = 4;
+constexpr int kRingPos = 4, kRingAcc = 4;
+constexpr int kPairRows = 2 * (64 + 4), kPairBytes = kPairRows * 128, kPairSlot = 18 * 1024;   // haloed pair, slot 1024-aligned
 constexpr int kRingEpiWarps = 8, kRingThreads = 64 + 32 * kRingEpiWarps;      // TMA warp, MMA warp, 8 epilogue warps
 struct RingSmem {
     static constexpr int kWBytes = 9 * 64 * 128;
     static constexpr int kRingOff = kWBytes;
-    static constexpr int kBarOff = kRingOff + kRingPos * 3 * kATileBytes;
+    static constexpr int kBarOff = kRingOff + kRingPos * kPairSlot;
     static constexpr int kBiasOff = kBarOff + 256;
     static constexpr int kTotal = kBiasOff + 256 + 1024;
 };
@@ -272,7 +280,7 @@ conv_ring_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* wsm = smem;
-    uint8_t* ring = smem + RingSmem::kRingOff;                     // [pos][shift][128 rows x 128 B]
+    uint8_t* ring = smem + RingSmem::kRingOff;                     // [pos][136 rows x 128 B], row = 2 * (w + 2) + tt
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + RingSmem::kBarOff);     // [pos]
     uint64_t* empty = full + kRingPos;                             // [pos]
     uint64_t* tmem_full = empty + kRingPos;                        // [kRingAcc]
@@ -309,10 +317,8 @@ conv_ring_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
                 const int k1 = min(PT, k0 + (g_end - g0));
                 for (int pk = k0 - 2; pk < k1; ++pk) {   // row pairs of the run (pk < 0: all zeros, the causal padding)
                     if (round > 0) umma::mbar_wait(&empty[pos], (uint32_t) ((round - 1) & 1));
-                    umma::mbar_arrive_expect_tx(&full[pos], 3 * kATileBytes);
-#pragma unroll
-                    for (int j = 0; j < 3; ++j)
-                        umma::tma_load_4d(ring + (pos * 3 + j) * kATileBytes, &tmap_x, &full[pos], 0, 2 * j - 2, 2 * pk, n);
+                    umma::mbar_arrive_expect_tx(&full[pos], kPairBytes);
+                    umma::tma_load_4d(ring + pos * kPairSlot, &tmap_x, &full[pos], 0, 2 * pk, -2, n);     // dims (C, T, W, N)
                     if (++pos == kRingPos) { pos = 0; ++round; }
                 }
                 g0 += k1 - k0;
@@ -321,7 +327,8 @@ conv_ring_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
     } else if (warp == 1) {
         if (g_begin < g_end) {
             // The whole warp walks this loop (warp-uniform control flow and operands); elect.sync inside the helpers picks the
-            // issuing lane.  Descriptors are base + constant offsets in units of 16 B: ring slot 1024, weight tap 512, k-step 2.
+            // issuing lane.  Descriptors are base + constant offsets in units of 16 B: ring slot 1152, column tap 32, weight tap 512,
+            // k-step 2.
             constexpr uint32_t idesc = umma::make_idesc_bf16(128, kNOut);
             const uint64_t a_base = umma::make_desc_k_sw128(umma::smem_u32(ring));
             const uint64_t b_base = umma::make_desc_k_sw128(umma::smem_u32(wsm));
@@ -333,7 +340,7 @@ conv_ring_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
                 for (int pk = k0 - 2; pk < k1; ++pk) {
                     umma::mbar_wait(&full[pos], (uint32_t) (round & 1));
                     umma::tc_fence_after();
-                    const uint64_t a_pos = a_base + (uint64_t) (pos * 3 * (kATileBytes >> 4));
+                    const uint64_t a_pos = a_base + (uint64_t) (pos * (kPairSlot >> 4));
 #pragma unroll
                     for (int ii = 0; ii < 3; ++ii) {      // oldest tile first: tile pk takes this pair with its last taps (i = 2)
                         const int i = 2 - ii;
@@ -350,7 +357,7 @@ conv_ring_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
                             for (int j = 0; j < 3; ++j) {
 #pragma unroll
                                 for (int kk = 0; kk < 4; ++kk)
-                                    umma::mma_bf16_ss_elect(d_tmem, a_pos + (uint64_t) (j * (kATileBytes >> 4) + kk * 2),
+                                    umma::mma_bf16_ss_elect(d_tmem, a_pos + (uint64_t) (j * (512 >> 4) + kk * 2),
                                                             b_base + (uint64_t) ((i * 3 + j) * (kNOut * 128 >> 4) + kk * 2), idesc,
                                                             (uint32_t) ((i | j | kk) != 0));
                             }
@@ -369,7 +376,7 @@ conv_ring_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
         // half.  Every thread owns 32 channels of one pixel = 64 contiguous bytes of the channels-last output, written with
         // two 256-bit stores (full 32-byte sectors).  Bias comes from shared memory as broadcast float4 reads.
         const int q = warp & 3, half = (warp - 2) >> 2;
-        const int row = q * 32 + lane;                // pixel row inside the tile: (t0 + row / 64, row % 64)
+        const int row = q * 32 + lane;                // TMEM lane = pixel (t0 + (row & 1), row >> 1)
         const int c0 = half * 32;
         const float4* b4 = reinterpret_cast<const float4*>(s_bias + c0);
         for (int g = g_begin; g < g_end; ++g) {
@@ -377,8 +384,8 @@ conv_ring_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
             const int c = g - g_begin, acc = c & (kRingAcc - 1);
             umma::mbar_wait(&tmem_full[acc], (uint32_t) ((c / kRingAcc) & 1));
             umma::tc_fence_after();
-            const bool ok = t0 + row / W < T;
-            uint8_t* gout = reinterpret_cast<uint8_t*>(y) + ((((int64_t) n * T + t0) * W) + row) * (int64_t) (kNOut * 2) + c0 * 2;
+            const bool ok = t0 + (row & 1) < T;
+            uint8_t* gout = reinterpret_cast<uint8_t*>(y) + ((((int64_t) n * T + t0 + (row & 1)) * W) + (row >> 1)) * (int64_t) (kNOut * 2) + c0 * 2;
             uint32_t r[32];
             umma::tmem_ld_32x32(tmem_base + ((uint32_t) (q * 32) << 16) + (uint32_t) (acc * kNOut + c0), r);
             umma::tmem_ld_wait();
@@ -448,9 +455,17 @@ int launch_conv_umma(const void* x, const float* weight, const float* bias, void
             const int grid_r = num_tiles < sms ? num_tiles : sms;
             const int per = (num_tiles + grid_r - 1) / grid_r;
             const int grid_used = (num_tiles + per - 1) / per;
+            CUtensorMap txp;                      // the same tensor with W and T swapped: a box is (64 ch, 2 rows, 68 columns)
+            {
+                const uint64_t dims[4] = {(uint64_t) C, (uint64_t) T, (uint64_t) W, (uint64_t) N};
+                const uint64_t strides[3] = {(uint64_t) W * C * 2, (uint64_t) C * 2, (uint64_t) T * W * C * 2};
+                const uint32_t box[4] = {64, 2, (uint32_t) (W + 4), 1};
+                int rc = make_tmap_bf16_sw128(&txp, const_cast<void*>(x), 4, dims, strides, box);
+                if (rc) return rc;
+            }
             auto kr = conv_ring_umma_kernel<kRelu>;
             SEA_CUDA_TRY(cudaFuncSetAttribute(kr, cudaFuncAttributeMaxDynamicSharedMemorySize, RingSmem::kTotal), "smem attr");
-            kr<<<grid_used, kRingThreads, RingSmem::kTotal, s>>>(tx, tw, bias, reinterpret_cast<__nv_bfloat16*>(y), N, T, tblocks, per);
+            kr<<<grid_used, kRingThreads, RingSmem::kTotal, s>>>(txp, tw, bias, reinterpret_cast<__nv_bfloat16*>(y), N, T, tblocks, per);
             SEA_CHECK_LAUNCH("conv_ring_umma_kernel");
             return SEA_OK;
         }
