@@ -49,19 +49,21 @@ __global__ void pack_mlp_weights_kernel(const float* __restrict__ enc_w, const f
     }
 }
 
-// GELU(erf) with erf from Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7, far below the bf16 rounding of the result): one
-// reciprocal, one exp2 and a degree-5 Horner chain instead of erff()'s branchy ~30 instructions -- the epilogue is issue-bound.
+// GELU(erf) with erf from Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7, far below the bf16 rounding of the result).  The
+// epilogue is issue-bound, so the formula is folded to 13 instructions with two MUFU ops (approximate reciprocal and exp2):
+//   gelu(x) = x/2 * (1 + sign(x) * erf(|x|/sqrt2)) = max(x, 0) - |x| * exp(-x^2/2) * (poly(t) * t / 2),  t = 1 / (1 + p|x|/sqrt2)
 __device__ __forceinline__ float gelu_erf_(float x) {
-    const float z = fabsf(x) * 0.70710678118654752440f;
-    const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
-    float p = fmaf(1.061405429f, t, -1.453152027f);
-    p = fmaf(p, t, 1.421413741f);
-    p = fmaf(p, t, -0.284496736f);
-    p = fmaf(p, t, 0.254829592f);
-    float e;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-z * z * 1.4426950408889634f));
-    const float erf_abs = fmaf(-p * t, e, 1.0f);                 // erf(|x| / sqrt 2)
-    return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+    const float ax = fabsf(x);
+    float t, e;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f * 0.70710678118654752440f, ax, 1.0f)));
+    float q = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);
+    q = fmaf(q, t, 0.5f * 1.421413741f);
+    q = fmaf(q, t, 0.5f * -0.284496736f);
+    q = fmaf(q, t, 0.5f * 0.254829592f);
+    q *= t;
+    const float u = ax * 0.84932180028801904272f;               // sqrt(log2(e) / 2): exp(-x^2 / 2) = 2^(-u^2)
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-u * u));
+    return fmaf(-(ax * e), q, fmaxf(x, 0.0f));
 }
 
 __global__ void __maxnreg__(96)
@@ -98,7 +100,7 @@ mlp_umma_kernel(const __grid_constant__ CUtensorMap tmap_ctx, const __grid_const
         umma::prefetch_tensormap(&tmap_ctx); umma::prefetch_tensormap(&tmap_v);
         umma::prefetch_tensormap(&tmap_w1); umma::prefetch_tensormap(&tmap_w2);
         for (int b = 0; b < 2; ++b) { umma::mbar_init(&full1[b], 1); umma::mbar_init(&empty1[b], 1); }
-        umma::mbar_init(acc1_full, 1); umma::mbar_init(a2_full, kMlpEpiThreads); umma::mbar_init(acc2_full, 1); umma::mbar_init(wbar, 1);
+        umma::mbar_init(acc1_full, 1); umma::mbar_init(a2_full, kMlpEpiWarps); umma::mbar_init(acc2_full, 1); umma::mbar_init(wbar, 1);
         umma::fence_barrier_init();
     }
     if (warp == 1) umma::tmem_alloc(tmem_ptr, 512);
@@ -216,7 +218,8 @@ mlp_umma_kernel(const __grid_constant__ CUtensorMap tmap_ctx, const __grid_const
             }
             umma::fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
             umma::tc_fence_before();
-            umma::mbar_arrive(a2_full);
+            __syncwarp();
+            if (lane == 0) umma::mbar_arrive(a2_full);        // one arrival per warp: 16 instead of 512 on the same barrier word
             // ---------------- epilogue 2: dec_row bias, LayerNorm(W) per split, scales, channels-last store ----------------
             umma::mbar_wait(acc2_full, tphase);
             umma::tc_fence_after();
