@@ -56,21 +56,27 @@ struct PerfSmem {
 };
 
 // ---- cooperative loads -------------------------------------------------------------------------------------------
+// The fp32 operands (projection, positional embedding, prefixed state) go through registers to be rounded to bf16.  Their
+// loads are split into an "issue" and a "commit" half so that a kernel can put ALL of its global loads in flight before it
+// consumes the first one: one DRAM round trip per CTA instead of one per operand (the CTAs are latency-bound at 2 per SM).
 template <int kFp>
-__device__ __forceinline__ void load_proj(__nv_bfloat16* Ps, const float* __restrict__ proj, int F) {
-    // [F x 64] fp32 -> bf16 [kFp x kLdQ]; all of a thread's 16-byte loads are issued before the first conversion
-    constexpr int kVec = kFp * kDm / 4, kIt = (kVec + kThreads - 1) / kThreads;
-    float4 p[kIt];
+struct ProjRegs { static constexpr int kVec = kFp * kDm / 4, kIt = (kVec + kThreads - 1) / kThreads; float4 p[kIt]; };
+template <int kFp>
+__device__ __forceinline__ void issue_proj(ProjRegs<kFp>& r, const float* __restrict__ proj, int F) {
 #pragma unroll
-    for (int it = 0; it < kIt; ++it) {
+    for (int it = 0; it < ProjRegs<kFp>::kIt; ++it) {
         const int idx = threadIdx.x + it * kThreads, f = idx / (kDm / 4);
-        p[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (idx < kVec && f < F) p[it] = __ldg(reinterpret_cast<const float4*>(proj) + idx);
+        r.p[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (idx < ProjRegs<kFp>::kVec && f < F) r.p[it] = __ldg(reinterpret_cast<const float4*>(proj) + idx);
     }
+}
+template <int kFp>
+__device__ __forceinline__ void commit_proj(__nv_bfloat16* Ps, const ProjRegs<kFp>& r) {      // [F x 64] fp32 -> bf16 [kFp x kLdQ]
 #pragma unroll
-    for (int it = 0; it < kIt; ++it) {
+    for (int it = 0; it < ProjRegs<kFp>::kIt; ++it) {
         const int idx = threadIdx.x + it * kThreads, f = idx / (kDm / 4), c4 = idx % (kDm / 4);
-        if (idx < kVec) *reinterpret_cast<uint2*>(Ps + f * kLdQ + c4 * 4) = make_uint2(pack_bf16(p[it].x, p[it].y), pack_bf16(p[it].z, p[it].w));
+        if (idx < ProjRegs<kFp>::kVec)
+            *reinterpret_cast<uint2*>(Ps + f * kLdQ + c4 * 4) = make_uint2(pack_bf16(r.p[it].x, r.p[it].y), pack_bf16(r.p[it].z, r.p[it].w));
     }
 }
 // 16-byte asynchronous global->shared copy (LDGSTS); src_bytes = 0 zero-fills the destination
@@ -91,29 +97,29 @@ __device__ __forceinline__ void load_rows_bf16(__nv_bfloat16* dst, int ld, const
         cp_async16(dst + r * ld + c8 * 8, src + (int64_t) (r0 + (ok ? r : 0)) * row_stride + c8 * 8, ok ? 16 : 0);
     }
 }
-__device__ __forceinline__ void load_v2ext(__nv_bfloat16* Vs, const __nv_bfloat16* __restrict__ v, int64_t v_st, const float* __restrict__ pos,
-                                           int r0, int nvalid) {
-    load_rows_bf16(Vs + kDm, kLdV, v, v_st, r0, nvalid);      // v -> cols 64..127 (async)
-    {   // pos_emb (fp32) -> cols 0..63
-        constexpr int kIt = kCh * (kDm / 4) / kThreads;
-        float4 p[kIt];
+struct PosRegs { static constexpr int kIt = kCh * (kDm / 4) / kThreads; float4 p[kIt]; };
+// V2ext = [pos_emb | v | 1 0 ...]: v -> cols 64..127 by cp.async, pos_emb (fp32) -> registers
+__device__ __forceinline__ void issue_v2ext(PosRegs& r, __nv_bfloat16* Vs, const __nv_bfloat16* __restrict__ v, int64_t v_st,
+                                            const float* __restrict__ pos, int r0, int nvalid) {
+    load_rows_bf16(Vs + kDm, kLdV, v, v_st, r0, nvalid);
 #pragma unroll
-        for (int it = 0; it < kIt; ++it) {
-            const int idx = threadIdx.x + it * kThreads, r = idx >> 4, c4 = idx & 15;
-            p[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (r < nvalid) p[it] = __ldg(reinterpret_cast<const float4*>(pos + (int64_t) (r0 + r) * kDm) + c4);
-        }
+    for (int it = 0; it < PosRegs::kIt; ++it) {
+        const int idx = threadIdx.x + it * kThreads, row = idx >> 4, c4 = idx & 15;
+        r.p[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row < nvalid) r.p[it] = __ldg(reinterpret_cast<const float4*>(pos + (int64_t) (r0 + row) * kDm) + c4);
+    }
+}
+__device__ __forceinline__ void commit_v2ext(__nv_bfloat16* Vs, const PosRegs& r, int nvalid) {
 #pragma unroll
-        for (int it = 0; it < kIt; ++it) {
-            const int idx = threadIdx.x + it * kThreads, r = idx >> 4, c4 = idx & 15;
-            *reinterpret_cast<uint2*>(Vs + r * kLdV + c4 * 4) = make_uint2(pack_bf16(p[it].x, p[it].y), pack_bf16(p[it].z, p[it].w));
-        }
+    for (int it = 0; it < PosRegs::kIt; ++it) {                                // pos_emb -> cols 0..63
+        const int idx = threadIdx.x + it * kThreads, row = idx >> 4, c4 = idx & 15;
+        *reinterpret_cast<uint2*>(Vs + row * kLdV + c4 * 4) = make_uint2(pack_bf16(r.p[it].x, r.p[it].y), pack_bf16(r.p[it].z, r.p[it].w));
     }
     for (int idx = threadIdx.x; idx < kCh * 3; idx += kThreads) {             // cols 128..151: ones column then zeros
-        const int r = idx / 3, part = idx % 3;
+        const int row = idx / 3, part = idx % 3;
         uint4 val = make_uint4(0, 0, 0, 0);
-        if (part == 0 && r < nvalid) val.x = 0x00003F80u;                      // bf16(1.0) at column 128
-        *reinterpret_cast<uint4*>(Vs + r * kLdV + kE + part * 8) = val;
+        if (part == 0 && row < nvalid) val.x = 0x00003F80u;                    // bf16(1.0) at column 128
+        *reinterpret_cast<uint4*>(Vs + row * kLdV + kE + part * 8) = val;
     }
 }
 
@@ -153,9 +159,15 @@ performer_sums_mma_kernel(const __nv_bfloat16* __restrict__ k, int64_t k_sn, int
     const int chunk = blockIdx.x, nh = blockIdx.y, n = nh / H, h = nh % H;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tq = lane & 3;
     const int r0 = chunk * kCh, nvalid = min(kCh, T - r0);
-    load_proj<kFp>(Ps, proj, F);
-    load_rows_bf16(Ks, kLdQ, k + (int64_t) n * k_sn + (int64_t) h * k_sh, k_st, r0, nvalid);
-    load_v2ext(Vs, v + (int64_t) n * v_sn + (int64_t) h * v_sh, v_st, pos_emb, r0, nvalid);
+    {   // all global loads in flight first (cp.async tiles + both register batches), then the bf16 roundings
+        ProjRegs<kFp> pr;
+        PosRegs po;
+        load_rows_bf16(Ks, kLdQ, k + (int64_t) n * k_sn + (int64_t) h * k_sh, k_st, r0, nvalid);
+        issue_v2ext(po, Vs, v + (int64_t) n * v_sn + (int64_t) h * v_sh, v_st, pos_emb, r0, nvalid);
+        issue_proj<kFp>(pr, proj, F);
+        commit_v2ext(Vs, po, nvalid);
+        commit_proj<kFp>(Ps, pr);
+    }
     cp_async_wait_all();
     __syncthreads();
     const float norm = rsqrtf(sqrtf((float) kDm));
@@ -236,11 +248,13 @@ performer_out_mma_kernel(const __nv_bfloat16* __restrict__ q, int64_t q_sn, int6
     const int chunk = blockIdx.x, nh = blockIdx.y, n = nh / H, h = nh % H;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tq = lane & 3;
     const int r0 = chunk * kCh, nvalid = min(kCh, T - r0);
-    load_proj<kFp>(Ps, proj, F);
-    load_rows_bf16(Qs, kLdQ, q + (int64_t) n * q_sn + (int64_t) h * q_sh, q_st, r0, nvalid);
-    load_rows_bf16(Ks, kLdQ, k + (int64_t) n * k_sn + (int64_t) h * k_sh, k_st, r0, nvalid);
-    load_v2ext(Vs, v + (int64_t) n * v_sn + (int64_t) h * v_sh, v_st, pos_emb, r0, nvalid);
-    {   // S_prev (exclusive prefix, fp32) -> bf16; the z column gets the +1e-6 of the reference's denominator
+    {   // all global loads in flight first: q/k/v tiles by cp.async, then the three fp32 register batches (S_prev, pos_emb,
+        // projection); only then the bf16 roundings -- one DRAM round trip per CTA instead of three
+        load_rows_bf16(Qs, kLdQ, q + (int64_t) n * q_sn + (int64_t) h * q_sh, q_st, r0, nvalid);
+        load_rows_bf16(Ks, kLdQ, k + (int64_t) n * k_sn + (int64_t) h * k_sh, k_st, r0, nvalid);
+        PosRegs po;
+        issue_v2ext(po, Vs, v + (int64_t) n * v_sn + (int64_t) h * v_sh, v_st, pos_emb, r0, nvalid);
+        // S_prev (exclusive prefix, fp32) -> bf16; the z column gets the +1e-6 of the reference's denominator
         const float* slot = ws + ((int64_t) nh * nchunks + chunk) * (kFp * kEx);
         constexpr int kVec = kFp * kEx / 4, kIt = (kVec + kThreads - 1) / kThreads;      // kEx % 4 == 0: a float4 never straddles rows
         float4 sv[kIt];
@@ -249,6 +263,9 @@ performer_out_mma_kernel(const __nv_bfloat16* __restrict__ q, int64_t q_sn, int6
             const int idx = threadIdx.x + it * kThreads;
             sv[it] = idx < kVec ? __ldcg(reinterpret_cast<const float4*>(slot) + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
+        ProjRegs<kFp> pr;
+        issue_proj<kFp>(pr, proj, F);
+        commit_v2ext(Vs, po, nvalid);
 #pragma unroll
         for (int it = 0; it < kIt; ++it) {
             const int idx = threadIdx.x + it * kThreads;
@@ -259,6 +276,7 @@ performer_out_mma_kernel(const __nv_bfloat16* __restrict__ q, int64_t q_sn, int6
             }
         }
         for (int idx = threadIdx.x; idx < kFp; idx += kThreads) *reinterpret_cast<uint4*>(Ss + idx * kLdV + kEx) = make_uint4(0, 0, 0, 0);
+        commit_proj<kFp>(Ps, pr);
     }
     cp_async_wait_all();
     __syncthreads();
