@@ -13,6 +13,7 @@
 // Warp-level mma.sync.m16n8k16 (bf16 in, fp32 accumulate) + ldmatrix: the FLOPs here are ~13 GF per layer, the stage is
 // bound by HBM and launch latency, not by the tensor pipe; tcgen05 would not change the roofline.
 // Reference: performer_pytorch.FastAttention call sites attention.py:159-164, 504-508, 527-534; running mean :1237-1241.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace sea {
@@ -379,6 +380,42 @@ performer_out_mma_kernel(const __nv_bfloat16* __restrict__ q, int64_t q_sn, int6
         if (row_lo < nvalid) *reinterpret_cast<uint32_t*>(cb + (int64_t) row_lo * kE + e0) = pack_bf16(O[nt][0] * inv_lo, O[nt][1] * inv_lo);
         if (row_hi < nvalid) *reinterpret_cast<uint32_t*>(cb + (int64_t) row_hi * kE + e0) = pack_bf16(O[nt][2] * inv_hi, O[nt][3] * inv_hi);
     }
+    // a13 running mean of v (attention.py:1237-1241), fused: cumavg[t] = (vsum_prev(chunk) + sum_{j <= t in chunk} v_j) / (t + 1).
+    // The in-chunk cumulative sum is L . V with L the lower-triangular ones matrix: the same V fragments as above against an
+    // all-ones A fragment (triangular on the diagonal tile); bf16 ones x bf16 v accumulate exactly in fp32.  vsum_prev is row F
+    // (the ones feature) of the prefixed state, columns 64..127, read in fp32 from the workspace.
+    if (cumavg != nullptr) {
+        float C[kDm / 8][4];
+#pragma unroll
+        for (int nt = 0; nt < kDm / 8; ++nt)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) C[nt][i] = 0.f;
+        constexpr uint32_t kOne2 = 0x3F803F80u;                    // two bf16 ones
+        for (int jt = 0; jt <= warp; ++jt) {
+            uint32_t la[4] = {kOne2, kOne2, kOne2, kOne2};
+            if (jt == warp) {                                      // diagonal tile: source column <= query row
+                const uint32_t tri = ((2 * tq <= g) ? 0x00003F80u : 0u) | ((2 * tq + 1 <= g) ? 0x3F800000u : 0u);
+                la[0] = tri; la[1] = kOne2; la[2] = 0u; la[3] = tri;
+            }
+#pragma unroll
+            for (int np = 0; np < kDm / 16; ++np) {
+                uint32_t b[4];
+                ldsm_x4_t(b, smem_u32(Vs + (jt * 16 + vr) * kLdV + kDm + np * 16 + vc));
+                mma16816(C[2 * np], la, b[0], b[1]);
+                mma16816(C[2 * np + 1], la, b[2], b[3]);
+            }
+        }
+        const float* vprev = ws + (((int64_t) nh * nchunks + chunk) * kFp + F) * kEx + kDm;
+        const float r_lo = 1.0f / (float) (r0 + row_lo + 1), r_hi = 1.0f / (float) (r0 + row_hi + 1);
+        __nv_bfloat16* ab = cumavg + (((int64_t) n * H + h) * T + r0) * kDm;
+#pragma unroll
+        for (int nt = 0; nt < kDm / 8; ++nt) {
+            const int e0 = nt * 8 + 2 * tq;
+            const float2 pv = __ldcg(reinterpret_cast<const float2*>(vprev + e0));
+            if (row_lo < nvalid) *reinterpret_cast<uint32_t*>(ab + (int64_t) row_lo * kDm + e0) = pack_bf16((C[nt][0] + pv.x) * r_lo, (C[nt][1] + pv.y) * r_lo);
+            if (row_hi < nvalid) *reinterpret_cast<uint32_t*>(ab + (int64_t) row_hi * kDm + e0) = pack_bf16((C[nt][2] + pv.x) * r_hi, (C[nt][3] + pv.y) * r_hi);
+        }
+    }
 }
 
 // a13 running mean of v (attention.py:1237-1241): cumavg[t] = (vsum_prev(chunk) + sum_{j<=t in chunk} v_j) / (t+1).
@@ -455,7 +492,9 @@ int launch_performer_mma(const void* q, int64_t q_sn, int64_t q_sh, int64_t q_st
     kc<<<grid, kThreads, SM::kBytes, s>>>((const B*) q, q_sn, q_sh, q_st, (const B*) k, k_sn, k_sh, k_st, (const B*) v, v_sn, v_sh, v_st,
                                           pos_emb, proj, ws, (B*) ctx, (B*) cumavg, H, T, F, nchunks);
     SEA_CHECK_LAUNCH("performer_out_mma_kernel");
-    if (cumavg != nullptr) {
+    // (the running mean of v is produced by performer_out_mma_kernel; cumavg_kernel stays as the stand-alone version)
+    static const bool separate_cumavg = getenv("SEA_CUMAVG_SEPARATE") != nullptr;      // development switch for A/B timing
+    if (cumavg != nullptr && separate_cumavg) {
         cumavg_kernel<kFp><<<grid, 1024, 0, s>>>((const B*) v, v_sn, v_sh, v_st, ws, (B*) cumavg, H, T, F, nchunks);
         SEA_CHECK_LAUNCH("cumavg_kernel");
     }
