@@ -387,7 +387,7 @@ def main():
             sb['attn'] = sb['attn'] - Z * 4 + N * T * H * P // 8
         sf = stage_flops(N, H, d, T, P, k, F, Z)
         entry_stage = {'sea_performer_causal_fwd': 'performer', 'sea_predictor_mlp_fwd': 'mlp', 'sea_causal_conv3x3_dil2_relu': 'conv',
-                       'sea_causal_conv3x3_dil2_relu_umma': 'conv', 'sea_conv1x1_umma': 'tail', 'sea_predictor_tail_topk_fwd': 'tail', 'sea_predictor_tail_topk_expand_fwd': 'tail',
+                       'sea_causal_conv3x3_dil2_relu_umma': 'conv', 'sea_conv1x1_umma': 'tail', 'sea_causal_conv3x3_dil2_relu_conv1x1_umma': 'conv', 'sea_predictor_tail_topk_fwd': 'tail', 'sea_predictor_tail_topk_expand_fwd': 'tail',
                        'sea_predictor_mlp_umma_fwd': 'mlp', 'sea_predictor_mlp_umma_fwd_ex': 'mlp', 'sea_performer_causal_mma_fwd': 'performer',
                        'sea_predictor_tail_fwd': 'tail', 'sea_topk_mask_bits': 'topk', 'sea_csr_count': 'csr', 'sea_csr_fill': 'csr', 'sea_crow_scan': 'csr',
                        'sea_sparse_attention_fwd': 'attn', 'sea_sparse_attention_bits_fwd': 'attn', 'sea_block_attention_fwd': 'attn'}

@@ -211,6 +211,15 @@ SEA_API int sea_causal_conv3x3_dil2_relu_umma(const void* x, const float* weight
                                               int N, int T, int W, int C, int O, void* stream);
 SEA_API int sea_conv1x1_umma(const void* x, const float* weight, const float* bias, float* y, void* workspace,
                              int N, int T, int W, int C, int O, void* stream);
+/* The second 3x3 convolution and the 1x1 convolution behind it (attention.py:274-276: CausalConv2d + ReLU, then -- commuted
+ * with the upsample -- CausalConv2d(C, H, 1)) in ONE kernel: y3 [N,T,W,O3] fp32 = conv1x1(relu(conv3x3(x))), the 64-channel
+ * activation between them stays in shared memory / TMEM.  Shapes: W = C = O = 64, O3 = 32 (..._supported() tells).
+ * workspace / workspace3: bf16 weight packings as for the two separate entries (sea_conv_umma_workspace_bytes(C, O) and
+ * (C, O3) bytes); weight == NULL / weight3 == NULL reuse the packing left there by an earlier call. */
+SEA_API int sea_conv3x3_conv1x1_umma_supported(int dtype, int W, int C, int O, int O3);
+SEA_API int sea_causal_conv3x3_dil2_relu_conv1x1_umma(const void* x, const float* weight, const float* bias, void* workspace,
+                                                      const float* weight3, const float* bias3, void* workspace3, float* y3,
+                                                      int N, int T, int W, int C, int O, int O3, void* stream);
 
 /* a5 tail + a6  (attention.py:275-280, 670-673): nearest x4 along W, CausalConv2d(C,H,1,padding=1)
  * (width P+2, the two pad columns equal the bias), area-resize to P, LayerNorm(P), softmax(P).

@@ -332,27 +332,29 @@ class PerlinAttention(nn.Module):
         # models whose 2H != 64 (e.g. OPT-125m, H = 12): run the 64-channel tcgen05 MLP / conv kernels on zero-padded channels
         pad_c = (q.dtype == torch.bfloat16 and d == 64 and S * H < 64 and H <= 32 and P % 32 == 0 and W in (16, 32, 64)
                  and ops.conv_umma_supported(q.dtype, W, 64, 64) and ctx.is_contiguous())
-        if pad_c:
-            wp = self._padded_conv_weights(w, S * H, H)
-            cnn_in, scales, _ = ops.predictor_mlp(ctx, v, w, S, W, packed=pk, c_out=64)
-            y1 = ops.causal_conv3x3_dil2_relu(cnn_in, wp['conv1_w'], wp['conv1_b'], packed=pk, slot='conv1', src=net[0].module.weight)
-            y = ops.causal_conv3x3_dil2_relu(y1, wp['conv2_w'], wp['conv2_b'], packed=pk, slot='conv2', src=net[2].module.weight)
+        # tensor-core tail: 1x1 conv before the upsample (tcgen05), then tail + softmax + top-k in one kernel
+        tc_tail = pad_c or (q.dtype == torch.bfloat16 and ops.conv_umma_supported(q.dtype, W, S * H, H) and P % 32 == 0)
+        cw = self._padded_conv_weights(w, S * H, H) if pad_c else w
+        # ... and where the shape allows (W = 64, 64 -> 64 -> 32 channels) that 1x1 conv runs inside the second 3x3 conv's kernel
+        fuse_c3 = tc_tail and ops.conv3x3_conv1x1_supported(q.dtype, W, 64, cw['conv2_w'].shape[0], cw['conv3_w'].shape[0])
+        y = y3 = None
+        cnn_in, scales, _ = ops.predictor_mlp(ctx, v, w, S, W, packed=pk, **({'c_out': 64} if pad_c else {}))
+        y1 = ops.causal_conv3x3_dil2_relu(cnn_in, cw['conv1_w'], cw['conv1_b'], packed=pk, slot='conv1', src=net[0].module.weight)
+        if fuse_c3:
+            y3 = ops.causal_conv3x3_relu_conv1x1(y1, cw['conv2_w'], cw['conv2_b'], cw['conv3_w'], cw['conv3_b'], packed=pk, slot='conv2',
+                                                 src=net[2].module.weight, slot3='conv3', src3=net[5].module.weight)
         else:
-            cnn_in, scales, _ = ops.predictor_mlp(ctx, v, w, S, W, packed=pk)
-            y1 = ops.causal_conv3x3_dil2_relu(cnn_in, w['conv1_w'], w['conv1_b'], packed=pk, slot='conv1', src=net[0].module.weight)
-            y = ops.causal_conv3x3_dil2_relu(y1, w['conv2_w'], w['conv2_b'], packed=pk, slot='conv2', src=net[2].module.weight)
+            y = ops.causal_conv3x3_dil2_relu(y1, cw['conv2_w'], cw['conv2_b'], packed=pk, slot='conv2', src=net[2].module.weight)
         if capture is not None:
             capture['cnn_in'], capture['conv1'] = cnn_in, y1
         # a5 .. a7
         kpr = k_per_row.repeat(N) if N > 1 else k_per_row
         expanded_ws = None
-        if pad_c or (q.dtype == torch.bfloat16 and ops.conv_umma_supported(q.dtype, W, S * H, H) and P % 32 == 0):
-            # tensor-core path: 1x1 conv before the upsample (tcgen05), then tail + softmax + top-k in one kernel
+        if tc_tail:
+            if y3 is None:
+                y3 = ops.conv1x1_umma(y, cw['conv3_w'], cw['conv3_b'], packed=pk, slot='conv3', src=net[5].module.weight)
             if pad_c:
-                y3 = ops.conv1x1_umma(y, wp['conv3_w'], wp['conv3_b'], packed=pk, slot='conv3', src=net[5].module.weight)
                 y3 = y3[..., :H].contiguous()
-            else:
-                y3 = ops.conv1x1_umma(y, w['conv3_w'], w['conv3_b'], packed=pk, slot='conv3', src=net[5].module.weight)
             needs_grad = torch.is_grad_enabled() and any(t_.requires_grad for t_ in (q_for_score, k_for_score, v))
             if (self.fuse_mask_expansion and not self.output_attentions and not needs_grad and ops.attention_bits_supported(q.dtype, d, P)
                     and ops.tail_expand_supported(H, P)):

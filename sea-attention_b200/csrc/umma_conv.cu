@@ -267,15 +267,22 @@ constexpr int kRingEpiWarps = 8, kRingThreads = 64 + 32 * kRingEpiWarps;      //
 struct RingSmem {
     static constexpr int kWBytes = 9 * 64 * 128;
     static constexpr int kRingOff = kWBytes;
-    static constexpr int kBarOff = kRingOff + kRingPos * kPairSlot;
+    static constexpr int kW3Off = kRingOff + kRingPos * kPairSlot;          // fused 1x1: [32 out][64 in] bf16, K-major SW128 (4 KB)
+    static constexpr int kA2Off = kW3Off + 4096;                            // fused 1x1: two 128 x 64 bf16 activation tiles
+    static constexpr int kBarOff = kA2Off + 2 * kATileBytes;
     static constexpr int kBiasOff = kBarOff + 256;
-    static constexpr int kTotal = kBiasOff + 256 + 1024;
+    static constexpr int kTotal = kBiasOff + 512 + 1024;      // 64 + 32 bias floats
 };
 
-template <bool kRelu>
+// kFuse1x1: the 1x1 convolution that follows the second 3x3 convolution (64 -> 32 channels, no activation) runs in the same
+// kernel: the epilogue warps write the ReLU'd bf16 tile into shared memory in the K-major SW128 layout instead of global
+// memory, the MMA warp multiplies it with the 32 x 64 weight (4 MMAs, N = 32) into a second TMEM accumulator one tile behind
+// the main chain, and a second epilogue pass stores fp32 [pixel][32].  The 64-channel activation never reaches HBM.
+template <bool kRelu, bool kFuse1x1>
 __global__ void __launch_bounds__(kRingThreads, 1)
 conv_ring_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
-                      const float* __restrict__ bias, __nv_bfloat16* __restrict__ y, int N, int T, int PT, int pairs_per_cta) {
+                      const __grid_constant__ CUtensorMap tmap_w3, const float* __restrict__ bias, const float* __restrict__ bias3,
+                      __nv_bfloat16* __restrict__ y, float* __restrict__ y3, int N, int T, int PT, int pairs_per_cta) {
     constexpr int kNOut = 64, W = 64;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -286,9 +293,14 @@ conv_ring_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
     uint64_t* tmem_full = empty + kRingPos;                        // [kRingAcc]
     uint64_t* tmem_empty = tmem_full + kRingAcc;                   // [kRingAcc]
     uint64_t* wbar = tmem_empty + kRingAcc;
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(wbar + 1);
+    uint64_t* a2_full = wbar + 1;                                  // [2]  (fused 1x1) activation tile written by the epilogue warps
+    uint64_t* acc2_full = a2_full + 2;                             // [2]  (fused 1x1) second accumulator complete
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc2_full + 2);
+    uint8_t* w3sm = smem + RingSmem::kW3Off;
+    uint8_t* a2sm = smem + RingSmem::kA2Off;
     float* s_bias = reinterpret_cast<float*>(smem + RingSmem::kBiasOff);
     if (threadIdx.x < kNOut) s_bias[threadIdx.x] = bias[threadIdx.x];
+    if (kFuse1x1 && threadIdx.x >= 64 && threadIdx.x < 96) s_bias[64 + threadIdx.x - 64] = bias3[threadIdx.x - 64];
     // the shuffle makes the warp index provably warp-uniform, so the role branches below stay in the uniform datapath
     const int warp = __shfl_sync(0xffffffffu, (int) (threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const int G = N * PT;
@@ -299,9 +311,11 @@ conv_ring_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
         for (int p = 0; p < kRingPos; ++p) { umma::mbar_init(&full[p], 1); umma::mbar_init(&empty[p], 1); }
         for (int a = 0; a < kRingAcc; ++a) { umma::mbar_init(&tmem_full[a], 1); umma::mbar_init(&tmem_empty[a], 32 * kRingEpiWarps); }
         umma::mbar_init(wbar, 1);
+        for (int a = 0; a < 2; ++a) { umma::mbar_init(&a2_full[a], kRingEpiWarps); umma::mbar_init(&acc2_full[a], 1); }
         umma::fence_barrier_init();
     }
-    if (warp == 1) umma::tmem_alloc(tmem_ptr, kRingAcc * kNOut);
+    constexpr uint32_t kTmemCols = kFuse1x1 ? 512 : kRingAcc * kNOut;       // + 2 x 32 columns for the 1x1 accumulators
+    if (warp == 1) umma::tmem_alloc(tmem_ptr, kTmemCols);
     umma::tc_fence_before();
     __syncthreads();
     umma::tc_fence_after();
@@ -309,8 +323,9 @@ conv_ring_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
 
     if (warp == 0) {
         if (lane == 0 && g_begin < g_end) {
-            umma::mbar_arrive_expect_tx(wbar, RingSmem::kWBytes);
+            umma::mbar_arrive_expect_tx(wbar, RingSmem::kWBytes + (kFuse1x1 ? 4096 : 0));
             for (int tap = 0; tap < 9; ++tap) umma::tma_load_2d(wsm + tap * kNOut * 128, &tmap_w, wbar, 0, tap * kNOut);
+            if (kFuse1x1) umma::tma_load_2d(w3sm, &tmap_w3, wbar, 0, 0);
             int pos = 0, round = 0;                      // ring position / how many times the ring has wrapped
             for (int g0 = g_begin; g0 < g_end;) {
                 const int n = g0 / PT, k0 = g0 % PT;     // one run: tiles [k0, k1) of batch item n
@@ -332,12 +347,30 @@ conv_ring_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
             constexpr uint32_t idesc = umma::make_idesc_bf16(128, kNOut);
             const uint64_t a_base = umma::make_desc_k_sw128(umma::smem_u32(ring));
             const uint64_t b_base = umma::make_desc_k_sw128(umma::smem_u32(wsm));
+            constexpr uint32_t idesc3 = umma::make_idesc_bf16(128, 32);
+            const uint64_t a2_base = umma::make_desc_k_sw128(umma::smem_u32(a2sm));
+            const uint64_t w3_base = umma::make_desc_k_sw128(umma::smem_u32(w3sm));
+            int done2 = 0;                                // tiles whose 1x1 MMAs have been issued
+            auto issue_1x1 = [&](int c) {                 // D2[128 x 32] = relu(conv2 tile c)[128 x 64] . W3^T
+                const int b2 = c & 1;
+                umma::mbar_wait(&a2_full[b2], (uint32_t) ((c >> 1) & 1));
+                umma::tc_fence_after();
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                    umma::mma_bf16_ss_elect(tmem_base + (uint32_t) (kRingAcc * kNOut + 32 * b2), a2_base + (uint64_t) (b2 * (kATileBytes >> 4) + kk * 2),
+                                            w3_base + (uint64_t) (kk * 2), idesc3, (uint32_t) (kk != 0));
+                umma::mma_commit_elect(&acc2_full[b2]);
+            };
             umma::mbar_wait(wbar, 0);
             int pos = 0, round = 0, c_base = 0;           // c_base: tiles of this CTA that belong to earlier runs
             for (int g0 = g_begin; g0 < g_end;) {
                 const int k0 = g0 % PT;
                 const int k1 = min(PT, k0 + (g_end - g0));
                 for (int pk = k0 - 2; pk < k1; ++pk) {
+                    if (kFuse1x1) {                       // one tile behind the main chain: its activation tile is long written
+                        const int completed = c_base + max(pk - k0, 0);
+                        while (done2 < completed - 1) issue_1x1(done2++);
+                    }
                     umma::mbar_wait(&full[pos], (uint32_t) (round & 1));
                     umma::tc_fence_after();
                     const uint64_t a_pos = a_base + (uint64_t) (pos * (kPairSlot >> 4));
@@ -370,6 +403,7 @@ conv_ring_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
                 c_base += k1 - k0;
                 g0 += k1 - k0;
             }
+            if (kFuse1x1) while (done2 < c_base) issue_1x1(done2++);
         }
     } else {
         // Eight epilogue warps: warp % 4 is the TMEM lane quarter the hardware lets a warp read, (warp - 2) / 4 the column
@@ -379,6 +413,28 @@ conv_ring_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
         const int row = q * 32 + lane;                // TMEM lane = pixel (t0 + (row & 1), row >> 1)
         const int c0 = half * 32;
         const float4* b4 = reinterpret_cast<const float4*>(s_bias + c0);
+        auto finish_1x1 = [&](int c) {                // second epilogue pass of tile c: 16 of the 32 output channels per thread
+            const int gg = g_begin + c, n2 = gg / PT, t2 = (gg % PT) * 2 + (row & 1);
+            umma::mbar_wait(&acc2_full[c & 1], (uint32_t) ((c >> 1) & 1));
+            umma::tc_fence_after();
+            uint32_t r2[16];
+            umma::tmem_ld_32x16(tmem_base + ((uint32_t) (q * 32) << 16) + (uint32_t) (kRingAcc * kNOut + 32 * (c & 1) + 16 * half), r2);
+            umma::tmem_ld_wait();
+            const float4* b3 = reinterpret_cast<const float4*>(s_bias + 64 + 16 * half);
+            float* dst = y3 + ((((int64_t) n2 * T + t2) * W) + (row >> 1)) * 32 + 16 * half;
+            if (t2 < T) {
+#pragma unroll
+                for (int hv = 0; hv < 2; ++hv) {
+                    const float4 ba = b3[2 * hv], bb = b3[2 * hv + 1];
+                    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst + 8 * hv),
+                                 "f"(__uint_as_float(r2[8 * hv]) + ba.x), "f"(__uint_as_float(r2[8 * hv + 1]) + ba.y),
+                                 "f"(__uint_as_float(r2[8 * hv + 2]) + ba.z), "f"(__uint_as_float(r2[8 * hv + 3]) + ba.w),
+                                 "f"(__uint_as_float(r2[8 * hv + 4]) + bb.x), "f"(__uint_as_float(r2[8 * hv + 5]) + bb.y),
+                                 "f"(__uint_as_float(r2[8 * hv + 6]) + bb.z), "f"(__uint_as_float(r2[8 * hv + 7]) + bb.w)
+                                 : "memory");
+                }
+            }
+        };
         for (int g = g_begin; g < g_end; ++g) {
             const int n = g / PT, t0 = (g % PT) * 2;
             const int c = g - g_begin, acc = c & (kRingAcc - 1);
@@ -402,25 +458,43 @@ conv_ring_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
                 o[2 * i] = *reinterpret_cast<uint32_t*>(&p0);
                 o[2 * i + 1] = *reinterpret_cast<uint32_t*>(&p1);
             }
-            if (ok) {
+            if (!kFuse1x1) {
+                if (ok) {
 #pragma unroll
-                for (int hv = 0; hv < 2; ++hv)
-                    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(gout + hv * 32), "r"(o[8 * hv]), "r"(o[8 * hv + 1]),
-                                 "r"(o[8 * hv + 2]), "r"(o[8 * hv + 3]), "r"(o[8 * hv + 4]), "r"(o[8 * hv + 5]), "r"(o[8 * hv + 6]), "r"(o[8 * hv + 7])
-                                 : "memory");
+                    for (int hv = 0; hv < 2; ++hv)
+                        asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(gout + hv * 32), "r"(o[8 * hv]), "r"(o[8 * hv + 1]),
+                                     "r"(o[8 * hv + 2]), "r"(o[8 * hv + 3]), "r"(o[8 * hv + 4]), "r"(o[8 * hv + 5]), "r"(o[8 * hv + 6]), "r"(o[8 * hv + 7])
+                                     : "memory");
+                }
+            } else {
+                // activation tile c -> shared memory, K-major SW128: row = TMEM lane, 16-byte chunk ch at (ch ^ (row & 7)); this
+                // buffer was last read by the 1x1 MMAs of tile c-2, whose completion this warp awaited in finish_1x1(c-2)
+                uint8_t* arow = a2sm + (c & 1) * kATileBytes + row * 128;
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch)
+                    *reinterpret_cast<uint4*>(arow + (((half * 4 + ch) ^ (row & 7)) << 4)) = make_uint4(o[4 * ch], o[4 * ch + 1], o[4 * ch + 2], o[4 * ch + 3]);
+                umma::fence_proxy_async();            // generic-proxy smem writes -> visible to the tensor core (async proxy)
+                umma::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) umma::mbar_arrive(&a2_full[c & 1]);
+                if (c > 0) finish_1x1(c - 1);
             }
         }
+        if (kFuse1x1 && g_begin < g_end) finish_1x1(g_end - g_begin - 1);
     }
     umma::tc_fence_before();
     __syncthreads();
     if (warp == 1) {
         umma::tc_fence_after();
-        umma::tmem_dealloc(tmem_base, kRingAcc * kNOut);
+        umma::tmem_dealloc(tmem_base, kTmemCols);
     }
 }
 
+struct Fuse1x1 { const float* w3; const float* b3; void* ws3; float* y3; };      // the 1x1 conv fused behind a 3x3 conv (ring kernel only)
+
 template <int kTaps, int kNOut, bool kRelu, typename OutT>
-int launch_conv_umma(const void* x, const float* weight, const float* bias, void* y, void* ws, int N, int T, int W, int C, cudaStream_t s) {
+int launch_conv_umma(const void* x, const float* weight, const float* bias, void* y, void* ws, int N, int T, int W, int C, cudaStream_t s,
+                     const Fuse1x1* fuse = nullptr) {
     using SM = ConvSmem<kTaps, kNOut>;
     __nv_bfloat16* wpack = reinterpret_cast<__nv_bfloat16*>(ws);
     const int nel = kTaps * kNOut * C;
@@ -463,12 +537,32 @@ int launch_conv_umma(const void* x, const float* weight, const float* bias, void
                 int rc = make_tmap_bf16_sw128(&txp, const_cast<void*>(x), 4, dims, strides, box);
                 if (rc) return rc;
             }
-            auto kr = conv_ring_umma_kernel<kRelu>;
-            SEA_CUDA_TRY(cudaFuncSetAttribute(kr, cudaFuncAttributeMaxDynamicSharedMemorySize, RingSmem::kTotal), "smem attr");
-            kr<<<grid_used, kRingThreads, RingSmem::kTotal, s>>>(txp, tw, bias, reinterpret_cast<__nv_bfloat16*>(y), N, T, tblocks, per);
+            if (fuse == nullptr) {
+                auto kr = conv_ring_umma_kernel<kRelu, false>;
+                SEA_CUDA_TRY(cudaFuncSetAttribute(kr, cudaFuncAttributeMaxDynamicSharedMemorySize, RingSmem::kTotal), "smem attr");
+                kr<<<grid_used, kRingThreads, RingSmem::kTotal, s>>>(txp, tw, tw, bias, nullptr, reinterpret_cast<__nv_bfloat16*>(y), nullptr, N, T, tblocks, per);
+            } else {
+                // + the 1x1 convolution 64 -> 32 (fp32 output), its bf16 weight packing [32][64] lives in fuse->ws3
+                __nv_bfloat16* w3pack = reinterpret_cast<__nv_bfloat16*>(fuse->ws3);
+                if (fuse->w3 != nullptr) pack_conv_weights_kernel<<<(32 * 64 + 255) / 256, 256, 0, s>>>(fuse->w3, w3pack, 32, C, 1);
+                SEA_CHECK_LAUNCH("pack_conv_weights_kernel");
+                CUtensorMap tw3;
+                const uint64_t dims[2] = {(uint64_t) C, 32};
+                const uint64_t strides[1] = {(uint64_t) C * 2};
+                const uint32_t box[2] = {64, 32};
+                int rc = make_tmap_bf16_sw128(&tw3, w3pack, 2, dims, strides, box);
+                if (rc) return rc;
+                auto kr = conv_ring_umma_kernel<kRelu, true>;
+                SEA_CUDA_TRY(cudaFuncSetAttribute(kr, cudaFuncAttributeMaxDynamicSharedMemorySize, RingSmem::kTotal), "smem attr");
+                kr<<<grid_used, kRingThreads, RingSmem::kTotal, s>>>(txp, tw, tw3, bias, fuse->b3, nullptr, fuse->y3, N, T, tblocks, per);
+            }
             SEA_CHECK_LAUNCH("conv_ring_umma_kernel");
             return SEA_OK;
         }
+    }
+    if (fuse != nullptr) {
+        set_error("conv3x3 + conv1x1 fusion needs the row-pair ring kernel (W = 64)");
+        return SEA_ERR_UNSUPPORTED;
     }
     auto kern = conv_umma_kernel<kTaps, kNOut, kRelu, OutT>;
     SEA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kTotal), "smem attr");
@@ -502,6 +596,25 @@ int sea_causal_conv3x3_dil2_relu_umma(const void* x, const float* weight, const 
     SEA_CHECK_ARG((((uintptr_t) x) & 127) == 0 && (((uintptr_t) y) & 15) == 0 && (((uintptr_t) workspace) & 127) == 0,
                   "sea_causal_conv3x3_dil2_relu_umma: misaligned pointer");
     return launch_conv_umma<9, 64, true, __nv_bfloat16>(x, weight, bias, y, workspace, N, T, W, C, (cudaStream_t) stream);
+}
+
+int sea_conv3x3_conv1x1_umma_supported(int dtype, int W, int C, int O, int O3) {
+    return dtype == SEA_DTYPE_BF16 && W == 64 && C == 64 && O == 64 && O3 == 32 && getenv("SEA_CONV_NO_RING") == nullptr;
+}
+
+int sea_causal_conv3x3_dil2_relu_conv1x1_umma(const void* x, const float* weight, const float* bias, void* workspace,
+                                              const float* weight3, const float* bias3, void* workspace3, float* y3,
+                                              int N, int T, int W, int C, int O, int O3, void* stream) {
+    SEA_CHECK_ARG(x && bias && workspace && bias3 && workspace3 && y3, "sea_causal_conv3x3_dil2_relu_conv1x1_umma: null pointer");
+    SEA_CHECK_ARG(N > 0 && T > 0, "sea_causal_conv3x3_dil2_relu_conv1x1_umma: bad shape");
+    if (!sea_conv3x3_conv1x1_umma_supported(SEA_DTYPE_BF16, W, C, O, O3)) {
+        set_error("sea_causal_conv3x3_dil2_relu_conv1x1_umma: unsupported shape W=%d C=%d O=%d O3=%d (need W=C=O=64, O3=32)", W, C, O, O3);
+        return SEA_ERR_UNSUPPORTED;
+    }
+    SEA_CHECK_ARG((((uintptr_t) x) & 127) == 0 && (((uintptr_t) y3) & 31) == 0 && (((uintptr_t) workspace) & 127) == 0 && (((uintptr_t) workspace3) & 127) == 0,
+                  "sea_causal_conv3x3_dil2_relu_conv1x1_umma: misaligned pointer");
+    const Fuse1x1 fuse{weight3, bias3, workspace3, y3};
+    return launch_conv_umma<9, 64, true, __nv_bfloat16>(x, weight, bias, nullptr, workspace, N, T, W, C, (cudaStream_t) stream, &fuse);
 }
 
 int sea_conv1x1_umma(const void* x, const float* weight, const float* bias, float* y, void* workspace,

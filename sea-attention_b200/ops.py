@@ -370,6 +370,26 @@ def conv1x1_umma(x, weight, bias, packed: 'PackedWeights' = None, slot: str = 'c
     return y
 
 
+def conv3x3_conv1x1_supported(dtype, W: int, C: int, O: int, O3: int) -> bool:
+    return dtype == torch.bfloat16 and bool(_lib.load().sea_conv3x3_conv1x1_umma_supported(_lib.SEA_DTYPE_BF16, W, C, O, O3))
+
+
+def causal_conv3x3_relu_conv1x1(x, weight, bias, weight3, bias3, packed: 'PackedWeights' = None, slot: str = 'conv', src=None,
+                                slot3: str = 'conv1x1', src3=None):
+    """a5: the second CausalConv2d(64,64,3,dilation 2)+ReLU and the 1x1 CausalConv2d(64 -> 32) behind it in one tcgen05 kernel:
+    x bf16 [N,T,W,64] -> y3 fp32 [N,T,W,32]; the activation between the two convolutions never reaches HBM."""
+    _cuda(x, weight, bias, weight3, bias3)
+    N, T, W, C = x.shape
+    O, O3 = weight.shape[0], weight3.shape[0]
+    y3 = torch.empty((N, T, W, O3), dtype=torch.float32, device=x.device)
+    ws, wptr = _packed_conv_ws(packed, slot, weight, src, C, O, x.device)
+    ws3, wptr3 = _packed_conv_ws(packed, slot3, weight3, src3, C, O3, x.device)
+    _lib.call('sea_causal_conv3x3_dil2_relu_conv1x1_umma', x.data_ptr(), wptr, bias.data_ptr(), ws.data_ptr(),
+              wptr3, bias3.data_ptr(), ws3.data_ptr(), y3.data_ptr(), N, T, W, C, O, O3, _stream(),
+              kernels=1 + (wptr is not None) + (wptr3 is not None))
+    return y3
+
+
 def performer_state_new(N: int, H: int, D: int, F: int, device) -> torch.Tensor:
     """Zeroed decode state of the causal Performer + running mean (fp32; S | z | vsum per (n, h))."""
     return torch.zeros((int(_lib.load().sea_performer_state_floats(N, H, D, F)),), dtype=torch.float32, device=device)

@@ -48,6 +48,28 @@ def test_conv1x1_umma_matches_oracle(sea, N, T, W):
     torch.testing.assert_close(y.cpu(), ref, rtol=1e-2, atol=1e-2)
 
 
+@pytest.mark.parametrize('N,T', [(1, 8), (2, 37), (3, 700), (1, 601), (1, 2)])
+def test_conv3x3_conv1x1_fused_matches_separate(sea, N, T):
+    """the second 3x3 conv with the 1x1 conv fused behind it == the two tcgen05 kernels run one after the other (same bf16
+    rounding of the activation between them), and == the oracle within the bf16 tolerance"""
+    W = C = 64
+    g = torch.Generator().manual_seed(T * 3 + N)
+    x = torch.randn(N, T, W, C, generator=g).bfloat16().to(DEV)
+    w2 = torch.zeros(64, C, 5, 3)
+    w2[:, :, :3, :] = torch.randn(64, C, 3, 3, generator=g) * 0.05
+    b2 = torch.randn(64, generator=g) * 0.1
+    w3 = torch.randn(32, 64, generator=g) * 0.1
+    b3 = torch.randn(32, generator=g)
+    assert sea.ops.conv3x3_conv1x1_supported(torch.bfloat16, W, C, 64, 32)
+    y3 = sea.ops.causal_conv3x3_relu_conv1x1(x, w2.to(DEV), b2.to(DEV), w3.to(DEV), b3.to(DEV))
+    y = sea.ops.causal_conv3x3_dil2_relu(x, w2.to(DEV), b2.to(DEV))
+    y3_sep = sea.ops.conv1x1_umma(y, w3.to(DEV), b3.to(DEV))
+    torch.cuda.synchronize()
+    torch.testing.assert_close(y3.cpu(), y3_sep.cpu(), rtol=1e-5, atol=1e-5)
+    ref = _conv_ref(x.float().cpu(), w2.bfloat16().float(), b2).bfloat16().float() @ w3.bfloat16().float().t() + b3
+    torch.testing.assert_close(y3.cpu(), ref, rtol=2e-2, atol=2e-2)
+
+
 @pytest.mark.parametrize('ties', [False, True])
 @pytest.mark.parametrize('N,H,T,W,P,k', [(1, 32, 40, 64, 256, 64), (2, 8, 33, 16, 64, 8), (1, 4, 20, 8, 32, 4), (1, 32, 12, 32, 128, 16),
                                         (1, 32, 300, 64, 256, 8), (1, 16, 90, 64, 256, 16), (1, 12, 50, 64, 256, 64)])
