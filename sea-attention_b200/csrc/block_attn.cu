@@ -337,6 +337,8 @@ __global__ void __launch_bounds__(256)
 expand_mask_kernel(const uint32_t* __restrict__ mask_bits, unsigned long long* __restrict__ dmask, uint32_t* __restrict__ tile_act, int act_words, int W64,
                    int N, int H, int T_DST, int T_SRC, int P, int p_lg, int is_causal) {
     extern __shared__ uint32_t ex_sm[];                   // [H][2 * wneed]
+    pdl_launch_dependents();
+    pdl_wait();
     const int nw = P >> 5;
     const int row = blockIdx.x, n = row / T_DST, t = row % T_DST;
     const int src_off = is_causal ? (T_SRC - T_DST) : 0;
@@ -435,7 +437,8 @@ int sea_block_attention_fwd(const uint32_t* mask_bits,
         const size_t smem = (size_t) H * W64 * 8 + (size_t) H * act_words * 4;
         SEA_CHECK_ARG(smem <= 200 * 1024, "sea_block_attention_fwd: H * T_SRC too large for the mask expansion");
         SEA_CUDA_TRY(cudaFuncSetAttribute(expand_mask_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem), "smem attr");
-        expand_mask_kernel<<<(unsigned) ((int64_t) N * T_DST), 256, smem, s>>>(mask_bits, dmask, tile_act, act_words, W64, N, H, T_DST, T_SRC, P, p_lg, is_causal);
+        SEA_CUDA_TRY(launch_pdl(expand_mask_kernel, dim3((unsigned) ((int64_t) N * T_DST)), dim3(256), (size_t) smem, s, mask_bits, dmask, tile_act, act_words, W64, N, H, T_DST,
+                                T_SRC, P, p_lg, is_causal), "expand_mask_kernel launch");
         SEA_CHECK_LAUNCH("expand_mask_kernel");
     }
     // bf16: the two contractions on tcgen05 / TMEM (block_attn_umma.cu); fp16 (and SEA_ATTN_MMA_SYNC=1, for A/B timing): mma.sync

@@ -98,6 +98,8 @@ block_attention_umma_kernel(const uint32_t* __restrict__ tile_act, int act_words
 
     // warp index (and below the tile count) through a shuffle: provably warp-uniform, which keeps the MMA issue loop in the uniform datapath
     const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    pdl_launch_dependents();
+    pdl_wait();                // the set-up below already reads the tile activity written by the expansion kernel
     const int rb = n_row_blocks - 1 - (int) (blockIdx.x / (unsigned) (N * H));       // heavy (late) row blocks first
     const int nh = (int) (blockIdx.x % (unsigned) (N * H));
     const int n = nh / H, h = nh % H;
@@ -365,9 +367,9 @@ int launch_block_attention_umma(const unsigned long long* dmask, int W64, const 
     const size_t smem = 1024 + (size_t) USmem::kList + (size_t) ((max_tiles + 7) & ~7) * 2;
     const unsigned grid = (unsigned) ((int64_t) n_row_blocks * N * H);
     SEA_CUDA_TRY(cudaFuncSetAttribute(block_attention_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem), "smem attr");
-    block_attention_umma_kernel<<<grid, kUThreads, smem, s>>>(tile_act, act_words, t_q, t_k, t_v, t_m, scales, (const __nv_bfloat16*) cumavg, avg_sh, avg_st,
-                                                              use_scaler, (__nv_bfloat16*) out, N, H, T_DST, T_SRC, is_causal, n_row_blocks, max_tiles);
-    SEA_CHECK_LAUNCH("block_attention_umma_kernel");
+    SEA_CUDA_TRY(launch_pdl(block_attention_umma_kernel, dim3(grid), dim3(kUThreads), (size_t) smem, s, tile_act, act_words, t_q, t_k, t_v, t_m, scales,
+                            (const __nv_bfloat16*) cumavg, avg_sh, avg_st, use_scaler, (__nv_bfloat16*) out, N, H, T_DST, T_SRC, is_causal, n_row_blocks, max_tiles),
+                 "block_attention_umma_kernel launch");
     return SEA_OK;
 }
 

@@ -5,6 +5,8 @@
 #include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
+#include <utility>
 
 #include "../../include/sea_b200.h"
 
@@ -105,5 +107,29 @@ __device__ __forceinline__ int64_t ld_idx(const void* p, int64_t i) {
     } while (0)
 
 inline int cdiv(int64_t a, int64_t b) { return (int) ((a + b - 1) / b); }
+
+
+// ---- programmatic dependent launch (PDL) -------------------------------------------------------------------------------
+// Kernels of the layer's main chain are launched with cudaLaunchAttributeProgrammaticStreamSerialization: a kernel may be
+// scheduled while its predecessor in the stream still runs (its CTAs become resident as the predecessor's drain), and blocks in
+// pdl_wait() until the predecessor grid has completed and its memory is visible.  Rules kept by every such kernel: (1)
+// pdl_wait() precedes every access to activations, reads AND writes (the allocator may recycle a buffer the predecessor still
+// reads); only parameters (weights, biases) and shape arithmetic may come before it; (2) every kernel calls pdl_wait() in at
+// least the threads that touch global memory, so completion stays transitive along the chain; (3) pdl_launch_dependents() at
+// the top lets the successor start early.  SEA_NO_PDL=1 launches without the attribute (A/B timing).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+    static const bool no_pdl = getenv("SEA_NO_PDL") != nullptr;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = no_pdl ? 0 : 1;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 }  // namespace sea

@@ -157,6 +157,8 @@ performer_sums_mma_kernel(const __nv_bfloat16* __restrict__ k, int64_t k_sn, int
     using SM = PerfSmem<kFp>;
     extern __shared__ __align__(16) __nv_bfloat16 sm[];
     __nv_bfloat16 *Ps = sm + SM::kP, *Ks = sm + SM::kK, *PhiK = sm + SM::kPhiK, *Vs = sm + SM::kV;
+    pdl_launch_dependents();
+    pdl_wait();
     const int chunk = blockIdx.x, nh = blockIdx.y, n = nh / H, h = nh % H;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tq = lane & 3;
     const int r0 = chunk * kCh, nvalid = min(kCh, T - r0);
@@ -246,6 +248,8 @@ performer_out_mma_kernel(const __nv_bfloat16* __restrict__ q, int64_t q_sn, int6
     using SM = PerfSmem<kFp>;
     extern __shared__ __align__(16) __nv_bfloat16 sm[];
     __nv_bfloat16 *Ps = sm + SM::kP, *Qs = sm + SM::kQ, *Ks = sm + SM::kK, *PhiK = sm + SM::kPhiK, *Vs = sm + SM::kV, *Ss = sm + SM::kS;
+    pdl_launch_dependents();
+    pdl_wait();
     const int chunk = blockIdx.x, nh = blockIdx.y, n = nh / H, h = nh % H;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tq = lane & 3;
     const int r0 = chunk * kCh, nvalid = min(kCh, T - r0);
@@ -455,6 +459,8 @@ cumavg_kernel(const __nv_bfloat16* __restrict__ v, int64_t v_sn, int64_t v_sh, i
 // independent; a naive load/store loop serialises on aliasing and costs one L2 round trip per chunk).
 __global__ void __launch_bounds__(256)
 prefix_chunks_kernel(float* __restrict__ ws, int nchunks, int64_t stride) {
+    pdl_launch_dependents();
+    pdl_wait();
     float* base = ws + (int64_t) blockIdx.y * nchunks * stride;
     constexpr int kBatch = 16;
     for (int64_t idx = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; idx < stride; idx += (int64_t) gridDim.x * blockDim.x) {
@@ -484,14 +490,13 @@ int launch_performer_mma(const void* q, int64_t q_sn, int64_t q_sh, int64_t q_st
     SEA_CUDA_TRY(cudaFuncSetAttribute(ka, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kBytes), "smem attr");
     SEA_CUDA_TRY(cudaFuncSetAttribute(kc, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kBytes), "smem attr");
     using B = __nv_bfloat16;
-    ka<<<grid, kThreads, SM::kBytes, s>>>((const B*) k, k_sn, k_sh, k_st, (const B*) v, v_sn, v_sh, v_st, pos_emb, proj, ws, H, T, F, nchunks);
-    SEA_CHECK_LAUNCH("performer_sums_mma_kernel");
+    SEA_CUDA_TRY(launch_pdl(ka, grid, dim3(kThreads), (size_t) SM::kBytes, s, (const B*) k, k_sn, k_sh, k_st, (const B*) v, v_sn, v_sh, v_st, pos_emb, proj, ws, H, T, F,
+                            nchunks), "performer_sums_mma_kernel launch");
     const int64_t stride = (int64_t) kFp * kEx;
-    prefix_chunks_kernel<<<dim3((unsigned) ((stride + 255) / 256), N * H), 256, 0, s>>>(ws, nchunks, stride);
-    SEA_CHECK_LAUNCH("prefix_chunks_kernel");
-    kc<<<grid, kThreads, SM::kBytes, s>>>((const B*) q, q_sn, q_sh, q_st, (const B*) k, k_sn, k_sh, k_st, (const B*) v, v_sn, v_sh, v_st,
-                                          pos_emb, proj, ws, (B*) ctx, (B*) cumavg, H, T, F, nchunks);
-    SEA_CHECK_LAUNCH("performer_out_mma_kernel");
+    SEA_CUDA_TRY(launch_pdl(prefix_chunks_kernel, dim3((unsigned) ((stride + 255) / 256), N * H), dim3(256), (size_t) 0, s, ws, nchunks, stride),
+                 "prefix_chunks_kernel launch");
+    SEA_CUDA_TRY(launch_pdl(kc, grid, dim3(kThreads), (size_t) SM::kBytes, s, (const B*) q, q_sn, q_sh, q_st, (const B*) k, k_sn, k_sh, k_st, (const B*) v, v_sn, v_sh, v_st,
+                            pos_emb, proj, (const float*) ws, (B*) ctx, (B*) cumavg, H, T, F, nchunks), "performer_out_mma_kernel launch");
     // (the running mean of v is produced by performer_out_mma_kernel; cumavg_kernel stays as the stand-alone version)
     static const bool separate_cumavg = getenv("SEA_CUMAVG_SEPARATE") != nullptr;      // development switch for A/B timing
     if (cumavg != nullptr && separate_cumavg) {

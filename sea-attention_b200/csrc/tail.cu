@@ -169,6 +169,8 @@ tail_topk_reg_kernel(const float* __restrict__ y3, const float* __restrict__ bia
     uint32_t* img = sbits + (G >> 5);                           // [H][2 * wneed] dense element mask of this row (fused a8 expansion)
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int n = blockIdx.x / Tn, t = blockIdx.x % Tn;
+    pdl_launch_dependents();
+    pdl_wait();
     // fused a8 expansion (short-context attention path, block_attn.cu): words a kMaskRowBlock-row query block can see
     const int ex_src_off = ex.is_causal ? (ex.T_SRC - Tn) : 0;
     const int ex_blk_end = ex.is_causal ? ex_src_off + min((t / kMaskRowBlock + 1) * kMaskRowBlock, Tn) : ex.T_SRC;
@@ -544,7 +546,8 @@ static int tail_topk_impl(const float* y3, const float* bias, const float* ln_w,
         {                                                                                                                  \
             auto kern = tail_topk_reg_kernel<PL, HP, UP, EX>;                                                              \
             SEA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_r), "smem attr"); \
-            kern<<<grid, kTopkThreads, smem_r, s>>>(y3, bias, ln_w, ln_b, k_per_row, probs, mask_bits, crow_counts, k_clamp, N, T, W, H, ex); \
+            SEA_CUDA_TRY(launch_pdl(kern, dim3(grid), dim3(kTopkThreads), smem_r, s, y3, bias, ln_w, ln_b, k_per_row, probs, mask_bits, crow_counts, k_clamp, N, T, W, H, ex), \
+                         "tail_topk_reg_kernel launch"); \
         }
 #define SEA_TAILR(PL, HP)                                                                                                  \
         {                                                                                                                  \

@@ -93,6 +93,13 @@ __device__ __forceinline__ void mma_bf16_ss(uint32_t tmem_d, uint64_t adesc, uin
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// Programmatic dependent launch (PDL).  A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while
+// its predecessor in the stream is still running: everything before pdl_wait() (barrier init, TMEM allocation, tensor-map
+// prefetch, loads of weights that no kernel writes) overlaps the predecessor's tail; pdl_wait() returns once the predecessor
+// grid has completed and its memory is visible, so every access to activations -- reads AND writes, the allocator may have
+// recycled a buffer the predecessor still reads -- must come after it.  pdl_launch_dependents() lets the successor start.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 // Warp-converged variants: all 32 lanes execute the call with identical operands, elect.sync picks the issuing lane inside
 // the asm block.  This keeps the surrounding loop warp-uniform, so ptxas computes descriptors in the uniform datapath
 // instead of wrapping every UTCHMMA in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop (measured: 18 -> 6 SASS instr per MMA).

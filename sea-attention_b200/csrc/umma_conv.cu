@@ -305,6 +305,7 @@ conv_ring_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
     const int warp = __shfl_sync(0xffffffffu, (int) (threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const int G = N * PT;
     const int g_begin = blockIdx.x * pairs_per_cta, g_end = min(G, g_begin + pairs_per_cta);
+    umma::pdl_launch_dependents();                 // the next kernel may run its prologue under this one
     if (threadIdx.x == 0) {
         umma::prefetch_tensormap(&tmap_x);
         umma::prefetch_tensormap(&tmap_w);
@@ -326,6 +327,7 @@ conv_ring_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
             umma::mbar_arrive_expect_tx(wbar, RingSmem::kWBytes + (kFuse1x1 ? 4096 : 0));
             for (int tap = 0; tap < 9; ++tap) umma::tma_load_2d(wsm + tap * kNOut * 128, &tmap_w, wbar, 0, tap * kNOut);
             if (kFuse1x1) umma::tma_load_2d(w3sm, &tmap_w3, wbar, 0, 0);
+            umma::pdl_wait();                             // weights are parameters; the activations need the previous kernel
             int pos = 0, round = 0;                      // ring position / how many times the ring has wrapped
             for (int g0 = g_begin; g0 < g_end;) {
                 const int n = g0 / PT, k0 = g0 % PT;     // one run: tiles [k0, k1) of batch item n
@@ -413,6 +415,7 @@ conv_ring_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
         const int row = q * 32 + lane;                // TMEM lane = pixel (t0 + (row & 1), row >> 1)
         const int c0 = half * 32;
         const float4* b4 = reinterpret_cast<const float4*>(s_bias + c0);
+        umma::pdl_wait();                                 // before the first store: the output buffer may alias a predecessor's input
         auto finish_1x1 = [&](int c) {                // second epilogue pass of tile c: 16 of the 32 output channels per thread
             const int gg = g_begin + c, n2 = gg / PT, t2 = (gg % PT) * 2 + (row & 1);
             umma::mbar_wait(&acc2_full[c & 1], (uint32_t) ((c >> 1) & 1));
@@ -537,10 +540,19 @@ int launch_conv_umma(const void* x, const float* weight, const float* bias, void
                 int rc = make_tmap_bf16_sw128(&txp, const_cast<void*>(x), 4, dims, strides, box);
                 if (rc) return rc;
             }
+            // programmatic dependent launch: the prologue (barriers, TMEM, 74-78 KB of weights) overlaps the previous kernel's tail
+            static const bool no_pdl = getenv("SEA_NO_PDL") != nullptr;          // development switch for A/B timing
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned) grid_used); cfg.blockDim = dim3(kRingThreads); cfg.dynamicSmemBytes = RingSmem::kTotal; cfg.stream = s;
+            cudaLaunchAttribute pdl_attr[1];
+            pdl_attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            pdl_attr[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = pdl_attr; cfg.numAttrs = no_pdl ? 0 : 1;
             if (fuse == nullptr) {
                 auto kr = conv_ring_umma_kernel<kRelu, false>;
                 SEA_CUDA_TRY(cudaFuncSetAttribute(kr, cudaFuncAttributeMaxDynamicSharedMemorySize, RingSmem::kTotal), "smem attr");
-                kr<<<grid_used, kRingThreads, RingSmem::kTotal, s>>>(txp, tw, tw, bias, nullptr, reinterpret_cast<__nv_bfloat16*>(y), nullptr, N, T, tblocks, per);
+                SEA_CUDA_TRY(cudaLaunchKernelEx(&cfg, kr, txp, tw, tw, bias, (const float*) nullptr, reinterpret_cast<__nv_bfloat16*>(y), (float*) nullptr, N, T,
+                                                tblocks, per), "conv_ring_umma_kernel launch");
             } else {
                 // + the 1x1 convolution 64 -> 32 (fp32 output), its bf16 weight packing [32][64] lives in fuse->ws3
                 __nv_bfloat16* w3pack = reinterpret_cast<__nv_bfloat16*>(fuse->ws3);
@@ -554,7 +566,8 @@ int launch_conv_umma(const void* x, const float* weight, const float* bias, void
                 if (rc) return rc;
                 auto kr = conv_ring_umma_kernel<kRelu, true>;
                 SEA_CUDA_TRY(cudaFuncSetAttribute(kr, cudaFuncAttributeMaxDynamicSharedMemorySize, RingSmem::kTotal), "smem attr");
-                kr<<<grid_used, kRingThreads, RingSmem::kTotal, s>>>(txp, tw, tw3, bias, fuse->b3, nullptr, fuse->y3, N, T, tblocks, per);
+                SEA_CUDA_TRY(cudaLaunchKernelEx(&cfg, kr, txp, tw, tw3, bias, fuse->b3, (__nv_bfloat16*) nullptr, fuse->y3, N, T, tblocks, per),
+                             "conv_ring_umma_kernel launch");
             }
             SEA_CHECK_LAUNCH("conv_ring_umma_kernel");
             return SEA_OK;

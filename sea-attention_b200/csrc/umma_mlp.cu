@@ -93,6 +93,7 @@ mlp_umma_kernel(const __grid_constant__ CUtensorMap tmap_ctx, const __grid_const
     const int N2 = SW + 16;
     // warp index through a shuffle: provably warp-uniform, so the role branches and the MMA issue loop use the uniform datapath
     const int warp = __shfl_sync(0xffffffffu, (int) (threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+    pdl_launch_dependents();
     for (int i = threadIdx.x; i < 128; i += kMlpTcThreads) { s_enc_b[i] = enc_b[i]; s_ln_w[i] = enc_ln_w[i]; s_ln_b[i] = enc_ln_b[i]; }
     for (int i = threadIdx.x; i < 144; i += kMlpTcThreads) s_dec_b[i] = i < SW ? dec_b[i] : (i < SW + 2 ? scl_b[i - SW] : 0.f);
     for (int i = threadIdx.x; i < W; i += kMlpTcThreads) { s_cw[i] = cnn_ln_w[i]; s_cb[i] = cnn_ln_b[i]; }
@@ -109,6 +110,7 @@ mlp_umma_kernel(const __grid_constant__ CUtensorMap tmap_ctx, const __grid_const
     umma::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
     const uint32_t acc1 = tmem_base, acc2 = tmem_base + 128;
+    pdl_wait();       // set-up above (parameters only) overlaps the previous kernel; activations and outputs from here on
 
     if (warp == 0) {
         if (lane == 0) {
@@ -387,10 +389,9 @@ int sea_predictor_mlp_umma_fwd_ex(const void* ctx, const void* v, int64_t v_sn, 
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     SEA_CUDA_TRY(cudaFuncSetAttribute(mlp_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MlpSmem::kTotal), "smem attr");
     const int grid = num_tiles < sms ? num_tiles : sms;
-    mlp_umma_kernel<<<grid, kMlpTcThreads, MlpSmem::kTotal, s>>>(t_ctx, t_v, t_w1, t_w2, enc_b, enc_ln_w, enc_ln_b, dec_b, scl_b, cnn_ln_w,
-                                                                 cnn_ln_b, reinterpret_cast<__nv_bfloat16*>(cnn_in), scales, N, H, T, W, TT,
-                                                                 tblocks, num_tiles, Cout);
-    SEA_CHECK_LAUNCH("mlp_umma_kernel");
+    SEA_CUDA_TRY(launch_pdl(mlp_umma_kernel, dim3((unsigned) grid), dim3(kMlpTcThreads), (size_t) MlpSmem::kTotal, s, t_ctx, t_v, t_w1, t_w2, enc_b, enc_ln_w, enc_ln_b,
+                            dec_b, scl_b, cnn_ln_w, cnn_ln_b, reinterpret_cast<__nv_bfloat16*>(cnn_in), scales, N, H, T, W, TT, tblocks, num_tiles, Cout),
+                 "mlp_umma_kernel launch");
     return SEA_OK;
 }
 
