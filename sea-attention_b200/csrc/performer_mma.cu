@@ -248,6 +248,7 @@ performer_out_mma_kernel(const __nv_bfloat16* __restrict__ q, int64_t q_sn, int6
     using SM = PerfSmem<kFp>;
     extern __shared__ __align__(16) __nv_bfloat16 sm[];
     __nv_bfloat16 *Ps = sm + SM::kP, *Qs = sm + SM::kQ, *Ks = sm + SM::kK, *PhiK = sm + SM::kPhiK, *Vs = sm + SM::kV, *Ss = sm + SM::kS;
+    float* vprev_s = reinterpret_cast<float*>(sm + SM::kElems);          // [64] fp32
     pdl_launch_dependents();
     pdl_wait();
     const int chunk = blockIdx.x, nh = blockIdx.y, n = nh / H, h = nh % H;
@@ -277,6 +278,7 @@ performer_out_mma_kernel(const __nv_bfloat16* __restrict__ q, int64_t q_sn, int6
             if (idx < kVec) {
                 const int f = idx / (kEx / 4), e = (idx % (kEx / 4)) * 4;
                 if (e == kE && f < F) sv[it].x += 1e-6f;
+                if (f == F && e >= kDm && e < kE) *reinterpret_cast<float4*>(vprev_s + (e - kDm)) = sv[it];     // vsum of the earlier chunks, kept in fp32
                 *reinterpret_cast<uint2*>(Ss + f * kLdV + e) = make_uint2(pack_bf16(sv[it].x, sv[it].y), pack_bf16(sv[it].z, sv[it].w));
             }
         }
@@ -387,7 +389,7 @@ performer_out_mma_kernel(const __nv_bfloat16* __restrict__ q, int64_t q_sn, int6
     // a13 running mean of v (attention.py:1237-1241), fused: cumavg[t] = (vsum_prev(chunk) + sum_{j <= t in chunk} v_j) / (t + 1).
     // The in-chunk cumulative sum is L . V with L the lower-triangular ones matrix: the same V fragments as above against an
     // all-ones A fragment (triangular on the diagonal tile); bf16 ones x bf16 v accumulate exactly in fp32.  vsum_prev is row F
-    // (the ones feature) of the prefixed state, columns 64..127, read in fp32 from the workspace.
+    // (the ones feature) of the prefixed state, columns 64..127, kept in fp32 in shared memory by the S_prev load above.
     if (cumavg != nullptr) {
         float C[kDm / 8][4];
 #pragma unroll
@@ -409,13 +411,12 @@ performer_out_mma_kernel(const __nv_bfloat16* __restrict__ q, int64_t q_sn, int6
                 mma16816(C[2 * np + 1], la, b[2], b[3]);
             }
         }
-        const float* vprev = ws + (((int64_t) nh * nchunks + chunk) * kFp + F) * kEx + kDm;
         const float r_lo = 1.0f / (float) (r0 + row_lo + 1), r_hi = 1.0f / (float) (r0 + row_hi + 1);
         __nv_bfloat16* ab = cumavg + (((int64_t) n * H + h) * T + r0) * kDm;
 #pragma unroll
         for (int nt = 0; nt < kDm / 8; ++nt) {
             const int e0 = nt * 8 + 2 * tq;
-            const float2 pv = __ldcg(reinterpret_cast<const float2*>(vprev + e0));
+            const float2 pv = *reinterpret_cast<const float2*>(vprev_s + e0);
             if (row_lo < nvalid) *reinterpret_cast<uint32_t*>(ab + (int64_t) row_lo * kDm + e0) = pack_bf16((C[nt][0] + pv.x) * r_lo, (C[nt][1] + pv.y) * r_lo);
             if (row_hi < nvalid) *reinterpret_cast<uint32_t*>(ab + (int64_t) row_hi * kDm + e0) = pack_bf16((C[nt][2] + pv.x) * r_hi, (C[nt][3] + pv.y) * r_hi);
         }
