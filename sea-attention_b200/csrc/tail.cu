@@ -180,22 +180,22 @@ tail_topk_reg_kernel(const float* __restrict__ y3, const float* __restrict__ bia
     if (tid == 0) { s_orand[0] = 0u; s_orand[1] = 0xffffffffu; }
     const int ldy = kUp > 0 ? ((P / (kUp > 0 ? kUp : 1) + 2) | 1) : ((W + 2) | 1);        // compile-time when the upsample factor is (W == P / kUp)
     const float* yr = y3 + ((int64_t) n * Tn + t) * W * H;
-    for (int base = 0; base < W * H; base += 8 * kTopkThreads) {
-        // 8 independent loads in flight per thread before the first (transposing) shared-memory store
-        float tmp[8];
+    // The first batch of conv outputs (8 loads per thread = the whole row at the north-star shape) and the LayerNorm parameters
+    // are requested before the tap table is computed, so that table's integer divisions run under the load latency, and one
+    // barrier covers both the row image and the table.
+    float tmp0[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int idx = base + u * kTopkThreads + tid;
-            tmp[u] = idx < W * H ? __ldg(yr + idx) : 0.f;
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int idx = base + u * kTopkThreads + tid;
-            if (idx < W * H) ys[(idx % H) * ldy + idx / H] = tmp[u];
-        }
+    for (int u = 0; u < 8; ++u) {
+        const int idx = u * kTopkThreads + tid;
+        tmp0[u] = idx < W * H ? __ldg(yr + idx) : 0.f;
     }
-    for (int h = tid; h < H; h += kTopkThreads) { ys[h * ldy + W] = bias[h]; ys[h * ldy + W + 1] = 0.f; }
-    __syncthreads();
+    float lw[kPerLane], lb[kPerLane];
+#pragma unroll
+    for (int i = 0; i < kPerLane; ++i) {
+        const int j = lane * kPerLane + i;
+        lw[i] = __ldg(ln_w + j);
+        lb[i] = __ldg(ln_b + j);
+    }
     constexpr int PW = P + 2;
     const int up = kUp > 0 ? kUp : P / W;
     // area-resize window of every output column, resolved once per CTA (thread = column) into three slots of the per-head
@@ -211,17 +211,36 @@ tail_topk_reg_kernel(const float* __restrict__ y3, const float* __restrict__ bia
         }
         stap[(j % kPerLane) * 32 + j / kPerLane] = make_int4(tp[0], tp[1], tp[2], __float_as_int(1.0f / (float) cnt));   // [i][lane]: conflict-free reads
     }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        const int idx = u * kTopkThreads + tid;
+        if (idx < W * H) ys[(idx % H) * ldy + idx / H] = tmp0[u];
+    }
+    for (int base = 8 * kTopkThreads; base < W * H; base += 8 * kTopkThreads) {
+        // 8 independent loads in flight per thread before the first (transposing) shared-memory store
+        float tmp[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int idx = base + u * kTopkThreads + tid;
+            tmp[u] = idx < W * H ? __ldg(yr + idx) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int idx = base + u * kTopkThreads + tid;
+            if (idx < W * H) ys[(idx % H) * ldy + idx / H] = tmp[u];
+        }
+    }
+    for (int h = tid; h < H; h += kTopkThreads) { ys[h * ldy + W] = bias[h]; ys[h * ldy + W + 1] = 0.f; }
     __syncthreads();
     int tap[kPerLane][3];
-    float rc[kPerLane], lw[kPerLane], lb[kPerLane];
+    float rc[kPerLane];
 #pragma unroll
     for (int i = 0; i < kPerLane; ++i) {
-        const int j = lane * kPerLane + i;
         const int4 tp = stap[i * 32 + lane];
         tap[i][0] = tp.x; tap[i][1] = tp.y; tap[i][2] = tp.z;
         rc[i] = __int_as_float(tp.w);
-        lw[i] = ln_w[j] * kLog2eT;          // softmax in the log2 domain: exp(x - max) == exp2(x * log2e - max * log2e)
-        lb[i] = ln_b[j] * kLog2eT;
+        lw[i] *= kLog2eT;                   // softmax in the log2 domain: exp(x - max) == exp2(x * log2e - max * log2e)
+        lb[i] *= kLog2eT;
     }
     constexpr float invP = 1.0f / (float) P;
     // The kHPW heads of this warp advance through LayerNorm / softmax stage by stage, so that the kHPW warp reductions of a
