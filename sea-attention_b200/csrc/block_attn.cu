@@ -336,7 +336,7 @@ block_attention_bits_kernel(const uint32_t* __restrict__ tile_act, int act_words
 __global__ void __launch_bounds__(256)
 expand_mask_kernel(const uint32_t* __restrict__ mask_bits, unsigned long long* __restrict__ dmask, uint32_t* __restrict__ tile_act, int act_words, int W64,
                    int N, int H, int T_DST, int T_SRC, int P, int p_lg, int is_causal) {
-    extern __shared__ uint32_t ex_sm[];                   // [H][2 * wneed]
+    extern __shared__ uint32_t ex_sm[];                   // [H][2 * W64] row image | [H][act_words] | [8 warps][1024] pixel lists
     pdl_launch_dependents();
     pdl_wait();
     const int nw = P >> 5;
@@ -350,11 +350,26 @@ expand_mask_kernel(const uint32_t* __restrict__ mask_bits, unsigned long long* _
     for (int i = threadIdx.x; i < H * 2 * wneed; i += blockDim.x) ex_sm[i] = 0u;
     __syncthreads();
     const uint32_t* brow = mask_bits + (int64_t) row * ((int64_t) H * nw);
-    for (int idx = threadIdx.x; idx < H * nw; idx += blockDim.x) {
-        const int h = idx / nw, w = idx - h * nw;
-        uint32_t* img = ex_sm + h * 2 * wneed;
-        for (uint32_t x = __ldg(brow + idx); x; x &= x - 1) {
-            const int m = (w << 5) + __ffs(x) - 1;
+    // Alive pixels are first compacted into a per-warp list (scan of the words' popcounts), then processed one pixel per lane:
+    // a per-thread loop over the set bits of its own word runs at the pace of the fullest word of the warp (ncu: 7 of 32 lanes
+    // active on the edge arithmetic and the atomics, which are most of this kernel's instructions).
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    uint16_t* lst = reinterpret_cast<uint16_t*>(ex_sm + H * 2 * W64 + H * act_words) + wrp * 1024;      // [1024] (head << 10) | pixel  (P <= 1024, H <= 64)
+    for (int base = 0; base < H * nw; base += blockDim.x) {
+        const int idx = base + threadIdx.x;
+        uint32_t x = 0u;
+        int h = 0, w = 0;
+        if (idx < H * nw) { x = __ldg(brow + idx); h = idx / nw; w = idx - h * nw; }
+        const int cnt = __popc(x);
+        const int incl = warp_scan_incl_i(cnt, lane);
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        int off = incl - cnt;
+        for (; x; x &= x - 1) lst[off++] = (uint16_t) ((h << 10) | ((w << 5) + __ffs(x) - 1));
+        __syncwarp();
+        for (int i = lane; i < total; i += 32) {
+            const uint32_t e = lst[i];
+            const int m = (int) (e & 1023u);
+            uint32_t* img = ex_sm + (e >> 10) * 2 * wneed;
             const int a = rs.edge(m), b = rs.edge(m + 1);
             if (b > a)
                 for (int wd = a >> 5; wd <= ((b - 1) >> 5); ++wd) {
@@ -362,6 +377,7 @@ expand_mask_kernel(const uint32_t* __restrict__ mask_bits, unsigned long long* _
                     atomicOr(img + wd, (hi - lo >= 32 ? 0xffffffffu : ((1u << (hi - lo)) - 1u)) << lo);
                 }
         }
+        __syncwarp();
     }
     __syncthreads();
     // tile activity of the (head, 128-row query block): which 64-token tiles hold an alive element of any of its rows.
@@ -369,11 +385,13 @@ expand_mask_kernel(const uint32_t* __restrict__ mask_bits, unsigned long long* _
     uint32_t* act_sm = ex_sm + H * 2 * W64;                                   // [H][act_words]
     for (int i = threadIdx.x; i < H * act_words; i += blockDim.x) act_sm[i] = 0u;
     __syncthreads();
-    for (int i = threadIdx.x; i < H * wneed; i += blockDim.x) {
-        const int h = i / wneed, w = i - h * wneed;
-        const uint2 v = *reinterpret_cast<const uint2*>(ex_sm + 2 * (h * wneed + w));
-        dmask[(((int64_t) n * H + h) * T_DST + t) * W64 + w] = (unsigned long long) v.x | ((unsigned long long) v.y << 32);
-        if ((v.x | v.y) != 0u) atomicOr(act_sm + h * act_words + (w >> 5), 1u << (w & 31));
+    for (int h = wrp; h < H; h += (int) (blockDim.x >> 5)) {                  // warp per head: no division in the write-out loop
+        unsigned long long* drow = dmask + (((int64_t) n * H + h) * T_DST + t) * W64;
+        for (int w = lane; w < wneed; w += 32) {
+            const uint2 v = *reinterpret_cast<const uint2*>(ex_sm + 2 * (h * wneed + w));
+            drow[w] = (unsigned long long) v.x | ((unsigned long long) v.y << 32);
+            if ((v.x | v.y) != 0u) atomicOr(act_sm + h * act_words + (w >> 5), 1u << (w & 31));
+        }
     }
     __syncthreads();
     uint32_t* act_blk = tile_act + (int64_t) n * H * ((T_DST + kBM - 1) / kBM) * act_words + (int64_t) (t / kBM) * act_words;
@@ -404,7 +422,7 @@ extern "C" {
 
 int64_t sea_block_attention_workspace_bytes(int N, int H, int T_DST, int T_SRC, int D, int P, int k_clamp, int dtype) {
     if (dtype != SEA_DTYPE_BF16 && dtype != SEA_DTYPE_F16) return 0;
-    if (N <= 0 || H <= 0 || T_DST <= 0 || T_SRC < T_DST || !block_attention_eligible(D, T_SRC, P, k_clamp)) return 0;
+    if (N <= 0 || H <= 0 || H > 64 || T_DST <= 0 || T_SRC < T_DST || !block_attention_eligible(D, T_SRC, P, k_clamp)) return 0;      // (H <= 64: 6-bit head field of the expansion's pixel list)
     return (int64_t) N * H * T_DST * mask_row_words(T_SRC) * 8 + mask_act_bytes(N, H, T_DST, T_SRC);      // dense bit mask + tile activity
 }
 
@@ -434,7 +452,7 @@ int sea_block_attention_fwd(const uint32_t* mask_bits,
     const int p_lg = exact_edge_shift(P, T_SRC);      // integer pixel edges are exact iff P is a power of two and m * L stays below 2^24
     if (mask_bits != nullptr) {      // nullptr: `workspace` was filled by sea_predictor_tail_topk_expand_fwd (mask expansion fused into the top-k)
         SEA_CUDA_TRY(cudaMemsetAsync(tile_act, 0, (size_t) mask_act_bytes(N, H, T_DST, T_SRC), s), "memset tile activity");
-        const size_t smem = (size_t) H * W64 * 8 + (size_t) H * act_words * 4;
+        const size_t smem = (size_t) H * W64 * 8 + (size_t) H * act_words * 4 + (size_t) 8 * 1024 * 2;      // row image + tile activity + per-warp pixel lists
         SEA_CHECK_ARG(smem <= 200 * 1024, "sea_block_attention_fwd: H * T_SRC too large for the mask expansion");
         SEA_CUDA_TRY(cudaFuncSetAttribute(expand_mask_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem), "smem attr");
         SEA_CUDA_TRY(launch_pdl(expand_mask_kernel, dim3((unsigned) ((int64_t) N * T_DST)), dim3(256), (size_t) smem, s, mask_bits, dmask, tile_act, act_words, W64, N, H, T_DST,
