@@ -120,6 +120,21 @@ inline int cdiv(int64_t a, int64_t b) { return (int) ((a + b - 1) / b); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// launch_pdl_if(allow, ...): allow = false gives a plain, fully serialised launch.  Needed when the predecessor in the stream wrote
+// something the kernel reads BEFORE its pdl_wait() -- i.e. a weight-packing kernel launched just before a kernel that prefetches
+// its packed weights during the set-up.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl_if(bool allow, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+    static const bool no_pdl = getenv("SEA_NO_PDL") != nullptr;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = (no_pdl || !allow) ? 0 : 1;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
     static const bool no_pdl = getenv("SEA_NO_PDL") != nullptr;

@@ -547,7 +547,9 @@ int launch_conv_umma(const void* x, const float* weight, const float* bias, void
             cudaLaunchAttribute pdl_attr[1];
             pdl_attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
             pdl_attr[0].val.programmaticStreamSerializationAllowed = 1;
-            cfg.attrs = pdl_attr; cfg.numAttrs = no_pdl ? 0 : 1;
+            // (not right behind a weight-packing kernel: the packed weights are loaded before pdl_wait())
+            const bool fresh_pack = weight != nullptr || (fuse != nullptr && fuse->w3 != nullptr);
+            cfg.attrs = pdl_attr; cfg.numAttrs = (no_pdl || fresh_pack) ? 0 : 1;
             if (fuse == nullptr) {
                 auto kr = conv_ring_umma_kernel<kRelu, false>;
                 SEA_CUDA_TRY(cudaFuncSetAttribute(kr, cudaFuncAttributeMaxDynamicSharedMemorySize, RingSmem::kTotal), "smem attr");

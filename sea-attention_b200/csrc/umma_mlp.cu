@@ -103,6 +103,10 @@ mlp_umma_kernel(const __grid_constant__ CUtensorMap tmap_ctx, const __grid_const
         for (int b = 0; b < 2; ++b) { umma::mbar_init(&full1[b], 1); umma::mbar_init(&empty1[b], 1); }
         umma::mbar_init(acc1_full, 1); umma::mbar_init(a2_full, kMlpEpiWarps); umma::mbar_init(acc2_full, 1); umma::mbar_init(wbar, 1);
         umma::fence_barrier_init();
+        // the packed weights are parameters: request them before pdl_wait(), under the previous kernel's tail
+        umma::mbar_arrive_expect_tx(wbar, 3 * kTile + 2 * N2 * 128);
+        for (int a = 0; a < 3; ++a) umma::tma_load_2d(smem + MlpSmem::kW1 + a * kTile, &tmap_w1, wbar, a * 64, 0);
+        for (int a = 0; a < 2; ++a) umma::tma_load_2d(smem + MlpSmem::kW2 + a * MlpSmem::kW2Atom, &tmap_w2, wbar, a * 64, 0);
     }
     if (warp == 1) umma::tmem_alloc(tmem_ptr, 512);
     umma::tc_fence_before();
@@ -114,9 +118,6 @@ mlp_umma_kernel(const __grid_constant__ CUtensorMap tmap_ctx, const __grid_const
 
     if (warp == 0) {
         if (lane == 0) {
-            umma::mbar_arrive_expect_tx(wbar, 3 * kTile + 2 * N2 * 128);
-            for (int a = 0; a < 3; ++a) umma::tma_load_2d(smem + MlpSmem::kW1 + a * kTile, &tmap_w1, wbar, a * 64, 0);
-            for (int a = 0; a < 2; ++a) umma::tma_load_2d(smem + MlpSmem::kW2 + a * MlpSmem::kW2Atom, &tmap_w2, wbar, a * 64, 0);
             int buf = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -389,7 +390,8 @@ int sea_predictor_mlp_umma_fwd_ex(const void* ctx, const void* v, int64_t v_sn, 
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     SEA_CUDA_TRY(cudaFuncSetAttribute(mlp_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MlpSmem::kTotal), "smem attr");
     const int grid = num_tiles < sms ? num_tiles : sms;
-    SEA_CUDA_TRY(launch_pdl(mlp_umma_kernel, dim3((unsigned) grid), dim3(kMlpTcThreads), (size_t) MlpSmem::kTotal, s, t_ctx, t_v, t_w1, t_w2, enc_b, enc_ln_w, enc_ln_b,
+    // (a fresh packing was just written by pack_mlp_weights_kernel: the kernel prefetches the packed weights before pdl_wait(), so serialise fully)
+    SEA_CUDA_TRY(launch_pdl_if(enc_w == nullptr, mlp_umma_kernel, dim3((unsigned) grid), dim3(kMlpTcThreads), (size_t) MlpSmem::kTotal, s, t_ctx, t_v, t_w1, t_w2, enc_b, enc_ln_w, enc_ln_b,
                             dec_b, scl_b, cnn_ln_w, cnn_ln_b, reinterpret_cast<__nv_bfloat16*>(cnn_in), scales, N, H, T, W, TT, tblocks, num_tiles, Cout),
                  "mlp_umma_kernel launch");
     return SEA_OK;
