@@ -30,7 +30,6 @@ sys.path.insert(0, ROOT)
 METRIC = 'SEA attn fwd tokens/sec @OPT-1.3B 4k ctx'
 UNIT = 'tokens/s'
 NS = dict(H=32, d=64, T=4096, P=256, k=64, nbf=8)
-CPU_SAMPLE_T = 2048
 
 
 def _peaks():
@@ -147,44 +146,99 @@ def _emit(line):
     os.write(_STDOUT_FD if _STDOUT_FD is not None else 1, (json.dumps(line) + '\n').encode())
 
 
-def run_reference(args):
-    """--impl reference: the reference's CPU implementation of the path.  /root/reference is python and absent
-    on the GPU box, so this times its restatement (oracle/sea_oracle.py, dense torch path = what the reference
-    itself runs on a CPU, attention.py benchmarking=False) with every host thread."""
-    rank = int(os.environ.get('RANK', '0'))
-    if rank != 0:
-        return
+WORKLOAD = 'SEA attention layer fwd, OPT-1.3B shape: 32 heads d=64 seq 4096 k=64 predictor_length=256 nbf=8, causal, N=1/GPU'
+# identical in both arms (the driver compares the arms' `config`)
+CONFIG = {'workload': WORKLOAD,
+          'sharding': 'batch (one item per GPU, no collective on the hot path)',
+          'weights': 'random-init (seed 42)',
+          'l2': 'GPU arm: flushed between steps (256 MiB memset), per-step CUDA events; CPU reference arm: not applicable'}
+
+
+def _reference_step(H, d, T, P, k, nbf, causal=True, k_flatten_dim=None):
+    """-> (step callable, kind, note).  kind 'reference' = the UNMODIFIED reference module (oracle/_ref, the verbatim copy
+    `make -C oracle` makes in the build container; /root/reference itself does not exist on the GPU box) running its own
+    dense torch CPU path (benchmarking=False, fp32, no_grad: what the reference runs on a CPU, SURVEY 8d);
+    kind 'port' = the oracle restatement, only when no copy of the reference travelled."""
+    from oracle import ref_harness as rh
+    q = torch.randn(1, H, T, d) * (d ** -0.5 if causal else 1.0)
+    kk = torch.randn(1, H, T, d)
+    v = torch.randn(1, H, T, d)
+    if rh.reference_available():
+        m = rh.build_reference_attention(H, d, T, k, P, nbf, causal, k_flatten_dim=k_flatten_dim)
+        m.benchmarking = False
+        mask = rh.causal_additive_mask(T, torch.float32) if causal else torch.zeros(1, 1, 1, T)
+
+        def step():
+            with torch.no_grad():
+                return m(q, kk, v, q, kk, v, q, kk, mask, None, None)
+        return step, 'reference', f'unmodified reference PerlinAttention ({os.path.relpath(rh.REFERENCE_ROOT, ROOT)}), benchmarking=False dense torch path'
     from oracle import sea_oracle as so
     import transformers
     sea = importlib.import_module('sea-attention_b200')
-    torch.set_num_threads(os.cpu_count())
-    H, d, P, k, nbf = NS['H'], NS['d'], NS['P'], NS['k'], NS['nbf']
-    T = CPU_SAMPLE_T
-    torch.manual_seed(42)
-    cfg = transformers.BertConfig(hidden_size=H * d, num_attention_heads=H, max_position_embeddings=NS['T'])
-    mod = sea.PerlinAttention(cfg, sea.PerlinAttentionConfig(performer_nb_factor=nbf, k=k, attention_predictor_length=P, causal=True)).eval()
+    cfg = transformers.BertConfig(hidden_size=H * d, num_attention_heads=H, max_position_embeddings=T)
+    mod = sea.PerlinAttention(cfg, sea.PerlinAttentionConfig(performer_nb_factor=nbf, k=k, attention_predictor_length=P, causal=causal)).eval()
     sd = {k_: v_.detach().float() for k_, v_ in mod.state_dict().items() if 'enc_per_layer' not in k_}
-    q = torch.randn(1, H, T, d) * d ** -0.5
-    kk = torch.randn(1, H, T, d)
-    v = torch.randn(1, H, T, d)
-    with torch.no_grad():
-        for _ in range(max(1, min(args.warmup, 2))):
-            so.perlin_forward_causal(sd, q, kk, v, k_top=k, P=P, sparse=False)
-        steps = max(1, min(args.steps, 10))
-        t0 = time.perf_counter()
-        for _ in range(steps):
-            so.perlin_forward_causal(sd, q, kk, v, k_top=k, P=P, sparse=False)
-        dt = (time.perf_counter() - t0) / steps
+    fwd = so.perlin_forward_causal if causal else so.perlin_forward_noncausal
+
+    def step():
+        with torch.no_grad():
+            return fwd(sd, q, kk, v, k_top=k, P=P, sparse=False)
+    return step, 'port', 'oracle restatement of the dense torch path (no copy of the reference on this box)'
+
+
+def _time_cpu(step, warmup, steps):
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    return (time.perf_counter() - t0) / steps
+
+
+def cpu_config1_row():
+    """BASELINE configs[0] (the reference's own CPU-runnable case): BERT-base PerlinAttention layer fwd, seq 512, k=64,
+    predictor length 128, nbf=1, non-causal, k_flatten_dim='batch' -- the mandatory CPU row of BASELINE.md section 3."""
+    torch.manual_seed(42)
+    step, kind, note = _reference_step(12, 64, 512, 128, 64, 1, causal=False, k_flatten_dim='batch')
+    dt = _time_cpu(step, 3, 5)
+    return {'workload': 'BERT-base PerlinAttention layer fwd, seq 512, k=64, predictor-length 128, nbf=1, fp32 torch CPU path',
+            'value': 512 / dt, 'unit': UNIT, 'ms_per_step': dt * 1e3, 'cores': torch.get_num_threads(), 'kind': kind, 'steps': 5, 'warmup': 3}
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path on this box's host cores, at the arm's own
+    config (full T = 4096), with exactly --warmup / --steps iterations.  Rank 0 only under torchrun."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    torch.set_num_threads(os.cpu_count())
+    H, d, T, P, k, nbf = (NS[x] for x in ('H', 'd', 'T', 'P', 'k', 'nbf'))
+    torch.manual_seed(42)
+    step, kind, note = _reference_step(H, d, T, P, k, nbf)
+    # exactly --warmup / --steps iterations, unless that would run past the wall-clock budget (then fewer, and the line says so)
+    budget = float(os.environ.get('SEA_REF_BUDGET_S', '900'))
+    t0 = time.perf_counter()
+    step()
+    first = time.perf_counter() - t0
+    warmup = max(1, min(args.warmup, int(budget * 0.2 / first)))
+    steps = max(1, min(args.steps, int(budget * 0.8 / first)))
+    dt = _time_cpu(step, warmup - 1, steps)
+    args.steps, args.warmup = steps, warmup
     val = T / dt
-    sample = f'first {T} of {NS["T"]} tokens of the north-star layer (causal prefix), fp32 dense torch path, {steps} steps'
+    sample = f'the full workload (all {T} tokens), fp32, {note}; {args.warmup} warm-up + {args.steps} timed steps'
     line = {
-        'metric': METRIC, 'value': val, 'unit': UNIT, 'impl': 'reference', 'n_gpus': args.gpus, 'steps': steps, 'warmup': args.warmup,
+        'metric': METRIC, 'value': val, 'unit': UNIT, 'impl': 'reference', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': dt * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': 'SEA attention layer fwd, OPT-1.3B shape: 32 heads d=64 seq 4096 k=64 predictor_length=256 nbf=8, causal, N=1/GPU',
-                   'sample': sample},
-        'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port', 'sample': sample},
+        'config': dict(CONFIG),
+        'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': kind, 'sample': sample,
+                         'cpu_count': os.cpu_count()},
         'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
+    if not args.no_cpu_baseline:
+        try:
+            line['cpu_config1'] = cpu_config1_row()
+        except Exception as e:          # the BERT row is extra information; never lose the headline line over it
+            line['cpu_config1'] = {'error': repr(e)[:200]}
     _emit(line)
 
 
@@ -222,6 +276,7 @@ def main():
     mod = sea.PerlinAttention(cfg, pc).eval().to(dev)
     mod.benchmarking = True
     mod.check_padding = False                                 # synthetic data has no padding; keeps the step free of host syncs
+    mod.freeze_packed_weights()                               # inference: weights are constant, bf16 packings made once
     F = mod.performer_nb_features
     gen = torch.Generator().manual_seed(42 + rank)
     hq = (torch.randn(N, H, T, d, generator=gen) * d ** -0.5).to(dt).pin_memory()
@@ -421,10 +476,9 @@ def main():
         line = {
             'metric': METRIC, 'value': tokens / (ms_dev * 1e-3), 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': warm,
             'ms_per_step': ms_dev, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': args.dtype, 'data': 'synthetic',
-            'config': {'workload': 'SEA attention layer fwd, OPT-1.3B shape: 32 heads d=64 seq 4096 k=64 predictor_length=256 nbf=8, causal, N=1/GPU',
-                       'sharding': 'batch (one item per GPU, no collective on the hot path)', 'l2': 'flushed between steps (256 MiB memset), per-step CUDA events',
-                       'launch': 'one CUDA graph replay per step' if use_graph else 'eager kernel launches',
-                       'weights': 'random-init (seed 42)', 'outputs': 'context_layer + estimated_attention_probs (output_attentions=False)', 'nnz': Z},
+            'config': dict(CONFIG),
+            'notes': {'launch': 'one CUDA graph replay per step' if use_graph else 'eager kernel launches',
+                      'outputs': 'context_layer + estimated_attention_probs (output_attentions=False)', 'nnz': Z},
             'e2e': {'value': tokens / (ms_e2e * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': 3 * q.numel() * q.element_size(),
                     'd2h_bytes_per_step': hout.numel() * hout.element_size(), 'ms_per_step': ms_e2e,
                     'note': 'causal additive mask is a shape constant kept on the device; H2D / forward / D2H on three streams, double-buffered, '
@@ -437,20 +491,14 @@ def main():
             'clocks': clocks,
         }
         if not args.no_cpu_baseline and world == 1:
-            from oracle import sea_oracle as so
+            # bounded sample of the SAME workload on the host cores: 1 warm-up + 2 timed steps of the full T = 4096 layer
             torch.set_num_threads(os.cpu_count())
-            Ts = CPU_SAMPLE_T
-            sd = {k_: v_.detach().float().cpu() for k_, v_ in mod.state_dict().items() if 'enc_per_layer' not in k_}
-            cq, ck, cv = hq[:, :, :Ts].float(), hk[:, :, :Ts].float(), hv[:, :, :Ts].float()
-            with torch.no_grad():
-                so.perlin_forward_causal(sd, cq, ck, cv, k_top=k, P=P, sparse=False)
-                t0 = time.perf_counter()
-                reps = 3
-                for _ in range(reps):
-                    so.perlin_forward_causal(sd, cq, ck, cv, k_top=k, P=P, sparse=False)
-                cdt = (time.perf_counter() - t0) / reps
-            line['cpu_baseline'] = {'value': Ts / cdt, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',
-                                    'sample': f'first {Ts} of {T} tokens (causal prefix) of the same layer, fp32 dense torch path, {reps} steps'}
+            torch.manual_seed(42)
+            step, kind, note = _reference_step(H, d, T, P, k, nbf)
+            cdt = _time_cpu(step, 1, 2)
+            line['cpu_baseline'] = {'value': T / cdt, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': kind, 'cpu_count': os.cpu_count(),
+                                    'ms_per_step': cdt * 1e3,
+                                    'sample': f'the full workload (all {T} tokens), fp32, {note}; 1 warm-up + 2 timed steps'}
         _emit(line)
     if dist is not None:
         dist.barrier()

@@ -1,7 +1,8 @@
-"""TEST INFRASTRUCTURE ONLY -- loads the UNMODIFIED reference from /root/reference (this container
-only; the path does not exist on the GPU box, so nothing under `-m gpu`, smoke() or bench.py may
-import this file).  Used by oracle/make_golden.py and by the CPU tests that pin the oracle against
-the reference itself (they skip when /root/reference is absent).
+"""TEST INFRASTRUCTURE ONLY -- loads the UNMODIFIED reference: from /root/reference in the build container, else
+from oracle/_ref (the verbatim, git-ignored copy of the hot path's files that `make -C oracle` makes in the
+build container and that travels to the GPU box with the snapshot).  Used by oracle/make_golden.py, by the
+tests that pin the oracle / the CUDA path against the reference itself (they skip when neither tree exists),
+by bench.py's `--impl reference` / `cpu_baseline` legs and by scripts/ref_triton_gpu.py.  Never by the product.
 
 Recipe = SURVEY.md appendix B:
   * `src.models.hf_bert` fails to import under transformers 5.x; it is only used as the name of a
@@ -15,8 +16,20 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get('SEA_REFERENCE_ROOT', '/root/reference')
 _HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _pick_root():
+    env = os.environ.get('SEA_REFERENCE_ROOT')
+    if env:
+        return env
+    for cand in ('/root/reference', os.path.join(_HERE, '_ref')):
+        if os.path.isdir(os.path.join(cand, 'src', 'models', 'perlin_attention')):
+            return cand
+    return '/root/reference'
+
+
+REFERENCE_ROOT = _pick_root()
 
 
 def reference_available() -> bool:
@@ -53,12 +66,20 @@ def _patch_interpreter_boolops():
     ti.ASTTransformer._sea_boolop_patched = True
 
 
-def load_reference(interpret_triton: bool = True):
-    """Returns the reference's `src.models.perlin_attention` package (imported, not copied)."""
+def load_reference(interpret_triton=None):
+    """Returns the reference's `src.models.perlin_attention` package (imported, not copied).
+    interpret_triton: True = Triton's numpy interpreter (CPU), False = compiled Triton (needs a GPU), None = interpreter
+    exactly when no CUDA device is visible.  The choice is fixed by the first call of a process (Triton reads
+    TRITON_INTERPRET when the kernels are decorated)."""
     if not reference_available():
         raise RuntimeError(f'reference tree not found at {REFERENCE_ROOT}')
+    if interpret_triton is None:
+        import torch
+        interpret_triton = not torch.cuda.is_available()
     if interpret_triton:
         os.environ.setdefault('TRITON_INTERPRET', '1')
+    else:
+        os.environ['TRITON_INTERPRET'] = '0'
     import transformers  # noqa: F401
     restated = os.path.join(_HERE, 'third_party_restated')
     for p in (REFERENCE_ROOT, restated):

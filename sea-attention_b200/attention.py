@@ -10,7 +10,9 @@ What runs on the device per call (causal prefill, the reference's `benchmarking`
 :518-573, 595-673, 774-947, 1036-1042, 1151-1173, 1208-1282):
   performer (3 launches) -> predictor MLP -> conv x2 -> predictor tail (+softmax) -> grouped top-k ->
   CSR count+scan -> CSR fill -> fused sparse attention (+scaler, +running-mean mix, +permute)
-with ZERO host synchronisations (the reference has >= 8 `.item()`/`nonzero()` syncs).
+with no host synchronisation inside the chain (the reference has >= 8 `.item()`/`nonzero()` syncs).  The one host
+read a default call does is the padding check (`check_padding`, N*T booleans); set `check_padding = False` for sync-free
+calls / CUDA-graph capture.  `output_attentions` adds one nnz read-back (the reference's own `.item()`).
 """
 import math
 import os
@@ -144,6 +146,21 @@ def _csr_alloc_upper_bound(H: int, k: int, P: int, T_SRC: int, T_DST: int, k_per
     return int(per_row.sum().item()) + 32
 
 
+def _csr_outputs(crow, col, pvals, size):
+    """partial_attention_mask / partial_attention_probs exactly as the reference returns them (causal_resize_m_to_t.py:757-762):
+    batched CSR with int64 indices and Z = max_n nnz_n columns (rows of items with fewer entries are zero-padded at the tail).
+    The kernels work on int32 indices in a buffer allocated at a shape-derived upper bound; `output_attentions` is off the hot
+    path, so the nnz is read back once here (the reference's own `.item()`, :667) and the buffers are trimmed."""
+    Z = int(crow[:, -1].max().item())
+    crow64, col64 = crow.to(torch.int64), col[:, :Z].to(torch.int64).contiguous()
+    ones = torch.ones((col64.shape[0], Z), dtype=torch.float32, device=col.device)
+    vals = pvals[:, :Z].contiguous()
+    if col64.shape[0] > 1:       # the tail past an item's own nnz must be zero (it is uninitialised in the over-allocated buffer)
+        dead = torch.arange(Z, device=col.device).view(1, Z) >= crow64[:, -1:].to(col.device)
+        col64.masked_fill_(dead, 0)
+    return torch.sparse_csr_tensor(crow64, col64, ones, size=size), torch.sparse_csr_tensor(crow64, col64, vals, size=size)
+
+
 class PerlinAttention(nn.Module):
     def __init__(self, config, perlin_config: PerlinAttentionConfig = None):
         super().__init__()
@@ -236,6 +253,35 @@ class PerlinAttention(nn.Module):
                       'conv3_w': f(net[5].weight), 'conv3_b': f(net[5].bias)})
         return w
 
+    # ------------------------------------------------------------------------------------------------ weight packings
+    def freeze_packed_weights(self, on: bool = True):
+        """Declare the predictor weights constant (inference loops, CUDA-graph capture, benchmarks): the bf16 packings and the
+        zero-padded conv weights made by the next forward are reused by later ones.  Not frozen (default): they are re-made on
+        every call, so ANY way of writing a parameter -- including `.data` writes, which bump no version counter -- is seen."""
+        self._packed.freeze(on)
+        self._padded_cache = None
+        return self
+
+    def invalidate_packed(self):
+        """Drop every cached weight packing (call after modifying parameters of a frozen module)."""
+        self._packed.invalidate()
+        self._padded_cache = None
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        self.invalidate_packed()
+        return super()._load_from_state_dict(*args, **kwargs)
+
+    def _apply(self, fn, *args, **kwargs):
+        if getattr(self, '_packed', None) is not None:
+            self.invalidate_packed()
+        return super()._apply(fn, *args, **kwargs)
+
+    def train(self, mode: bool = True):
+        if mode and getattr(self, '_packed', None) is not None:
+            self._packed.freeze(False)
+            self._padded_cache = None
+        return super().train(mode)
+
     def _padded_conv_weights(self, w, C, H):
         """Zero-padded copies of the CNN weights for the 64-channel tcgen05 kernels (conv 3x3: [C,C,5,3] -> [64,64,5,3]; 1x1:
         [H,C] -> [32,64]); cached until a source parameter changes."""
@@ -243,7 +289,7 @@ class PerlinAttention(nn.Module):
         src = (net[0].module.weight, net[0].module.bias, net[2].module.weight, net[2].module.bias, net[5].module.weight, net[5].module.bias)
         stamp = tuple((int(t.data_ptr()), int(t._version)) for t in src)
         hit = self._padded_cache
-        if hit is not None and hit[0] == stamp:
+        if hit is not None and hit[0] == stamp and self._packed.frozen:
             return hit[1]
         dev = w['conv1_w'].device
         out = {}
@@ -392,9 +438,7 @@ class PerlinAttention(nn.Module):
                                                   head_ptr=head_ptr)
         partial_probs = partial_mask = None
         if self.output_attentions:
-            size = (N, T, H * T)
-            partial_mask = torch.sparse_csr_tensor(crow, col, torch.ones((N, Z), dtype=torch.float32, device=q.device), size=size)
-            partial_probs = torch.sparse_csr_tensor(crow, col, pvals, size=size)
+            partial_mask, partial_probs = _csr_outputs(crow, col, pvals, (N, T, H * T))
         return PerlinAttentionOutput(
             loss=0, context_layer=context, partial_attention_probs=partial_probs, partial_attention_mask=partial_mask,
             estimated_attention_probs_m=probs, estimated_attention_probs=probs, dense_attention_probs=None,
@@ -436,6 +480,9 @@ class PerlinAttention(nn.Module):
             raise SeaError('v_for_atten must alias v (LoRA-in-approximation is not implemented)')
         if last_state.t + T_new != T_SRC:
             raise SeaError(f'state has consumed {last_state.t} tokens, got {T_new} new queries but {T_SRC} keys')
+        if T_SRC > self.v_eye_learned_causal.shape[2]:
+            raise SeaError(f'decode position {T_SRC} exceeds max_position_embeddings = {self.v_eye_learned_causal.shape[2]} '
+                           f'(v_eye_learned_causal has no row for it)')
         # functional update like the reference: the caller's state object is left untouched.  Only the Performer sums are advanced in
         # place by the kernel, so only they are copied; the CNN windows are rebuilt (torch.cat) every step anyway.
         st = PerlinAttentionState(t=last_state.t, performer=last_state.performer.clone(), cnn_in_win=last_state.cnn_in_win,
@@ -535,9 +582,7 @@ class PerlinAttention(nn.Module):
             context, pvals = ops.sparse_attention(crow, col, q_for_score, k_for_score, v, scales, avg,
                                                   use_scaler=pc.partial_attention_scaler, want_probs=self.output_attentions, head_ptr=head_ptr)
             if self.output_attentions:
-                size = (N, T, H * T)
-                partial_mask = torch.sparse_csr_tensor(crow, col, torch.ones((N, Z), dtype=torch.float32, device=q.device), size=size)
-                partial_probs = torch.sparse_csr_tensor(crow, col, pvals, size=size)
+                partial_mask, partial_probs = _csr_outputs(crow, col, pvals, (N, T, H * T))
         return PerlinAttentionOutput(
             loss=0, context_layer=context, partial_attention_probs=partial_probs, partial_attention_mask=partial_mask,
             estimated_attention_probs_m=probs, estimated_attention_probs=probs, dense_attention_probs=None,

@@ -1,5 +1,6 @@
 """Host-side mirror of the reference operator package `src/models/perlin_attention/ops/__init__.py:1-7`
 (same names, argument meaning and error behaviour), backed by the sm_100a kernels of libsea_b200.so.
+Host synchronisations: none in the stage ops; the standalone CSR ops read the nnz back once, like the reference's `.item()`.
 
 Every function takes CUDA tensors, allocates its outputs with torch (ownership convention of the
 reference: ops return fresh tensors, inputs are never mutated) and launches on torch's current stream.
@@ -36,6 +37,33 @@ def _cuda(*tensors):
 
 def _p(t: Optional[torch.Tensor]) -> int:
     return 0 if t is None else t.data_ptr()
+
+
+def _dense(t: torch.Tensor, dtype=None) -> torch.Tensor:
+    """Stage ops hand raw pointers with implicit dense strides to the library: make the tensor contiguous (and of the
+    expected dtype) instead of silently reading a strided view as if it were dense."""
+    if t is None:
+        return None
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _on_tensor_device(fn):
+    """Runs an op with the device of its first CUDA tensor argument current, so that the stream handed to the library and the
+    context the kernels launch in belong to the tensors' device (modules placed on a non-current GPU, e.g. HF `device_map`)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(*args, **kwargs):
+        for a in args:
+            if isinstance(a, torch.Tensor) and a.is_cuda:
+                if a.device.index == torch.cuda.current_device():
+                    break
+                with torch.cuda.device(a.device):
+                    return fn(*args, **kwargs)
+        return fn(*args, **kwargs)
+    return wrapped
 
 
 def _inner_contig(t: torch.Tensor) -> torch.Tensor:
@@ -270,18 +298,36 @@ def performer_causal(q, k, v, pos_emb, proj, want_cumavg=True, force_simt=False)
 
 
 class PackedWeights:
-    """Per-module cache of the bf16 weight packings the tensor-core kernels keep in their workspace: a packing is reused
-    (weight pointer NULL in the C call) as long as the source tensors' (data_ptr, _version) are unchanged."""
+    """Per-module holder of the bf16 weight packings the tensor-core kernels keep in their workspace.
+
+    Default (not frozen): the packing kernels run on EVERY call (three tiny launches, ~10 us) -- nothing is trusted across calls,
+    because PyTorch offers no reliable change stamp: `Tensor._version` is not bumped by writes through `.data`
+    (`p.data.copy_()`, HF `_init_weights`, DeepSpeed / apex master -> bf16 copies, LoRA merges).
+    `freeze()` (PerlinAttention.freeze_packed_weights) declares the weights constant: packings made by the next call are then
+    reused (weight pointer NULL in the C call) until `invalidate()` -- for inference loops, CUDA-graph capture and the
+    benchmark.  Even when frozen a packing is dropped when a source tensor's (data_ptr, _version) changes."""
 
     def __init__(self):
         self._slots = {}
+        self.frozen = False
+
+    def freeze(self, on: bool = True):
+        self.frozen = bool(on)
+        if not on:
+            self._slots.clear()
+
+    def invalidate(self):
+        self._slots.clear()
 
     def get(self, slot, sources, nbytes, device):
         """-> (workspace tensor, fresh): fresh = the caller must let the kernel re-pack."""
         stamp = tuple((int(t.data_ptr()), int(t._version)) for t in sources) + (str(device), int(nbytes))
         hit = self._slots.get(slot)
-        if hit is not None and hit[0] == stamp:
-            return hit[1], False
+        if hit is not None and hit[0][-2:] == stamp[-2:]:
+            if self.frozen and hit[0] == stamp:
+                return hit[1], False
+            self._slots[slot] = (stamp, hit[1])
+            return hit[1], True               # same buffer (stable address under CUDA graphs), packed again
         ws = torch.empty((nbytes,), dtype=torch.uint8, device=device)
         self._slots[slot] = (stamp, ws)
         return ws, True
@@ -345,6 +391,7 @@ def causal_conv3x3_dil2_relu(x, weight, bias, force_simt=False, packed: 'PackedW
     weight fp32 in the reference layout [O,C,5,3].  bf16 with C=O=64 runs the tcgen05 implicit-GEMM kernel,
     everything else the fp32 SIMT kernel."""
     _cuda(x, weight, bias)
+    x, weight, bias = _dense(x), _dense(weight, torch.float32), _dense(bias, torch.float32)
     N, T, W, C = x.shape
     O = weight.shape[0]
     y = torch.empty((N, T, W, O), dtype=x.dtype, device=x.device)
@@ -361,6 +408,7 @@ def causal_conv3x3_dil2_relu(x, weight, bias, force_simt=False, packed: 'PackedW
 def conv1x1_umma(x, weight, bias, packed: 'PackedWeights' = None, slot: str = 'conv1x1', src=None):
     """1x1 CausalConv2d(64 -> 32) before the upsample, tcgen05: x bf16 [N,T,W,64] -> y fp32 [N,T,W,32]."""
     _cuda(x, weight, bias)
+    x, weight, bias = _dense(x), _dense(weight, torch.float32), _dense(bias, torch.float32)
     N, T, W, C = x.shape
     O = weight.shape[0]
     y = torch.empty((N, T, W, O), dtype=torch.float32, device=x.device)
@@ -379,6 +427,7 @@ def causal_conv3x3_relu_conv1x1(x, weight, bias, weight3, bias3, packed: 'Packed
     """a5: the second CausalConv2d(64,64,3,dilation 2)+ReLU and the 1x1 CausalConv2d(64 -> 32) behind it in one tcgen05 kernel:
     x bf16 [N,T,W,64] -> y3 fp32 [N,T,W,32]; the activation between the two convolutions never reaches HBM."""
     _cuda(x, weight, bias, weight3, bias3)
+    x, weight, bias, weight3, bias3 = _dense(x), _dense(weight, torch.float32), _dense(bias, torch.float32), _dense(weight3, torch.float32), _dense(bias3, torch.float32)
     N, T, W, C = x.shape
     O, O3 = weight.shape[0], weight3.shape[0]
     y3 = torch.empty((N, T, W, O3), dtype=torch.float32, device=x.device)
@@ -400,6 +449,9 @@ def performer_state_build(k, v, pos_emb, proj, state: torch.Tensor):
     _cuda(k, v, pos_emb, proj, state)
     N, H, T, D = k.shape
     k, v = _inner_contig(k), _inner_contig(v)
+    pos_emb, proj = _dense(pos_emb.reshape(-1, D), torch.float32), _dense(proj, torch.float32)
+    if pos_emb.shape[0] < T:
+        raise SeaError(f'v_eye_learned_causal holds {pos_emb.shape[0]} positions < T={T}')
     _lib.call('sea_performer_state_build', k.data_ptr(), k.stride(0), k.stride(1), k.stride(2), v.data_ptr(), v.stride(0), v.stride(1), v.stride(2),
               pos_emb.data_ptr(), proj.data_ptr(), _dtype_code(k), state.data_ptr(), N, H, T, D, proj.shape[0], _stream())
     return state
@@ -412,6 +464,10 @@ def performer_causal_state(q, k, v, pos_emb, proj, state: torch.Tensor, t0: int,
     N, H, T_new, D = q.shape
     F = proj.shape[0]
     q, k, v = _inner_contig(q), _inner_contig(k), _inner_contig(v)
+    pos_emb, proj = _dense(pos_emb.reshape(-1, D), torch.float32), _dense(proj, torch.float32)
+    if pos_emb.shape[0] < int(t0) + T_new:
+        raise SeaError(f'v_eye_learned_causal holds {pos_emb.shape[0]} positions < t0 + T_new = {int(t0) + T_new} '
+                       f'(decode past max_position_embeddings)')
     ctx = torch.empty((N, H, T_new, 2 * D), dtype=q.dtype, device=q.device)
     avg = torch.empty((N, H, T_new, D), dtype=q.dtype, device=q.device) if want_cumavg else None
     _lib.call('sea_performer_causal_state_fwd', q.data_ptr(), q.stride(0), q.stride(1), q.stride(2), k.data_ptr(), k.stride(0), k.stride(1), k.stride(2),
@@ -435,6 +491,7 @@ def predictor_tail_topk(y3, bias, ln_w, ln_b, k_per_row, P: int, want_probs=True
     expand = (workspace, D, k_clamp, dtype): also fuses the mask expansion of the block attention (causal prefill) into the kernel;
     pass the same workspace to sparse_attention_from_bits(..., expanded=workspace)."""
     _cuda(y3, bias, ln_w, ln_b, k_per_row)
+    y3, bias, ln_w, ln_b = _dense(y3, torch.float32), _dense(bias, torch.float32), _dense(ln_w, torch.float32), _dense(ln_b, torch.float32)
     N, T, W, H = y3.shape
     probs = torch.empty((N, H, T, P), dtype=torch.float32, device=y3.device) if want_probs else None
     bits = torch.empty((N, T, (H * P) // 32), dtype=torch.int32, device=y3.device) if want_bits else None
@@ -459,6 +516,7 @@ def tail_expand_supported(H: int, P: int) -> bool:
 def predictor_tail(x, weight, bias, ln_w, ln_b, P: int, want_scores=False):
     """a5 tail + a6 -> probs fp32 [N,H,T,P] (and the pre-softmax scores when asked)."""
     _cuda(x, weight)
+    x, weight, bias, ln_w, ln_b = _dense(x), _dense(weight, torch.float32), _dense(bias, torch.float32), _dense(ln_w, torch.float32), _dense(ln_b, torch.float32)
     N, T, W, C = x.shape
     H = weight.shape[0]
     probs = torch.empty((N, H, T, P), dtype=torch.float32, device=x.device)
@@ -611,6 +669,7 @@ def performer_noncausal(q, k, v, proj):
 def conv3x3_cl(x, weight, bias, stride_t=1, up=1, relu=True):
     """Conv2d(C,O,3,padding=1,stride=(stride_t,1)) on channels-last x [N,Tin,W,C] (rows nearest-upsampled by `up` first)."""
     _cuda(x, weight, bias)
+    x, weight, bias = _dense(x), _dense(weight, torch.float32), _dense(bias, torch.float32)
     N, Tin, W, C = x.shape
     O = weight.shape[0]
     Tout = (Tin * up + 2 - 3) // stride_t + 1
@@ -623,6 +682,7 @@ def conv3x3_cl(x, weight, bias, stride_t=1, up=1, relu=True):
 def bert_tail(y, T: int, P: int, want_scores=False):
     """bilinear resize of channels-last y [N,Tin,Win,H] to (T,P) + softmax(P) -> probs fp32 [N,H,T,P]."""
     _cuda(y)
+    y = _dense(y)
     N, Tin, Win, H = y.shape
     probs = torch.empty((N, H, T, P), dtype=torch.float32, device=y.device)
     scores = torch.empty_like(probs) if want_scores else None
@@ -660,3 +720,10 @@ def bert_avg(probs, v):
     _lib.call('sea_bert_avg_fwd', probs.contiguous().data_ptr(), v.data_ptr(), v.stride(0), v.stride(1), v.stride(2), _dtype_code(v), avg.data_ptr(),
               N, H, T, P, D, _stream())
     return avg
+
+
+# every public op runs on the device of its tensors (see _on_tensor_device)
+for _name, _fn in list(globals().items()):
+    if callable(_fn) and not _name.startswith('_') and getattr(_fn, '__module__', None) == __name__ and not isinstance(_fn, type):
+        globals()[_name] = _on_tensor_device(_fn)
+del _name, _fn

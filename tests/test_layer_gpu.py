@@ -178,7 +178,9 @@ def test_layer_forward_bf16(sea):
 
 
 def test_packed_weight_cache_follows_parameter_updates(sea):
-    """The tensor-core kernels keep bf16 weight packings per module; an in-place parameter update must invalidate them."""
+    """The tensor-core kernels keep bf16 weight packings per module.  Not frozen (default) they are re-made on every call, so every
+    way of writing a parameter is seen -- including `.data` writes, which bump no version counter (HF `_init_weights`, DeepSpeed
+    master -> bf16 copies, LoRA merges).  Frozen, they are reused until invalidate_packed() / load_state_dict / .to()."""
     import copy
     N, H, d, T, P, k, nbf = 1, 32, 64, 128, 64, 16, 8          # H | 128, W = 16: tcgen05 MLP + conv path
     mod, _ = _random_sd(sea, H, d, T, P, k, nbf, seed=5)
@@ -188,16 +190,49 @@ def test_packed_weight_cache_follows_parameter_updates(sea):
     q, kk, v = mk(d ** -0.5), mk(1.0), mk(1.0)
     am = so.causal_additive_mask(T, torch.bfloat16, N).to(DEV)
     run = lambda m: m(q, kk, v, q, kk, v, q, kk, am, None, None).estimated_attention_probs.float().cpu()
+
+    def fresh_result(m):
+        f = copy.deepcopy(m)
+        f._packed = sea.ops.PackedWeights()
+        f._padded_cache = None
+        return run(f)
     p0 = run(mod)
-    torch.testing.assert_close(run(mod), p0, rtol=0, atol=0)                       # second call: cached packings, same result
-    with torch.no_grad():
+    torch.testing.assert_close(run(mod), p0, rtol=0, atol=0)
+    with torch.no_grad():                                       # tracked in-place update
         mod.attention_predictor_cnn[1].module.net[0].module.weight.mul_(1.7)
         mod.attention_predictor_enc[0].weight.mul_(0.6)
     p1 = run(mod)
-    fresh = copy.deepcopy(mod)
-    fresh._packed = sea.ops.PackedWeights()
-    torch.testing.assert_close(p1, run(fresh), rtol=0, atol=0)
+    torch.testing.assert_close(p1, fresh_result(mod), rtol=0, atol=0)
     assert float((p1 - p0).abs().max()) > 0
+    # untracked `.data` writes (no _version bump, same data_ptr)
+    mod.attention_predictor_cnn[1].module.net[2].module.weight.data.mul_(0.5)
+    mod.attention_predictor_dec_row[0].weight.data.add_(0.01)
+    p2 = run(mod)
+    torch.testing.assert_close(p2, fresh_result(mod), rtol=0, atol=0)
+    assert float((p2 - p1).abs().max()) > 0
+    # frozen: packings are reused (same result, fewer launches) ...
+    mod.freeze_packed_weights()
+    run(mod)
+    sea._lib.LAUNCH_COUNT = 0
+    p3 = run(mod)
+    frozen_launches = sea._lib.LAUNCH_COUNT
+    torch.testing.assert_close(p3, p2, rtol=0, atol=0)
+    # ... a `.data` write is then invisible by contract until invalidate_packed()
+    mod.attention_predictor_enc[0].weight.data.mul_(1.3)
+    torch.testing.assert_close(run(mod), p3, rtol=0, atol=0)
+    mod.invalidate_packed()
+    p4 = run(mod)
+    torch.testing.assert_close(p4, fresh_result(mod), rtol=0, atol=0)
+    assert float((p4 - p3).abs().max()) > 0
+    # load_state_dict invalidates too
+    sd = {k_: v_.clone() for k_, v_ in mod.state_dict().items()}
+    sd['attention_predictor_enc.0.weight'] = sd['attention_predictor_enc.0.weight'] * 0.7
+    mod.load_state_dict(sd)
+    torch.testing.assert_close(run(mod), fresh_result(mod), rtol=0, atol=0)
+    mod.freeze_packed_weights(False)
+    sea._lib.LAUNCH_COUNT = 0
+    run(mod)
+    assert sea._lib.LAUNCH_COUNT > frozen_launches              # the packing kernels run again
 
 
 def test_unsupported_modes_fail_loudly(sea):

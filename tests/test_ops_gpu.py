@@ -285,6 +285,31 @@ def test_attention_from_bits_equals_csr_path(sea, N, H, T_DST, T_SRC, P, k, d, c
         assert d != 64 or (T_SRC + P - 1) // P + 1 > k
 
 
+@pytest.mark.parametrize('H,T,P,k,kernel', [(2, 2048, 256, 64, 'block'), (3, 1000, 64, 32, 'block'), (2, 2048, 256, 64, 'gather')])
+def test_attention_from_bits_matches_oracle_directly(sea, H, T, P, k, kernel):
+    """The tcgen05 block attention (and the gather kernel) against the CPU oracle's flat-CSR chain itself
+    (flat_csr_masked_bmm -> softmax -> elmul -> sdbmm -> mix; attention.py:1151-1173, 1237-1250), not via the repo's CSR kernel."""
+    N, d = 1, 64
+    g = torch.Generator().manual_seed(T + P)
+    probs = torch.softmax(torch.randn(N, H, T, P, generator=g) * 2, -1)
+    mask = so.topk_mask_causal_batch(probs, k)
+    crow, col, Z = so.resize_from_m_to_t_csr(mask, k, T, True)
+    q = (torch.randn(N, H, T, d, generator=g) * d ** -0.5).bfloat16()
+    kk = torch.randn(N, H, T, d, generator=g).bfloat16()
+    v = torch.randn(N, H, T, d, generator=g).bfloat16()
+    scales = torch.randn(N, H, T, 2, generator=g)
+    avg = (v.float().cumsum(-2) / torch.arange(1, T + 1).view(1, 1, T, 1)).bfloat16()
+    s = so.flat_csr_masked_bmm(q.float(), kk.float(), crow, col)
+    p = so.flat_csr_elmul_rowscale(so.flat_csr_softmax(s, crow, col, H, T), crow, col, torch.sigmoid(scales[..., 0]), T)
+    ctx = so.flat_csr_sdbmm(p, crow, col, v.float(), H)
+    a = torch.sigmoid(scales[..., 1:2])
+    ref = (ctx * a + (1 - a) * avg.float()).permute(0, 2, 1, 3).reshape(N, T, H * d)
+    bits = sea.ops.mask_to_bits(mask.to(DEV))
+    out = sea.ops.sparse_attention_from_bits(bits, q.to(DEV), kk.to(DEV), v.to(DEV), scales.to(DEV), avg.to(DEV), P, k, True, True, kernel=kernel)
+    torch.testing.assert_close(out.float().cpu(), ref, rtol=2e-2, atol=1e-2)
+    assert float((out.float().cpu() - ref).abs().mean()) < 2e-3
+
+
 def test_attention_from_bits_strided_inputs(sea):
     """q / k / v as transposed views of [N,T,H,d] buffers (what a caller gets from .view(...).transpose(1, 2)): the TMA tensor
     maps and the gather kernels take the strides as they are."""

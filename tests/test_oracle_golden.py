@@ -5,7 +5,9 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import golden_layer, load_golden
+import os
+
+from conftest import ROOT, golden_layer, load_golden
 from oracle import sea_oracle as so
 
 LAYERS = ['layer_causal_h4_t128', 'layer_causal_h3_t100']
@@ -141,3 +143,26 @@ def test_backward_oracle_forward_matches_reference_dense_path(name):
     fp = so.sparse_attention_grads(alive, qp, k, v, scales, dout)[0].double().sum()
     fm = so.sparse_attention_grads(alive, qm, k, v, scales, dout)[0].double().sum()
     assert abs(float((fp - fm) / (2 * eps)) - float(dq[0, 1, 7, 3])) < 5e-3 * max(1.0, abs(float(dq[0, 1, 7, 3])))
+
+
+@pytest.mark.parametrize('causal,d,F,T', [(True, 64, 33, 96), (True, 32, 27, 50), (False, 64, 266, 40), (False, 16, 11, 24)])
+def test_performer_restatements_pinned_to_in_tree_jax_original(causal, d, F, T):
+    """The only Performer specification under /root/reference is the JAX original it vendors
+    (_lra_benchmarks/models/performer/performer_attention.py); oracle/jax_performer_numpy.py is its line-by-line fp64 numpy
+    port.  Both restatements the checker relies on -- the `performer_pytorch.FastAttention` stand-in that the imported
+    reference ran with when the fixtures were generated, and sea_oracle.performer_* -- must equal it (the two published
+    implementations differ only in how the normaliser is stabilised, a ~1e-6-relative term)."""
+    import sys
+    from oracle import jax_performer_numpy as jp
+    sys.path.insert(0, os.path.join(ROOT, 'oracle', 'third_party_restated'))
+    import performer_pytorch as pp
+    g = torch.Generator().manual_seed(d + T)
+    q = torch.randn(1, 2, T, d, generator=g, dtype=torch.float64) * (d ** -0.5 if causal else 1.0)
+    k = torch.randn(1, 2, T, d, generator=g, dtype=torch.float64)
+    v = torch.randn(1, 2, T, 2 * d, generator=g, dtype=torch.float64)
+    fa = pp.FastAttention(d, F, causal=causal, generalized_attention=causal).double()
+    proj = fa.projection_matrix
+    want = torch.from_numpy(jp.fast_attention(q.numpy(), k.numpy(), v.numpy(), proj.numpy(), causal))
+    torch.testing.assert_close(fa(q, k, v), want, rtol=1e-5, atol=1e-8)
+    mine = so.performer_causal(q, k, v, proj) if causal else so.performer_noncausal(q, k, v, proj)
+    torch.testing.assert_close(mine.double(), want, rtol=2e-4, atol=1e-6)       # sea_oracle computes the features in fp32

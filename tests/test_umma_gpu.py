@@ -118,9 +118,16 @@ def test_mlp_umma_matches_simt(sea, N, H, T, P):
     a_in, a_sc, _ = sea.ops.predictor_mlp(ctx, v, w, S, W)
     b_in, b_sc, _ = sea.ops.predictor_mlp(ctx, v, w, S, W, force_simt=True)
     torch.cuda.synchronize()
-    # bf16 operands (weights and the GELU output are rounded to bf16 before each GEMM): 2e-2-class tolerance
-    torch.testing.assert_close(a_sc.cpu(), b_sc.cpu(), rtol=3e-2, atol=3e-2)
-    torch.testing.assert_close(a_in.float().cpu(), b_in.float().cpu(), rtol=5e-2, atol=5e-2)
+    # bf16 operands (weights and the GELU output are rounded to bf16 before each GEMM): the north star's bf16 tolerance, 2e-2,
+    # against the repo's own SIMT kernel ...
+    torch.testing.assert_close(a_sc.cpu(), b_sc.cpu(), rtol=2e-2, atol=2e-2)
+    torch.testing.assert_close(a_in.float().cpu(), b_in.float().cpu(), rtol=2e-2, atol=2e-2)
+    # ... and directly against the CPU oracle (attention.py:190-196,242-245,289-291 + the CNN's first LayerNorm, :268)
+    sd = {k_: v_.detach().float().cpu() for k_, v_ in mod.state_dict().items()}
+    t_ref = so.predictor_enc(torch.cat([ctx.float().cpu(), v.float().cpu()], -1), sd)
+    x0 = so.layer_norm(so.predictor_dec_row(t_ref, sd, S), sd['attention_predictor_cnn.0.module.weight'], sd['attention_predictor_cnn.0.module.bias'])
+    torch.testing.assert_close(a_sc.cpu(), so.predictor_dec_scaler(t_ref, sd), rtol=2e-2, atol=2e-2)
+    torch.testing.assert_close(a_in.float().cpu().permute(0, 3, 1, 2), x0, rtol=2e-2, atol=2e-2)
     if 2 * H < 64:      # zero-padded channels for the 64-channel tcgen05 convolutions (OPT-125m: H = 12)
         p_in, p_sc, _ = sea.ops.predictor_mlp(ctx, v, w, S, W, c_out=64)
         assert p_in.shape == (N, T, W, 64)
