@@ -270,24 +270,17 @@ SEA_API int sea_sparse_attention_bits_fwd(const uint32_t* mask_bits,
                                           const float* scales, const void* cumavg, int64_t avg_sh, int64_t avg_st, int use_scaler, int dtype, void* out,
                                           int N, int H, int T_DST, int T_SRC, int D, int P, int k_clamp, int is_causal, void* stream);
 
-/* a8 + a9-a14 fused, short-context form (csrc/block_attn.cu): the same result as sea_sparse_attention_bits_fwd, computed as a
- * tile-skipping, element-masked flash attention: the top-k bit mask is first expanded to the dense bit-packed
- * partial_attention_mask (one u64 per head / query row / 64-token tile, in `workspace`), then 128-row query blocks share
- * TMA-staged K/V tiles.  Replaces flat_csr_masked_bmm -> flat_csr_softmax -> flat_csr_elmul -> flat_csr_sdbmm
- * (reference attention.py:1159-1173) when the caller does not need the CSR tensors.
+/* a8 + a9-a14 fused, short-context form (csrc/block_attn_umma.cu, csrc/block_attn.cu): the same result as
+ * sea_sparse_attention_bits_fwd, computed as a tile-skipping, element-masked flash attention in which 128-row query blocks share
+ * TMA-staged K/V tiles.  Replaces resize_from_m_to_t_csr -> flat_csr_masked_bmm -> flat_csr_softmax -> flat_csr_elmul ->
+ * flat_csr_sdbmm (reference attention.py:1036-1042, 1159-1173) when the caller does not need the CSR tensors.
+ *   bf16, T_SRC <= 4096: tcgen05 kernel; the a8 interpolation (causal_resize_m_to_t.py:648-762) runs inside it, straight from
+ *     the top-k bit mask -- `workspace` is not touched (sea_block_attention_workspace_bytes returns a token 16 bytes);
+ *   fp16 or T_SRC <= 8192: mma.sync kernel over the dense bit-packed partial_attention_mask (one u64 per head / query row /
+ *     64-token tile) that an expansion kernel first writes into `workspace`.
  * Supported iff sea_block_attention_workspace_bytes(...) > 0: 16-bit activations, D == 64, P % 32 == 0, P <= 1024,
  * no clamped pixel (ceil(T_SRC / P) + 1 <= k_clamp) and T_SRC <= 8192 (work is O(T^2) in the worst case).
- * `workspace` must be 16-byte aligned; it is overwritten -- unless mask_bits == NULL, which means the workspace was already filled
- * by sea_predictor_tail_topk_expand_fwd (the expansion fused into the top-k kernel). */
-/* sea_predictor_tail_topk_fwd (causal prefill) with the mask expansion of sea_block_attention_fwd fused in: besides probs
- * and the top-k bit mask it fills `workspace` (>= sea_block_attention_workspace_bytes(N, H, T, T, D, P, k_clamp, dtype)) with the
- * dense bit-packed partial_attention_mask and the tile activity; sea_block_attention_fwd is then called with mask_bits = NULL
- * and the same workspace.  Needs the register-resident top-k (H % 8 == 0, (H/8) * (P/32) <= 32). */
-SEA_API int sea_predictor_tail_expand_supported(int H, int P);
-SEA_API int sea_predictor_tail_topk_expand_fwd(const float* y3, const float* bias, const float* ln_w, const float* ln_b,
-                                               const float* k_per_row, float* probs, uint32_t* mask_bits, int k_clamp,
-                                               int N, int H, int T, int W, int P, int D, int dtype, void* workspace, int64_t workspace_bytes,
-                                               void* stream);
+ * `workspace` must be 16-byte aligned; it is overwritten.  mask_bits must not be NULL. */
 SEA_API int64_t sea_block_attention_workspace_bytes(int N, int H, int T_DST, int T_SRC, int D, int P, int k_clamp, int dtype);
 SEA_API int sea_block_attention_fwd(const uint32_t* mask_bits,
                                     const void* q, int64_t q_sn, int64_t q_sh, int64_t q_st,

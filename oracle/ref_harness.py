@@ -103,7 +103,7 @@ def load_reference(interpret_triton=None):
                     return tl.where(x64 < 0, -r, r).to(tl.float32)
                 tl.math.round = _round_half_away
             else:
-                from triton.language.extra import libdevice
+                from triton.language.extra.cuda import libdevice
                 tl.math.round = libdevice.round
     except Exception:  # triton missing: dense path still works
         pass

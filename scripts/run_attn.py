@@ -27,3 +27,6 @@ for _ in range(iters):
     out = ops.sparse_attention_from_bits(bits, q, kk, v, scales, avg, P, k, True, True)
 e1.record(); torch.cuda.synchronize()
 print('attn us', e0.elapsed_time(e1) / iters * 1000, 'mean|out|', float(out.float().abs().mean()))
+ref = ops.sparse_attention_from_bits(bits, q, kk, v, scales, avg, P, k, True, True, kernel='gather')
+dd = (out.float() - ref.float()).abs()
+print('vs gather kernel: max abs diff', float(dd.max()), 'mean', float(dd.mean()), 'nan', int(torch.isnan(out.float()).sum()))

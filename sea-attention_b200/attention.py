@@ -225,7 +225,6 @@ class PerlinAttention(nn.Module):
         self.v_eye_learned_causal = nn.Parameter(torch.randn((1, 1, max_pos, d)))
         self._shape_cache = {}
         self._packed = ops.PackedWeights()
-        self.fuse_mask_expansion = False
         self._padded_cache = None
 
     # ------------------------------------------------------------------------------------------------
@@ -395,20 +394,12 @@ class PerlinAttention(nn.Module):
             capture['cnn_in'], capture['conv1'] = cnn_in, y1
         # a5 .. a7
         kpr = k_per_row.repeat(N) if N > 1 else k_per_row
-        expanded_ws = None
         if tc_tail:
             if y3 is None:
                 y3 = ops.conv1x1_umma(y, cw['conv3_w'], cw['conv3_b'], packed=pk, slot='conv3', src=net[5].module.weight)
             if pad_c:
                 y3 = y3[..., :H].contiguous()
-            needs_grad = torch.is_grad_enabled() and any(t_.requires_grad for t_ in (q_for_score, k_for_score, v))
-            if (self.fuse_mask_expansion and not self.output_attentions and not needs_grad and ops.attention_bits_supported(q.dtype, d, P)
-                    and ops.tail_expand_supported(H, P)):
-                # optional: the dense bit-packed mask the block attention consumes is written by the top-k kernel itself (measured
-                # slower than the separate expansion kernel at the north-star shape: 0.616 vs 0.581 ms/step, so off by default)
-                expanded_ws = ops.block_attention_workspace(N, H, T, T, d, P, pc.k, q.dtype, q.device)
-            res = ops.predictor_tail_topk(y3, w['conv3_b'], w['out_ln_w'], w['out_ln_b'], kpr, P, count_k=pc.k if self.output_attentions else 0,
-                                          expand=None if expanded_ws is None else (expanded_ws, d, pc.k, q.dtype))
+            res = ops.predictor_tail_topk(y3, w['conv3_b'], w['out_ln_w'], w['out_ln_b'], kpr, P, count_k=pc.k if self.output_attentions else 0)
             probs, bits, crow_counts = res if len(res) == 3 else (res[0], res[1], None)
         else:
             probs, _ = ops.predictor_tail(y, w['conv3_w'], w['conv3_b'], w['out_ln_w'], w['out_ln_b'], P)
@@ -425,7 +416,7 @@ class PerlinAttention(nn.Module):
                                                                   use_scaler=pc.partial_attention_scaler, is_causal=True)
             else:
                 context = ops.sparse_attention_from_bits(bits, q_for_score, k_for_score, v, scales, cumavg, P, pc.k,
-                                                         use_scaler=pc.partial_attention_scaler, is_causal=True, expanded=expanded_ws)
+                                                         use_scaler=pc.partial_attention_scaler, is_causal=True)
             pvals = crow = col = None
             Z = 0
         else:

@@ -420,9 +420,17 @@ using namespace sea;
 
 extern "C" {
 
+// bf16 up to T_SRC = 4096 runs the tcgen05 kernel, which interpolates the mask itself from the top-k bits (no dense mask, no
+// expansion kernel); fp16 and longer rows run the mma.sync kernel over the dense bit mask written by expand_mask_kernel.
+static bool use_umma_kernel(int dtype, int T_SRC) {
+    static const bool force_mma_sync = getenv("SEA_ATTN_MMA_SYNC") != nullptr;      // A/B timing switch
+    return dtype == SEA_DTYPE_BF16 && !force_mma_sync && T_SRC <= 4096;              // measured: mma.sync ahead at T = 8192
+}
+
 int64_t sea_block_attention_workspace_bytes(int N, int H, int T_DST, int T_SRC, int D, int P, int k_clamp, int dtype) {
     if (dtype != SEA_DTYPE_BF16 && dtype != SEA_DTYPE_F16) return 0;
     if (N <= 0 || H <= 0 || H > 64 || T_DST <= 0 || T_SRC < T_DST || !block_attention_eligible(D, T_SRC, P, k_clamp)) return 0;      // (H <= 64: 6-bit head field of the expansion's pixel list)
+    if (use_umma_kernel(dtype, T_SRC)) return 16;                                                          // no workspace use; > 0 = "supported"
     return (int64_t) N * H * T_DST * mask_row_words(T_SRC) * 8 + mask_act_bytes(N, H, T_DST, T_SRC);      // dense bit mask + tile activity
 }
 
@@ -445,12 +453,18 @@ int sea_block_attention_fwd(const uint32_t* mask_bits,
                   ((((uintptr_t) q) | ((uintptr_t) k) | ((uintptr_t) v) | ((uintptr_t) out) | ((uintptr_t) cumavg) | ((uintptr_t) workspace)) & 15) == 0,
                   "sea_block_attention_fwd: rows must be 16-byte aligned");
     cudaStream_t s = (cudaStream_t) stream;
+    const int p_lg = exact_edge_shift(P, T_SRC);      // integer pixel edges are exact iff P is a power of two and m * L stays below 2^24
+    if (use_umma_kernel(dtype, T_SRC)) {
+        SEA_CHECK_ARG(mask_bits != nullptr, "sea_block_attention_fwd: the tcgen05 kernel needs the top-k bit mask");
+        return launch_block_attention_umma(mask_bits, P, p_lg, q, q_sn, q_sh, q_st, k, k_sn, k_sh, k_st, v, v_sn, v_sh, v_st, scales, cumavg,
+                                           avg_sh, avg_st, use_scaler, out, N, H, T_DST, T_SRC, is_causal, s);
+    }
     const int W64 = mask_row_words(T_SRC);
     unsigned long long* dmask = reinterpret_cast<unsigned long long*>(workspace);
     uint32_t* tile_act = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(workspace) + (int64_t) N * H * T_DST * W64 * 8);
     const int act_words = mask_act_words(T_SRC);
-    const int p_lg = exact_edge_shift(P, T_SRC);      // integer pixel edges are exact iff P is a power of two and m * L stays below 2^24
-    if (mask_bits != nullptr) {      // nullptr: `workspace` was filled by sea_predictor_tail_topk_expand_fwd (mask expansion fused into the top-k)
+    SEA_CHECK_ARG(mask_bits != nullptr, "sea_block_attention_fwd: null mask_bits");
+    {
         SEA_CUDA_TRY(cudaMemsetAsync(tile_act, 0, (size_t) mask_act_bytes(N, H, T_DST, T_SRC), s), "memset tile activity");
         const size_t smem = (size_t) H * W64 * 8 + (size_t) H * act_words * 4 + (size_t) 8 * 1024 * 2;      // row image + tile activity + per-warp pixel lists
         SEA_CHECK_ARG(smem <= 200 * 1024, "sea_block_attention_fwd: H * T_SRC too large for the mask expansion");
@@ -459,11 +473,7 @@ int sea_block_attention_fwd(const uint32_t* mask_bits,
                                 T_SRC, P, p_lg, is_causal), "expand_mask_kernel launch");
         SEA_CHECK_LAUNCH("expand_mask_kernel");
     }
-    // bf16: the two contractions on tcgen05 / TMEM (block_attn_umma.cu); fp16 (and SEA_ATTN_MMA_SYNC=1, for A/B timing): mma.sync
-    static const bool force_mma_sync = getenv("SEA_ATTN_MMA_SYNC") != nullptr;
-    if (dtype == SEA_DTYPE_BF16 && !force_mma_sync && T_SRC <= 4096)      // measured: tcgen05 0.18 ms vs 0.18 ms at T = 4096, mma.sync ahead at 8192
-        return launch_block_attention_umma(dmask, W64, tile_act, act_words, q, q_sn, q_sh, q_st, k, k_sn, k_sh, k_st, v, v_sn, v_sh, v_st, scales, cumavg,
-                                           avg_sh, avg_st, use_scaler, out, N, H, T_DST, T_SRC, is_causal, s);
+    // fp16, T_SRC > 4096 (and SEA_ATTN_MMA_SYNC=1, for A/B timing): mma.sync over the expanded mask
     const int n_row_blocks = (T_DST + kBM - 1) / kBM;
     const int max_tiles = (T_SRC + kBN - 1) / kBN;
     CUtensorMap t_k, t_v;

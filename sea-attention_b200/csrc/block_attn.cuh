@@ -4,8 +4,9 @@
 
 namespace sea {
 
-// block_attn_umma.cu: tcgen05 / TMEM version (bf16, d = 64) of the masked block attention over the dense bit-packed mask.
-int launch_block_attention_umma(const unsigned long long* dmask, int W64, const uint32_t* tile_act, int act_words,
+// block_attn_umma.cu: tcgen05 / TMEM version (bf16, d = 64) of the masked block attention, driven directly by the top-k pixel
+// bits [N][T_DST][H * P / 32] (the a8 interpolation happens inside the kernel; p_lg = exact_edge_shift(P, T_SRC)).
+int launch_block_attention_umma(const uint32_t* mask_bits, int P, int p_lg,
                                 const void* q, int64_t q_sn, int64_t q_sh, int64_t q_st,
                                 const void* k, int64_t k_sn, int64_t k_sh, int64_t k_st,
                                 const void* v, int64_t v_sn, int64_t v_sh, int64_t v_st,

@@ -1,52 +1,70 @@
-// a9-a14 of the short-context path on the 5th-generation tensor cores (bf16, d = 64): same algorithm, inputs (dense bit-packed
-// mask from expand_mask_kernel) and results as block_attention_bits_kernel (block_attn.cu), but the two contractions of a tile
-// are tcgen05.mma instructions with the accumulators in TMEM, so the 128 softmax threads work thread-per-row with no
-// ldmatrix / mma.sync / shuffle traffic at all -- the mma.sync kernel is issue-bound on exactly that work.
+// a8-a14 of the short-context path on the 5th-generation tensor cores (bf16, d = 64): same algorithm and results as
+// block_attention_bits_kernel (block_attn.cu), but the two contractions of a tile are tcgen05.mma instructions with the
+// accumulators in TMEM, and the a8 interpolation happens INSIDE the kernel, straight from the top-k pixel bits: no dense mask, no
+// expansion kernel -- the only mask bytes the attention reads from HBM are the N*T*H*P/8 top-k bits.
 //
-// CTA = 128 query rows of one head, 192 threads:
-//   warp 0 (one lane)  TMA producer: Q tile once; per active source tile one stage = K [64 x 128 B], V [64 x 128 B] (both
-//                      SWIZZLE_128B boxes straight from the strided [N,H,T,d] tensors) + the tile pair's element masks
-//   warp 1 (one lane)  MMA issuer:  S[128 x 64]  = Q . K^T      (A = Q K-major, B = K K-major, 4 k-steps of 16)  -> TMEM S[j & 1]
-//                                   O[128 x 64] += P . V        (A = P K-major from shared memory, B = V as the MN-major
-//                                                                operand: rows = source tokens, 128 B = 64 channels)
+// CTA = 256 query rows of one head = two 128-row Q tiles (A, B) that share every K/V tile (halves the L2 -> SM tile traffic of a
+// 128-row CTA), 640 threads, 1 CTA / SM:
+//   warp 0 (one lane)  TMA producer: both Q tiles once; per source tile one stage = K [64 x 128 B] | V [64 x 128 B] (SWIZZLE_128B
+//                      boxes straight from the strided [N,H,T,d] tensors), 4-stage full / empty mbarrier ring
+//   warp 1             MMA issuer (warp-converged, elect.sync inside the helpers), per source tile j and Q tile g:
+//                        S_g[128 x 64]  = Q_g . K^T    (both K-major, 4 k-steps)                     -> TMEM S_g[j & 1]
+//                        O_g[128 x 64] += P_g . V      (A = P K-major from shared memory, B = V as the MN-major operand)
+//                        l_g[128 x 16] += P_g . 1      (B = a constant tile of ones): the softmax denominator comes out of the
+//                                                       tensor core, consistent with the bf16-rounded P that P.V uses
 //                      S of tile j + 1 is issued before P.V of tile j, so it overlaps the softmax of tile j
-//   warps 2-5          softmax, thread = query row: tcgen05.ld of the row's 64 scores, element mask from the stage's mask
-//                      block with immediate bit tests, lazy running maximum (the row reference only moves when a tile exceeds
-//                      it by 2^8; the rare O correction is a tcgen05.ld / st round trip), P -> bf16 -> shared memory in the
-//                      swizzled K-major layout tcgen05 reads; 16-column groups with no alive element in the warp's 32 rows
-//                      are skipped (zeros stored).
-// TMEM: 2 x 64 columns of S + 64 columns of O (256 allocated) -> 2 CTAs per SM.  Reference: attention.py:1151-1173, 1237-1244,
-// 1279-1282; mask semantics causal_resize_m_to_t.py:648-762 (via the dense mask).
+//   warps 4-19         softmax, TWO threads per query row (32 of the 64 tile columns each; Q tile g = (warp - 4) / 8):
+//                        * mask: every 8 tiles ONE of the row's two threads (they alternate) turns the alive pixels of the row that
+//                          fall into the next 512 source tokens into eight 64-bit element masks in shared memory (pixel cursor
+//                          kept in shared memory; pixels and tokens both ascend; exact a8 edge arithmetic, csr_common.cuh::
+//                          RowScale).  The loop is warp-uniform: one pixel (or one cursor step) per lane and iteration.
+//                        * no running maximum: the reference exponent of a row is fixed BEFORE the loop from the score of the
+//                          row's first alive element (one 64-wide dot product per thread) plus a 2^32 head-room, so p = 2^(s - ref)
+//                          needs no per-element max, no per-tile rescale and no per-tile exchange between the two halves of a
+//                          row; every alive p is checked for p >= 2 through an OR of the packed bf16 results (bit 14).  Only then
+//                          (a score e^22 above the reference: practically never) the tile's true maximum is taken, and at the next
+//                          8-tile boundary -- where the two halves of a row meet at a named barrier anyway -- the reference moves
+//                          and O / l are rescaled in TMEM (fp32 / bf16 hold p up to 2^127, so deferring is exact).
+//                        * 8-column groups with no alive element in the warp's 32 rows are skipped (zeros stored)
+//                        * P -> bf16 -> shared memory in the swizzled K-major layout tcgen05 reads
+// TMEM (512 columns): S_A[2], S_B[2] (4 x 64), O_A, O_B (2 x 64), l_A, l_B (2 x 16).
+// Reference: attention.py:1036-1042 (a8), 1151-1173, 1237-1244, 1279-1282; mask semantics causal_resize_m_to_t.py:648-762.
 #include "common.cuh"
+#include "csr_common.cuh"
 #include "umma.cuh"
 #include "block_attn.cuh"
+#include <type_traits>
 
 namespace sea {
 namespace {
 
-constexpr int kUM = 128;                 // query rows per CTA
+constexpr int kUM = 128;                 // query rows per Q tile
 constexpr int kUN = 64;                  // source tokens per tile
 constexpr int kUD = 64;                  // head dim
-constexpr int kUStages = 3;
+constexpr int kUStages = 4;             // per ring: K tiles and V tiles travel in separate rings (K is released after S, two tiles before V)
 constexpr int kUTile = kUN * kUD * 2;    // 8 KB (K or V tile)
-constexpr int kUMask = kUM * 16;         // 2 KB
-constexpr int kUStage = 2 * kUTile + kUMask;
-constexpr int kUQ = kUM * kUD * 2;       // 16 KB
+constexpr int kUQ = kUM * kUD * 2;       // 16 KB per Q tile
 constexpr int kUP = kUM * kUN * 2;       // 16 KB per P buffer
-constexpr int kUSoftmaxThreads = 256;          // 2 threads per query row: 32 of the 64 tile columns each
-constexpr int kUThreads = 64 + kUSoftmaxThreads;
-constexpr int kUMaxTileWords = 64;
+constexpr int kUChunk = 8;               // tiles per mask-generation chunk
+// G = Q tiles per CTA.  G = 2: 256 rows share every K/V tile (half the L2 -> SM traffic), 1 CTA / SM (512 TMEM columns, 640 threads).
+// G = 1: 128 rows, 2 CTAs / SM (256 TMEM columns, 384 threads): the set-up / epilogue of one CTA runs under the other's main loop.
+__host__ __device__ constexpr int urows(int G) { return G * kUM; }
+__host__ __device__ constexpr int uthreads(int G) { return 128 + G * 8 * 32; }   // warp 0: TMA; warps 1 .. G: MMA issuer of Q tile g; warps 4 ..: softmax (Q tile, column half, TMEM lane quarter)
+constexpr float kUMargin = 32.0f;        // head-room (log2) between a row's reference score and p = 1
 
+template <int G>
 struct USmem {
+    static constexpr int kUG = G, kURows = G * kUM;
     static constexpr int kQ = 0;
-    static constexpr int kKV = kQ + kUQ;
-    static constexpr int kP = kKV + kUStages * kUStage;          // kUStage is a multiple of 1024
-    static constexpr int kAct = kP + 2 * kUP;
-    static constexpr int kXch = kAct + kUMaxTileWords * 4;       // float [2 (tile parity)][2 halves][128 rows]: row maxima / sums exchanged between the halves
-    static constexpr int kBar = kXch + 4 * kUM * 4;
-    static constexpr int kNumBars = 1 + 2 * kUStages + 2 + 2 + 2 + 2;
-    static constexpr int kList = kBar + kNumBars * 8 + 16;
+    static constexpr int kKV = kQ + kUG * kUQ;
+    static constexpr int kMw = kKV + 2 * kUStages * kUTile;                     // u64 [2 (chunk parity)][kUChunk][256 rows]
+    static constexpr int kCur = kMw + 2 * kUChunk * kURows * 8;  // {int word, u32 remaining bits} [256 rows]: pixel cursor
+    static constexpr int kXch = kCur + kURows * 8;               // float [2 (chunk parity)][2 halves][256 rows]
+    static constexpr int kBar = kXch + 6 * kURows * 4;          // (+ [2 halves][256 rows] for the final row-sum exchange)
+    static constexpr int kNumBars = 1 + 4 * kUStages + 4 * kUG * 2;
+    static constexpr int kBits = kBar + kNumBars * 8 + 16;       // u32 [256 rows][ubits_stride(P / 32)]
 };
+__host__ __device__ constexpr int ubits_stride(int nw) { return nw | 1; }       // odd stride: row-strided reads hit distinct banks
 
 // kind::f16 instruction descriptor, D fp32, A = B = bf16, A K-major, B MN-major (bit 16), N >> 3 at [17,23), M >> 4 at [24,29)
 __host__ __device__ constexpr uint32_t idesc_bf16_b_mn(uint32_t M, uint32_t N) {
@@ -63,6 +81,28 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r
           "r"(r[30]), "r"(r[31])
         : "memory");
 }
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+          "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem desc]: the A operand (bf16 pairs, one 32-bit TMEM column per two K elements, lane = row) never
+// touches shared memory.  Warp-converged like umma::mma_bf16_ss_elect.
+__device__ __forceinline__ void mma_bf16_ts_elect(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p, e;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x2(uint32_t taddr, const uint32_t (&r)[2]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr), "r"(r[0]), "r"(r[1]) : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ float ex2u(float x) {
     float y;
@@ -74,243 +114,453 @@ __device__ __forceinline__ uint32_t pack_bf(float a, float b) {
     __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&p);
 }
+__device__ __forceinline__ float dot8_bf(uint4 a, uint4 b, float acc) {
+    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        acc = fmaf(__uint_as_float(aw[i] << 16), __uint_as_float(bw[i] << 16), acc);
+        acc = fmaf(__uint_as_float(aw[i] & 0xffff0000u), __uint_as_float(bw[i] & 0xffff0000u), acc);
+    }
+    return acc;
+}
+// explicit shared-window accesses (the dynamic shared memory base is re-aligned by hand, which hides the address space from the
+// compiler: plain C++ accesses through it become generic LD / ST)
+__device__ __forceinline__ uint32_t lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ uint2 lds64(uint32_t a) { uint2 v; asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ void sts64(uint32_t a, uint2 v) { asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(a), "r"(v.x), "r"(v.y) : "memory"); }
+__device__ __forceinline__ void sts128(uint32_t a, uint4 v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_addr(uint32_t a) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a) : "memory"); }
+constexpr float kLog2e = 1.4426950408889634f;
 
-__global__ void __launch_bounds__(kUThreads, 2)
-block_attention_umma_kernel(const uint32_t* __restrict__ tile_act, int act_words,
+
+// eight scores (one 8-column group) -> four packed bf16 pairs of p = 2^(s * log2e + nms), dead elements exactly 0
+template <int kBase>
+__device__ __forceinline__ void exp_group(const uint32_t (&s)[32], uint32_t mword, float nms, uint4& out, float& l0, float& l1) {
+    float p[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float x = fmaf(__uint_as_float(s[kBase + i]), kLog2e, nms);
+        p[i] = ex2u((mword & (1u << (kBase + i))) ? x : -INFINITY);
+    }
+    l0 += (p[0] + p[1]) + (p[2] + p[3]);
+    l1 += (p[4] + p[5]) + (p[6] + p[7]);
+    out = make_uint4(pack_bf(p[0], p[1]), pack_bf(p[2], p[3]), pack_bf(p[4], p[5]), pack_bf(p[6], p[7]));
+}
+
+template <int kUG>
+__global__ void __launch_bounds__(uthreads(kUG), 3 - kUG)
+block_attention_umma_kernel(const uint32_t* __restrict__ mask_bits, int P, int p_lg,
                             const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
-                            const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_m,
+                            const __grid_constant__ CUtensorMap tmap_v,
+                            const __nv_bfloat16* __restrict__ qg, int64_t q_sn, int64_t q_sh, int64_t q_st,
+                            const __nv_bfloat16* __restrict__ kg, int64_t k_sn, int64_t k_sh, int64_t k_st,
                             const float* __restrict__ scales, const __nv_bfloat16* __restrict__ cumavg, int64_t avg_sh, int64_t avg_st, int use_scaler,
-                            __nv_bfloat16* __restrict__ out, int N, int H, int T_DST, int T_SRC, int is_causal, int n_row_blocks, int max_tiles) {
+                            __nv_bfloat16* __restrict__ out, int N, int H, int T_DST, int T_SRC, int is_causal, int n_pairs) {
+    constexpr int kURows = urows(kUG), kUThreads = uthreads(kUG), kUSoftmaxWarps = 8 * kUG;
+    using USmem = USmem<kUG>;
     extern __shared__ uint8_t usm_raw[];
     uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(usm_raw) + 1023) & ~(uintptr_t) 1023);
-    uint32_t* sact = reinterpret_cast<uint32_t*>(sm + USmem::kAct);
+    const uint32_t sm_a = umma::smem_u32(sm);
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + USmem::kBar);
     uint64_t* q_full = bars;                         // [1]
-    uint64_t* kv_full = bars + 1;                    // [stages]
-    uint64_t* kv_empty = kv_full + kUStages;         // [stages]
-    uint64_t* s_full = kv_empty + kUStages;          // [2]
-    uint64_t* s_empty = s_full + 2;                  // [2]
-    uint64_t* p_full = s_empty + 2;                  // [2]
-    uint64_t* p_empty = p_full + 2;                  // [2]   (= P.V of the tile that used the buffer has completed)
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(p_empty + 2);
-    uint16_t* slist = reinterpret_cast<uint16_t*>(sm + USmem::kList);
-    __shared__ int s_nact;
+    uint64_t* k_full = bars + 1;                     // [stages]
+    uint64_t* k_empty = k_full + kUStages;           // [stages]  (= S of the tile has completed, for every Q tile)
+    uint64_t* v_full = k_empty + kUStages;           // [stages]
+    uint64_t* v_empty = v_full + kUStages;           // [stages]  (= P.V of the tile has completed, for every Q tile)
+    uint64_t* s_full = v_empty + kUStages;           // [g][b]
+    uint64_t* p_full = s_full + kUG * 2;             // [g][b]
+    uint64_t* p_empty = p_full + kUG * 2;            // [g][b]   (= P.V of the tile that used the buffer has completed)
+    uint64_t* s_empty = p_empty + kUG * 2;           // [g][b]   (= the softmax warps have read S out of TMEM)
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(s_empty + kUG * 2);
 
-    // warp index (and below the tile count) through a shuffle: provably warp-uniform, which keeps the MMA issue loop in the uniform datapath
+    // warp index through a shuffle: provably warp-uniform, which keeps the MMA issue loop in the uniform datapath
     const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     pdl_launch_dependents();
-    pdl_wait();                // the set-up below already reads the tile activity written by the expansion kernel
-    const int rb = n_row_blocks - 1 - (int) (blockIdx.x / (unsigned) (N * H));       // heavy (late) row blocks first
+    pdl_wait();                // the set-up below already reads the top-k bits written by the predecessor
+    const int rbp = n_pairs - 1 - (int) (blockIdx.x / (unsigned) (N * H));       // heavy (late) row blocks first
     const int nh = (int) (blockIdx.x % (unsigned) (N * H));
     const int n = nh / H, h = nh % H;
-    const int r0 = rb * kUM;
+    const int r0 = rbp * kURows;
+    const int src_off = is_causal ? (T_SRC - T_DST) : 0;
+    // source tiles each Q tile needs (causal: up to its last row's diagonal)
+    int ntg[kUG];
+#pragma unroll
+    for (int g = 0; g < kUG; ++g) {
+        const int rf = r0 + g * kUM;
+        const int lim = rf >= T_DST ? 0 : (is_causal ? min(src_off + min(rf + kUM, T_DST), T_SRC) : T_SRC);
+        ntg[g] = (lim + kUN - 1) / kUN;
+    }
+    const int nt = max(ntg[0], ntg[kUG - 1]);
 
     // ---- set-up -------------------------------------------------------------------------------------------------------
-    if (tid < kUMaxTileWords)
-        sact[tid] = tid < act_words ? __ldg(tile_act + (((int64_t) n * H + h) * n_row_blocks + rb) * act_words + tid) : 0u;
+    const int nw = P >> 5, bst = ubits_stride(nw);
+    // top-k pixel bits of this head's 256 query rows -> shared memory (rows past T_DST: no alive pixel); pixel cursors
+    for (int i = tid; i < kURows * nw; i += kUThreads) {
+        const int r = i / nw, w = i - r * nw, tr = r0 + r;
+        const uint32_t v = tr < T_DST ? __ldg(mask_bits + (((int64_t) n * T_DST + tr) * H + h) * nw + w) : 0u;
+        sts32(sm_a + USmem::kBits + (uint32_t) (r * bst + w) * 4, v);
+        if (w == 0) sts64(sm_a + USmem::kCur + (uint32_t) r * 8, make_uint2(0u, v));
+    }
     if (tid == 0) {
-        umma::prefetch_tensormap(&tmap_q); umma::prefetch_tensormap(&tmap_k); umma::prefetch_tensormap(&tmap_v); umma::prefetch_tensormap(&tmap_m);
+        umma::prefetch_tensormap(&tmap_q); umma::prefetch_tensormap(&tmap_k); umma::prefetch_tensormap(&tmap_v);
         umma::mbar_init(q_full, 1);
-        for (int s = 0; s < kUStages; ++s) { umma::mbar_init(&kv_full[s], 1); umma::mbar_init(&kv_empty[s], 1); }
-        for (int b = 0; b < 2; ++b) {
-            umma::mbar_init(&s_full[b], 1); umma::mbar_init(&s_empty[b], kUSoftmaxThreads);
-            umma::mbar_init(&p_full[b], kUSoftmaxThreads); umma::mbar_init(&p_empty[b], 1);
+        for (int s = 0; s < kUStages; ++s) {
+            umma::mbar_init(&k_full[s], 1); umma::mbar_init(&k_empty[s], kUG); umma::mbar_init(&v_full[s], 1); umma::mbar_init(&v_empty[s], kUG);
+        }
+        for (int b = 0; b < kUG * 2; ++b) {
+            umma::mbar_init(&s_full[b], 1); umma::mbar_init(&p_full[b], kUSoftmaxWarps / kUG); umma::mbar_init(&p_empty[b], 1);
+            umma::mbar_init(&s_empty[b], kUSoftmaxWarps / kUG);
         }
         umma::fence_barrier_init();
     }
-    if (warp == 1) umma::tmem_alloc(tmem_ptr, 256);
+    if (warp == 1) umma::tmem_alloc(tmem_ptr, 256 * kUG);
     umma::tc_fence_before();
     __syncthreads();
     umma::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
-    if (warp == 0) {
-        const int nwords = (max_tiles + 31) >> 5;
-        int base = 0;
-        for (int w0 = 0; w0 < nwords; w0 += 32) {
-            const uint32_t word = (w0 + lane) < nwords ? sact[w0 + lane] : 0u;
-            const int pc = __popc(word);
-            const int incl = warp_scan_incl_i(pc, lane);
-            int pos = base + incl - pc;
-            for (uint32_t x = word; x; x &= x - 1) slist[pos++] = (uint16_t) (((w0 + lane) << 5) + __ffs(x) - 1);
-            base += __shfl_sync(kFull, incl, 31);
-        }
-        if (lane == 0) s_nact = base;
-    }
-    __syncthreads();
-    const int nact = __shfl_sync(0xffffffffu, s_nact, 0);
-    const uint32_t tS0 = tmem_base, tS1 = tmem_base + 64, tO = tmem_base + 128;
+    // TMEM columns: S_g[b] at 128 g + 64 b, O_g at 128 G + 64 g, P_g[b] (bf16 pairs) at 192 G + 64 g + 32 b
 
     if (warp == 0) {
         // ---------------------------------------------------------------- TMA producer
-        if (lane == 0 && nact > 0) {        // (no active tile: nothing may be left in flight when the CTA exits)
-            umma::mbar_arrive_expect_tx(q_full, kUQ);
-            umma::tma_load_4d(sm + USmem::kQ, &tmap_q, q_full, 0, r0, h, n);
-            for (int j = 0; j < nact; ++j) {
-                const int s = j % kUStages;
-                if (j >= kUStages) umma::mbar_wait(&kv_empty[s], (uint32_t) ((j / kUStages - 1) & 1));
-                uint8_t* dst = sm + USmem::kKV + s * kUStage;
-                const int tile = (int) slist[j];
-                umma::mbar_arrive_expect_tx(&kv_full[s], kUStage);
-                umma::tma_load_4d(dst, &tmap_k, &kv_full[s], 0, tile * kUN, h, n);
-                umma::tma_load_4d(dst + kUTile, &tmap_v, &kv_full[s], 0, tile * kUN, h, n);
-                umma::tma_load_3d(dst + 2 * kUTile, &tmap_m, &kv_full[s], (tile & ~1) * 2, r0, n * H + h);
+        if (lane == 0 && nt > 0) {
+            umma::mbar_arrive_expect_tx(q_full, (uint32_t) ((ntg[0] > 0) + (kUG > 1 && ntg[kUG - 1] > 0)) * kUQ);
+            if (ntg[0] > 0) umma::tma_load_4d(sm + USmem::kQ, &tmap_q, q_full, 0, r0, h, n);
+            if (kUG > 1 && ntg[kUG - 1] > 0) umma::tma_load_4d(sm + USmem::kQ + kUQ, &tmap_q, q_full, 0, r0 + kUM, h, n);
+            // K runs kLag tiles ahead of V: S of tile j + 2 is issued while P.V is still at tile j, so K stages turn over earlier
+            constexpr int kLag = 2;
+            for (int jj = 0; jj < nt + kLag; ++jj) {
+                if (jj < nt) {
+                    const int s = jj % kUStages;
+                    if (jj >= kUStages) umma::mbar_wait_sleep(&k_empty[s], (uint32_t) ((jj / kUStages - 1) & 1), 256);
+                    umma::mbar_arrive_expect_tx(&k_full[s], kUTile);
+                    umma::tma_load_4d(sm + USmem::kKV + s * kUTile, &tmap_k, &k_full[s], 0, jj * kUN, h, n);
+                }
+                const int j = jj - kLag;
+                if (j >= 0) {
+                    const int s = j % kUStages;
+                    if (j >= kUStages) umma::mbar_wait_sleep(&v_empty[s], (uint32_t) ((j / kUStages - 1) & 1), 256);
+                    umma::mbar_arrive_expect_tx(&v_full[s], kUTile);
+                    umma::tma_load_4d(sm + USmem::kKV + (kUStages + s) * kUTile, &tmap_v, &v_full[s], 0, j * kUN, h, n);
+                }
             }
         }
-    } else if (warp == 1) {
-        // ---------------------------------------------------------------- MMA issuer
-        if (nact > 0) {          // all 32 lanes walk the loop; elect.sync inside the *_elect helpers picks the issuing lane
-            const uint32_t idesc_s = umma::make_idesc_bf16(kUM, kUN);          // A, B K-major
-            const uint32_t idesc_o = idesc_bf16_b_mn(kUM, kUD);                // B = V, MN-major
-            const uint32_t q_addr = umma::smem_u32(sm + USmem::kQ);
-            const uint32_t kv_addr = umma::smem_u32(sm + USmem::kKV);
-            const uint32_t p_addr = umma::smem_u32(sm + USmem::kP);
-            auto issue_s = [&](int j) {
-                const int s = j % kUStages, b = j & 1;
-                umma::mbar_wait(&kv_full[s], (uint32_t) ((j / kUStages) & 1));
-                if (j >= 2) umma::mbar_wait(&s_empty[b], (uint32_t) (((j >> 1) - 1) & 1));
-                umma::tc_fence_after();
-                const uint32_t ka = kv_addr + (uint32_t) s * kUStage;
+    } else if (warp >= 1 && warp <= kUG) {
+        // ---------------------------------------------------------------- MMA issuer of Q tile g.  One warp per Q tile: a serial
+        // uniform-datapath issue stream costs tens of cycles per MMA (descriptor arithmetic), and with both Q tiles on one warp that
+        // stream -- not the tensor core, not the softmax -- set the pace of the whole CTA (measured).
+        const int g0 = warp - 1, g1 = g0 + 1;
+        const int nt_a = ntg[0], nt_b = ntg[kUG - 1];
+        const uint32_t idesc_s = umma::make_idesc_bf16(kUM, kUN);          // A, B K-major
+        const uint32_t idesc_o = idesc_bf16_b_mn(kUM, kUD);                // B = V, MN-major
+        // descriptors of the k = 0 step; a k-step adds a constant to the 14-bit (address >> 4) field (no carry: smem < 256 KB)
+        const uint64_t d_q0 = umma::make_desc_k_sw128(sm_a + USmem::kQ);
+        const uint64_t d_kv = umma::make_desc_k_sw128(sm_a + USmem::kKV);
+        auto issue_s = [&](int j) {
+            const int s = j % kUStages, b = j & 1;
+            umma::mbar_wait(&k_full[s], (uint32_t) ((j / kUStages) & 1));
+            umma::tc_fence_after();
+            const uint64_t d_k = d_kv + (uint64_t) (s * (kUTile >> 4));
+            for (int g = g0; g < g1; ++g) {
+                if (j < (g ? nt_b : nt_a)) {
+                    const uint64_t d_q = d_q0 + (uint64_t) (g * (kUQ >> 4));
 #pragma unroll
-                for (int k = 0; k < kUD / 16; ++k)
-                    umma::mma_bf16_ss_elect(b ? tS1 : tS0, umma::make_desc_k_sw128(q_addr + k * 32), umma::make_desc_k_sw128(ka + k * 32), idesc_s, (uint32_t) (k != 0));
-                umma::mma_commit_elect(&s_full[b]);
-            };
+                    for (int k = 0; k < kUD / 16; ++k)
+                        umma::mma_bf16_ss_elect(tmem_base + 128 * g + 64 * b, d_q + 2 * k, d_k + 2 * k, idesc_s, (uint32_t) (k != 0));
+                    umma::mma_commit_elect(&s_full[g * 2 + b]);
+                }
+            }
+            // the K stage is free once S of every Q tile on it has completed; a warp whose Q tile does not use tile j still arrives, but
+            // only after it has seen the tile land (the wait above), so it can never run a whole ring ahead of the other warp and
+            // complete a later phase of the barrier on its own
+            umma::mma_commit_elect(&k_empty[s]);
+        };
+        if (nt > 0) {          // all 32 lanes walk the loop; elect.sync inside the *_elect helpers picks the issuing lane
             umma::mbar_wait(q_full, 0);
             issue_s(0);
-            for (int j = 0; j < nact; ++j) {
-                const int s = j % kUStages, b = j & 1;
-                if (j + 1 < nact) issue_s(j + 1);
-                umma::mbar_wait(&p_full[b], (uint32_t) ((j >> 1) & 1));
-                umma::tc_fence_after();
-                const uint32_t va = kv_addr + (uint32_t) s * kUStage + kUTile;
-                const uint32_t pa = p_addr + (uint32_t) b * kUP;
-#pragma unroll
-                for (int k = 0; k < kUN / 16; ++k)       // 16 source tokens per step: A advances 32 B inside the row, B two 8-token groups
-                    umma::mma_bf16_ss_elect(tO, umma::make_desc_k_sw128(pa + k * 32), umma::make_desc_k_sw128(va + k * 2048), idesc_o, (uint32_t) ((j | k) != 0));
-                umma::mma_commit_elect(&kv_empty[s]);
-                umma::mma_commit_elect(&p_empty[b]);
-            }
+            if (nt > 1) issue_s(1);
         }
-    } else {
-        // ---------------------------------------------------------------- softmax warps: 2 threads per query row
-        // warps 2-5 take tile columns 0-31 of their TMEM lane quarter's rows, warps 6-9 columns 32-63 (and the matching halves
-        // of P and O); the two halves of a row agree on the row maximum through shared memory + a 64-thread named barrier
-        const int qd = warp & 3;                                  // TMEM lane quarter this warp may access
-        const int half = (warp - 2) >> 2;
-        const int row = qd * 32 + lane;
-        const int t = r0 + row;
-        const uint32_t lane_addr = (uint32_t) (qd * 32) << 16;
-        float* xch = reinterpret_cast<float*>(sm + USmem::kXch);
-        constexpr float kLog2e = 1.4426950408889634f;
-        constexpr float kLazy = 8.0f / kLog2e;
-        float m_run = -INFINITY, l_run = 0.f, nms = 0.f;
-        for (int j = 0; j < nact; ++j) {
+        for (int j = 0; j < nt; ++j) {
             const int s = j % kUStages, b = j & 1;
-            const int tile = (int) slist[j];
-            umma::mbar_wait(&kv_full[s], (uint32_t) ((j / kUStages) & 1));         // acquire the TMA-written mask block
-            const uint32_t mw = *reinterpret_cast<const uint32_t*>(sm + USmem::kKV + s * kUStage + 2 * kUTile + row * 16 + (tile & 1) * 8 + half * 4);
-            const uint32_t act = __reduce_or_sync(kFull, ((mw & 0xffffu) ? 1u : 0u) | ((mw >> 16) ? 2u : 0u));
-            umma::mbar_wait(&s_full[b], (uint32_t) ((j >> 1) & 1));
-            umma::tc_fence_after();
-            float sc[32];
-            {
-                uint32_t r32[32];
-                umma::tmem_ld_32x32((b ? tS1 : tS0) + lane_addr + 32u * half, r32);
-                umma::tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 32; ++i) sc[i] = __uint_as_float(r32[i]);
+            // scores run two tiles ahead: S of tile j + 2 goes into the buffer of tile j as soon as the softmax warps have pulled tile j
+            // out of TMEM (s_empty, early in their work on tile j), not after their P of tile j is complete
+            if (j + 2 < nt) {
+                for (int g = g0; g < g1; ++g)
+                    if (j + 2 < (g ? nt_b : nt_a)) umma::mbar_wait(&s_empty[g * 2 + b], (uint32_t) ((j >> 1) & 1));
+                issue_s(j + 2);
             }
-            umma::tc_fence_before();
-            umma::mbar_arrive(&s_empty[b]);                        // S[b] may be overwritten by the scores of tile j + 2
-            float mx = -INFINITY;
+            umma::mbar_wait(&v_full[s], (uint32_t) ((j / kUStages) & 1));
+            for (int g = g0; g < g1; ++g) {
+                if (j < (g ? nt_b : nt_a)) {
+                    umma::mbar_wait(&p_full[g * 2 + b], (uint32_t) ((j >> 1) & 1));
+                    umma::tc_fence_after();
+                    const uint64_t d_v = d_kv + (uint64_t) (((kUStages + s) * kUTile) >> 4);
+                    const uint32_t tP = tmem_base + 192 * kUG + 64 * g + 32 * b;
 #pragma unroll
-            for (int cg = 0; cg < 2; ++cg) {
-                if (act & (1u << cg)) {
+                    for (int k = 0; k < kUN / 16; ++k)       // 16 source tokens per step: A = 8 TMEM columns of bf16 pairs, B two 8-token groups of V (2048 B)
+                        mma_bf16_ts_elect(tmem_base + 128 * kUG + 64 * g, tP + 8 * k, d_v + 128 * k, idesc_o, (uint32_t) ((j | k) != 0));
+                    umma::mma_commit_elect(&p_empty[g * 2 + b]);
+                }
+            }
+            umma::mma_commit_elect(&v_empty[s]);          // (same rule as k_empty: v_full was waited on above)
+        }
+    } else if (warp >= 4) {
+        // ---------------------------------------------------------------- softmax warps: two threads per query row
+        const int g = (warp - 4) >> 3;
+        const int half = ((warp - 4) >> 2) & 1;
+        const int qd = warp & 3;                                  // TMEM lane quarter this warp may access
+        const int row = qd * 32 + lane, grow = g * kUM + row;
+        const int t = r0 + grow;
+        const int my_nt = g ? ntg[kUG - 1] : ntg[0];
+        const int bar_id = 1 + g * 4 + qd;                        // named barrier of the row's two threads' warps (64 threads)
+        const uint32_t lane_addr = (uint32_t) (qd * 32) << 16;
+        const uint32_t tS = tmem_base + 128 * g + 32 * half + lane_addr, tO = tmem_base + 128 * kUG + 64 * g + 32 * half + lane_addr;
+        const uint32_t tP = tmem_base + 192 * kUG + 64 * g + 16 * half + lane_addr;
+        const uint32_t a_s_full = umma::smem_u32(s_full + g * 2), a_p_full = umma::smem_u32(p_full + g * 2), a_p_empty = umma::smem_u32(p_empty + g * 2), a_s_empty = umma::smem_u32(s_empty + g * 2);
+        // a8 edge arithmetic of this thread's query row
+        RowScale rs;
+        rs.L = t < T_DST ? (is_causal ? min(src_off + t + 1, T_SRC) : T_SRC) : 1; rs.lg = p_lg; rs.halfP = P >> 1;
+        rs.s = __fdiv_rn((float) rs.L, (float) P);
+        const uint32_t a_brow = sm_a + USmem::kBits + (uint32_t) (grow * bst) * 4;
+        const uint32_t a_mw = sm_a + USmem::kMw + (uint32_t) grow * 8;            // + ((parity * kUChunk + i) * 256) * 8
+        const uint32_t a_cur = sm_a + USmem::kCur + (uint32_t) grow * 8;
+        const uint32_t a_xch = sm_a + USmem::kXch + (uint32_t) grow * 4;          // + ((parity * 2 + half) * 256) * 4
+
+        // pixel cursor of this row -> element masks of chunk c (tiles 8c .. 8c+7); warp-uniform loop, one cursor step or one pixel
+        // per lane and iteration.  Cost ~ alive pixels of the row (16384 / L at the north-star shape): right for all but the
+        // shortest rows.
+        auto gen_chunk = [&](int c) {
+            const uint32_t a_w = a_mw + (uint32_t) ((c & 1) * kUChunk * kURows) * 8;
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const int c = cg * 16 + i;
-                        sc[c] = (mw & (1u << c)) ? sc[c] : -INFINITY;
-                        mx = fmaxf(mx, sc[c]);
+            for (int i = 0; i < kUChunk; ++i) sts64(a_w + i * kURows * 8, make_uint2(0u, 0u));
+            const int c_lo = c * (kUChunk * kUN), c_hi = c_lo + kUChunk * kUN;
+            const uint2 cur = lds64(a_cur);
+            int cur_w = (int) cur.x;
+            uint32_t cur_x = cur.y;
+            // runs ascend, so the 64-bit word under construction lives in registers and is stored (never re-read) when a run moves on
+            int acc_w = 0;
+            uint32_t acc_lo = 0u, acc_hi = 0u;
+            bool done = cur_w >= nw || rs.L <= c_lo;
+            while (!__all_sync(kFull, done)) {
+                if (!done) {
+                    if (cur_x == 0u) {
+                        if (++cur_w >= nw) done = true; else cur_x = lds32(a_brow + cur_w * 4);
+                    } else {
+                        const int m = (cur_w << 5) + __ffs(cur_x) - 1;
+                        const int a = rs.edge(m);
+                        if (a >= c_hi) {
+                            done = true;
+                        } else {
+                            const int b = rs.edge(m + 1);
+                            const int lo = max(a, c_lo) - c_lo, hi = min(b, c_hi) - c_lo;
+                            for (int w = lo >> 6; w <= ((hi - 1) >> 6) && hi > lo; ++w) {
+                                if (w != acc_w) {
+                                    if (acc_lo | acc_hi) sts64(a_w + acc_w * kURows * 8, make_uint2(acc_lo, acc_hi));
+                                    acc_w = w; acc_lo = acc_hi = 0u;
+                                }
+                                const int l = max(lo - (w << 6), 0), hh = min(hi - (w << 6), 64);          // bits [l, hh) of word w
+                                const uint32_t lo_l = min(l, 32), lo_h = min(hh, 32), hi_l = max(l, 32) - 32, hi_h = max(hh, 32) - 32;
+                                acc_lo |= lo_h > lo_l ? ((0xffffffffu >> (32 - (lo_h - lo_l))) << lo_l) : 0u;
+                                acc_hi |= hi_h > hi_l ? ((0xffffffffu >> (32 - (hi_h - hi_l))) << hi_l) : 0u;
+                            }
+                            if (b > c_hi) done = true;      // the run continues in the next chunk: the pixel stays under the cursor
+                            else cur_x &= cur_x - 1;
+                        }
                     }
                 }
             }
-            // row maximum of the tile across both halves
-            xch[(b * 2 + half) * kUM + row] = mx;                  // slots alternate with the tile parity: no write-after-read race
-            asm volatile("bar.sync %0, 64;" ::"r"(1 + qd) : "memory");
-            mx = fmaxf(mx, xch[(b * 2 + (half ^ 1)) * kUM + row]);
-            // lazy reference maximum; the (rare) O correction needs P.V of tile j - 1 to have completed
-            const bool grow = mx > m_run + kLazy;
-            if (__any_sync(kFull, grow)) {
-                const float mn = grow ? mx : m_run;
-                const float al = mn == -INFINITY ? 1.f : ex2u((m_run - mn) * kLog2e);           // m_run = -inf -> 0
-                m_run = mn;
-                nms = mn == -INFINITY ? 0.f : -mn * kLog2e;
-                l_run *= al;
-                if (j > 0) {
-                    umma::mbar_wait(&p_empty[(j - 1) & 1], (uint32_t) (((j - 1) >> 1) & 1));
+            if (acc_lo | acc_hi) sts64(a_w + acc_w * kURows * 8, make_uint2(acc_lo, acc_hi));
+            sts64(a_cur, make_uint2((uint32_t) cur_w, cur_x));
+        };
+        // The shortest rows (L <= 320 tokens: up to P alive pixels, most of them empty) go token-parallel instead: lane = source
+        // token, its pixel is the largest m with edge(m) <= c, i.e. m = floor(((c + 1) P - P/2 - 1) / L) for the exact integer edges
+        // (edge(m) = (m L + P/2) >> lg), and a ballot of the pixels' alive bits IS the element mask word.  The warp walks its 32 rows.
+        auto gen_tokens = [&]() {
+            const int wrow0 = g * kUM + qd * 32;
+            for (int rr = 0; rr < 32; ++rr) {
+                const int tr = r0 + wrow0 + rr;
+                if (tr >= T_DST) break;
+                const int Lr = is_causal ? min(src_off + tr + 1, T_SRC) : T_SRC;
+                const float inv_l = 1.0f / (float) Lr;
+                const uint32_t a_b = sm_a + USmem::kBits + (uint32_t) ((wrow0 + rr) * bst) * 4;
+                const uint32_t a_w0 = sm_a + USmem::kMw + (uint32_t) (wrow0 + rr) * 8;
+                for (int w32 = 0; w32 < ((Lr + 31) >> 5); ++w32) {
+                    const int cc = (w32 << 5) + lane;
+                    const int x1 = (cc + 1) * P - (P >> 1) - 1;
+                    int m = (int) ((float) x1 * inv_l);
+                    if ((m + 1) * Lr <= x1) ++m;
+                    if (m * Lr > x1) --m;
+                    m = min(m, P - 1);
+                    const bool alive = cc < Lr && ((lds32(a_b + (m >> 5) * 4) >> (m & 31)) & 1u);
+                    const uint32_t word = __ballot_sync(kFull, alive);
+                    if (lane == 0) sts32(a_w0 + (uint32_t) ((w32 >> 1) * kURows) * 8 + (w32 & 1) * 4, word);
+                }
+            }
+        };
+        // ---- small CTAs (<= 16 source tiles): all element masks are generated up front.  The row's two threads split its pixel
+        // words (first / second half of the pixels) and OR their runs into the row's words with shared-memory reductions.
+        const bool small_cta = nt <= 2 * kUChunk;
+        int cstar = -1;                          // first alive source token of the row
+        if (small_cta && my_nt > 0) {
+            const int warp_last = r0 + g * kUM + qd * 32 + 31;
+            const bool by_token = p_lg >= 0 && (is_causal ? src_off + warp_last + 1 : T_SRC) <= 96;         // warp-uniform
+#pragma unroll
+            for (int i = 0; i < kUChunk; ++i) sts64(a_mw + (uint32_t) ((half * kUChunk + i) * kURows) * 8, make_uint2(0u, 0u));
+            asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+            if (by_token) {
+                if (half == 0) gen_tokens();
+            } else {
+                const int w_end = half ? nw : (nw >> 1);
+                int cur_w = half ? (nw >> 1) : 0;
+                uint32_t cur_x = cur_w < w_end ? lds32(a_brow + cur_w * 4) : 0u;
+                bool done = cur_w >= w_end;
+                while (!done) {
+                    if (cur_x == 0u) {
+                        if (++cur_w >= w_end) done = true; else cur_x = lds32(a_brow + cur_w * 4);
+                    } else {
+                        const int m = (cur_w << 5) + __ffs(cur_x) - 1;
+                        cur_x &= cur_x - 1;
+                        const int pa = rs.edge(m), pb = rs.edge(m + 1);
+                        for (int c32 = pa >> 5; c32 <= ((pb - 1) >> 5) && pb > pa; ++c32) {
+                            const int l = max(pa - (c32 << 5), 0), hh = min(pb - (c32 << 5), 32);
+                            const uint32_t bits = (0xffffffffu >> (32 - (hh - l))) << l;
+                            asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(a_mw + (uint32_t) ((c32 >> 1) * kURows) * 8 + (c32 & 1) * 4), "r"(bits) : "memory");
+                        }
+                    }
+                }
+            }
+            asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+            for (int tile = 0; tile < my_nt && cstar < 0; ++tile) {
+                const uint2 w = lds64(a_mw + (uint32_t) (tile * kURows) * 8);
+                if (w.x) cstar = tile * kUN + __ffs(w.x) - 1;
+                else if (w.y) cstar = tile * kUN + 32 + __ffs(w.y) - 1;
+            }
+        } else if (my_nt > 0) {
+            for (int wq = 0; wq < nw && cstar < 0; ++wq)
+                for (uint32_t x = lds32(a_brow + wq * 4); x; x &= x - 1) {
+                    const int m = (wq << 5) + __ffs(x) - 1;
+                    const int a = rs.edge(m);
+                    if (rs.L >= P || rs.edge(m + 1) > a) { cstar = a; break; }      // L >= P: no pixel is empty
+                }
+        }
+        // reference exponent: score of the row's first alive element (+ head-room), so that every alive p stays far below 2
+        float nms = 0.f;
+        if (cstar >= 0) {
+            const uint4* qp = reinterpret_cast<const uint4*>(qg + (int64_t) n * q_sn + (int64_t) h * q_sh + (int64_t) t * q_st);
+            const uint4* kp = reinterpret_cast<const uint4*>(kg + (int64_t) n * k_sn + (int64_t) h * k_sh + (int64_t) cstar * k_st);
+            float acc = 0.f;
+#pragma unroll
+            for (int i = 0; i < kUD / 8; ++i) acc = dot8_bf(__ldg(qp + i), __ldg(kp + i), acc);
+            nms = -(acc * kLog2e + kUMargin);
+        }
+        // epilogue inputs, requested early
+        float sc0 = 0.f, sc1 = 0.f;
+        if (t < T_DST) {
+            const float* sp = scales + ((((int64_t) n * H + h) * T_DST + t) << 1);
+            sc0 = __ldg(sp); sc1 = __ldg(sp + 1);
+        }
+        if (half == 0 && my_nt > 0 && !small_cta) gen_chunk(0);
+        float l_a = 0.f, l_b = 0.f;              // fp32 row sum of this thread's 32 columns (two chains)
+        float trig_mx = -INFINITY;              // largest alive score (log2 domain) of the tiles that overflowed the head-room since the last boundary
+
+        for (int j = 0; j < my_nt; ++j) {
+            const int b = j & 1;
+            const int c = j / kUChunk, jc = j % kUChunk;
+            if (jc == 0) {
+                // ---- 8-tile boundary: the row's two threads meet; masks of chunk c become visible, chunk c + 1 is generated by one
+                // of them, and a pending reference move (rare) is applied by both
+                sts32(a_xch + (uint32_t) (((c & 1) * 2 + half) * kURows) * 4, __float_as_uint(trig_mx));
+                asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+                const float mxb = fmaxf(trig_mx, __uint_as_float(lds32(a_xch + (uint32_t) (((c & 1) * 2 + (half ^ 1)) * kURows) * 4)));
+                trig_mx = -INFINITY;
+                if (__any_sync(kFull, mxb > -INFINITY)) {
+                    const bool mv = mxb > -INFINITY;
+                    const float nms_new = mv ? -(mxb + kUMargin) : nms;
+                    const float al = mv ? ex2u(nms_new - nms) : 1.0f;
+                    nms = nms_new;
+                    // j >= kUChunk here; P.V of tile j - 1 must have completed before O / l are touched
+                    umma::mbar_wait_addr(a_p_empty + 8u * ((j - 1) & 1), (uint32_t) (((j - 1) >> 1) & 1));
                     umma::tc_fence_after();
                     uint32_t o32[32];
-                    umma::tmem_ld_32x32(tO + lane_addr + 32u * half, o32);
+                    umma::tmem_ld_32x32(tO, o32);
                     umma::tmem_ld_wait();
 #pragma unroll
                     for (int i = 0; i < 32; ++i) o32[i] = __float_as_uint(__uint_as_float(o32[i]) * al);
-                    tmem_st_32x32(tO + lane_addr + 32u * half, o32);
+                    tmem_st_32x32(tO, o32);
+                    l_a *= al; l_b *= al;
                     tmem_st_wait();
                 }
+                if (half == ((c + 1) & 1) && (c + 1) * kUChunk < my_nt && !small_cta) gen_chunk(c + 1);
             }
-            // P[b] is free once P.V of tile j - 2 has completed
-            if (j >= 2) umma::mbar_wait(&p_empty[b], (uint32_t) (((j >> 1) - 1) & 1));
-            uint8_t* prow = sm + USmem::kP + b * kUP + row * 128;
-            float ps = 0.f;
+            const uint32_t mw = lds32(a_mw + (uint32_t) (((c & 1) * kUChunk + jc) * kURows) * 8 + half * 4);
+            const uint32_t um = __reduce_or_sync(kFull, mw);       // column union of the warp's 32 rows
+            umma::mbar_wait_addr(a_s_full + 8u * b, (uint32_t) ((j >> 1) & 1));
+            umma::tc_fence_after();
+            uint4 pk[4];
+            uint32_t orv = 0u;
+            {
+                uint32_t s0[32];
+                umma::tmem_ld_32x32(tS + 64 * b, s0);
+                umma::tmem_ld_wait();
+                umma::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_addr(a_s_empty + 8u * b);         // S[b] may be overwritten by the scores of tile j + 2
+                if (um & 0xffu) { exp_group<0>(s0, mw, nms, pk[0], l_a, l_b); orv |= pk[0].x | pk[0].y; orv |= pk[0].z | pk[0].w; } else pk[0] = make_uint4(0, 0, 0, 0);
+                if (um & 0xff00u) { exp_group<8>(s0, mw, nms, pk[1], l_a, l_b); orv |= pk[1].x | pk[1].y; orv |= pk[1].z | pk[1].w; } else pk[1] = make_uint4(0, 0, 0, 0);
+                if (um & 0xff0000u) { exp_group<16>(s0, mw, nms, pk[2], l_a, l_b); orv |= pk[2].x | pk[2].y; orv |= pk[2].z | pk[2].w; } else pk[2] = make_uint4(0, 0, 0, 0);
+                if (um & 0xff000000u) { exp_group<24>(s0, mw, nms, pk[3], l_a, l_b); orv |= pk[3].x | pk[3].y; orv |= pk[3].z | pk[3].w; } else pk[3] = make_uint4(0, 0, 0, 0);
+                const bool grow_ref = (orv & 0x40004000u) != 0u;         // some alive p >= 2 (or inf)
+                if (__any_sync(kFull, grow_ref)) {
+                    // rare: remember the tile's true maximum; the reference moves at the next boundary (p up to 2^127 is exact meanwhile)
+                    float mx = -INFINITY;
 #pragma unroll
-            for (int cg = 0; cg < 2; ++cg) {
-                uint4 c0 = make_uint4(0, 0, 0, 0), c1 = make_uint4(0, 0, 0, 0);
-                if (act & (1u << cg)) {
-                    float p[16];
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) { p[i] = ex2u(fmaf(sc[cg * 16 + i], kLog2e, nms)); ps += p[i]; }
-                    c0 = make_uint4(pack_bf(p[0], p[1]), pack_bf(p[2], p[3]), pack_bf(p[4], p[5]), pack_bf(p[6], p[7]));
-                    c1 = make_uint4(pack_bf(p[8], p[9]), pack_bf(p[10], p[11]), pack_bf(p[12], p[13]), pack_bf(p[14], p[15]));
+                    for (int i = 0; i < 32; ++i)
+                        if (mw & (1u << i)) mx = fmaxf(mx, __uint_as_float(s0[i]) * kLog2e);
+                    if (grow_ref) trig_mx = fmaxf(trig_mx, mx);
                 }
-                const int ch = half * 4 + 2 * cg;                 // 16-byte chunk (8 source tokens) inside the 128-byte row
-                *reinterpret_cast<uint4*>(prow + ((ch ^ (row & 7)) << 4)) = c0;
-                *reinterpret_cast<uint4*>(prow + (((ch + 1) ^ (row & 7)) << 4)) = c1;
             }
-            l_run += ps;
-            umma::fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
+            // P[b] (TMEM) is free once P.V of tile j - 2 has completed
+            if (j >= 2) umma::mbar_wait_addr(a_p_empty + 8u * b, (uint32_t) (((j >> 1) - 1) & 1));
+            umma::tc_fence_after();
+            {
+                const uint32_t p16[16] = {pk[0].x, pk[0].y, pk[0].z, pk[0].w, pk[1].x, pk[1].y, pk[1].z, pk[1].w,
+                                          pk[2].x, pk[2].y, pk[2].z, pk[2].w, pk[3].x, pk[3].y, pk[3].z, pk[3].w};
+                tmem_st_32x16(tP + 32 * b, p16);
+                tmem_st_wait();
+            }
             umma::tc_fence_before();
-            umma::mbar_arrive(&p_full[b]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive_addr(a_p_full + 8u * b);
         }
         // ---- epilogue: O / l, * sigmoid(s0), mix with the running mean, permuted store (32 channels per thread) -------------
-        asm volatile("bar.sync %0, 64;" ::"r"(1 + qd) : "memory");         // the partner is done with the last exchange slot
-        xch[half * kUM + row] = l_run;
-        asm volatile("bar.sync %0, 64;" ::"r"(1 + qd) : "memory");
-        l_run += xch[(half ^ 1) * kUM + row];
-        float o[32];
-        if (nact > 0) {
-            umma::mbar_wait(&p_empty[(nact - 1) & 1], (uint32_t) (((nact - 1) >> 1) & 1));
+        // row sum: the two halves of a row exchange their partial sums
+        sts32(a_xch + (uint32_t) ((4 + half) * kURows) * 4, __float_as_uint(l_a + l_b));
+        asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+        const float l_run = (l_a + l_b) + __uint_as_float(lds32(a_xch + (uint32_t) ((4 + (half ^ 1)) * kURows) * 4));
+        uint32_t o0[32];
+        if (my_nt > 0) {
+            umma::mbar_wait_addr(a_p_empty + 8u * ((my_nt - 1) & 1), (uint32_t) (((my_nt - 1) >> 1) & 1));
             umma::tc_fence_after();
-            uint32_t r32[32];
-            umma::tmem_ld_32x32(tO + lane_addr + 32u * half, r32);
+            umma::tmem_ld_32x32(tO, o0);
             umma::tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __uint_as_float(r32[i]);
         } else {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = 0.f;
+            for (int i = 0; i < 32; ++i) o0[i] = 0u;
         }
         if (t < T_DST) {
             const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
-            const float* sp = scales + ((((int64_t) n * H + h) * T_DST + t) << 1);
-            const float psc = use_scaler ? sigu(sp[0]) : 1.0f;
-            const float a = sigu(sp[1]);
+            const float psc = use_scaler ? sigu(sc0) : 1.0f;
+            const float a = sigu(sc1);
+            const float w = inv * psc;
             __nv_bfloat16* orow = out + ((int64_t) n * T_DST + t) * ((int64_t) H * kUD) + (int64_t) h * kUD + 32 * half;
             const uint4* arow = cumavg ? reinterpret_cast<const uint4*>(cumavg + ((int64_t) n * H + h) * avg_sh + (int64_t) t * avg_st + 32 * half) : nullptr;
 #pragma unroll
             for (int c8 = 0; c8 < 4; ++c8) {
                 float x[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) x[i] = l_run > 0.f ? o[c8 * 8 + i] * inv * psc : 0.f;
+                for (int i = 0; i < 8; ++i) x[i] = l_run > 0.f ? __uint_as_float(o0[c8 * 8 + i]) * w : 0.f;
                 if (arow) {
                     const uint4 av = __ldg(arow + c8);
                     const uint32_t aw[4] = {av.x, av.y, av.z, av.w};
@@ -328,22 +578,20 @@ block_attention_umma_kernel(const uint32_t* __restrict__ tile_act, int act_words
     __syncthreads();
     if (warp == 1) {
         umma::tc_fence_after();
-        umma::tmem_dealloc(tmem_base, 256);
+        umma::tmem_dealloc(tmem_base, 256 * kUG);
     }
 }
 
 }  // namespace
 
-int launch_block_attention_umma(const unsigned long long* dmask, int W64, const uint32_t* tile_act, int act_words,
+int launch_block_attention_umma(const uint32_t* mask_bits, int P, int p_lg,
                                 const void* q, int64_t q_sn, int64_t q_sh, int64_t q_st,
                                 const void* k, int64_t k_sn, int64_t k_sh, int64_t k_st,
                                 const void* v, int64_t v_sn, int64_t v_sh, int64_t v_st,
                                 const float* scales, const void* cumavg, int64_t avg_sh, int64_t avg_st, int use_scaler, void* out,
                                 int N, int H, int T_DST, int T_SRC, int is_causal, cudaStream_t s) {
-    const int n_row_blocks = (T_DST + kUM - 1) / kUM;
-    const int max_tiles = (T_SRC + kUN - 1) / kUN;
-    SEA_CHECK_ARG(max_tiles <= kUMaxTileWords * 32, "block attention: T_SRC too large");
-    CUtensorMap t_q, t_k, t_v, t_m;
+    SEA_CHECK_ARG(mask_bits != nullptr && (P % 32) == 0 && P <= 1024, "block attention: needs the top-k bit mask, P %% 32 == 0, P <= 1024");
+    CUtensorMap t_q, t_k, t_v;
     {
         const uint64_t qdims[4] = {(uint64_t) kUD, (uint64_t) T_DST, (uint64_t) H, (uint64_t) N};
         const uint64_t dims[4] = {(uint64_t) kUD, (uint64_t) T_SRC, (uint64_t) H, (uint64_t) N};
@@ -358,19 +606,23 @@ int launch_block_attention_umma(const unsigned long long* dmask, int W64, const 
         if (rc) return rc;
         rc = make_tmap_bf16_sw128(&t_v, const_cast<void*>(v), 4, dims, vs, box);
         if (rc) return rc;
-        const uint64_t mdims[3] = {(uint64_t) W64 * 2, (uint64_t) T_DST, (uint64_t) N * H};
-        const uint64_t mstr[2] = {(uint64_t) W64 * 8, (uint64_t) T_DST * W64 * 8};
-        const uint32_t mbox[3] = {4, (uint32_t) kUM, 1};
-        rc = make_tmap_u32_plain(&t_m, const_cast<unsigned long long*>(dmask), 3, mdims, mstr, mbox);
-        if (rc) return rc;
     }
-    const size_t smem = 1024 + (size_t) USmem::kList + (size_t) ((max_tiles + 7) & ~7) * 2;
-    const unsigned grid = (unsigned) ((int64_t) n_row_blocks * N * H);
-    SEA_CUDA_TRY(cudaFuncSetAttribute(block_attention_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem), "smem attr");
-    SEA_CUDA_TRY(launch_pdl(block_attention_umma_kernel, dim3(grid), dim3(kUThreads), (size_t) smem, s, tile_act, act_words, t_q, t_k, t_v, t_m, scales,
-                            (const __nv_bfloat16*) cumavg, avg_sh, avg_st, use_scaler, (__nv_bfloat16*) out, N, H, T_DST, T_SRC, is_causal, n_row_blocks, max_tiles),
-                 "block_attention_umma_kernel launch");
-    return SEA_OK;
+    static const int g_env = getenv("SEA_ATTN_QTILES") ? atoi(getenv("SEA_ATTN_QTILES")) : 0;       // A/B timing switch
+    const int G = g_env == 1 || g_env == 2 ? g_env : (T_DST > kUM ? 2 : 1);       // measured at the north-star shape: 179 vs 186 us
+    auto launch = [&](auto kernel, auto g_tag) -> int {
+        constexpr int kG = decltype(g_tag)::value;
+        const int n_blocks = (T_DST + urows(kG) - 1) / urows(kG);
+        const size_t smem = 1024 + (size_t) USmem<kG>::kBits + (size_t) urows(kG) * ubits_stride(P >> 5) * 4;
+        const unsigned grid = (unsigned) ((int64_t) n_blocks * N * H);
+        SEA_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem), "smem attr");
+        SEA_CUDA_TRY(launch_pdl(kernel, dim3(grid), dim3(uthreads(kG)), (size_t) smem, s, mask_bits, P, p_lg, t_q, t_k, t_v,
+                                (const __nv_bfloat16*) q, q_sn, q_sh, q_st, (const __nv_bfloat16*) k, k_sn, k_sh, k_st, scales,
+                                (const __nv_bfloat16*) cumavg, avg_sh, avg_st, use_scaler, (__nv_bfloat16*) out, N, H, T_DST, T_SRC, is_causal, n_blocks),
+                     "block_attention_umma_kernel launch");
+        return SEA_OK;
+    };
+    if (G == 2) return launch(block_attention_umma_kernel<2>, std::integral_constant<int, 2>{});
+    return launch(block_attention_umma_kernel<1>, std::integral_constant<int, 1>{});
 }
 
 }  // namespace sea

@@ -54,10 +54,5 @@ inline int64_t mask_act_bytes(int N, int H, int T_DST, int T_SRC) {
     const int64_t words = (int64_t) N * H * ((T_DST + kMaskRowBlock - 1) / kMaskRowBlock) * mask_act_words(T_SRC);
     return (words * 4 + 15) & ~(int64_t) 15;
 }
-struct MaskExpandArgs {            // dmask == nullptr: no expansion
-    unsigned long long* dmask;
-    uint32_t* tile_act;
-    int act_words, W64, T_SRC, p_lg, is_causal;
-};
 
 }  // namespace sea

@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(kTopkThreads, 3)
 tail_topk_reg_kernel(const float* __restrict__ y3, const float* __restrict__ bias, const float* __restrict__ ln_w,
                      const float* __restrict__ ln_b, const float* __restrict__ k_per_row, float* __restrict__ probs,
                      uint32_t* __restrict__ mask_bits, int32_t* __restrict__ crow_counts, int k_clamp,
-                     int N, int Tn, int W, int Hr, MaskExpandArgs ex) {
+                     int N, int Tn, int W, int Hr) {
     // Hmax = 8 * kHPW head slots; Hr <= Hmax real heads (kExactH: Hr == Hmax, everything below folds to constants).  The slots
     // h >= Hr hold no keys: they are skipped in every key loop and their alive bits stay 0.
     constexpr int P = 32 * kPerLane, Hmax = 8 * kHPW;
@@ -166,16 +166,10 @@ tail_topk_reg_kernel(const float* __restrict__ y3, const float* __restrict__ bia
     __shared__ int4 stap[P];
     float* ys = reinterpret_cast<float*>(smem_u);               // [H][W+2]: W conv outputs, then the bias (pad columns), then 0
     uint32_t* sbits = smem_u + H * (W + 3);                     // [G/32] (only for the fused row counts)
-    uint32_t* img = sbits + (G >> 5);                           // [H][2 * wneed] dense element mask of this row (fused a8 expansion)
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int n = blockIdx.x / Tn, t = blockIdx.x % Tn;
     pdl_launch_dependents();
     pdl_wait();
-    // fused a8 expansion (short-context attention path, block_attn.cu): words a kMaskRowBlock-row query block can see
-    const int ex_src_off = ex.is_causal ? (ex.T_SRC - Tn) : 0;
-    const int ex_blk_end = ex.is_causal ? ex_src_off + min((t / kMaskRowBlock + 1) * kMaskRowBlock, Tn) : ex.T_SRC;
-    const int wneed = ex.dmask != nullptr ? min(ex.W64, (ex_blk_end + 63) >> 6) : 0;
-    for (int i = tid; i < H * 2 * wneed; i += kTopkThreads) img[i] = 0u;
     hist[tid] = 0;
     if (tid == 0) { s_orand[0] = 0u; s_orand[1] = 0xffffffffu; }
     const int ldy = kUp > 0 ? ((P / (kUp > 0 ? kUp : 1) + 2) | 1) : ((W + 2) | 1);        // compile-time when the upsample factor is (W == P / kUp)
@@ -486,38 +480,6 @@ tail_topk_reg_kernel(const float* __restrict__ y3, const float* __restrict__ bia
             if (crow_counts != nullptr) sbits[w] = word;
         }
     }
-    if (ex.dmask != nullptr) {
-        // every alive pixel ORs its token run into the row image; then coalesced stores + the query block's tile activity
-        RowScale rs;
-        rs.L = ex.is_causal ? (ex_src_off + t + 1) : ex.T_SRC; rs.lg = ex.p_lg; rs.halfP = P >> 1;
-        rs.s = __fdiv_rn((float) rs.L, (float) P);
-#pragma unroll
-        for (int hh = 0; hh < kHPW; ++hh) {
-            uint32_t* himg = img + (wid + 8 * hh) * 2 * wneed;
-            for (uint32_t x = (kExactH || wid + 8 * hh < H) ? alive[hh] : 0u; x; x &= x - 1) {
-                const int m = lane * kPerLane + __ffs(x) - 1;
-                const int a = rs.edge(m), b = rs.edge(m + 1);
-                if (b > a)
-                    for (int wd = a >> 5; wd <= ((b - 1) >> 5); ++wd) {
-                        const int lo = max(a - (wd << 5), 0), hi = min(b - (wd << 5), 32);
-                        atomicOr(himg + wd, (hi - lo >= 32 ? 0xffffffffu : ((1u << (hi - lo)) - 1u)) << lo);
-                    }
-            }
-        }
-        __syncthreads();
-        const int nrb = (Tn + kMaskRowBlock - 1) / kMaskRowBlock;
-        uint32_t* act_blk = ex.tile_act + (int64_t) n * H * nrb * ex.act_words + (int64_t) (t / kMaskRowBlock) * ex.act_words;
-        const int64_t act_hs = (int64_t) nrb * ex.act_words;
-        for (int i = tid; i < H * wneed; i += kTopkThreads) {
-            const int h = i / wneed, w = i - h * wneed;
-            const uint2 v = *reinterpret_cast<const uint2*>(img + 2 * i);
-            ex.dmask[(((int64_t) n * H + h) * Tn + t) * ex.W64 + w] = (unsigned long long) v.x | ((unsigned long long) v.y << 32);
-            if ((v.x | v.y) != 0u) {
-                uint32_t* aw = act_blk + h * act_hs + (w >> 5);
-                if (!((*aw >> (w & 31)) & 1u)) atomicOr(aw, 1u << (w & 31));
-            }
-        }
-    }
     if (crow_counts != nullptr) {
         // a8 pass 1 fused: crow[n, t+1] = entries of this row (sea_crow_scan turns the counts into offsets)
         __syncthreads();
@@ -543,7 +505,7 @@ using namespace sea;
 
 static int tail_topk_impl(const float* y3, const float* bias, const float* ln_w, const float* ln_b,
                           const float* k_per_row, float* probs, uint32_t* mask_bits, int32_t* crow_counts, int k_clamp,
-                          int N, int H, int T, int W, int P, void* stream, const MaskExpandArgs& ex) {
+                          int N, int H, int T, int W, int P, void* stream) {
     SEA_CHECK_ARG(y3 && bias && ln_w && ln_b && (probs || mask_bits), "sea_predictor_tail_topk_fwd: null pointer");
     SEA_CHECK_ARG(mask_bits == nullptr || k_per_row != nullptr, "sea_predictor_tail_topk_fwd: k_per_row is required for the top-k");
     SEA_CHECK_ARG(N > 0 && H > 0 && T > 0 && W > 0 && P > 0, "sea_predictor_tail_topk_fwd: bad shape");
@@ -558,14 +520,14 @@ static int tail_topk_impl(const float* y3, const float* bias, const float* ln_w,
     static const bool no_reg = getenv("SEA_TAIL_SMEM") != nullptr;        // development switch for A/B timing
     const int hp_slots = (H + 7) / 8;
     if (!no_reg && hp_slots * (P / 32) <= 32 && P <= 1024 && H <= 64) {
-        const size_t smem_r = (size_t) H * (W + 3) * 4 + (size_t) (G >> 5) * 4 + 16 + (ex.dmask ? (size_t) H * ex.W64 * 8 : 0);
+        const size_t smem_r = (size_t) H * (W + 3) * 4 + (size_t) (G >> 5) * 4 + 16;
         SEA_CHECK_ARG(smem_r <= 72 * 1024, "sea_predictor_tail_topk: row image too large for the fused mask expansion");
         bool launched = true;
 #define SEA_TAILR_L(PL, HP, UP, EX)                                                                                        \
         {                                                                                                                  \
             auto kern = tail_topk_reg_kernel<PL, HP, UP, EX>;                                                              \
             SEA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_r), "smem attr"); \
-            SEA_CUDA_TRY(launch_pdl(kern, dim3(grid), dim3(kTopkThreads), smem_r, s, y3, bias, ln_w, ln_b, k_per_row, probs, mask_bits, crow_counts, k_clamp, N, T, W, H, ex), \
+            SEA_CUDA_TRY(launch_pdl(kern, dim3(grid), dim3(kTopkThreads), smem_r, s, y3, bias, ln_w, ln_b, k_per_row, probs, mask_bits, crow_counts, k_clamp, N, T, W, H), \
                          "tail_topk_reg_kernel launch"); \
         }
 #define SEA_TAILR(PL, HP)                                                                                                  \
@@ -606,10 +568,6 @@ static int tail_topk_impl(const float* y3, const float* bias, const float* ln_w,
             return SEA_OK;
         }
     }
-    if (ex.dmask != nullptr) {
-        set_error("sea_predictor_tail_topk_expand_fwd: needs the register-resident top-k (H %% 8 == 0, (H/8) * (P/32) <= 32)");
-        return SEA_ERR_UNSUPPORTED;
-    }
     const size_t smem = ((size_t) G + (G >> 5)) * 4 + (size_t) H * (W + 2) * 4 + 16;
     SEA_CHECK_ARG(smem <= 220 * 1024, "sea_predictor_tail_topk_fwd: H*P=%d keys do not fit shared memory", G);
 #define SEA_TAIL_LAUNCH(PL, UP)                                                                                       \
@@ -640,39 +598,7 @@ extern "C" {
 int sea_predictor_tail_topk_fwd(const float* y3, const float* bias, const float* ln_w, const float* ln_b,
                                 const float* k_per_row, float* probs, uint32_t* mask_bits, int32_t* crow_counts, int k_clamp,
                                 int N, int H, int T, int W, int P, void* stream) {
-    MaskExpandArgs ex = {nullptr, nullptr, 0, 0, 0, -1, 0};
-    return tail_topk_impl(y3, bias, ln_w, ln_b, k_per_row, probs, mask_bits, crow_counts, k_clamp, N, H, T, W, P, stream, ex);
-}
-
-int64_t sea_block_attention_workspace_bytes(int N, int H, int T_DST, int T_SRC, int D, int P, int k_clamp, int dtype);
-
-int sea_predictor_tail_expand_supported(int H, int P) {
-    if (H % 8 != 0 || P % 32 != 0) return 0;
-    const int pl = P / 32, hp = H / 8;
-    return (pl == 8 && (hp == 4 || hp == 2 || hp == 1)) || (pl == 4 && (hp == 4 || hp == 2 || hp == 1)) || (pl == 2 && (hp == 4 || hp == 2 || hp == 1)) ||
-           (pl == 16 && (hp == 2 || hp == 1));
-}
-
-int sea_predictor_tail_topk_expand_fwd(const float* y3, const float* bias, const float* ln_w, const float* ln_b,
-                                       const float* k_per_row, float* probs, uint32_t* mask_bits, int k_clamp,
-                                       int N, int H, int T, int W, int P, int D, int dtype, void* workspace, int64_t workspace_bytes, void* stream) {
-    SEA_CHECK_ARG(mask_bits && workspace, "sea_predictor_tail_topk_expand_fwd: null pointer");
-    const int64_t need = sea_block_attention_workspace_bytes(N, H, T, T, D, P, k_clamp, dtype);
-    if (need == 0) {
-        set_error("sea_predictor_tail_topk_expand_fwd: the block attention does not support this shape");
-        return SEA_ERR_UNSUPPORTED;
-    }
-    SEA_CHECK_ARG(workspace_bytes >= need && (((uintptr_t) workspace) & 15) == 0, "sea_predictor_tail_topk_expand_fwd: workspace too small or misaligned");
-    MaskExpandArgs ex;
-    ex.W64 = mask_row_words(T);
-    ex.dmask = reinterpret_cast<unsigned long long*>(workspace);
-    ex.tile_act = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(workspace) + (int64_t) N * H * T * ex.W64 * 8);
-    ex.act_words = mask_act_words(T);
-    ex.T_SRC = T;
-    ex.p_lg = exact_edge_shift(P, T);
-    ex.is_causal = 1;
-    SEA_CUDA_TRY(cudaMemsetAsync(ex.tile_act, 0, (size_t) mask_act_bytes(N, H, T, T), (cudaStream_t) stream), "memset tile activity");
-    return tail_topk_impl(y3, bias, ln_w, ln_b, k_per_row, probs, mask_bits, nullptr, k_clamp, N, H, T, W, P, stream, ex);
+    return tail_topk_impl(y3, bias, ln_w, ln_b, k_per_row, probs, mask_bits, crow_counts, k_clamp, N, H, T, W, P, stream);
 }
 
 }  // extern "C"

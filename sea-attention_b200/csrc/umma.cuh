@@ -40,6 +40,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {
     }
 }
+// wait with a back-off between polls: for waits that are not latency critical (a failed try_wait re-issues at once, and in an
+// issue-bound kernel those polls take slots from the warps doing the work)
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, uint32_t ns) {
+    while (!mbar_try_wait(bar, parity)) __nanosleep(ns);
+}
 // same, on a precomputed shared-window address (keeps the generic->shared conversion out of hot loops)
 __device__ __forceinline__ void mbar_wait_addr(uint32_t bar_addr, uint32_t parity) {
     asm volatile(

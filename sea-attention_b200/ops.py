@@ -476,20 +476,9 @@ def performer_causal_state(q, k, v, pos_emb, proj, state: torch.Tensor, t0: int,
     return ctx, avg
 
 
-def block_attention_workspace(N, H, T_DST, T_SRC, D, P, k_clamp, dtype, device):
-    """Workspace of the short-context block attention (dense bit-packed mask + tile activity), or None when the library does
-    not support the shape (the gather kernel is used then)."""
-    if os.environ.get('SEA_ATTN_GATHER') or dtype not in _DTYPES:
-        return None
-    nbytes = int(_lib.load().sea_block_attention_workspace_bytes(N, H, T_DST, T_SRC, D, int(P), int(k_clamp), _DTYPES[dtype]))
-    return torch.empty((nbytes,), dtype=torch.uint8, device=device) if nbytes > 0 else None
-
-
-def predictor_tail_topk(y3, bias, ln_w, ln_b, k_per_row, P: int, want_probs=True, want_bits=True, count_k: int = 0, expand=None):
+def predictor_tail_topk(y3, bias, ln_w, ln_b, k_per_row, P: int, want_probs=True, want_bits=True, count_k: int = 0):
     """a5 tail + a6 + a7 fused: y3 fp32 [N,T,W,H] (conv1x1_umma) -> probs fp32 [N,H,T,P], top-k bit mask [N,T,H*P/32].
-    count_k > 0 additionally fuses pass 1 of a8 (causal prefill): returns int32 crow [N,T+1] holding per-row counts.
-    expand = (workspace, D, k_clamp, dtype): also fuses the mask expansion of the block attention (causal prefill) into the kernel;
-    pass the same workspace to sparse_attention_from_bits(..., expanded=workspace)."""
+    count_k > 0 additionally fuses pass 1 of a8 (causal prefill): returns int32 crow [N,T+1] holding per-row counts."""
     _cuda(y3, bias, ln_w, ln_b, k_per_row)
     y3, bias, ln_w, ln_b = _dense(y3, torch.float32), _dense(bias, torch.float32), _dense(ln_w, torch.float32), _dense(ln_b, torch.float32)
     N, T, W, H = y3.shape
@@ -497,20 +486,11 @@ def predictor_tail_topk(y3, bias, ln_w, ln_b, k_per_row, P: int, want_probs=True
     bits = torch.empty((N, T, (H * P) // 32), dtype=torch.int32, device=y3.device) if want_bits else None
     crow = torch.empty((N, T + 1), dtype=torch.int32, device=y3.device) if count_k > 0 else None
     kpr = None if k_per_row is None else k_per_row.reshape(-1).float().contiguous()
-    if expand is not None:
-        ws, D, k_clamp, dtype = expand
-        _lib.call('sea_predictor_tail_topk_expand_fwd', y3.data_ptr(), bias.data_ptr(), ln_w.data_ptr(), ln_b.data_ptr(), _p(kpr), _p(probs),
-                  _p(bits), int(k_clamp), N, H, T, W, P, int(D), _DTYPES[dtype], ws.data_ptr(), ws.numel(), _stream())
-        return probs, bits
     _lib.call('sea_predictor_tail_topk_fwd', y3.data_ptr(), bias.data_ptr(), ln_w.data_ptr(), ln_b.data_ptr(), _p(kpr), _p(probs),
               _p(bits), _p(crow), int(count_k), N, H, T, W, P, _stream())
     if count_k > 0:
         return probs, bits, crow
     return probs, bits
-
-
-def tail_expand_supported(H: int, P: int) -> bool:
-    return bool(_lib.load().sea_predictor_tail_expand_supported(int(H), int(P)))
 
 
 def predictor_tail(x, weight, bias, ln_w, ln_b, P: int, want_scores=False):
@@ -556,8 +536,7 @@ def sparse_attention(crow, col, q, k, v, scales, cumavg, use_scaler=True, want_p
     return out, pv
 
 
-def sparse_attention_from_bits(bits, q, k, v, scales, cumavg, P: int, k_clamp: int, use_scaler=True, is_causal=True, kernel: str = 'auto',
-                               expanded=None):
+def sparse_attention_from_bits(bits, q, k, v, scales, cumavg, P: int, k_clamp: int, use_scaler=True, is_causal=True, kernel: str = 'auto'):
     """a8 + a9-a14 fused: attention driven directly by the top-k bit mask (no CSR tensors are materialised).
 
     kernel = 'auto' picks the tile-skipping block kernel (sea_block_attention_fwd) where the library supports the shape
@@ -571,13 +550,6 @@ def sparse_attention_from_bits(bits, q, k, v, scales, cumavg, P: int, k_clamp: i
     ca, avg_sh, avg_st = _avg_arg(cumavg, N, H, T_DST, D)
     if kernel not in ('auto', 'gather', 'block'):
         raise SeaError(f'unknown attention kernel {kernel!r}')
-    if expanded is not None:
-        # the dense mask was already written by predictor_tail_topk(expand=...): mask_bits = NULL skips the expansion kernel
-        _lib.call('sea_block_attention_fwd', None, q.data_ptr(), q.stride(0), q.stride(1), q.stride(2),
-                  k.data_ptr(), k.stride(0), k.stride(1), k.stride(2), v.data_ptr(), v.stride(0), v.stride(1), v.stride(2),
-                  sc.data_ptr(), _p(ca), avg_sh, avg_st, int(bool(use_scaler)), _dtype_code(q), out.data_ptr(), N, H, T_DST, T_SRC, D, int(P),
-                  int(k_clamp), int(bool(is_causal)), expanded.data_ptr(), expanded.numel(), _stream(), kernels=1)
-        return out
     if kernel == 'auto' and os.environ.get('SEA_ATTN_GATHER'):
         kernel = 'gather'             # development switch for A/B timing
     ws_bytes = 0
@@ -590,7 +562,7 @@ def sparse_attention_from_bits(bits, q, k, v, scales, cumavg, P: int, k_clamp: i
         _lib.call('sea_block_attention_fwd', bits.data_ptr(), q.data_ptr(), q.stride(0), q.stride(1), q.stride(2),
                   k.data_ptr(), k.stride(0), k.stride(1), k.stride(2), v.data_ptr(), v.stride(0), v.stride(1), v.stride(2),
                   sc.data_ptr(), _p(ca), avg_sh, avg_st, int(bool(use_scaler)), _dtype_code(q), out.data_ptr(), N, H, T_DST, T_SRC, D, int(P),
-                  int(k_clamp), int(bool(is_causal)), ws.data_ptr(), ws_bytes, _stream())
+                  int(k_clamp), int(bool(is_causal)), ws.data_ptr(), ws_bytes, _stream(), kernels=1 if ws_bytes <= 16 else 2)
         return out
     _lib.call('sea_sparse_attention_bits_fwd', bits.data_ptr(), q.data_ptr(), q.stride(0), q.stride(1), q.stride(2),
               k.data_ptr(), k.stride(0), k.stride(1), k.stride(2), v.data_ptr(), v.stride(0), v.stride(1), v.stride(2),

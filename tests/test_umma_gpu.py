@@ -175,30 +175,3 @@ def test_tail_topk_fused_row_counts(sea):
     mask = sea.ops.bits_to_mask(bits, H, P).cpu()
     crow_r, col_r, Z_r = so.resize_from_m_to_t_csr(mask, k, T, True)
     assert torch.equal(crow3.cpu().long(), crow_r) and torch.equal(col3.cpu().long(), col_r)
-
-
-@pytest.mark.parametrize('N,H,T,W,P,k', [(2, 32, 300, 64, 256, 64), (1, 8, 200, 16, 64, 16), (1, 16, 130, 32, 128, 32)])
-def test_tail_topk_fused_mask_expansion(sea, N, H, T, W, P, k):
-    """The top-k kernel can also write the dense bit-packed mask of the block attention: same bits, and the attention that
-    consumes the pre-expanded workspace equals the one that expands the bit mask itself (bit for bit)."""
-    import numpy as np
-    d = 64
-    g = torch.Generator().manual_seed(P + T)
-    y3 = torch.randn(N, T, W, H, generator=g).to(DEV)
-    bias = torch.randn(H, generator=g).to(DEV)
-    ln_w, ln_b = torch.ones(P, device=DEV), torch.zeros(P, device=DEV)
-    kpr = torch.from_numpy(np.tile(so.per_item_top_k_causal(H, k, 1.0, P, T), N)).to(DEV)
-    ws = sea.ops.block_attention_workspace(N, H, T, T, d, P, k, torch.bfloat16, DEV)
-    assert ws is not None
-    ws.fill_(0xAB)                                                          # stale garbage must not leak into the masks
-    probs0, bits0 = sea.ops.predictor_tail_topk(y3, bias, ln_w, ln_b, kpr, P)
-    probs1, bits1 = sea.ops.predictor_tail_topk(y3, bias, ln_w, ln_b, kpr, P, expand=(ws, d, k, torch.bfloat16))
-    assert torch.equal(bits0, bits1) and torch.equal(probs0, probs1)
-    q = (torch.randn(N, H, T, d, generator=g) * d ** -0.5).bfloat16().to(DEV)
-    kk = torch.randn(N, H, T, d, generator=g).bfloat16().to(DEV)
-    v = torch.randn(N, H, T, d, generator=g).bfloat16().to(DEV)
-    scales = torch.randn(N, H, T, 2, generator=g).to(DEV)
-    avg = torch.randn(N, H, T, d, generator=g).bfloat16().to(DEV)
-    ref = sea.ops.sparse_attention_from_bits(bits0, q, kk, v, scales, avg, P, k, True, True, kernel='block')
-    out = sea.ops.sparse_attention_from_bits(bits1, q, kk, v, scales, avg, P, k, True, True, expanded=ws)
-    assert torch.equal(out, ref)
