@@ -279,18 +279,29 @@ def topk_mask_noncausal(probs: torch.Tensor, k, k_oversample: float, token_lengt
 
 
 # ----------------------------------------------------------------------------- a8 CSR interpolation
-def resize_from_m_to_t_csr(mask: torch.Tensor, k: int, target_width: Optional[int] = None, is_causal: bool = True):
+def resize_from_m_to_t_csr(mask: torch.Tensor, k: int, target_width: Optional[int] = None, is_causal: bool = True,
+                           scale_mode: str = 'ieee'):
     """causal_resize_m_to_t.py:910-1007 -> scan_col METHOD 1 (:648-762) -> __scan_col_4_compute (:493-572).
     mask [N,H,T_DST,P] 0/1.  Returns (crow [N,T_DST+1] i64, col [N,Z] i64, Z) with Z = max_n nnz_n;
     rows of items with fewer nnz are zero padded at the tail (:669).  Entry order: (t, h, m) then
-    descending column inside a pixel (:561-572)."""
+    descending column inside a pixel (:561-572).
+
+    scale_mode: how `scales = target_width / original_width` (:642, int64 tensor / python int) is evaluated.  'ieee' = fp32(L) / fp32(P),
+    what torch does on the CPU (and what the CUDA kernels of this repo do).  'cuda_reciprocal' = fp32(L) * (1.0f / fp32(P)), what
+    torch's CUDA true-division kernel does when the divisor is a host scalar (ATen BinaryDivTrueKernel.cu) -- i.e. the reference
+    run on a GPU.  The two agree whenever P is a power of two (every shipped config); for other P a few pixel edges move by one."""
     N, H, T_DST, P = mask.shape
     T_SRC = target_width if target_width is not None else T_DST
     if is_causal:
         tw = np.arange(1, T_SRC + 1, dtype=np.int64)[-T_DST:]          # :954
     else:
         tw = np.full((T_SRC,), T_SRC, dtype=np.int64)[-T_DST:]         # :957
-    scales = (torch.from_numpy(tw) / P).numpy()                        # :642 int64 / int -> fp32
+    if scale_mode == 'ieee':
+        scales = (torch.from_numpy(tw) / P).numpy()                    # :642 int64 / int -> fp32
+    elif scale_mode == 'cuda_reciprocal':
+        scales = (tw.astype(np.float32) * (np.float32(1.0) / np.float32(P))).astype(np.float32)
+    else:
+        raise ValueError(scale_mode)
     assert scales.dtype == np.float32
     b = np.arange(P, dtype=np.int64).reshape(1, P)
     vs = round_half_away((b.astype(np.float32) * scales.reshape(T_DST, 1)).astype(np.float32))        # :654
