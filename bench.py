@@ -242,6 +242,83 @@ def run_reference(args):
     _emit(line)
 
 
+def run_c5(args):
+    """BASELINE configs[4]: SEA attention layer alone, 32 heads, sequence sweep, query-block sharded over the ranks (strong scaling:
+    the sequence is fixed, every rank holds all of q / k / v and produces its own query blocks; no collective on the data path).
+    One JSON line: tokens/s per sequence length, device-timed, max over ranks."""
+    import transformers
+    sea = importlib.import_module('sea-attention_b200')
+    par = importlib.import_module('sea-attention_b200.parallel')
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    dev = torch.device('cuda', local_rank)
+    torch.cuda.set_device(dev)
+    H, P, nbf = 32, 256, 8
+    d, k = (128, 128) if args.workload == 'c5' else (64, 64)
+    dt = torch.bfloat16
+    seqs = [int(x) for x in args.seqs.split(',')]
+    max_T = max(seqs)
+    torch.manual_seed(42)
+    cfg = transformers.BertConfig(hidden_size=H * d, num_attention_heads=H, max_position_embeddings=max_T)
+    mod = sea.PerlinAttention(cfg, sea.PerlinAttentionConfig(performer_nb_factor=nbf, k=k, attention_predictor_length=P, causal=True)).eval().to(dev)
+    mod.benchmarking = True
+    mod.check_padding = False
+    mod.freeze_packed_weights()
+    rows_per_block = 16384                                     # a rank walks its rows in blocks of at most this many (bounds the fp32 probabilities)
+    sweep = []
+    for T in seqs:
+        gen = torch.Generator().manual_seed(T)
+        q = (torch.randn(1, H, T, d, generator=gen) * d ** -0.5).to(dt).to(dev)
+        kk = torch.randn(1, H, T, d, generator=gen).to(dt).to(dev)
+        v = torch.randn(1, H, T, d, generator=gen).to(dt).to(dev)
+        n_blocks = max(world, -(-T // rows_per_block))
+        n_blocks = -(-n_blocks // world) * world
+        mine = [par.query_block_bounds(T, n_blocks, b) for b in range(rank, n_blocks, world)]       # round-robin: late (longer) blocks spread evenly
+
+        def step():
+            outs = None
+            for t0, t1 in mine:
+                if t1 > t0:
+                    outs = mod.forward_query_block(q, kk, v, t0, t1).context_layer
+            return outs
+
+        with torch.no_grad():
+            for _ in range(max(1, min(args.warmup, 2))):
+                step()
+            if dist is not None:
+                dist.barrier()
+            torch.cuda.synchronize()
+            steps = max(1, min(args.steps, 3))
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                step()
+            e1.record()
+            torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        if dist is not None:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        sweep.append({'T': T, 'ms': ms, 'tokens_per_s': T / ms * 1e3, 'blocks': n_blocks})
+        del q, kk, v
+        torch.cuda.empty_cache()
+    if rank == 0:
+        _emit({'metric': 'SEA attn layer fwd tokens/sec, long-context sweep (BASELINE configs[4])', 'unit': 'tokens/s', 'n_gpus': world,
+               'value': sweep[-1]['tokens_per_s'], 'higher_is_better': True, 'scaling': 'strong', 'dtype': 'bf16', 'data': 'synthetic',
+               'config': {'workload': f'SEA attention layer alone, 32 heads d={d}, k={k}, predictor_length={P}, nbf={nbf}, causal, N=1, seq sweep',
+                          'sharding': 'query blocks (K/V replicated, Performer prefix recomputed locally, 8-row CNN halo); no collective'},
+               'sweep': sweep})
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -251,10 +328,16 @@ def main():
     ap.add_argument('--dtype', default='bf16')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='launch the kernels eagerly instead of replaying one CUDA graph per step')
+    ap.add_argument('--workload', default='ns', choices=['ns', 'c5', 'c5-d64'],
+                    help="ns: the north-star layer forward (default, the contract line); c5 / c5-d64: BASELINE configs[4], the layer alone over a "
+                         "sequence sweep, query-block sharded over the ranks (d=128 k=128 / d=64 k=64)")
+    ap.add_argument('--seqs', default='4096,8192,16384,32768,65536,131072')
     args = ap.parse_args()
     _claim_stdout()
     if args.impl == 'reference':
         return run_reference(args)
+    if args.workload != 'ns':
+        return run_c5(args)
 
     import transformers
     sea = importlib.import_module('sea-attention_b200')

@@ -345,17 +345,45 @@ class PerlinAttention(nn.Module):
             return self._forward_causal_stateful(q, k, v, q_for_atten, k_for_atten, v_for_atten, q_for_score, k_for_score, attention_mask, last_state)
         return self._forward_causal_prefill(q, k, v, q_for_atten, k_for_atten, v_for_atten, q_for_score, k_for_score, attention_mask)
 
+    def forward_query_block(self, q, k, v, t0: int, t1: int):
+        """Query-block sharded causal prefill (BASELINE configs[4]): q, k, v [N,H,T,d] hold the whole sequence; returns
+        the PerlinAttentionOutput of query rows [t0, t1) only (context_layer [N, t1-t0, H*d]).  Concatenating the blocks of a
+        partition of [0, T) reproduces forward() on the whole sequence; blocks need nothing from each other."""
+        if not self.pconfig.causal:
+            raise SeaError('query-block sharding is defined for the causal model')
+        if self.training:
+            raise SeaError('forward_query_block is an inference path')
+        return self._forward_causal_prefill(q, k, v, q, k, v, q, k, None, block=(t0, t1))
+
     # ------------------------------------------------------------------------------------------------
-    def _forward_causal_prefill(self, q, k, v, q_for_atten, k_for_atten, v_for_atten, q_for_score, k_for_score, attention_mask, capture=None):
-        """Causal prefill (T_DST == T_SRC).  `capture` (dict) receives the CNN intermediates the decode state is built from."""
+    def _forward_causal_prefill(self, q, k, v, q_for_atten, k_for_atten, v_for_atten, q_for_score, k_for_score, attention_mask, capture=None,
+                                block=None):
+        """Causal prefill (T_DST == T_SRC).  `capture` (dict) receives the CNN intermediates the decode state is built from.
+
+        block = (t0, t1): query-block sharding of a long prefill: q / k / v hold the whole sequence (K and V are
+        replicated on every rank), and only the query rows [t0, t1) are produced -- context [N, t1-t0, H*d], probabilities
+        [N,H,t1-t0,P].  No exchange with the other blocks is needed: the Performer prefix sums are recomputed locally over [0, t1)
+        (linear, the cheapest stage), the predictor MLP and the two dilated causal convolutions run on rows [t0-8, t1) -- each conv
+        looks 4 rows back, so 8 halo rows make every kept row exact --, top-k is per row (K_t uses the absolute t), and the
+        sparse attention takes T_DST = t1-t0 query rows against T_SRC = t1 source tokens."""
         pc = self.pconfig
         N, H, T, d = q.shape
-        assert attention_mask.shape == (N, 1, T, T), f'causal additive mask must be [N,1,T,T], got {tuple(attention_mask.shape)}'
+        assert attention_mask is None or attention_mask.shape == (N, 1, T, T), f'causal additive mask must be [N,1,T,T], got {tuple(attention_mask.shape)}'
         assert k.shape == (N, H, T, d) and v.shape == (N, H, T, d)
         if v_for_atten.data_ptr() != v.data_ptr() or v_for_atten.shape != v.shape:
             raise SeaError('v_for_atten must alias v (LoRA-in-approximation, self_attention.py:104-120, is not implemented)')
         P = pc.attention_predictor_length
-        if self.check_padding:
+        t0, t1 = (0, T) if block is None else (int(block[0]), int(block[1]))
+        if not (0 <= t0 < t1 <= T):
+            raise SeaError(f'bad query block [{t0}, {t1}) of {T} rows')
+        h0 = max(t0 - 8, 0)                       # first halo row
+        if block is not None:
+            if capture is not None or self.output_attentions:
+                raise SeaError('a query block returns context and probabilities only (no decode state, no CSR tensors)')
+            q, k, v = q[:, :, :t1], k[:, :, :t1], v[:, :, :t1]
+            q_for_atten, k_for_atten = q_for_atten[:, :, :t1], k_for_atten[:, :, :t1]
+            q_for_score, k_for_score = q_for_score[:, :, t0:t1], k_for_score[:, :, :t1]
+        if self.check_padding and attention_mask is not None:
             # dst_attention_mask = causal_attention_mask[:,:,:,:1] (attention.py:432); the reference reads the
             # whole [N,1,T,T] mask and syncs (:434) -- only the first column matters.
             if not bool((attention_mask[:, 0, :, 0] > -1).all()):
@@ -364,10 +392,14 @@ class PerlinAttention(nn.Module):
         w = self._weights_fp32()
         S = self.attention_predictor_dec_row_splits
         W = P // self.attention_predictor_dec_row_down_scale
-        k_per_row, z_alloc = self._shape_consts(H, P, T, T, q.device)
+        k_per_row, z_alloc = self._shape_consts(H, P, t1, t1 - t0, q.device)
 
         # a2+a3 (+ running mean for a13)
         ctx, cumavg = ops.performer_causal(q_for_atten, k_for_atten, v, w['pos'], w['proj'])
+        v_mlp = v
+        if block is not None:
+            ctx, v_mlp = ctx[:, :, h0:t1].contiguous(), v[:, :, h0:t1]
+            cumavg = cumavg[:, :, t0:t1]
         # a4
         # (weight packings of the tensor-core kernels are cached per module and re-made only when a parameter changes)
         pk = self._packed
@@ -383,7 +415,7 @@ class PerlinAttention(nn.Module):
         # ... and where the shape allows (W = 64, 64 -> 64 -> 32 channels) that 1x1 conv runs inside the second 3x3 conv's kernel
         fuse_c3 = tc_tail and ops.conv3x3_conv1x1_supported(q.dtype, W, 64, cw['conv2_w'].shape[0], cw['conv3_w'].shape[0])
         y = y3 = None
-        cnn_in, scales, _ = ops.predictor_mlp(ctx, v, w, S, W, packed=pk, **({'c_out': 64} if pad_c else {}))
+        cnn_in, scales, _ = ops.predictor_mlp(ctx, v_mlp, w, S, W, packed=pk, **({'c_out': 64} if pad_c else {}))
         y1 = ops.causal_conv3x3_dil2_relu(cnn_in, cw['conv1_w'], cw['conv1_b'], packed=pk, slot='conv1', src=net[0].module.weight)
         if fuse_c3:
             y3 = ops.causal_conv3x3_relu_conv1x1(y1, cw['conv2_w'], cw['conv2_b'], cw['conv3_w'], cw['conv3_b'], packed=pk, slot='conv2',
@@ -392,6 +424,12 @@ class PerlinAttention(nn.Module):
             y = ops.causal_conv3x3_dil2_relu(y1, cw['conv2_w'], cw['conv2_b'], packed=pk, slot='conv2', src=net[2].module.weight)
         if capture is not None:
             capture['cnn_in'], capture['conv1'] = cnn_in, y1
+        if t0 > h0:                               # drop the halo rows (their conv outputs saw zero padding instead of real rows)
+            if y3 is not None:
+                y3 = y3[:, t0 - h0:].contiguous()
+            else:
+                y = y[:, t0 - h0:].contiguous()
+            scales = scales[:, :, t0 - h0:].contiguous()
         # a5 .. a7
         kpr = k_per_row.repeat(N) if N > 1 else k_per_row
         if tc_tail:
@@ -421,7 +459,7 @@ class PerlinAttention(nn.Module):
             Z = 0
         else:
             # a8 (int32 indices internally; no host sync: col is allocated at a shape-derived upper bound)
-            crow, col, Z, head_ptr = ops.csr_from_bits(bits, H, P, pc.k, T, is_causal=True, index_dtype=torch.int32, z_alloc=z_alloc,
+            crow, col, Z, head_ptr = ops.csr_from_bits(bits, H, P, pc.k, t1, is_causal=True, index_dtype=torch.int32, z_alloc=z_alloc,
                                                        want_head_ptr=True, crow_counts=crow_counts)
             # a9-a14
             context, pvals = ops.sparse_attention(crow, col, q_for_score, k_for_score, v, scales, cumavg,
@@ -429,7 +467,7 @@ class PerlinAttention(nn.Module):
                                                   head_ptr=head_ptr)
         partial_probs = partial_mask = None
         if self.output_attentions:
-            partial_mask, partial_probs = _csr_outputs(crow, col, pvals, (N, T, H * T))
+            partial_mask, partial_probs = _csr_outputs(crow, col, pvals, (N, t1 - t0, H * t1))
         return PerlinAttentionOutput(
             loss=0, context_layer=context, partial_attention_probs=partial_probs, partial_attention_mask=partial_mask,
             estimated_attention_probs_m=probs, estimated_attention_probs=probs, dense_attention_probs=None,
@@ -573,7 +611,7 @@ class PerlinAttention(nn.Module):
             context, pvals = ops.sparse_attention(crow, col, q_for_score, k_for_score, v, scales, avg,
                                                   use_scaler=pc.partial_attention_scaler, want_probs=self.output_attentions, head_ptr=head_ptr)
             if self.output_attentions:
-                partial_mask, partial_probs = _csr_outputs(crow, col, pvals, (N, T, H * T))
+                partial_mask, partial_probs = _csr_outputs(crow, col, pvals, (N, t1 - t0, H * t1))
         return PerlinAttentionOutput(
             loss=0, context_layer=context, partial_attention_probs=partial_probs, partial_attention_mask=partial_mask,
             estimated_attention_probs_m=probs, estimated_attention_probs=probs, dense_attention_probs=None,

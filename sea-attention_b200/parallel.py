@@ -42,6 +42,40 @@ def all_gather_context(ctx_local: torch.Tensor, total_batch: int, group: Optiona
     return torch.cat([bufs[r][: sizes[r][1] - sizes[r][0]] for r in range(world)], dim=0)
 
 
+def query_block_bounds(T: int, world_size: int, rank: int, align: int = 128) -> Tuple[int, int]:
+    """Query rows [t0, t1) of `rank` for a long-context prefill sharded by query block: contiguous blocks of equal
+    size rounded to `align` rows (the row-block of the attention kernels); causal nnz per row is ~ H * k, so equal blocks balance
+    the sparse stages."""
+    per = -(-T // world_size)
+    per = -(-per // align) * align
+    t0 = min(rank * per, T)
+    return t0, min(t0 + per, T)
+
+
+def forward_query_sharded(module, q, k, v, world_size: int, rank: int, gather: bool = False, group: Optional[dist.ProcessGroup] = None):
+    """One rank's share of a query-block sharded prefill: q, k, v [N,H,T,d] replicated on every rank; returns this rank's context
+    rows [N, t1-t0, H*d], or -- gather=True -- the whole [N,T,H*d] on every rank (one all-gather over NVLink / NVSwitch, the only
+    collective; ranks whose block is empty contribute nothing)."""
+    T = q.shape[2]
+    t0, t1 = query_block_bounds(T, world_size, rank)
+    if t1 > t0:
+        ctx = module.forward_query_block(q, k, v, t0, t1).context_layer
+    else:
+        ctx = torch.zeros((q.shape[0], 0, q.shape[1] * q.shape[3]), dtype=q.dtype, device=q.device)
+    if not gather:
+        return ctx
+    per = query_block_bounds(T, world_size, 0)[1]
+    pad = torch.zeros((ctx.shape[0], per, ctx.shape[2]), dtype=ctx.dtype, device=ctx.device)
+    pad[:, : ctx.shape[1]] = ctx
+    bufs = [torch.empty_like(pad) for _ in range(world_size)]
+    dist.all_gather(bufs, pad, group=group)
+    parts = []
+    for r in range(world_size):
+        b, e = query_block_bounds(T, world_size, r)
+        parts.append(bufs[r][:, : e - b])
+    return torch.cat(parts, dim=1)
+
+
 def max_over_ranks(value: float, device, group: Optional[dist.ProcessGroup] = None) -> float:
     """Device-side timing reduction used by bench.py: the slowest rank defines the step time."""
     if not dist.is_initialized() or dist.get_world_size(group) == 1:

@@ -66,3 +66,48 @@ def test_shard_bounds_cover_everything(sea):
             assert max(sizes) - min(sizes) <= 1
     with pytest.raises(ValueError):
         par.shard_bounds(4, 2, 2)
+
+
+class _StubModule:
+    """Stands in for PerlinAttention.forward_query_block on the CPU: context row t depends on query row t only."""
+    def forward_query_block(self, q, k, v, t0, t1):
+        import types
+        N, H, T, d = q.shape
+        return types.SimpleNamespace(context_layer=(q[:, :, t0:t1] * 2.0 + 1.0).permute(0, 2, 1, 3).reshape(N, t1 - t0, H * d))
+
+
+def _qb_worker(rank, world, port, T, out_q):
+    import importlib
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    par = importlib.import_module('sea-attention_b200.parallel')
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(1)
+        q = torch.randn(2, 3, T, 4, generator=g)
+        mine = par.forward_query_sharded(_StubModule(), q, q, q, world, rank, gather=False)
+        t0, t1 = par.query_block_bounds(T, world, rank)
+        full = par.forward_query_sharded(_StubModule(), q, q, q, world, rank, gather=True)
+        want = (q * 2.0 + 1.0).permute(0, 2, 1, 3).reshape(2, T, 12)
+        out_q.put((rank, mine.shape[1] == t1 - t0, bool(torch.equal(full, want))))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('T', [100, 256, 700])
+def test_query_block_sharding_and_gather_gloo(T):
+    """world_size 2, gloo: query-block bounds tile [0, T), each rank computes only its rows, the optional all-gather rebuilds the
+    whole context on every rank (blocks of unequal size, including an empty one when T <= the 128-row alignment)."""
+    ctx = mp.get_context('spawn')
+    out_q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_qb_worker, args=(r, 2, port, T, out_q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [out_q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(a and b for _, a, b in res), res

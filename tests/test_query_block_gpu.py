@@ -1,0 +1,64 @@
+"""GPU: query-block sharding of a causal prefill (SURVEY 8e / BASELINE configs[4]): the blocks of a partition of [0, T), each computed
+with nothing from the others (replicated K / V, locally recomputed Performer prefix, 8-row CNN halo), concatenate to the
+unsharded forward."""
+import importlib
+
+import pytest
+import torch
+import transformers
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+def _module(sea, H, d, T, P, k, nbf=8):
+    torch.manual_seed(5)
+    cfg = transformers.BertConfig(hidden_size=H * d, num_attention_heads=H, max_position_embeddings=T)
+    m = sea.PerlinAttention(cfg, sea.PerlinAttentionConfig(performer_nb_factor=nbf, k=k, attention_predictor_length=P, causal=True)).eval().to(DEV)
+    m.benchmarking = True
+    return m
+
+
+@pytest.mark.parametrize('H,d,T,P,k,dtype,world', [(32, 64, 2048, 256, 64, torch.bfloat16, 4), (4, 64, 1000, 64, 16, torch.bfloat16, 3),
+                                                   (4, 32, 700, 64, 16, torch.float32, 2), (8, 128, 1024, 128, 32, torch.float32, 4)])
+def test_query_blocks_concatenate_to_the_full_prefill(sea, H, d, T, P, k, dtype, world):
+    par = importlib.import_module(sea.__name__ + '.parallel')
+    m = _module(sea, H, d, T, P, k)
+    g = torch.Generator().manual_seed(T)
+    q = (torch.randn(1, H, T, d, generator=g) * d ** -0.5).to(dtype).to(DEV)
+    kk = torch.randn(1, H, T, d, generator=g).to(dtype).to(DEV)
+    v = torch.randn(1, H, T, d, generator=g).to(dtype).to(DEV)
+    from oracle import sea_oracle as so
+    am = so.causal_additive_mask(T, dtype, 1).to(DEV)
+    with torch.no_grad():
+        full = m(q, kk, v, q, kk, v, q, kk, am, None, None)
+        parts, probs = [], []
+        covered = 0
+        for r in range(world):
+            t0, t1 = par.query_block_bounds(T, world, r)
+            assert t0 == covered
+            covered = t1
+            if t1 > t0:
+                o = m.forward_query_block(q, kk, v, t0, t1)
+                assert o.context_layer.shape == (1, t1 - t0, H * d)
+                parts.append(o.context_layer)
+                probs.append(o.estimated_attention_probs)
+        assert covered == T
+    torch.cuda.synchronize()
+    ctx = torch.cat(parts, dim=1)
+    pr = torch.cat(probs, dim=2)
+    # the predictor of a block sees exactly the rows the full run sees (8 halo rows cover both dilated convs): same probabilities,
+    # hence the same top-k and the same context, up to the summation order inside kernels whose tiling depends on the row count
+    torch.testing.assert_close(pr, full.estimated_attention_probs, rtol=1e-4, atol=1e-7)
+    tol = dict(rtol=2e-2, atol=2e-2) if dtype == torch.bfloat16 else dict(rtol=1e-3, atol=1e-5)
+    bad = (ctx.float() - full.context_layer.float()).abs() > tol['atol'] + tol['rtol'] * full.context_layer.float().abs()
+    assert float(bad.float().mean()) < 1e-3, float(bad.float().mean())
+
+
+def test_query_block_argument_checks(sea):
+    m = _module(sea, 4, 64, 256, 64, 16)
+    x = torch.randn(1, 4, 256, 64, device=DEV).bfloat16()
+    with pytest.raises(sea.SeaError):
+        m.forward_query_block(x, x, x, 128, 128)
+    with pytest.raises(sea.SeaError):
+        m.forward_query_block(x, x, x, 0, 300)
