@@ -147,12 +147,65 @@ def golden_layer(name, H, d, T, k, P, nbf, causal, k_flatten_dim=None, seed_inpu
     print(f'{name}: dense-vs-sparse context max err {err:.3e}  nnz {int(csr.crow_indices()[0, -1])}  ({time.time() - t0:.0f}s)')
 
 
+def golden_state_ops():
+    """The reference's three stateful decode ops (attention_state.py:43-98 StatefulCausalPerformer, :142-187 StatefulCausalCNN,
+    :205-224 StatefulCumAvg) driven exactly as PerlinAttention drives them during a token-by-token decode, on seeded inputs."""
+    rh.load_reference()
+    from src.models.perlin_attention import attention_state as ast_
+    from src.models.perlin_attention.modules import CausalConv2d
+    g = torch.Generator().manual_seed(99)
+    N, H, T, F_, E = 2, 3, 37, 9, 10
+    chunks = [5, 1, 1, 3, 1, 16, 1, 9]                                     # prompt of 5 tokens, then single tokens / small chunks
+    assert sum(chunks) == T
+    parent = ast_.PerlinAttentionState(None)
+    parent.num_heads, parent.head_dim, parent.embd_dim = H, E, H * E
+    # --- performer recurrence (operates on whatever q / k it is given; fp64 running sums, eps 1e-12)
+    qf = torch.rand(N, H, T, F_, generator=g) + 1e-3
+    kf = torch.rand(N, H, T, F_, generator=g) + 1e-3
+    v = torch.randn(N, H, T, E, generator=g)
+    perf = ast_.StatefulCausalPerformer(parent, None)
+    outs, t = [], 0
+    for c in chunks:
+        outs.append(perf(qf[:, :, t:t + c], kf[:, :, :t + c], v[:, :, :t + c]))
+        t += c
+    perf_out = torch.cat(outs, dim=-2)
+    # --- running mean
+    ca = ast_.StatefulCumAvg(parent)
+    outs, t = [], 0
+    for c in chunks:
+        outs.append(ca(v[:, :, :t + c], c))
+        t += c
+    cumavg_out = torch.cat(outs, dim=-2)
+    # --- windowed causal CNN: two dilated causal 3x3 convs + ReLU, the receptive field of the predictor CNN (8 rows < window 24)
+    C, Wd = 4, 6
+    torch.manual_seed(7)
+    cnn = torch.nn.Sequential(CausalConv2d(C, C, 3, padding=2, dilation=2, causal=True), torch.nn.ReLU(),
+                              CausalConv2d(C, C, 3, padding=2, dilation=2, causal=True), torch.nn.ReLU())
+    x = torch.randn(N, C, T, Wd, generator=g)
+    st = ast_.StatefulCausalCNN(parent)
+    outs, t = [], 0
+    with torch.no_grad():
+        for c in chunks:
+            outs.append(st(cnn, x[:, :, t:t + c], c))
+            t += c
+        cnn_out = torch.cat(outs, dim=-2)
+        cnn_full = cnn(x)
+    sd = {k_: _np(v_) for k_, v_ in cnn.state_dict().items()}
+    np.savez_compressed(os.path.join(GOLDEN, 'state_ops.npz'), chunks=np.array(chunks), qf=_np(qf), kf=_np(kf), v=_np(v), performer_out=_np(perf_out),
+                        cumavg_out=_np(cumavg_out), cnn_x=_np(x), cnn_out=_np(cnn_out), cnn_full=_np(cnn_full),
+                        **{'cnn.' + k_: v_ for k_, v_ in sd.items()})
+    print('state_ops: windowed CNN vs full CNN max err', float((cnn_out - cnn_full).abs().max()))
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
+    if '--state-only' in sys.argv:
+        return golden_state_ops()
     golden_kat_causal_resize()
     golden_kat_causal_conv()
     golden_layer('layer_causal_h4_t128', H=4, d=64, T=128, k=8, P=32, nbf=8, causal=True)
     golden_layer('layer_causal_h3_t100', H=3, d=32, T=100, k=6, P=16, nbf=4, causal=True)
+    golden_state_ops()
     if '--with-bert' in sys.argv:
         golden_layer('layer_bert_h4_t64', H=4, d=64, T=64, k=8, P=32, nbf=1, causal=False, k_flatten_dim='batch')
 

@@ -626,3 +626,74 @@ def sparse_attention_grads(alive: torch.Tensor, q, k, v, scales, dout, use_scale
     out = ctx.permute(0, 2, 1, 3).reshape(N, T_DST, H * D)
     out.backward(dout.double())
     return out.detach().float(), q_.grad.float(), k_.grad.float(), v_.grad.float(), s_.grad.float()
+
+
+# =====================================================================================================================
+# a17: the stateful decode ops of attention_state.py, restated (pinned by tests/golden/state_ops.npz, which the unmodified
+# reference classes produced -- oracle/make_golden.py::golden_state_ops)
+# =====================================================================================================================
+class StatefulCausalPerformerOracle:
+    """attention_state.py:43-98.  Linear-attention recurrence on the q / k it is handed: running sums in fp64 (:87,:91), cast
+    back to the input dtype before every contraction, eps 1e-12 on the normaliser (:89).  The new tokens are cut with
+    torch.chunk(min(T_new, 16)) (:84-86) -- i.e. into that many pieces, not pieces of that size."""
+
+    def __init__(self):
+        self.k_cumsum = 0
+        self.context_cumsum = 0
+
+    def __call__(self, q, k, v):
+        T_new = q.shape[-2]
+        n_chunks = min(T_new, 16)
+        outs = []
+        for qc, kc, vc in zip(q.chunk(n_chunks, dim=-2), k[..., -T_new:, :].chunk(n_chunks, dim=-2), v[..., -T_new:, :].chunk(n_chunks, dim=-2)):
+            k_cum = self.k_cumsum + kc.cumsum(dim=-2, dtype=torch.float64)
+            d_inv = 1.0 / torch.einsum('...nd,...nd->...n', qc, k_cum.type_as(qc) + 1e-12)
+            ctx = torch.einsum('...nd,...ne->...nde', kc, vc)
+            ctx_cum = self.context_cumsum + ctx.cumsum(dim=-3, dtype=torch.float64)
+            outs.append(torch.einsum('...nde,...nd,...n->...ne', ctx_cum.type_as(qc), qc, d_inv))
+            self.k_cumsum = k_cum[:, :, -1:]
+            self.context_cumsum = ctx_cum[:, :, -1:]
+        return torch.cat(outs, dim=-2)
+
+
+class StatefulCumAvgOracle:
+    """attention_state.py:205-224: running mean of v over the absolute position, advanced by q_len tokens per call."""
+
+    def __init__(self):
+        self.cumsum = 0
+        self.prev_len = 0
+
+    def __call__(self, v, q_len: int):
+        cs = v[..., -q_len:, :].cumsum(dim=-2) + self.cumsum
+        self.cumsum = cs[..., -1:, :].clone()
+        cs = cs / torch.arange(self.prev_len + 1, self.prev_len + 1 + cs.shape[-2]).view(1, 1, -1, 1)
+        self.prev_len += q_len
+        return cs
+
+
+class StatefulCausalCNNOracle:
+    """attention_state.py:142-187: the CNN is re-run on a window of the most recent rows -- at least max(T_new, 24) of them,
+    extended back to the start of the oldest stored piece -- and the last T_new output rows are kept.  Exact as long as the
+    CNN's causal receptive field (8 rows for the predictor's two dilated 3x3 convs) fits into the window."""
+
+    def __init__(self, window_size: int = 24):
+        self.window_size = window_size
+        self.xs = []
+        self.xs_len = 0
+
+    def __call__(self, cnn, x, x_len: int):
+        self.xs.append(x)
+        self.xs_len += x.shape[-2]
+        x_start = max(self.xs_len - max(x.shape[-2], self.window_size), 0)
+        need = self.xs_len - x_start
+        keep, got = [], 0
+        for piece in reversed(self.xs):
+            if got >= need:
+                break
+            keep.append(piece)
+            got += piece.shape[-2]
+        keep.reverse()
+        self.xs = keep
+        window = torch.cat(keep, dim=-2)
+        window = window[..., -min(window.shape[-2], need):, :]
+        return cnn(window)[..., -x_len:, :].clone()

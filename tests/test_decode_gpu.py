@@ -100,3 +100,59 @@ def test_decode_bf16_tensor_core_shape(sea):
     ctx = torch.cat(rows, dim=1).float()
     assert torch.isfinite(ctx).all()
     assert _close_rows(ctx, full.context_layer[:, T0:].float(), 5e-2, 5e-2) >= 0.5
+
+
+def test_decode_primitives_match_the_stateful_oracle(sea):
+    """a17 against an oracle of attention_state.py (oracle.StatefulCausalPerformerOracle / StatefulCumAvgOracle /
+    StatefulCausalCNNOracle, pinned to the unmodified reference classes by tests/golden/state_ops.npz): the incremental Performer
+    + running mean kernel and the windowed causal convolutions, advanced over the same token chunks.
+
+    The reference's recurrence is fed what its stateless Performer feeds the same sums: the generalized-attention features of
+    q / k (common/performer.py, FastAttention) and v_for_atten = cat(v_eye_learned_causal, v).  (attention_state.py:287-301 hands
+    the recurrence the raw q / k instead -- the reference's own 'TODO: fix numerical stability' path -- so the decode of the
+    reference is not its prefill; here row t of a decode IS row t of the prefill, the property test_perlin_opt_cache.py wants.)"""
+    N, H, d, T, F = 2, 3, 32, 37, 11
+    chunks = [5, 1, 1, 3, 1, 16, 1, 9]
+    g = torch.Generator().manual_seed(11)
+    q = (torch.randn(N, H, T, d, generator=g) * d ** -0.5)
+    kk = torch.randn(N, H, T, d, generator=g)
+    v = torch.randn(N, H, T, d, generator=g)
+    proj = torch.randn(F, d, generator=g)
+    pos = torch.randn(T, d, generator=g)
+    qf, kf = so.performer_features_generalized(q, proj), so.performer_features_generalized(kk, proj)
+    vfa = torch.cat([pos.view(1, 1, T, d).expand(N, H, T, d), v], dim=-1)
+    perf, ca = so.StatefulCausalPerformerOracle(), so.StatefulCumAvgOracle()
+    state = sea.ops.performer_state_new(N, H, d, F, DEV)
+    qd, kd, vd, pd, prd = (x.to(DEV) for x in (q, kk, v, pos, proj))
+    t = 0
+    for i, c in enumerate(chunks):
+        want_ctx = perf(qf[:, :, t:t + c], kf[:, :, :t + c], vfa[:, :, :t + c])
+        want_avg = ca(v[:, :, :t + c], c)
+        if i == 0:          # the prompt: the state a prefill leaves behind
+            sea.ops.performer_state_build(kd[:, :, :c], vd[:, :, :c], pd, prd, state)
+            got_ctx, got_avg = sea.ops.performer_causal(qd[:, :, :c], kd[:, :, :c], vd[:, :, :c], pd, prd)
+        else:
+            got_ctx, got_avg = sea.ops.performer_causal_state(qd[:, :, t:t + c], kd[:, :, t:t + c], vd[:, :, t:t + c], pd, prd, state, t)
+        torch.testing.assert_close(got_ctx.cpu(), want_ctx, rtol=2e-4, atol=2e-5)
+        torch.testing.assert_close(got_avg.cpu(), want_avg, rtol=1e-5, atol=1e-6)
+        t += c
+    # windowed CNN: the decode keeps the last 4 rows of each dilated conv's input (5-row windows); the oracle re-runs >= 24 rows
+    import numpy as np, os
+    fx = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'state_ops.npz'))
+    w0, m0, b0 = (torch.from_numpy(fx['cnn.0.' + n]) for n in ('weight', 'weight_mask', 'bias'))
+    w2, m2, b2 = (torch.from_numpy(fx['cnn.2.' + n]) for n in ('weight', 'weight_mask', 'bias'))
+    x = torch.from_numpy(fx['cnn_x'])                       # [N,C,T,W]
+    xcl = x.permute(0, 2, 3, 1).contiguous().to(DEV)         # channels-last [N,T,W,C]
+    Nc, C, Tc, Wc = x.shape
+    win_x = torch.zeros(Nc, 4, Wc, C, device=DEV)
+    win_y = torch.zeros(Nc, 4, Wc, C, device=DEV)
+    rows = []
+    for tt in range(Tc):
+        xw = torch.cat([win_x, xcl[:, tt:tt + 1]], dim=1)
+        y1 = sea.ops.causal_conv3x3_dil2_relu(xw, (w0 * m0).to(DEV), b0.to(DEV))[:, 4:5].contiguous()
+        yw = torch.cat([win_y, y1], dim=1)
+        y2 = sea.ops.causal_conv3x3_dil2_relu(yw, (w2 * m2).to(DEV), b2.to(DEV))[:, 4:5].contiguous()
+        rows.append(y2)
+        win_x, win_y = xw[:, 1:].contiguous(), yw[:, 1:].contiguous()
+    got = torch.cat(rows, dim=1).permute(0, 3, 1, 2).cpu()
+    torch.testing.assert_close(got, torch.from_numpy(fx['cnn_out']), rtol=1e-4, atol=1e-5)

@@ -166,3 +166,39 @@ def test_performer_restatements_pinned_to_in_tree_jax_original(causal, d, F, T):
     torch.testing.assert_close(fa(q, k, v), want, rtol=1e-5, atol=1e-8)
     mine = so.performer_causal(q, k, v, proj) if causal else so.performer_noncausal(q, k, v, proj)
     torch.testing.assert_close(mine.double(), want, rtol=2e-4, atol=1e-6)       # sea_oracle computes the features in fp32
+
+
+def test_stateful_decode_ops_match_reference_fixture():
+    """a17: the oracle's restatement of attention_state.py's three stateful ops against the outputs of the unmodified reference
+    classes (tests/golden/state_ops.npz, oracle/make_golden.py::golden_state_ops), driven token by token the same way."""
+    import os
+    import numpy as np
+    import torch
+    from oracle import sea_oracle as so
+    fx = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'state_ops.npz'))
+    chunks = [int(c) for c in fx['chunks']]
+    qf, kf, v = (torch.from_numpy(fx[n]) for n in ('qf', 'kf', 'v'))
+    perf, ca = so.StatefulCausalPerformerOracle(), so.StatefulCumAvgOracle()
+    outs_p, outs_a, t = [], [], 0
+    for c in chunks:
+        outs_p.append(perf(qf[:, :, t:t + c], kf[:, :, :t + c], v[:, :, :t + c]))
+        outs_a.append(ca(v[:, :, :t + c], c))
+        t += c
+    assert torch.equal(torch.cat(outs_p, dim=-2), torch.from_numpy(fx['performer_out']))
+    assert torch.equal(torch.cat(outs_a, dim=-2), torch.from_numpy(fx['cumavg_out']))
+    # windowed CNN: two dilated causal convs + ReLU from the fixture's weights, through the oracle's own conv
+    w0, m0, b0 = (torch.from_numpy(fx['cnn.0.' + n]) for n in ('weight', 'weight_mask', 'bias'))
+    w2, m2, b2 = (torch.from_numpy(fx['cnn.2.' + n]) for n in ('weight', 'weight_mask', 'bias'))
+
+    def cnn(x):
+        y = torch.relu(so.causal_conv2d(x, w0, m0, b0, 3, 2, 2))
+        return torch.relu(so.causal_conv2d(y, w2, m2, b2, 3, 2, 2))
+    x = torch.from_numpy(fx['cnn_x'])
+    st = so.StatefulCausalCNNOracle()
+    outs, t = [], 0
+    for c in chunks:
+        outs.append(st(cnn, x[:, :, t:t + c], c))
+        t += c
+    got = torch.cat(outs, dim=-2)
+    torch.testing.assert_close(got, torch.from_numpy(fx['cnn_out']), rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(got, torch.from_numpy(fx['cnn_full']), rtol=1e-5, atol=1e-6)
