@@ -147,6 +147,33 @@ def golden_layer(name, H, d, T, k, P, nbf, causal, k_flatten_dim=None, seed_inpu
     print(f'{name}: dense-vs-sparse context max err {err:.3e}  nnz {int(csr.crow_indices()[0, -1])}  ({time.time() - t0:.0f}s)')
 
 
+def golden_layer_padded(name, H, d, T, k, P, nbf, lengths, seed_inputs=4321):
+    """Causal layer with PADDED query rows (attention.py:401-449: a row t is padded iff causal_mask[n,0,t,0] <= -1; :512-514 zeroes
+    v / v_for_atten there, :928-931 kills its top-k): batch of len(lengths) items, item n has lengths[n] real rows, the rest of its
+    mask rows are fully masked.  Dense path only (benchmarking=False)."""
+    N = len(lengths)
+    m = rh.build_reference_attention(H, d, T, k, P, nbf, True)
+    g = torch.Generator().manual_seed(seed_inputs)
+    q = torch.randn(N, H, T, d, generator=g) * d ** -0.5
+    kk = torch.randn(N, H, T, d, generator=g)
+    v = torch.randn(N, H, T, d, generator=g)
+    mask = rh.causal_additive_mask(T, torch.float32).expand(N, 1, T, T).clone()
+    fmin = float(mask.min())
+    for n, L in enumerate(lengths):
+        mask[n, :, L:, :] = fmin
+    out_d, buf_d = _run_layer(m, q.clone(), kk.clone(), v.clone(), mask, False)       # (the reference masks v in place)
+    sd = {k_: _np(v_) for k_, v_ in m.state_dict().items() if not k_.startswith(_UNUSED)}
+    fx = {'sd.' + k_: v_ for k_, v_ in sd.items()}
+    fx.update(q=_np(q), k=_np(kk), v=_np(v), lengths=np.array(lengths))
+    for b in ('performer_context_layer', 'estimated_attention_probs', 'estimated_scales', 'average_context_layer', 'partial_context_layer'):
+        fx['dense.' + b] = _np(buf_d[b]).astype(np.float32)
+    fx['dense.mask_before_interp_alive'] = np.packbits((_np(buf_d['partial_attention_mask_before_interp']) > -1))
+    fx['dense.context_layer'] = _np(out_d.context_layer).astype(np.float32)
+    fx['meta'] = np.array([N, H, d, T, k, P, nbf, 1])
+    np.savez_compressed(os.path.join(GOLDEN, name + '.npz'), **fx)
+    print(name, 'written; context abs mean', float(out_d.context_layer.abs().mean()))
+
+
 def golden_state_ops():
     """The reference's three stateful decode ops (attention_state.py:43-98 StatefulCausalPerformer, :142-187 StatefulCausalCNN,
     :205-224 StatefulCumAvg) driven exactly as PerlinAttention drives them during a token-by-token decode, on seeded inputs."""
@@ -201,11 +228,14 @@ def main():
     os.makedirs(GOLDEN, exist_ok=True)
     if '--state-only' in sys.argv:
         return golden_state_ops()
+    if '--padded-only' in sys.argv:
+        return golden_layer_padded('layer_causal_padded_h3_t64', H=3, d=32, T=64, k=6, P=16, nbf=4, lengths=[64, 45])
     golden_kat_causal_resize()
     golden_kat_causal_conv()
     golden_layer('layer_causal_h4_t128', H=4, d=64, T=128, k=8, P=32, nbf=8, causal=True)
     golden_layer('layer_causal_h3_t100', H=3, d=32, T=100, k=6, P=16, nbf=4, causal=True)
     golden_state_ops()
+    golden_layer_padded('layer_causal_padded_h3_t64', H=3, d=32, T=64, k=6, P=16, nbf=4, lengths=[64, 45])
     if '--with-bert' in sys.argv:
         golden_layer('layer_bert_h4_t64', H=4, d=64, T=64, k=8, P=32, nbf=1, causal=False, k_flatten_dim='batch')
 

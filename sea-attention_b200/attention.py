@@ -383,19 +383,31 @@ class PerlinAttention(nn.Module):
             q, k, v = q[:, :, :t1], k[:, :, :t1], v[:, :, :t1]
             q_for_atten, k_for_atten = q_for_atten[:, :, :t1], k_for_atten[:, :, :t1]
             q_for_score, k_for_score = q_for_score[:, :, t0:t1], k_for_score[:, :, :t1]
+        row_valid = None
         if self.check_padding and attention_mask is not None:
             # dst_attention_mask = causal_attention_mask[:,:,:,:1] (attention.py:432); the reference reads the
             # whole [N,1,T,T] mask and syncs (:434) -- only the first column matters.
-            if not bool((attention_mask[:, 0, :, 0] > -1).all()):
-                raise SeaError('padded query rows are not implemented yet (SURVEY 8f-3)')
-
+            valid_b = attention_mask[:, 0, :, 0] > -1
+            if not bool(valid_b.all()):
+                # padded query rows (:512-514, :928-931): v and v_for_atten are zeroed there, their top-k is empty.  (The reference
+                # zeroes the caller's v in place; a masked copy is used here.)
+                if block is not None:
+                    raise SeaError('padded rows and query-block sharding are not combined')
+                row_valid = valid_b
+                v = v * valid_b.view(N, 1, T, 1).to(v.dtype)
         w = self._weights_fp32()
         S = self.attention_predictor_dec_row_splits
         W = P // self.attention_predictor_dec_row_down_scale
         k_per_row, z_alloc = self._shape_consts(H, P, t1, t1 - t0, q.device)
 
         # a2+a3 (+ running mean for a13)
-        ctx, cumavg = ops.performer_causal(q_for_atten, k_for_atten, v, w['pos'], w['proj'])
+        if row_valid is None:
+            ctx, cumavg = ops.performer_causal(q_for_atten, k_for_atten, v, w['pos'], w['proj'])
+        else:
+            # v_for_atten = cat(v_eye_learned_causal, v) is zeroed on padded rows as a whole: the position half differs per batch item
+            parts = [ops.performer_causal(q_for_atten[n:n + 1], k_for_atten[n:n + 1], v[n:n + 1],
+                                          w['pos'].reshape(-1, d)[:T] * row_valid[n].view(T, 1).to(w['pos'].dtype), w['proj']) for n in range(N)]
+            ctx, cumavg = torch.cat([p_[0] for p_ in parts], dim=0), torch.cat([p_[1] for p_ in parts], dim=0)
         v_mlp = v
         if block is not None:
             ctx, v_mlp = ctx[:, :, h0:t1].contiguous(), v[:, :, h0:t1]
@@ -439,9 +451,11 @@ class PerlinAttention(nn.Module):
                 y3 = y3[..., :H].contiguous()
             res = ops.predictor_tail_topk(y3, w['conv3_b'], w['out_ln_w'], w['out_ln_b'], kpr, P, count_k=pc.k if self.output_attentions else 0)
             probs, bits, crow_counts = res if len(res) == 3 else (res[0], res[1], None)
+            if row_valid is not None:             # (off the hot path: the grouped top-k again, with the padded rows' keys zeroed)
+                bits, crow_counts = ops.topk_mask_bits(probs, kpr, 'causal_batch', row_valid=row_valid), None
         else:
             probs, _ = ops.predictor_tail(y, w['conv3_w'], w['conv3_b'], w['out_ln_w'], w['out_ln_b'], P)
-            bits = ops.topk_mask_bits(probs, kpr, 'causal_batch')
+            bits = ops.topk_mask_bits(probs, kpr, 'causal_batch', row_valid=row_valid)
             crow_counts = None
         if not self.output_attentions and ops.attention_bits_supported(q.dtype, d, P):
             # a8 + a9-a14 in one kernel: the CSR column list is a pure function of the bit mask, so it is only

@@ -246,3 +246,38 @@ def test_unsupported_modes_fail_loudly(sea):
     padded[:, :, 10:, :] = so.fp_min_for(torch.float32)
     with pytest.raises(sea.SeaError):
         mod(q, q, q, q, q, q, q, q, padded, None, None)
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_causal_layer_with_padded_rows_matches_reference_fixture(sea, dtype):
+    """Padded query rows in the causal model (attention.py:401-449, 512-514, 928-931) against the unmodified reference's own run
+    (tests/golden/layer_causal_padded_h3_t64.npz: 2 items, the second with 45 real rows of 64)."""
+    import transformers
+    from conftest import golden_layer
+    g, m, sd = golden_layer('layer_causal_padded_h3_t64')
+    N, H, d, T, P, k, nbf = (m[x] for x in ('N', 'H', 'd', 'T', 'P', 'k', 'nbf'))
+    cfg = transformers.BertConfig(hidden_size=H * d, num_attention_heads=H, max_position_embeddings=T)
+    mod = sea.PerlinAttention(cfg, sea.PerlinAttentionConfig(performer_nb_factor=nbf, k=k, attention_predictor_length=P, causal=True)).eval()
+    missing, unexpected = mod.load_state_dict(sd, strict=False)
+    assert not unexpected
+    mod = mod.to(DEV)
+    q, kk, v = (torch.from_numpy(g[x]).to(dtype).to(DEV) for x in 'qkv')
+    mask = so.causal_additive_mask(T, dtype, N).clone()
+    fmin = float(mask.min())
+    for n, L in enumerate(g['lengths'].tolist()):
+        mask[n, :, L:, :] = fmin
+    v_before = v.clone()
+    with torch.no_grad():
+        out = mod(q, kk, v, q, kk, v, q, kk, mask.to(DEV), None, None)
+    assert torch.equal(v, v_before)
+    tol = dict(rtol=1e-3, atol=2e-5) if dtype == torch.float32 else dict(rtol=3e-2, atol=3e-3)
+    torch.testing.assert_close(out.estimated_attention_probs.float().cpu(), torch.from_numpy(g['dense.estimated_attention_probs']), **tol)
+    if dtype == torch.float32:
+        # rows whose top-k the oracle reproduces exactly (no tie among the keys) must give the reference's context
+        valid = (torch.arange(T).view(1, T) < torch.from_numpy(g['lengths']).view(N, 1)).float()
+        b = so.perlin_forward_causal(sd, q.cpu(), kk.cpu(), v.cpu(), k_top=k, P=P, sparse=True, dst_valid=valid)
+        torch.testing.assert_close(out.context_layer.cpu(), b['context_layer'], rtol=1e-3, atol=3e-5)
+        ref_ctx = torch.from_numpy(g['dense.context_layer'])
+        close = ((out.context_layer.cpu() - ref_ctx).abs() <= 3e-5 + 1e-3 * ref_ctx.abs()).all(dim=-1)
+        assert close.float().mean() > 0.5            # the rest differ by the tie rule only (see test_oracle_golden.py)
+        assert bool(close[1, 45:].all())             # padded rows: context = (1 - a) * running mean of the zeroed v

@@ -202,3 +202,31 @@ def test_stateful_decode_ops_match_reference_fixture():
     got = torch.cat(outs, dim=-2)
     torch.testing.assert_close(got, torch.from_numpy(fx['cnn_out']), rtol=1e-5, atol=1e-6)
     torch.testing.assert_close(got, torch.from_numpy(fx['cnn_full']), rtol=1e-5, atol=1e-6)
+
+
+def test_padded_causal_layer_matches_reference_fixture():
+    """Padded query rows in the causal model (attention.py:401-449, 512-514, 928-931): the oracle's `dst_valid` branch against the
+    unmodified reference run on a 2-item batch whose second item has 45 real rows of 64 (make_golden.py::golden_layer_padded)."""
+    g, m, sd = golden_layer('layer_causal_padded_h3_t64')
+    q, k, v = (torch.from_numpy(g[x]) for x in 'qkv')
+    N, H, T, P = m['N'], m['H'], m['T'], m['P']
+    valid = (torch.arange(T).view(1, T) < torch.from_numpy(g['lengths']).view(N, 1)).float()
+    b = so.perlin_forward_causal(sd, q, k, v, k_top=m['k'], P=P, sparse=False, dst_valid=valid)
+    for key in ['performer_context_layer', 'estimated_attention_probs', 'estimated_scales', 'average_context_layer']:
+        torch.testing.assert_close(b[key], torch.from_numpy(g['dense.' + key]), rtol=1e-3, atol=2e-5, msg=key)
+    ref_alive = _bits(g, 'dense.mask_before_interp_alive', (N, H, T, P)).astype(bool)
+    mine = b['partial_attention_mask_before_interp'].numpy().astype(bool)
+    # padded rows: nothing alive; real rows: the same alive keys up to exact ties
+    assert not mine[1, :, 45:].any() and not ref_alive[1, :, 45:].any()
+    probs = b['estimated_attention_probs']
+    for n in range(N):
+        pr = probs[n].transpose(0, 1).reshape(T, H * P).numpy()
+        a1 = mine[n].transpose(1, 0, 2).reshape(T, H * P)
+        a2 = ref_alive[n].transpose(1, 0, 2).reshape(T, H * P)
+        for t in range(T):
+            assert np.array_equal(np.sort(pr[t][a1[t]]), np.sort(pr[t][a2[t]])), f'item {n} row {t}: alive key multisets differ'
+    same = torch.from_numpy((mine == ref_alive).all(axis=(1, 3)))                               # rows with identical masks [N,T]
+    ctx = b['context_layer']
+    ref_ctx = torch.from_numpy(g['dense.context_layer'])
+    assert same.float().mean() > 0.5          # (exact ties of the x4-upsampled predictor are frequent at P = 16; the tie rule is the only freedom)
+    torch.testing.assert_close(ctx[same], ref_ctx[same], rtol=1e-3, atol=2e-5)
