@@ -463,7 +463,7 @@ def state_dict_of(module) -> Dict[str, torch.Tensor]:
 def perlin_forward_causal(sd: Dict[str, torch.Tensor], q, k, v, *, k_top: int, P: int,
                           k_oversample: float = 1.0, partial_attention_scaler: bool = True,
                           sparse: bool = True, dst_valid: Optional[torch.Tensor] = None,
-                          keep_dense: bool = False) -> Dict[str, torch.Tensor]:
+                          keep_dense: bool = False, query_skips: int = 1) -> Dict[str, torch.Tensor]:
     """attention.py:333-1359, causal prefill, `context_output_method='mix'`.
     sparse=True follows the `benchmarking` branch (CSR mask + flat_csr ops, :1036-1042, :1151-1173);
     sparse=False follows the dense branch (:960-962, :1066-1133) the reference itself runs on CPU.
@@ -481,11 +481,18 @@ def perlin_forward_causal(sd: Dict[str, torch.Tensor], q, k, v, *, k_top: int, P
     pcl = performer_causal(q, k, v_for_atten, sd['performer.projection_matrix'])
     buf['performer_context_layer'] = pcl
     # a4
-    t_pred = predictor_enc(torch.cat([pcl, v], dim=-1), sd)
-    buf['t_attention_predictor'] = t_pred
+    pv = torch.cat([pcl, v], dim=-1)
+    if query_skips > 1:                                                                          # :617-619
+        assert T % query_skips == 0
+        pv = pv[:, :, ::query_skips, :]
+    t_pred = predictor_enc(pv, sd)
     dec = predictor_dec_row(t_pred, sd, splits=2)
     # a5 + a6
     score = predictor_cnn_causal(dec, sd)
+    if query_skips > 1:                                                                          # :640-644: every result repeated
+        score = score.repeat_interleave(query_skips, dim=2)
+        t_pred = t_pred.repeat_interleave(query_skips, dim=2)
+    buf['t_attention_predictor'] = t_pred
     buf['estimated_attention_score'] = score
     probs = torch.softmax(score, dim=-1)
     buf['estimated_attention_probs'] = probs

@@ -321,8 +321,9 @@ class PerlinAttention(nn.Module):
         dynamic_k = int(os.environ.get('DYNAMIC_K', '0'))     # attention.py:348-351
         if dynamic_k > 0:
             pc.k = dynamic_k
-        if int(os.environ.get('QUERY_SKIPS', '1')) != 1:
-            raise SeaError('QUERY_SKIPS > 1 (attention.py:598) is not implemented')
+        query_skips = int(os.environ.get('QUERY_SKIPS', '1'))      # attention.py:598
+        if query_skips != 1 and (not pc.causal or pc.use_cache or last_state is not None):
+            raise SeaError('QUERY_SKIPS > 1 (attention.py:598) is implemented for the causal prefill only')
         if not q.is_cuda:
             raise SeaError('PerlinAttention (sea-attention_b200) runs on CUDA tensors only; there is no CPU path')
         if (pc.use_cache or last_state is not None) and not pc.causal:
@@ -343,7 +344,8 @@ class PerlinAttention(nn.Module):
 
         if pc.use_cache or last_state is not None:
             return self._forward_causal_stateful(q, k, v, q_for_atten, k_for_atten, v_for_atten, q_for_score, k_for_score, attention_mask, last_state)
-        return self._forward_causal_prefill(q, k, v, q_for_atten, k_for_atten, v_for_atten, q_for_score, k_for_score, attention_mask)
+        return self._forward_causal_prefill(q, k, v, q_for_atten, k_for_atten, v_for_atten, q_for_score, k_for_score, attention_mask,
+                                            query_skips=query_skips)
 
     def forward_query_block(self, q, k, v, t0: int, t1: int):
         """Query-block sharded causal prefill (BASELINE configs[4]): q, k, v [N,H,T,d] hold the whole sequence; returns
@@ -357,7 +359,7 @@ class PerlinAttention(nn.Module):
 
     # ------------------------------------------------------------------------------------------------
     def _forward_causal_prefill(self, q, k, v, q_for_atten, k_for_atten, v_for_atten, q_for_score, k_for_score, attention_mask, capture=None,
-                                block=None):
+                                block=None, query_skips: int = 1):
         """Causal prefill (T_DST == T_SRC).  `capture` (dict) receives the CNN intermediates the decode state is built from.
 
         block = (t0, t1): query-block sharding of a long prefill: q / k / v hold the whole sequence (K and V are
@@ -409,6 +411,12 @@ class PerlinAttention(nn.Module):
                                           w['pos'].reshape(-1, d)[:T] * row_valid[n].view(T, 1).to(w['pos'].dtype), w['proj']) for n in range(N)]
             ctx, cumavg = torch.cat([p_[0] for p_ in parts], dim=0), torch.cat([p_[1] for p_ in parts], dim=0)
         v_mlp = v
+        if query_skips > 1:
+            # QUERY_SKIPS (attention.py:617-619, 640-644): the predictor MLP + CNN see every query_skips-th row only (consecutively, as
+            # a shorter sequence) and every result -- scores and scales -- is repeated query_skips times
+            if block is not None or capture is not None or T % query_skips:
+                raise SeaError('QUERY_SKIPS > 1 needs T % QUERY_SKIPS == 0 and is not combined with query blocks / the decode state')
+            ctx, v_mlp = ctx[:, :, ::query_skips].contiguous(), v[:, :, ::query_skips].contiguous()
         if block is not None:
             ctx, v_mlp = ctx[:, :, h0:t1].contiguous(), v[:, :, h0:t1]
             cumavg = cumavg[:, :, t0:t1]
@@ -436,6 +444,12 @@ class PerlinAttention(nn.Module):
             y = ops.causal_conv3x3_dil2_relu(y1, cw['conv2_w'], cw['conv2_b'], packed=pk, slot='conv2', src=net[2].module.weight)
         if capture is not None:
             capture['cnn_in'], capture['conv1'] = cnn_in, y1
+        if query_skips > 1:
+            if y3 is not None:
+                y3 = y3.repeat_interleave(query_skips, dim=1)
+            else:
+                y = y.repeat_interleave(query_skips, dim=1)
+            scales = scales.repeat_interleave(query_skips, dim=2)
         if t0 > h0:                               # drop the halo rows (their conv outputs saw zero padding instead of real rows)
             if y3 is not None:
                 y3 = y3[:, t0 - h0:].contiguous()

@@ -242,10 +242,8 @@ def test_unsupported_modes_fail_loudly(sea):
     mask = so.causal_additive_mask(16).to(DEV)
     with pytest.raises(sea.SeaError):
         mod(q, q, q, q, q, q, q, q, mask, torch.zeros(1, 2, 16, 16, device=DEV), None)      # teacher tensors -> training branch
-    padded = mask.clone()
-    padded[:, :, 10:, :] = so.fp_min_for(torch.float32)
     with pytest.raises(sea.SeaError):
-        mod(q, q, q, q, q, q, q, q, padded, None, None)
+        mod(q, q, q, q, q, q.clone(), q, q, mask, None, None)                                   # v_for_atten != v (LoRA in the approximation)
 
 
 @pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
@@ -281,3 +279,25 @@ def test_causal_layer_with_padded_rows_matches_reference_fixture(sea, dtype):
         close = ((out.context_layer.cpu() - ref_ctx).abs() <= 3e-5 + 1e-3 * ref_ctx.abs()).all(dim=-1)
         assert close.float().mean() > 0.5            # the rest differ by the tie rule only (see test_oracle_golden.py)
         assert bool(close[1, 45:].all())             # padded rows: context = (1 - a) * running mean of the zeroed v
+
+
+def test_query_skips_matches_reference_fixture(sea, monkeypatch):
+    """QUERY_SKIPS=2 (attention.py:598, 617-619, 640-644) against the unmodified reference's run (tests/golden)."""
+    import transformers
+    from conftest import golden_layer
+    g, m, sd = golden_layer('layer_causal_skips2_h3_t64')
+    N, H, d, T, P, k, nbf = (m[x] for x in ('N', 'H', 'd', 'T', 'P', 'k', 'nbf'))
+    cfg = transformers.BertConfig(hidden_size=H * d, num_attention_heads=H, max_position_embeddings=T)
+    mod = sea.PerlinAttention(cfg, sea.PerlinAttentionConfig(performer_nb_factor=nbf, k=k, attention_predictor_length=P, causal=True)).eval()
+    assert not mod.load_state_dict(sd, strict=False)[1]
+    mod = mod.to(DEV)
+    q, kk, v = (torch.from_numpy(g[x]).to(DEV) for x in 'qkv')
+    monkeypatch.setenv('QUERY_SKIPS', str(int(g['skips'])))
+    with torch.no_grad():
+        out = mod(q, kk, v, q, kk, v, q, kk, so.causal_additive_mask(T, torch.float32, N).to(DEV), None, None)
+    torch.testing.assert_close(out.estimated_attention_probs.cpu(), torch.from_numpy(g['dense.estimated_attention_probs']), rtol=1e-3, atol=2e-5)
+    b = so.perlin_forward_causal(sd, q.cpu(), kk.cpu(), v.cpu(), k_top=k, P=P, sparse=True, query_skips=int(g['skips']))
+    torch.testing.assert_close(out.context_layer.cpu(), b['context_layer'], rtol=1e-3, atol=3e-5)
+    ref_ctx = torch.from_numpy(g['dense.context_layer'])
+    close = ((out.context_layer.cpu() - ref_ctx).abs() <= 3e-5 + 1e-3 * ref_ctx.abs()).all(dim=-1)
+    assert close.float().mean() > 0.5

@@ -230,3 +230,17 @@ def test_padded_causal_layer_matches_reference_fixture():
     ref_ctx = torch.from_numpy(g['dense.context_layer'])
     assert same.float().mean() > 0.5          # (exact ties of the x4-upsampled predictor are frequent at P = 16; the tie rule is the only freedom)
     torch.testing.assert_close(ctx[same], ref_ctx[same], rtol=1e-3, atol=2e-5)
+
+
+def test_query_skips_layer_matches_reference_fixture():
+    """QUERY_SKIPS=2 (attention.py:598, 617-619, 640-644) against the unmodified reference's run."""
+    g, m, sd = golden_layer('layer_causal_skips2_h3_t64')
+    q, k, v = (torch.from_numpy(g[x]) for x in 'qkv')
+    b = so.perlin_forward_causal(sd, q, k, v, k_top=m['k'], P=m['P'], sparse=False, query_skips=int(g['skips']))
+    for key in ['estimated_attention_probs', 'estimated_scales']:
+        torch.testing.assert_close(b[key], torch.from_numpy(g['dense.' + key]), rtol=1e-3, atol=2e-5, msg=key)
+    ref_alive = _bits(g, 'dense.mask_before_interp_alive', (1, m['H'], m['T'], m['P'])).astype(bool)
+    mine = b['partial_attention_mask_before_interp'].numpy().astype(bool)
+    same = torch.from_numpy((mine == ref_alive).all(axis=(1, 3)))
+    assert same.float().mean() > 0.5
+    torch.testing.assert_close(b['context_layer'][same], torch.from_numpy(g['dense.context_layer'])[same], rtol=1e-3, atol=2e-5)
