@@ -335,8 +335,8 @@ class PerlinAttention(nn.Module):
             raise SeaError('only the mlp predictor with the performer backend is implemented')
         if pc.context_output_method != 'mix' or pc.random_lookup or pc.out_add_performer_context:
             raise SeaError("only context_output_method='mix' without random lookup is implemented")
-        if float(pc.k_oversample) != 1.0:
-            raise SeaError('k_oversample != 1.0 is not implemented')
+        # (k_oversample: the sparse path only scales per_item_top_k with it, attention.py:837-853; the CSR interpolation ignores its
+        # `oversampled` argument, causal_resize_m_to_t.py:638 -- both are followed here)
         if not pc.causal:
             return self._forward_noncausal(q, k, v, q_for_atten, k_for_atten, v_for_atten, q_for_score, k_for_score, attention_mask)
         if pc.k_flatten_dim != 'causal_batch' or not pc.k_flatten:
@@ -372,8 +372,11 @@ class PerlinAttention(nn.Module):
         N, H, T, d = q.shape
         assert attention_mask is None or attention_mask.shape == (N, 1, T, T), f'causal additive mask must be [N,1,T,T], got {tuple(attention_mask.shape)}'
         assert k.shape == (N, H, T, d) and v.shape == (N, H, T, d)
-        if v_for_atten.data_ptr() != v.data_ptr() or v_for_atten.shape != v.shape:
-            raise SeaError('v_for_atten must alias v (LoRA-in-approximation, self_attention.py:104-120, is not implemented)')
+        if v_for_atten.shape != v.shape:
+            raise SeaError('v_for_atten must have the shape of v')
+        # LoRA in the approximation (self_attention.py:104-120): the Performer sums take v_for_atten, everything else (performer_value,
+        # running mean, sparse attention) takes v
+        lora_v = None if v_for_atten.data_ptr() == v.data_ptr() else v_for_atten
         P = pc.attention_predictor_length
         t0, t1 = (0, T) if block is None else (int(block[0]), int(block[1]))
         if not (0 <= t0 < t1 <= T):
@@ -384,6 +387,7 @@ class PerlinAttention(nn.Module):
                 raise SeaError('a query block returns context and probabilities only (no decode state, no CSR tensors)')
             q, k, v = q[:, :, :t1], k[:, :, :t1], v[:, :, :t1]
             q_for_atten, k_for_atten = q_for_atten[:, :, :t1], k_for_atten[:, :, :t1]
+            lora_v = None if lora_v is None else lora_v[:, :, :t1]
             q_for_score, k_for_score = q_for_score[:, :, t0:t1], k_for_score[:, :, :t1]
         row_valid = None
         if self.check_padding and attention_mask is not None:
@@ -403,7 +407,12 @@ class PerlinAttention(nn.Module):
         k_per_row, z_alloc = self._shape_consts(H, P, t1, t1 - t0, q.device)
 
         # a2+a3 (+ running mean for a13)
-        if row_valid is None:
+        if lora_v is not None:
+            if row_valid is not None:
+                raise SeaError('padded rows together with a separate v_for_atten are not implemented')
+            ctx, _ = ops.performer_causal(q_for_atten, k_for_atten, lora_v, w['pos'], w['proj'])
+            _, cumavg = ops.performer_causal(q_for_atten, k_for_atten, v, w['pos'], w['proj'])          # (running mean of v; off the hot path)
+        elif row_valid is None:
             ctx, cumavg = ops.performer_causal(q_for_atten, k_for_atten, v, w['pos'], w['proj'])
         else:
             # v_for_atten = cat(v_eye_learned_causal, v) is zeroed on padded rows as a whole: the position half differs per batch item

@@ -243,7 +243,7 @@ def test_unsupported_modes_fail_loudly(sea):
     with pytest.raises(sea.SeaError):
         mod(q, q, q, q, q, q, q, q, mask, torch.zeros(1, 2, 16, 16, device=DEV), None)      # teacher tensors -> training branch
     with pytest.raises(sea.SeaError):
-        mod(q, q, q, q, q, q.clone(), q, q, mask, None, None)                                   # v_for_atten != v (LoRA in the approximation)
+        mod(q, q, q, q, q, q[:, :, :8], q, q, mask, None, None)                                 # v_for_atten of another shape
 
 
 @pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
@@ -301,3 +301,63 @@ def test_query_skips_matches_reference_fixture(sea, monkeypatch):
     ref_ctx = torch.from_numpy(g['dense.context_layer'])
     close = ((out.context_layer.cpu() - ref_ctx).abs() <= 3e-5 + 1e-3 * ref_ctx.abs()).all(dim=-1)
     assert close.float().mean() > 0.5
+
+
+def test_k_oversample_follows_oracle(sea):
+    """k_oversample != 1 (config.py:24; attention.py:849): per_item_top_k is scaled, nothing else changes on the sparse path."""
+    N, H, d, T, P, k, nbf = 1, 4, 64, 192, 32, 8, 8
+    torch.manual_seed(2)
+    cfg = transformers.BertConfig(hidden_size=H * d, num_attention_heads=H, max_position_embeddings=T)
+    pc = sea.PerlinAttentionConfig(performer_nb_factor=nbf, k=k, attention_predictor_length=P, causal=True, k_oversample=1.5)
+    mod = sea.PerlinAttention(cfg, pc).eval()
+    sd = {k_: v_.detach().clone().float() for k_, v_ in mod.state_dict().items()}
+    mod = mod.to(DEV)
+    mod.benchmarking = True
+    mod.output_attentions = True
+    g = torch.Generator().manual_seed(3)
+    q = torch.randn(N, H, T, d, generator=g) * d ** -0.5
+    kk = torch.randn(N, H, T, d, generator=g)
+    v = torch.randn(N, H, T, d, generator=g)
+    qd, kd, vd = q.to(DEV), kk.to(DEV), v.to(DEV)
+    with torch.no_grad():
+        out = mod(qd, kd, vd, qd, kd, vd, qd, kd, so.causal_additive_mask(T, torch.float32, N).to(DEV), None, None)
+    b = so.perlin_forward_causal(sd, q, kk, v, k_top=k, P=P, k_oversample=1.5, sparse=True)
+    b1 = so.perlin_forward_causal(sd, q, kk, v, k_top=k, P=P, k_oversample=1.0, sparse=True)
+    assert int(b['crow_indices'][0, -1]) > int(b1['crow_indices'][0, -1])
+    mask_m = so.topk_mask_causal_batch(out.estimated_attention_probs.cpu(), k, 1.5)
+    crow_r, col_r, _ = so.resize_from_m_to_t_csr(mask_m, k, T, True)
+    assert torch.equal(out.partial_attention_mask.crow_indices().cpu(), crow_r)
+    assert torch.equal(out.partial_attention_mask.col_indices().cpu(), col_r)
+    same = (out.partial_attention_mask.crow_indices().cpu() == b['crow_indices'])
+    torch.testing.assert_close(out.estimated_attention_probs.cpu(), b['estimated_attention_probs'], rtol=2e-3, atol=1e-6)
+
+
+def test_separate_v_for_atten_follows_oracle(sea):
+    """LoRA in the approximation (self_attention.py:104-120): q_for_atten / k_for_atten / v_for_atten differ from q / k / v.  The
+    Performer estimate uses the *_for_atten tensors, performer_value, the running mean and the sparse attention use v, the scores
+    use q_for_score / k_for_score (attention.py:527-534, 577-590, 1159-1173, 1237-1241)."""
+    N, H, d, T, P, k, nbf = 1, 4, 64, 160, 32, 8, 8
+    mod, sd = _random_sd(sea, H, d, T, P, k, nbf, seed=4)
+    mod = mod.to(DEV)
+    mod.benchmarking = True
+    g = torch.Generator().manual_seed(8)
+    q, kk, v = torch.randn(N, H, T, d, generator=g) * d ** -0.5, torch.randn(N, H, T, d, generator=g), torch.randn(N, H, T, d, generator=g)
+    qa, ka, va = q + 0.1 * torch.randn(N, H, T, d, generator=g), kk + 0.1 * torch.randn(N, H, T, d, generator=g), v + 0.1 * torch.randn(N, H, T, d, generator=g)
+    with torch.no_grad():
+        out = mod(q.to(DEV), kk.to(DEV), v.to(DEV), qa.to(DEV), ka.to(DEV), va.to(DEV), q.to(DEV), kk.to(DEV),
+                  so.causal_additive_mask(T, torch.float32, N).to(DEV), None, None)
+    # oracle, stage by stage with the same substitutions
+    pos = sd['v_eye_learned_causal'][:, :, :T, :].expand(N, H, T, d)
+    pcl = so.performer_causal(qa, ka, torch.cat([pos, va], -1), sd['performer.projection_matrix'])
+    t_pred = so.predictor_enc(torch.cat([pcl, v], -1), sd)
+    probs = torch.softmax(so.predictor_cnn_causal(so.predictor_dec_row(t_pred, sd, 2), sd), -1)
+    torch.testing.assert_close(out.estimated_attention_probs.cpu(), probs, rtol=2e-3, atol=1e-6)
+    mask_m = so.topk_mask_causal_batch(out.estimated_attention_probs.cpu(), k, 1.0)
+    crow, col, _ = so.resize_from_m_to_t_csr(mask_m, k, T, True)
+    scales = so.predictor_dec_scaler(t_pred, sd)
+    p = so.flat_csr_softmax(so.flat_csr_masked_bmm(q, kk, crow, col), crow, col, H, T)
+    p = so.flat_csr_elmul_rowscale(p, crow, col, torch.sigmoid(scales[..., 0]), T)
+    ctx = so.flat_csr_sdbmm(p, crow, col, v, H)
+    a = torch.sigmoid(scales[..., 1:2])
+    want = (ctx * a + (1 - a) * (v.cumsum(-2) / torch.arange(1, T + 1).view(1, 1, T, 1))).permute(0, 2, 1, 3).reshape(N, T, H * d)
+    torch.testing.assert_close(out.context_layer.cpu(), want, rtol=1e-3, atol=3e-5)
