@@ -200,6 +200,33 @@ def golden_layer_query_skips(name, H, d, T, k, P, nbf, skips, seed_inputs=777):
     print(name, 'written')
 
 
+def golden_layer_deeper(name, H, d, T, k, P, nbf, seed_inputs=99):
+    """PERLIN_HOTFIX_OPT_DEEPER=1 (attention.py:246-263): the predictor CNN with a third dilated causal conv.  The switch is read
+    by the reference's constructor.  Dense path, causal, no padding."""
+    os.environ['PERLIN_HOTFIX_OPT_DEEPER'] = '1'
+    try:
+        m = rh.build_reference_attention(H, d, T, k, P, nbf, True)
+    finally:
+        del os.environ['PERLIN_HOTFIX_OPT_DEEPER']
+    g = torch.Generator().manual_seed(seed_inputs)
+    q = torch.randn(1, H, T, d, generator=g) * d ** -0.5
+    kk = torch.randn(1, H, T, d, generator=g)
+    v = torch.randn(1, H, T, d, generator=g)
+    mask = rh.causal_additive_mask(T, torch.float32)
+    out_d, buf_d = _run_layer(m, q, kk, v, mask, False)
+    sd = {k_: _np(v_) for k_, v_ in m.state_dict().items() if not k_.startswith(_UNUSED)}
+    assert 'attention_predictor_cnn.1.module.net.7.module.weight' in sd
+    fx = {'sd.' + k_: v_ for k_, v_ in sd.items()}
+    fx.update(q=_np(q), k=_np(kk), v=_np(v))
+    for b in ('estimated_attention_score', 'estimated_attention_probs', 'estimated_scales'):
+        fx['dense.' + b] = _np(buf_d[b]).astype(np.float32)
+    fx['dense.mask_before_interp_alive'] = np.packbits((_np(buf_d['partial_attention_mask_before_interp']) > -1))
+    fx['dense.context_layer'] = _np(out_d.context_layer).astype(np.float32)
+    fx['meta'] = np.array([1, H, d, T, k, P, nbf, 1])
+    np.savez_compressed(os.path.join(GOLDEN, name + '.npz'), **fx)
+    print(name, 'written')
+
+
 def golden_state_ops():
     """The reference's three stateful decode ops (attention_state.py:43-98 StatefulCausalPerformer, :142-187 StatefulCausalCNN,
     :205-224 StatefulCumAvg) driven exactly as PerlinAttention drives them during a token-by-token decode, on seeded inputs."""
@@ -256,6 +283,8 @@ def main():
         return golden_state_ops()
     if '--skips-only' in sys.argv:
         return golden_layer_query_skips('layer_causal_skips2_h3_t64', H=3, d=32, T=64, k=6, P=16, nbf=4, skips=2)
+    if '--deeper-only' in sys.argv:
+        return golden_layer_deeper('layer_causal_deeper_h3_t64', H=3, d=32, T=64, k=6, P=16, nbf=4)
     if '--padded-only' in sys.argv:
         return golden_layer_padded('layer_causal_padded_h3_t64', H=3, d=32, T=64, k=6, P=16, nbf=4, lengths=[64, 45])
     golden_kat_causal_resize()
@@ -265,6 +294,7 @@ def main():
     golden_state_ops()
     golden_layer_padded('layer_causal_padded_h3_t64', H=3, d=32, T=64, k=6, P=16, nbf=4, lengths=[64, 45])
     golden_layer_query_skips('layer_causal_skips2_h3_t64', H=3, d=32, T=64, k=6, P=16, nbf=4, skips=2)
+    golden_layer_deeper('layer_causal_deeper_h3_t64', H=3, d=32, T=64, k=6, P=16, nbf=4)
     if '--with-bert' in sys.argv:
         golden_layer('layer_bert_h4_t64', H=4, d=64, T=64, k=8, P=32, nbf=1, causal=False, k_flatten_dim='batch')
 

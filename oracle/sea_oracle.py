@@ -175,11 +175,13 @@ def predictor_cnn_causal(x, sd):
     -> CausalConv2d(2H,H,1,pad 1) (width P+2) -> area resize to P (KeepRes, modules.py:42-55) -> LN(P)."""
     p = 'attention_predictor_cnn.'
     y = layer_norm(x, sd[p + '0.module.weight'], sd[p + '0.module.bias'])
-    for idx in ('0', '2'):
+    # PERLIN_HOTFIX_OPT_DEEPER=1 (attention.py:246-263): a third dilated conv + ReLU; the 1x1 conv then sits at index 7 instead of 5
+    deeper = (p + '1.module.net.7.module.weight') in sd
+    for idx in (('0', '2', '4') if deeper else ('0', '2')):
         q = p + f'1.module.net.{idx}.module.'
         y = torch.relu(causal_conv2d(y, sd[q + 'weight'], sd[q + 'weight_mask'], sd[q + 'bias'], 3, 2, 2))
     y = y.repeat_interleave(4, dim=-1)                       # UpsampleFP32((1,4)) nearest, modules.py:77-92
-    q = p + '1.module.net.5.module.'
+    q = p + ('1.module.net.7.module.' if deeper else '1.module.net.5.module.')
     y = causal_conv2d(y, sd[q + 'weight'], sd[q + 'weight_mask'], sd[q + 'bias'], 1, 1, 1)
     y = area_resize_width(y, sd[p + '2.module.weight'].shape[0])
     return layer_norm(y, sd[p + '2.module.weight'], sd[p + '2.module.bias'])

@@ -199,18 +199,20 @@ class PerlinAttention(nn.Module):
                 nn.Conv2d(4 * H, H, 3, padding=1))))
         else:
             inner_ch = int(os.environ.get('PERLIN_HOTFIX_OPT_INNER_CH', '2'))
-            if int(os.environ.get('PERLIN_HOTFIX_OPT_DEEPER', '0')) == 1:
-                raise SeaError('PERLIN_HOTFIX_OPT_DEEPER predictor variant is not implemented')
+            # PERLIN_HOTFIX_OPT_DEEPER=1 (attention.py:246-263): a third dilated causal conv + ReLU in the predictor CNN
+            self._deeper = int(os.environ.get('PERLIN_HOTFIX_OPT_DEEPER', '0')) == 1
             self.attention_predictor_dec_row_down_scale = 4
             self.attention_predictor_dec_row_splits = inner_ch
             self.attention_predictor_dec_row_out_ch = (P // 4) * inner_ch
             self.attention_predictor_dec_row = nn.Sequential(nn.Linear(2 * d, self.attention_predictor_dec_row_out_ch), nn.Identity())
             C = inner_ch * H
+            convs = []
+            for _ in range(3 if self._deeper else 2):
+                convs += [_Holder('module', _CausalConvParams(C, C, 3)), nn.ReLU()]
             self.attention_predictor_cnn = nn.Sequential(
                 _Holder('module', nn.LayerNorm(P // 4)),
                 _Holder('module', _Holder('net', nn.Sequential(
-                    _Holder('module', _CausalConvParams(C, C, 3)), nn.ReLU(),
-                    _Holder('module', _CausalConvParams(C, C, 3)), nn.ReLU(),
+                    *convs,
                     _Holder('module', nn.Identity()),
                     _Holder('module', _CausalConvParams(C, H, 1))))),
                 _Holder('module', nn.LayerNorm(P)))
@@ -228,6 +230,13 @@ class PerlinAttention(nn.Module):
         self._padded_cache = None
 
     # ------------------------------------------------------------------------------------------------
+    def _cnn_convs(self):
+        """(the dilated 3x3 CausalConv2d parameter holders in order, the 1x1 one) of the causal predictor CNN: net indices
+        0, 2 (, 4 with PERLIN_HOTFIX_OPT_DEEPER) and 5 (7)."""
+        net = self.attention_predictor_cnn[1].module.net
+        n3 = 3 if getattr(self, '_deeper', False) else 2
+        return [net[2 * i].module for i in range(n3)], net[2 * n3 + 1].module
+
     def _weights_fp32(self):
         f = lambda t: t.detach().float().contiguous()
         enc, dec, scl, cnn = self.attention_predictor_enc, self.attention_predictor_dec_row, self.attention_predictor_dec_scaler, self.attention_predictor_cnn
@@ -237,15 +246,16 @@ class PerlinAttention(nn.Module):
             'proj': f(self.performer.projection_matrix),
         }
         if self.pconfig.causal:
-            net = cnn[1].module.net
+            c3x3, c1x1 = self._cnn_convs()
             w.update({
                 'cnn_ln_w': f(cnn[0].module.weight), 'cnn_ln_b': f(cnn[0].module.bias),
-                'conv1_w': f(net[0].module.weight), 'conv1_b': f(net[0].module.bias),
-                'conv2_w': f(net[2].module.weight), 'conv2_b': f(net[2].module.bias),
-                'conv3_w': f(net[5].module.weight).reshape(net[5].module.weight.shape[0], -1), 'conv3_b': f(net[5].module.bias),
+                'conv3_w': f(c1x1.weight).reshape(c1x1.weight.shape[0], -1), 'conv3_b': f(c1x1.bias),
                 'out_ln_w': f(cnn[2].module.weight), 'out_ln_b': f(cnn[2].module.bias),
                 'pos': f(self.v_eye_learned_causal).reshape(-1, self.attention_head_size),
             })
+            for i, c in enumerate(c3x3):        # 'conv1', 'conv2' (, 'conv2b': the DEEPER variant's third dilated conv)
+                name = ('conv1', 'conv2', 'conv2b')[i]
+                w[name + '_w'], w[name + '_b'] = f(c.weight), f(c.bias)
         else:
             net = cnn[0].net
             w.update({'conv1_w': f(net[0].weight), 'conv1_b': f(net[0].bias), 'conv2_w': f(net[2].weight), 'conv2_b': f(net[2].bias),
@@ -284,15 +294,15 @@ class PerlinAttention(nn.Module):
     def _padded_conv_weights(self, w, C, H):
         """Zero-padded copies of the CNN weights for the 64-channel tcgen05 kernels (conv 3x3: [C,C,5,3] -> [64,64,5,3]; 1x1:
         [H,C] -> [32,64]); cached until a source parameter changes."""
-        net = self.attention_predictor_cnn[1].module.net
-        src = (net[0].module.weight, net[0].module.bias, net[2].module.weight, net[2].module.bias, net[5].module.weight, net[5].module.bias)
+        c3x3, c1x1 = self._cnn_convs()
+        src = tuple(t for c in c3x3 + [c1x1] for t in (c.weight, c.bias))
         stamp = tuple((int(t.data_ptr()), int(t._version)) for t in src)
         hit = self._padded_cache
         if hit is not None and hit[0] == stamp and self._packed.frozen:
             return hit[1]
         dev = w['conv1_w'].device
         out = {}
-        for name in ('conv1', 'conv2'):
+        for name in ('conv1', 'conv2', 'conv2b')[:len(c3x3)]:
             wt = torch.zeros((64, 64, 5, 3), dtype=torch.float32, device=dev)
             wt[:C, :C] = w[name + '_w']
             b = torch.zeros((64,), dtype=torch.float32, device=dev)
@@ -328,6 +338,8 @@ class PerlinAttention(nn.Module):
             raise SeaError('PerlinAttention (sea-attention_b200) runs on CUDA tensors only; there is no CPU path')
         if (pc.use_cache or last_state is not None) and not pc.causal:
             raise SeaError('use_cache / PerlinAttentionState is only defined for the causal model (attention_state.py)')
+        if (pc.use_cache or last_state is not None) and getattr(self, '_deeper', False):
+            raise SeaError('use_cache with the PERLIN_HOTFIX_OPT_DEEPER predictor is not implemented (the decode state keeps two CNN windows)')
         if self.training or attention_scores_truth is not None or context_layer_truth is not None:
             raise SeaError('the training branch (dense path + KD losses, attention.py:707-765, 1066-1133) is not implemented yet '
                            '(SURVEY 8f-1); call under eval() without teacher tensors')
@@ -365,8 +377,8 @@ class PerlinAttention(nn.Module):
         block = (t0, t1): query-block sharding of a long prefill: q / k / v hold the whole sequence (K and V are
         replicated on every rank), and only the query rows [t0, t1) are produced -- context [N, t1-t0, H*d], probabilities
         [N,H,t1-t0,P].  No exchange with the other blocks is needed: the Performer prefix sums are recomputed locally over [0, t1)
-        (linear, the cheapest stage), the predictor MLP and the two dilated causal convolutions run on rows [t0-8, t1) -- each conv
-        looks 4 rows back, so 8 halo rows make every kept row exact --, top-k is per row (K_t uses the absolute t), and the
+        (linear, the cheapest stage), the predictor MLP and the dilated causal convolutions run on rows [t0-8, t1) -- each conv
+        looks 4 rows back, so 8 halo rows (12 with the DEEPER predictor) make every kept row exact --, top-k is per row (K_t uses the absolute t), and the
         sparse attention takes T_DST = t1-t0 query rows against T_SRC = t1 source tokens."""
         pc = self.pconfig
         N, H, T, d = q.shape
@@ -381,7 +393,8 @@ class PerlinAttention(nn.Module):
         t0, t1 = (0, T) if block is None else (int(block[0]), int(block[1]))
         if not (0 <= t0 < t1 <= T):
             raise SeaError(f'bad query block [{t0}, {t1}) of {T} rows')
-        h0 = max(t0 - 8, 0)                       # first halo row
+        c3x3, c1x1 = self._cnn_convs()
+        h0 = max(t0 - 4 * len(c3x3), 0)           # first halo row: every dilated conv looks 4 rows back
         if block is not None:
             if capture is not None or self.output_attentions:
                 raise SeaError('a query block returns context and probabilities only (no decode state, no CSR tensors)')
@@ -433,7 +446,6 @@ class PerlinAttention(nn.Module):
         # (weight packings of the tensor-core kernels are cached per module and re-made only when a parameter changes)
         pk = self._packed
         enc, dec, scl = self.attention_predictor_enc, self.attention_predictor_dec_row, self.attention_predictor_dec_scaler
-        net = self.attention_predictor_cnn[1].module.net
         w['_src_mlp'] = (enc[0].weight, dec[0].weight, scl[0].weight)
         # models whose 2H != 64 (e.g. OPT-125m, H = 12): run the 64-channel tcgen05 MLP / conv kernels on zero-padded channels
         pad_c = (q.dtype == torch.bfloat16 and d == 64 and S * H < 64 and H <= 32 and P % 32 == 0 and W in (16, 32, 64)
@@ -445,14 +457,18 @@ class PerlinAttention(nn.Module):
         fuse_c3 = tc_tail and ops.conv3x3_conv1x1_supported(q.dtype, W, 64, cw['conv2_w'].shape[0], cw['conv3_w'].shape[0])
         y = y3 = None
         cnn_in, scales, _ = ops.predictor_mlp(ctx, v_mlp, w, S, W, packed=pk, **({'c_out': 64} if pad_c else {}))
-        y1 = ops.causal_conv3x3_dil2_relu(cnn_in, cw['conv1_w'], cw['conv1_b'], packed=pk, slot='conv1', src=net[0].module.weight)
+        # the dilated convs 'conv1', 'conv2' (, 'conv2b' with PERLIN_HOTFIX_OPT_DEEPER); the last one may carry the 1x1 conv
+        names = ('conv1', 'conv2', 'conv2b')[:len(c3x3)]
+        y1 = cnn_in
+        for name, cm in zip(names[:-1], c3x3[:-1]):
+            y1 = ops.causal_conv3x3_dil2_relu(y1, cw[name + '_w'], cw[name + '_b'], packed=pk, slot=name, src=cm.weight)
+            if capture is not None and name == 'conv1':
+                capture['cnn_in'], capture['conv1'] = cnn_in, y1
         if fuse_c3:
-            y3 = ops.causal_conv3x3_relu_conv1x1(y1, cw['conv2_w'], cw['conv2_b'], cw['conv3_w'], cw['conv3_b'], packed=pk, slot='conv2',
-                                                 src=net[2].module.weight, slot3='conv3', src3=net[5].module.weight)
+            y3 = ops.causal_conv3x3_relu_conv1x1(y1, cw[names[-1] + '_w'], cw[names[-1] + '_b'], cw['conv3_w'], cw['conv3_b'], packed=pk, slot=names[-1],
+                                                 src=c3x3[-1].weight, slot3='conv3', src3=c1x1.weight)
         else:
-            y = ops.causal_conv3x3_dil2_relu(y1, cw['conv2_w'], cw['conv2_b'], packed=pk, slot='conv2', src=net[2].module.weight)
-        if capture is not None:
-            capture['cnn_in'], capture['conv1'] = cnn_in, y1
+            y = ops.causal_conv3x3_dil2_relu(y1, cw[names[-1] + '_w'], cw[names[-1] + '_b'], packed=pk, slot=names[-1], src=c3x3[-1].weight)
         if query_skips > 1:
             if y3 is not None:
                 y3 = y3.repeat_interleave(query_skips, dim=1)
@@ -469,7 +485,7 @@ class PerlinAttention(nn.Module):
         kpr = k_per_row.repeat(N) if N > 1 else k_per_row
         if tc_tail:
             if y3 is None:
-                y3 = ops.conv1x1_umma(y, cw['conv3_w'], cw['conv3_b'], packed=pk, slot='conv3', src=net[5].module.weight)
+                y3 = ops.conv1x1_umma(y, cw['conv3_w'], cw['conv3_b'], packed=pk, slot='conv3', src=c1x1.weight)
             if pad_c:
                 y3 = y3[..., :H].contiguous()
             res = ops.predictor_tail_topk(y3, w['conv3_b'], w['out_ln_w'], w['out_ln_b'], kpr, P, count_k=pc.k if self.output_attentions else 0)
@@ -648,7 +664,7 @@ class PerlinAttention(nn.Module):
             context, pvals = ops.sparse_attention(crow, col, q_for_score, k_for_score, v, scales, avg,
                                                   use_scaler=pc.partial_attention_scaler, want_probs=self.output_attentions, head_ptr=head_ptr)
             if self.output_attentions:
-                partial_mask, partial_probs = _csr_outputs(crow, col, pvals, (N, t1 - t0, H * t1))
+                partial_mask, partial_probs = _csr_outputs(crow, col, pvals, (N, T, H * T))
         return PerlinAttentionOutput(
             loss=0, context_layer=context, partial_attention_probs=partial_probs, partial_attention_mask=partial_mask,
             estimated_attention_probs_m=probs, estimated_attention_probs=probs, dense_attention_probs=None,

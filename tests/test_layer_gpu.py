@@ -361,3 +361,37 @@ def test_separate_v_for_atten_follows_oracle(sea):
     a = torch.sigmoid(scales[..., 1:2])
     want = (ctx * a + (1 - a) * (v.cumsum(-2) / torch.arange(1, T + 1).view(1, 1, T, 1))).permute(0, 2, 1, 3).reshape(N, T, H * d)
     torch.testing.assert_close(out.context_layer.cpu(), want, rtol=1e-3, atol=3e-5)
+
+
+def test_deeper_predictor_matches_reference_fixture(sea, monkeypatch):
+    """PERLIN_HOTFIX_OPT_DEEPER=1 (attention.py:246-263: a third dilated causal conv in the predictor CNN; the switch is read by
+    the constructor) against the unmodified reference's run (tests/golden), plus query-block sharding with its 12-row halo."""
+    import transformers
+    from conftest import golden_layer
+    g, m, sd = golden_layer('layer_causal_deeper_h3_t64')
+    N, H, d, T, P, k, nbf = (m[x] for x in ('N', 'H', 'd', 'T', 'P', 'k', 'nbf'))
+    cfg = transformers.BertConfig(hidden_size=H * d, num_attention_heads=H, max_position_embeddings=T)
+    monkeypatch.setenv('PERLIN_HOTFIX_OPT_DEEPER', '1')
+    mod = sea.PerlinAttention(cfg, sea.PerlinAttentionConfig(performer_nb_factor=nbf, k=k, attention_predictor_length=P, causal=True)).eval()
+    monkeypatch.delenv('PERLIN_HOTFIX_OPT_DEEPER')
+    missing, unexpected = mod.load_state_dict(sd, strict=False)
+    assert not unexpected and not [x for x in missing if 'attention_predictor_cnn' in x]
+    mod = mod.to(DEV)
+    q, kk, v = (torch.from_numpy(g[x]).to(DEV) for x in 'qkv')
+    with torch.no_grad():
+        out = mod(q, kk, v, q, kk, v, q, kk, so.causal_additive_mask(T, torch.float32, N).to(DEV), None, None)
+        blocks = [mod.forward_query_block(q, kk, v, a, b) for a, b in ((0, 20), (20, 33), (33, T))]
+    torch.testing.assert_close(out.estimated_attention_probs.cpu(), torch.from_numpy(g['dense.estimated_attention_probs']), rtol=1e-3, atol=2e-5)
+    b = so.perlin_forward_causal(sd, q.cpu(), kk.cpu(), v.cpu(), k_top=k, P=P, sparse=True)
+    torch.testing.assert_close(out.context_layer.cpu(), b['context_layer'], rtol=1e-3, atol=3e-5)
+    ref_ctx = torch.from_numpy(g['dense.context_layer'])
+    close = ((out.context_layer.cpu() - ref_ctx).abs() <= 3e-5 + 1e-3 * ref_ctx.abs()).all(dim=-1)
+    assert close.float().mean() > 0.5
+    torch.testing.assert_close(torch.cat([x.estimated_attention_probs for x in blocks], dim=2), out.estimated_attention_probs, rtol=1e-4, atol=1e-6)
+    torch.testing.assert_close(torch.cat([x.context_layer for x in blocks], dim=1), out.context_layer, rtol=1e-4, atol=1e-5)
+    with pytest.raises(sea.SeaError):
+        mod.pconfig.use_cache = True
+        try:
+            mod(q, kk, v, q, kk, v, q, kk, so.causal_additive_mask(T, torch.float32, N).to(DEV), None, None)
+        finally:
+            mod.pconfig.use_cache = False

@@ -244,3 +244,18 @@ def test_query_skips_layer_matches_reference_fixture():
     same = torch.from_numpy((mine == ref_alive).all(axis=(1, 3)))
     assert same.float().mean() > 0.5
     torch.testing.assert_close(b['context_layer'][same], torch.from_numpy(g['dense.context_layer'])[same], rtol=1e-3, atol=2e-5)
+
+
+def test_deeper_cnn_layer_matches_reference_fixture():
+    """PERLIN_HOTFIX_OPT_DEEPER=1 (attention.py:246-263: a third dilated causal conv) against the unmodified reference's run."""
+    g, m, sd = golden_layer('layer_causal_deeper_h3_t64')
+    assert 'attention_predictor_cnn.1.module.net.7.module.weight' in sd
+    q, k, v = (torch.from_numpy(g[x]) for x in 'qkv')
+    b = so.perlin_forward_causal(sd, q, k, v, k_top=m['k'], P=m['P'], sparse=False)
+    for key in ['estimated_attention_score', 'estimated_attention_probs', 'estimated_scales']:
+        torch.testing.assert_close(b[key], torch.from_numpy(g['dense.' + key]), rtol=1e-3, atol=2e-5, msg=key)
+    ref_alive = _bits(g, 'dense.mask_before_interp_alive', (1, m['H'], m['T'], m['P'])).astype(bool)
+    mine = b['partial_attention_mask_before_interp'].numpy().astype(bool)
+    same = torch.from_numpy((mine == ref_alive).all(axis=(1, 3)))
+    assert same.float().mean() > 0.5
+    torch.testing.assert_close(b['context_layer'][same], torch.from_numpy(g['dense.context_layer'])[same], rtol=1e-3, atol=2e-5)
