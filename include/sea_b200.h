@@ -192,6 +192,20 @@ SEA_API int sea_predictor_mlp_umma_fwd_ex(const void* ctx, const void* v, int64_
                                        const float* scl_w, const float* scl_b, void* cnn_in, float* scales, void* workspace,
                                        int N, int H, int T, int D, int S, int W, int Cout, void* stream);
 
+/* a4 on the tensor cores for any head dim (bf16; csrc/mlp_mma.cu): the same computation as warp-level mma.sync GEMMs chained
+ * through registers, the weights streamed through shared memory in K chunks -- for the head dims whose weights do not fit the
+ * tcgen05 kernel's shared memory (OPT-2.7B D = 80, the long-context sweep D = 128; reference: attention.py:190-196, 242-245, 267,
+ * 289-291, 599-625 take any attention_head_size).  Shapes: D in {32,64,80,96,128}, S = 2, H <= 128, W in {32,64}; ctx contiguous
+ * [N,H,T,2D] bf16; cnn_in bf16 [N,T,W,Cout], Cout >= 2H (channels 2H.. are written as zeros).
+ * workspace: >= sea_predictor_mlp_mma_workspace_bytes(D,S,W) bytes, 16-byte aligned; weights NULL = reuse the packing in it. */
+SEA_API int sea_predictor_mlp_mma_supported(int dtype, int H, int D, int S, int W);
+SEA_API int64_t sea_predictor_mlp_mma_workspace_bytes(int D, int S, int W);
+SEA_API int sea_predictor_mlp_mma_fwd(const void* ctx, const void* v, int64_t v_sn, int64_t v_sh, int64_t v_st,
+                                      const float* enc_w, const float* enc_b, const float* enc_ln_w, const float* enc_ln_b,
+                                      const float* dec_w, const float* dec_b, const float* cnn_ln_w, const float* cnn_ln_b,
+                                      const float* scl_w, const float* scl_b, void* cnn_in, float* scales, void* workspace,
+                                      int N, int H, int T, int D, int S, int W, int Cout, void* stream);
+
 /* a5  one CausalConv2d(C,C,3,padding=2,dilation=2,causal) + ReLU (modules.py:96-192;
  *     attention.py:271-274) on channels-last activations [N,T,W,C]:
  *   y[t,w,o] = relu(b[o] + sum_{i,j<3} sum_c Wt[o,c,i,j] x[t-4+2i, w-2+2j, c])   (zero outside)

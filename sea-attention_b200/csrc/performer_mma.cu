@@ -1,4 +1,7 @@
-// a2 + a3 (+ a13 running mean) for bf16, D = 64: the causal Performer estimate as chunk-parallel tensor-core GEMMs.
+// a2 + a3 (+ a13 running mean) for bf16: the causal Performer estimate as chunk-parallel tensor-core GEMMs.  Written for D = 64
+// (one slab); any head dim that is a multiple of 16 (OPT-2.7B D = 80, the long-context sweep D = 128) runs the same kernels once per
+// 128-column SLAB of V2 = [pos_emb | v] (blockIdx.z): the output columns of linear attention are independent given phi(q), phi(k), so
+// a slab only recomputes the two feature maps (K dimension D) and carries its own ones column for the denominator.
 //
 // Everything the stage needs per 128-row chunk is a small GEMM, chained through REGISTERS (accumulator fragments are
 // re-packed as the next MMA's A fragments, flash-attention style), so nothing but q, k, v is read and nothing but
@@ -21,11 +24,31 @@ namespace {
 
 constexpr int kCh = 128;            // rows per chunk
 constexpr int kThreads = 256;       // 8 warps x 16 rows
-constexpr int kDm = 64;             // head dim
-constexpr int kE = 128;             // v2 width
-constexpr int kEx = 144;            // v2ext width (ones column at 128)
-constexpr int kLdQ = kDm + 8;       // smem row strides (elements); +8 keeps ldmatrix rows on distinct banks
-constexpr int kLdV = kEx + 8;
+constexpr int kE = 128;             // v2 slab width
+constexpr int kEx = 144;            // v2ext slab width (ones column at 128)
+constexpr int kLdV = kEx + 8;       // smem row strides (elements); +8 keeps ldmatrix rows on distinct banks
+__host__ __device__ constexpr int ld_q(int D) { return D + 8; }
+__host__ __device__ constexpr int n_slabs(int D) { return (2 * D + kE - 1) / kE; }
+
+// which columns of slab z of V2 = [pos_emb (D) | v (D)] come from where (all bounds multiples of 16)
+struct Slab {
+    int pos_hi;      // slab columns [0, pos_hi) = pos_emb[:, pos_off + c]
+    int pos_off;
+    int v_lo, v_hi;  // slab columns [v_lo, v_hi) = v[:, v_off + c - v_lo]
+    int v_off;
+    int width;       // real columns of the slab (the rest up to 128 is zero)
+};
+__device__ __forceinline__ Slab make_slab(int D, int z) {
+    const int g0 = z * kE;
+    Slab s;
+    s.pos_hi = max(0, min(kE, D - g0));
+    s.pos_off = g0;
+    s.v_lo = max(0, D - g0);
+    s.v_hi = max(s.v_lo, min(kE, 2 * D - g0));
+    s.v_off = max(0, g0 - D);
+    s.width = max(s.pos_hi, s.v_hi);
+    return s;
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
 __device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
@@ -44,8 +67,9 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     return *reinterpret_cast<uint32_t*>(&p);
 }
 
-template <int kFp>
+template <int kFp, int kDm>
 struct PerfSmem {
+    static constexpr int kLdQ = ld_q(kDm);
     static constexpr int kP = 0;                                // [kFp][kLdQ]
     static constexpr int kQ = kP + kFp * kLdQ;                  // [kCh][kLdQ]
     static constexpr int kK = kQ + kCh * kLdQ;                  // [kCh][kLdQ]
@@ -53,31 +77,31 @@ struct PerfSmem {
     static constexpr int kV = kPhiK + kCh * (kFp + 8);          // [kCh][kLdV]
     static constexpr int kS = kV + kCh * kLdV;                  // [kFp][kLdV]
     static constexpr int kElems = kS + kFp * kLdV;
-    static constexpr int kBytes = kElems * 2 + 64 * 4;          // + vsum_prev fp32 [64]
+    static constexpr int kBytes = kElems * 2 + kE * 4;          // + vsum_prev fp32 [<= 128]
 };
 
 // ---- cooperative loads -------------------------------------------------------------------------------------------
 // The fp32 operands (projection, positional embedding, prefixed state) go through registers to be rounded to bf16.  Their
 // loads are split into an "issue" and a "commit" half so that a kernel can put ALL of its global loads in flight before it
 // consumes the first one: one DRAM round trip per CTA instead of one per operand (the CTAs are latency-bound at 2 per SM).
-template <int kFp>
+template <int kFp, int kDm>
 struct ProjRegs { static constexpr int kVec = kFp * kDm / 4, kIt = (kVec + kThreads - 1) / kThreads; float4 p[kIt]; };
-template <int kFp>
-__device__ __forceinline__ void issue_proj(ProjRegs<kFp>& r, const float* __restrict__ proj, int F) {
+template <int kFp, int kDm>
+__device__ __forceinline__ void issue_proj(ProjRegs<kFp, kDm>& r, const float* __restrict__ proj, int F) {
 #pragma unroll
-    for (int it = 0; it < ProjRegs<kFp>::kIt; ++it) {
+    for (int it = 0; it < ProjRegs<kFp, kDm>::kIt; ++it) {
         const int idx = threadIdx.x + it * kThreads, f = idx / (kDm / 4);
         r.p[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (idx < ProjRegs<kFp>::kVec && f < F) r.p[it] = __ldg(reinterpret_cast<const float4*>(proj) + idx);
+        if (idx < ProjRegs<kFp, kDm>::kVec && f < F) r.p[it] = __ldg(reinterpret_cast<const float4*>(proj) + idx);
     }
 }
-template <int kFp>
-__device__ __forceinline__ void commit_proj(__nv_bfloat16* Ps, const ProjRegs<kFp>& r) {      // [F x 64] fp32 -> bf16 [kFp x kLdQ]
+template <int kFp, int kDm>
+__device__ __forceinline__ void commit_proj(__nv_bfloat16* Ps, const ProjRegs<kFp, kDm>& r) {      // [F x D] fp32 -> bf16 [kFp x kLdQ]
 #pragma unroll
-    for (int it = 0; it < ProjRegs<kFp>::kIt; ++it) {
+    for (int it = 0; it < ProjRegs<kFp, kDm>::kIt; ++it) {
         const int idx = threadIdx.x + it * kThreads, f = idx / (kDm / 4), c4 = idx % (kDm / 4);
-        if (idx < ProjRegs<kFp>::kVec)
-            *reinterpret_cast<uint2*>(Ps + f * kLdQ + c4 * 4) = make_uint2(pack_bf16(r.p[it].x, r.p[it].y), pack_bf16(r.p[it].z, r.p[it].w));
+        if (idx < ProjRegs<kFp, kDm>::kVec)
+            *reinterpret_cast<uint2*>(Ps + f * ld_q(kDm) + c4 * 4) = make_uint2(pack_bf16(r.p[it].x, r.p[it].y), pack_bf16(r.p[it].z, r.p[it].w));
     }
 }
 // 16-byte asynchronous global->shared copy (LDGSTS); src_bytes = 0 zero-fills the destination
@@ -86,35 +110,56 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
+template <int kDm>
 __device__ __forceinline__ void load_rows_bf16(__nv_bfloat16* dst, int ld, const __nv_bfloat16* __restrict__ src, int64_t row_stride,
                                                int r0, int nvalid) {
-    // 128 rows x 64 bf16 as 16-byte async copies: no registers are held while the data is in flight, so the q, k and v
+    // 128 rows x D bf16 as 16-byte async copies: no registers are held while the data is in flight, so the q, k and v
     // tiles of a chunk are all requested at once; rows beyond nvalid are zero-filled
-    constexpr int kIt = kCh * (kDm / 8) / kThreads;
+    constexpr int kPieces = kDm / 8, kIt = (kCh * kPieces + kThreads - 1) / kThreads;
 #pragma unroll
     for (int it = 0; it < kIt; ++it) {
-        const int idx = threadIdx.x + it * kThreads, r = idx >> 3, c8 = idx & 7;
+        const int idx = threadIdx.x + it * kThreads, r = idx / kPieces, c8 = idx % kPieces;
+        const bool ok = r < nvalid;
+        if (idx < kCh * kPieces) cp_async16(dst + r * ld + c8 * 8, src + (int64_t) (r0 + (ok ? r : 0)) * row_stride + c8 * 8, ok ? 16 : 0);
+    }
+}
+// the v part of a slab: `pieces` 16-byte pieces per row (run-time: depends on the slab)
+__device__ __forceinline__ void load_rows_bf16_n(__nv_bfloat16* dst, int ld, const __nv_bfloat16* __restrict__ src, int64_t row_stride,
+                                                 int r0, int nvalid, int pieces) {
+    for (int idx = threadIdx.x; idx < kCh * pieces; idx += kThreads) {
+        const int r = idx / pieces, c8 = idx - r * pieces;
         const bool ok = r < nvalid;
         cp_async16(dst + r * ld + c8 * 8, src + (int64_t) (r0 + (ok ? r : 0)) * row_stride + c8 * 8, ok ? 16 : 0);
     }
 }
-struct PosRegs { static constexpr int kIt = kCh * (kDm / 4) / kThreads; float4 p[kIt]; };
-// V2ext = [pos_emb | v | 1 0 ...]: v -> cols 64..127 by cp.async, pos_emb (fp32) -> registers
-__device__ __forceinline__ void issue_v2ext(PosRegs& r, __nv_bfloat16* Vs, const __nv_bfloat16* __restrict__ v, int64_t v_st,
-                                            const float* __restrict__ pos, int r0, int nvalid) {
-    load_rows_bf16(Vs + kDm, kLdV, v, v_st, r0, nvalid);
+template <int kDm>
+struct PosRegs { static constexpr int kPosVec = (kDm < kE ? kDm : kE) / 4, kIt = kCh * kPosVec / kThreads; float4 p[kIt]; };
+// V2ext slab = [pos_emb part | v part | 0 ... | 1 0 ...]: v -> its columns by cp.async, pos_emb (fp32) -> registers
+template <int kDm>
+__device__ __forceinline__ void issue_v2ext(PosRegs<kDm>& r, __nv_bfloat16* Vs, const __nv_bfloat16* __restrict__ v, int64_t v_st,
+                                            const float* __restrict__ pos, int r0, int nvalid, const Slab& sl) {
+    if (sl.v_hi > sl.v_lo) load_rows_bf16_n(Vs + sl.v_lo, kLdV, v + sl.v_off, v_st, r0, nvalid, (sl.v_hi - sl.v_lo) >> 3);
 #pragma unroll
-    for (int it = 0; it < PosRegs::kIt; ++it) {
-        const int idx = threadIdx.x + it * kThreads, row = idx >> 4, c4 = idx & 15;
+    for (int it = 0; it < PosRegs<kDm>::kIt; ++it) {
+        const int idx = threadIdx.x + it * kThreads, row = idx / PosRegs<kDm>::kPosVec, c4 = idx % PosRegs<kDm>::kPosVec;
         r.p[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (row < nvalid) r.p[it] = __ldg(reinterpret_cast<const float4*>(pos + (int64_t) (r0 + row) * kDm) + c4);
+        if (row < nvalid && c4 * 4 < sl.pos_hi) r.p[it] = __ldg(reinterpret_cast<const float4*>(pos + (int64_t) (r0 + row) * kDm + sl.pos_off) + c4);
     }
 }
-__device__ __forceinline__ void commit_v2ext(__nv_bfloat16* Vs, const PosRegs& r, int nvalid) {
+template <int kDm>
+__device__ __forceinline__ void commit_v2ext(__nv_bfloat16* Vs, const PosRegs<kDm>& r, int nvalid, const Slab& sl) {
 #pragma unroll
-    for (int it = 0; it < PosRegs::kIt; ++it) {                                // pos_emb -> cols 0..63
-        const int idx = threadIdx.x + it * kThreads, row = idx >> 4, c4 = idx & 15;
-        *reinterpret_cast<uint2*>(Vs + row * kLdV + c4 * 4) = make_uint2(pack_bf16(r.p[it].x, r.p[it].y), pack_bf16(r.p[it].z, r.p[it].w));
+    for (int it = 0; it < PosRegs<kDm>::kIt; ++it) {                                // pos_emb -> cols 0 .. pos_hi
+        const int idx = threadIdx.x + it * kThreads, row = idx / PosRegs<kDm>::kPosVec, c4 = idx % PosRegs<kDm>::kPosVec;
+        if (c4 * 4 < sl.pos_hi)
+            *reinterpret_cast<uint2*>(Vs + row * kLdV + c4 * 4) = make_uint2(pack_bf16(r.p[it].x, r.p[it].y), pack_bf16(r.p[it].z, r.p[it].w));
+    }
+    if (sl.width < kE) {                                                         // zero columns of a partly filled slab
+        const int zp = (kE - sl.width) >> 3;
+        for (int idx = threadIdx.x; idx < kCh * zp; idx += kThreads) {
+            const int row = idx / zp, part = idx - row * zp;
+            *reinterpret_cast<uint4*>(Vs + row * kLdV + sl.width + part * 8) = make_uint4(0, 0, 0, 0);
+        }
     }
     for (int idx = threadIdx.x; idx < kCh * 3; idx += kThreads) {             // cols 128..151: ones column then zeros
         const int row = idx / 3, part = idx % 3;
@@ -124,8 +169,8 @@ __device__ __forceinline__ void commit_v2ext(__nv_bfloat16* Vs, const PosRegs& r
     }
 }
 
-// phi of this warp's 16 rows: acc[kFp/8][4] = X[16 x 64] . P^T, then relu(norm * acc) + 1e-3 on the valid features
-template <int kFp>
+// phi of this warp's 16 rows: acc[kFp/8][4] = X[16 x D] . P^T, then relu(norm * acc) + 1e-3 on the valid features
+template <int kFp, int kDm>
 __device__ __forceinline__ void phi_rows(float (&acc)[kFp / 8][4], const __nv_bfloat16* Xs, const __nv_bfloat16* Ps, int warp, int lane) {
 #pragma unroll
     for (int nt = 0; nt < kFp / 8; ++nt)
@@ -133,6 +178,7 @@ __device__ __forceinline__ void phi_rows(float (&acc)[kFp / 8][4], const __nv_bf
         for (int i = 0; i < 4; ++i) acc[nt][i] = 0.f;
     const int arow = 16 * warp + (lane & 7) + 8 * ((lane >> 3) & 1), acol = 8 * (lane >> 4);
     const int brow = (lane & 7) + 8 * (lane >> 4), bcol = 8 * ((lane >> 3) & 1);       // B from [n][k] storage
+    constexpr int kLdQ = ld_q(kDm);
 #pragma unroll
     for (int ks = 0; ks < kDm / 16; ++ks) {
         uint32_t a[4];
@@ -148,13 +194,14 @@ __device__ __forceinline__ void phi_rows(float (&acc)[kFp / 8][4], const __nv_bf
 }
 
 // ---- pass A: per-chunk state sums -----------------------------------------------------------------------------
-template <int kFp>
+template <int kFp, int kDm>
 __global__ void __launch_bounds__(kThreads)
 performer_sums_mma_kernel(const __nv_bfloat16* __restrict__ k, int64_t k_sn, int64_t k_sh, int64_t k_st,
                           const __nv_bfloat16* __restrict__ v, int64_t v_sn, int64_t v_sh, int64_t v_st,
                           const float* __restrict__ pos_emb, const float* __restrict__ proj, float* __restrict__ ws,
                           int H, int T, int F, int nchunks) {
-    using SM = PerfSmem<kFp>;
+    using SM = PerfSmem<kFp, kDm>;
+    constexpr int kLdQ = SM::kLdQ;
     extern __shared__ __align__(16) __nv_bfloat16 sm[];
     __nv_bfloat16 *Ps = sm + SM::kP, *Ks = sm + SM::kK, *PhiK = sm + SM::kPhiK, *Vs = sm + SM::kV;
     pdl_launch_dependents();
@@ -162,21 +209,22 @@ performer_sums_mma_kernel(const __nv_bfloat16* __restrict__ k, int64_t k_sn, int
     const int chunk = blockIdx.x, nh = blockIdx.y, n = nh / H, h = nh % H;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tq = lane & 3;
     const int r0 = chunk * kCh, nvalid = min(kCh, T - r0);
+    const Slab sl = make_slab(kDm, (int) blockIdx.z);
     {   // all global loads in flight first (cp.async tiles + both register batches), then the bf16 roundings
-        ProjRegs<kFp> pr;
-        PosRegs po;
-        load_rows_bf16(Ks, kLdQ, k + (int64_t) n * k_sn + (int64_t) h * k_sh, k_st, r0, nvalid);
-        issue_v2ext(po, Vs, v + (int64_t) n * v_sn + (int64_t) h * v_sh, v_st, pos_emb, r0, nvalid);
-        issue_proj<kFp>(pr, proj, F);
-        commit_v2ext(Vs, po, nvalid);
-        commit_proj<kFp>(Ps, pr);
+        ProjRegs<kFp, kDm> pr;
+        PosRegs<kDm> po;
+        load_rows_bf16<kDm>(Ks, kLdQ, k + (int64_t) n * k_sn + (int64_t) h * k_sh, k_st, r0, nvalid);
+        issue_v2ext<kDm>(po, Vs, v + (int64_t) n * v_sn + (int64_t) h * v_sh, v_st, pos_emb, r0, nvalid, sl);
+        issue_proj<kFp, kDm>(pr, proj, F);
+        commit_v2ext<kDm>(Vs, po, nvalid, sl);
+        commit_proj<kFp, kDm>(Ps, pr);
     }
     cp_async_wait_all();
     __syncthreads();
     const float norm = rsqrtf(sqrtf((float) kDm));
     {
         float acc[kFp / 8][4];
-        phi_rows<kFp>(acc, Ks, Ps, warp, lane);
+        phi_rows<kFp, kDm>(acc, Ks, Ps, warp, lane);
 #pragma unroll
         for (int nt = 0; nt < kFp / 8; ++nt) {
 #pragma unroll
@@ -223,7 +271,7 @@ performer_sums_mma_kernel(const __nv_bfloat16* __restrict__ k, int64_t k_sn, int
             }
         }
     }
-    float* slot = ws + ((int64_t) nh * nchunks + chunk) * (kFp * kEx);
+    float* slot = ws + (((int64_t) nh * gridDim.z + blockIdx.z) * nchunks + chunk) * (kFp * kEx);
 #pragma unroll
     for (int mt = 0; mt < kMT; ++mt)
 #pragma unroll
@@ -238,30 +286,32 @@ performer_sums_mma_kernel(const __nv_bfloat16* __restrict__ k, int64_t k_sn, int
 }
 
 // ---- pass C: outputs ------------------------------------------------------------------------------------------
-template <int kFp>
-__global__ void __launch_bounds__(kThreads, 2)
+template <int kFp, int kDm>
+__global__ void __launch_bounds__(kThreads, (kDm <= 64 ? 2 : 1))
 performer_out_mma_kernel(const __nv_bfloat16* __restrict__ q, int64_t q_sn, int64_t q_sh, int64_t q_st,
                          const __nv_bfloat16* __restrict__ k, int64_t k_sn, int64_t k_sh, int64_t k_st,
                          const __nv_bfloat16* __restrict__ v, int64_t v_sn, int64_t v_sh, int64_t v_st,
                          const float* __restrict__ pos_emb, const float* __restrict__ proj, const float* __restrict__ ws,
                          __nv_bfloat16* __restrict__ ctx, __nv_bfloat16* __restrict__ cumavg, int H, int T, int F, int nchunks) {
-    using SM = PerfSmem<kFp>;
+    using SM = PerfSmem<kFp, kDm>;
+    constexpr int kLdQ = SM::kLdQ;
     extern __shared__ __align__(16) __nv_bfloat16 sm[];
     __nv_bfloat16 *Ps = sm + SM::kP, *Qs = sm + SM::kQ, *Ks = sm + SM::kK, *PhiK = sm + SM::kPhiK, *Vs = sm + SM::kV, *Ss = sm + SM::kS;
-    float* vprev_s = reinterpret_cast<float*>(sm + SM::kElems);          // [64] fp32
+    float* vprev_s = reinterpret_cast<float*>(sm + SM::kElems);          // [v columns of the slab] fp32
     pdl_launch_dependents();
     pdl_wait();
     const int chunk = blockIdx.x, nh = blockIdx.y, n = nh / H, h = nh % H;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tq = lane & 3;
     const int r0 = chunk * kCh, nvalid = min(kCh, T - r0);
+    const Slab sl = make_slab(kDm, (int) blockIdx.z);
     {   // all global loads in flight first: q/k/v tiles by cp.async, then the three fp32 register batches (S_prev, pos_emb,
         // projection); only then the bf16 roundings -- one DRAM round trip per CTA instead of three
-        load_rows_bf16(Qs, kLdQ, q + (int64_t) n * q_sn + (int64_t) h * q_sh, q_st, r0, nvalid);
-        load_rows_bf16(Ks, kLdQ, k + (int64_t) n * k_sn + (int64_t) h * k_sh, k_st, r0, nvalid);
-        PosRegs po;
-        issue_v2ext(po, Vs, v + (int64_t) n * v_sn + (int64_t) h * v_sh, v_st, pos_emb, r0, nvalid);
+        load_rows_bf16<kDm>(Qs, kLdQ, q + (int64_t) n * q_sn + (int64_t) h * q_sh, q_st, r0, nvalid);
+        load_rows_bf16<kDm>(Ks, kLdQ, k + (int64_t) n * k_sn + (int64_t) h * k_sh, k_st, r0, nvalid);
+        PosRegs<kDm> po;
+        issue_v2ext<kDm>(po, Vs, v + (int64_t) n * v_sn + (int64_t) h * v_sh, v_st, pos_emb, r0, nvalid, sl);
         // S_prev (exclusive prefix, fp32) -> bf16; the z column gets the +1e-6 of the reference's denominator
-        const float* slot = ws + ((int64_t) nh * nchunks + chunk) * (kFp * kEx);
+        const float* slot = ws + (((int64_t) nh * gridDim.z + blockIdx.z) * nchunks + chunk) * (kFp * kEx);
         constexpr int kVec = kFp * kEx / 4, kIt = (kVec + kThreads - 1) / kThreads;      // kEx % 4 == 0: a float4 never straddles rows
         float4 sv[kIt];
 #pragma unroll
@@ -269,21 +319,21 @@ performer_out_mma_kernel(const __nv_bfloat16* __restrict__ q, int64_t q_sn, int6
             const int idx = threadIdx.x + it * kThreads;
             sv[it] = idx < kVec ? __ldcg(reinterpret_cast<const float4*>(slot) + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        ProjRegs<kFp> pr;
-        issue_proj<kFp>(pr, proj, F);
-        commit_v2ext(Vs, po, nvalid);
+        ProjRegs<kFp, kDm> pr;
+        issue_proj<kFp, kDm>(pr, proj, F);
+        commit_v2ext<kDm>(Vs, po, nvalid, sl);
 #pragma unroll
         for (int it = 0; it < kIt; ++it) {
             const int idx = threadIdx.x + it * kThreads;
             if (idx < kVec) {
                 const int f = idx / (kEx / 4), e = (idx % (kEx / 4)) * 4;
                 if (e == kE && f < F) sv[it].x += 1e-6f;
-                if (f == F && e >= kDm && e < kE) *reinterpret_cast<float4*>(vprev_s + (e - kDm)) = sv[it];     // vsum of the earlier chunks, kept in fp32
+                if (f == F && e >= sl.v_lo && e < sl.v_hi) *reinterpret_cast<float4*>(vprev_s + (e - sl.v_lo)) = sv[it];     // vsum of the earlier chunks, kept in fp32
                 *reinterpret_cast<uint2*>(Ss + f * kLdV + e) = make_uint2(pack_bf16(sv[it].x, sv[it].y), pack_bf16(sv[it].z, sv[it].w));
             }
         }
         for (int idx = threadIdx.x; idx < kFp; idx += kThreads) *reinterpret_cast<uint4*>(Ss + idx * kLdV + kEx) = make_uint4(0, 0, 0, 0);
-        commit_proj<kFp>(Ps, pr);
+        commit_proj<kFp, kDm>(Ps, pr);
     }
     cp_async_wait_all();
     __syncthreads();
@@ -291,7 +341,7 @@ performer_out_mma_kernel(const __nv_bfloat16* __restrict__ q, int64_t q_sn, int6
     uint32_t aq[kFp / 16][4];     // phi(q) of this warp's rows as A fragments
     {
         float acc[kFp / 8][4];
-        phi_rows<kFp>(acc, Ks, Ps, warp, lane);
+        phi_rows<kFp, kDm>(acc, Ks, Ps, warp, lane);
 #pragma unroll
         for (int nt = 0; nt < kFp / 8; ++nt)
 #pragma unroll
@@ -305,7 +355,7 @@ performer_out_mma_kernel(const __nv_bfloat16* __restrict__ q, int64_t q_sn, int6
                 }
                 *reinterpret_cast<uint32_t*>(PhiK + row * (kFp + 8) + nt * 8 + 2 * tq) = pack_bf16(o[0], o[1]);
             }
-        phi_rows<kFp>(acc, Qs, Ps, warp, lane);
+        phi_rows<kFp, kDm>(acc, Qs, Ps, warp, lane);
 #pragma unroll
         for (int ks = 0; ks < kFp / 16; ++ks) {
             float o[2][4];
@@ -379,21 +429,26 @@ performer_out_mma_kernel(const __nv_bfloat16* __restrict__ q, int64_t q_sn, int6
     const float den_hi = __shfl_sync(kFull, O[kE / 8][2], lane & ~3);
     const float inv_lo = 1.0f / den_lo, inv_hi = 1.0f / den_hi;
     const int row_lo = 16 * warp + g, row_hi = row_lo + 8;
-    __nv_bfloat16* cb = ctx + (((int64_t) n * H + h) * T + r0) * kE;
+    constexpr int kCtxW = 2 * kDm;                  // ctx row = [pos part (D) | v part (D)]; this slab owns columns 128 z ..
+    __nv_bfloat16* cb = ctx + (((int64_t) n * H + h) * T + r0) * kCtxW + (int) blockIdx.z * kE;
 #pragma unroll
     for (int nt = 0; nt < kE / 8; ++nt) {
         const int e0 = nt * 8 + 2 * tq;
-        if (row_lo < nvalid) *reinterpret_cast<uint32_t*>(cb + (int64_t) row_lo * kE + e0) = pack_bf16(O[nt][0] * inv_lo, O[nt][1] * inv_lo);
-        if (row_hi < nvalid) *reinterpret_cast<uint32_t*>(cb + (int64_t) row_hi * kE + e0) = pack_bf16(O[nt][2] * inv_hi, O[nt][3] * inv_hi);
+        if (nt * 8 < sl.width) {
+            if (row_lo < nvalid) *reinterpret_cast<uint32_t*>(cb + (int64_t) row_lo * kCtxW + e0) = pack_bf16(O[nt][0] * inv_lo, O[nt][1] * inv_lo);
+            if (row_hi < nvalid) *reinterpret_cast<uint32_t*>(cb + (int64_t) row_hi * kCtxW + e0) = pack_bf16(O[nt][2] * inv_hi, O[nt][3] * inv_hi);
+        }
     }
     // a13 running mean of v (attention.py:1237-1241), fused: cumavg[t] = (vsum_prev(chunk) + sum_{j <= t in chunk} v_j) / (t + 1).
     // The in-chunk cumulative sum is L . V with L the lower-triangular ones matrix: the same V fragments as above against an
     // all-ones A fragment (triangular on the diagonal tile); bf16 ones x bf16 v accumulate exactly in fp32.  vsum_prev is row F
     // (the ones feature) of the prefixed state, columns 64..127, kept in fp32 in shared memory by the S_prev load above.
-    if (cumavg != nullptr) {
-        float C[kDm / 8][4];
+    if (cumavg != nullptr && sl.v_hi > sl.v_lo) {
+        constexpr int kCT = (kDm < kE ? kDm : kE) / 8;          // n-tiles of v columns a slab can hold
+        const int vtiles = (sl.v_hi - sl.v_lo) >> 3;           // ... and holds (even)
+        float C[kCT][4];
 #pragma unroll
-        for (int nt = 0; nt < kDm / 8; ++nt)
+        for (int nt = 0; nt < kCT; ++nt)
 #pragma unroll
             for (int i = 0; i < 4; ++i) C[nt][i] = 0.f;
         constexpr uint32_t kOne2 = 0x3F803F80u;                    // two bf16 ones
@@ -404,55 +459,26 @@ performer_out_mma_kernel(const __nv_bfloat16* __restrict__ q, int64_t q_sn, int6
                 la[0] = tri; la[1] = kOne2; la[2] = 0u; la[3] = tri;
             }
 #pragma unroll
-            for (int np = 0; np < kDm / 16; ++np) {
-                uint32_t b[4];
-                ldsm_x4_t(b, smem_u32(Vs + (jt * 16 + vr) * kLdV + kDm + np * 16 + vc));
-                mma16816(C[2 * np], la, b[0], b[1]);
-                mma16816(C[2 * np + 1], la, b[2], b[3]);
+            for (int np = 0; np < kCT / 2; ++np) {
+                if (2 * np < vtiles) {
+                    uint32_t b[4];
+                    ldsm_x4_t(b, smem_u32(Vs + (jt * 16 + vr) * kLdV + sl.v_lo + np * 16 + vc));
+                    mma16816(C[2 * np], la, b[0], b[1]);
+                    mma16816(C[2 * np + 1], la, b[2], b[3]);
+                }
             }
         }
         const float r_lo = 1.0f / (float) (r0 + row_lo + 1), r_hi = 1.0f / (float) (r0 + row_hi + 1);
-        __nv_bfloat16* ab = cumavg + (((int64_t) n * H + h) * T + r0) * kDm;
+        __nv_bfloat16* ab = cumavg + (((int64_t) n * H + h) * T + r0) * kDm + sl.v_off;
 #pragma unroll
-        for (int nt = 0; nt < kDm / 8; ++nt) {
+        for (int nt = 0; nt < kCT; ++nt) {
             const int e0 = nt * 8 + 2 * tq;
-            const float2 pv = *reinterpret_cast<const float2*>(vprev_s + e0);
-            if (row_lo < nvalid) *reinterpret_cast<uint32_t*>(ab + (int64_t) row_lo * kDm + e0) = pack_bf16((C[nt][0] + pv.x) * r_lo, (C[nt][1] + pv.y) * r_lo);
-            if (row_hi < nvalid) *reinterpret_cast<uint32_t*>(ab + (int64_t) row_hi * kDm + e0) = pack_bf16((C[nt][2] + pv.x) * r_hi, (C[nt][3] + pv.y) * r_hi);
+            if (nt < vtiles) {
+                const float2 pv = *reinterpret_cast<const float2*>(vprev_s + e0);
+                if (row_lo < nvalid) *reinterpret_cast<uint32_t*>(ab + (int64_t) row_lo * kDm + e0) = pack_bf16((C[nt][0] + pv.x) * r_lo, (C[nt][1] + pv.y) * r_lo);
+                if (row_hi < nvalid) *reinterpret_cast<uint32_t*>(ab + (int64_t) row_hi * kDm + e0) = pack_bf16((C[nt][2] + pv.x) * r_hi, (C[nt][3] + pv.y) * r_hi);
+            }
         }
-    }
-}
-
-// a13 running mean of v (attention.py:1237-1241): cumavg[t] = (vsum_prev(chunk) + sum_{j<=t in chunk} v_j) / (t+1).
-// vsum_prev is row F (the ones feature) of the prefixed state, columns 64..127.  Thread = (8-row group, channel);
-// group partial sums are combined through shared memory, then each thread walks its 8 rows.
-template <int kFp>
-__global__ void __launch_bounds__(1024)
-cumavg_kernel(const __nv_bfloat16* __restrict__ v, int64_t v_sn, int64_t v_sh, int64_t v_st, const float* __restrict__ ws,
-              __nv_bfloat16* __restrict__ cumavg, int H, int T, int F, int nchunks) {
-    __shared__ float part[16][kDm];
-    const int chunk = blockIdx.x, nh = blockIdx.y, n = nh / H, h = nh % H;
-    const int c = threadIdx.x & 63, grp = threadIdx.x >> 6;      // 16 groups x 8 rows
-    const int r0 = chunk * kCh;
-    const __nv_bfloat16* vb = v + (int64_t) n * v_sn + (int64_t) h * v_sh;
-    float x[8];
-    float s = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int t = r0 + grp * 8 + i;
-        x[i] = t < T ? __bfloat162float(vb[(int64_t) t * v_st + c]) : 0.f;
-        s += x[i];
-    }
-    part[grp][c] = s;
-    __syncthreads();
-    float run = ws[((int64_t) nh * nchunks + chunk) * (kFp * kEx) + F * kEx + kDm + c];
-    for (int gidx = 0; gidx < grp; ++gidx) run += part[gidx][c];
-    __nv_bfloat16* ab = cumavg + (((int64_t) n * H + h) * T) * kDm;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int t = r0 + grp * 8 + i;
-        run += x[i];
-        if (t < T) ab[(int64_t) t * kDm + c] = __float2bfloat16_rn(__fdividef(run, (float) (t + 1)));
     }
 }
 
@@ -481,31 +507,27 @@ prefix_chunks_kernel(float* __restrict__ ws, int nchunks, int64_t stride) {
     }
 }
 
-template <int kFp>
+template <int kFp, int kDm>
 int launch_performer_mma(const void* q, int64_t q_sn, int64_t q_sh, int64_t q_st, const void* k, int64_t k_sn, int64_t k_sh, int64_t k_st,
                          const void* v, int64_t v_sn, int64_t v_sh, int64_t v_st, const float* pos_emb, const float* proj,
                          void* ctx, void* cumavg, float* ws, int N, int H, int T, int F, cudaStream_t s) {
-    using SM = PerfSmem<kFp>;
+    using SM = PerfSmem<kFp, kDm>;
     const int nchunks = (T + kCh - 1) / kCh;
-    dim3 grid(nchunks, N * H);
-    auto ka = performer_sums_mma_kernel<kFp>;
-    auto kc = performer_out_mma_kernel<kFp>;
+    constexpr int kSlabs = n_slabs(kDm);
+    dim3 grid(nchunks, N * H, kSlabs);
+    auto ka = performer_sums_mma_kernel<kFp, kDm>;
+    auto kc = performer_out_mma_kernel<kFp, kDm>;
     SEA_CUDA_TRY(cudaFuncSetAttribute(ka, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kBytes), "smem attr");
     SEA_CUDA_TRY(cudaFuncSetAttribute(kc, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kBytes), "smem attr");
     using B = __nv_bfloat16;
     SEA_CUDA_TRY(launch_pdl(ka, grid, dim3(kThreads), (size_t) SM::kBytes, s, (const B*) k, k_sn, k_sh, k_st, (const B*) v, v_sn, v_sh, v_st, pos_emb, proj, ws, H, T, F,
                             nchunks), "performer_sums_mma_kernel launch");
     const int64_t stride = (int64_t) kFp * kEx;
-    SEA_CUDA_TRY(launch_pdl(prefix_chunks_kernel, dim3((unsigned) ((stride / 4 + 255) / 256), N * H), dim3(256), (size_t) 0, s, ws, nchunks, stride),
+    // one exclusive prefix per (n, h, slab): the slabs' chunk slots are laid out [nh][slab][chunk]
+    SEA_CUDA_TRY(launch_pdl(prefix_chunks_kernel, dim3((unsigned) ((stride / 4 + 255) / 256), N * H * kSlabs), dim3(256), (size_t) 0, s, ws, nchunks, stride),
                  "prefix_chunks_kernel launch");
     SEA_CUDA_TRY(launch_pdl(kc, grid, dim3(kThreads), (size_t) SM::kBytes, s, (const B*) q, q_sn, q_sh, q_st, (const B*) k, k_sn, k_sh, k_st, (const B*) v, v_sn, v_sh, v_st,
                             pos_emb, proj, (const float*) ws, (B*) ctx, (B*) cumavg, H, T, F, nchunks), "performer_out_mma_kernel launch");
-    // (the running mean of v is produced by performer_out_mma_kernel; cumavg_kernel stays as the stand-alone version)
-    static const bool separate_cumavg = getenv("SEA_CUMAVG_SEPARATE") != nullptr;      // development switch for A/B timing
-    if (cumavg != nullptr && separate_cumavg) {
-        cumavg_kernel<kFp><<<grid, 1024, 0, s>>>((const B*) v, v_sn, v_sh, v_st, ws, (B*) cumavg, H, T, F, nchunks);
-        SEA_CHECK_LAUNCH("cumavg_kernel");
-    }
     return SEA_OK;
 }
 
@@ -516,12 +538,24 @@ using namespace sea;
 
 extern "C" {
 
-int sea_performer_mma_supported(int dtype, int D, int F) { return dtype == SEA_DTYPE_BF16 && D == 64 && F >= 1 && F <= 63; }
+// feature counts the kernels are instantiated for, per head dim (Fp = F + 1 rounded up to 16; F = int(D ln D / nb_factor))
+int sea_performer_mma_supported(int dtype, int D, int F) {
+    if (dtype != SEA_DTYPE_BF16 || F < 1) return 0;
+    const int Fp = ((F + 1) + 15) & ~15;
+    switch (D) {
+        case 32: return Fp <= 32;
+        case 64: return Fp <= 64;
+        case 80: return Fp >= 32 && Fp <= 64;
+        case 96: return Fp == 64;
+        case 128: return Fp >= 48 && Fp <= 80;
+    }
+    return 0;
+}
 
 int64_t sea_performer_mma_workspace_floats(int N, int H, int T, int D, int F) {
-    if (N <= 0 || H <= 0 || T <= 0 || F <= 0) return 0;
+    if (N <= 0 || H <= 0 || T <= 0 || F <= 0 || D <= 0) return 0;
     const int Fp = ((F + 1) + 15) & ~15;
-    return (int64_t) N * H * ((T + kCh - 1) / kCh) * Fp * kEx;
+    return (int64_t) N * H * ((2 * D + kE - 1) / kE) * ((T + kCh - 1) / kCh) * Fp * kEx;
 }
 
 int sea_performer_causal_mma_fwd(const void* q, int64_t q_sn, int64_t q_sh, int64_t q_st,
@@ -531,7 +565,7 @@ int sea_performer_causal_mma_fwd(const void* q, int64_t q_sn, int64_t q_sh, int6
                                  int N, int H, int T, int D, int F, void* stream) {
     SEA_CHECK_ARG(q && k && v && pos_emb && proj && ctx && workspace, "sea_performer_causal_mma_fwd: null pointer");
     if (!sea_performer_mma_supported(SEA_DTYPE_BF16, D, F)) {
-        set_error("sea_performer_causal_mma_fwd: unsupported shape D=%d F=%d (need D=64, F<=63)", D, F);
+        set_error("sea_performer_causal_mma_fwd: unsupported shape D=%d F=%d", D, F);
         return SEA_ERR_UNSUPPORTED;
     }
     SEA_CHECK_ARG(N > 0 && H > 0 && T > 0 && (int64_t) N * H <= 65535, "sea_performer_causal_mma_fwd: bad shape");
@@ -540,13 +574,16 @@ int sea_performer_causal_mma_fwd(const void* q, int64_t q_sn, int64_t q_sh, int6
                   "sea_performer_causal_mma_fwd: q/k/v rows must be 16-byte aligned");
     cudaStream_t s = (cudaStream_t) stream;
     const int Fp = ((F + 1) + 15) & ~15;
-    switch (Fp) {
-        case 16: return launch_performer_mma<16>(q, q_sn, q_sh, q_st, k, k_sn, k_sh, k_st, v, v_sn, v_sh, v_st, pos_emb, proj, ctx, cumavg, workspace, N, H, T, F, s);
-        case 32: return launch_performer_mma<32>(q, q_sn, q_sh, q_st, k, k_sn, k_sh, k_st, v, v_sn, v_sh, v_st, pos_emb, proj, ctx, cumavg, workspace, N, H, T, F, s);
-        case 48: return launch_performer_mma<48>(q, q_sn, q_sh, q_st, k, k_sn, k_sh, k_st, v, v_sn, v_sh, v_st, pos_emb, proj, ctx, cumavg, workspace, N, H, T, F, s);
-        case 64: return launch_performer_mma<64>(q, q_sn, q_sh, q_st, k, k_sn, k_sh, k_st, v, v_sn, v_sh, v_st, pos_emb, proj, ctx, cumavg, workspace, N, H, T, F, s);
-    }
-    set_error("sea_performer_causal_mma_fwd: unsupported padded feature count %d", Fp);
+#define SEA_PF_CASE(FF, DD)                                                                                                                   \
+    if (Fp == FF && D == DD)                                                                                                                  \
+        return launch_performer_mma<FF, DD>(q, q_sn, q_sh, q_st, k, k_sn, k_sh, k_st, v, v_sn, v_sh, v_st, pos_emb, proj, ctx, cumavg, workspace, N, H, T, F, s)
+    SEA_PF_CASE(16, 32); SEA_PF_CASE(32, 32);
+    SEA_PF_CASE(16, 64); SEA_PF_CASE(32, 64); SEA_PF_CASE(48, 64); SEA_PF_CASE(64, 64);
+    SEA_PF_CASE(32, 80); SEA_PF_CASE(48, 80); SEA_PF_CASE(64, 80);
+    SEA_PF_CASE(64, 96);
+    SEA_PF_CASE(48, 128); SEA_PF_CASE(64, 128); SEA_PF_CASE(80, 128);
+#undef SEA_PF_CASE
+    set_error("sea_performer_causal_mma_fwd: no kernel for D=%d, padded feature count %d", D, Fp);
     return SEA_ERR_UNSUPPORTED;
 }
 

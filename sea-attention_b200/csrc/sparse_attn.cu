@@ -433,16 +433,32 @@ template <typename T16, int D>
 __device__ __forceinline__ void attn_chunk_mma(T16* __restrict__ Ks, T16* __restrict__ Vs, const uint4* __restrict__ kb, const uint4* __restrict__ vb,
                                                uint32_t k_sv, uint32_t v_sv, int jmine, int cnt, const uint32_t (&qb)[D / 16][2],
                                                float& m_run, float& l_run, float (&acc)[D / 8][4], int lane) {
-    constexpr int LPR = D / 8, EPI = 32 / LPR, NI = LPR, kLd = AttnMmaCfg<D>::kLd;
+    constexpr int LPR = D / 8, kLd = AttnMmaCfg<D>::kLd;
     constexpr float kLog2e = 1.4426950408889634f;
-    const int sub = lane % LPR, grp = lane / LPR;
+    if constexpr (32 % LPR == 0) {
+        constexpr int EPI = 32 / LPR, NI = LPR;
+        const int sub = lane % LPR, grp = lane / LPR;
 #pragma unroll
-    for (int i = 0; i < NI; ++i) {
-        const int e = i * EPI + grp;
-        const uint32_t j = (uint32_t) __shfl_sync(kFull, jmine, e);
-        const bool ok = e < cnt;
-        cp_async16_zfill(Ks + e * kLd + sub * 8, kb + (ok ? j * k_sv : 0u), ok ? 16 : 0);
-        cp_async16_zfill(Vs + e * kLd + sub * 8, vb + (ok ? j * v_sv : 0u), ok ? 16 : 0);
+        for (int i = 0; i < NI; ++i) {
+            const int e = i * EPI + grp;
+            const uint32_t j = (uint32_t) __shfl_sync(kFull, jmine, e);
+            const bool ok = e < cnt;
+            cp_async16_zfill(Ks + e * kLd + sub * 8, kb + (ok ? j * k_sv : 0u), ok ? 16 : 0);
+            cp_async16_zfill(Vs + e * kLd + sub * 8, vb + (ok ? j * v_sv : 0u), ok ? 16 : 0);
+        }
+    } else {
+        // head dims whose row is not a power-of-two number of 16-byte pieces (D = 80: 10, D = 96: 12): piece idx -> (entry, piece)
+        static_assert((32 * LPR) % 32 == 0, "piece count");
+        const uint4* kb0 = kb - (lane % LPR);
+        const uint4* vb0 = vb - (lane % LPR);
+#pragma unroll
+        for (int i = 0; i < LPR; ++i) {
+            const int idx = i * 32 + lane, e = idx / LPR, sb = idx - e * LPR;
+            const uint32_t j = (uint32_t) __shfl_sync(kFull, jmine, e);
+            const bool ok = e < cnt;
+            cp_async16_zfill(Ks + e * kLd + sb * 8, kb0 + sb + (ok ? j * k_sv : 0u), ok ? 16 : 0);
+            cp_async16_zfill(Vs + e * kLd + sb * 8, vb0 + sb + (ok ? j * v_sv : 0u), ok ? 16 : 0);
+        }
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncwarp();
@@ -694,8 +710,8 @@ extern "C" int sea_sparse_attention_bits_fwd(const uint32_t* mask_bits,
                                              int N, int H, int T_DST, int T_SRC, int D, int P, int k_clamp, int is_causal, void* stream) {
     SEA_CHECK_ARG(mask_bits && q && k && v && scales && out, "sea_sparse_attention_bits_fwd: null pointer");
     SEA_CHECK_ARG(N > 0 && H > 0 && T_DST > 0 && T_SRC >= T_DST && k_clamp > 0, "sea_sparse_attention_bits_fwd: bad shape");
-    if (dtype == SEA_DTYPE_F32 || !(D == 32 || D == 64 || D == 128) || (P % 32) != 0 || P > 1024) {
-        set_error("sea_sparse_attention_bits_fwd: unsupported (needs 16-bit activations, D in {32,64,128}, P %% 32 == 0, P <= 1024)");
+    if (dtype == SEA_DTYPE_F32 || !(D == 32 || D == 64 || D == 80 || D == 96 || D == 128) || (P % 32) != 0 || P > 1024) {
+        set_error("sea_sparse_attention_bits_fwd: unsupported (needs 16-bit activations, D in {32,64,80,96,128}, P %% 32 == 0, P <= 1024)");
         return SEA_ERR_UNSUPPORTED;
     }
     SEA_CHECK_ARG(((q_sn | q_sh | q_st | k_sn | k_sh | k_st | v_sn | v_sh | v_st) % 8) == 0 &&
@@ -712,9 +728,11 @@ extern "C" int sea_sparse_attention_bits_fwd(const uint32_t* mask_bits,
             k_sh, k_st, (const TT*) v, v_sn, v_sh, v_st, scales, (const TT*) cumavg, avg_sh, avg_st, use_scaler, (TT*) out, N, H, T_DST, T_SRC, P, k_clamp, is_causal); \
     } while (0)
     if (dtype == SEA_DTYPE_BF16) {
-        if (D == 32) SEA_ATTN_BITS(__nv_bfloat16, 32); else if (D == 64) SEA_ATTN_BITS(__nv_bfloat16, 64); else SEA_ATTN_BITS(__nv_bfloat16, 128);
+        if (D == 32) SEA_ATTN_BITS(__nv_bfloat16, 32); else if (D == 64) SEA_ATTN_BITS(__nv_bfloat16, 64); else if (D == 80) SEA_ATTN_BITS(__nv_bfloat16, 80);
+        else if (D == 96) SEA_ATTN_BITS(__nv_bfloat16, 96); else SEA_ATTN_BITS(__nv_bfloat16, 128);
     } else {
-        if (D == 32) SEA_ATTN_BITS(__half, 32); else if (D == 64) SEA_ATTN_BITS(__half, 64); else SEA_ATTN_BITS(__half, 128);
+        if (D == 32) SEA_ATTN_BITS(__half, 32); else if (D == 64) SEA_ATTN_BITS(__half, 64); else if (D == 80) SEA_ATTN_BITS(__half, 80);
+        else if (D == 96) SEA_ATTN_BITS(__half, 96); else SEA_ATTN_BITS(__half, 128);
     }
 #undef SEA_ATTN_BITS
     SEA_CHECK_LAUNCH("sparse_attention_bits_mma_kernel");

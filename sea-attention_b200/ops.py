@@ -333,7 +333,8 @@ class PackedWeights:
         return ws, True
 
 
-def predictor_mlp(ctx, v, w, S: int, W: int, want_t_pred=False, force_simt=False, packed: 'PackedWeights' = None, c_out: int = None):
+def predictor_mlp(ctx, v, w, S: int, W: int, want_t_pred=False, force_simt=False, packed: 'PackedWeights' = None, c_out: int = None,
+                  force_mma=False):
     """a4.  `w` = dict of fp32 contiguous weights (enc_w, enc_b, enc_ln_w, enc_ln_b, dec_w, dec_b, cnn_ln_w, cnn_ln_b,
     scl_w, scl_b) -> cnn_in [N,T,W,H*S] channels-last, scales fp32 [N,H,T,2], t_pred or None."""
     _cuda(ctx, v)
@@ -344,7 +345,7 @@ def predictor_mlp(ctx, v, w, S: int, W: int, want_t_pred=False, force_simt=False
     cnn_in = torch.empty((N, T, W, c_out), dtype=ctx.dtype, device=ctx.device)
     scales = torch.empty((N, H, T, 2), dtype=torch.float32, device=ctx.device)
     lib = _lib.load()
-    if (not want_t_pred and not force_simt and ctx.is_contiguous() and w.get('cnn_ln_w') is not None
+    if (not want_t_pred and not force_simt and not force_mma and ctx.is_contiguous() and w.get('cnn_ln_w') is not None
             and lib.sea_predictor_mlp_umma_supported(_DTYPES.get(ctx.dtype, -1), H, D, S, W)
             and v.stride(0) % 8 == 0 and v.stride(1) % 8 == 0 and v.stride(2) % 8 == 0):
         nbytes = lib.sea_predictor_mlp_umma_workspace_bytes()
@@ -359,8 +360,24 @@ def predictor_mlp(ctx, v, w, S: int, W: int, want_t_pred=False, force_simt=False
                   wp(w['scl_w']), w['scl_b'].data_ptr(), cnn_in.data_ptr(), scales.data_ptr(), ws.data_ptr(),
                   N, H, T, D, S, W, c_out, _stream(), kernels=2 if fresh else 1)
         return cnn_in, scales, None
+    if (not want_t_pred and not force_simt and ctx.is_contiguous() and w.get('cnn_ln_w') is not None
+            and lib.sea_predictor_mlp_mma_supported(_DTYPES.get(ctx.dtype, -1), H, D, S, W)
+            and v.stride(0) % 8 == 0 and v.stride(1) % 8 == 0 and v.stride(2) % 8 == 0 and W * c_out * 2 <= 32 * 1024 and c_out % 8 == 0):
+        # any head dim (D = 80, 128, ...): warp-level tensor-core GEMMs with streamed weights (csrc/mlp_mma.cu)
+        nbytes = lib.sea_predictor_mlp_mma_workspace_bytes(D, S, W)
+        if packed is not None:
+            ws, fresh = packed.get('mlp_mma', w.get('_src_mlp', (w['enc_w'], w['dec_w'], w['scl_w'])), nbytes, ctx.device)
+        else:
+            ws, fresh = torch.empty((nbytes,), dtype=torch.uint8, device=ctx.device), True
+        wp = (lambda t: t.data_ptr()) if fresh else (lambda t: None)
+        _lib.call('sea_predictor_mlp_mma_fwd', ctx.data_ptr(), v.data_ptr(), v.stride(0), v.stride(1), v.stride(2),
+                  wp(w['enc_w']), w['enc_b'].data_ptr(), w['enc_ln_w'].data_ptr(), w['enc_ln_b'].data_ptr(),
+                  wp(w['dec_w']), w['dec_b'].data_ptr(), w['cnn_ln_w'].data_ptr(), w['cnn_ln_b'].data_ptr(),
+                  wp(w['scl_w']), w['scl_b'].data_ptr(), cnn_in.data_ptr(), scales.data_ptr(), ws.data_ptr(),
+                  N, H, T, D, S, W, c_out, _stream(), kernels=2 if fresh else 1)
+        return cnn_in, scales, None
     if c_out != H * S:
-        raise SeaError('predictor_mlp: padded output channels need the tensor-core kernel (bf16, D = 64, contiguous ctx)')
+        raise SeaError('predictor_mlp: padded output channels need a tensor-core kernel (bf16, contiguous ctx)')
     t_pred = torch.empty((N, H, T, D2), dtype=ctx.dtype, device=ctx.device) if want_t_pred else None
     _lib.call('sea_predictor_mlp_fwd', ctx.data_ptr(), v.data_ptr(), v.stride(0), v.stride(1), v.stride(2), _dtype_code(ctx),
               w['enc_w'].data_ptr(), w['enc_b'].data_ptr(), w['enc_ln_w'].data_ptr(), w['enc_ln_b'].data_ptr(),
@@ -619,7 +636,7 @@ def sparse_attention_from_bits_autograd(bits, q, k, v, scales, cumavg, P: int, k
 
 
 def attention_bits_supported(dtype, D: int, P: int) -> bool:
-    return dtype in (torch.bfloat16, torch.float16) and D in (32, 64, 128) and P % 32 == 0 and P <= 1024
+    return dtype in (torch.bfloat16, torch.float16) and D in (32, 64, 80, 96, 128) and P % 32 == 0 and P <= 1024
 
 
 # --------------------------------------------------------------------------------------------- non-causal (BERT)

@@ -135,10 +135,12 @@ def test_mlp_umma_matches_simt(sea, N, H, T, P):
         assert float(p_in[..., 2 * H:].float().abs().max()) == 0.0
 
 
-@pytest.mark.parametrize('N,H,T,nbf', [(1, 2, 128, 8), (2, 3, 200, 8), (1, 4, 515, 8), (1, 2, 96, 5), (1, 1, 300, 16), (1, 1, 40, 32)])
-def test_performer_mma_matches_oracle(sea, N, H, T, nbf):
+@pytest.mark.parametrize('N,H,T,nbf,d', [(1, 2, 128, 8, 64), (2, 3, 200, 8, 64), (1, 4, 515, 8, 64), (1, 2, 96, 5, 64), (1, 1, 300, 16, 64), (1, 1, 40, 32, 64),
+                                         # other head dims run the same kernels once per 128-column slab of [pos | v]
+                                         (1, 2, 300, 8, 128), (2, 2, 131, 8, 80), (1, 3, 260, 8, 32), (1, 1, 140, 4, 32), (1, 2, 200, 8, 96),
+                                         (1, 1, 257, 10, 128), (1, 2, 129, 6, 80)])
+def test_performer_mma_matches_oracle(sea, N, H, T, nbf, d):
     import math
-    d = 64
     F = int(d * math.log(d) / nbf)
     g = torch.Generator().manual_seed(T + nbf)
     q = (torch.randn(N, H, T, d, generator=g) * d ** -0.5).bfloat16()
@@ -175,3 +177,38 @@ def test_tail_topk_fused_row_counts(sea):
     mask = sea.ops.bits_to_mask(bits, H, P).cpu()
     crow_r, col_r, Z_r = so.resize_from_m_to_t_csr(mask, k, T, True)
     assert torch.equal(crow3.cpu().long(), crow_r) and torch.equal(col3.cpu().long(), col_r)
+
+
+@pytest.mark.parametrize('N,H,d,T,P', [(1, 32, 128, 40, 256), (2, 32, 80, 37, 256), (1, 12, 80, 45, 256), (1, 16, 128, 50, 128),
+                                       (1, 20, 96, 19, 128), (1, 32, 64, 33, 256), (1, 4, 32, 70, 256)])
+def test_mlp_mma_any_head_dim_matches_oracle(sea, N, H, d, T, P):
+    """csrc/mlp_mma.cu (warp-level tensor-core MLP for any head dim: OPT-2.7B d = 80, the long-context sweep d = 128) against the CPU
+    oracle (attention.py:190-196,242-245,289-291 + the CNN's first LayerNorm, :268) and the repo's fp32 SIMT kernel."""
+    import transformers
+    S, W = 2, P // 4
+    torch.manual_seed(P + H + d)
+    cfg = transformers.BertConfig(hidden_size=H * d, num_attention_heads=H, max_position_embeddings=T)
+    pc = sea.PerlinAttentionConfig(performer_nb_factor=8, k=8, attention_predictor_length=P, causal=True)
+    mod = sea.PerlinAttention(cfg, pc).eval().to(DEV)
+    for n_, p_ in mod.named_parameters():
+        if p_.ndim == 1:
+            p_.data.add_(0.1 * torch.randn_like(p_))
+    w = mod._weights_fp32()
+    ctx = torch.randn(N, H, T, 2 * d, device=DEV).bfloat16()
+    v = torch.randn(N, H, T, d, device=DEV).bfloat16()
+    assert sea._lib.load().sea_predictor_mlp_mma_supported(1, H, d, S, W)
+    a_in, a_sc, _ = sea.ops.predictor_mlp(ctx, v, w, S, W, force_mma=True)
+    b_in, b_sc, _ = sea.ops.predictor_mlp(ctx, v, w, S, W, force_simt=True)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(a_sc.cpu(), b_sc.cpu(), rtol=2e-2, atol=2e-2)
+    torch.testing.assert_close(a_in.float().cpu(), b_in.float().cpu(), rtol=2e-2, atol=3e-2)
+    sd = {k_: v_.detach().float().cpu() for k_, v_ in mod.state_dict().items()}
+    t_ref = so.predictor_enc(torch.cat([ctx.float().cpu(), v.float().cpu()], -1), sd)
+    x0 = so.layer_norm(so.predictor_dec_row(t_ref, sd, S), sd['attention_predictor_cnn.0.module.weight'], sd['attention_predictor_cnn.0.module.bias'])
+    torch.testing.assert_close(a_sc.cpu(), so.predictor_dec_scaler(t_ref, sd), rtol=2e-2, atol=2e-2)
+    torch.testing.assert_close(a_in.float().cpu().permute(0, 3, 1, 2), x0, rtol=2e-2, atol=3e-2)
+    if 2 * H < 64:      # zero-padded channels for the 64-channel tcgen05 convolutions
+        p_in, p_sc, _ = sea.ops.predictor_mlp(ctx, v, w, S, W, c_out=64, force_mma=True)
+        assert p_in.shape == (N, T, W, 64)
+        assert torch.equal(p_in[..., :2 * H], a_in) and torch.equal(p_sc, a_sc)
+        assert float(p_in[..., 2 * H:].float().abs().max()) == 0.0
