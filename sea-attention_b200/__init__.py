@@ -10,11 +10,12 @@ from ._lib import SeaError
 from .attention import PerlinAttention, PerlinAttentionOutput, ProjectionUpdater
 from .attention_state import PerlinAttentionState
 from .config import PerlinAttentionConfig, get_default_config, register_default_config
+from .opt_attention import SeaOPTAttention
 from .ops import (flat_csr_elmul, flat_csr_masked_bmm, flat_csr_sdbmm, flat_csr_softmax, flat_csr_to_dense,
                   resize_from_m_to_t, resize_from_m_to_t_csr)
 
 __all__ = [
-    'PerlinAttention', 'PerlinAttentionOutput', 'PerlinAttentionConfig', 'PerlinAttentionState', 'ProjectionUpdater', 'SeaError',
+    'PerlinAttention', 'PerlinAttentionOutput', 'PerlinAttentionConfig', 'PerlinAttentionState', 'ProjectionUpdater', 'SeaError', 'SeaOPTAttention',
     'get_default_config', 'register_default_config', 'ops',
     'resize_from_m_to_t', 'resize_from_m_to_t_csr', 'flat_csr_elmul', 'flat_csr_masked_bmm', 'flat_csr_sdbmm',
     'flat_csr_softmax', 'flat_csr_to_dense',

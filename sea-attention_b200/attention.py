@@ -178,6 +178,10 @@ class PerlinAttention(nn.Module):
         self.output_attentions = False
         # one tiny host read of N*T booleans to reject padded batches (set False under CUDA graphs)
         self.check_padding = True
+        # estimated_attention_probs [N,H,T,P] fp32 is an OUTPUT of the reference (attention.py:1349-1359), but its OPT caller drops it
+        # (perlin_opt.py:477) unless output_attentions; False = the fused tail keeps the probabilities in registers (top-k only) and
+        # the two estimated_* fields of the output tuple are None (134 MB less HBM traffic per layer at the north-star shape)
+        self.keep_estimated_probs = True
 
         self.performer_nb_features = int(d * math.log(d) / pc.performer_nb_factor)
         self.performer = _PerformerParams(d, self.performer_nb_features, causal=pc.causal)
@@ -488,7 +492,9 @@ class PerlinAttention(nn.Module):
                 y3 = ops.conv1x1_umma(y, cw['conv3_w'], cw['conv3_b'], packed=pk, slot='conv3', src=c1x1.weight)
             if pad_c:
                 y3 = y3[..., :H].contiguous()
-            res = ops.predictor_tail_topk(y3, w['conv3_b'], w['out_ln_w'], w['out_ln_b'], kpr, P, count_k=pc.k if self.output_attentions else 0)
+            want_probs = self.keep_estimated_probs or self.output_attentions or row_valid is not None
+            res = ops.predictor_tail_topk(y3, w['conv3_b'], w['out_ln_w'], w['out_ln_b'], kpr, P, want_probs=want_probs,
+                                          count_k=pc.k if self.output_attentions else 0)
             probs, bits, crow_counts = res if len(res) == 3 else (res[0], res[1], None)
             if row_valid is not None:             # (off the hot path: the grouped top-k again, with the padded rows' keys zeroed)
                 bits, crow_counts = ops.topk_mask_bits(probs, kpr, 'causal_batch', row_valid=row_valid), None
