@@ -78,6 +78,12 @@ struct PerfSmem {
     static constexpr int kS = kV + kCh * kLdV;                  // [kFp][kLdV]
     static constexpr int kElems = kS + kFp * kLdV;
     static constexpr int kBytes = kElems * 2 + kE * 4;          // + vsum_prev fp32 [<= 128]
+    // pass A needs neither Q nor S_prev, and its phi(k) tile may overwrite the K tile it was computed from: [P | K = PhiK | V]
+    // (64 KB at Fp = 48, D = 64 -> three CTAs per SM instead of two)
+    static constexpr int kSumsK = kFp * kLdQ;
+    static constexpr int kSumsV = kSumsK + kCh * kLdQ;
+    static constexpr int kSumsBytes = (kSumsV + kCh * kLdV) * 2;
+    static_assert(kFp + 8 <= kLdQ, "phi(k) rows must fit the K rows they replace");
 };
 
 // ---- cooperative loads -------------------------------------------------------------------------------------------
@@ -203,7 +209,7 @@ performer_sums_mma_kernel(const __nv_bfloat16* __restrict__ k, int64_t k_sn, int
     using SM = PerfSmem<kFp, kDm>;
     constexpr int kLdQ = SM::kLdQ;
     extern __shared__ __align__(16) __nv_bfloat16 sm[];
-    __nv_bfloat16 *Ps = sm + SM::kP, *Ks = sm + SM::kK, *PhiK = sm + SM::kPhiK, *Vs = sm + SM::kV;
+    __nv_bfloat16 *Ps = sm, *Ks = sm + SM::kSumsK, *PhiK = Ks, *Vs = sm + SM::kSumsV;
     pdl_launch_dependents();
     pdl_wait();
     const int chunk = blockIdx.x, nh = blockIdx.y, n = nh / H, h = nh % H;
@@ -225,6 +231,7 @@ performer_sums_mma_kernel(const __nv_bfloat16* __restrict__ k, int64_t k_sn, int
     {
         float acc[kFp / 8][4];
         phi_rows<kFp, kDm>(acc, Ks, Ps, warp, lane);
+        __syncthreads();           // phi(k) is written over the K tile: every warp must have read its K rows
 #pragma unroll
         for (int nt = 0; nt < kFp / 8; ++nt) {
 #pragma unroll
@@ -517,10 +524,10 @@ int launch_performer_mma(const void* q, int64_t q_sn, int64_t q_sh, int64_t q_st
     dim3 grid(nchunks, N * H, kSlabs);
     auto ka = performer_sums_mma_kernel<kFp, kDm>;
     auto kc = performer_out_mma_kernel<kFp, kDm>;
-    SEA_CUDA_TRY(cudaFuncSetAttribute(ka, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kBytes), "smem attr");
+    SEA_CUDA_TRY(cudaFuncSetAttribute(ka, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kSumsBytes), "smem attr");
     SEA_CUDA_TRY(cudaFuncSetAttribute(kc, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kBytes), "smem attr");
     using B = __nv_bfloat16;
-    SEA_CUDA_TRY(launch_pdl(ka, grid, dim3(kThreads), (size_t) SM::kBytes, s, (const B*) k, k_sn, k_sh, k_st, (const B*) v, v_sn, v_sh, v_st, pos_emb, proj, ws, H, T, F,
+    SEA_CUDA_TRY(launch_pdl(ka, grid, dim3(kThreads), (size_t) SM::kSumsBytes, s, (const B*) k, k_sn, k_sh, k_st, (const B*) v, v_sn, v_sh, v_st, pos_emb, proj, ws, H, T, F,
                             nchunks), "performer_sums_mma_kernel launch");
     const int64_t stride = (int64_t) kFp * kEx;
     // one exclusive prefix per (n, h, slab): the slabs' chunk slots are laid out [nh][slab][chunk]

@@ -56,3 +56,22 @@ def test_state_dict_keys_match_reference_fixture(sea):
         assert tuple(own[key].shape) == tuple(val.shape), key
     missing, unexpected = mod.load_state_dict(sd, strict=False)
     assert not unexpected
+
+
+def test_caller_block_has_reference_parameter_names_and_no_cpu_path(sea):
+    """SeaOPTAttention keeps the reference's parameter names (perlin_opt.py:300-330, self_attention.py:52) and, like
+    every other entry of the package, refuses CPU tensors instead of falling back."""
+    import pytest
+    import torch
+    import transformers
+    cfg = transformers.BertConfig(hidden_size=64, num_attention_heads=2, max_position_embeddings=16)
+    pc = sea.PerlinAttentionConfig(performer_nb_factor=8, k=4, attention_predictor_length=8, causal=True)
+    blk = sea.SeaOPTAttention(64, 2, cfg, pc).eval()
+    keys = set(blk.state_dict().keys())
+    for name in ('q_proj.weight', 'k_proj.bias', 'v_proj.weight', 'out_proj.weight', 'perlin_self_attention.attention.performer.projection_matrix',
+                 'perlin_self_attention.attention.attention_predictor_cnn.1.module.net.5.module.weight'):
+        assert name in keys, name
+    with pytest.raises(sea.SeaError):
+        blk(torch.zeros(1, 16, 64))
+    with pytest.raises(sea.SeaError):
+        sea.SeaOPTAttention(64, 2, cfg, sea.PerlinAttentionConfig(causal=False))
