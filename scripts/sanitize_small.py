@@ -35,5 +35,23 @@ o6 = mod2(q2, k2, v2, q2, k2, v2, q2, k2, am, None, None)
 # BERT layer
 mod3 = sea.PerlinAttention(cfg2, sea.PerlinAttentionConfig(performer_nb_factor=1, k=k, attention_predictor_length=P, causal=False, k_flatten_dim='batch')).eval().to(DEV)
 o7 = mod3(q2, k2, v2, q2, k2, v2, q2, k2, torch.zeros(N, 1, 1, T, device=DEV, dtype=torch.bfloat16), None, None)
+# other head dims: slab Performer, mma.sync MLP, gather attention (d = 80: 10 pieces per row), query block, DEEPER predictor, caller block
+outs = []
+for (H4, d4, T4, P4, k4) in ((32, 80, 150, 128, 16), (32, 128, 140, 256, 32), (8, 96, 70, 128, 8), (4, 32, 90, 128, 8)):
+    cfg4 = transformers.BertConfig(hidden_size=H4 * d4, num_attention_heads=H4, max_position_embeddings=T4)
+    m4 = sea.PerlinAttention(cfg4, sea.PerlinAttentionConfig(performer_nb_factor=nbf, k=k4, attention_predictor_length=P4, causal=True)).eval().to(DEV)
+    q4 = (torch.randn(N, H4, T4, d4, device=DEV) * d4 ** -0.5).bfloat16(); k4_ = torch.randn(N, H4, T4, d4, device=DEV).bfloat16(); v4 = torch.randn(N, H4, T4, d4, device=DEV).bfloat16()
+    outs.append(m4(q4, k4_, v4, q4, k4_, v4, q4, k4_, None, None, None))
+    outs.append(m4.forward_query_block(q4, k4_, v4, T4 // 3, T4 - 5))
+os.environ['PERLIN_HOTFIX_OPT_DEEPER'] = '1'
+m5 = sea.PerlinAttention(cfg, sea.PerlinAttentionConfig(performer_nb_factor=nbf, k=k, attention_predictor_length=P, causal=True)).eval().to(DEV)
+del os.environ['PERLIN_HOTFIX_OPT_DEEPER']
+outs.append(m5(sl(q, 0, T), sl(kk, 0, T), sl(v, 0, T), sl(q, 0, T), sl(kk, 0, T), sl(v, 0, T), sl(q, 0, T), sl(kk, 0, T), None, None, None))
+blk = sea.SeaOPTAttention(H * d, H, cfg, sea.PerlinAttentionConfig(performer_nb_factor=nbf, k=k, attention_predictor_length=P, causal=True)).eval().to(DEV).bfloat16()
+x = torch.randn(1, T, H * d, device=DEV).bfloat16()
+y, _, past = blk(x, use_cache=True)
+y2, _, past = blk(torch.randn(1, 1, H * d, device=DEV).bfloat16(), past_key_value=past, use_cache=True)
+torch.cuda.synchronize()
+print('new paths ok', [float(x_.context_layer.float().abs().mean()) for x_ in outs], float(y.float().abs().mean()), float(y2.float().abs().mean()))
 torch.cuda.synchronize()
 print('ok', [float(x.context_layer.float().abs().mean()) for x in (o, o2, o3, o5, o6, o7)])

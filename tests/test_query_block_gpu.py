@@ -20,7 +20,9 @@ def _module(sea, H, d, T, P, k, nbf=8):
 
 
 @pytest.mark.parametrize('H,d,T,P,k,dtype,world', [(32, 64, 2048, 256, 64, torch.bfloat16, 4), (4, 64, 1000, 64, 16, torch.bfloat16, 3),
-                                                   (4, 32, 700, 64, 16, torch.float32, 2), (8, 128, 1024, 128, 32, torch.float32, 4)])
+                                                   (4, 32, 700, 64, 16, torch.float32, 2), (8, 128, 1024, 128, 32, torch.float32, 4),
+                                                   # BASELINE configs[4] / [3] head shapes on the tensor-core path for those head dims
+                                                   (32, 128, 2048, 256, 128, torch.bfloat16, 4), (32, 80, 1536, 256, 64, torch.bfloat16, 3)])
 def test_query_blocks_concatenate_to_the_full_prefill(sea, H, d, T, P, k, dtype, world):
     par = importlib.import_module(sea.__name__ + '.parallel')
     m = _module(sea, H, d, T, P, k)
@@ -62,3 +64,31 @@ def test_query_block_argument_checks(sea):
         m.forward_query_block(x, x, x, 128, 128)
     with pytest.raises(sea.SeaError):
         m.forward_query_block(x, x, x, 0, 300)
+
+
+@pytest.mark.parametrize('H,d,T,P,k', [(32, 80, 16384, 256, 64), (32, 128, 8192, 256, 128)])
+def test_long_context_fast_path_equals_csr_path(sea, H, d, T, P, k):
+    """BASELINE configs[3] (OPT-2.7B head shape at its full T = 16384) and a configs[4] point at sizes the CPU oracle cannot reach:
+    the production path (tensor-core Performer / MLP, attention straight from the top-k bits, clamped pixels since T/P = 64 >= k)
+    against the CSR-materialising path of the same module, plus the size-independent properties of the CSR: strictly causal
+    columns, per-row nnz <= H*k + slack, crow monotone."""
+    m = _module(sea, H, d, T, P, k)
+    g = torch.Generator().manual_seed(T + d)
+    q = (torch.randn(1, H, T, d, generator=g) * d ** -0.5).bfloat16().to(DEV)
+    kk = torch.randn(1, H, T, d, generator=g).bfloat16().to(DEV)
+    v = torch.randn(1, H, T, d, generator=g).bfloat16().to(DEV)
+    with torch.no_grad():
+        fast = m(q, kk, v, q, kk, v, q, kk, None, None, None)
+        m.output_attentions = True
+        slow = m(q, kk, v, q, kk, v, q, kk, None, None, None)
+        m.output_attentions = False
+    torch.cuda.synchronize()
+    assert torch.equal(fast.estimated_attention_probs, slow.estimated_attention_probs)
+    torch.testing.assert_close(fast.context_layer.float(), slow.context_layer.float(), rtol=2e-2, atol=2e-2)
+    crow, col = slow.partial_attention_mask.crow_indices()[0], slow.partial_attention_mask.col_indices()[0]
+    nnz_row = crow[1:] - crow[:-1]
+    assert bool((nnz_row >= 0).all()) and int(crow[-1]) == col.numel()
+    assert int(nnz_row.max()) <= H * (k + -(-T // P))                                   # the reference's own max_col_z bound (causal_resize_m_to_t.py:946)
+    rows = torch.repeat_interleave(torch.arange(T, device=DEV), nnz_row)
+    assert bool(((col % T) <= rows).all()) and bool((col // T < H).all())                 # strictly causal, valid head
+    assert torch.isfinite(fast.context_layer.float()).all()
