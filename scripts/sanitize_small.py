@@ -1,5 +1,8 @@
-"""Small end-to-end exercise of the new kernels for compute-sanitizer (memcheck): bf16 prefill (tcgen05 path, block attention in
-both variants), backward, decode steps, BERT layer."""
+"""Small end-to-end exercise of every kernel family on ragged shapes, run natively (a plain smoke of the paths: bf16 prefill on the
+tcgen05 path, block attention in both variants, backward, decode steps, BERT layer, the other head dims, query blocks, the DEEPER
+predictor, the caller block).  compute-sanitizer is not available on the GPU pool, so out-of-bounds WRITES are hunted by
+tests/test_guard_bytes_gpu.py instead (outputs carved out of sentinel-filled buffers, guard bytes checked after the launch) and reads by
+the comparisons with the CPU oracle on the same ragged shapes."""
 import importlib, sys, os, torch, transformers
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sea = importlib.import_module('sea-attention_b200')

@@ -395,3 +395,21 @@ def test_deeper_predictor_matches_reference_fixture(sea, monkeypatch):
             mod(q, kk, v, q, kk, v, q, kk, so.causal_additive_mask(T, torch.float32, N).to(DEV), None, None)
         finally:
             mod.pconfig.use_cache = False
+
+
+@pytest.mark.parametrize('N,H,d,T,P,k', [(4, 32, 64, 1024, 256, 64), (2, 32, 128, 512, 256, 128), (3, 12, 64, 700, 256, 64), (2, 32, 80, 640, 128, 32)])
+def test_batched_forward_equals_per_item_forwards_bf16(sea, N, H, d, T, P, k):
+    """BASELINE configs[2] runs N = 8 items per call: every stage must index the batch dimension like N independent layer calls
+    (the path is independent across N).  Production bf16 path, batched vs item by item."""
+    mod, _ = _random_sd(sea, H, d, T, P, k, 8, seed=11)
+    mod = mod.to(DEV)
+    g = torch.Generator().manual_seed(N + T)
+    q = (torch.randn(N, H, T, d, generator=g) * d ** -0.5).bfloat16().to(DEV)
+    kk = torch.randn(N, H, T, d, generator=g).bfloat16().to(DEV)
+    v = torch.randn(N, H, T, d, generator=g).bfloat16().to(DEV)
+    with torch.no_grad():
+        full = mod(q, kk, v, q, kk, v, q, kk, None, None, None)
+        for n in range(N):
+            one = mod(q[n:n + 1], kk[n:n + 1], v[n:n + 1], q[n:n + 1], kk[n:n + 1], v[n:n + 1], q[n:n + 1], kk[n:n + 1], None, None, None)
+            assert torch.equal(one.estimated_attention_probs[0], full.estimated_attention_probs[n]), n
+            torch.testing.assert_close(one.context_layer[0].float(), full.context_layer[n].float(), rtol=2e-2, atol=2e-2)
