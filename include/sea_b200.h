@@ -83,6 +83,13 @@ SEA_API int sea_csr_count(const uint32_t* mask_bits, void* crow, int idx64,
  * head h starts in row t, head_ptr[..., H] = end of the row; an auxiliary index for sea_sparse_attention_fwd. */
 SEA_API int sea_csr_fill(const uint32_t* mask_bits, const void* crow, void* col, int idx64, int64_t Z, int32_t* head_ptr,
                  int N, int H, int T_DST, int P, int T_SRC, int k, int is_causal, void* stream);
+/* The same two passes for a RIGHT-PADDED non-causal batch: lengths (int32 [N], nullable) = valid tokens of item n, used as the
+ * interpolation width of every row of that item (what the reference's dense path does through the mask cumsum, resize_m_to_t.py:36-47;
+ * its sparse path uses T_SRC regardless, causal_resize_m_to_t.py:955-957), so no column of a padded token is produced. */
+SEA_API int sea_csr_count_len(const uint32_t* mask_bits, void* crow, int idx64,
+                  int N, int H, int T_DST, int P, int T_SRC, int k, int is_causal, const int32_t* lengths, void* stream);
+SEA_API int sea_csr_fill_len(const uint32_t* mask_bits, const void* crow, void* col, int idx64, int64_t Z, int32_t* head_ptr,
+                 int N, int H, int T_DST, int P, int T_SRC, int k, int is_causal, const int32_t* lengths, void* stream);
 
 /* flat_csr_to_dense (ops/kernels/flat_csr_to_dense.py:3-36): out [N,H,T_DST,T_SRC] fp32, zero filled
  * then out[n,h,t,j] = values[n,z] (values == NULL -> 1.0). */
@@ -354,6 +361,13 @@ SEA_API int sea_performer_noncausal_fwd(const void* q, int64_t q_sn, int64_t q_s
                                         const void* v, int64_t v_sn, int64_t v_sh, int64_t v_st,
                                         const float* proj, int dtype, void* ctx, float* workspace,
                                         int N, int H, int T, int D, int F, void* stream);
+/* right-padded batch (attention.py:447-449, 482, 512-514): lengths (int32 [N], nullable) = valid tokens of item n; the identity grid
+ * follows the rank among the valid tokens and v_for_atten is zero on the padded ones (k is NOT masked, like the reference). */
+SEA_API int sea_performer_noncausal_len_fwd(const void* q, int64_t q_sn, int64_t q_sh, int64_t q_st,
+                                            const void* k, int64_t k_sn, int64_t k_sh, int64_t k_st,
+                                            const void* v, int64_t v_sn, int64_t v_sh, int64_t v_st,
+                                            const float* proj, int dtype, void* ctx, float* workspace, const int32_t* lengths,
+                                            int N, int H, int T, int D, int F, void* stream);
 SEA_API int sea_conv3x3_cl(const void* x, const float* weight, const float* bias, void* y, int dtype,
                            int N, int Tin, int Tout, int W, int C, int O, int stride_t, int up, int relu, void* stream);
 SEA_API int sea_bert_tail_fwd(const void* y, int dtype, float* probs, float* scores, int N, int H, int Tin, int Win, int T, int P, void* stream);
@@ -366,6 +380,9 @@ SEA_API int sea_topk_mask_bits_batch_ws(const float* keys, const float* k_per_gr
                                         int N, int H, int T, int P, int group_heads, void* stream);
 SEA_API int sea_bert_avg_fwd(const float* probs, const void* v, int64_t v_sn, int64_t v_sh, int64_t v_st, int dtype, void* avg,
                              int N, int H, int T, int P, int D, void* stream);
+/* the same with per-item token lengths (right-padded batch): the resize width is lengths[n], padded tokens weigh 0 */
+SEA_API int sea_bert_avg_len_fwd(const float* probs, const void* v, int64_t v_sn, int64_t v_sh, int64_t v_st, int dtype, void* avg,
+                                 const int32_t* lengths, int N, int H, int T, int P, int D, void* stream);
 
 #ifdef __cplusplus
 }

@@ -227,6 +227,37 @@ def golden_layer_deeper(name, H, d, T, k, P, nbf, seed_inputs=99):
     print(name, 'written')
 
 
+def golden_layer_bert_padded(name, H, d, T, k, P, nbf, lengths, seed_inputs=2468):
+    """Non-causal (BERT) layer with a RIGHT-PADDED batch: attention_mask [N,1,1,T] is fully negative on the padded tokens of each item
+    (attention.py:401-449, 482, 512-514, 777-778, 837, 1209-1219; dense interpolation width = token length, resize_m_to_t.py:36-47).
+    Dense path only (benchmarking=False): the reference's sparse non-causal path ignores padding in the interpolation
+    (causal_resize_m_to_t.py:955-957, "TODO confirm correctness")."""
+    N = len(lengths)
+    m = rh.build_reference_attention(H, d, T, k, P, nbf, False, k_flatten_dim='batch')
+    g = torch.Generator().manual_seed(seed_inputs)
+    q = torch.randn(N, H, T, d, generator=g)
+    kk = torch.randn(N, H, T, d, generator=g)
+    v = torch.randn(N, H, T, d, generator=g)
+    fmin = float(torch.finfo(torch.float32).min / 2)
+    mask = torch.zeros(N, 1, 1, T)
+    for n, L in enumerate(lengths):
+        mask[n, :, :, L:] = fmin
+    out_d, buf_d = _run_layer(m, q.clone(), kk.clone(), v.clone(), mask, False)       # (the reference masks v in place)
+    sd = {k_: _np(v_) for k_, v_ in m.state_dict().items() if not k_.startswith(_UNUSED)}
+    fx = {'sd.' + k_: v_ for k_, v_ in sd.items()}
+    fx.update(q=_np(q), k=_np(kk), v=_np(v), lengths=np.array(lengths))
+    for b in ('performer_context_layer', 'estimated_attention_score', 'estimated_attention_probs', 'estimated_scales', 'average_context_layer',
+              'partial_context_layer'):
+        if b in buf_d and buf_d[b] is not None:
+            fx['dense.' + b] = _np(buf_d[b]).astype(np.float32)
+    fx['dense.mask_before_interp_alive'] = np.packbits((_np(buf_d['partial_attention_mask_before_interp']) > -1))
+    fx['dense.partial_attention_mask_alive'] = np.packbits((_np(buf_d['partial_attention_mask']) > -1))
+    fx['dense.context_layer'] = _np(out_d.context_layer).astype(np.float32)
+    fx['meta'] = np.array([N, H, d, T, k, P, nbf, 0])
+    np.savez_compressed(os.path.join(GOLDEN, name + '.npz'), **fx)
+    print(name, 'written; buffers', sorted(k_ for k_ in fx if k_.startswith('dense.')))
+
+
 def golden_state_ops():
     """The reference's three stateful decode ops (attention_state.py:43-98 StatefulCausalPerformer, :142-187 StatefulCausalCNN,
     :205-224 StatefulCumAvg) driven exactly as PerlinAttention drives them during a token-by-token decode, on seeded inputs."""
@@ -283,6 +314,8 @@ def main():
         return golden_state_ops()
     if '--skips-only' in sys.argv:
         return golden_layer_query_skips('layer_causal_skips2_h3_t64', H=3, d=32, T=64, k=6, P=16, nbf=4, skips=2)
+    if '--bert-padded-only' in sys.argv:
+        return golden_layer_bert_padded('layer_bert_padded_h4_t64', H=4, d=64, T=64, k=8, P=32, nbf=1, lengths=[64, 45, 23])
     if '--deeper-only' in sys.argv:
         return golden_layer_deeper('layer_causal_deeper_h3_t64', H=3, d=32, T=64, k=6, P=16, nbf=4)
     if '--padded-only' in sys.argv:
@@ -296,6 +329,7 @@ def main():
     golden_layer_query_skips('layer_causal_skips2_h3_t64', H=3, d=32, T=64, k=6, P=16, nbf=4, skips=2)
     golden_layer_deeper('layer_causal_deeper_h3_t64', H=3, d=32, T=64, k=6, P=16, nbf=4)
     if '--with-bert' in sys.argv:
+        golden_layer_bert_padded('layer_bert_padded_h4_t64', H=4, d=64, T=64, k=8, P=32, nbf=1, lengths=[64, 45, 23])
         golden_layer('layer_bert_h4_t64', H=4, d=64, T=64, k=8, P=32, nbf=1, causal=False, k_flatten_dim='batch')
 
 

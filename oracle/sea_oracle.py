@@ -282,7 +282,7 @@ def topk_mask_noncausal(probs: torch.Tensor, k, k_oversample: float, token_lengt
 
 # ----------------------------------------------------------------------------- a8 CSR interpolation
 def resize_from_m_to_t_csr(mask: torch.Tensor, k: int, target_width: Optional[int] = None, is_causal: bool = True,
-                           scale_mode: str = 'ieee'):
+                           scale_mode: str = 'ieee', noncausal_width: Optional[int] = None):
     """causal_resize_m_to_t.py:910-1007 -> scan_col METHOD 1 (:648-762) -> __scan_col_4_compute (:493-572).
     mask [N,H,T_DST,P] 0/1.  Returns (crow [N,T_DST+1] i64, col [N,Z] i64, Z) with Z = max_n nnz_n;
     rows of items with fewer nnz are zero padded at the tail (:669).  Entry order: (t, h, m) then
@@ -297,7 +297,10 @@ def resize_from_m_to_t_csr(mask: torch.Tensor, k: int, target_width: Optional[in
     if is_causal:
         tw = np.arange(1, T_SRC + 1, dtype=np.int64)[-T_DST:]          # :954
     else:
-        tw = np.full((T_SRC,), T_SRC, dtype=np.int64)[-T_DST:]         # :957
+        # :957 uses T_SRC for every row ("TODO confirm correctness" there: the reference's sparse non-causal path ignores padding in
+        # the interpolation).  noncausal_width = the item's token length gives the width its DENSE path uses (resize_m_to_t.py:36-47,
+        # the per-item mask cumsum) -- what a padded non-causal batch needs; None keeps the reference's sparse behaviour.
+        tw = np.full((T_SRC,), T_SRC if noncausal_width is None else int(noncausal_width), dtype=np.int64)[-T_DST:]
     if scale_mode == 'ieee':
         scales = (torch.from_numpy(tw) / P).numpy()                    # :642 int64 / int -> fp32
     elif scale_mode == 'cuda_reciprocal':
@@ -559,12 +562,22 @@ def v_identity_grid(N: int, H: int, T: int, d: int, valid: Optional[torch.Tensor
 
 def perlin_forward_noncausal(sd: Dict[str, torch.Tensor], q, k, v, *, k_top: int, P: int, k_flatten_dim: str = 'batch',
                              k_oversample: float = 1.0, partial_attention_scaler: bool = True, sparse: bool = True,
-                             keep_dense: bool = False) -> Dict[str, torch.Tensor]:
-    """attention.py:333-1359 with `causal=False` (BERT), no padding, context_output_method='mix'."""
+                             keep_dense: bool = False, lengths: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+    """attention.py:333-1359 with `causal=False` (BERT), context_output_method='mix'.  lengths [N] (optional): right-padded batch, item n
+    has lengths[n] real tokens (attention_mask [N,1,1,T] <= -1 on the rest): v and v_for_atten are zeroed on padded tokens (:512-514), the
+    identity grid follows the valid-token rank (:482), the probabilities of padded query rows are zeroed (:777-778), per_item_top_k uses
+    the token length (:837), the interpolation width is the token length (dense path, resize_m_to_t.py:36-47), the average context
+    skips padded tokens (:1209-1219).  Rows of padded queries are not meaningful (the reference leaves them to the caller's masking)."""
     q, k, v = q.float(), k.float(), v.float()
     N, H, T, d = q.shape
     buf: Dict[str, torch.Tensor] = {}
-    v_for_atten = torch.cat([v_identity_grid(N, H, T, d), v], dim=-1)                           # :462-502
+    valid = None
+    if lengths is not None:
+        valid = (torch.arange(T).view(1, T) < lengths.view(N, 1)).float()
+        v = v * valid.view(N, 1, T, 1)
+    v_for_atten = torch.cat([v_identity_grid(N, H, T, d, valid), v], dim=-1)                    # :462-502
+    if valid is not None:
+        v_for_atten = v_for_atten * valid.view(N, 1, T, 1)                                       # :512-514
     pcl = performer_noncausal(q, k, v_for_atten, sd['performer.projection_matrix'])              # :527-534
     buf['performer_context_layer'] = pcl
     t_pred = predictor_enc(torch.cat([pcl, v], dim=-1), sd)                                      # :577-620
@@ -574,13 +587,26 @@ def perlin_forward_noncausal(sd: Dict[str, torch.Tensor], q, k, v, *, k_top: int
     buf['estimated_attention_score'] = score
     probs = torch.softmax(score, dim=-1)                                                         # :670-673
     buf['estimated_attention_probs'] = probs
-    token_length = torch.full((N,), T, dtype=torch.long)
-    mask_m = topk_mask_noncausal(probs, k_top, k_oversample, token_length, k_flatten_dim)        # :833-947
+    token_length = torch.full((N,), T, dtype=torch.long) if lengths is None else lengths.long()
+    if valid is not None:
+        probs = probs * valid.view(N, 1, T, 1)                                                   # :777-778
+    mask_m = topk_mask_noncausal(probs, k_top, k_oversample, token_length, k_flatten_dim,
+                                 dst_valid=None if valid is None else valid)                     # :833-947
     buf['partial_attention_mask_before_interp'] = mask_m
     scales = predictor_dec_scaler(t_pred, sd)
     buf['estimated_scales'] = scales
+    fmin = fp_min_for(torch.float32)
+    amask = torch.zeros(N, 1, 1, T) if valid is None else ((1.0 - valid) * fmin).view(N, 1, 1, T)
     if sparse:
-        crow, col, Z = resize_from_m_to_t_csr(mask_m, k_top, target_width=T, is_causal=False)    # :1025-1027
+        if lengths is None:
+            crow, col, Z = resize_from_m_to_t_csr(mask_m, k_top, target_width=T, is_causal=False)    # :1025-1027
+        else:       # per-item interpolation width = token length (see resize_from_m_to_t_csr)
+            per = [resize_from_m_to_t_csr(mask_m[n:n + 1], k_top, target_width=T, is_causal=False, noncausal_width=int(lengths[n])) for n in range(N)]
+            Z = max(p_[2] for p_ in per)
+            crow = torch.cat([p_[0] for p_ in per], dim=0)
+            col = torch.zeros((N, Z), dtype=torch.long)
+            for n, p_ in enumerate(per):
+                col[n, :p_[2]] = p_[1][0]
         buf['crow_indices'], buf['col_indices'] = crow, col
         s = flat_csr_masked_bmm(q, k, crow, col)
         p = flat_csr_softmax(s, crow, col, H, T)
@@ -591,8 +617,6 @@ def perlin_forward_noncausal(sd: Dict[str, torch.Tensor], q, k, v, *, k_top: int
         if keep_dense:
             buf['partial_attention_mask'] = flat_csr_to_dense(crow, col, torch.ones_like(p), T, H)
     else:
-        fmin = fp_min_for(torch.float32)
-        amask = torch.zeros(N, 1, 1, T)
         pm = resize_from_m_to_t_dense((1.0 - mask_m) * fmin, fmin, amask, target_width=T, is_causal=False, k=k_top, oversampled=k_oversample)
         if keep_dense:
             buf['partial_attention_mask'] = (pm > -1).float()
@@ -602,8 +626,7 @@ def perlin_forward_noncausal(sd: Dict[str, torch.Tensor], q, k, v, *, k_top: int
             p = p * torch.sigmoid(scales[..., 0:1])
         ctx = p @ v
     buf['partial_context_layer_1'] = ctx
-    # :1209-1219: probability-weighted mean of v
-    amask = torch.zeros(N, 1, 1, T)
+    # :1209-1219: probability-weighted mean of v (v is already zero on padded tokens)
     wts = resize_from_m_to_t_dense(probs.mean(-2, keepdim=True), 0.0, amask, target_width=T, is_causal=False)   # [N,H,1,T]
     avg = (v * wts.transpose(-1, -2)).sum(-2, keepdim=True)
     buf['average_context_layer'] = avg

@@ -631,19 +631,35 @@ class PerlinAttention(nn.Module):
         assert attention_mask.shape == (N, 1, 1, T), f'non-causal additive mask must be [N,1,1,T], got {tuple(attention_mask.shape)}'
         if v_for_atten.data_ptr() != v.data_ptr():
             raise SeaError('v_for_atten must alias v (LoRA-in-approximation is not implemented)')
-        if self.check_padding and not bool((attention_mask > -1).all()):
-            raise SeaError('padded batches are not implemented yet (SURVEY 8f-3)')
+        lengths = None
+        if self.check_padding:
+            valid = attention_mask[:, 0, 0, :] > -1                                      # [N,T]
+            if not bool(valid.all()):
+                # right-padded batch (attention.py:401-449): item n has lengths[n] real tokens.  v and v_for_atten are zeroed on the padded
+                # tokens (:512-514; a masked copy here, the reference writes into the caller's v), the identity grid follows the rank among
+                # the valid tokens (:482), the probabilities of padded query rows are zeroed before the top-k (:777-778), the interpolation
+                # width is the token length (the reference's dense path, resize_m_to_t.py:36-47), the average context skips padded tokens.
+                lengths = valid.sum(-1).to(torch.int32)
+                if not bool((valid == (torch.arange(T, device=q.device).view(1, T) < lengths.view(N, 1))).all()):
+                    raise SeaError('non-causal padding must be right padding (valid tokens first); other masks are not implemented')
+                if bool((lengths < 1).any()):
+                    raise SeaError('a batch item without any valid token')
+                v = v * valid.view(N, 1, T, 1).to(v.dtype)
         P = pc.attention_predictor_length
         w = self._weights_fp32()
         S, W = self.attention_predictor_dec_row_splits, P // self.attention_predictor_dec_row_down_scale
-        ctx = ops.performer_noncausal(q_for_atten, k_for_atten, v, w['proj'])
+        ctx = ops.performer_noncausal(q_for_atten, k_for_atten, v, w['proj'], lengths=lengths)
         cnn_in, scales, _ = ops.predictor_mlp(ctx, v, w, S, W)                      # [N,T,W,4H], no leading LayerNorm
         y = ops.conv3x3_cl(cnn_in, w['conv1_w'], w['conv1_b'], stride_t=2, relu=True)
         y = ops.conv3x3_cl(y, w['conv2_w'], w['conv2_b'], relu=True)
         y = ops.conv3x3_cl(y, w['conv3_w'], w['conv3_b'], up=2, relu=False)       # nearest (2,1) upsample folded into the conv
         probs, _ = ops.bert_tail(y, T, P)
         kf = float(pc.k) * float(pc.k_oversample) * P
-        tl_ = torch.full((N,), T, dtype=torch.long, device=q.device)
+        tl_ = torch.full((N,), T, dtype=torch.long, device=q.device) if lengths is None else lengths.long()
+        row_valid = None
+        if lengths is not None:
+            row_valid = valid
+            probs = probs * valid.view(N, 1, T, 1).to(probs.dtype)                       # :777-778
         mode = pc.k_flatten_dim if pc.k_flatten else 'query'
         if mode == 'batch':
             kpi = torch.clamp_min(torch.round(tl_ * H * (kf / tl_)), 1)                                         # attention.py:837,856,866
@@ -653,20 +669,21 @@ class PerlinAttention(nn.Module):
             bits = ops.topk_mask_bits_batch(probs, kpi, group_heads=1)
         elif mode == 'query':
             kpi = torch.clamp_min(torch.round(kf / tl_), 1)                                                      # :853
-            bits = ops.topk_mask_bits(probs, kpi, 'query')
+            bits = ops.topk_mask_bits(probs, kpi, 'query', row_valid=row_valid)
         elif mode == 'causal_batch':
             kpi = torch.clamp_min(torch.round(H * (kf / tl_)), 1).view(N, 1).expand(N, T).reshape(-1)             # :846
-            bits = ops.topk_mask_bits(probs, kpi, 'causal_batch')
+            bits = ops.topk_mask_bits(probs, kpi, 'causal_batch', row_valid=row_valid)
         else:
             raise SeaError(f"k_flatten_dim='{mode}' is not implemented")
-        avg = ops.bert_avg(probs, v)
+        avg = ops.bert_avg(probs, v, lengths=lengths)
         partial_probs = partial_mask = None
-        if not self.output_attentions and ops.attention_bits_supported(q.dtype, d, P):
+        if lengths is None and not self.output_attentions and ops.attention_bits_supported(q.dtype, d, P):
             context = ops.sparse_attention_from_bits(bits, q_for_score, k_for_score, v, scales, avg, P, pc.k,
                                                      use_scaler=pc.partial_attention_scaler, is_causal=False)
         else:
             # exact-size CSR (one host read of the nnz, like the reference's own .item(), causal_resize_m_to_t.py:667)
-            crow, col, Z, head_ptr = ops.csr_from_bits(bits, H, P, pc.k, T, is_causal=False, index_dtype=torch.int32, want_head_ptr=True)
+            crow, col, Z, head_ptr = ops.csr_from_bits(bits, H, P, pc.k, T, is_causal=False, index_dtype=torch.int32, want_head_ptr=True,
+                                                       lengths=lengths)
             context, pvals = ops.sparse_attention(crow, col, q_for_score, k_for_score, v, scales, avg,
                                                   use_scaler=pc.partial_attention_scaler, want_probs=self.output_attentions, head_ptr=head_ptr)
             if self.output_attentions:

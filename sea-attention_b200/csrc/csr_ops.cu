@@ -109,11 +109,12 @@ constexpr int kCsrThreads = 256;
 template <typename IdxT>
 __global__ void __launch_bounds__(kCsrThreads)
 csr_count_kernel(const uint32_t* __restrict__ bits, IdxT* __restrict__ crow,
-                 int N, int H, int T_DST, int P, int T_SRC, int k, int is_causal, int words_per_row) {
+                 int N, int H, int T_DST, int P, int T_SRC, int k, int is_causal, int words_per_row, const int32_t* __restrict__ lengths) {
     __shared__ int wsum[kCsrThreads / 32];
     const int64_t row = blockIdx.x;
     const int n = (int) (row / T_DST), t = (int) (row % T_DST);
-    const int L = is_causal ? (T_SRC - T_DST + t + 1) : T_SRC;
+    // non-causal: the interpolation width is T_SRC, or the item's token length for a right-padded batch (resize_m_to_t.py:36-47)
+    const int L = is_causal ? (T_SRC - T_DST + t + 1) : (lengths ? max(1, min(lengths[n], T_SRC)) : T_SRC);
     const float s = __fdiv_rn((float) L, (float) P);
     const uint32_t* rb = bits + row * words_per_row;
     int cnt = 0;
@@ -171,13 +172,14 @@ crow_scan_kernel(IdxT* __restrict__ crow, int T_DST) {
 template <typename IdxT>
 __global__ void __launch_bounds__(kCsrThreads)
 csr_fill_kernel(const uint32_t* __restrict__ bits, const IdxT* __restrict__ crow, IdxT* __restrict__ col, int64_t Z,
-                int32_t* __restrict__ head_ptr, int N, int H, int T_DST, int P, int T_SRC, int k, int is_causal, int words_per_row) {
+                int32_t* __restrict__ head_ptr, int N, int H, int T_DST, int P, int T_SRC, int k, int is_causal, int words_per_row,
+                const int32_t* __restrict__ lengths) {
     __shared__ int wsum[kCsrThreads / 32];
     __shared__ int carry_s;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int64_t row = blockIdx.x;
     const int n = (int) (row / T_DST), t = (int) (row % T_DST);
-    const int L = is_causal ? (T_SRC - T_DST + t + 1) : T_SRC;
+    const int L = is_causal ? (T_SRC - T_DST + t + 1) : (lengths ? max(1, min(lengths[n], T_SRC)) : T_SRC);
     const float s = __fdiv_rn((float) L, (float) P);
     const uint32_t* rb = bits + row * words_per_row;
     IdxT* out = col + (int64_t) n * Z;
@@ -517,14 +519,20 @@ int sea_mask_bits_to_float(const uint32_t* mask_bits, float* mask, int N, int H,
 
 int sea_csr_count(const uint32_t* mask_bits, void* crow, int idx64, int N, int H, int T_DST, int P, int T_SRC, int k,
                   int is_causal, void* stream) {
+    return sea_csr_count_len(mask_bits, crow, idx64, N, H, T_DST, P, T_SRC, k, is_causal, nullptr, stream);
+}
+
+int sea_csr_count_len(const uint32_t* mask_bits, void* crow, int idx64, int N, int H, int T_DST, int P, int T_SRC, int k,
+                      int is_causal, const int32_t* lengths, void* stream) {
     SEA_CHECK_ARG(mask_bits && crow, "sea_csr_count: null pointer");
+    SEA_CHECK_ARG(lengths == nullptr || !is_causal, "sea_csr_count: per-item lengths belong to the non-causal interpolation");
     SEA_CHECK_ARG(N > 0 && H > 0 && T_DST > 0 && P > 0 && T_SRC >= T_DST && k > 0, "sea_csr_count: bad shape");
     SEA_CHECK_ARG((int64_t) H * T_SRC < (1ll << 24), "sea_csr_count: H*T_SRC must stay below 2^24 (fp32-exact column ids, as in the reference)");
     const int wpr = (H * P + 31) >> 5;
     const int64_t rows = (int64_t) N * T_DST;
     cudaStream_t s = (cudaStream_t) stream;
     SEA_DISPATCH_IDX(idx64, I, {
-        csr_count_kernel<I><<<(unsigned) rows, kCsrThreads, 0, s>>>(mask_bits, (I*) crow, N, H, T_DST, P, T_SRC, k, is_causal, wpr);
+        csr_count_kernel<I><<<(unsigned) rows, kCsrThreads, 0, s>>>(mask_bits, (I*) crow, N, H, T_DST, P, T_SRC, k, is_causal, wpr, lengths);
         SEA_CHECK_LAUNCH("csr_count_kernel");
         crow_scan_kernel<I><<<N, 1024, 0, s>>>((I*) crow, T_DST);
         SEA_CHECK_LAUNCH("crow_scan_kernel");
@@ -543,14 +551,20 @@ int sea_crow_scan(void* crow, int idx64, int N, int T_DST, void* stream) {
 
 int sea_csr_fill(const uint32_t* mask_bits, const void* crow, void* col, int idx64, int64_t Z, int32_t* head_ptr, int N, int H, int T_DST,
                  int P, int T_SRC, int k, int is_causal, void* stream) {
+    return sea_csr_fill_len(mask_bits, crow, col, idx64, Z, head_ptr, N, H, T_DST, P, T_SRC, k, is_causal, nullptr, stream);
+}
+
+int sea_csr_fill_len(const uint32_t* mask_bits, const void* crow, void* col, int idx64, int64_t Z, int32_t* head_ptr, int N, int H, int T_DST,
+                     int P, int T_SRC, int k, int is_causal, const int32_t* lengths, void* stream) {
     SEA_CHECK_ARG(mask_bits && crow && (col || Z == 0), "sea_csr_fill: null pointer");
+    SEA_CHECK_ARG(lengths == nullptr || !is_causal, "sea_csr_fill: per-item lengths belong to the non-causal interpolation");
     SEA_CHECK_ARG(N > 0 && H > 0 && T_DST > 0 && P > 0 && T_SRC >= T_DST && k > 0 && Z >= 0, "sea_csr_fill: bad shape");
     SEA_CHECK_ARG(head_ptr == nullptr || (P % 32) == 0, "sea_csr_fill: head_ptr needs P %% 32 == 0");
     const int wpr = (H * P + 31) >> 5;
     const int64_t rows = (int64_t) N * T_DST;
     SEA_DISPATCH_IDX(idx64, I, {
         csr_fill_kernel<I><<<(unsigned) rows, kCsrThreads, 0, (cudaStream_t) stream>>>(
-            mask_bits, (const I*) crow, (I*) col, Z, head_ptr, N, H, T_DST, P, T_SRC, k, is_causal, wpr);
+            mask_bits, (const I*) crow, (I*) col, Z, head_ptr, N, H, T_DST, P, T_SRC, k, is_causal, wpr, lengths);
         SEA_CHECK_LAUNCH("csr_fill_kernel");
     });
     return SEA_OK;

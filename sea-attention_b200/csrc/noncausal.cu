@@ -16,7 +16,8 @@ constexpr int kNcThreads = 256;
 constexpr int kNcRows = 32;       // token rows per CTA tile
 
 // hat-function value of the grid-sampled identity (closed form of F.grid_sample(eye, bilinear, align_corners=True))
-__device__ __forceinline__ float v_identity(int t, int T, int c, int D) {
+__device__ __forceinline__ float v_identity(int t, int T, int c, int D) {      // T = valid tokens of the item; padded tokens (t >= T) give 0
+    if (t >= T) return 0.f;
     const float y_norm = ((float) t / (((float) T - 1.0f) + 1e-8f)) * 2.0f - 1.0f;      // (cumsum-1)/((sum-1)+1e-8)*2-1
     const float ypix = (y_norm + 1.0f) * 0.5f * (float) (D - 1);
     if (ypix < 0.f || ypix > (float) (D - 1)) return 0.f;
@@ -26,6 +27,7 @@ __device__ __forceinline__ float v_identity(int t, int T, int c, int D) {
 struct NcPerfDims {
     int N, H, T, D, F, Fp, E, nchunks;
     int64_t slot;      // floats per chunk partial: Fp*E + Fp
+    const int32_t* lengths;   // [N] valid tokens per item of a right-padded batch (attention.py:482, 512-514), or nullptr
 };
 
 // pass 1: per-(n,h) maximum of d^-1/4 k . P^T over (T, F) -- the stabiliser of the key features
@@ -89,7 +91,8 @@ nc_ksum_kernel(const T* __restrict__ k, int64_t k_sn, int64_t k_sh, int64_t k_st
     for (int idx = threadIdx.x; idx < kNcRows * E; idx += kNcThreads) {
         int r = idx / E, c = idx % E;
         float val = 0.f;
-        if (r < nv) val = c < D ? v_identity(r0 + r, dm.T, c, D) : to_f32(vb[(int64_t) (r0 + r) * v_st + (c - D)]);
+        const int len = dm.lengths ? min(dm.lengths[n], dm.T) : dm.T;      // v_for_atten (identity part AND v part) is zero on padded tokens
+        if (r < nv && r0 + r < len) val = c < D ? v_identity(r0 + r, len, c, D) : to_f32(vb[(int64_t) (r0 + r) * v_st + (c - D)]);
         v2[idx] = val;
     }
     __syncthreads();
@@ -582,7 +585,7 @@ tkb_bits_kernel(const float* __restrict__ keys, const uint32_t* __restrict__ ws,
 template <typename T>
 __global__ void __launch_bounds__(256)
 bert_avg_kernel(const float* __restrict__ probs, const T* __restrict__ v, int64_t v_sn, int64_t v_sh, int64_t v_st,
-                T* __restrict__ avg, int H, int Tn, int P, int D) {
+                T* __restrict__ avg, int H, int Tn, int P, int D, const int32_t* __restrict__ lengths) {
     extern __shared__ __align__(16) float smem[];
     float* pm = smem;             // [P]
     float* part = pm + P;         // [8][D]
@@ -596,12 +599,13 @@ bert_avg_kernel(const float* __restrict__ probs, const T* __restrict__ v, int64_
     __syncthreads();
     const T* vb = v + (int64_t) n * v_sn + (int64_t) h * v_sh;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int L = lengths ? max(1, min(lengths[n], Tn)) : Tn;      // right-padded batch: columns >= L read the fill value 0 and v is 0 there
     for (int c = lane; c < D; c += 32) {
         float s = 0.f;
-        for (int j = wid; j < Tn; j += 8) {
-            // floor(((cs - 1) + 0.5) / L * P - 1e-4), cs = j + 1, L = T   (resize_m_to_t.py:46)
+        for (int j = wid; j < L; j += 8) {
+            // floor(((cs - 1) + 0.5) / L * P - 1e-4), cs = j + 1, L = valid tokens   (resize_m_to_t.py:36-47)
             const float a = __fadd_rn(__fsub_rn((float) (j + 1), 1.0f), 0.5f);
-            int idx = (int) floorf(__fsub_rn(__fmul_rn(__fdiv_rn(a, (float) Tn), (float) P), 1e-4f));
+            int idx = (int) floorf(__fsub_rn(__fmul_rn(__fdiv_rn(a, (float) L), (float) P), 1e-4f));
             idx = max(0, min(idx, P - 1));
             s = fmaf(pm[idx], to_f32(vb[(int64_t) j * v_st + c]), s);
         }
@@ -622,6 +626,7 @@ static NcPerfDims nc_dims(int N, int H, int T, int D, int F) {
     dm.E = 2 * D;
     dm.nchunks = (T + kNcRows - 1) / kNcRows;
     dm.slot = (int64_t) dm.Fp * dm.E + dm.Fp;
+    dm.lengths = nullptr;
     return dm;
 }
 
@@ -642,9 +647,19 @@ int sea_performer_noncausal_fwd(const void* q, int64_t q_sn, int64_t q_sh, int64
                                 const void* v, int64_t v_sn, int64_t v_sh, int64_t v_st,
                                 const float* proj, int dtype, void* ctx, float* workspace,
                                 int N, int H, int T, int D, int F, void* stream) {
+    return sea_performer_noncausal_len_fwd(q, q_sn, q_sh, q_st, k, k_sn, k_sh, k_st, v, v_sn, v_sh, v_st, proj, dtype, ctx, workspace, nullptr,
+                                           N, H, T, D, F, stream);
+}
+
+int sea_performer_noncausal_len_fwd(const void* q, int64_t q_sn, int64_t q_sh, int64_t q_st,
+                                    const void* k, int64_t k_sn, int64_t k_sh, int64_t k_st,
+                                    const void* v, int64_t v_sn, int64_t v_sh, int64_t v_st,
+                                    const float* proj, int dtype, void* ctx, float* workspace, const int32_t* lengths,
+                                    int N, int H, int T, int D, int F, void* stream) {
     SEA_CHECK_ARG(q && k && v && proj && ctx && workspace, "sea_performer_noncausal_fwd: null pointer");
     SEA_CHECK_ARG(N > 0 && H > 0 && T > 0 && D > 0 && F > 0 && (D & 3) == 0 && (int64_t) N * H <= 65535, "sea_performer_noncausal_fwd: bad shape");
     NcPerfDims dm = nc_dims(N, H, T, D, F);
+    dm.lengths = lengths;
     const size_t sm1 = ((size_t) D * dm.Fp + (size_t) kNcRows * D) * 4;
     const size_t sm2 = ((size_t) D * dm.Fp + (size_t) kNcRows * D + kNcRows + (size_t) dm.Fp * kNcRows + (size_t) kNcRows * dm.E) * 4;
     const size_t regionA = (size_t) D * dm.Fp > (size_t) dm.Fp * dm.E + dm.Fp ? (size_t) D * dm.Fp : (size_t) dm.Fp * dm.E + dm.Fp;
@@ -763,10 +778,15 @@ int sea_topk_mask_bits_batch_ws(const float* keys, const float* k_per_group, uin
 
 int sea_bert_avg_fwd(const float* probs, const void* v, int64_t v_sn, int64_t v_sh, int64_t v_st, int dtype, void* avg,
                      int N, int H, int T, int P, int D, void* stream) {
+    return sea_bert_avg_len_fwd(probs, v, v_sn, v_sh, v_st, dtype, avg, nullptr, N, H, T, P, D, stream);
+}
+
+int sea_bert_avg_len_fwd(const float* probs, const void* v, int64_t v_sn, int64_t v_sh, int64_t v_st, int dtype, void* avg, const int32_t* lengths,
+                         int N, int H, int T, int P, int D, void* stream) {
     SEA_CHECK_ARG(probs && v && avg && N > 0 && H > 0 && T > 0 && P > 0 && D > 0, "sea_bert_avg_fwd: bad argument");
     const size_t smem = ((size_t) P + 8 * (size_t) D) * 4;
     SEA_DISPATCH_DTYPE(dtype, T_, {
-        bert_avg_kernel<T_><<<N * H, 256, smem, (cudaStream_t) stream>>>(probs, (const T_*) v, v_sn, v_sh, v_st, (T_*) avg, H, T, P, D);
+        bert_avg_kernel<T_><<<N * H, 256, smem, (cudaStream_t) stream>>>(probs, (const T_*) v, v_sn, v_sh, v_st, (T_*) avg, H, T, P, D, lengths);
         SEA_CHECK_LAUNCH("bert_avg_kernel");
     });
     return SEA_OK;

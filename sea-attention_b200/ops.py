@@ -114,12 +114,25 @@ def topk_mask_bits(probs: torch.Tensor, k_per_group: torch.Tensor, group_mode: s
 
 
 # --------------------------------------------------------------------------------------------- a8
+def _lengths_arg(lengths, N, device):
+    if lengths is None:
+        return None
+    ln = lengths.reshape(-1).to(device=device, dtype=torch.int32).contiguous()
+    if ln.numel() != N:
+        raise SeaError(f'lengths must hold one token count per batch item ({N}), got {ln.numel()}')
+    return ln
+
+
 def csr_from_bits(bits: torch.Tensor, H: int, P: int, k: int, T_SRC: int, is_causal: bool = True,
-                  index_dtype=torch.int64, z_alloc: Optional[int] = None, want_head_ptr: bool = False, crow_counts=None):
+                  index_dtype=torch.int64, z_alloc: Optional[int] = None, want_head_ptr: bool = False, crow_counts=None, lengths=None):
     """bit mask -> (crow, col, Z).  z_alloc=None reads the exact nnz back (one host sync, like the
-    reference's `.item()` at causal_resize_m_to_t.py:667); an int skips the sync and over-allocates."""
+    reference's `.item()` at causal_resize_m_to_t.py:667); an int skips the sync and over-allocates.
+    lengths (non-causal only): valid tokens per item of a right-padded batch = the interpolation width of that item's rows."""
     N, T_DST, _ = bits.shape
     idx64 = 1 if index_dtype == torch.int64 else 0
+    ln = _lengths_arg(lengths, N, bits.device)
+    if ln is not None and is_causal:
+        raise SeaError('csr_from_bits: per-item lengths belong to the non-causal interpolation')
     if crow_counts is not None:      # per-row counts already produced by the fused predictor tail: only scan them
         crow = crow_counts
         if crow.dtype != index_dtype:
@@ -127,12 +140,12 @@ def csr_from_bits(bits: torch.Tensor, H: int, P: int, k: int, T_SRC: int, is_cau
         _lib.call('sea_crow_scan', crow.data_ptr(), idx64, N, T_DST, _stream())
     else:
         crow = torch.empty((N, T_DST + 1), dtype=index_dtype, device=bits.device)
-        _lib.call('sea_csr_count', bits.data_ptr(), crow.data_ptr(), idx64, N, H, T_DST, P, T_SRC, int(k), int(is_causal), _stream())
+        _lib.call('sea_csr_count_len', bits.data_ptr(), crow.data_ptr(), idx64, N, H, T_DST, P, T_SRC, int(k), int(is_causal), _p(ln), _stream())
     Z = int(crow[:, -1].max().item()) if z_alloc is None else int(z_alloc)
     col = torch.empty((N, Z), dtype=index_dtype, device=bits.device)
     hp = torch.empty((N, T_DST, H + 1), dtype=torch.int32, device=bits.device) if (want_head_ptr and P % 32 == 0) else None
-    _lib.call('sea_csr_fill', bits.data_ptr(), crow.data_ptr(), col.data_ptr(), idx64, Z, _p(hp), N, H, T_DST, P, T_SRC, int(k),
-              int(is_causal), _stream())
+    _lib.call('sea_csr_fill_len', bits.data_ptr(), crow.data_ptr(), col.data_ptr(), idx64, Z, _p(hp), N, H, T_DST, P, T_SRC, int(k),
+              int(is_causal), _p(ln), _stream())
     if want_head_ptr:
         return crow, col, Z, hp
     return crow, col, Z
@@ -640,8 +653,8 @@ def attention_bits_supported(dtype, D: int, P: int) -> bool:
 
 
 # --------------------------------------------------------------------------------------------- non-causal (BERT)
-def performer_noncausal(q, k, v, proj):
-    """a2'+a3': cat(grid-sampled identity, v) + FAVOR+ Performer -> ctx [N,H,T,2D]."""
+def performer_noncausal(q, k, v, proj, lengths=None):
+    """a2'+a3': cat(grid-sampled identity, v) + FAVOR+ Performer -> ctx [N,H,T,2D].  lengths: valid tokens per item (right-padded batch)."""
     _cuda(q, k, v, proj)
     N, H, T, D = q.shape
     F = proj.shape[0]
@@ -649,8 +662,9 @@ def performer_noncausal(q, k, v, proj):
     pj = proj.float().contiguous()
     ctx = torch.empty((N, H, T, 2 * D), dtype=q.dtype, device=q.device)
     ws = torch.empty((_lib.load().sea_performer_noncausal_workspace_floats(N, H, T, D, F),), dtype=torch.float32, device=q.device)
-    _lib.call('sea_performer_noncausal_fwd', q.data_ptr(), q.stride(0), q.stride(1), q.stride(2), k.data_ptr(), k.stride(0), k.stride(1),
-              k.stride(2), v.data_ptr(), v.stride(0), v.stride(1), v.stride(2), pj.data_ptr(), _dtype_code(q), ctx.data_ptr(), ws.data_ptr(),
+    ln = _lengths_arg(lengths, N, q.device)
+    _lib.call('sea_performer_noncausal_len_fwd', q.data_ptr(), q.stride(0), q.stride(1), q.stride(2), k.data_ptr(), k.stride(0), k.stride(1),
+              k.stride(2), v.data_ptr(), v.stride(0), v.stride(1), v.stride(2), pj.data_ptr(), _dtype_code(q), ctx.data_ptr(), ws.data_ptr(), _p(ln),
               N, H, T, D, F, _stream())
     return ctx
 
@@ -699,15 +713,16 @@ def topk_mask_bits_batch(probs, k_per_item, single_cta: bool = False, group_head
     return bits
 
 
-def bert_avg(probs, v):
-    """a13': probability-weighted mean of v -> [N,H,1,D] (dtype of v)."""
+def bert_avg(probs, v, lengths=None):
+    """a13': probability-weighted mean of v -> [N,H,1,D] (dtype of v).  lengths: valid tokens per item (right-padded batch)."""
     _cuda(probs, v)
     N, H, T, P = probs.shape
     D = v.shape[-1]
     v = _inner_contig(v)
     avg = torch.empty((N, H, 1, D), dtype=v.dtype, device=v.device)
-    _lib.call('sea_bert_avg_fwd', probs.contiguous().data_ptr(), v.data_ptr(), v.stride(0), v.stride(1), v.stride(2), _dtype_code(v), avg.data_ptr(),
-              N, H, T, P, D, _stream())
+    ln = _lengths_arg(lengths, N, v.device)
+    _lib.call('sea_bert_avg_len_fwd', probs.contiguous().data_ptr(), v.data_ptr(), v.stride(0), v.stride(1), v.stride(2), _dtype_code(v), avg.data_ptr(),
+              _p(ln), N, H, T, P, D, _stream())
     return avg
 
 

@@ -157,3 +157,60 @@ def test_bert_layer_matches_oracle(sea, mode):
     out2 = mod(qb, kb, vb, qb, kb, vb, qb, kb, torch.zeros(N, 1, 1, T, device=DEV, dtype=torch.bfloat16), None, None)
     assert out2.context_layer.dtype == torch.bfloat16 and out2.partial_attention_mask is None
     assert float((out2.context_layer.float().cpu() - b['context_layer']).abs().mean()) < 3e-2
+
+
+def _padded_mask(lengths, T, dtype=torch.float32):
+    fmin = torch.finfo(torch.float16).min / 2 if dtype != torch.float32 else torch.finfo(torch.float32).min / 2
+    mask = torch.zeros(len(lengths), 1, 1, T, dtype=dtype)
+    for n, L in enumerate(lengths):
+        mask[n, :, :, L:] = fmin
+    return mask
+
+
+def test_bert_padded_batch_matches_reference_fixture_fp32(sea):
+    """Right-padded non-causal batch (attention.py:401-449, 482, 512-514, 777-778, 837, 1209-1219) against the unmodified
+    reference's dense path (tests/golden/layer_bert_padded_h4_t64.npz, lengths 64 / 45 / 23 of T = 64) on the valid query rows, and
+    against the oracle's sparse branch bit for bit on the CSR."""
+    g, m, sd = golden_layer('layer_bert_padded_h4_t64')
+    N, H, T, P, d, k = m['N'], m['H'], m['T'], m['P'], m['d'], m['k']
+    lengths = [int(x) for x in g['lengths']]
+    mod = _bert_module(sea, m, sd)
+    mod.output_attentions = True
+    q, kk, v = (torch.from_numpy(g[x]) for x in 'qkv')
+    v_in = v.clone().to(DEV)
+    out = mod(q.to(DEV), kk.to(DEV), v_in, q.to(DEV), kk.to(DEV), v_in, q.to(DEV), kk.to(DEV), _padded_mask(lengths, T).to(DEV), None, None)
+    assert torch.equal(v_in.cpu(), v)                                            # the caller's v is not modified (a masked copy is used)
+    valid = torch.arange(T).view(1, T) < torch.tensor(lengths).view(N, 1)
+    rows4, rows3 = valid.view(N, 1, T, 1), valid.view(N, T, 1)
+    ref_probs = torch.from_numpy(g['dense.estimated_attention_probs'])
+    torch.testing.assert_close(out.estimated_attention_probs.cpu() * rows4, ref_probs * rows4, rtol=2e-3, atol=1e-6)
+    b = so.perlin_forward_noncausal(sd, q, kk, v, k_top=k, P=P, sparse=True, keep_dense=True, lengths=torch.tensor(lengths))
+    pm = out.partial_attention_mask
+    crow, col = pm.crow_indices().cpu(), pm.col_indices().cpu()
+    mine = so.flat_csr_to_dense(crow.long(), col.long(), torch.ones(col.shape), T, H).numpy().astype(bool)
+    theirs = b['partial_attention_mask'].numpy().astype(bool)
+    vt = rows4.expand(N, H, T, T).numpy()
+    agree = float(((mine == theirs) | ~vt).mean())
+    assert agree >= 0.999, agree
+    for n in range(N):                                                           # no column of a padded token
+        nnz = int(crow[n, -1])
+        assert nnz > 0 and int((col[n, :nnz] % T).max()) < lengths[n]
+    same = torch.from_numpy(((mine == theirs) | ~vt).all(axis=(1, 3))) & valid
+    assert float(same.float().sum() / valid.float().sum()) > 0.9
+    ref_ctx = torch.from_numpy(g['dense.context_layer'])
+    # rows whose interpolated mask equals the reference dense path's: same context
+    dense_alive = np.unpackbits(g['dense.partial_attention_mask_alive'])[:N * H * T * T].reshape(N, H, T, T).astype(bool)
+    same_ref = torch.from_numpy(((mine == dense_alive) | ~vt).all(axis=(1, 3))) & valid
+    assert float(same_ref.float().sum() / valid.float().sum()) > 0.9
+    torch.testing.assert_close(out.context_layer.cpu()[same_ref], ref_ctx[same_ref], rtol=1e-3, atol=3e-5)
+    torch.testing.assert_close(out.context_layer.cpu()[same], b['context_layer'][same], rtol=1e-3, atol=3e-5)
+    # bf16 runs the same path; a mask that is not right padding is refused
+    mod.output_attentions = False
+    qb, kb, vb = q.bfloat16().to(DEV), kk.bfloat16().to(DEV), v.bfloat16().to(DEV)
+    out2 = mod(qb, kb, vb, qb, kb, vb, qb, kb, _padded_mask(lengths, T, torch.bfloat16).to(DEV), None, None)
+    d2 = (out2.context_layer.float().cpu() - ref_ctx).abs() * rows3
+    assert float((d2 > 5e-2 + 5e-2 * ref_ctx.abs()).float().mean()) < 0.03
+    bad = _padded_mask(lengths, T)
+    bad[1, :, :, 3] = bad[1, :, :, -1]
+    with pytest.raises(sea.SeaError):
+        mod(qb, kb, vb, qb, kb, vb, qb, kb, bad.to(DEV).bfloat16(), None, None)

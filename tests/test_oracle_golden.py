@@ -259,3 +259,40 @@ def test_deeper_cnn_layer_matches_reference_fixture():
     same = torch.from_numpy((mine == ref_alive).all(axis=(1, 3)))
     assert same.float().mean() > 0.5
     torch.testing.assert_close(b['context_layer'][same], torch.from_numpy(g['dense.context_layer'])[same], rtol=1e-3, atol=2e-5)
+
+
+def test_bert_padded_batch_oracle_matches_reference():
+    """Right-padded non-causal batch (lengths 64 / 45 / 23 of T = 64) against the unmodified reference's dense path: every float buffer,
+    the top-k mask, the interpolated mask and the context -- on the VALID query rows (the reference leaves the rows of padded
+    queries to the caller's masking).  The oracle's sparse branch (CSR interpolation with the token length as width) is then held
+    to its own dense branch on those rows."""
+    g, m, sd = golden_layer('layer_bert_padded_h4_t64')
+    N, H, T, P, d = m['N'], m['H'], m['T'], m['P'], m['d']
+    lengths = torch.from_numpy(g['lengths']).long()
+    q, k, v = (torch.from_numpy(g[x]) for x in 'qkv')
+    valid = torch.arange(T).view(1, T) < lengths.view(N, 1)                                   # [N,T]
+    rows4 = valid.view(N, 1, T, 1)
+    bd = so.perlin_forward_noncausal(sd, q, k, v, k_top=m['k'], P=P, sparse=False, keep_dense=True, lengths=lengths)
+    for key in ['performer_context_layer', 'estimated_attention_score', 'estimated_scales']:
+        ref = torch.from_numpy(g['dense.' + key])
+        torch.testing.assert_close(bd[key] * rows4, ref * rows4, rtol=1e-3, atol=2e-5, msg=key)
+    torch.testing.assert_close(bd['average_context_layer'], torch.from_numpy(g['dense.average_context_layer']), rtol=1e-3, atol=2e-5)
+    alive = _bits(g, 'dense.mask_before_interp_alive', (N, H, T, P)).astype(bool)
+    mine = bd['partial_attention_mask_before_interp'].numpy().astype(bool)
+    v4 = rows4.expand(N, H, T, P).numpy()
+    assert np.array_equal(alive & v4, mine & v4)
+    dense_alive = _bits(g, 'dense.partial_attention_mask_alive', (N, H, T, T)).astype(bool)
+    vt = rows4.expand(N, H, T, T).numpy()
+    assert np.array_equal(dense_alive & vt, bd['partial_attention_mask'].numpy().astype(bool) & vt)
+    ref_ctx = torch.from_numpy(g['dense.context_layer'])
+    rows3 = valid.view(N, T, 1)
+    torch.testing.assert_close(bd['context_layer'] * rows3, ref_ctx * rows3, rtol=1e-3, atol=2e-5)
+    # sparse branch: same rows, same context (the two interpolation rules agree up to exact .5 pixel edges)
+    bs = so.perlin_forward_noncausal(sd, q, k, v, k_top=m['k'], P=P, sparse=True, keep_dense=True, lengths=lengths)
+    same = torch.from_numpy((bs['partial_attention_mask'].numpy().astype(bool) == bd['partial_attention_mask'].numpy().astype(bool)).all(axis=(1, 3))) & valid
+    assert float(same.float().sum() / valid.float().sum()) > 0.9
+    torch.testing.assert_close(bs['context_layer'][same], ref_ctx[same], rtol=1e-3, atol=2e-5)
+    # no column of a padded token is ever selected
+    for n in range(N):
+        nnz = int(bs['crow_indices'][n, -1])
+        assert int((bs['col_indices'][n, :nnz] % T).max()) < int(lengths[n])
