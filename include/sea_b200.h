@@ -343,6 +343,30 @@ SEA_API int sea_performer_causal_state_fwd(const void* q, int64_t q_sn, int64_t 
                                            const float* pos_emb, const float* proj, int dtype, float* state, void* ctx, void* cumavg,
                                            int N, int H, int T_new, int t0, int D, int F, void* stream);
 
+/* One decode step (use_cache, one new token per item) of the causal layer in ONE call (csrc/decode_step.cu; reference:
+ * attention_state.py:43-236 + attention.py:559-572, 627-639, 774-947, 1151-1173, 1222-1244): incremental Performer + running mean,
+ * predictor MLP on the token, the two dilated convs on 5-row windows, tail + softmax, top-k of the row, sparse attention of the row over
+ * the KV cache k / v [N,H,t+1,D].  q [N,H,1,D].  All weights fp32 in the reference layouts (conv weights [C,C,5,3]; C > S*H = zero-padded
+ * channels for the 64-channel tensor-core convs; conv3_w [H, S*H]); mlp_ws / conv1_ws / conv2_ws: packed-weight workspaces of the tensor-core
+ * kernels (NULL -> SIMT kernels), re-packed when `repack` != 0.  k_per_row: device pointer to per_item_top_k of position t.
+ * State (functional): perf_in -> perf_out (sea_performer_state_floats floats), xwin / ywin [N,4,W,C] = last 4 rows of the CNN input and of
+ * conv 1's output.  Outputs: context [N,1,H*D] (`dtype`), probs fp32 [N,H,1,P].  workspace: sea_decode_step_workspace_bytes, 256-B aligned. */
+SEA_API int64_t sea_decode_step_workspace_bytes(int N, int H, int D, int P, int S, int C, int k_clamp, int dtype);
+SEA_API int sea_decode_step(const void* q, int64_t q_sn, int64_t q_sh,
+                            const void* k, int64_t k_sn, int64_t k_sh, int64_t k_st,
+                            const void* v, int64_t v_sn, int64_t v_sh, int64_t v_st, int dtype,
+                            const float* pos_emb, const float* proj,
+                            const float* enc_w, const float* enc_b, const float* enc_ln_w, const float* enc_ln_b,
+                            const float* dec_w, const float* dec_b, const float* cnn_ln_w, const float* cnn_ln_b,
+                            const float* scl_w, const float* scl_b,
+                            const float* conv1_w, const float* conv1_b, const float* conv2_w, const float* conv2_b,
+                            const float* conv3_w, const float* conv3_b, const float* out_ln_w, const float* out_ln_b,
+                            void* mlp_ws, void* conv1_ws, void* conv2_ws, int repack,
+                            const float* k_per_row,
+                            const float* perf_in, float* perf_out, const void* xwin_in, void* xwin_out, const void* ywin_in, void* ywin_out,
+                            void* context, float* probs, void* workspace, int64_t workspace_bytes,
+                            int N, int H, int D, int F, int P, int S, int C, int t, int k_clamp, int use_scaler, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Non-causal (BERT) variant, csrc/noncausal.cu.  No padding.
  * sea_performer_noncausal_fwd: v_for_atten = cat(grid-sampled identity, v) (attention.py:462-502) and the FAVOR+

@@ -182,6 +182,10 @@ class PerlinAttention(nn.Module):
         # (perlin_opt.py:477) unless output_attentions; False = the fused tail keeps the probabilities in registers (top-k only) and
         # the two estimated_* fields of the output tuple are None (134 MB less HBM traffic per layer at the north-star shape)
         self.keep_estimated_probs = True
+        # decode (use_cache): one native call per token (sea_decode_step) instead of the per-op python sequence; False keeps the latter
+        # (same kernels, same results; it is what the tests compare the native step with)
+        self.decode_native = True
+        self._decode_ws = {}
 
         self.performer_nb_features = int(d * math.log(d) / pc.performer_nb_factor)
         self.performer = _PerformerParams(d, self.performer_nb_features, causal=pc.causal)
@@ -232,6 +236,7 @@ class PerlinAttention(nn.Module):
         self._shape_cache = {}
         self._packed = ops.PackedWeights()
         self._padded_cache = None
+        self._w_cache = None
 
     # ------------------------------------------------------------------------------------------------
     def _cnn_convs(self):
@@ -242,6 +247,15 @@ class PerlinAttention(nn.Module):
         return [net[2 * i].module for i in range(n3)], net[2 * n3 + 1].module
 
     def _weights_fp32(self):
+        """fp32 contiguous views / copies of the predictor parameters, keyed like the C entries name them.  Frozen module
+        (freeze_packed_weights): made once and reused -- a bf16 / fp16 module would otherwise convert ~20 tensors per call."""
+        if self._packed.frozen and self._w_cache is not None:
+            return dict(self._w_cache)
+        w = self._weights_fp32_uncached()
+        self._w_cache = dict(w) if self._packed.frozen else None
+        return w
+
+    def _weights_fp32_uncached(self):
         f = lambda t: t.detach().float().contiguous()
         enc, dec, scl, cnn = self.attention_predictor_enc, self.attention_predictor_dec_row, self.attention_predictor_dec_scaler, self.attention_predictor_cnn
         w = {
@@ -273,12 +287,14 @@ class PerlinAttention(nn.Module):
         every call, so ANY way of writing a parameter -- including `.data` writes, which bump no version counter -- is seen."""
         self._packed.freeze(on)
         self._padded_cache = None
+        self._w_cache = None
         return self
 
     def invalidate_packed(self):
         """Drop every cached weight packing (call after modifying parameters of a frozen module)."""
         self._packed.invalidate()
         self._padded_cache = None
+        self._w_cache = None
 
     def _load_from_state_dict(self, *args, **kwargs):
         self.invalidate_packed()
@@ -293,6 +309,7 @@ class PerlinAttention(nn.Module):
         if mode and getattr(self, '_packed', None) is not None:
             self._packed.freeze(False)
             self._padded_cache = None
+            self._w_cache = None
         return super().train(mode)
 
     def _padded_conv_weights(self, w, C, H):
@@ -573,7 +590,7 @@ class PerlinAttention(nn.Module):
                            f'(v_eye_learned_causal has no row for it)')
         # functional update like the reference: the caller's state object is left untouched.  Only the Performer sums are advanced in
         # place by the kernel, so only they are copied; the CNN windows are rebuilt (torch.cat) every step anyway.
-        st = PerlinAttentionState(t=last_state.t, performer=last_state.performer.clone(), cnn_in_win=last_state.cnn_in_win,
+        st = PerlinAttentionState(t=last_state.t, performer=last_state.performer, cnn_in_win=last_state.cnn_in_win,
                                   conv1_win=last_state.conv1_win)
         pk = self._packed
         net = self.attention_predictor_cnn[1].module.net
@@ -590,8 +607,68 @@ class PerlinAttention(nn.Module):
             kpr_all = _k_per_row_causal(H, pc.k, pc.k_oversample, P, max_pos, max_pos, q.device)
             self._shape_cache[key] = kpr_all
         contexts, prob_rows = [], []
+        native = (self.decode_native and q_for_atten.data_ptr() == q_for_score.data_ptr() and k_for_atten.data_ptr() == k_for_score.data_ptr()
+                  and q.dtype == k.dtype == v.dtype and k.stride(-1) == 1 and v.stride(-1) == 1 and q.stride(-1) == 1
+                  and k_for_score.stride() == k.stride() and st.cnn_in_win.is_contiguous() and st.conv1_win.is_contiguous())
+        if native:
+            lib = ops._lib.load()
+            dcode = ops._dtype_code(q)
+            if q.dtype == torch.bfloat16 and lib.sea_predictor_mlp_umma_supported(dcode, H, d, S, W):
+                mlp_ws, fresh_m = pk.get('mlp', w['_src_mlp'], lib.sea_predictor_mlp_umma_workspace_bytes(), q.device)
+            elif q.dtype == torch.bfloat16 and lib.sea_predictor_mlp_mma_supported(dcode, H, d, S, W):
+                mlp_ws, fresh_m = pk.get('mlp_mma', w['_src_mlp'], lib.sea_predictor_mlp_mma_workspace_bytes(d, S, W), q.device)
+            else:
+                mlp_ws, fresh_m = None, False
+            if q.dtype == torch.bfloat16 and C_win == 64 and ops.conv_umma_supported(q.dtype, W, C_win, C_win):
+                nb = lib.sea_conv_umma_workspace_bytes(C_win, C_win)
+                c1_ws, fresh_1 = pk.get('conv1', (net[0].module.weight,), nb, q.device)
+                c2_ws, fresh_2 = pk.get('conv2', (net[2].module.weight,), nb, q.device)
+            else:
+                c1_ws = c2_ws = None
+                fresh_1 = fresh_2 = False
+            repack = int(fresh_m or fresh_1 or fresh_2)
+            wkey = (N, H, d, P, S, C_win, int(pc.k), q.dtype, str(q.device))
+            ws = self._decode_ws.get(wkey)
+            if ws is None:
+                nbytes = int(lib.sea_decode_step_workspace_bytes(N, H, d, P, S, C_win, int(pc.k), dcode))
+                ws = torch.empty((nbytes + 256,), dtype=torch.uint8, device=q.device)
+                ws = ws[(-ws.data_ptr()) % 256:][:nbytes]
+                self._decode_ws = {wkey: ws}
+            qn = q_for_score
+        else:
+            st.performer = st.performer.clone()          # the per-op kernel advances the sums in place
         for i in range(T_new):
             t = st.t
+            if native:
+                # (the new token's k / v rows are rows t of the caches; every intermediate lives in the workspace)
+                new = PerlinAttentionState(t=t + 1, performer=torch.empty_like(st.performer), cnn_in_win=torch.empty_like(st.cnn_in_win),
+                                           conv1_win=torch.empty_like(st.conv1_win))
+                context = torch.empty((N, 1, H * d), dtype=q.dtype, device=q.device)
+                probs = torch.empty((N, H, 1, P), dtype=torch.float32, device=q.device)
+                qi = qn[:, :, i:i + 1]
+                with torch.cuda.device(q.device):
+                    ops._lib.call('sea_decode_step', qi.data_ptr(), qi.stride(0), qi.stride(1),
+                                  k_for_score.data_ptr(), k_for_score.stride(0), k_for_score.stride(1), k_for_score.stride(2),
+                                  v.data_ptr(), v.stride(0), v.stride(1), v.stride(2), dcode,
+                                  w['pos'].data_ptr(), w['proj'].data_ptr(),
+                                  w['enc_w'].data_ptr(), w['enc_b'].data_ptr(), w['enc_ln_w'].data_ptr(), w['enc_ln_b'].data_ptr(),
+                                  w['dec_w'].data_ptr(), w['dec_b'].data_ptr(), w['cnn_ln_w'].data_ptr(), w['cnn_ln_b'].data_ptr(),
+                                  w['scl_w'].data_ptr(), w['scl_b'].data_ptr(),
+                                  wp['conv1_w'].data_ptr(), wp['conv1_b'].data_ptr(), wp['conv2_w'].data_ptr(), wp['conv2_b'].data_ptr(),
+                                  w['conv3_w'].data_ptr(), w['conv3_b'].data_ptr(), w['out_ln_w'].data_ptr(), w['out_ln_b'].data_ptr(),
+                                  None if mlp_ws is None else mlp_ws.data_ptr(), None if c1_ws is None else c1_ws.data_ptr(),
+                                  None if c2_ws is None else c2_ws.data_ptr(), repack,
+                                  kpr_all.data_ptr() + 4 * t,
+                                  st.performer.data_ptr(), new.performer.data_ptr(), st.cnn_in_win.data_ptr(), new.cnn_in_win.data_ptr(),
+                                  st.conv1_win.data_ptr(), new.conv1_win.data_ptr(),
+                                  context.data_ptr(), probs.data_ptr(), ws.data_ptr(), ws.numel(),
+                                  N, H, d, F, P, S, C_win, t, int(pc.k), int(bool(pc.partial_attention_scaler)),
+                                  torch.cuda.current_stream(q.device).cuda_stream)
+                repack = 0
+                st = new
+                contexts.append(context)
+                prob_rows.append(probs)
+                continue
             qa, ka, v1 = q_for_atten[:, :, i:i + 1], k_for_atten[:, :, t:t + 1], v[:, :, t:t + 1]
             ctx, cumavg = ops.performer_causal_state(qa, ka, v1, w['pos'], w['proj'], st.performer, t)
             cnn_row, scales, _ = ops.predictor_mlp(ctx, v1, w, S, W, packed=pk, c_out=C_win if pad_c else None)      # [N,1,W,C]

@@ -1,0 +1,170 @@
+// One decode step (use_cache, T_new = 1) of the causal layer as ONE C-ABI call: the ~10 kernels of a step are enqueued
+// back to back from native code, with every intermediate in a caller-provided workspace -- no per-kernel python dispatch, no tensor
+// allocation, no torch.cat.  Same kernels and same results as the per-op python sequence (attention.py::_forward_causal_stateful):
+//   incremental Performer + running mean of v (StatefulCausalPerformer / StatefulCumAvg, attention_state.py:43-98, 205-224)
+//   -> predictor MLP on the new token -> CNN input window (last 4 rows + new row) -> dilated conv 1 on the 5-row window -> its
+//   window -> dilated conv 2 (windowed CNN of attention_state.py:142-187) -> 1x1 conv + upsample + area resize + LayerNorm + softmax
+//   -> grouped top-k of the one query row (attention.py:774-947) -> sparse attention of that row over the whole KV cache.
+// The state is functional like the reference's (the caller's old state is left untouched): state_in buffers are read, state_out
+// buffers written.
+#include "common.cuh"
+
+namespace sea {
+namespace {
+
+__global__ void broadcast_float_kernel(float* __restrict__ dst, const float* __restrict__ src, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[0];
+}
+
+inline int64_t align256(int64_t x) { return (x + 255) & ~(int64_t) 255; }
+
+struct DecodeWs {
+    int64_t ctx, cumavg, cnn_row, xwin5, y1full, ywin5, y2full, y2row, scales, bits, kpr, crow, col, head_ptr, total;
+    int64_t z_alloc;
+};
+
+DecodeWs decode_ws(int N, int H, int D, int P, int S, int C, int k_clamp, int esz) {
+    const int W = P / 4;
+    DecodeWs w;
+    int64_t o = 0;
+    auto take = [&](int64_t bytes) { const int64_t at = o; o += align256(bytes); return at; };
+    w.ctx = take((int64_t) N * H * 2 * D * esz);
+    w.cumavg = take((int64_t) N * H * D * esz);
+    w.cnn_row = take((int64_t) N * W * C * esz);
+    w.xwin5 = take((int64_t) N * 5 * W * C * esz);
+    w.y1full = take((int64_t) N * 5 * W * C * esz);
+    w.ywin5 = take((int64_t) N * 5 * W * C * esz);
+    w.y2full = take((int64_t) N * 5 * W * C * esz);
+    w.y2row = take((int64_t) N * W * S * H * esz);
+    w.scales = take((int64_t) N * H * 2 * 4);
+    w.bits = take((int64_t) N * ((H * P + 31) / 32) * 4);
+    w.kpr = take((int64_t) N * 4);
+    // CSR of one query row per item (only the fp32 path materialises it).  K_t = round(H k P / L) pixels, each min(floor(L/P) + 1, k) wide:
+    // nnz <= H k (1 + P / L) <= 2 H k for L >= P, and <= H L < H P for L < P (pixels at most one token wide)
+    w.z_alloc = (int64_t) H * (2 * k_clamp > P ? 2 * k_clamp : P) + k_clamp + 64;      // + one pixel (<= k wide) for the rounding of K_t
+    w.crow = take((int64_t) N * 2 * 4);
+    w.col = take((int64_t) N * w.z_alloc * 4);
+    w.head_ptr = take((int64_t) N * (H + 1) * 4);
+    w.total = o;
+    return w;
+}
+
+}  // namespace
+}  // namespace sea
+
+using namespace sea;
+
+extern "C" {
+
+int64_t sea_decode_step_workspace_bytes(int N, int H, int D, int P, int S, int C, int k_clamp, int dtype) {
+    if (N <= 0 || H <= 0 || D <= 0 || P <= 0 || S <= 0 || C < S * H || k_clamp <= 0) return 0;
+    return decode_ws(N, H, D, P, S, C, k_clamp, dtype == SEA_DTYPE_F32 ? 4 : 2).total;
+}
+
+int sea_decode_step(const void* q, int64_t q_sn, int64_t q_sh,
+                    const void* k, int64_t k_sn, int64_t k_sh, int64_t k_st,
+                    const void* v, int64_t v_sn, int64_t v_sh, int64_t v_st, int dtype,
+                    const float* pos_emb, const float* proj,
+                    const float* enc_w, const float* enc_b, const float* enc_ln_w, const float* enc_ln_b,
+                    const float* dec_w, const float* dec_b, const float* cnn_ln_w, const float* cnn_ln_b,
+                    const float* scl_w, const float* scl_b,
+                    const float* conv1_w, const float* conv1_b, const float* conv2_w, const float* conv2_b,
+                    const float* conv3_w, const float* conv3_b, const float* out_ln_w, const float* out_ln_b,
+                    void* mlp_ws, void* conv1_ws, void* conv2_ws, int repack,
+                    const float* k_per_row,
+                    const float* perf_in, float* perf_out, const void* xwin_in, void* xwin_out, const void* ywin_in, void* ywin_out,
+                    void* context, float* probs, void* workspace, int64_t workspace_bytes,
+                    int N, int H, int D, int F, int P, int S, int C, int t, int k_clamp, int use_scaler, void* stream) {
+    SEA_CHECK_ARG(q && k && v && pos_emb && proj && enc_w && enc_b && enc_ln_w && enc_ln_b && dec_w && dec_b && cnn_ln_w && cnn_ln_b && scl_w && scl_b &&
+                  conv1_w && conv1_b && conv2_w && conv2_b && conv3_w && conv3_b && out_ln_w && out_ln_b && k_per_row && perf_in && perf_out &&
+                  xwin_in && xwin_out && ywin_in && ywin_out && context && probs && workspace, "sea_decode_step: null pointer");
+    SEA_CHECK_ARG(N > 0 && H > 0 && D > 0 && F > 0 && P > 0 && (P % 4) == 0 && S > 0 && C >= S * H && t >= 0 && k_clamp > 0, "sea_decode_step: bad shape");
+    SEA_CHECK_ARG(dtype == SEA_DTYPE_F32 || dtype == SEA_DTYPE_BF16 || dtype == SEA_DTYPE_F16, "sea_decode_step: bad dtype");
+    const int esz = dtype == SEA_DTYPE_F32 ? 4 : 2;
+    const int W = P / 4, T_SRC = t + 1, SH = S * H;
+    const DecodeWs ws = decode_ws(N, H, D, P, S, C, k_clamp, esz);
+    SEA_CHECK_ARG(workspace_bytes >= ws.total && (((uintptr_t) workspace) & 255) == 0, "sea_decode_step: workspace too small or misaligned (%lld B needed)", (long long) ws.total);
+    cudaStream_t s = (cudaStream_t) stream;
+    uint8_t* wb = reinterpret_cast<uint8_t*>(workspace);
+    void *ctx = wb + ws.ctx, *cumavg = wb + ws.cumavg, *cnn_row = wb + ws.cnn_row, *xwin5 = wb + ws.xwin5, *y1full = wb + ws.y1full;
+    void *ywin5 = wb + ws.ywin5, *y2full = wb + ws.y2full, *y2row = wb + ws.y2row;
+    float* scales = reinterpret_cast<float*>(wb + ws.scales);
+    uint32_t* bits = reinterpret_cast<uint32_t*>(wb + ws.bits);
+    float* kpr = reinterpret_cast<float*>(wb + ws.kpr);
+    int rc;
+
+    // ---- a2 + a3 + a13 from the running sums (functional state: sums copied, then advanced in place)
+    const int64_t perf_floats = sea_performer_state_floats(N, H, D, F);
+    SEA_CUDA_TRY(cudaMemcpyAsync(perf_out, perf_in, (size_t) perf_floats * 4, cudaMemcpyDeviceToDevice, s), "state copy");
+    const uint8_t* k_new = reinterpret_cast<const uint8_t*>(k) + (int64_t) t * k_st * esz;
+    const uint8_t* v_new = reinterpret_cast<const uint8_t*>(v) + (int64_t) t * v_st * esz;
+    rc = sea_performer_causal_state_fwd(q, q_sn, q_sh, D, k_new, k_sn, k_sh, k_st, v_new, v_sn, v_sh, v_st, pos_emb, proj, dtype, perf_out, ctx, cumavg,
+                                        N, H, 1, t, D, F, stream);
+    if (rc) return rc;
+
+    // ---- a4 on the new token -> one CNN input row [N,1,W,C]
+    const bool bf16 = dtype == SEA_DTYPE_BF16;
+    const bool aligned_v = ((v_sn | v_sh | v_st) % 8) == 0;
+    if (bf16 && mlp_ws && aligned_v && sea_predictor_mlp_umma_supported(dtype, H, D, S, W) && (int64_t) W * C * 2 <= 32 * 1024 && (C % 8) == 0) {
+        rc = sea_predictor_mlp_umma_fwd_ex(ctx, v_new, v_sn, v_sh, v_st, repack ? enc_w : nullptr, enc_b, enc_ln_w, enc_ln_b, repack ? dec_w : nullptr, dec_b,
+                                           cnn_ln_w, cnn_ln_b, repack ? scl_w : nullptr, scl_b, cnn_row, scales, mlp_ws, N, H, 1, D, S, W, C, stream);
+    } else if (bf16 && mlp_ws && aligned_v && sea_predictor_mlp_mma_supported(dtype, H, D, S, W) && (int64_t) W * C * 2 <= 32 * 1024 && (C % 8) == 0) {
+        rc = sea_predictor_mlp_mma_fwd(ctx, v_new, v_sn, v_sh, v_st, repack ? enc_w : nullptr, enc_b, enc_ln_w, enc_ln_b, repack ? dec_w : nullptr, dec_b,
+                                       cnn_ln_w, cnn_ln_b, repack ? scl_w : nullptr, scl_b, cnn_row, scales, mlp_ws, N, H, 1, D, S, W, C, stream);
+    } else {
+        SEA_CHECK_ARG(C == SH, "sea_decode_step: zero-padded channels need the tensor-core MLP");
+        rc = sea_predictor_mlp_fwd(ctx, v_new, v_sn, v_sh, v_st, dtype, enc_w, enc_b, enc_ln_w, enc_ln_b, dec_w, dec_b, cnn_ln_w, cnn_ln_b, scl_w, scl_b,
+                                   cnn_row, scales, nullptr, N, H, 1, D, S, W, stream);
+    }
+    if (rc) return rc;
+
+    // ---- windowed CNN: rows t-4 .. t of the CNN input, conv 1, rows t-4 .. t of its output, conv 2 (each conv looks 4 rows back)
+    const size_t row_b = (size_t) W * C * esz;
+    SEA_CUDA_TRY(cudaMemcpy2DAsync(xwin5, 5 * row_b, xwin_in, 4 * row_b, 4 * row_b, N, cudaMemcpyDeviceToDevice, s), "window copy");
+    SEA_CUDA_TRY(cudaMemcpy2DAsync(reinterpret_cast<uint8_t*>(xwin5) + 4 * row_b, 5 * row_b, cnn_row, row_b, row_b, N, cudaMemcpyDeviceToDevice, s), "window copy");
+    const bool conv_tc = bf16 && conv1_ws && conv2_ws && sea_conv_umma_supported(dtype, W, C, C) && C == 64;
+    if (conv_tc) rc = sea_causal_conv3x3_dil2_relu_umma(xwin5, repack ? conv1_w : nullptr, conv1_b, y1full, conv1_ws, N, 5, W, C, C, stream);
+    else rc = sea_causal_conv3x3_dil2_relu(xwin5, conv1_w, conv1_b, y1full, dtype, N, 5, W, C, C, stream);
+    if (rc) return rc;
+    SEA_CUDA_TRY(cudaMemcpy2DAsync(ywin5, 5 * row_b, ywin_in, 4 * row_b, 4 * row_b, N, cudaMemcpyDeviceToDevice, s), "window copy");
+    SEA_CUDA_TRY(cudaMemcpy2DAsync(reinterpret_cast<uint8_t*>(ywin5) + 4 * row_b, 5 * row_b, reinterpret_cast<uint8_t*>(y1full) + 4 * row_b, 5 * row_b, row_b, N,
+                                   cudaMemcpyDeviceToDevice, s), "window copy");
+    if (conv_tc) rc = sea_causal_conv3x3_dil2_relu_umma(ywin5, repack ? conv2_w : nullptr, conv2_b, y2full, conv2_ws, N, 5, W, C, C, stream);
+    else rc = sea_causal_conv3x3_dil2_relu(ywin5, conv2_w, conv2_b, y2full, dtype, N, 5, W, C, C, stream);
+    if (rc) return rc;
+    // the windows the next step starts from: rows 1 .. 4
+    SEA_CUDA_TRY(cudaMemcpy2DAsync(xwin_out, 4 * row_b, reinterpret_cast<uint8_t*>(xwin5) + row_b, 5 * row_b, 4 * row_b, N, cudaMemcpyDeviceToDevice, s), "window copy");
+    SEA_CUDA_TRY(cudaMemcpy2DAsync(ywin_out, 4 * row_b, reinterpret_cast<uint8_t*>(ywin5) + row_b, 5 * row_b, 4 * row_b, N, cudaMemcpyDeviceToDevice, s), "window copy");
+    // last row of conv 2, real channels only: [N, W, S*H]
+    for (int n = 0; n < N; ++n)
+        SEA_CUDA_TRY(cudaMemcpy2DAsync(reinterpret_cast<uint8_t*>(y2row) + (size_t) n * W * SH * esz, (size_t) SH * esz,
+                                       reinterpret_cast<uint8_t*>(y2full) + ((size_t) n * 5 + 4) * row_b, (size_t) C * esz, (size_t) SH * esz, W,
+                                       cudaMemcpyDeviceToDevice, s), "row copy");
+
+    // ---- a5 tail + a6, a7 of the one query row
+    rc = sea_predictor_tail_fwd(y2row, dtype, conv3_w, conv3_b, out_ln_w, out_ln_b, probs, nullptr, N, H, 1, W, SH, P, stream);
+    if (rc) return rc;
+    broadcast_float_kernel<<<(N + 127) / 128, 128, 0, s>>>(kpr, k_per_row, N);
+    SEA_CHECK_LAUNCH("broadcast_float_kernel");
+    rc = sea_topk_mask_bits(probs, (int64_t) H * P, (int64_t) P, (int64_t) P, kpr, nullptr, bits, N, H, 1, P, 0, stream);
+    if (rc) return rc;
+
+    // ---- a8 - a14: the query row against the whole KV cache
+    if (dtype != SEA_DTYPE_F32 && (D == 32 || D == 64 || D == 80 || D == 96 || D == 128) && (P % 32) == 0 && P <= 1024 &&
+        ((q_sn | q_sh | k_sn | k_sh | k_st | v_sn | v_sh | v_st) % 8) == 0) {
+        return sea_sparse_attention_bits_fwd(bits, q, q_sn, q_sh, D, k, k_sn, k_sh, k_st, v, v_sn, v_sh, v_st, scales, cumavg, (int64_t) D, (int64_t) D,
+                                             use_scaler, dtype, context, N, H, 1, T_SRC, D, P, k_clamp, 1, stream);
+    }
+    int32_t* crow = reinterpret_cast<int32_t*>(wb + ws.crow);
+    int32_t* col = reinterpret_cast<int32_t*>(wb + ws.col);
+    int32_t* head_ptr = (P % 32) == 0 ? reinterpret_cast<int32_t*>(wb + ws.head_ptr) : nullptr;
+    rc = sea_csr_count(bits, crow, 0, N, H, 1, P, T_SRC, k_clamp, 1, stream);
+    if (rc) return rc;
+    rc = sea_csr_fill(bits, crow, col, 0, ws.z_alloc, head_ptr, N, H, 1, P, T_SRC, k_clamp, 1, stream);
+    if (rc) return rc;
+    return sea_sparse_attention_fwd(crow, col, 0, ws.z_alloc, q, q_sn, q_sh, D, k, k_sn, k_sh, k_st, v, v_sn, v_sh, v_st, scales, cumavg, (int64_t) D, (int64_t) D,
+                                    use_scaler, dtype, context, nullptr, head_ptr, N, H, 1, T_SRC, D, stream);
+}
+
+}  // extern "C"

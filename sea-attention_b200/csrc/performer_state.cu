@@ -97,15 +97,15 @@ __global__ void __launch_bounds__(kStThreads)
 performer_state_build_kernel(const T* __restrict__ k, int64_t k_sn, int64_t k_sh, int64_t k_st,
                              const T* __restrict__ v, int64_t v_sn, int64_t v_sh, int64_t v_st,
                              const float* __restrict__ pos_emb, const float* __restrict__ proj, float* __restrict__ state,
-                             int H, int Tn, int D, int F) {
+                             int H, int Tn, int D, int F, int chunk) {
     extern __shared__ float sb_sm[];
     const int E = 2 * D;
     float* pr = sb_sm;                          // [F][D]
     float* xk = pr + F * D;                     // [chunk][D]
-    float* v2 = xk + kBuildChunk * D;           // [chunk][E]
-    float* fk = v2 + kBuildChunk * E;           // [chunk][F]
+    float* v2 = xk + chunk * D;                 // [chunk][E]
+    float* fk = v2 + chunk * E;                 // [chunk][F]
     const int nh = blockIdx.y, n = nh / H, h = nh % H;
-    const int t0 = blockIdx.x * kBuildChunk, nt = min(kBuildChunk, Tn - t0);
+    const int t0 = blockIdx.x * chunk, nt = min(chunk, Tn - t0);
     const int tid = threadIdx.x;
     const T* kb = k + (int64_t) n * k_sn + (int64_t) h * k_sh;
     const T* vb = v + (int64_t) n * v_sn + (int64_t) h * v_sh;
@@ -182,13 +182,16 @@ int sea_performer_state_build(const void* k, int64_t k_sn, int64_t k_sh, int64_t
                               int N, int H, int T, int D, int F, void* stream) {
     SEA_CHECK_ARG(k && v && pos_emb && proj && state, "sea_performer_state_build: null pointer");
     SEA_CHECK_ARG(N > 0 && H > 0 && T > 0 && D > 0 && F > 0 && (int64_t) N * H <= 65535, "sea_performer_state_build: bad shape");
-    const size_t smem = ((size_t) F * D + (size_t) kBuildChunk * (3 * D + F)) * sizeof(float);
+    // rows per CTA: as many as fit 200 KB of shared memory next to the projection (128 at d = 64; 64 at d = 128, F = 77)
+    int chunk = kBuildChunk;
+    while (chunk > 8 && ((size_t) F * D + (size_t) chunk * (3 * D + F)) * sizeof(float) > 200 * 1024) chunk >>= 1;
+    const size_t smem = ((size_t) F * D + (size_t) chunk * (3 * D + F)) * sizeof(float);
     SEA_CHECK_ARG(smem <= 200 * 1024, "sea_performer_state_build: F * D too large");
     SEA_DISPATCH_DTYPE(dtype, T_, {
         auto kern = performer_state_build_kernel<T_>;
         SEA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem), "smem attr");
-        kern<<<dim3((unsigned) ((T + kBuildChunk - 1) / kBuildChunk), (unsigned) (N * H)), kStThreads, smem, (cudaStream_t) stream>>>(
-            (const T_*) k, k_sn, k_sh, k_st, (const T_*) v, v_sn, v_sh, v_st, pos_emb, proj, state, H, T, D, F);
+        kern<<<dim3((unsigned) ((T + chunk - 1) / chunk), (unsigned) (N * H)), kStThreads, smem, (cudaStream_t) stream>>>(
+            (const T_*) k, k_sn, k_sh, k_st, (const T_*) v, v_sn, v_sh, v_st, pos_emb, proj, state, H, T, D, F, chunk);
         SEA_CHECK_LAUNCH("performer_state_build_kernel");
     });
     return SEA_OK;

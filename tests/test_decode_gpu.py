@@ -156,3 +156,34 @@ def test_decode_primitives_match_the_stateful_oracle(sea):
         win_x, win_y = xw[:, 1:].contiguous(), yw[:, 1:].contiguous()
     got = torch.cat(rows, dim=1).permute(0, 3, 1, 2).cpu()
     torch.testing.assert_close(got, torch.from_numpy(fx['cnn_out']), rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize('N,H,d,T,T0,P,k,dtype', [(1, 32, 64, 72, 64, 64, 16, torch.bfloat16), (2, 12, 64, 40, 30, 256, 16, torch.bfloat16),
+                                                 (1, 32, 128, 70, 64, 256, 32, torch.bfloat16), (2, 3, 32, 24, 2, 32, 8, torch.float32),
+                                                 (1, 4, 64, 300, 290, 32, 8, torch.float32), (1, 8, 80, 50, 45, 128, 8, torch.bfloat16)])
+def test_native_decode_step_equals_the_per_op_sequence(sea, N, H, d, T, T0, P, k, dtype):
+    """sea_decode_step (one C call per token, csrc/decode_step.cu) enqueues the same kernels as the per-op python sequence: context,
+    probabilities and the whole state must come out identical -- tensor-core shapes, zero-padded channels (H = 12), other head dims,
+    fp32 (CSR attention with the shape-derived nnz bound), N > 1, a prompt shorter than the 4-row CNN window."""
+    mod = _module(sea, H, d, T, P, k, 8, seed=T + H + d)
+    g = torch.Generator().manual_seed(21)
+    q = (torch.randn(N, H, T, d, generator=g) * d ** -0.5).to(dtype).to(DEV)
+    kk = torch.randn(N, H, T, d, generator=g).to(dtype).to(DEV)
+    v = torch.randn(N, H, T, d, generator=g).to(dtype).to(DEV)
+    mod.pconfig.use_cache = True
+    s = lambda x, a, b: x[:, :, a:b]
+    o = mod(s(q, 0, T0), s(kk, 0, T0), s(v, 0, T0), s(q, 0, T0), s(kk, 0, T0), s(v, 0, T0), s(q, 0, T0), s(kk, 0, T0), None, None, None)
+    st_a = st_b = o.state
+    for t in range(T0, T):
+        args = (s(q, t, t + 1), s(kk, 0, t + 1), s(v, 0, t + 1), s(q, t, t + 1), s(kk, 0, t + 1), s(v, 0, t + 1), s(q, t, t + 1), s(kk, 0, t + 1), None, None, None)
+        mod.decode_native = True
+        a = mod(*args, last_state=st_a)
+        mod.decode_native = False
+        b = mod(*args, last_state=st_b)
+        mod.decode_native = True
+        assert a.state.t == b.state.t == t + 1
+        assert torch.equal(a.estimated_attention_probs, b.estimated_attention_probs), t
+        assert torch.equal(a.context_layer, b.context_layer), t
+        assert torch.equal(a.state.performer, b.state.performer) and torch.equal(a.state.cnn_in_win, b.state.cnn_in_win.contiguous())
+        assert torch.equal(a.state.conv1_win, b.state.conv1_win.contiguous())
+        st_a, st_b = a.state, b.state
