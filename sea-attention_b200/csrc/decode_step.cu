@@ -12,9 +12,54 @@
 namespace sea {
 namespace {
 
-__global__ void broadcast_float_kernel(float* __restrict__ dst, const float* __restrict__ src, int n) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) dst[i] = src[0];
+// The window bookkeeping of a step is a handful of small strided copies; each group of them is ONE launch (a cudaMemcpy2DAsync per
+// copy costs more in launch latency than the copy itself).  A job copies `width` 4-byte words for every (n, r): dst + n d_sn + r d_sr
+// <- src + n s_sn + r s_sr (strides in words).
+struct CopyJob {
+    uint32_t* dst;
+    const uint32_t* src;
+    int64_t d_sn, d_sr, s_sn, s_sr;
+    int N, R, width;
+};
+struct CopyJobs {
+    CopyJob j[3];
+    int count;
+    float* bcast_dst;           // optional: bcast_dst[0 .. bcast_n) = bcast_src[0]
+    const float* bcast_src;
+    int bcast_n;
+};
+
+__global__ void __launch_bounds__(256)
+decode_copy_kernel(CopyJobs jobs) {
+    const int64_t tid = (int64_t) blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t) gridDim.x * blockDim.x;
+    for (int q = 0; q < jobs.count; ++q) {
+        const CopyJob jb = jobs.j[q];
+        const int64_t per_n = (int64_t) jb.R * jb.width, total = per_n * jb.N;
+        for (int64_t i = tid; i < total; i += nth) {
+            const int n = (int) (i / per_n);
+            const int64_t rem = i - (int64_t) n * per_n;
+            const int r = (int) (rem / jb.width), c = (int) (rem - (int64_t) r * jb.width);
+            jb.dst[n * jb.d_sn + r * jb.d_sr + c] = jb.src[n * jb.s_sn + r * jb.s_sr + c];
+        }
+    }
+    if (jobs.bcast_dst != nullptr)
+        for (int64_t i = tid; i < jobs.bcast_n; i += nth) jobs.bcast_dst[i] = jobs.bcast_src[0];
+}
+
+inline CopyJob make_job(void* dst, const void* src, int64_t d_sn_b, int64_t d_sr_b, int64_t s_sn_b, int64_t s_sr_b, int N, int R, int64_t width_b) {
+    CopyJob j;
+    j.dst = reinterpret_cast<uint32_t*>(dst); j.src = reinterpret_cast<const uint32_t*>(src);
+    j.d_sn = d_sn_b >> 2; j.d_sr = d_sr_b >> 2; j.s_sn = s_sn_b >> 2; j.s_sr = s_sr_b >> 2;
+    j.N = N; j.R = R; j.width = (int) (width_b >> 2);
+    return j;
+}
+
+inline cudaError_t launch_copies(const CopyJobs& jobs, cudaStream_t s) {
+    int64_t words = jobs.bcast_n;
+    for (int q = 0; q < jobs.count; ++q) words += (int64_t) jobs.j[q].N * jobs.j[q].R * jobs.j[q].width;
+    const int blocks = (int) ((words + 1023) / 1024 < 1 ? 1 : ((words + 1023) / 1024 > 296 ? 296 : (words + 1023) / 1024));
+    decode_copy_kernel<<<blocks, 256, 0, s>>>(jobs);
+    return cudaGetLastError();
 }
 
 inline int64_t align256(int64_t x) { return (x + 255) & ~(int64_t) 255; }
@@ -120,33 +165,44 @@ int sea_decode_step(const void* q, int64_t q_sn, int64_t q_sh,
     if (rc) return rc;
 
     // ---- windowed CNN: rows t-4 .. t of the CNN input, conv 1, rows t-4 .. t of its output, conv 2 (each conv looks 4 rows back)
-    const size_t row_b = (size_t) W * C * esz;
-    SEA_CUDA_TRY(cudaMemcpy2DAsync(xwin5, 5 * row_b, xwin_in, 4 * row_b, 4 * row_b, N, cudaMemcpyDeviceToDevice, s), "window copy");
-    SEA_CUDA_TRY(cudaMemcpy2DAsync(reinterpret_cast<uint8_t*>(xwin5) + 4 * row_b, 5 * row_b, cnn_row, row_b, row_b, N, cudaMemcpyDeviceToDevice, s), "window copy");
+    const int64_t row_b = (int64_t) W * C * esz;          // bytes of one window row; C = 2H (or 64) is even, so every size below is a multiple of 4
+    SEA_CHECK_ARG((C % 2) == 0 && (SH % 2) == 0, "sea_decode_step: odd channel count");
+    uint8_t *xw5 = reinterpret_cast<uint8_t*>(xwin5), *yw5 = reinterpret_cast<uint8_t*>(ywin5);
+    {   // x window = [last 4 rows | new row]; the window the next step starts from = its rows 1 .. 4; k_per_row broadcast for the top-k
+        CopyJobs jobs = {};
+        jobs.j[0] = make_job(xw5, xwin_in, 5 * row_b, 0, 4 * row_b, 0, N, 1, 4 * row_b);
+        jobs.j[1] = make_job(xw5 + 4 * row_b, cnn_row, 5 * row_b, 0, row_b, 0, N, 1, row_b);
+        jobs.count = 2;
+        jobs.bcast_dst = kpr; jobs.bcast_src = k_per_row; jobs.bcast_n = N;
+        SEA_CUDA_TRY(launch_copies(jobs, s), "decode_copy_kernel");
+    }
     const bool conv_tc = bf16 && conv1_ws && conv2_ws && sea_conv_umma_supported(dtype, W, C, C) && C == 64;
     if (conv_tc) rc = sea_causal_conv3x3_dil2_relu_umma(xwin5, repack ? conv1_w : nullptr, conv1_b, y1full, conv1_ws, N, 5, W, C, C, stream);
     else rc = sea_causal_conv3x3_dil2_relu(xwin5, conv1_w, conv1_b, y1full, dtype, N, 5, W, C, C, stream);
     if (rc) return rc;
-    SEA_CUDA_TRY(cudaMemcpy2DAsync(ywin5, 5 * row_b, ywin_in, 4 * row_b, 4 * row_b, N, cudaMemcpyDeviceToDevice, s), "window copy");
-    SEA_CUDA_TRY(cudaMemcpy2DAsync(reinterpret_cast<uint8_t*>(ywin5) + 4 * row_b, 5 * row_b, reinterpret_cast<uint8_t*>(y1full) + 4 * row_b, 5 * row_b, row_b, N,
-                                   cudaMemcpyDeviceToDevice, s), "window copy");
+    {   // y window = [last 4 rows of conv 1's output | its new row]
+        CopyJobs jobs = {};
+        jobs.j[0] = make_job(yw5, ywin_in, 5 * row_b, 0, 4 * row_b, 0, N, 1, 4 * row_b);
+        jobs.j[1] = make_job(yw5 + 4 * row_b, reinterpret_cast<uint8_t*>(y1full) + 4 * row_b, 5 * row_b, 0, 5 * row_b, 0, N, 1, row_b);
+        jobs.count = 2;
+        SEA_CUDA_TRY(launch_copies(jobs, s), "decode_copy_kernel");
+    }
     if (conv_tc) rc = sea_causal_conv3x3_dil2_relu_umma(ywin5, repack ? conv2_w : nullptr, conv2_b, y2full, conv2_ws, N, 5, W, C, C, stream);
     else rc = sea_causal_conv3x3_dil2_relu(ywin5, conv2_w, conv2_b, y2full, dtype, N, 5, W, C, C, stream);
     if (rc) return rc;
-    // the windows the next step starts from: rows 1 .. 4
-    SEA_CUDA_TRY(cudaMemcpy2DAsync(xwin_out, 4 * row_b, reinterpret_cast<uint8_t*>(xwin5) + row_b, 5 * row_b, 4 * row_b, N, cudaMemcpyDeviceToDevice, s), "window copy");
-    SEA_CUDA_TRY(cudaMemcpy2DAsync(ywin_out, 4 * row_b, reinterpret_cast<uint8_t*>(ywin5) + row_b, 5 * row_b, 4 * row_b, N, cudaMemcpyDeviceToDevice, s), "window copy");
-    // last row of conv 2, real channels only: [N, W, S*H]
-    for (int n = 0; n < N; ++n)
-        SEA_CUDA_TRY(cudaMemcpy2DAsync(reinterpret_cast<uint8_t*>(y2row) + (size_t) n * W * SH * esz, (size_t) SH * esz,
-                                       reinterpret_cast<uint8_t*>(y2full) + ((size_t) n * 5 + 4) * row_b, (size_t) C * esz, (size_t) SH * esz, W,
-                                       cudaMemcpyDeviceToDevice, s), "row copy");
+    {   // the windows the next step starts from (rows 1 .. 4), and the last row of conv 2 with its real channels only: [N, W, S*H]
+        CopyJobs jobs = {};
+        jobs.j[0] = make_job(xwin_out, xw5 + row_b, 4 * row_b, 0, 5 * row_b, 0, N, 1, 4 * row_b);
+        jobs.j[1] = make_job(ywin_out, yw5 + row_b, 4 * row_b, 0, 5 * row_b, 0, N, 1, 4 * row_b);
+        jobs.j[2] = make_job(y2row, reinterpret_cast<uint8_t*>(y2full) + 4 * row_b, (int64_t) W * SH * esz, (int64_t) SH * esz, 5 * row_b, (int64_t) C * esz, N, W,
+                             (int64_t) SH * esz);
+        jobs.count = 3;
+        SEA_CUDA_TRY(launch_copies(jobs, s), "decode_copy_kernel");
+    }
 
     // ---- a5 tail + a6, a7 of the one query row
     rc = sea_predictor_tail_fwd(y2row, dtype, conv3_w, conv3_b, out_ln_w, out_ln_b, probs, nullptr, N, H, 1, W, SH, P, stream);
     if (rc) return rc;
-    broadcast_float_kernel<<<(N + 127) / 128, 128, 0, s>>>(kpr, k_per_row, N);
-    SEA_CHECK_LAUNCH("broadcast_float_kernel");
     rc = sea_topk_mask_bits(probs, (int64_t) H * P, (int64_t) P, (int64_t) P, kpr, nullptr, bits, N, H, 1, P, 0, stream);
     if (rc) return rc;
 
