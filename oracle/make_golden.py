@@ -258,6 +258,57 @@ def golden_layer_bert_padded(name, H, d, T, k, P, nbf, lengths, seed_inputs=2468
     print(name, 'written; buffers', sorted(k_ for k_ in fx if k_.startswith('dense.')))
 
 
+def golden_layer_training(name, H, d, T, k, P, nbf, N=2, seed_inputs=1357):
+    """TRAINING branch of the causal layer (attention.py:680-765, 1066-1133, 1328-1332): module in train() mode, benchmarking=False, teacher
+    tensors given -> the distillation loss: KL + MSE of the resized estimated scores, KL + MSE of the dense scores, MSE of the context.
+    The only randomness of the branch is the 10 % index jitter of resize_from_m_to_t(training=True) (resize_m_to_t.py:40-45, python
+    `random.random()`): it is switched off for the fixture by pinning random.random to 1.0, so that the run is deterministic.
+    FORWARD ONLY: in fp32 without autocast the reference's own backward cannot run -- `partial_attention_probs.masked_fill_` (:1120) writes
+    into the softmax output autograd saved (softmax_bf16 only makes a copy when it casts, i.e. under half-precision autocast on a GPU);
+    gradients are therefore checked against autograd of the oracle's restatement of this forward (tests/test_training_*.py)."""
+    import random
+    m = rh.build_reference_attention(H, d, T, k, P, nbf, True)
+    m.train()
+    m.benchmarking = False
+    g = torch.Generator().manual_seed(seed_inputs)
+    q = torch.randn(N, H, T, d, generator=g) * d ** -0.5
+    kk = torch.randn(N, H, T, d, generator=g)
+    v = torch.randn(N, H, T, d, generator=g)
+    scores_truth = torch.randn(N, H, T, T, generator=g) * 2.0
+    context_truth = torch.randn(N, T, H * d, generator=g) * 0.3
+    mask = rh.causal_additive_mask(T, torch.float32).expand(N, 1, T, T).clone()
+    from src.utils import get_bench
+    real_random = random.random
+    random.random = lambda: 1.0
+    try:
+        with torch.no_grad():
+            out_nt = m(q, kk, v, q, kk, v, q, kk, mask, None, None)                       # no teacher: loss == 0
+            get_bench().activate_temp_buffers = True
+            get_bench().reset_temp_buffers()
+            out = m(q, kk, v, q, kk, v, q, kk, mask, scores_truth.clone(), context_truth.clone())
+            bufs = {k_: v_[-1] for k_, v_ in get_bench().buffers.items()}
+            get_bench().activate_temp_buffers = False
+    finally:
+        random.random = real_random
+    assert float(out_nt.loss) == 0.0
+    sd = {k_: _np(v_) for k_, v_ in m.state_dict().items() if not k_.startswith(_UNUSED)}
+    fx = {'sd.' + k_: v_ for k_, v_ in sd.items()}
+    fx.update(q=_np(q), k=_np(kk), v=_np(v), scores_truth=_np(scores_truth), context_truth=_np(context_truth))
+    fx['loss'] = np.array(float(out.loss))
+    fx['context_layer'] = _np(out.context_layer).astype(np.float32)
+    fx['estimated_attention_probs_m'] = _np(out.estimated_attention_probs_m).astype(np.float32)
+    fx['estimated_attention_probs'] = _np(out.estimated_attention_probs).astype(np.float32)          # resized to [N,H,T,T] (:1338)
+    fx['partial_attention_probs'] = _np(out.partial_attention_probs).astype(np.float32)
+    fx['dense_attention_probs'] = _np(out.dense_attention_probs).astype(np.float32)
+    fx['partial_attention_mask_alive'] = np.packbits(_np(out.partial_attention_mask) > -1)
+    # the reference's own top-k selection (its CPU sort breaks the exact ties of the x4-upsampled predictor arbitrarily): lets a checker
+    # evaluate the loss on the SAME mask
+    fx['mask_before_interp_alive'] = np.packbits(_np(bufs['partial_attention_mask_before_interp']) > -1)
+    fx['meta'] = np.array([N, H, d, T, k, P, nbf, 1])
+    np.savez_compressed(os.path.join(GOLDEN, name + '.npz'), **fx)
+    print(name, 'written; loss', float(out.loss))
+
+
 def golden_state_ops():
     """The reference's three stateful decode ops (attention_state.py:43-98 StatefulCausalPerformer, :142-187 StatefulCausalCNN,
     :205-224 StatefulCumAvg) driven exactly as PerlinAttention drives them during a token-by-token decode, on seeded inputs."""
@@ -314,6 +365,8 @@ def main():
         return golden_state_ops()
     if '--skips-only' in sys.argv:
         return golden_layer_query_skips('layer_causal_skips2_h3_t64', H=3, d=32, T=64, k=6, P=16, nbf=4, skips=2)
+    if '--training-only' in sys.argv:
+        return golden_layer_training('layer_causal_training_h3_t48', H=3, d=32, T=48, k=6, P=16, nbf=4)
     if '--bert-padded-only' in sys.argv:
         return golden_layer_bert_padded('layer_bert_padded_h4_t64', H=4, d=64, T=64, k=8, P=32, nbf=1, lengths=[64, 45, 23])
     if '--deeper-only' in sys.argv:
@@ -328,6 +381,7 @@ def main():
     golden_layer_padded('layer_causal_padded_h3_t64', H=3, d=32, T=64, k=6, P=16, nbf=4, lengths=[64, 45])
     golden_layer_query_skips('layer_causal_skips2_h3_t64', H=3, d=32, T=64, k=6, P=16, nbf=4, skips=2)
     golden_layer_deeper('layer_causal_deeper_h3_t64', H=3, d=32, T=64, k=6, P=16, nbf=4)
+    golden_layer_training('layer_causal_training_h3_t48', H=3, d=32, T=48, k=6, P=16, nbf=4)
     if '--with-bert' in sys.argv:
         golden_layer_bert_padded('layer_bert_padded_h4_t64', H=4, d=64, T=64, k=8, P=32, nbf=1, lengths=[64, 45, 23])
         golden_layer('layer_bert_h4_t64', H=4, d=64, T=64, k=8, P=32, nbf=1, causal=False, k_flatten_dim='batch')

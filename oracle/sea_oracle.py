@@ -234,7 +234,7 @@ def topk_mask_causal_batch(probs: torch.Tensor, k, k_oversample: float = 1.0,
     t = probs
     if dst_valid is not None:
         t = t * dst_valid.view(N, 1, T, 1).to(t.dtype)
-    keys = t.transpose(1, 2).reshape(N * T, H * P).float().numpy()
+    keys = t.detach().transpose(1, 2).reshape(N * T, H * P).float().numpy()       # (the mask carries no gradient)
     if floor_variant:
         tl_ = torch.arange(1, T + 1, dtype=torch.long)
         K = torch.clamp(H * torch.floor(k * P / tl_), 1, H * P).numpy().astype(np.float32)
@@ -468,7 +468,7 @@ def state_dict_of(module) -> Dict[str, torch.Tensor]:
 def perlin_forward_causal(sd: Dict[str, torch.Tensor], q, k, v, *, k_top: int, P: int,
                           k_oversample: float = 1.0, partial_attention_scaler: bool = True,
                           sparse: bool = True, dst_valid: Optional[torch.Tensor] = None,
-                          keep_dense: bool = False, query_skips: int = 1) -> Dict[str, torch.Tensor]:
+                          keep_dense: bool = False, query_skips: int = 1, mask_override: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
     """attention.py:333-1359, causal prefill, `context_output_method='mix'`.
     sparse=True follows the `benchmarking` branch (CSR mask + flat_csr ops, :1036-1042, :1151-1173);
     sparse=False follows the dense branch (:960-962, :1066-1133) the reference itself runs on CPU.
@@ -502,7 +502,8 @@ def perlin_forward_causal(sd: Dict[str, torch.Tensor], q, k, v, *, k_top: int, P
     probs = torch.softmax(score, dim=-1)
     buf['estimated_attention_probs'] = probs
     # a7
-    mask_m = topk_mask_causal_batch(probs, k_top, k_oversample, dst_valid)
+    # mask_override: a given top-k selection [N,H,T,P] (e.g. the reference's own, whose unstable CPU sort cuts exact ties arbitrarily)
+    mask_m = topk_mask_causal_batch(probs, k_top, k_oversample, dst_valid) if mask_override is None else mask_override.float()
     buf['partial_attention_mask_before_interp'] = mask_m
     scales = predictor_dec_scaler(t_pred, sd)
     buf['estimated_scales'] = scales
@@ -540,6 +541,39 @@ def perlin_forward_causal(sd: Dict[str, torch.Tensor], q, k, v, *, k_top: int, P
     out = ctx * a + (1 - a) * avg
     # a14 (:1279-1282)
     buf['context_layer'] = out.permute(0, 2, 1, 3).reshape(N, T, H * d).contiguous()
+    return buf
+
+
+def perlin_train_forward(sd: Dict[str, torch.Tensor], q, k, v, scores_truth, context_truth, *, k_top: int, P: int,
+                         partial_attention_scaler: bool = True, mask_override: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+    """TRAINING branch, causal, no padding, the 10 % resize jitter off (attention.py:680-765 predictor distillation on the resized
+    estimated scores, :1066-1102 the same two terms on the dense q.k^T scores, :1328-1332 MSE of the context).  Built on the dense
+    branch of perlin_forward_causal, so it is differentiable by autograd w.r.t. q, k, v and every tensor of `sd` that requires grad:
+    the gradient reference of tests/test_training_*.py (the unmodified reference pins the forward values, see make_golden.py)."""
+    buf = perlin_forward_causal(sd, q, k, v, k_top=k_top, P=P, sparse=False, keep_dense=True, partial_attention_scaler=partial_attention_scaler,
+                                mask_override=mask_override)
+    N, H, T, d = q.shape
+    fmin = fp_min_for(torch.float32)
+    cmask = causal_additive_mask(T, torch.float32, N)
+    dead = cmask < -1
+    score, probs = buf['estimated_attention_score'], buf['estimated_attention_probs']
+    # handle_oversample=False -> oversampled = 1.0 (:691-703): the under-sampling test of resize_m_to_t.py:54-71 keeps every column
+    est_probs_resized = resize_from_m_to_t_dense(probs, 0.0, cmask, target_width=T, is_causal=True, k=k_top, oversampled=1.0)
+    est_score_resized = resize_from_m_to_t_dense(score, fmin, cmask, target_width=T, is_causal=True, k=k_top, oversampled=1.0)
+
+    def kd(scores):
+        inp = TF.log_softmax(scores.masked_fill(dead, fmin), dim=-1).reshape(-1, T)                       # :743, :1087
+        target = TF.softmax(scores_truth.float().masked_fill(dead, fmin), dim=-1).reshape(-1, T)           # :745, :1089
+        return TF.kl_div(inp, target, reduction='batchmean') * 0.1 + \
+            TF.mse_loss(TF.softmax(scores.masked_fill(dead, fmin), dim=-1).reshape(-1, T), target)        # :747-758, :1091-1101
+
+    loss = kd(est_score_resized)
+    dense = q.float() @ k.float().transpose(-1, -2)
+    loss = loss + kd(dense)
+    loss = loss + TF.mse_loss(context_truth.float(), buf['context_layer'])                                 # :1328-1332
+    buf['loss'] = loss
+    buf['estimated_attention_probs_resized'] = est_probs_resized
+    buf['dense_attention_probs'] = torch.softmax(dense.masked_fill(dead, fmin) + cmask, dim=-1)             # :1111-1115
     return buf
 
 

@@ -361,15 +361,22 @@ class PerlinAttention(nn.Module):
             raise SeaError('use_cache / PerlinAttentionState is only defined for the causal model (attention_state.py)')
         if (pc.use_cache or last_state is not None) and getattr(self, '_deeper', False):
             raise SeaError('use_cache with the PERLIN_HOTFIX_OPT_DEEPER predictor is not implemented (the decode state keeps two CNN windows)')
-        if self.training or attention_scores_truth is not None or context_layer_truth is not None:
-            raise SeaError('the training branch (dense path + KD losses, attention.py:707-765, 1066-1133) is not implemented yet '
-                           '(SURVEY 8f-1); call under eval() without teacher tensors')
         if pc.attention_predictor_method != 'mlp' or pc.attention_predictor_backend != 'performer' or pc.attention_predictor_enc_per_layer:
             raise SeaError('only the mlp predictor with the performer backend is implemented')
         if pc.context_output_method != 'mix' or pc.random_lookup or pc.out_add_performer_context:
             raise SeaError("only context_output_method='mix' without random lookup is implemented")
         # (k_oversample: the sparse path only scales per_item_top_k with it, attention.py:837-853; the CSR interpolation ignores its
         # `oversampled` argument, causal_resize_m_to_t.py:638 -- both are followed here)
+        if self.training or attention_scores_truth is not None or context_layer_truth is not None:
+            # training branch (the reference's benchmarking=False path with its distillation losses, attention.py:680-765, 1066-1133,
+            # 1328-1332): dense O(T^2) by definition, composed of differentiable torch operations on the GPU + the CUDA top-k (training.py)
+            if not pc.causal:
+                raise SeaError('the training branch is implemented for the causal model only')
+            if pc.use_cache or last_state is not None or query_skips != 1:
+                raise SeaError('the training branch takes no decode state and no QUERY_SKIPS')
+            from . import training
+            return training.forward_train(self, q, k, v, q_for_atten, k_for_atten, v_for_atten, q_for_score, k_for_score, attention_mask,
+                                          attention_scores_truth, context_layer_truth, PerlinAttentionOutput)
         if not pc.causal:
             return self._forward_noncausal(q, k, v, q_for_atten, k_for_atten, v_for_atten, q_for_score, k_for_score, attention_mask)
         if pc.k_flatten_dim != 'causal_batch' or not pc.k_flatten:

@@ -240,8 +240,10 @@ def test_unsupported_modes_fail_loudly(sea):
     mod = mod.to(DEV)
     q = torch.zeros(1, 2, 16, 32, device=DEV)
     mask = so.causal_additive_mask(16).to(DEV)
+    out = mod(q, q, q, q, q, q, q, q, mask, torch.zeros(1, 2, 16, 16, device=DEV), None)  # teacher tensors -> training branch (training.py)
+    assert torch.is_tensor(out.loss) and out.loss.ndim == 0 and out.partial_attention_probs.shape == (1, 2, 16, 16)
     with pytest.raises(sea.SeaError):
-        mod(q, q, q, q, q, q, q, q, mask, torch.zeros(1, 2, 16, 16, device=DEV), None)      # teacher tensors -> training branch
+        mod(q.cpu(), q.cpu(), q.cpu(), q.cpu(), q.cpu(), q.cpu(), q.cpu(), q.cpu(), mask.cpu(), torch.zeros(1, 2, 16, 16), None)      # no CPU path, training included
     with pytest.raises(sea.SeaError):
         mod(q, q, q, q, q, q[:, :, :8], q, q, mask, None, None)                                 # v_for_atten of another shape
 
