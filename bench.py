@@ -301,9 +301,11 @@ def run_c5(args):
 
         def step():
             outs = None
-            for t0, t1 in mine:
-                if t1 > t0:
-                    outs = mod.forward_query_block(q, kk, v, t0, t1).context_layer
+            live = [(t0, t1) for t0, t1 in mine if t1 > t0]
+            # a rank that walks several blocks runs the linear-attention stage once over its longest prefix (no exchange with other ranks)
+            perf = mod.performer_prefix(q, kk, v, max(t1 for _, t1 in live)) if len(live) > 1 else None
+            for t0, t1 in live:
+                outs = mod.forward_query_block(q, kk, v, t0, t1, performer=perf).context_layer
             return outs
 
         with torch.no_grad():

@@ -387,19 +387,28 @@ class PerlinAttention(nn.Module):
         return self._forward_causal_prefill(q, k, v, q_for_atten, k_for_atten, v_for_atten, q_for_score, k_for_score, attention_mask,
                                             query_skips=query_skips)
 
-    def forward_query_block(self, q, k, v, t0: int, t1: int):
+    def forward_query_block(self, q, k, v, t0: int, t1: int, performer=None):
         """Query-block sharded causal prefill (BASELINE configs[4]): q, k, v [N,H,T,d] hold the whole sequence; returns
         the PerlinAttentionOutput of query rows [t0, t1) only (context_layer [N, t1-t0, H*d]).  Concatenating the blocks of a
-        partition of [0, T) reproduces forward() on the whole sequence; blocks need nothing from each other."""
+        partition of [0, T) reproduces forward() on the whole sequence; blocks need nothing from each other.
+        performer = performer_prefix(q, k, v, t_end >= t1): a rank that walks SEVERAL blocks computes the linear-attention stage once
+        over its longest prefix and hands it to every block, instead of recomputing the prefix sums per block."""
         if not self.pconfig.causal:
             raise SeaError('query-block sharding is defined for the causal model')
         if self.training:
             raise SeaError('forward_query_block is an inference path')
-        return self._forward_causal_prefill(q, k, v, q, k, v, q, k, None, block=(t0, t1))
+        return self._forward_causal_prefill(q, k, v, q, k, v, q, k, None, block=(t0, t1), performer=performer)
+
+    def performer_prefix(self, q, k, v, t_end: int = None):
+        """(ctx [N,H,t_end,2d], running mean of v [N,H,t_end,d]) of the first t_end tokens: stage a2 + a3 (+ a13) alone, for
+        forward_query_block(..., performer=...)."""
+        t_end = q.shape[2] if t_end is None else int(t_end)
+        w = self._weights_fp32()
+        return ops.performer_causal(q[:, :, :t_end], k[:, :, :t_end], v[:, :, :t_end], w['pos'], w['proj'])
 
     # ------------------------------------------------------------------------------------------------
     def _forward_causal_prefill(self, q, k, v, q_for_atten, k_for_atten, v_for_atten, q_for_score, k_for_score, attention_mask, capture=None,
-                                block=None, query_skips: int = 1):
+                                block=None, query_skips: int = 1, performer=None):
         """Causal prefill (T_DST == T_SRC).  `capture` (dict) receives the CNN intermediates the decode state is built from.
 
         block = (t0, t1): query-block sharding of a long prefill: q / k / v hold the whole sequence (K and V are
@@ -448,7 +457,11 @@ class PerlinAttention(nn.Module):
         k_per_row, z_alloc = self._shape_consts(H, P, t1, t1 - t0, q.device)
 
         # a2+a3 (+ running mean for a13)
-        if lora_v is not None:
+        if performer is not None:
+            if block is None or lora_v is not None or row_valid is not None or performer[0].shape[2] < t1:
+                raise SeaError('a precomputed Performer prefix belongs to a query block and must cover its rows')
+            ctx, cumavg = performer[0][:, :, :t1], performer[1][:, :, :t1]
+        elif lora_v is not None:
             if row_valid is not None:
                 raise SeaError('padded rows together with a separate v_for_atten are not implemented')
             ctx, _ = ops.performer_causal(q_for_atten, k_for_atten, lora_v, w['pos'], w['proj'])

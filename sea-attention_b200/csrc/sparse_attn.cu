@@ -423,7 +423,12 @@ __device__ __forceinline__ void mma_16816<__half>(float (&c)[4], const uint32_t 
 template <int D>
 struct AttnMmaCfg {
     static constexpr int kLd = D + 8;                       // padded row (elements): ldmatrix rows hit distinct banks
-    static constexpr int kWarpElems = 2 * 32 * kLd;         // K tile + V tile per warp
+    // D <= 64: a K tile and a V tile per warp, both gathered at once (3 CTAs / SM).  Larger head dims: ONE tile buffer per warp, filled
+    // with the K rows for the scores and then with the V rows for P.V -- with two tiles a d = 128 CTA needs 139 KB and the SM holds a
+    // single CTA of 8 warps, latency-bound on its gathers (and at the 80-register cap of 3 CTAs / SM the 64 accumulator registers spill)
+    static constexpr bool kShare = D > 64;
+    static constexpr int kMinBlocks = kShare ? 2 : 3;          // (2: 128 registers, no spills with the 64 accumulators of d = 128; at 3 CTAs / SM the d = 80 / 96 instances spill ~400 B)
+    static constexpr int kWarpElems = (kShare ? 1 : 2) * 32 * kLd;
     static constexpr int kSmemBytes = kAttnWarps * kWarpElems * 2;
 };
 
@@ -434,32 +439,34 @@ __device__ __forceinline__ void attn_chunk_mma(T16* __restrict__ Ks, T16* __rest
                                                uint32_t k_sv, uint32_t v_sv, int jmine, int cnt, const uint32_t (&qb)[D / 16][2],
                                                float& m_run, float& l_run, float (&acc)[D / 8][4], int lane) {
     constexpr int LPR = D / 8, kLd = AttnMmaCfg<D>::kLd;
+    constexpr bool kShare = AttnMmaCfg<D>::kShare;
     constexpr float kLog2e = 1.4426950408889634f;
-    if constexpr (32 % LPR == 0) {
-        constexpr int EPI = 32 / LPR, NI = LPR;
-        const int sub = lane % LPR, grp = lane / LPR;
+    // gather of the 32 rows `jmine` of one operand (base pointer already offset by the lane's piece, row stride in 16-byte units)
+    auto gather = [&](T16* dst, const uint4* base, uint32_t sv) {
+        if constexpr (32 % LPR == 0) {
+            constexpr int EPI = 32 / LPR, NI = LPR;
+            const int sub = lane % LPR, grp = lane / LPR;
 #pragma unroll
-        for (int i = 0; i < NI; ++i) {
-            const int e = i * EPI + grp;
-            const uint32_t j = (uint32_t) __shfl_sync(kFull, jmine, e);
-            const bool ok = e < cnt;
-            cp_async16_zfill(Ks + e * kLd + sub * 8, kb + (ok ? j * k_sv : 0u), ok ? 16 : 0);
-            cp_async16_zfill(Vs + e * kLd + sub * 8, vb + (ok ? j * v_sv : 0u), ok ? 16 : 0);
-        }
-    } else {
-        // head dims whose row is not a power-of-two number of 16-byte pieces (D = 80: 10, D = 96: 12): piece idx -> (entry, piece)
-        static_assert((32 * LPR) % 32 == 0, "piece count");
-        const uint4* kb0 = kb - (lane % LPR);
-        const uint4* vb0 = vb - (lane % LPR);
+            for (int i = 0; i < NI; ++i) {
+                const int e = i * EPI + grp;
+                const uint32_t j = (uint32_t) __shfl_sync(kFull, jmine, e);
+                const bool ok = e < cnt;
+                cp_async16_zfill(dst + e * kLd + sub * 8, base + (ok ? j * sv : 0u), ok ? 16 : 0);
+            }
+        } else {
+            // head dims whose row is not a power-of-two number of 16-byte pieces (D = 80: 10, D = 96: 12): piece idx -> (entry, piece)
+            const uint4* base0 = base - (lane % LPR);
 #pragma unroll
-        for (int i = 0; i < LPR; ++i) {
-            const int idx = i * 32 + lane, e = idx / LPR, sb = idx - e * LPR;
-            const uint32_t j = (uint32_t) __shfl_sync(kFull, jmine, e);
-            const bool ok = e < cnt;
-            cp_async16_zfill(Ks + e * kLd + sb * 8, kb0 + sb + (ok ? j * k_sv : 0u), ok ? 16 : 0);
-            cp_async16_zfill(Vs + e * kLd + sb * 8, vb0 + sb + (ok ? j * v_sv : 0u), ok ? 16 : 0);
+            for (int i = 0; i < LPR; ++i) {
+                const int idx = i * 32 + lane, e = idx / LPR, sb = idx - e * LPR;
+                const uint32_t j = (uint32_t) __shfl_sync(kFull, jmine, e);
+                const bool ok = e < cnt;
+                cp_async16_zfill(dst + e * kLd + sb * 8, base0 + sb + (ok ? j * sv : 0u), ok ? 16 : 0);
+            }
         }
-    }
+    };
+    gather(Ks, kb, k_sv);
+    if constexpr (!kShare) gather(Vs, vb, v_sv);
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncwarp();
     const int g = lane >> 2, tq = lane & 3;
@@ -499,6 +506,10 @@ __device__ __forceinline__ void attn_chunk_mma(T16* __restrict__ Ks, T16* __rest
     psum = __shfl_sync(kFull, psum, lane & ~3);
     l_run = l_run * alpha + psum;
     m_run = m_new;
+    if constexpr (kShare) {     // the K rows are consumed (the scores live in registers): the V rows take their place
+        __syncwarp();
+        gather(Vs, vb, v_sv);
+    }
 #pragma unroll
     for (int nt = 0; nt < D / 8; ++nt) { acc[nt][0] *= alpha; acc[nt][1] *= alpha; }
     // p as the A operand (row 0 only): lane (g == 0, tq) needs entries 16ks+2tq, +1, 16ks+8+2tq, +1
@@ -515,6 +526,10 @@ __device__ __forceinline__ void attn_chunk_mma(T16* __restrict__ Ks, T16* __rest
         pa[ks][2] = row0 ? pack2<T16>(hi0, hi1) : 0u;
         pa[ks][3] = 0u;
     }
+    if constexpr (kShare) {
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncwarp();
+    }
 #pragma unroll
     for (int ks = 0; ks < 2; ++ks) {
 #pragma unroll
@@ -529,7 +544,7 @@ __device__ __forceinline__ void attn_chunk_mma(T16* __restrict__ Ks, T16* __rest
 }
 
 template <typename T16, int D>
-__global__ void __launch_bounds__(kAttnWarps * 32, 3)
+__global__ void __launch_bounds__(kAttnWarps * 32, AttnMmaCfg<D>::kMinBlocks)
 sparse_attention_bits_mma_kernel(const uint32_t* __restrict__ mask_bits,
                                  const T16* __restrict__ q, int64_t q_sn, int64_t q_sh, int64_t q_st,
                                  const T16* __restrict__ k, int64_t k_sn, int64_t k_sh, int64_t k_st,
@@ -540,7 +555,7 @@ sparse_attention_bits_mma_kernel(const uint32_t* __restrict__ mask_bits,
     constexpr int LPR = D / 8;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     T16* Ks = reinterpret_cast<T16*>(attn_smem) + warp * AttnMmaCfg<D>::kWarpElems;
-    T16* Vs = Ks + 32 * AttnMmaCfg<D>::kLd;
+    T16* Vs = AttnMmaCfg<D>::kShare ? Ks : Ks + 32 * AttnMmaCfg<D>::kLd;
     const int64_t task = (int64_t) blockIdx.x * kAttnWarps + warp;
     if (task >= (int64_t) N * T_DST * H) return;
     const int t = (int) (task % T_DST);

@@ -59,7 +59,7 @@ def forward_query_sharded(module, q, k, v, world_size: int, rank: int, gather: b
     T = q.shape[2]
     t0, t1 = query_block_bounds(T, world_size, rank)
     if t1 > t0:
-        ctx = module.forward_query_block(q, k, v, t0, t1).context_layer
+        ctx = module.forward_query_block(q, k, v, t0, t1).context_layer          # (one block per rank: the prefix is computed inside)
     else:
         ctx = torch.zeros((q.shape[0], 0, q.shape[1] * q.shape[3]), dtype=q.dtype, device=q.device)
     if not gather:

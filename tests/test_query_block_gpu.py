@@ -92,3 +92,23 @@ def test_long_context_fast_path_equals_csr_path(sea, H, d, T, P, k):
     rows = torch.repeat_interleave(torch.arange(T, device=DEV), nnz_row)
     assert bool(((col % T) <= rows).all()) and bool((col // T < H).all())                 # strictly causal, valid head
     assert torch.isfinite(fast.context_layer.float()).all()
+
+
+def test_query_blocks_with_a_shared_performer_prefix(sea):
+    """A rank that walks several blocks computes the linear-attention stage once (performer_prefix) and hands it to every block:
+    identical outputs to blocks that recompute their own prefix."""
+    H, d, T, P, k = 32, 128, 1536, 256, 64
+    m = _module(sea, H, d, T, P, k)
+    g = torch.Generator().manual_seed(3)
+    q = (torch.randn(1, H, T, d, generator=g) * d ** -0.5).bfloat16().to(DEV)
+    kk = torch.randn(1, H, T, d, generator=g).bfloat16().to(DEV)
+    v = torch.randn(1, H, T, d, generator=g).bfloat16().to(DEV)
+    with torch.no_grad():
+        perf = m.performer_prefix(q, kk, v, 1400)
+        for t0, t1 in ((0, 300), (300, 1111), (1111, 1400)):
+            a = m.forward_query_block(q, kk, v, t0, t1, performer=perf)
+            b = m.forward_query_block(q, kk, v, t0, t1)
+            assert torch.equal(a.estimated_attention_probs, b.estimated_attention_probs)
+            assert torch.equal(a.context_layer, b.context_layer)
+        with pytest.raises(sea.SeaError):
+            m.forward_query_block(q, kk, v, 1300, 1500, performer=perf)            # the prefix does not cover the block
