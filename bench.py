@@ -299,8 +299,17 @@ def run_c5(args):
         n_blocks = -(-n_blocks // world) * world
         mine = [par.query_block_bounds(T, n_blocks, b) for b in range(rank, n_blocks, world)]       # round-robin: late (longer) blocks spread evenly
 
+        exchange = world > 1 and not args.no_exchange and sea.ops.performer_range_supported(q, mod.performer.projection_matrix)
+
         def step():
             outs = None
+            if exchange:
+                # contiguous rows per rank (the O(T k) gather attention costs the same for every row); the linear-attention stage runs over
+                # the rank's own rows only, started from the state sums the ranks exchange (one NCCL all-gather of ~3 MB per rank)
+                perf, (r0, r1) = par.performer_exchanged(mod, q, kk, v, world, rank)
+                for b0 in range(r0, r1, rows_per_block):
+                    outs = mod.forward_query_block(q, kk, v, b0, min(b0 + rows_per_block, r1), performer=perf).context_layer
+                return outs
             live = [(t0, t1) for t0, t1 in mine if t1 > t0]
             # a rank that walks several blocks runs the linear-attention stage once over its longest prefix (no exchange with other ranks)
             perf = mod.performer_prefix(q, kk, v, max(t1 for _, t1 in live)) if len(live) > 1 else None
@@ -333,7 +342,9 @@ def run_c5(args):
         _emit({'metric': 'SEA attn layer fwd tokens/sec, long-context sweep (BASELINE configs[4])', 'unit': 'tokens/s', 'n_gpus': world,
                'value': sweep[-1]['tokens_per_s'], 'higher_is_better': True, 'scaling': 'strong', 'dtype': 'bf16', 'data': 'synthetic',
                'config': {'workload': f'SEA attention layer alone, 32 heads d={d}, k={k}, predictor_length={P}, nbf={nbf}, causal, N=1, seq sweep',
-                          'sharding': 'query blocks (K/V replicated, Performer prefix recomputed locally, 8-row CNN halo); no collective'},
+                          'sharding': ('contiguous query rows per rank, K/V replicated, 8-row CNN halo; one collective: all-gather of the Performer state sums '
+                                       '(exclusive scan across ranks)') if world > 1 and not args.no_exchange else
+                                      'query blocks (K/V replicated, Performer prefix computed once per rank, 8-row CNN halo); no collective'},
                'sweep': sweep})
     if dist is not None:
         dist.barrier()
@@ -353,6 +364,7 @@ def main():
                     help="ns: the north-star layer forward (default, the contract line); c5 / c5-d64: BASELINE configs[4], the layer alone over a "
                          "sequence sweep, query-block sharded over the ranks (d=128 k=128 / d=64 k=64)")
     ap.add_argument('--seqs', default='4096,8192,16384,32768,65536,131072')
+    ap.add_argument('--no-exchange', action='store_true', help='c5 at N > 1: every rank recomputes the Performer prefix instead of exchanging state sums')
     args = ap.parse_args()
     _claim_stdout()
     if args.impl == 'reference':

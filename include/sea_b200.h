@@ -161,6 +161,17 @@ SEA_API int sea_performer_causal_mma_fwd(const void* q, int64_t q_sn, int64_t q_
                                          const void* v, int64_t v_sn, int64_t v_sh, int64_t v_st,
                                          const float* pos_emb, const float* proj, void* ctx, void* cumavg, float* workspace,
                                          int N, int H, int T, int D, int F, void* stream);
+/* The same stage for a RANGE of a sequence that is sharded over ranks by query block: q / k / v / pos_emb point at the first
+ * row of the range (T rows), t_off = its absolute position.  phase 1: per-chunk sums of the range into `workspace` and their total
+ * (`total`, sea_performer_mma_state_floats floats: S, z and the running sum of v, per (n, h, slab)) -- what the ranks exchange;
+ * phase 2: exclusive prefix starting from `init` (the summed totals of everything before the range; NULL = zero) + the outputs, reusing
+ * the workspace of phase 1; phase 0: both, from zero.  q and ctx may be NULL in phase 1. */
+SEA_API int64_t sea_performer_mma_state_floats(int N, int H, int D, int F);
+SEA_API int sea_performer_causal_mma_range(const void* q, int64_t q_sn, int64_t q_sh, int64_t q_st,
+                                           const void* k, int64_t k_sn, int64_t k_sh, int64_t k_st,
+                                           const void* v, int64_t v_sn, int64_t v_sh, int64_t v_st,
+                                           const float* pos_emb, const float* proj, void* ctx, void* cumavg, float* workspace,
+                                           const float* init, float* total, int N, int H, int T, int D, int F, int t_off, int phase, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * a4  predictor MLP (attention.py:190-196,242-245,289-291,577-625) for the causal predictor:

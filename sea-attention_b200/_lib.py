@@ -54,6 +54,8 @@ _SIGNATURES = {
     'sea_performer_mma_supported': (_I, [_I, _I, _I]),
     'sea_performer_mma_workspace_floats': (_L, [_I, _I, _I, _I, _I]),
     'sea_performer_causal_mma_fwd': (_I, [_P, _L, _L, _L, _P, _L, _L, _L, _P, _L, _L, _L, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    'sea_performer_mma_state_floats': (_L, [_I, _I, _I, _I]),
+    'sea_performer_causal_mma_range': (_I, [_P, _L, _L, _L, _P, _L, _L, _L, _P, _L, _L, _L, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     'sea_predictor_mlp_umma_supported': (_I, [_I, _I, _I, _I, _I]),
     'sea_predictor_mlp_umma_workspace_bytes': (_L, []),
     'sea_predictor_mlp_umma_fwd': (_I, [_P, _P, _L, _L, _L] + [_P] * 10 + [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
@@ -122,7 +124,7 @@ def load():
 KERNELS_PER_CALL = {
     'sea_topk_mask_bits': 1, 'sea_mask_float_to_bits': 1, 'sea_mask_bits_to_float': 1, 'sea_csr_count': 2, 'sea_csr_fill': 1, 'sea_csr_count_len': 2, 'sea_csr_fill_len': 1, 'sea_performer_noncausal_len_fwd': 4, 'sea_bert_avg_len_fwd': 1, 'sea_decode_step': 9, 'sea_crow_scan': 1,
     'sea_flat_csr_to_dense': 1, 'sea_flat_csr_masked_bmm': 1, 'sea_flat_csr_softmax': 1, 'sea_flat_csr_elmul': 1,
-    'sea_flat_csr_sdbmm': 1, 'sea_resize_m_to_t_dense': 1, 'sea_performer_causal_fwd': 3, 'sea_performer_causal_mma_fwd': 3, 'sea_predictor_mlp_fwd': 1,
+    'sea_flat_csr_sdbmm': 1, 'sea_resize_m_to_t_dense': 1, 'sea_performer_causal_fwd': 3, 'sea_performer_causal_mma_fwd': 3, 'sea_performer_causal_mma_range': 2, 'sea_predictor_mlp_fwd': 1,
     'sea_causal_conv3x3_dil2_relu': 1, 'sea_causal_conv3x3_dil2_relu_umma': 2, 'sea_conv1x1_umma': 2, 'sea_causal_conv3x3_dil2_relu_conv1x1_umma': 3, 'sea_predictor_mlp_umma_fwd': 2, 'sea_predictor_mlp_umma_fwd_ex': 2, 'sea_predictor_mlp_mma_fwd': 2, 'sea_predictor_tail_topk_fwd': 1, 'sea_predictor_tail_fwd': 1, 'sea_sparse_attention_fwd': 1, 'sea_sparse_attention_bits_fwd': 1, 'sea_block_attention_fwd': 1, 'sea_sparse_attention_bits_bwd': 2, 'sea_performer_noncausal_fwd': 4, 'sea_conv3x3_cl': 1, 'sea_bert_tail_fwd': 1,
     'sea_topk_mask_bits_batch': 1, 'sea_topk_mask_bits_batch_ws': 12, 'sea_bert_avg_fwd': 1,
 }

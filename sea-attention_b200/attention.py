@@ -392,7 +392,9 @@ class PerlinAttention(nn.Module):
         the PerlinAttentionOutput of query rows [t0, t1) only (context_layer [N, t1-t0, H*d]).  Concatenating the blocks of a
         partition of [0, T) reproduces forward() on the whole sequence; blocks need nothing from each other.
         performer = performer_prefix(q, k, v, t_end >= t1): a rank that walks SEVERAL blocks computes the linear-attention stage once
-        over its longest prefix and hands it to every block, instead of recomputing the prefix sums per block."""
+        over its longest prefix and hands it to every block, instead of recomputing the prefix sums per block.  A triple
+        (ctx, cumavg, t_start) covers rows [t_start, ...) only (parallel.performer_exchanged: each rank computes its own range and the
+        ranks exchange their state sums)."""
         if not self.pconfig.causal:
             raise SeaError('query-block sharding is defined for the causal model')
         if self.training:
@@ -458,9 +460,10 @@ class PerlinAttention(nn.Module):
 
         # a2+a3 (+ running mean for a13)
         if performer is not None:
-            if block is None or lora_v is not None or row_valid is not None or performer[0].shape[2] < t1:
-                raise SeaError('a precomputed Performer prefix belongs to a query block and must cover its rows')
-            ctx, cumavg = performer[0][:, :, :t1], performer[1][:, :, :t1]
+            ts = int(performer[2]) if len(performer) > 2 else 0
+            if block is None or lora_v is not None or row_valid is not None or ts > h0 or ts + performer[0].shape[2] < t1:
+                raise SeaError('a precomputed Performer prefix belongs to a query block and must cover its rows (halo included)')
+            ctx, cumavg = performer[0], performer[1]          # rows [ts, ...): sliced to the block below
         elif lora_v is not None:
             if row_valid is not None:
                 raise SeaError('padded rows together with a separate v_for_atten are not implemented')
@@ -481,8 +484,9 @@ class PerlinAttention(nn.Module):
                 raise SeaError('QUERY_SKIPS > 1 needs T % QUERY_SKIPS == 0 and is not combined with query blocks / the decode state')
             ctx, v_mlp = ctx[:, :, ::query_skips].contiguous(), v[:, :, ::query_skips].contiguous()
         if block is not None:
-            ctx, v_mlp = ctx[:, :, h0:t1].contiguous(), v[:, :, h0:t1]
-            cumavg = cumavg[:, :, t0:t1]
+            ts = (int(performer[2]) if len(performer) > 2 else 0) if performer is not None else 0
+            ctx, v_mlp = ctx[:, :, h0 - ts:t1 - ts].contiguous(), v[:, :, h0:t1]
+            cumavg = cumavg[:, :, t0 - ts:t1 - ts]
         # a4
         # (weight packings of the tensor-core kernels are cached per module and re-made only when a parameter changes)
         pk = self._packed

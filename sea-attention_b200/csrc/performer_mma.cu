@@ -299,7 +299,7 @@ performer_out_mma_kernel(const __nv_bfloat16* __restrict__ q, int64_t q_sn, int6
                          const __nv_bfloat16* __restrict__ k, int64_t k_sn, int64_t k_sh, int64_t k_st,
                          const __nv_bfloat16* __restrict__ v, int64_t v_sn, int64_t v_sh, int64_t v_st,
                          const float* __restrict__ pos_emb, const float* __restrict__ proj, const float* __restrict__ ws,
-                         __nv_bfloat16* __restrict__ ctx, __nv_bfloat16* __restrict__ cumavg, int H, int T, int F, int nchunks) {
+                         __nv_bfloat16* __restrict__ ctx, __nv_bfloat16* __restrict__ cumavg, int H, int T, int F, int nchunks, int t_off) {
     using SM = PerfSmem<kFp, kDm>;
     constexpr int kLdQ = SM::kLdQ;
     extern __shared__ __align__(16) __nv_bfloat16 sm[];
@@ -475,7 +475,8 @@ performer_out_mma_kernel(const __nv_bfloat16* __restrict__ q, int64_t q_sn, int6
                 }
             }
         }
-        const float r_lo = 1.0f / (float) (r0 + row_lo + 1), r_hi = 1.0f / (float) (r0 + row_hi + 1);
+        // (t_off: absolute position of row 0 when the call covers a later range of the sequence)
+        const float r_lo = 1.0f / (float) (t_off + r0 + row_lo + 1), r_hi = 1.0f / (float) (t_off + r0 + row_hi + 1);
         __nv_bfloat16* ab = cumavg + (((int64_t) n * H + h) * T + r0) * kDm + sl.v_off;
 #pragma unroll
         for (int nt = 0; nt < kCT; ++nt) {
@@ -492,7 +493,10 @@ performer_out_mma_kernel(const __nv_bfloat16* __restrict__ q, int64_t q_sn, int6
 // exclusive prefix over the chunk slots of one (n, h).  The loads of a batch of chunks are issued together (they are
 // independent; a naive load/store loop serialises on aliasing and costs one L2 round trip per chunk).
 __global__ void __launch_bounds__(256)
-prefix_chunks_kernel(float* __restrict__ ws, int nchunks, int64_t stride) {
+prefix_chunks_kernel(float* __restrict__ ws, int nchunks, int64_t stride, const float* __restrict__ init, float* __restrict__ total, int write_prefix) {
+    // init (nullable, [gridDim.y][stride]): the state BEFORE the first chunk (a rank's share of a sequence sharded over ranks starts from
+    // the sums of the ranks before it); total (nullable): init + all chunks; write_prefix = 0: only `total` is produced (the chunk slots
+    // keep their per-chunk sums for a later prefix pass with the exchanged init)
     pdl_launch_dependents();
     pdl_wait();
     // 16-byte accesses (stride = kFp * kEx is a multiple of 4): a quarter of the load/store instructions, same bytes in flight
@@ -500,24 +504,29 @@ prefix_chunks_kernel(float* __restrict__ ws, int nchunks, int64_t stride) {
     const int64_t stride4 = stride >> 2;
     constexpr int kBatch = 16;
     for (int64_t idx = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; idx < stride4; idx += (int64_t) gridDim.x * blockDim.x) {
-        float4 run = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 run = init ? __ldg(reinterpret_cast<const float4*>(init) + (int64_t) blockIdx.y * stride4 + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
         for (int c0 = 0; c0 < nchunks; c0 += kBatch) {
             float4 cur[kBatch];
 #pragma unroll
             for (int i = 0; i < kBatch; ++i) cur[i] = (c0 + i < nchunks) ? __ldcg(base + (int64_t) (c0 + i) * stride4 + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int i = 0; i < kBatch; ++i) {
-                if (c0 + i < nchunks) __stcg(base + (int64_t) (c0 + i) * stride4 + idx, run);
+                if (write_prefix && c0 + i < nchunks) __stcg(base + (int64_t) (c0 + i) * stride4 + idx, run);
                 run.x += cur[i].x; run.y += cur[i].y; run.z += cur[i].z; run.w += cur[i].w;
             }
         }
+        if (total) reinterpret_cast<float4*>(total)[(int64_t) blockIdx.y * stride4 + idx] = run;
     }
 }
 
+// phase 0: the whole stage (sums, prefix from zero, outputs).  Sequence sharded over ranks: phase 1 = per-chunk sums of this
+// rank's range + their total (-> exchanged between the ranks), phase 2 = prefix starting from `init` (the sums of everything before the
+// range) + outputs; `ws` carries the per-chunk sums from phase 1 to phase 2.
 template <int kFp, int kDm>
 int launch_performer_mma(const void* q, int64_t q_sn, int64_t q_sh, int64_t q_st, const void* k, int64_t k_sn, int64_t k_sh, int64_t k_st,
                          const void* v, int64_t v_sn, int64_t v_sh, int64_t v_st, const float* pos_emb, const float* proj,
-                         void* ctx, void* cumavg, float* ws, int N, int H, int T, int F, cudaStream_t s) {
+                         void* ctx, void* cumavg, float* ws, int N, int H, int T, int F, cudaStream_t s,
+                         int phase = 0, const float* init = nullptr, float* total = nullptr, int t_off = 0) {
     using SM = PerfSmem<kFp, kDm>;
     const int nchunks = (T + kCh - 1) / kCh;
     constexpr int kSlabs = n_slabs(kDm);
@@ -527,14 +536,19 @@ int launch_performer_mma(const void* q, int64_t q_sn, int64_t q_sh, int64_t q_st
     SEA_CUDA_TRY(cudaFuncSetAttribute(ka, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kSumsBytes), "smem attr");
     SEA_CUDA_TRY(cudaFuncSetAttribute(kc, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kBytes), "smem attr");
     using B = __nv_bfloat16;
-    SEA_CUDA_TRY(launch_pdl(ka, grid, dim3(kThreads), (size_t) SM::kSumsBytes, s, (const B*) k, k_sn, k_sh, k_st, (const B*) v, v_sn, v_sh, v_st, pos_emb, proj, ws, H, T, F,
-                            nchunks), "performer_sums_mma_kernel launch");
     const int64_t stride = (int64_t) kFp * kEx;
+    const dim3 pgrid((unsigned) ((stride / 4 + 255) / 256), N * H * kSlabs);
+    if (phase == 0 || phase == 1)
+        SEA_CUDA_TRY(launch_pdl(ka, grid, dim3(kThreads), (size_t) SM::kSumsBytes, s, (const B*) k, k_sn, k_sh, k_st, (const B*) v, v_sn, v_sh, v_st, pos_emb, proj, ws, H, T, F,
+                                nchunks), "performer_sums_mma_kernel launch");
+    if (phase == 1) {
+        SEA_CUDA_TRY(launch_pdl(prefix_chunks_kernel, pgrid, dim3(256), (size_t) 0, s, ws, nchunks, stride, (const float*) nullptr, total, 0), "prefix_chunks_kernel launch");
+        return SEA_OK;
+    }
     // one exclusive prefix per (n, h, slab): the slabs' chunk slots are laid out [nh][slab][chunk]
-    SEA_CUDA_TRY(launch_pdl(prefix_chunks_kernel, dim3((unsigned) ((stride / 4 + 255) / 256), N * H * kSlabs), dim3(256), (size_t) 0, s, ws, nchunks, stride),
-                 "prefix_chunks_kernel launch");
+    SEA_CUDA_TRY(launch_pdl(prefix_chunks_kernel, pgrid, dim3(256), (size_t) 0, s, ws, nchunks, stride, init, total, 1), "prefix_chunks_kernel launch");
     SEA_CUDA_TRY(launch_pdl(kc, grid, dim3(kThreads), (size_t) SM::kBytes, s, (const B*) q, q_sn, q_sh, q_st, (const B*) k, k_sn, k_sh, k_st, (const B*) v, v_sn, v_sh, v_st,
-                            pos_emb, proj, (const float*) ws, (B*) ctx, (B*) cumavg, H, T, F, nchunks), "performer_out_mma_kernel launch");
+                            pos_emb, proj, (const float*) ws, (B*) ctx, (B*) cumavg, H, T, F, nchunks, t_off), "performer_out_mma_kernel launch");
     return SEA_OK;
 }
 
@@ -570,7 +584,24 @@ int sea_performer_causal_mma_fwd(const void* q, int64_t q_sn, int64_t q_sh, int6
                                  const void* v, int64_t v_sn, int64_t v_sh, int64_t v_st,
                                  const float* pos_emb, const float* proj, void* ctx, void* cumavg, float* workspace,
                                  int N, int H, int T, int D, int F, void* stream) {
-    SEA_CHECK_ARG(q && k && v && pos_emb && proj && ctx && workspace, "sea_performer_causal_mma_fwd: null pointer");
+    return sea_performer_causal_mma_range(q, q_sn, q_sh, q_st, k, k_sn, k_sh, k_st, v, v_sn, v_sh, v_st, pos_emb, proj, ctx, cumavg, workspace, nullptr, nullptr,
+                                          N, H, T, D, F, 0, 0, stream);
+}
+
+int64_t sea_performer_mma_state_floats(int N, int H, int D, int F) {
+    if (N <= 0 || H <= 0 || F <= 0 || D <= 0) return 0;
+    const int Fp = ((F + 1) + 15) & ~15;
+    return (int64_t) N * H * ((2 * D + kE - 1) / kE) * Fp * kEx;
+}
+
+int sea_performer_causal_mma_range(const void* q, int64_t q_sn, int64_t q_sh, int64_t q_st,
+                                   const void* k, int64_t k_sn, int64_t k_sh, int64_t k_st,
+                                   const void* v, int64_t v_sn, int64_t v_sh, int64_t v_st,
+                                   const float* pos_emb, const float* proj, void* ctx, void* cumavg, float* workspace,
+                                   const float* init, float* total, int N, int H, int T, int D, int F, int t_off, int phase, void* stream) {
+    SEA_CHECK_ARG(k && v && pos_emb && proj && workspace && (phase == 1 || (q && ctx)) && phase >= 0 && phase <= 2 && t_off >= 0 &&
+                  (phase != 1 || total), "sea_performer_causal_mma_fwd: null pointer");
+    if (phase == 1) { q = k; q_sn = k_sn; q_sh = k_sh; q_st = k_st; }
     if (!sea_performer_mma_supported(SEA_DTYPE_BF16, D, F)) {
         set_error("sea_performer_causal_mma_fwd: unsupported shape D=%d F=%d", D, F);
         return SEA_ERR_UNSUPPORTED;
@@ -583,7 +614,8 @@ int sea_performer_causal_mma_fwd(const void* q, int64_t q_sn, int64_t q_sh, int6
     const int Fp = ((F + 1) + 15) & ~15;
 #define SEA_PF_CASE(FF, DD)                                                                                                                   \
     if (Fp == FF && D == DD)                                                                                                                  \
-        return launch_performer_mma<FF, DD>(q, q_sn, q_sh, q_st, k, k_sn, k_sh, k_st, v, v_sn, v_sh, v_st, pos_emb, proj, ctx, cumavg, workspace, N, H, T, F, s)
+        return launch_performer_mma<FF, DD>(q, q_sn, q_sh, q_st, k, k_sn, k_sh, k_st, v, v_sn, v_sh, v_st, pos_emb, proj, ctx, cumavg, workspace, N, H, T, F, s, \
+                                            phase, init, total, t_off)
     SEA_PF_CASE(16, 32); SEA_PF_CASE(32, 32);
     SEA_PF_CASE(16, 64); SEA_PF_CASE(32, 64); SEA_PF_CASE(48, 64); SEA_PF_CASE(64, 64);
     SEA_PF_CASE(32, 80); SEA_PF_CASE(48, 80); SEA_PF_CASE(64, 80);

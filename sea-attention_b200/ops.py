@@ -310,6 +310,50 @@ def performer_causal(q, k, v, pos_emb, proj, want_cumavg=True, force_simt=False)
     return ctx, avg
 
 
+def performer_range_supported(q, proj) -> bool:
+    """Can the ranged (sharded-sequence) Performer entries take these tensors?  (bf16, a head dim / feature count the MMA kernels cover)"""
+    return bool(q.is_cuda and _lib.load().sea_performer_mma_supported(_DTYPES.get(q.dtype, -1), q.shape[-1], proj.shape[0]))
+
+
+def performer_causal_range_sums(k, v, pos_rows, proj):
+    """Phase 1 of the Performer over a RANGE of a sequence sharded over ranks: k, v [N,H,Tr,D] and pos_rows fp32 [Tr,D] are
+    the rows of the range.  -> (workspace with the per-chunk sums, total fp32 [state_floats]): `total` = (S, z, sum of v) of the range,
+    the quantity the ranks exchange."""
+    _cuda(k, v, pos_rows, proj)
+    N, H, Tr, D = k.shape
+    F = proj.shape[0]
+    k, v = _inner_contig(k), _inner_contig(v)
+    pos = _dense(pos_rows.reshape(-1, D), torch.float32)
+    pj = _dense(proj, torch.float32)
+    lib = _lib.load()
+    if pos.shape[0] < Tr or not lib.sea_performer_mma_supported(_DTYPES.get(k.dtype, -1), D, F):
+        raise SeaError('performer_causal_range_sums: unsupported dtype / head dim / feature count, or too few position rows')
+    ws = torch.empty((lib.sea_performer_mma_workspace_floats(N, H, Tr, D, F),), dtype=torch.float32, device=k.device)
+    total = torch.empty((lib.sea_performer_mma_state_floats(N, H, D, F),), dtype=torch.float32, device=k.device)
+    _lib.call('sea_performer_causal_mma_range', None, 0, 0, 0, k.data_ptr(), k.stride(0), k.stride(1), k.stride(2), v.data_ptr(), v.stride(0), v.stride(1), v.stride(2),
+              pos.data_ptr(), pj.data_ptr(), None, None, ws.data_ptr(), None, total.data_ptr(), N, H, Tr, D, F, 0, 1, _stream())
+    return ws, total
+
+
+def performer_causal_range_out(q, k, v, pos_rows, proj, ws, init, t_off: int, want_cumavg=True):
+    """Phase 2: outputs of the range whose per-chunk sums `ws` holds (performer_causal_range_sums on the same rows), starting from `init`
+    = the summed totals of everything before the range (None = the range starts the sequence); t_off = absolute position of its first
+    row.  -> ctx [N,H,Tr,2D], cumavg [N,H,Tr,D]."""
+    _cuda(q, k, v, pos_rows, proj, ws, init)
+    N, H, Tr, D = q.shape
+    F = proj.shape[0]
+    q, k, v = _inner_contig(q), _inner_contig(k), _inner_contig(v)
+    pos = _dense(pos_rows.reshape(-1, D), torch.float32)
+    pj = _dense(proj, torch.float32)
+    ini = None if init is None else _dense(init, torch.float32)
+    ctx = torch.empty((N, H, Tr, 2 * D), dtype=q.dtype, device=q.device)
+    avg = torch.empty((N, H, Tr, D), dtype=q.dtype, device=q.device) if want_cumavg else None
+    _lib.call('sea_performer_causal_mma_range', q.data_ptr(), q.stride(0), q.stride(1), q.stride(2), k.data_ptr(), k.stride(0), k.stride(1), k.stride(2),
+              v.data_ptr(), v.stride(0), v.stride(1), v.stride(2), pos.data_ptr(), pj.data_ptr(), ctx.data_ptr(), _p(avg), ws.data_ptr(), _p(ini), None,
+              N, H, Tr, D, F, int(t_off), 2, _stream())
+    return ctx, avg
+
+
 class PackedWeights:
     """Per-module holder of the bf16 weight packings the tensor-core kernels keep in their workspace.
 

@@ -2,8 +2,10 @@
 
 The path shards with NO exchange step: every stage is independent across batch items, and -- for long contexts --
 across query blocks given replicated K/V.  One process per GPU; `torch.distributed` (NCCL over NVLink/NVSwitch on the
-GPU box, gloo in the CPU tests) is used only (a) for barriers / max-over-ranks timing and (b) when a caller asks for
-the full context tensor on every rank (`all_gather_context`).  Nothing here launches a collective on the hot path.
+GPU box, gloo in the CPU tests) is used (a) for barriers / max-over-ranks timing, (b) when a caller asks for
+the full context tensor on every rank (`all_gather_context`), and (c) for the one exchange a sharded long-context prefill has: the
+exclusive scan of the Performer state sums across ranks (`performer_exchanged`, an all-gather of ~3 MB per rank), which replaces
+every rank's recomputation of the prefix before its rows.
 """
 from typing import List, Optional, Tuple
 
@@ -74,6 +76,70 @@ def forward_query_sharded(module, q, k, v, world_size: int, rank: int, gather: b
         b, e = query_block_bounds(T, world_size, r)
         parts.append(bufs[r][:, : e - b])
     return torch.cat(parts, dim=1)
+
+
+def contiguous_query_range(T: int, world_size: int, rank: int, align: int = 128) -> Tuple[int, int]:
+    """Rank `rank`'s CONTIGUOUS share [t0, t1) of T query rows, boundaries on multiples of `align`.  For long contexts the attention
+    is the O(T k) gather kernel -- a constant number of entries per row -- so equal contiguous ranges are balanced."""
+    blocks = -(-T // align)
+    b0, b1 = shard_bounds(blocks, world_size, rank)
+    return min(b0 * align, T), min(b1 * align, T)
+
+
+def performer_range_state(module, q, k, v, t0: int, t1: int, is_last: bool):
+    """Step 1 of performer_exchanged for the rows [t0, t1) of one rank: the chunk sums of its range [h0, t1) (h0 = t0 - halo) and the
+    [2, state] tensor the ranks exchange -- row 0 the sums of the range, row 1 the sums of its last `halo` rows (zero for the last rank),
+    which the next rank's range overlaps.  -> (workspace or None, state, h0)."""
+    from . import ops
+    halo = 4 * len(module._cnn_convs()[0])
+    h0 = max(t0 - halo, 0)
+    w = module._weights_fp32()
+    pos, proj = w['pos'], w['proj']
+    if t1 <= t0:
+        n = int(ops._lib.load().sea_performer_mma_state_floats(q.shape[0], q.shape[1], q.shape[3], proj.shape[0]))
+        return None, torch.zeros((2, n), dtype=torch.float32, device=q.device), h0
+    ws, total = ops.performer_causal_range_sums(k[:, :, h0:t1], v[:, :, h0:t1], pos[h0:t1], proj)
+    if not is_last and t1 - halo >= h0:
+        _, tail = ops.performer_causal_range_sums(k[:, :, t1 - halo:t1], v[:, :, t1 - halo:t1], pos[t1 - halo:t1], proj)
+    else:
+        tail = torch.zeros_like(total)
+    return ws, torch.stack([total, tail]), h0
+
+
+def performer_range_finish(module, q, k, v, t0: int, t1: int, ws, states_before: List[torch.Tensor]):
+    """Step 2: prefix from state(h0) = sum over the ranks before of (total - tail), then the outputs of [h0, t1).
+    -> (ctx [N,H,t1-h0,2d], cumavg [N,H,t1-h0,d], h0), the `performer=` argument of PerlinAttention.forward_query_block."""
+    from . import ops
+    halo = 4 * len(module._cnn_convs()[0])
+    h0 = max(t0 - halo, 0)
+    w = module._weights_fp32()
+    init = None
+    for st in states_before:
+        part = st[0] - st[1]
+        init = part if init is None else init + part
+    ctx, cumavg = ops.performer_causal_range_out(q[:, :, h0:t1], k[:, :, h0:t1], v[:, :, h0:t1], w['pos'][h0:t1], w['proj'], ws, init, h0)
+    return ctx, cumavg, h0
+
+
+def performer_exchanged(module, q, k, v, world_size: int, rank: int, group: Optional[dist.ProcessGroup] = None, t_range: Optional[Tuple[int, int]] = None):
+    """The linear-attention stage of a query-block sharded prefill WITHOUT redundant prefix work ("one tiny exclusive-scan
+    exchange of the Performer state"): every rank runs the chunk sums over its own rows [h0, t1) only (h0 = t0 - halo: the predictor CNN of
+    its first rows looks `halo` rows back), the ranks all-gather two small state tensors -- the sums of their range and of its last `halo`
+    rows, which the next rank's range overlaps -- and each rank starts its prefix from the sums of everything before h0:
+        state(h0_r) = sum_{r' < r} (total_r' - tail_r')            (S, z and the running sum of v; fp32)
+    This is the one collective of the path (NCCL all-gather of ~3 MB per rank over NVLink / NVSwitch); K and V stay replicated.
+    -> ((ctx, cumavg, h0) or None for an empty range, (t0, t1))."""
+    T = q.shape[2]
+    t0, t1 = contiguous_query_range(T, world_size, rank) if t_range is None else t_range
+    ws, state, h0 = performer_range_state(module, q, k, v, t0, t1, is_last=rank == world_size - 1)
+    if world_size > 1:
+        gathered = [torch.empty_like(state) for _ in range(world_size)]
+        dist.all_gather(gathered, state, group=group)
+    else:
+        gathered = [state]
+    if t1 <= t0:
+        return None, (t0, t1)
+    return performer_range_finish(module, q, k, v, t0, t1, ws, gathered[:rank]), (t0, t1)
 
 
 def max_over_ranks(value: float, device, group: Optional[dist.ProcessGroup] = None) -> float:

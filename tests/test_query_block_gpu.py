@@ -112,3 +112,39 @@ def test_query_blocks_with_a_shared_performer_prefix(sea):
             assert torch.equal(a.context_layer, b.context_layer)
         with pytest.raises(sea.SeaError):
             m.forward_query_block(q, kk, v, 1300, 1500, performer=perf)            # the prefix does not cover the block
+
+
+@pytest.mark.parametrize('H,d,T,P,k,world', [(32, 128, 2048, 256, 128, 4), (32, 64, 1900, 256, 64, 3), (8, 80, 1000, 128, 32, 2)])
+def test_exchanged_performer_state_reproduces_the_full_prefill(sea, H, d, T, P, k, world):
+    """parallel.performer_exchanged without the network: every "rank" computes the sums of its own rows only, the [2, state] tensors
+    are passed around in place of the all-gather, and each rank's blocks, started from sum(total - tail) of the ranks before it,
+    concatenate to the unsharded forward."""
+    par = importlib.import_module(sea.__name__ + '.parallel')
+    m = _module(sea, H, d, T, P, k)
+    g = torch.Generator().manual_seed(T)
+    q = (torch.randn(1, H, T, d, generator=g) * d ** -0.5).bfloat16().to(DEV)
+    kk = torch.randn(1, H, T, d, generator=g).bfloat16().to(DEV)
+    v = torch.randn(1, H, T, d, generator=g).bfloat16().to(DEV)
+    with torch.no_grad():
+        full = m(q, kk, v, q, kk, v, q, kk, None, None, None)
+        ranges = [par.contiguous_query_range(T, world, r) for r in range(world)]
+        assert ranges[0][0] == 0 and ranges[-1][1] == T and all(ranges[i][1] == ranges[i + 1][0] for i in range(world - 1))
+        step1 = [par.performer_range_state(m, q, kk, v, t0, t1, is_last=(r == world - 1)) for r, (t0, t1) in enumerate(ranges)]
+        parts, probs = [], []
+        for r, (t0, t1) in enumerate(ranges):
+            if t1 <= t0:
+                continue
+            perf = par.performer_range_finish(m, q, kk, v, t0, t1, step1[r][0], [s_[1] for s_ in step1[:r]])
+            assert perf[2] == max(t0 - 8, 0) and perf[0].shape[2] == t1 - perf[2]
+            o = m.forward_query_block(q, kk, v, t0, t1, performer=perf)
+            parts.append(o.context_layer)
+            probs.append(o.estimated_attention_probs)
+    torch.cuda.synchronize()
+    pr = torch.cat(probs, dim=2)
+    # the prefix state reaches a row through a different summation order (per-rank totals instead of per-chunk prefixes): bf16-level noise
+    # on the Performer output, near-ties of the top-k may move
+    err = (pr - full.estimated_attention_probs).abs()
+    assert float(err.max()) < 2e-2 and float(err.mean()) < 2e-5, (float(err.max()), float(err.mean()))
+    ctx = torch.cat(parts, dim=1)
+    bad = (ctx.float() - full.context_layer.float()).abs() > 3e-2 + 3e-2 * full.context_layer.float().abs()
+    assert float(bad.float().mean()) < 1e-2, float(bad.float().mean())          # (moved near-ties of the top-k: a few rows pick other pixels)
