@@ -235,7 +235,7 @@ def run_reference(args):
     torch.manual_seed(42)
     step, kind, note = _reference_step(H, d, T, P, k, nbf)
     # exactly --warmup / --steps iterations, unless that would run past the wall-clock budget (then fewer, and the line says so)
-    budget = float(os.environ.get('SEA_REF_BUDGET_S', '900'))
+    budget = float(os.environ.get('SEA_REF_BUDGET_S', '240'))
     t0 = time.perf_counter()
     step()
     first = time.perf_counter() - t0
