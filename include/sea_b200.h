@@ -354,6 +354,11 @@ SEA_API int sea_performer_causal_state_fwd(const void* q, int64_t q_sn, int64_t 
                                            const float* pos_emb, const float* proj, int dtype, float* state, void* ctx, void* cumavg,
                                            int N, int H, int T_new, int t0, int D, int F, void* stream);
 
+/* Development aid: with SEA_ATTN_TRACE=1 in the environment sea_block_attention_fwd launches an instrumented instance of the tcgen05
+ * attention kernel that records, per CTA and warp, eight cycle counters (where the softmax and MMA warps wait); this call copies the
+ * counters of the last such launch to `host` ([ctas][20][8] uint32) and returns the number of CTAs (0: nothing traced). Synchronises. */
+SEA_API int64_t sea_debug_attn_trace_read(uint32_t* host, int64_t max_words);
+
 /* One decode step (use_cache, one new token per item) of the causal layer in ONE call (csrc/decode_step.cu; reference:
  * attention_state.py:43-236 + attention.py:559-572, 627-639, 774-947, 1151-1173, 1222-1244): incremental Performer + running mean,
  * predictor MLP on the token, the two dilated convs on 5-row windows, tail + softmax, top-k of the row, sparse attention of the row over

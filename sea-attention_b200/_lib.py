@@ -91,6 +91,7 @@ _SIGNATURES = {
     'sea_topk_batch_workspace_bytes': (_L, [_I, _I, _I, _I, _I]),
     'sea_topk_mask_bits_batch_ws': (_I, [_P, _P, _P, _P, _L, _I, _I, _I, _I, _I, _P]),
     'sea_bert_avg_fwd': (_I, [_P, _P, _L, _L, _L, _I, _P, _I, _I, _I, _I, _I, _P]),
+    'sea_debug_attn_trace_read': (_L, [_P, _L]),
     'sea_decode_step_workspace_bytes': (_L, [_I] * 8),
     'sea_decode_step': (_I, [_P, _L, _L, _P, _L, _L, _L, _P, _L, _L, _L, _I] + [_P] * 20 + [_P, _P, _P, _I, _P] + [_P] * 6 + [_P, _P, _P, _L]
                         + [_I] * 10 + [_P]),

@@ -422,15 +422,16 @@ extern "C" {
 
 // bf16 up to T_SRC = 4096 runs the tcgen05 kernel, which interpolates the mask itself from the top-k bits (no dense mask, no
 // expansion kernel); fp16 and longer rows run the mma.sync kernel over the dense bit mask written by expand_mask_kernel.
-static bool use_umma_kernel(int dtype, int T_SRC) {
+static bool use_umma_kernel(int dtype, int T_SRC, int P) {
     static const bool force_mma_sync = getenv("SEA_ATTN_MMA_SYNC") != nullptr;      // A/B timing switch
-    return dtype == SEA_DTYPE_BF16 && !force_mma_sync && T_SRC <= 4096;              // measured: mma.sync ahead at T = 8192
+    // (its in-kernel interpolation uses the exact integer pixel edges: P a power of two, <= 512)
+    return dtype == SEA_DTYPE_BF16 && !force_mma_sync && T_SRC <= 4096 && P <= 512 && exact_edge_shift(P, T_SRC) >= 0;      // measured: mma.sync ahead at T = 8192
 }
 
 int64_t sea_block_attention_workspace_bytes(int N, int H, int T_DST, int T_SRC, int D, int P, int k_clamp, int dtype) {
     if (dtype != SEA_DTYPE_BF16 && dtype != SEA_DTYPE_F16) return 0;
     if (N <= 0 || H <= 0 || H > 64 || T_DST <= 0 || T_SRC < T_DST || !block_attention_eligible(D, T_SRC, P, k_clamp)) return 0;      // (H <= 64: 6-bit head field of the expansion's pixel list)
-    if (use_umma_kernel(dtype, T_SRC)) return 16;                                                          // no workspace use; > 0 = "supported"
+    if (use_umma_kernel(dtype, T_SRC, P)) return 16;                                                          // no workspace use; > 0 = "supported"
     return (int64_t) N * H * T_DST * mask_row_words(T_SRC) * 8 + mask_act_bytes(N, H, T_DST, T_SRC);      // dense bit mask + tile activity
 }
 
@@ -454,7 +455,7 @@ int sea_block_attention_fwd(const uint32_t* mask_bits,
                   "sea_block_attention_fwd: rows must be 16-byte aligned");
     cudaStream_t s = (cudaStream_t) stream;
     const int p_lg = exact_edge_shift(P, T_SRC);      // integer pixel edges are exact iff P is a power of two and m * L stays below 2^24
-    if (use_umma_kernel(dtype, T_SRC)) {
+    if (use_umma_kernel(dtype, T_SRC, P)) {
         SEA_CHECK_ARG(mask_bits != nullptr, "sea_block_attention_fwd: the tcgen05 kernel needs the top-k bit mask");
         return launch_block_attention_umma(mask_bits, P, p_lg, q, q_sn, q_sh, q_st, k, k_sn, k_sh, k_st, v, v_sn, v_sh, v_st, scales, cumavg,
                                            avg_sh, avg_st, use_scaler, out, N, H, T_DST, T_SRC, is_causal, s);
@@ -509,5 +510,7 @@ int sea_block_attention_fwd(const uint32_t* mask_bits,
     SEA_CHECK_LAUNCH("block_attention_bits_kernel");
     return SEA_OK;
 }
+
+int64_t sea_debug_attn_trace_read(uint32_t* host, int64_t max_words) { return attn_trace_read(host, max_words); }
 
 }  // extern "C"

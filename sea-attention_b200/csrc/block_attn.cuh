@@ -13,4 +13,7 @@ int launch_block_attention_umma(const uint32_t* mask_bits, int P, int p_lg,
                                 const float* scales, const void* cumavg, int64_t avg_sh, int64_t avg_st, int use_scaler, void* out,
                                 int N, int H, int T_DST, int T_SRC, int is_causal, cudaStream_t s);
 
+// development aid (SEA_ATTN_TRACE=1): per-warp cycle counters of the last traced launch -> host; returns the number of CTAs
+int64_t attn_trace_read(uint32_t* host, int64_t max_words);
+
 }  // namespace sea

@@ -150,7 +150,14 @@ __device__ __forceinline__ void exp_group(const uint32_t (&s)[32], uint32_t mwor
     out = make_uint4(pack_bf(p[0], p[1]), pack_bf(p[2], p[3]), pack_bf(p[4], p[5]), pack_bf(p[6], p[7]));
 }
 
-template <int kUG>
+// Development aid (SEA_ATTN_TRACE=1): per-CTA cycle counters of where the softmax and MMA warps spend their time, written by lane 0 of
+// every warp into a global buffer [cta][warp][8] (read back with sea_debug_attn_trace_read; scripts/attn_trace.py prints the averages).
+// Softmax warps: 0 wait S, 1 tcgen05.ld, 2 exp / pack, 3 wait P buffer, 4 tcgen05.st + hand-off, 5 chunk boundary + mask word, 6 set-up,
+// 7 whole loop (6 = mask word + column union).  MMA warps: 0 wait S buffer, 1 issue S, 2 wait V, 3 wait P, 4 issue P.V, 5 wait K, 7 whole loop.
+__device__ uint32_t* g_attn_trace = nullptr;
+__device__ __forceinline__ uint32_t clock_lo() { return (uint32_t) clock64(); }
+
+template <int kUG, bool kTrace = false>
 __global__ void __launch_bounds__(uthreads(kUG), 3 - kUG)
 block_attention_umma_kernel(const uint32_t* __restrict__ mask_bits, int P, int p_lg,
                             const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
@@ -178,6 +185,17 @@ block_attention_umma_kernel(const uint32_t* __restrict__ mask_bits, int P, int p
 
     // warp index through a shuffle: provably warp-uniform, which keeps the MMA issue loop in the uniform datapath
     const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    uint32_t t_entry = 0;
+    if constexpr (kTrace) {
+        t_entry = clock_lo();
+        if (tid == 96 && g_attn_trace) {          // (warp 3, the idle warp, owns the CTA-level slot: SM id, start time in ns)
+            uint32_t smid; uint64_t gt;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+            g_attn_trace[((int64_t) blockIdx.x * 20 + 3) * 16 + 0] = smid;
+            g_attn_trace[((int64_t) blockIdx.x * 20 + 3) * 16 + 1] = (uint32_t) gt;
+        }
+    }
     pdl_launch_dependents();
     pdl_wait();                // the set-up below already reads the top-k bits written by the predecessor
     const int rbp = n_pairs - 1 - (int) (blockIdx.x / (unsigned) (N * H));       // heavy (late) row blocks first
@@ -221,6 +239,8 @@ block_attention_umma_kernel(const uint32_t* __restrict__ mask_bits, int P, int p
     __syncthreads();
     umma::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+#define SEA_STAMP(i) if constexpr (kTrace) { if (warp == 4 && lane == 0 && g_attn_trace) g_attn_trace[((int64_t) blockIdx.x * 20 + 3) * 16 + (i)] = clock_lo() - t_entry; }
+    SEA_STAMP(8)                 // bits in shared memory, barriers, TMEM
     // TMEM columns: S_g[b] at 128 g + 64 b, O_g at 128 G + 64 g, P_g[b] (bf16 pairs) at 192 G + 64 g + 32 b
 
     if (warp == 0) {
@@ -258,9 +278,12 @@ block_attention_umma_kernel(const uint32_t* __restrict__ mask_bits, int P, int p
         // descriptors of the k = 0 step; a k-step adds a constant to the 14-bit (address >> 4) field (no carry: smem < 256 KB)
         const uint64_t d_q0 = umma::make_desc_k_sw128(sm_a + USmem::kQ);
         const uint64_t d_kv = umma::make_desc_k_sw128(sm_a + USmem::kKV);
+        uint32_t tr[8] = {0, 0, 0, 0, 0, 0, 0, 0}, c0 = 0, cstart = 0;
+#define SEA_TR(i) if constexpr (kTrace) { const uint32_t c1_ = clock_lo(); tr[i] += c1_ - c0; c0 = c1_; }
         auto issue_s = [&](int j) {
             const int s = j % kUStages, b = j & 1;
             umma::mbar_wait(&k_full[s], (uint32_t) ((j / kUStages) & 1));
+            SEA_TR(5)
             umma::tc_fence_after();
             const uint64_t d_k = d_kv + (uint64_t) (s * (kUTile >> 4));
             for (int g = g0; g < g1; ++g) {
@@ -282,6 +305,7 @@ block_attention_umma_kernel(const uint32_t* __restrict__ mask_bits, int P, int p
             issue_s(0);
             if (nt > 1) issue_s(1);
         }
+        if constexpr (kTrace) { cstart = c0 = clock_lo(); tr[5] = 0; }
         for (int j = 0; j < nt; ++j) {
             const int s = j % kUStages, b = j & 1;
             // scores run two tiles ahead: S of tile j + 2 goes into the buffer of tile j as soon as the softmax warps have pulled tile j
@@ -289,12 +313,16 @@ block_attention_umma_kernel(const uint32_t* __restrict__ mask_bits, int P, int p
             if (j + 2 < nt) {
                 for (int g = g0; g < g1; ++g)
                     if (j + 2 < (g ? nt_b : nt_a)) umma::mbar_wait(&s_empty[g * 2 + b], (uint32_t) ((j >> 1) & 1));
+                SEA_TR(0)
                 issue_s(j + 2);
+                SEA_TR(1)
             }
             umma::mbar_wait(&v_full[s], (uint32_t) ((j / kUStages) & 1));
+            SEA_TR(2)
             for (int g = g0; g < g1; ++g) {
                 if (j < (g ? nt_b : nt_a)) {
                     umma::mbar_wait(&p_full[g * 2 + b], (uint32_t) ((j >> 1) & 1));
+                    SEA_TR(3)
                     umma::tc_fence_after();
                     const uint64_t d_v = d_kv + (uint64_t) (((kUStages + s) * kUTile) >> 4);
                     const uint32_t tP = tmem_base + 192 * kUG + 64 * g + 32 * b;
@@ -305,6 +333,11 @@ block_attention_umma_kernel(const uint32_t* __restrict__ mask_bits, int P, int p
                 }
             }
             umma::mma_commit_elect(&v_empty[s]);          // (same rule as k_empty: v_full was waited on above)
+            SEA_TR(4)
+        }
+        if constexpr (kTrace) {
+            tr[7] = clock_lo() - cstart;
+            if (lane == 0 && g_attn_trace) for (int i = 0; i < 8; ++i) g_attn_trace[((int64_t) blockIdx.x * 20 + warp) * 16 + i] = tr[i];
         }
     } else if (warp >= 4) {
         // ---------------------------------------------------------------- softmax warps: two threads per query row
@@ -328,52 +361,6 @@ block_attention_umma_kernel(const uint32_t* __restrict__ mask_bits, int P, int p
         const uint32_t a_cur = sm_a + USmem::kCur + (uint32_t) grow * 8;
         const uint32_t a_xch = sm_a + USmem::kXch + (uint32_t) grow * 4;          // + ((parity * 2 + half) * 256) * 4
 
-        // pixel cursor of this row -> element masks of chunk c (tiles 8c .. 8c+7); warp-uniform loop, one cursor step or one pixel
-        // per lane and iteration.  Cost ~ alive pixels of the row (16384 / L at the north-star shape): right for all but the
-        // shortest rows.
-        auto gen_chunk = [&](int c) {
-            const uint32_t a_w = a_mw + (uint32_t) ((c & 1) * kUChunk * kURows) * 8;
-#pragma unroll
-            for (int i = 0; i < kUChunk; ++i) sts64(a_w + i * kURows * 8, make_uint2(0u, 0u));
-            const int c_lo = c * (kUChunk * kUN), c_hi = c_lo + kUChunk * kUN;
-            const uint2 cur = lds64(a_cur);
-            int cur_w = (int) cur.x;
-            uint32_t cur_x = cur.y;
-            // runs ascend, so the 64-bit word under construction lives in registers and is stored (never re-read) when a run moves on
-            int acc_w = 0;
-            uint32_t acc_lo = 0u, acc_hi = 0u;
-            bool done = cur_w >= nw || rs.L <= c_lo;
-            while (!__all_sync(kFull, done)) {
-                if (!done) {
-                    if (cur_x == 0u) {
-                        if (++cur_w >= nw) done = true; else cur_x = lds32(a_brow + cur_w * 4);
-                    } else {
-                        const int m = (cur_w << 5) + __ffs(cur_x) - 1;
-                        const int a = rs.edge(m);
-                        if (a >= c_hi) {
-                            done = true;
-                        } else {
-                            const int b = rs.edge(m + 1);
-                            const int lo = max(a, c_lo) - c_lo, hi = min(b, c_hi) - c_lo;
-                            for (int w = lo >> 6; w <= ((hi - 1) >> 6) && hi > lo; ++w) {
-                                if (w != acc_w) {
-                                    if (acc_lo | acc_hi) sts64(a_w + acc_w * kURows * 8, make_uint2(acc_lo, acc_hi));
-                                    acc_w = w; acc_lo = acc_hi = 0u;
-                                }
-                                const int l = max(lo - (w << 6), 0), hh = min(hi - (w << 6), 64);          // bits [l, hh) of word w
-                                const uint32_t lo_l = min(l, 32), lo_h = min(hh, 32), hi_l = max(l, 32) - 32, hi_h = max(hh, 32) - 32;
-                                acc_lo |= lo_h > lo_l ? ((0xffffffffu >> (32 - (lo_h - lo_l))) << lo_l) : 0u;
-                                acc_hi |= hi_h > hi_l ? ((0xffffffffu >> (32 - (hi_h - hi_l))) << hi_l) : 0u;
-                            }
-                            if (b > c_hi) done = true;      // the run continues in the next chunk: the pixel stays under the cursor
-                            else cur_x &= cur_x - 1;
-                        }
-                    }
-                }
-            }
-            if (acc_lo | acc_hi) sts64(a_w + acc_w * kURows * 8, make_uint2(acc_lo, acc_hi));
-            sts64(a_cur, make_uint2((uint32_t) cur_w, cur_x));
-        };
         // The shortest rows (L <= 320 tokens: up to P alive pixels, most of them empty) go token-parallel instead: lane = source
         // token, its pixel is the largest m with edge(m) <= c, i.e. m = floor(((c + 1) P - P/2 - 1) / L) for the exact integer edges
         // (edge(m) = (m L + P/2) >> lg), and a ballot of the pixels' alive bits IS the element mask word.  The warp walks its 32 rows.
@@ -401,7 +388,12 @@ block_attention_umma_kernel(const uint32_t* __restrict__ mask_bits, int P, int p
         };
         // ---- small CTAs (<= 16 source tiles): all element masks are generated up front.  The row's two threads split its pixel
         // words (first / second half of the pixels) and OR their runs into the row's words with shared-memory reductions.
-        const bool small_cta = nt <= 2 * kUChunk;
+        // "small" CTA = one that holds rows too short for the pixel window of the lazy masks (32 P / L + 2 <= 31 bits needs L >= 1.11 P):
+        // its first row decides (rows only get longer); such a CTA has at most (1.11 P + 256) / 64 <= 2 kUChunk source tiles for
+        // P <= 512, and its masks are generated up front.  (Before the lazy masks every CTA of <= 16 tiles took this path: at the
+        // north-star shape that was 4 of 16 row blocks, each spending 9 - 12 us in the up-front generation.)
+        const int min_l = is_causal ? src_off + r0 + 1 : T_SRC;
+        const bool small_cta = nt <= 2 * kUChunk && ((int64_t) min_l * 29 < (int64_t) 32 * P || P > 512);
         int cstar = -1;                          // first alive source token of the row
         if (small_cta && my_nt > 0) {
             const int warp_last = r0 + g * kUM + qd * 32 + 31;
@@ -445,6 +437,7 @@ block_attention_umma_kernel(const uint32_t* __restrict__ mask_bits, int P, int p
                     if (rs.L >= P || rs.edge(m + 1) > a) { cstar = a; break; }      // L >= P: no pixel is empty
                 }
         }
+        SEA_STAMP(9)             // small CTAs: element masks of all tiles; first alive token
         // reference exponent: score of the row's first alive element (+ head-room), so that every alive p stays far below 2
         float nms = 0.f;
         if (cstar >= 0) {
@@ -455,15 +448,37 @@ block_attention_umma_kernel(const uint32_t* __restrict__ mask_bits, int P, int p
             for (int i = 0; i < kUD / 8; ++i) acc = dot8_bf(__ldg(qp + i), __ldg(kp + i), acc);
             nms = -(acc * kLog2e + kUMargin);
         }
+        SEA_STAMP(10)            // q . k of the first alive element
         // epilogue inputs, requested early
         float sc0 = 0.f, sc1 = 0.f;
         if (t < T_DST) {
             const float* sp = scales + ((((int64_t) n * H + h) * T_DST + t) << 1);
             sc0 = __ldg(sp); sc1 = __ldg(sp + 1);
         }
-        if (half == 0 && my_nt > 0 && !small_cta) gen_chunk(0);
+        // ---- large CTAs (every row longer than 1024 tokens: a pixel is >= 4 tokens wide): the element masks are produced tile by tile by
+        // the thread that consumes them, from the row's pixel bitmap.  The first pixel that can reach into the thread's 32 columns of tile j,
+        // m(j) = floor(((c0 + 1) P - P/2 - 1) / L), advances by a per-row constant (quotient / remainder of 64 P / L: no division in the
+        // loop); a window of the next <= 32 P / L + 2 pixel bits comes out of two bitmap words with one funnel shift.  The window is
+        // empty for ~90 % of the (row, tile) pairs (a row has k P / L alive pixels per head: 4 at L = 4096): those cost ~12 non-divergent
+        // instructions; an alive pixel costs its two edges and a clipped run.  No shared-memory mask arrays, no generation burst at the
+        // 8-tile boundaries (SEA_ATTN_TRACE: the chunked generation + the barrier imbalance it caused took 25 % of the softmax warps'
+        // time, reading the mask words back another 9 %).
+        int lz_m = 0, lz_r = 0, lz_q = 0, lz_s = 0;
+        uint32_t lz_nb = 0u;
+        if (my_nt > 0 && !small_cta) {
+            const int step = kUN * P, x0 = (32 * half + 1) * P - (P >> 1) - 1;
+            lz_q = step / rs.L; lz_s = step - lz_q * rs.L;
+            lz_m = x0 / rs.L; lz_r = x0 - lz_m * rs.L;
+            const int nb = min(31, (32 * P) / rs.L + 2);
+            lz_nb = (1u << nb) - 1u;
+        }
         float l_a = 0.f, l_b = 0.f;              // fp32 row sum of this thread's 32 columns (two chains)
         float trig_mx = -INFINITY;              // largest alive score (log2 domain) of the tiles that overflowed the head-room since the last boundary
+        uint32_t tr[8] = {0, 0, 0, 0, 0, 0, 0, 0}, c0 = 0, cstart = 0;
+        if constexpr (kTrace) {
+            cstart = c0 = clock_lo();
+            if (warp == 4 && lane == 0 && g_attn_trace) g_attn_trace[((int64_t) blockIdx.x * 20 + 3) * 16 + 4] = cstart - t_entry;      // set-up
+        }
 
         for (int j = 0; j < my_nt; ++j) {
             const int b = j & 1;
@@ -492,11 +507,30 @@ block_attention_umma_kernel(const uint32_t* __restrict__ mask_bits, int P, int p
                     l_a *= al; l_b *= al;
                     tmem_st_wait();
                 }
-                if (half == ((c + 1) & 1) && (c + 1) * kUChunk < my_nt && !small_cta) gen_chunk(c + 1);
             }
-            const uint32_t mw = lds32(a_mw + (uint32_t) (((c & 1) * kUChunk + jc) * kURows) * 8 + half * 4);
+            SEA_TR(5)
+            uint32_t mw;
+            if (small_cta) {
+                mw = lds32(a_mw + (uint32_t) (((c & 1) * kUChunk + jc) * kURows) * 8 + half * 4);
+            } else {
+                const int c0_ = j * kUN + 32 * half, c1_ = c0_ + 32;           // this thread's columns of the tile
+                const int wq = lz_m >> 5;
+                const uint32_t lo = wq < nw ? lds32(a_brow + wq * 4) : 0u, hi = wq + 1 < nw ? lds32(a_brow + wq * 4 + 4) : 0u;
+                uint32_t win = __funnelshift_r(lo, hi, lz_m & 31) & lz_nb;       // bit i: pixel lz_m + i alive
+                mw = 0u;
+                while (win) {
+                    const int mm = lz_m + __ffs(win) - 1;
+                    win &= win - 1;
+                    const int l = max(rs.edge(mm), c0_) - c0_, hh = min(rs.edge(mm + 1), c1_) - c0_;
+                    if (hh > l) mw |= (0xffffffffu >> (32 - (hh - l))) << l;
+                }
+                lz_m += lz_q; lz_r += lz_s;                                      // first pixel of the next tile's columns
+                if (lz_r >= rs.L) { lz_r -= rs.L; ++lz_m; }
+            }
             const uint32_t um = __reduce_or_sync(kFull, mw);       // column union of the warp's 32 rows
+            SEA_TR(6)
             umma::mbar_wait_addr(a_s_full + 8u * b, (uint32_t) ((j >> 1) & 1));
+            SEA_TR(0)
             umma::tc_fence_after();
             uint4 pk[4];
             uint32_t orv = 0u;
@@ -507,6 +541,7 @@ block_attention_umma_kernel(const uint32_t* __restrict__ mask_bits, int P, int p
                 umma::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_addr(a_s_empty + 8u * b);         // S[b] may be overwritten by the scores of tile j + 2
+                SEA_TR(1)
                 if (um & 0xffu) { exp_group<0>(s0, mw, nms, pk[0], l_a, l_b); orv |= pk[0].x | pk[0].y; orv |= pk[0].z | pk[0].w; } else pk[0] = make_uint4(0, 0, 0, 0);
                 if (um & 0xff00u) { exp_group<8>(s0, mw, nms, pk[1], l_a, l_b); orv |= pk[1].x | pk[1].y; orv |= pk[1].z | pk[1].w; } else pk[1] = make_uint4(0, 0, 0, 0);
                 if (um & 0xff0000u) { exp_group<16>(s0, mw, nms, pk[2], l_a, l_b); orv |= pk[2].x | pk[2].y; orv |= pk[2].z | pk[2].w; } else pk[2] = make_uint4(0, 0, 0, 0);
@@ -522,7 +557,9 @@ block_attention_umma_kernel(const uint32_t* __restrict__ mask_bits, int P, int p
                 }
             }
             // P[b] (TMEM) is free once P.V of tile j - 2 has completed
+            SEA_TR(2)
             if (j >= 2) umma::mbar_wait_addr(a_p_empty + 8u * b, (uint32_t) (((j >> 1) - 1) & 1));
+            SEA_TR(3)
             umma::tc_fence_after();
             {
                 const uint32_t p16[16] = {pk[0].x, pk[0].y, pk[0].z, pk[0].w, pk[1].x, pk[1].y, pk[1].z, pk[1].w,
@@ -533,12 +570,20 @@ block_attention_umma_kernel(const uint32_t* __restrict__ mask_bits, int P, int p
             umma::tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_addr(a_p_full + 8u * b);
+            SEA_TR(4)
         }
+        if constexpr (kTrace) {
+            tr[7] = clock_lo() - cstart;
+            if (lane == 0 && g_attn_trace) for (int i = 0; i < 8; ++i) g_attn_trace[((int64_t) blockIdx.x * 20 + warp) * 16 + i] = tr[i];
+            if (warp == 4 && lane == 0 && g_attn_trace) g_attn_trace[((int64_t) blockIdx.x * 20 + 3) * 16 + 5] = clock_lo() - t_entry;           // end of the loop
+        }
+#undef SEA_TR
         // ---- epilogue: O / l, * sigmoid(s0), mix with the running mean, permuted store (32 channels per thread) -------------
         // row sum: the two halves of a row exchange their partial sums
         sts32(a_xch + (uint32_t) ((4 + half) * kURows) * 4, __float_as_uint(l_a + l_b));
         asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
         const float l_run = (l_a + l_b) + __uint_as_float(lds32(a_xch + (uint32_t) ((4 + (half ^ 1)) * kURows) * 4));
+        SEA_STAMP(11)            // row sums exchanged
         uint32_t o0[32];
         if (my_nt > 0) {
             umma::mbar_wait_addr(a_p_empty + 8u * ((my_nt - 1) & 1), (uint32_t) (((my_nt - 1) >> 1) & 1));
@@ -549,6 +594,7 @@ block_attention_umma_kernel(const uint32_t* __restrict__ mask_bits, int P, int p
 #pragma unroll
             for (int i = 0; i < 32; ++i) o0[i] = 0u;
         }
+        SEA_STAMP(12)            // last P.V complete, O in registers
         if (t < T_DST) {
             const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
             const float psc = use_scaler ? sigu(sc0) : 1.0f;
@@ -574,15 +620,29 @@ block_attention_umma_kernel(const uint32_t* __restrict__ mask_bits, int P, int p
             }
         }
     }
+    if constexpr (kTrace) {
+        if (warp == 4 && lane == 0 && g_attn_trace) g_attn_trace[((int64_t) blockIdx.x * 20 + 3) * 16 + 6] = clock_lo() - t_entry;               // end of the epilogue
+    }
     umma::tc_fence_before();
     __syncthreads();
     if (warp == 1) {
         umma::tc_fence_after();
         umma::tmem_dealloc(tmem_base, 256 * kUG);
     }
+    if constexpr (kTrace) {
+        if (tid == 96 && g_attn_trace) {
+            uint64_t gt;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+            g_attn_trace[((int64_t) blockIdx.x * 20 + 3) * 16 + 2] = (uint32_t) gt;
+            g_attn_trace[((int64_t) blockIdx.x * 20 + 3) * 16 + 7] = clock_lo() - t_entry;
+        }
+    }
 }
 
 }  // namespace
+
+static uint32_t* g_trace_buf = nullptr;
+static int64_t g_trace_words = 0, g_trace_ctas = 0;
 
 int launch_block_attention_umma(const uint32_t* mask_bits, int P, int p_lg,
                                 const void* q, int64_t q_sn, int64_t q_sh, int64_t q_st,
@@ -621,8 +681,31 @@ int launch_block_attention_umma(const uint32_t* mask_bits, int P, int p_lg,
                      "block_attention_umma_kernel launch");
         return SEA_OK;
     };
+    static const bool trace = getenv("SEA_ATTN_TRACE") != nullptr;
+    if (trace) {
+        const int64_t words = (int64_t) ((T_DST + urows(G) - 1) / urows(G)) * N * H * 20 * 16;
+        if (g_trace_words < words) {
+            if (g_trace_buf) cudaFree(g_trace_buf);
+            SEA_CUDA_TRY(cudaMalloc(&g_trace_buf, (size_t) words * 4), "trace buffer");
+            g_trace_words = words;
+            SEA_CUDA_TRY(cudaMemcpyToSymbol(g_attn_trace, &g_trace_buf, sizeof(g_trace_buf)), "trace symbol");
+        }
+        SEA_CUDA_TRY(cudaMemsetAsync(g_trace_buf, 0, (size_t) words * 4, s), "trace clear");
+        g_trace_ctas = words / (20 * 16);
+        if (G == 2) return launch(block_attention_umma_kernel<2, true>, std::integral_constant<int, 2>{});
+        return launch(block_attention_umma_kernel<1, true>, std::integral_constant<int, 1>{});
+    }
     if (G == 2) return launch(block_attention_umma_kernel<2>, std::integral_constant<int, 2>{});
     return launch(block_attention_umma_kernel<1>, std::integral_constant<int, 1>{});
+}
+
+// development aid: copies the trace of the last traced launch to the host (synchronises); returns the number of CTAs
+int64_t attn_trace_read(uint32_t* host, int64_t max_words) {
+    if (!g_trace_buf) return 0;
+    cudaDeviceSynchronize();
+    const int64_t words = g_trace_ctas * 20 * 16 < max_words ? g_trace_ctas * 20 * 16 : max_words;
+    cudaMemcpy(host, g_trace_buf, (size_t) words * 4, cudaMemcpyDeviceToHost);
+    return g_trace_ctas;
 }
 
 }  // namespace sea
