@@ -19,7 +19,7 @@
 //                          kept in shared memory; pixels and tokens both ascend; exact a8 edge arithmetic, csr_common.cuh::
 //                          RowScale).  The loop is warp-uniform: one pixel (or one cursor step) per lane and iteration.
 //                        * no running maximum: the reference exponent of a row is fixed BEFORE the loop from the score of the
-//                          row's first alive element (one 64-wide dot product per thread) plus a 2^32 head-room, so p = 2^(s - ref)
+//                          row's own position (q_t . k_t, half of the dot product per thread) plus a 2^32 head-room, so p = 2^(s - ref)
 //                          needs no per-element max, no per-tile rescale and no per-tile exchange between the two halves of a
 //                          row; every alive p is checked for p >= 2 through an OR of the packed bf16 results (bit 14).  Only then
 //                          (a score e^22 above the reference: practically never) the tile's true maximum is taken, and at the next
@@ -394,7 +394,7 @@ block_attention_umma_kernel(const uint32_t* __restrict__ mask_bits, int P, int p
         // north-star shape that was 4 of 16 row blocks, each spending 9 - 12 us in the up-front generation.)
         const int min_l = is_causal ? src_off + r0 + 1 : T_SRC;
         const bool small_cta = nt <= 2 * kUChunk && ((int64_t) min_l * 29 < (int64_t) 32 * P || P > 512);
-        int cstar = -1;                          // first alive source token of the row
+        int cstar = -1;                          // source token whose score fixes the row's reference exponent
         if (small_cta && my_nt > 0) {
             const int warp_last = r0 + g * kUM + qd * 32 + 31;
             const bool by_token = p_lg >= 0 && (is_causal ? src_off + warp_last + 1 : T_SRC) <= 96;         // warp-uniform
@@ -424,29 +424,25 @@ block_attention_umma_kernel(const uint32_t* __restrict__ mask_bits, int P, int p
                 }
             }
             asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
-            for (int tile = 0; tile < my_nt && cstar < 0; ++tile) {
-                const uint2 w = lds64(a_mw + (uint32_t) (tile * kURows) * 8);
-                if (w.x) cstar = tile * kUN + __ffs(w.x) - 1;
-                else if (w.y) cstar = tile * kUN + 32 + __ffs(w.y) - 1;
-            }
-        } else if (my_nt > 0) {
-            for (int wq = 0; wq < nw && cstar < 0; ++wq)
-                for (uint32_t x = lds32(a_brow + wq * 4); x; x &= x - 1) {
-                    const int m = (wq << 5) + __ffs(x) - 1;
-                    const int a = rs.edge(m);
-                    if (rs.L >= P || rs.edge(m + 1) > a) { cstar = a; break; }      // L >= P: no pixel is empty
-                }
         }
-        SEA_STAMP(9)             // small CTAs: element masks of all tiles; first alive token
-        // reference exponent: score of the row's first alive element (+ head-room), so that every alive p stays far below 2
+        // reference token of the row's exponent: its own position (causal: the last token it may attend to).  ANY per-row constant is
+        // exact -- it cancels in the normalisation, p only has to stay inside the bf16 / fp32 exponent range, and an alive p >= 2 is caught
+        // below -- and this one needs no search for the first alive token (1.6 us of every CTA's set-up) and reads K rows in row order.
+        if (t < T_DST && my_nt > 0) cstar = is_causal ? min(src_off + t, T_SRC - 1) : min(t, T_SRC - 1);
+        SEA_STAMP(9)             // small CTAs: element masks of all tiles
+        // reference exponent: score of that element (+ head-room), so that every alive p stays far below 2
+        // (each of the row's two threads gathers HALF of the two rows -- the 512 threads' row gathers were 2.8 us of every CTA's set-up --
+        // and the halves are added at the rendezvous that opens tile 0)
         float nms = 0.f;
-        if (cstar >= 0) {
-            const uint4* qp = reinterpret_cast<const uint4*>(qg + (int64_t) n * q_sn + (int64_t) h * q_sh + (int64_t) t * q_st);
-            const uint4* kp = reinterpret_cast<const uint4*>(kg + (int64_t) n * k_sn + (int64_t) h * k_sh + (int64_t) cstar * k_st);
+        {
             float acc = 0.f;
+            if (cstar >= 0) {
+                const uint4* qp = reinterpret_cast<const uint4*>(qg + (int64_t) n * q_sn + (int64_t) h * q_sh + (int64_t) t * q_st) + half * (kUD / 16);
+                const uint4* kp = reinterpret_cast<const uint4*>(kg + (int64_t) n * k_sn + (int64_t) h * k_sh + (int64_t) cstar * k_st) + half * (kUD / 16);
 #pragma unroll
-            for (int i = 0; i < kUD / 8; ++i) acc = dot8_bf(__ldg(qp + i), __ldg(kp + i), acc);
-            nms = -(acc * kLog2e + kUMargin);
+                for (int i = 0; i < kUD / 16; ++i) acc = dot8_bf(__ldg(qp + i), __ldg(kp + i), acc);
+            }
+            sts32(a_xch + (uint32_t) ((4 + half) * kURows) * 4, __float_as_uint(acc));       // (the slots of the final row-sum exchange)
         }
         SEA_STAMP(10)            // q . k of the first alive element
         // epilogue inputs, requested early
@@ -490,6 +486,10 @@ block_attention_umma_kernel(const uint32_t* __restrict__ mask_bits, int P, int p
                 asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
                 const float mxb = fmaxf(trig_mx, __uint_as_float(lds32(a_xch + (uint32_t) (((c & 1) * 2 + (half ^ 1)) * kURows) * 4)));
                 trig_mx = -INFINITY;
+                if (j == 0 && cstar >= 0) {      // reference exponent from the two half dot products (same value in both threads of the row)
+                    const float d0 = __uint_as_float(lds32(a_xch + (uint32_t) (4 * kURows) * 4)), d1 = __uint_as_float(lds32(a_xch + (uint32_t) (5 * kURows) * 4));
+                    nms = -((d0 + d1) * kLog2e + kUMargin);
+                }
                 if (__any_sync(kFull, mxb > -INFINITY)) {
                     const bool mv = mxb > -INFINITY;
                     const float nms_new = mv ? -(mxb + kUMargin) : nms;
