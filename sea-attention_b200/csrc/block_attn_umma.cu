@@ -584,6 +584,14 @@ block_attention_umma_kernel(const uint32_t* __restrict__ mask_bits, int P, int p
         asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
         const float l_run = (l_a + l_b) + __uint_as_float(lds32(a_xch + (uint32_t) ((4 + (half ^ 1)) * kURows) * 4));
         SEA_STAMP(11)            // row sums exchanged
+        // the running-mean row of the mix is requested BEFORE the wait for the last P.V (four 16-byte loads in flight under it)
+        uint4 av4[4] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+        const bool has_avg = cumavg != nullptr && t < T_DST;
+        if (has_avg) {
+            const uint4* arow0 = reinterpret_cast<const uint4*>(cumavg + ((int64_t) n * H + h) * avg_sh + (int64_t) t * avg_st + 32 * half);
+#pragma unroll
+            for (int c8 = 0; c8 < 4; ++c8) av4[c8] = __ldg(arow0 + c8);
+        }
         uint32_t o0[32];
         if (my_nt > 0) {
             umma::mbar_wait_addr(a_p_empty + 8u * ((my_nt - 1) & 1), (uint32_t) (((my_nt - 1) >> 1) & 1));
@@ -601,14 +609,13 @@ block_attention_umma_kernel(const uint32_t* __restrict__ mask_bits, int P, int p
             const float a = sigu(sc1);
             const float w = inv * psc;
             __nv_bfloat16* orow = out + ((int64_t) n * T_DST + t) * ((int64_t) H * kUD) + (int64_t) h * kUD + 32 * half;
-            const uint4* arow = cumavg ? reinterpret_cast<const uint4*>(cumavg + ((int64_t) n * H + h) * avg_sh + (int64_t) t * avg_st + 32 * half) : nullptr;
 #pragma unroll
             for (int c8 = 0; c8 < 4; ++c8) {
                 float x[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) x[i] = l_run > 0.f ? __uint_as_float(o0[c8 * 8 + i]) * w : 0.f;
-                if (arow) {
-                    const uint4 av = __ldg(arow + c8);
+                if (has_avg) {
+                    const uint4 av = av4[c8];
                     const uint32_t aw[4] = {av.x, av.y, av.z, av.w};
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
