@@ -425,10 +425,11 @@ block_attention_umma_kernel(const uint32_t* __restrict__ mask_bits, int P, int p
             }
             asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
         }
-        // reference token of the row's exponent: its own position (causal: the last token it may attend to).  ANY per-row constant is
-        // exact -- it cancels in the normalisation, p only has to stay inside the bf16 / fp32 exponent range, and an alive p >= 2 is caught
-        // below -- and this one needs no search for the first alive token (1.6 us of every CTA's set-up) and reads K rows in row order.
-        if (t < T_DST && my_nt > 0) cstar = is_causal ? min(src_off + t, T_SRC - 1) : min(t, T_SRC - 1);
+        // reference token of the row's exponent: source token 0 (inside every row's causal range).  ANY per-row constant is exact -- it
+        // cancels in the normalisation, p only has to stay inside the bf16 / fp32 exponent range (alive scores up to 65 nats below and 22
+        // above the reference; beyond that the p >= 2 test below moves it) -- and this one needs no search for the first alive token
+        // (1.6 us of every CTA's set-up) and no gather: k_0 is one broadcast row, q_t is read from the Q tile the TMA put in shared memory.
+        if (t < T_DST && my_nt > 0) cstar = 0;
         SEA_STAMP(9)             // small CTAs: element masks of all tiles
         // reference exponent: score of that element (+ head-room), so that every alive p stays far below 2
         // (each of the row's two threads gathers HALF of the two rows -- the 512 threads' row gathers were 2.8 us of every CTA's set-up --
@@ -436,11 +437,18 @@ block_attention_umma_kernel(const uint32_t* __restrict__ mask_bits, int P, int p
         float nms = 0.f;
         {
             float acc = 0.f;
+            if (my_nt > 0) umma::mbar_wait(q_full, 0);               // the Q tiles have landed (warp-uniform: my_nt depends on the Q tile only)
             if (cstar >= 0) {
-                const uint4* qp = reinterpret_cast<const uint4*>(qg + (int64_t) n * q_sn + (int64_t) h * q_sh + (int64_t) t * q_st) + half * (kUD / 16);
                 const uint4* kp = reinterpret_cast<const uint4*>(kg + (int64_t) n * k_sn + (int64_t) h * k_sh + (int64_t) cstar * k_st) + half * (kUD / 16);
+                // row `row` of Q tile g: 128 bytes, its 16-byte chunk c at position c ^ (row & 7) (SWIZZLE_128B)
+                const uint32_t a_q = sm_a + USmem::kQ + (uint32_t) g * kUQ + (uint32_t) row * 128;
 #pragma unroll
-                for (int i = 0; i < kUD / 16; ++i) acc = dot8_bf(__ldg(qp + i), __ldg(kp + i), acc);
+                for (int i = 0; i < kUD / 16; ++i) {
+                    const int c = half * (kUD / 16) + i;
+                    uint4 qv;
+                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(qv.x), "=r"(qv.y), "=r"(qv.z), "=r"(qv.w) : "r"(a_q + (uint32_t) ((c ^ (row & 7)) << 4)) : "memory");
+                    acc = dot8_bf(qv, __ldg(kp + i), acc);
+                }
             }
             sts32(a_xch + (uint32_t) ((4 + half) * kURows) * 4, __float_as_uint(acc));       // (the slots of the final row-sum exchange)
         }
