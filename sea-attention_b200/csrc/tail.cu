@@ -146,8 +146,8 @@ __device__ __forceinline__ float ex2_fast(float x) {
 }
 constexpr int kMaxCand = 1024;
 
-template <int kPerLane, int kHPW, int kUp, bool kExactH>
-__global__ void __launch_bounds__(kTopkThreads, 3)
+template <int kPerLane, int kHPW, int kUp, bool kExactH, int kMinBlocks = 3>
+__global__ void __launch_bounds__(kTopkThreads, kMinBlocks)
 tail_topk_reg_kernel(const float* __restrict__ y3, const float* __restrict__ bias, const float* __restrict__ ln_w,
                      const float* __restrict__ ln_b, const float* __restrict__ k_per_row, float* __restrict__ probs,
                      uint32_t* __restrict__ mask_bits, int32_t* __restrict__ crow_counts, int k_clamp,
@@ -192,18 +192,25 @@ tail_topk_reg_kernel(const float* __restrict__ y3, const float* __restrict__ bia
     }
     constexpr int PW = P + 2;
     const int up = kUp > 0 ? kUp : P / W;
+    // 4x upsampling with a lane owning a multiple of 4 pixels: the area-resize windows are known at compile time.  Column j averages the
+    // padded columns {j, j+1} (j < P/2) or {j+1, j+2} (j >= P/2) -- floor(j (P+2) / P) = j + [j >= P/2], two columns everywhere -- and
+    // padded column c is conv output (c-1)/4 (the bias for c = 0 and c = P+1).  A lane then needs its own kPerLane/4 conv outputs and ONE
+    // neighbour (the previous one in the lower half of the row, the next one in the upper half) instead of 3 table-driven loads per pixel.
+    constexpr bool kStaticTaps = kUp == 4 && kPerLane % 4 == 0;
     // area-resize window of every output column, resolved once per CTA (thread = column) into three slots of the per-head
     // vector: a conv output w, the bias slot W (the zero-padded columns of the 1x1 conv) or the zero slot W+1
-    for (int j = tid; j < P; j += kTopkThreads) {
-        const int st = (j * PW) / P;
-        const int cnt = ((j + 1) * PW + P - 1) / P - st;
-        int tp[3];
+    if constexpr (!kStaticTaps) {
+        for (int j = tid; j < P; j += kTopkThreads) {
+            const int st = (j * PW) / P;
+            const int cnt = ((j + 1) * PW + P - 1) / P - st;
+            int tp[3];
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            const int pcol = st + c;
-            tp[c] = c >= cnt ? W + 1 : ((pcol == 0 || pcol == PW - 1) ? W : (pcol - 1) / up);
+            for (int c = 0; c < 3; ++c) {
+                const int pcol = st + c;
+                tp[c] = c >= cnt ? W + 1 : ((pcol == 0 || pcol == PW - 1) ? W : (pcol - 1) / up);
+            }
+            stap[(j % kPerLane) * 32 + j / kPerLane] = make_int4(tp[0], tp[1], tp[2], __float_as_int(1.0f / (float) cnt));   // [i][lane]: conflict-free reads
         }
-        stap[(j % kPerLane) * 32 + j / kPerLane] = make_int4(tp[0], tp[1], tp[2], __float_as_int(1.0f / (float) cnt));   // [i][lane]: conflict-free reads
     }
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
@@ -226,16 +233,22 @@ tail_topk_reg_kernel(const float* __restrict__ y3, const float* __restrict__ bia
     }
     for (int h = tid; h < H; h += kTopkThreads) { ys[h * ldy + W] = bias[h]; ys[h * ldy + W + 1] = 0.f; }
     __syncthreads();
-    int tap[kPerLane][3];
-    float rc[kPerLane];
+    int tap[kStaticTaps ? 1 : kPerLane][3];
+    float rc[kStaticTaps ? 1 : kPerLane];
 #pragma unroll
     for (int i = 0; i < kPerLane; ++i) {
-        const int4 tp = stap[i * 32 + lane];
-        tap[i][0] = tp.x; tap[i][1] = tp.y; tap[i][2] = tp.z;
-        rc[i] = __int_as_float(tp.w);
+        if constexpr (!kStaticTaps) {
+            const int4 tp = stap[i * 32 + lane];
+            tap[i][0] = tp.x; tap[i][1] = tp.y; tap[i][2] = tp.z;
+            rc[i] = __int_as_float(tp.w);
+        }
         lw[i] *= kLog2eT;                   // softmax in the log2 domain: exp(x - max) == exp2(x * log2e - max * log2e)
         lb[i] *= kLog2eT;
     }
+    constexpr int kOwn = kPerLane / 4 > 0 ? kPerLane / 4 : 1;       // conv outputs under a lane's pixels (kStaticTaps)
+    const bool lower = lane < 16;
+    const int own0 = lane * kOwn;
+    const int nb_idx = lower ? (lane == 0 ? W : own0 - 1) : (lane == 31 ? W : own0 + kOwn);      // the neighbour; slot W holds the bias
     constexpr float invP = 1.0f / (float) P;
     // The kHPW heads of this warp advance through LayerNorm / softmax stage by stage, so that the kHPW warp reductions of a
     // stage are independent shuffle chains in flight together (a head-by-head loop exposes 4 x 5 dependent shuffles per head).
@@ -246,10 +259,25 @@ tail_topk_reg_kernel(const float* __restrict__ y3, const float* __restrict__ bia
         const bool hv = kExactH || wid + 8 * hh < H;                // warp-uniform
         const float* yh = ys + (hv ? wid + 8 * hh : 0) * ldy;
         float s = 0.f;
+        if constexpr (kStaticTaps) {
+            float c[kOwn];
 #pragma unroll
-        for (int i = 0; i < kPerLane; ++i) {
-            val[hh][i] = (yh[tap[i][0]] + yh[tap[i][1]] + yh[tap[i][2]]) * rc[i];
-            s += val[hh][i];
+            for (int r = 0; r < kOwn; ++r) c[r] = yh[own0 + r];
+            const float nb = yh[nb_idx];
+#pragma unroll
+            for (int i = 0; i < kPerLane; ++i) {
+                // (x + x + 0) * 0.5 == x: pixels whose two columns fall on the same conv output copy it, like the table path computes it
+                const float vl = i == 0 ? (nb + c[0]) * 0.5f : ((i - 1) / 4 == i / 4 ? c[i / 4] : (c[(i - 1) / 4] + c[i / 4]) * 0.5f);
+                const float vu = i == kPerLane - 1 ? (c[kOwn - 1] + nb) * 0.5f : ((i + 1) / 4 == i / 4 ? c[i / 4] : (c[i / 4] + c[(i + 1) / 4 < kOwn ? (i + 1) / 4 : 0]) * 0.5f);
+                val[hh][i] = lower ? vl : vu;
+                s += val[hh][i];
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < kPerLane; ++i) {
+                val[hh][i] = (yh[tap[i][0]] + yh[tap[i][1]] + yh[tap[i][2]]) * rc[i];
+                s += val[hh][i];
+            }
         }
         red[hh] = s;
     }
@@ -300,10 +328,14 @@ tail_topk_reg_kernel(const float* __restrict__ y3, const float* __restrict__ bia
     for (int hh = 0; hh < kHPW; ++hh) {
         const int h = wid + 8 * hh;
         const float inv = 1.0f / red[hh];
-#pragma unroll
         const bool hv = kExactH || h < H;
+        // probabilities are >= +0, so their bit patterns already order like the values: with every head slot in use the key IS the
+        // probability's register (no second 32-register array); with empty slots the sign bit is set to keep real keys above the 0 of a slot
 #pragma unroll
-        for (int i = 0; i < kPerLane; ++i) { val[hh][i] *= inv; key[hh][i] = hv ? (__float_as_uint(val[hh][i]) | 0x80000000u) : 0u; }   // == orderable(): val >= +0
+        for (int i = 0; i < kPerLane; ++i) {
+            val[hh][i] *= inv;
+            key[hh][i] = kExactH ? __float_as_uint(val[hh][i]) : (hv ? (__float_as_uint(val[hh][i]) | 0x80000000u) : 0u);
+        }
         if (probs && hv) {
             float* prow = probs + (((int64_t) n * H + h) * Tn + t) * P + lane * kPerLane;
             if constexpr (kPerLane % 4 == 0) {
@@ -392,16 +424,30 @@ tail_topk_reg_kernel(const float* __restrict__ y3, const float* __restrict__ bia
                 top = sh;
                 if (first && top > 0 && eq_total <= kMaxCand) {
                     // few keys share the pivot digit: list them and rank them directly instead of more radix passes
+                    // (one counter bump per warp: a per-key atomicAdd serialises the whole CTA on one shared-memory word)
                     const uint32_t dsel = dmask << sh, pdsel = (uint32_t) scratch[8] << sh;
+                    int mine = 0;
 #pragma unroll
                     for (int hh = 0; hh < kHPW; ++hh)
                         if (kExactH || wid + 8 * hh < H) {
 #pragma unroll
-                            for (int i = 0; i < kPerLane; ++i) {
-                                const uint32_t u = key[hh][i];
-                                if ((u & dsel) == pdsel) cand[atomicAdd(&scratch[11], 1)] = u;
-                            }
+                            for (int i = 0; i < kPerLane; ++i) mine += (key[hh][i] & dsel) == pdsel ? 1 : 0;
                         }
+                    const int incl = warp_scan_incl_i(mine, lane);
+                    int pos = 0;
+                    if (lane == 31 && incl > 0) pos = atomicAdd(&scratch[11], incl);
+                    pos = __shfl_sync(kFull, pos, 31) + incl - mine;
+                    if (mine > 0) {
+#pragma unroll
+                        for (int hh = 0; hh < kHPW; ++hh)
+                            if (kExactH || wid + 8 * hh < H) {
+#pragma unroll
+                                for (int i = 0; i < kPerLane; ++i) {
+                                    const uint32_t u = key[hh][i];
+                                    if ((u & dsel) == pdsel) cand[pos++] = u;
+                                }
+                            }
+                    }
                     __syncthreads();
                     const int nc = eq_total;
                     for (int ci = tid; ci < nc; ci += kTopkThreads) {
@@ -539,8 +585,15 @@ static int tail_topk_impl(const float* y3, const float* bias, const float* ln_w,
             if (P / W == 4) SEA_TAILR_L(PL, HP, 4, false) else SEA_TAILR_L(PL, HP, 0, false)                               \
         }
         const int pl = P / 32, hp = hp_slots;
+        static const bool minb3 = getenv("SEA_TAIL_MINB3") != nullptr;       // development switch for A/B timing
         if (H % 8 == 0) {
-            if (pl == 8 && hp == 4) SEA_TAILR(8, 4)
+            // the north-star instantiation runs 4 CTAs per SM (64 registers, 80 bytes of spills): 101 us against 106 us with 3 at N=1, T=4096
+            if (pl == 8 && hp == 4 && P / W == 4 && !minb3) {
+                auto kern = tail_topk_reg_kernel<8, 4, 4, true, 4>;
+                SEA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_r), "smem attr");
+                SEA_CUDA_TRY(launch_pdl(kern, dim3(grid), dim3(kTopkThreads), smem_r, s, y3, bias, ln_w, ln_b, k_per_row, probs, mask_bits, crow_counts, k_clamp, N, T, W, H),
+                             "tail_topk_reg_kernel launch");
+            } else if (pl == 8 && hp == 4) SEA_TAILR(8, 4)
             else if (pl == 8 && hp == 2) SEA_TAILR(8, 2)
             else if (pl == 8 && hp == 1) SEA_TAILR(8, 1)
             else if (pl == 4 && hp == 4) SEA_TAILR(4, 4)
