@@ -146,6 +146,48 @@ __device__ __forceinline__ float ex2_fast(float x) {
 }
 constexpr int kMaxCand = 1024;
 
+// Warp totals of R per-lane values at once (every lane ends with all R totals).  A butterfly that halves the number of values a lane
+// carries while it still has more than one (lanes with bit 4 set keep the upper heads, ...) needs 9 shuffles for R = 4 and 6 for R = 2
+// where R independent butterflies need 5 R.
+template <int R>
+__device__ __forceinline__ void warp_sum_multi(float (&r)[R], int lane) {
+    if constexpr (R == 4) {
+        const bool hi = (lane & 16) != 0, h8 = (lane & 8) != 0;
+        float k0 = hi ? r[2] : r[0], k1 = hi ? r[3] : r[1];
+        k0 += __shfl_xor_sync(kFull, hi ? r[0] : r[2], 16);
+        k1 += __shfl_xor_sync(kFull, hi ? r[1] : r[3], 16);
+        float kk = h8 ? k1 : k0;
+        kk += __shfl_xor_sync(kFull, h8 ? k0 : k1, 8);
+        kk += __shfl_xor_sync(kFull, kk, 4);
+        kk += __shfl_xor_sync(kFull, kk, 2);
+        kk += __shfl_xor_sync(kFull, kk, 1);                  // total of head 2 * [bit 4] + [bit 3]
+        const float o8 = __shfl_xor_sync(kFull, kk, 8);
+        const float a = h8 ? o8 : kk, b = h8 ? kk : o8;        // heads 2 * [bit 4] + {0, 1}
+        const float a16 = __shfl_xor_sync(kFull, a, 16), b16 = __shfl_xor_sync(kFull, b, 16);
+        r[0] = hi ? a16 : a; r[1] = hi ? b16 : b; r[2] = hi ? a : a16; r[3] = hi ? b : b16;
+    } else if constexpr (R == 2) {
+        const bool hi = (lane & 16) != 0;
+        float kk = hi ? r[1] : r[0];
+        kk += __shfl_xor_sync(kFull, hi ? r[0] : r[1], 16);
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) kk += __shfl_xor_sync(kFull, kk, o);
+        const float o16 = __shfl_xor_sync(kFull, kk, 16);
+        r[0] = hi ? o16 : kk; r[1] = hi ? kk : o16;
+    } else {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int hh = 0; hh < R; ++hh) r[hh] += __shfl_xor_sync(kFull, r[hh], o);
+        }
+    }
+}
+// warp maximum in one instruction (CREDUX.MAX.F32; sm_100a)
+__device__ __forceinline__ float warp_max_redux(float v) {
+    float r;
+    asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+    return r;
+}
+
 template <int kPerLane, int kHPW, int kUp, bool kExactH, int kMinBlocks = 3>
 __global__ void __launch_bounds__(kTopkThreads, kMinBlocks)
 tail_topk_reg_kernel(const float* __restrict__ y3, const float* __restrict__ bias, const float* __restrict__ ln_w,
@@ -155,6 +197,7 @@ tail_topk_reg_kernel(const float* __restrict__ y3, const float* __restrict__ bia
     // Hmax = 8 * kHPW head slots; Hr <= Hmax real heads (kExactH: Hr == Hmax, everything below folds to constants).  The slots
     // h >= Hr hold no keys: they are skipped in every key loop and their alive bits stay 0.
     constexpr int P = 32 * kPerLane, Hmax = 8 * kHPW;
+    static_assert(Hmax <= 32, "one lane per head in the tie-cut scan");
     const int H = kExactH ? Hmax : Hr, G = H * P;
     constexpr int kLanesPerWord = 32 / kPerLane > 0 ? 32 / kPerLane : 1;     // lanes that share one 32-pixel word (kPerLane <= 32)
     extern __shared__ __align__(16) uint32_t smem_u[];
@@ -171,7 +214,7 @@ tail_topk_reg_kernel(const float* __restrict__ y3, const float* __restrict__ bia
     pdl_launch_dependents();
     pdl_wait();
     hist[tid] = 0;
-    if (tid == 0) { s_orand[0] = 0u; s_orand[1] = 0xffffffffu; }
+    if (tid == 0) { s_orand[0] = 0u; s_orand[1] = 0xffffffffu; scratch[11] = 0; }       // scratch[11]: candidate counter (used once)
     const int ldy = kUp > 0 ? ((P / (kUp > 0 ? kUp : 1) + 2) | 1) : ((W + 2) | 1);        // compile-time when the upsample factor is (W == P / kUp)
     const float* yr = y3 + ((int64_t) n * Tn + t) * W * H;
     // The first batch of conv outputs (8 loads per thread = the whole row at the north-star shape) and the LayerNorm parameters
@@ -281,10 +324,7 @@ tail_topk_reg_kernel(const float* __restrict__ y3, const float* __restrict__ bia
         }
         red[hh] = s;
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-        for (int hh = 0; hh < kHPW; ++hh) red[hh] += __shfl_xor_sync(kFull, red[hh], o);
+    warp_sum_multi<kHPW>(red, lane);
     float mean[kHPW];
 #pragma unroll
     for (int hh = 0; hh < kHPW; ++hh) {
@@ -294,10 +334,7 @@ tail_topk_reg_kernel(const float* __restrict__ y3, const float* __restrict__ bia
         for (int i = 0; i < kPerLane; ++i) { const float d = val[hh][i] - mean[hh]; q = fmaf(d, d, q); }
         red[hh] = q;
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-        for (int hh = 0; hh < kHPW; ++hh) red[hh] += __shfl_xor_sync(kFull, red[hh], o);
+    warp_sum_multi<kHPW>(red, lane);
 #pragma unroll
     for (int hh = 0; hh < kHPW; ++hh) {
         const float rstd = rsqrtf(red[hh] * invP + 1e-5f);
@@ -308,9 +345,7 @@ tail_topk_reg_kernel(const float* __restrict__ y3, const float* __restrict__ bia
         red[hh] = mx;
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-        for (int hh = 0; hh < kHPW; ++hh) red[hh] = fmaxf(red[hh], __shfl_xor_sync(kFull, red[hh], o));
+    for (int hh = 0; hh < kHPW; ++hh) red[hh] = warp_max_redux(red[hh]);
 #pragma unroll
     for (int hh = 0; hh < kHPW; ++hh) {
         const float mx = red[hh];
@@ -319,10 +354,7 @@ tail_topk_reg_kernel(const float* __restrict__ y3, const float* __restrict__ bia
         for (int i = 0; i < kPerLane; ++i) { val[hh][i] = ex2_fast(val[hh][i] - mx); sum += val[hh][i]; }
         red[hh] = sum;
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-        for (int hh = 0; hh < kHPW; ++hh) red[hh] += __shfl_xor_sync(kFull, red[hh], o);
+    warp_sum_multi<kHPW>(red, lane);
     uint32_t key[kHPW][kPerLane];
 #pragma unroll
     for (int hh = 0; hh < kHPW; ++hh) {
@@ -400,32 +432,35 @@ tail_topk_reg_kernel(const float* __restrict__ y3, const float* __restrict__ bia
                         }
                 }
                 __syncthreads();
-                if (wid == 0) {
-                    // pivot digit by one warp: lane l owns digits 255-8l .. 248-8l (descending), suffix counts by warp scan
+                int pivot_digit;
+                {
+                    // pivot digit, by every warp for itself (8 shared loads and a scan, instead of one warp + a broadcast barrier):
+                    // lane l owns digits 255-8l .. 248-8l (descending), suffix counts by warp scan; exactly one (lane, j) matches
                     int c[8], loc = 0;
 #pragma unroll
                     for (int j = 0; j < 8; ++j) { c[j] = hist[255 - 8 * lane - j]; loc += c[j]; }
                     int above = warp_scan_incl_i(loc, lane) - loc;          // keys with a digit above this lane's range
+                    int dg = -1, rem = 0, eqt = 0;
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         if (above < remaining && remaining <= above + c[j]) {
-                            scratch[8] = 255 - 8 * lane - j;
-                            scratch[9] = remaining - above;
-                            scratch[10] = c[j];
+                            dg = 255 - 8 * lane - j;
+                            rem = remaining - above;
+                            eqt = c[j];
                         }
                         above += c[j];
                     }
-                    if (lane == 0) scratch[11] = 0;                         // candidate counter
+                    const int src = __ffs(__ballot_sync(kFull, dg >= 0)) - 1;
+                    pivot_digit = __shfl_sync(kFull, dg, src);
+                    remaining = __shfl_sync(kFull, rem, src);
+                    eq_total = __shfl_sync(kFull, eqt, src);
                 }
-                __syncthreads();
-                thr |= (uint32_t) scratch[8] << sh;
-                remaining = scratch[9];
-                eq_total = scratch[10];
+                thr |= (uint32_t) pivot_digit << sh;
                 top = sh;
                 if (first && top > 0 && eq_total <= kMaxCand) {
                     // few keys share the pivot digit: list them and rank them directly instead of more radix passes
                     // (one counter bump per warp: a per-key atomicAdd serialises the whole CTA on one shared-memory word)
-                    const uint32_t dsel = dmask << sh, pdsel = (uint32_t) scratch[8] << sh;
+                    const uint32_t dsel = dmask << sh, pdsel = (uint32_t) pivot_digit << sh;
                     int mine = 0;
 #pragma unroll
                     for (int hh = 0; hh < kHPW; ++hh)
@@ -437,7 +472,7 @@ tail_topk_reg_kernel(const float* __restrict__ y3, const float* __restrict__ bia
                     int pos = 0;
                     if (lane == 31 && incl > 0) pos = atomicAdd(&scratch[11], incl);
                     pos = __shfl_sync(kFull, pos, 31) + incl - mine;
-                    if (mine > 0) {
+                    if (mine > 0) {                              // (a vote per key slot instead of the count + scan was measured slower: +6 us)
 #pragma unroll
                         for (int hh = 0; hh < kHPW; ++hh)
                             if (kExactH || wid + 8 * hh < H) {
@@ -494,11 +529,13 @@ tail_topk_reg_kernel(const float* __restrict__ y3, const float* __restrict__ bia
             if (lane == 31) head_eq[wid + 8 * hh] = incl;
         }
         __syncthreads();
+        // equal keys in the heads before head l (exclusive scan of the per-head counts; Hmax <= 32)
+        const int he = lane < H ? head_eq[lane] : 0;
+        const int heads_before = warp_scan_incl_i(he, lane) - he;
 #pragma unroll
         for (int hh = 0; hh < kHPW; ++hh) {
             const int h = wid + 8 * hh;
-            int before = lane_before[hh];
-            for (int h2 = 0; h2 < h; ++h2) before += head_eq[h2];
+            const int before = lane_before[hh] + __shfl_sync(kFull, heads_before, h & 31);
             int take = remaining - before;                       // how many of my equal keys (in index order) stay alive
             if (take < eqc[hh]) {
                 uint32_t a = alive[hh];
