@@ -308,7 +308,10 @@ performer_out_mma_kernel(const __nv_bfloat16* __restrict__ q, int64_t q_sn, int6
     pdl_launch_dependents();
     pdl_wait();
     const int chunk = blockIdx.x, nh = blockIdx.y, n = nh / H, h = nh % H;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tq = lane & 3;
+    const int lane = threadIdx.x & 31, g = lane >> 2, tq = lane & 3;
+    // Row tile of this rt.  The causal loops below run rt + 1 steps, and warps w and w + 4 share an SM sub-partition (its tensor pipe):
+    // tiles {s, 7 - s} on sub-partition s make 9 steps everywhere instead of 5 .. 11.
+    const int rt = (threadIdx.x >> 5) < 4 ? (threadIdx.x >> 5) : 11 - (threadIdx.x >> 5);
     const int r0 = chunk * kCh, nvalid = min(kCh, T - r0);
     const Slab sl = make_slab(kDm, (int) blockIdx.z);
     {   // all global loads in flight first: q/k/v tiles by cp.async, then the three fp32 register batches (S_prev, pos_emb,
@@ -345,15 +348,15 @@ performer_out_mma_kernel(const __nv_bfloat16* __restrict__ q, int64_t q_sn, int6
     cp_async_wait_all();
     __syncthreads();
     const float norm = rsqrtf(sqrtf((float) kDm));
-    uint32_t aq[kFp / 16][4];     // phi(q) of this warp's rows as A fragments
+    uint32_t aq[kFp / 16][4];     // phi(q) of this rt's rows as A fragments
     {
         float acc[kFp / 8][4];
-        phi_rows<kFp, kDm>(acc, Ks, Ps, warp, lane);
+        phi_rows<kFp, kDm>(acc, Ks, Ps, rt, lane);
 #pragma unroll
         for (int nt = 0; nt < kFp / 8; ++nt)
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
-                const int row = 16 * warp + g + 8 * half;
+                const int row = 16 * rt + g + 8 * half;
                 float o[2];
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
@@ -362,7 +365,7 @@ performer_out_mma_kernel(const __nv_bfloat16* __restrict__ q, int64_t q_sn, int6
                 }
                 *reinterpret_cast<uint32_t*>(PhiK + row * (kFp + 8) + nt * 8 + 2 * tq) = pack_bf16(o[0], o[1]);
             }
-        phi_rows<kFp, kDm>(acc, Qs, Ps, warp, lane);
+        phi_rows<kFp, kDm>(acc, Qs, Ps, rt, lane);
 #pragma unroll
         for (int ks = 0; ks < kFp / 16; ++ks) {
             float o[2][4];
@@ -387,7 +390,7 @@ performer_out_mma_kernel(const __nv_bfloat16* __restrict__ q, int64_t q_sn, int6
         for (int i = 0; i < 4; ++i) O[nt][i] = 0.f;
     const int brow = (lane & 7) + 8 * (lane >> 4), bcol = 8 * ((lane >> 3) & 1);    // B from [n][k] storage (PhiK)
     const int vr = (lane & 7) + 8 * ((lane >> 3) & 1), vc = 8 * (lane >> 4);        // B from [k][n] storage (Vs, Ss), trans
-    for (int jt = 0; jt <= warp; ++jt) {
+    for (int jt = 0; jt <= rt; ++jt) {
         // P tile [16 x 16] = phi(q) . phi(k_j)^T for source rows 16jt .. 16jt+15
         float p[2][4];
 #pragma unroll
@@ -402,7 +405,7 @@ performer_out_mma_kernel(const __nv_bfloat16* __restrict__ q, int64_t q_sn, int6
             mma16816(p[1], aq[ks], b[2], b[3]);
         }
         uint32_t pa[4];
-        if (jt == warp) {       // diagonal tile: keep source j <= query i
+        if (jt == rt) {       // diagonal tile: keep source j <= query i
 #pragma unroll
             for (int t2 = 0; t2 < 2; ++t2)
 #pragma unroll
@@ -435,7 +438,7 @@ performer_out_mma_kernel(const __nv_bfloat16* __restrict__ q, int64_t q_sn, int6
     const float den_lo = __shfl_sync(kFull, O[kE / 8][0], lane & ~3);
     const float den_hi = __shfl_sync(kFull, O[kE / 8][2], lane & ~3);
     const float inv_lo = 1.0f / den_lo, inv_hi = 1.0f / den_hi;
-    const int row_lo = 16 * warp + g, row_hi = row_lo + 8;
+    const int row_lo = 16 * rt + g, row_hi = row_lo + 8;
     constexpr int kCtxW = 2 * kDm;                  // ctx row = [pos part (D) | v part (D)]; this slab owns columns 128 z ..
     __nv_bfloat16* cb = ctx + (((int64_t) n * H + h) * T + r0) * kCtxW + (int) blockIdx.z * kE;
 #pragma unroll
@@ -459,9 +462,9 @@ performer_out_mma_kernel(const __nv_bfloat16* __restrict__ q, int64_t q_sn, int6
 #pragma unroll
             for (int i = 0; i < 4; ++i) C[nt][i] = 0.f;
         constexpr uint32_t kOne2 = 0x3F803F80u;                    // two bf16 ones
-        for (int jt = 0; jt <= warp; ++jt) {
+        for (int jt = 0; jt <= rt; ++jt) {
             uint32_t la[4] = {kOne2, kOne2, kOne2, kOne2};
-            if (jt == warp) {                                      // diagonal tile: source column <= query row
+            if (jt == rt) {                                      // diagonal tile: source column <= query row
                 const uint32_t tri = ((2 * tq <= g) ? 0x00003F80u : 0u) | ((2 * tq + 1 <= g) ? 0x3F800000u : 0u);
                 la[0] = tri; la[1] = kOne2; la[2] = 0u; la[3] = tri;
             }
@@ -502,7 +505,7 @@ prefix_chunks_kernel(float* __restrict__ ws, int nchunks, int64_t stride, const 
     // 16-byte accesses (stride = kFp * kEx is a multiple of 4): a quarter of the load/store instructions, same bytes in flight
     float4* base = reinterpret_cast<float4*>(ws + (int64_t) blockIdx.y * nchunks * stride);
     const int64_t stride4 = stride >> 2;
-    constexpr int kBatch = 16;
+    constexpr int kBatch = 32;
     for (int64_t idx = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; idx < stride4; idx += (int64_t) gridDim.x * blockDim.x) {
         float4 run = init ? __ldg(reinterpret_cast<const float4*>(init) + (int64_t) blockIdx.y * stride4 + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
         for (int c0 = 0; c0 < nchunks; c0 += kBatch) {
