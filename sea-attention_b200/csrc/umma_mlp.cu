@@ -183,33 +183,45 @@ mlp_umma_kernel(const __grid_constant__ CUtensorMap tmap_ctx, const __grid_const
             // ---------------- epilogue 1: bias + LayerNorm(128) + GELU -> A2 (bf16, swizzled K-major) ----------------
             umma::mbar_wait(acc1_full, tphase);
             umma::tc_fence_after();
+            // (the epilogue is issue-bound: parameters come in as 16-byte shared-memory loads, and the LayerNorm statistics are taken in
+            // one pass -- sum and sum of squares, fp32 over 128 O(1) values -- so that the four column parts of a token meet once, not twice)
             float x[32];
+            float s = 0.f, s2 = 0.f;
             {
                 uint32_t r[32];
                 umma::tmem_ld_32x32(acc1 + lane_addr + (uint32_t) (cp * 32), r);
                 umma::tmem_ld_wait();
+                const float4* eb4 = reinterpret_cast<const float4*>(s_enc_b + cp * 32);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(r[i]) + s_enc_b[cp * 32 + i];
+                for (int i4 = 0; i4 < 8; ++i4) {
+                    const float4 eb = eb4[i4];
+                    x[4 * i4 + 0] = __uint_as_float(r[4 * i4 + 0]) + eb.x; x[4 * i4 + 1] = __uint_as_float(r[4 * i4 + 1]) + eb.y;
+                    x[4 * i4 + 2] = __uint_as_float(r[4 * i4 + 2]) + eb.z; x[4 * i4 + 3] = __uint_as_float(r[4 * i4 + 3]) + eb.w;
+                }
+#pragma unroll
+                for (int i = 0; i < 32; ++i) { s += x[i]; s2 = fmaf(x[i], x[i], s2); }
             }
-            float s = 0.f;
-#pragma unroll
-            for (int i = 0; i < 32; ++i) s += x[i];
-            red[cp * 128 + row].x = s;
+            *reinterpret_cast<float2*>(&red[cp * 128 + row]) = make_float2(s, s2);
             asm volatile("bar.sync 1, 512;" ::: "memory");
-            const float mean = (red[row].x + red[128 + row].x + red[256 + row].x + red[384 + row].x) * (1.0f / 128.0f);
-            float vq = 0.f;
-#pragma unroll
-            for (int i = 0; i < 32; ++i) { const float dlt = x[i] - mean; vq = fmaf(dlt, dlt, vq); }
-            red[cp * 128 + row].y = vq;
-            asm volatile("bar.sync 1, 512;" ::: "memory");
-            const float rstd = rsqrtf((red[row].y + red[128 + row].y + red[256 + row].y + red[384 + row].y) * (1.0f / 128.0f) + 1e-5f);
+            float mean, rstd;
+            {
+                const float2 a = *reinterpret_cast<const float2*>(&red[row]), b = *reinterpret_cast<const float2*>(&red[128 + row]);
+                const float2 c = *reinterpret_cast<const float2*>(&red[256 + row]), d = *reinterpret_cast<const float2*>(&red[384 + row]);
+                mean = (a.x + b.x + c.x + d.x) * (1.0f / 128.0f);
+                rstd = rsqrtf(fmaxf((a.y + b.y + c.y + d.y) * (1.0f / 128.0f) - mean * mean, 0.f) + 1e-5f);
+            }
+            const float nmr = -mean * rstd;
+            const float4* lw4 = reinterpret_cast<const float4*>(s_ln_w + cp * 32);
+            const float4* lb4 = reinterpret_cast<const float4*>(s_ln_b + cp * 32);
 #pragma unroll
             for (int c4 = 0; c4 < 4; ++c4) {
                 float g[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int c = cp * 32 + c4 * 8 + i;
-                    g[i] = gelu_erf_((x[c4 * 8 + i] - mean) * rstd * s_ln_w[c] + s_ln_b[c]);
+                for (int i4 = 0; i4 < 2; ++i4) {
+                    const float4 w4 = lw4[c4 * 2 + i4], b4 = lb4[c4 * 2 + i4];
+                    const float wv[4] = {w4.x, w4.y, w4.z, w4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) g[i4 * 4 + i] = gelu_erf_(fmaf(fmaf(x[c4 * 8 + i4 * 4 + i], rstd, nmr), wv[i], bv[i]));
                 }
                 uint4 pk;
                 __nv_bfloat162 p0 = __floats2bfloat162_rn(g[0], g[1]), p1 = __floats2bfloat162_rn(g[2], g[3]);
@@ -244,13 +256,21 @@ mlp_umma_kernel(const __grid_constant__ CUtensorMap tmap_ctx, const __grid_const
                 umma::tmem_ld_32x16(acc2 + lane_addr + (uint32_t) (W + cp * W4), r1);
                 umma::tmem_ld_wait();
                 float4 part = make_float4(0.f, 0.f, 0.f, 0.f);
+                const float4* db0 = reinterpret_cast<const float4*>(s_dec_b + cp * W4);          // W4 is a multiple of 4 (W in {16, 32, 64})
+                const float4* db1 = reinterpret_cast<const float4*>(s_dec_b + W + cp * W4);
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    if (i < W4) {
-                        y0[i] = __uint_as_float(r0[i]) + s_dec_b[cp * W4 + i];
-                        y1[i] = __uint_as_float(r1[i]) + s_dec_b[W + cp * W4 + i];
-                        part.x += y0[i]; part.y = fmaf(y0[i], y0[i], part.y);
-                        part.z += y1[i]; part.w = fmaf(y1[i], y1[i], part.w);
+                for (int i4 = 0; i4 < 4; ++i4) {
+                    if (i4 * 4 < W4) {
+                        const float4 b0 = db0[i4], b1 = db1[i4];
+                        const float b0v[4] = {b0.x, b0.y, b0.z, b0.w}, b1v[4] = {b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const int i = i4 * 4 + k;
+                            y0[i] = __uint_as_float(r0[i]) + b0v[k];
+                            y1[i] = __uint_as_float(r1[i]) + b1v[k];
+                            part.x += y0[i]; part.y = fmaf(y0[i], y0[i], part.y);
+                            part.z += y1[i]; part.w = fmaf(y1[i], y1[i], part.w);
+                        }
                     }
                 }
                 red[cp * 128 + row] = part;
@@ -273,13 +293,21 @@ mlp_umma_kernel(const __grid_constant__ CUtensorMap tmap_ctx, const __grid_const
                 for (int g = et; g < zchunks; g += kMlpEpiThreads) *reinterpret_cast<uint4*>(a2s + (size_t) g * 16) = make_uint4(0, 0, 0, 0);
                 asm volatile("bar.sync 1, 512;" ::: "memory");
             }
+            const float nm0 = -mu0 * rs0, nm1 = -mu1 * rs1;
+            const float4* cw4 = reinterpret_cast<const float4*>(s_cw + cp * W4);
+            const float4* cb4 = reinterpret_cast<const float4*>(s_cb + cp * W4);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                if (i < W4 && row < rows_used) {
-                    const int w = cp * W4 + i;
-                    const float v0 = (y0[i] - mu0) * rs0 * s_cw[w] + s_cb[w];
-                    const float v1 = (y1[i] - mu1) * rs1 * s_cw[w] + s_cb[w];
-                    *reinterpret_cast<__nv_bfloat162*>(stg + ((size_t) (tl * W + w) * C + 2 * h)) = __floats2bfloat162_rn(v0, v1);
+            for (int i4 = 0; i4 < 4; ++i4) {
+                if (i4 * 4 < W4 && row < rows_used) {
+                    const float4 cw = cw4[i4], cb = cb4[i4];
+                    const float cwv[4] = {cw.x, cw.y, cw.z, cw.w}, cbv[4] = {cb.x, cb.y, cb.z, cb.w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int i = i4 * 4 + k, w = cp * W4 + i;
+                        const float v0 = fmaf(fmaf(y0[i], rs0, nm0), cwv[k], cbv[k]);
+                        const float v1 = fmaf(fmaf(y1[i], rs1, nm1), cwv[k], cbv[k]);
+                        *reinterpret_cast<__nv_bfloat162*>(stg + ((size_t) (tl * W + w) * C + 2 * h)) = __floats2bfloat162_rn(v0, v1);
+                    }
                 }
             }
             umma::tc_fence_before();
