@@ -103,7 +103,7 @@ block_attention_bits_kernel(const uint32_t* __restrict__ tile_act, int act_words
                             const float* __restrict__ scales, const T16* __restrict__ cumavg, int64_t avg_sh, int64_t avg_st, int use_scaler,
                             T16* __restrict__ out, int N, int H, int T_DST, int T_SRC, int is_causal, int n_row_blocks, int max_tiles) {
     extern __shared__ uint8_t bsm_raw[];
-    uint8_t* bsm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(bsm_raw) + 1023) & ~(uintptr_t) 1023);   // swizzle atoms are 1 KB
+    uint8_t* bsm = bsm_raw + ((1024u - ((uint32_t) __cvta_generic_to_shared(bsm_raw) & 1023u)) & 1023u);      // (offset from the __shared__ array, not an integer round trip: keeps the shared address space -> LDS / STS, not generic LD / ST)   // swizzle atoms are 1 KB
     uint8_t* kv = bsm;                                                               // [stages][K 8 KB | V 8 KB | masks 2 KB]
     uint32_t* sact = reinterpret_cast<uint32_t*>(kv + kStages * kStageBytes);     // [kMaxTileWords]
     uint64_t* full = reinterpret_cast<uint64_t*>(sact + kMaxTileWords);              // [stages]

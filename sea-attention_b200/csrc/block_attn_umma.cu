@@ -169,7 +169,7 @@ block_attention_umma_kernel(const uint32_t* __restrict__ mask_bits, int P, int p
     constexpr int kURows = urows(kUG), kUThreads = uthreads(kUG), kUSoftmaxWarps = 8 * kUG;
     using USmem = USmem<kUG>;
     extern __shared__ uint8_t usm_raw[];
-    uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(usm_raw) + 1023) & ~(uintptr_t) 1023);
+    uint8_t* sm = usm_raw + ((1024u - ((uint32_t) __cvta_generic_to_shared(usm_raw) & 1023u)) & 1023u);      // (offset from the __shared__ array, not an integer round trip: keeps the shared address space -> LDS / STS, not generic LD / ST)
     const uint32_t sm_a = umma::smem_u32(sm);
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + USmem::kBar);
     uint64_t* q_full = bars;                         // [1]

@@ -102,7 +102,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                  const float* __restrict__ bias, OutT* __restrict__ y, int N, int T, int W, int TR, int tblocks, int num_tiles) {
     using SM = ConvSmem<kTaps, kNOut>;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - ((uint32_t) __cvta_generic_to_shared(smem_raw) & 1023u)) & 1023u);      // (offset from the __shared__ array, not an integer round trip: keeps the shared address space -> LDS / STS, not generic LD / ST)
     uint8_t* wsm = smem;
     uint8_t* asm_ = smem + SM::kStageOff;
     uint8_t* osm = smem + SM::kOutOff;
@@ -285,7 +285,7 @@ conv_ring_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
                       __nv_bfloat16* __restrict__ y, float* __restrict__ y3, int N, int T, int PT, int pairs_per_cta) {
     constexpr int kNOut = 64, W = 64;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - ((uint32_t) __cvta_generic_to_shared(smem_raw) & 1023u)) & 1023u);      // (offset from the __shared__ array, not an integer round trip: keeps the shared address space -> LDS / STS, not generic LD / ST)
     uint8_t* wsm = smem;
     uint8_t* ring = smem + RingSmem::kRingOff;                     // [pos][136 rows x 128 B], row = 2 * (w + 2) + tt
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + RingSmem::kBarOff);     // [pos]

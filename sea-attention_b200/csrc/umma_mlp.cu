@@ -75,7 +75,7 @@ mlp_umma_kernel(const __grid_constant__ CUtensorMap tmap_ctx, const __grid_const
                 __nv_bfloat16* __restrict__ cnn_in, float* __restrict__ scales,
                 int N, int H, int T, int W, int TT, int tblocks, int num_tiles, int Cout) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - ((uint32_t) __cvta_generic_to_shared(smem_raw) & 1023u)) & 1023u);      // (offset from the __shared__ array, not an integer round trip: keeps the shared address space -> LDS / STS, not generic LD / ST)
     float* par = reinterpret_cast<float*>(smem + MlpSmem::kPar);
     float* s_enc_b = par, *s_ln_w = par + 128, *s_ln_b = par + 256, *s_dec_b = par + 384, *s_cw = par + 528, *s_cb = par + 656;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + MlpSmem::kBar);
