@@ -285,9 +285,10 @@ performer_sums_mma_kernel(const __nv_bfloat16* __restrict__ k, int64_t k_sn, int
         for (int j = 0; j < 3; ++j) {
             const int nt = warp + 8 * j;
             if (nt < kEx / 8) {
+                // (rows above the ones feature F are identically zero: never written, scanned or read back)
                 const int f0 = mt * 16 + g, e0 = nt * 8 + 2 * tq;
-                *reinterpret_cast<float2*>(slot + f0 * kEx + e0) = make_float2(acc[mt][j][0], acc[mt][j][1]);
-                *reinterpret_cast<float2*>(slot + (f0 + 8) * kEx + e0) = make_float2(acc[mt][j][2], acc[mt][j][3]);
+                if (f0 <= F) *reinterpret_cast<float2*>(slot + f0 * kEx + e0) = make_float2(acc[mt][j][0], acc[mt][j][1]);
+                if (f0 + 8 <= F) *reinterpret_cast<float2*>(slot + (f0 + 8) * kEx + e0) = make_float2(acc[mt][j][2], acc[mt][j][3]);
             }
         }
 }
@@ -327,7 +328,7 @@ performer_out_mma_kernel(const __nv_bfloat16* __restrict__ q, int64_t q_sn, int6
 #pragma unroll
         for (int it = 0; it < kIt; ++it) {
             const int idx = threadIdx.x + it * kThreads;
-            sv[it] = idx < kVec ? __ldcg(reinterpret_cast<const float4*>(slot) + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+            sv[it] = (idx < kVec && idx / (kEx / 4) <= F) ? __ldcg(reinterpret_cast<const float4*>(slot) + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         ProjRegs<kFp, kDm> pr;
         issue_proj<kFp, kDm>(pr, proj, F);
@@ -496,7 +497,7 @@ performer_out_mma_kernel(const __nv_bfloat16* __restrict__ q, int64_t q_sn, int6
 // exclusive prefix over the chunk slots of one (n, h).  The loads of a batch of chunks are issued together (they are
 // independent; a naive load/store loop serialises on aliasing and costs one L2 round trip per chunk).
 __global__ void __launch_bounds__(256)
-prefix_chunks_kernel(float* __restrict__ ws, int nchunks, int64_t stride, const float* __restrict__ init, float* __restrict__ total, int write_prefix) {
+prefix_chunks_kernel(float* __restrict__ ws, int nchunks, int64_t stride, int64_t used4, const float* __restrict__ init, float* __restrict__ total, int write_prefix) {
     // init (nullable, [gridDim.y][stride]): the state BEFORE the first chunk (a rank's share of a sequence sharded over ranks starts from
     // the sums of the ranks before it); total (nullable): init + all chunks; write_prefix = 0: only `total` is produced (the chunk slots
     // keep their per-chunk sums for a later prefix pass with the exchanged init)
@@ -506,7 +507,8 @@ prefix_chunks_kernel(float* __restrict__ ws, int nchunks, int64_t stride, const 
     float4* base = reinterpret_cast<float4*>(ws + (int64_t) blockIdx.y * nchunks * stride);
     const int64_t stride4 = stride >> 2;
     constexpr int kBatch = 32;
-    for (int64_t idx = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; idx < stride4; idx += (int64_t) gridDim.x * blockDim.x) {
+    // used4: float4s of a slot that carry data (feature rows 0 .. F; the padding rows up to kFp are never written)
+    for (int64_t idx = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; idx < used4; idx += (int64_t) gridDim.x * blockDim.x) {
         float4 run = init ? __ldg(reinterpret_cast<const float4*>(init) + (int64_t) blockIdx.y * stride4 + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
         for (int c0 = 0; c0 < nchunks; c0 += kBatch) {
             float4 cur[kBatch];
@@ -540,16 +542,17 @@ int launch_performer_mma(const void* q, int64_t q_sn, int64_t q_sh, int64_t q_st
     SEA_CUDA_TRY(cudaFuncSetAttribute(kc, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kBytes), "smem attr");
     using B = __nv_bfloat16;
     const int64_t stride = (int64_t) kFp * kEx;
-    const dim3 pgrid((unsigned) ((stride / 4 + 255) / 256), N * H * kSlabs);
+    const int64_t used4 = (int64_t) (F + 1) * (kEx / 4);
+    const dim3 pgrid((unsigned) ((used4 + 255) / 256), N * H * kSlabs);
     if (phase == 0 || phase == 1)
         SEA_CUDA_TRY(launch_pdl(ka, grid, dim3(kThreads), (size_t) SM::kSumsBytes, s, (const B*) k, k_sn, k_sh, k_st, (const B*) v, v_sn, v_sh, v_st, pos_emb, proj, ws, H, T, F,
                                 nchunks), "performer_sums_mma_kernel launch");
     if (phase == 1) {
-        SEA_CUDA_TRY(launch_pdl(prefix_chunks_kernel, pgrid, dim3(256), (size_t) 0, s, ws, nchunks, stride, (const float*) nullptr, total, 0), "prefix_chunks_kernel launch");
+        SEA_CUDA_TRY(launch_pdl(prefix_chunks_kernel, pgrid, dim3(256), (size_t) 0, s, ws, nchunks, stride, used4, (const float*) nullptr, total, 0), "prefix_chunks_kernel launch");
         return SEA_OK;
     }
     // one exclusive prefix per (n, h, slab): the slabs' chunk slots are laid out [nh][slab][chunk]
-    SEA_CUDA_TRY(launch_pdl(prefix_chunks_kernel, pgrid, dim3(256), (size_t) 0, s, ws, nchunks, stride, init, total, 1), "prefix_chunks_kernel launch");
+    SEA_CUDA_TRY(launch_pdl(prefix_chunks_kernel, pgrid, dim3(256), (size_t) 0, s, ws, nchunks, stride, used4, init, total, 1), "prefix_chunks_kernel launch");
     SEA_CUDA_TRY(launch_pdl(kc, grid, dim3(kThreads), (size_t) SM::kBytes, s, (const B*) q, q_sn, q_sh, q_st, (const B*) k, k_sn, k_sh, k_st, (const B*) v, v_sn, v_sh, v_st,
                             pos_emb, proj, (const float*) ws, (B*) ctx, (B*) cumavg, H, T, F, nchunks, t_off), "performer_out_mma_kernel launch");
     return SEA_OK;

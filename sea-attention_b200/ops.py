@@ -329,7 +329,7 @@ def performer_causal_range_sums(k, v, pos_rows, proj):
     if pos.shape[0] < Tr or not lib.sea_performer_mma_supported(_DTYPES.get(k.dtype, -1), D, F):
         raise SeaError('performer_causal_range_sums: unsupported dtype / head dim / feature count, or too few position rows')
     ws = torch.empty((lib.sea_performer_mma_workspace_floats(N, H, Tr, D, F),), dtype=torch.float32, device=k.device)
-    total = torch.empty((lib.sea_performer_mma_state_floats(N, H, D, F),), dtype=torch.float32, device=k.device)
+    total = torch.zeros((lib.sea_performer_mma_state_floats(N, H, D, F),), dtype=torch.float32, device=k.device)     # (the kernels skip the zero padding rows)
     _lib.call('sea_performer_causal_mma_range', None, 0, 0, 0, k.data_ptr(), k.stride(0), k.stride(1), k.stride(2), v.data_ptr(), v.stride(0), v.stride(1), v.stride(2),
               pos.data_ptr(), pj.data_ptr(), None, None, ws.data_ptr(), None, total.data_ptr(), N, H, Tr, D, F, 0, 1, _stream())
     return ws, total

@@ -72,7 +72,8 @@ def test_conv3x3_conv1x1_fused_matches_separate(sea, N, T):
 
 @pytest.mark.parametrize('ties', [False, True])
 @pytest.mark.parametrize('N,H,T,W,P,k', [(1, 32, 40, 64, 256, 64), (2, 8, 33, 16, 64, 8), (1, 4, 20, 8, 32, 4), (1, 32, 12, 32, 128, 16),
-                                        (1, 32, 300, 64, 256, 8), (1, 16, 90, 64, 256, 16), (1, 12, 50, 64, 256, 64)])
+                                        (1, 32, 300, 64, 256, 8), (1, 16, 90, 64, 256, 16), (1, 12, 50, 64, 256, 64),
+                                        (1, 16, 37, 128, 512, 32), (1, 8, 21, 256, 1024, 16)])      # 16 / 32 pixels per lane: 4 / 8 conv outputs under a lane
 def test_tail_topk_fused_matches_oracle(sea, N, H, T, W, P, k, ties):
     import numpy as np
     g = torch.Generator().manual_seed(P + T)
