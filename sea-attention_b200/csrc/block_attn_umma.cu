@@ -215,13 +215,24 @@ block_attention_umma_kernel(const uint32_t* __restrict__ mask_bits, int P, int p
 
     // ---- set-up -------------------------------------------------------------------------------------------------------
     const int nw = P >> 5, bst = ubits_stride(nw);
-    // top-k pixel bits of this head's 256 query rows -> shared memory (rows past T_DST: no alive pixel); pixel cursors
-    for (int i = tid; i < kURows * nw; i += kUThreads) {
-        const int r = i / nw, w = i - r * nw, tr = r0 + r;
-        const uint32_t v = tr < T_DST ? __ldg(mask_bits + (((int64_t) n * T_DST + tr) * H + h) * nw + w) : 0u;
-        sts32(sm_a + USmem::kBits + (uint32_t) (r * bst + w) * 4, v);
-        if (w == 0) sts64(sm_a + USmem::kCur + (uint32_t) r * 8, make_uint2(0u, v));
-    }
+    // K runs kLag tiles ahead of V: S of tile j + 2 is issued while P.V is still at tile j, so K stages turn over earlier
+    constexpr int kLag = 2;
+    auto issue_kv = [&](int jj) {            // producer step jj: K tile jj and V tile jj - kLag (thread 0 only)
+        if (jj < nt) {
+            const int s = jj % kUStages;
+            if (jj >= kUStages) umma::mbar_wait_sleep(&k_empty[s], (uint32_t) ((jj / kUStages - 1) & 1), 256);
+            umma::mbar_arrive_expect_tx(&k_full[s], kUTile);
+            umma::tma_load_4d(sm + USmem::kKV + s * kUTile, &tmap_k, &k_full[s], 0, jj * kUN, h, n);
+        }
+        const int j = jj - kLag;
+        if (j >= 0) {
+            const int s = j % kUStages;
+            if (j >= kUStages) umma::mbar_wait_sleep(&v_empty[s], (uint32_t) ((j / kUStages - 1) & 1), 256);
+            umma::mbar_arrive_expect_tx(&v_full[s], kUTile);
+            umma::tma_load_4d(sm + USmem::kKV + (kUStages + s) * kUTile, &tmap_v, &v_full[s], 0, j * kUN, h, n);
+        }
+    };
+    int jj0 = 0;
     if (tid == 0) {
         umma::prefetch_tensormap(&tmap_q); umma::prefetch_tensormap(&tmap_k); umma::prefetch_tensormap(&tmap_v);
         umma::mbar_init(q_full, 1);
@@ -233,6 +244,22 @@ block_attention_umma_kernel(const uint32_t* __restrict__ mask_bits, int P, int p
             umma::mbar_init(&s_empty[b], kUSoftmaxWarps / kUG);
         }
         umma::fence_barrier_init();
+        // The Q tiles and the first ring stages (no stage is re-used below kUStages steps: no waits) are requested right here, by the
+        // thread that initialised their barriers, so that they are in flight under the pixel-bit copy, the TMEM allocation and the
+        // block barrier below instead of starting after them.
+        if (nt > 0) {
+            umma::mbar_arrive_expect_tx(q_full, (uint32_t) ((ntg[0] > 0) + (kUG > 1 && ntg[kUG - 1] > 0)) * kUQ);
+            if (ntg[0] > 0) umma::tma_load_4d(sm + USmem::kQ, &tmap_q, q_full, 0, r0, h, n);
+            if (kUG > 1 && ntg[kUG - 1] > 0) umma::tma_load_4d(sm + USmem::kQ + kUQ, &tmap_q, q_full, 0, r0 + kUM, h, n);
+            for (; jj0 < kUStages && jj0 < nt + kLag; ++jj0) issue_kv(jj0);
+        }
+    }
+    // top-k pixel bits of this head's 256 query rows -> shared memory (rows past T_DST: no alive pixel); pixel cursors
+    for (int i = tid; i < kURows * nw; i += kUThreads) {
+        const int r = i / nw, w = i - r * nw, tr = r0 + r;
+        const uint32_t v = tr < T_DST ? __ldg(mask_bits + (((int64_t) n * T_DST + tr) * H + h) * nw + w) : 0u;
+        sts32(sm_a + USmem::kBits + (uint32_t) (r * bst + w) * 4, v);
+        if (w == 0) sts64(sm_a + USmem::kCur + (uint32_t) r * 8, make_uint2(0u, v));
     }
     if (warp == 1) umma::tmem_alloc(tmem_ptr, 256 * kUG);
     umma::tc_fence_before();
@@ -246,26 +273,7 @@ block_attention_umma_kernel(const uint32_t* __restrict__ mask_bits, int P, int p
     if (warp == 0) {
         // ---------------------------------------------------------------- TMA producer
         if (lane == 0 && nt > 0) {
-            umma::mbar_arrive_expect_tx(q_full, (uint32_t) ((ntg[0] > 0) + (kUG > 1 && ntg[kUG - 1] > 0)) * kUQ);
-            if (ntg[0] > 0) umma::tma_load_4d(sm + USmem::kQ, &tmap_q, q_full, 0, r0, h, n);
-            if (kUG > 1 && ntg[kUG - 1] > 0) umma::tma_load_4d(sm + USmem::kQ + kUQ, &tmap_q, q_full, 0, r0 + kUM, h, n);
-            // K runs kLag tiles ahead of V: S of tile j + 2 is issued while P.V is still at tile j, so K stages turn over earlier
-            constexpr int kLag = 2;
-            for (int jj = 0; jj < nt + kLag; ++jj) {
-                if (jj < nt) {
-                    const int s = jj % kUStages;
-                    if (jj >= kUStages) umma::mbar_wait_sleep(&k_empty[s], (uint32_t) ((jj / kUStages - 1) & 1), 256);
-                    umma::mbar_arrive_expect_tx(&k_full[s], kUTile);
-                    umma::tma_load_4d(sm + USmem::kKV + s * kUTile, &tmap_k, &k_full[s], 0, jj * kUN, h, n);
-                }
-                const int j = jj - kLag;
-                if (j >= 0) {
-                    const int s = j % kUStages;
-                    if (j >= kUStages) umma::mbar_wait_sleep(&v_empty[s], (uint32_t) ((j / kUStages - 1) & 1), 256);
-                    umma::mbar_arrive_expect_tx(&v_full[s], kUTile);
-                    umma::tma_load_4d(sm + USmem::kKV + (kUStages + s) * kUTile, &tmap_v, &v_full[s], 0, j * kUN, h, n);
-                }
-            }
+            for (int jj = jj0; jj < nt + kLag; ++jj) issue_kv(jj);       // (steps below jj0 were issued before the block barrier)
         }
     } else if (warp >= 1 && warp <= kUG) {
         // ---------------------------------------------------------------- MMA issuer of Q tile g.  One warp per Q tile: a serial
