@@ -30,10 +30,25 @@ for t in range(T, T + 8):
     o = mod(s(q, t, t + 1), s(kk, 0, t + 1), s(v, 0, t + 1), s(q, t, t + 1), s(kk, 0, t + 1), s(v, 0, t + 1), s(q, t, t + 1), s(kk, 0, t + 1), dm, None, None, last_state=state)
     state = o.state
 torch.cuda.synchronize()
+state_start = state
 e0.record()
 n = 40
 for t in range(T + 8, T + 8 + n):
     o = mod(s(q, t, t + 1), s(kk, 0, t + 1), s(v, 0, t + 1), s(q, t, t + 1), s(kk, 0, t + 1), s(v, 0, t + 1), s(q, t, t + 1), s(kk, 0, t + 1), dm, None, None, last_state=state)
     state = o.state
-e1.record(); torch.cuda.synchronize()
+e1.record()
+import time
+t_host = time.perf_counter()
+torch.cuda.synchronize()
 print(f'decode step at context {T}: {e0.elapsed_time(e1) / n * 1000:.0f} us per token per layer (one sea_decode_step call per token)')
+# host side alone: the same loop enqueued without waiting (the GPU queue absorbs it while it is shorter than the device time)
+torch.cuda.synchronize()
+state = state_start
+t0_ = time.perf_counter()
+for t in range(T + 8, T + 8 + n):
+    o = mod(s(q, t, t + 1), s(kk, 0, t + 1), s(v, 0, t + 1), s(q, t, t + 1), s(kk, 0, t + 1), s(v, 0, t + 1), s(q, t, t + 1), s(kk, 0, t + 1), dm, None, None, last_state=state)
+    state = o.state
+t1_ = time.perf_counter()
+torch.cuda.synchronize()
+t2_ = time.perf_counter()
+print(f'host enqueue {(t1_ - t0_) / n * 1e6:.0f} us per token, drain after the loop {(t2_ - t1_) * 1e6:.0f} us')

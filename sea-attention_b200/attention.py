@@ -574,6 +574,38 @@ class PerlinAttention(nn.Module):
             key_for_score=k_for_score, state=None)
 
     # ------------------------------------------------------------------------------------------------
+    def _decode_native_planned(self, plan, st, qn, kc, v, N, H, d, F, P, S, C_win, T_new):
+        """The native decode step with every per-module constant taken from the plan (see _forward_causal_stateful)."""
+        pc = self.pconfig
+        contexts, prob_rows = [], []
+        mid, kpr0, ws_ptr, ws_n = plan['mid'], plan['kpr'], plan['ws'], plan['ws_n']
+        kargs = (kc.data_ptr(), kc.stride(0), kc.stride(1), kc.stride(2), v.data_ptr(), v.stride(0), v.stride(1), v.stride(2))
+        tail = (N, H, d, F, P, S, C_win)
+        k_, scaler = int(pc.k), int(bool(pc.partial_attention_scaler))
+        dev = qn.device
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            for i in range(T_new):
+                t = st.t
+                new = PerlinAttentionState(t=t + 1, performer=torch.empty_like(st.performer), cnn_in_win=torch.empty_like(st.cnn_in_win),
+                                           conv1_win=torch.empty_like(st.conv1_win))
+                context = torch.empty((N, 1, H * d), dtype=qn.dtype, device=dev)
+                probs = torch.empty((N, H, 1, P), dtype=torch.float32, device=dev)
+                qi = qn[:, :, i:i + 1]
+                ops._lib.call('sea_decode_step', qi.data_ptr(), qi.stride(0), qi.stride(1), *kargs, *mid, kpr0 + 4 * t,
+                              st.performer.data_ptr(), new.performer.data_ptr(), st.cnn_in_win.data_ptr(), new.cnn_in_win.data_ptr(),
+                              st.conv1_win.data_ptr(), new.conv1_win.data_ptr(), context.data_ptr(), probs.data_ptr(), ws_ptr, ws_n,
+                              *tail, t, k_, scaler, stream)
+                st = new
+                contexts.append(context)
+                prob_rows.append(probs)
+        context = contexts[0] if T_new == 1 else torch.cat(contexts, dim=1)
+        probs = prob_rows[0] if T_new == 1 else torch.cat(prob_rows, dim=2)
+        return PerlinAttentionOutput(
+            loss=0, context_layer=context, partial_attention_probs=None, partial_attention_mask=None,
+            estimated_attention_probs_m=probs, estimated_attention_probs=probs, dense_attention_probs=None,
+            key_for_score=kc, state=st)
+
     def _forward_causal_stateful(self, q, k, v, q_for_atten, k_for_atten, v_for_atten, q_for_score, k_for_score, attention_mask, last_state):
         """use_cache / decode path (reference attention_state.py + attention.py:559-572, 627-639, 1222-1236).
         q holds the T_new NEW query tokens, k / v all T_SRC tokens seen so far (the caller's KV cache).
@@ -617,11 +649,21 @@ class PerlinAttention(nn.Module):
         st = PerlinAttentionState(t=last_state.t, performer=last_state.performer, cnn_in_win=last_state.cnn_in_win,
                                   conv1_win=last_state.conv1_win)
         pk = self._packed
+        C_win = st.cnn_in_win.shape[-1]
+        pad_c = C_win != S * H                       # the state was built on the zero-padded 64-channel path
+        # Frozen module (inference loop): everything about the native step that does not change from token to token -- ~30 parameter
+        # pointers, the packing slots, the workspace -- is resolved once and kept beside the cached fp32 weights (dropped with them).
+        plan_key = (N, H, d, P, S, C_win, int(pc.k), q.dtype, q.device, bool(pc.partial_attention_scaler))
+        plan = self._w_cache.get('_decode_plan') if (self.decode_native and pk.frozen and self._w_cache is not None) else None
+        if plan is not None and plan['key'] != plan_key:
+            plan = None
+        if plan is not None and (q_for_atten.data_ptr() == q_for_score.data_ptr() and k_for_atten.data_ptr() == k_for_score.data_ptr()
+                                 and q.dtype == k.dtype == v.dtype and k.stride(-1) == 1 and v.stride(-1) == 1 and q.stride(-1) == 1
+                                 and k_for_score.stride() == k.stride() and st.cnn_in_win.is_contiguous() and st.conv1_win.is_contiguous()):
+            return self._decode_native_planned(plan, st, q_for_score, k_for_score, v, N, H, d, F, P, S, C_win, T_new)
         net = self.attention_predictor_cnn[1].module.net
         enc, dec, scl = self.attention_predictor_enc, self.attention_predictor_dec_row, self.attention_predictor_dec_scaler
         w['_src_mlp'] = (enc[0].weight, dec[0].weight, scl[0].weight)
-        C_win = st.cnn_in_win.shape[-1]
-        pad_c = C_win != S * H                       # the state was built on the zero-padded 64-channel path
         wp = self._padded_conv_weights(w, S * H, H) if pad_c else w
         # per_item_top_k of every position up to max_position_embeddings, computed once (it depends on shapes only)
         max_pos = self.v_eye_learned_causal.shape[2]
@@ -659,6 +701,17 @@ class PerlinAttention(nn.Module):
                 ws = ws[(-ws.data_ptr()) % 256:][:nbytes]
                 self._decode_ws = {wkey: ws}
             qn = q_for_score
+            if pk.frozen and not repack and self._w_cache is not None:
+                _pp = lambda t_: None if t_ is None else t_.data_ptr()
+                self._w_cache['_decode_plan'] = {
+                    'key': plan_key, 'keep': (w, wp, mlp_ws, c1_ws, c2_ws, ws, kpr_all), 'kpr': kpr_all.data_ptr(), 'ws': ws.data_ptr(), 'ws_n': ws.numel(),
+                    'mid': (dcode, w['pos'].data_ptr(), w['proj'].data_ptr(),
+                            w['enc_w'].data_ptr(), w['enc_b'].data_ptr(), w['enc_ln_w'].data_ptr(), w['enc_ln_b'].data_ptr(),
+                            w['dec_w'].data_ptr(), w['dec_b'].data_ptr(), w['cnn_ln_w'].data_ptr(), w['cnn_ln_b'].data_ptr(),
+                            w['scl_w'].data_ptr(), w['scl_b'].data_ptr(),
+                            wp['conv1_w'].data_ptr(), wp['conv1_b'].data_ptr(), wp['conv2_w'].data_ptr(), wp['conv2_b'].data_ptr(),
+                            w['conv3_w'].data_ptr(), w['conv3_b'].data_ptr(), w['out_ln_w'].data_ptr(), w['out_ln_b'].data_ptr(),
+                            _pp(mlp_ws), _pp(c1_ws), _pp(c2_ws), 0)}
         else:
             st.performer = st.performer.clone()          # the per-op kernel advances the sums in place
         for i in range(T_new):

@@ -64,8 +64,38 @@ inline cudaError_t launch_copies(const CopyJobs& jobs, cudaStream_t s) {
 
 inline int64_t align256(int64_t x) { return (x + 255) & ~(int64_t) 255; }
 
+// The 1x1 convolution of the one new row (attention.py:275-280 via modules.py:96-192 with a 1x1 kernel): y3[n][w][h] = bias[h] +
+// sum_c x[n][w][c] * weight[h][c], fp32 out -- the input the fused tail / top-k kernel of the prefill takes.  8 positions per CTA; the
+// weight goes through shared memory transposed ([c][h], rows padded by one word) so that both its store and its reads are conflict-free.
+template <typename T>
+__global__ void __launch_bounds__(256)
+decode_conv1x1_kernel(const T* __restrict__ x, const float* __restrict__ weight, const float* __restrict__ bias, float* __restrict__ y3,
+                      int W, int C, int H) {
+    extern __shared__ float dc_smem[];
+    float* wT = dc_smem;                    // [C][H + 1]
+    float* xs = dc_smem + C * (H + 1);      // [8][C]
+    const int n = blockIdx.y, w0 = blockIdx.x * 8, tid = threadIdx.x;
+    for (int i = tid; i < H * C; i += 256) {
+        const int h = i / C, c = i - h * C;
+        wT[c * (H + 1) + h] = __ldg(weight + i);
+    }
+    for (int i = tid; i < 8 * C; i += 256) {
+        const int wl = i / C, c = i - wl * C;
+        xs[i] = w0 + wl < W ? to_f32(x[((int64_t) n * W + w0 + wl) * C + c]) : 0.f;
+    }
+    __syncthreads();
+    for (int o = tid; o < 8 * H; o += 256) {
+        const int wl = o / H, h = o - wl * H;
+        if (w0 + wl >= W) continue;
+        float acc = __ldg(bias + h);
+        const float* xr = xs + wl * C;
+        for (int c = 0; c < C; ++c) acc = fmaf(xr[c], wT[c * (H + 1) + h], acc);
+        y3[((int64_t) n * W + w0 + wl) * H + h] = acc;
+    }
+}
+
 struct DecodeWs {
-    int64_t ctx, cumavg, cnn_row, xwin5, y1full, ywin5, y2full, y2row, scales, bits, kpr, crow, col, head_ptr, total;
+    int64_t ctx, cumavg, cnn_row, xwin5, y1full, ywin5, y2full, y2row, y3row, scales, bits, kpr, crow, col, head_ptr, total;
     int64_t z_alloc;
 };
 
@@ -82,6 +112,7 @@ DecodeWs decode_ws(int N, int H, int D, int P, int S, int C, int k_clamp, int es
     w.ywin5 = take((int64_t) N * 5 * W * C * esz);
     w.y2full = take((int64_t) N * 5 * W * C * esz);
     w.y2row = take((int64_t) N * W * S * H * esz);
+    w.y3row = take((int64_t) N * W * H * 4);
     w.scales = take((int64_t) N * H * 2 * 4);
     w.bits = take((int64_t) N * ((H * P + 31) / 32) * 4);
     w.kpr = take((int64_t) N * 4);
@@ -201,10 +232,25 @@ int sea_decode_step(const void* q, int64_t q_sn, int64_t q_sh,
     }
 
     // ---- a5 tail + a6, a7 of the one query row
-    rc = sea_predictor_tail_fwd(y2row, dtype, conv3_w, conv3_b, out_ln_w, out_ln_b, probs, nullptr, N, H, 1, W, SH, P, stream);
-    if (rc) return rc;
-    rc = sea_topk_mask_bits(probs, (int64_t) H * P, (int64_t) P, (int64_t) P, kpr, nullptr, bits, N, H, 1, P, 0, stream);
-    if (rc) return rc;
+    // The prefill's fused tail / top-k kernel (one CTA per row, keys in registers) behind a small 1x1 convolution: 15 us where the
+    // stand-alone tail (1x1 conv + resize + LayerNorm + softmax of all heads in one serial CTA) and the stand-alone top-k took 70 + 18 us
+    // of the ~150 us step.  Shapes the fused kernel does not take keep the two stand-alone kernels.
+    const bool fused_tail = (P % 32) == 0 && (P % W) == 0 && P <= 1024 && H <= 64 && ((H + 7) / 8) * (P / 32) <= 32 &&
+                            ((int64_t) SH * (H + 1) + 8 * SH) * 4 <= 48 * 1024;
+    if (fused_tail) {
+        float* y3row = reinterpret_cast<float*>(wb + ws.y3row);
+        const size_t smem = ((size_t) SH * (H + 1) + 8 * (size_t) SH) * 4;
+        const dim3 grid((unsigned) ((W + 7) / 8), (unsigned) N);
+        SEA_DISPATCH_DTYPE(dtype, T_, decode_conv1x1_kernel<T_><<<grid, 256, smem, s>>>(reinterpret_cast<const T_*>(y2row), conv3_w, conv3_b, y3row, W, SH, H));
+        SEA_CHECK_LAUNCH("decode_conv1x1_kernel");
+        rc = sea_predictor_tail_topk_fwd(y3row, conv3_b, out_ln_w, out_ln_b, kpr, probs, bits, nullptr, 0, N, H, 1, W, P, stream);
+        if (rc) return rc;
+    } else {
+        rc = sea_predictor_tail_fwd(y2row, dtype, conv3_w, conv3_b, out_ln_w, out_ln_b, probs, nullptr, N, H, 1, W, SH, P, stream);
+        if (rc) return rc;
+        rc = sea_topk_mask_bits(probs, (int64_t) H * P, (int64_t) P, (int64_t) P, kpr, nullptr, bits, N, H, 1, P, 0, stream);
+        if (rc) return rc;
+    }
 
     // ---- a8 - a14: the query row against the whole KV cache
     if (dtype != SEA_DTYPE_F32 && (D == 32 || D == 64 || D == 80 || D == 96 || D == 128) && (P % 32) == 0 && P <= 1024 &&
