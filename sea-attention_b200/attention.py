@@ -653,7 +653,8 @@ class PerlinAttention(nn.Module):
         pad_c = C_win != S * H                       # the state was built on the zero-padded 64-channel path
         # Frozen module (inference loop): everything about the native step that does not change from token to token -- ~30 parameter
         # pointers, the packing slots, the workspace -- is resolved once and kept beside the cached fp32 weights (dropped with them).
-        plan_key = (N, H, d, P, S, C_win, int(pc.k), q.dtype, q.device, bool(pc.partial_attention_scaler))
+        plan_key = (N, H, d, P, S, C_win, int(pc.k), float(pc.k_oversample), q.dtype, q.device, bool(pc.partial_attention_scaler),
+                    int(self.v_eye_learned_causal.shape[2]))
         plan = self._w_cache.get('_decode_plan') if (self.decode_native and pk.frozen and self._w_cache is not None) else None
         if plan is not None and plan['key'] != plan_key:
             plan = None
