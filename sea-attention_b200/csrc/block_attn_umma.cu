@@ -433,21 +433,24 @@ block_attention_umma_kernel(const uint32_t* __restrict__ mask_bits, int P, int p
             }
             asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
         }
-        // reference token of the row's exponent: source token 0 (inside every row's causal range).  ANY per-row constant is exact -- it
+        // reference of the row's exponent: the SMALLER of its scores against source tokens 1 and 2.  ANY per-row constant is exact -- it
         // cancels in the normalisation, p only has to stay inside the bf16 / fp32 exponent range (alive scores up to 65 nats below and 22
-        // above the reference; beyond that the p >= 2 test below moves it) -- and this one needs no search for the first alive token
-        // (1.6 us of every CTA's set-up) and no gather: k_0 is one broadcast row, q_t is read from the Q tile the TMA put in shared memory.
-        if (t < T_DST && my_nt > 0) cstar = 0;
+        // above the reference; above that the p >= 2 test below moves it, which is exact but slow; below that p would underflow, which is
+        // NOT detected).  Hence two probes and their minimum -- a reference that is too high needs BOTH probe tokens to score 65 nats above
+        // every alive one -- and hence not token 0, the usual attention sink.  Needs no search for the first alive token (1.6 us of every
+        // CTA's set-up) and no gather: the probe keys are two broadcast rows, q_t is read from the Q tile the TMA put in shared memory.
+        if (t < T_DST && my_nt > 0) cstar = min(1, T_SRC - 1);
         SEA_STAMP(9)             // small CTAs: element masks of all tiles
         // reference exponent: score of that element (+ head-room), so that every alive p stays far below 2
         // (each of the row's two threads gathers HALF of the two rows -- the 512 threads' row gathers were 2.8 us of every CTA's set-up --
         // and the halves are added at the rendezvous that opens tile 0)
         float nms = 0.f;
         {
-            float acc = 0.f;
+            float acc = 0.f, acc_b = 0.f;
             if (my_nt > 0) umma::mbar_wait(q_full, 0);               // the Q tiles have landed (warp-uniform: my_nt depends on the Q tile only)
             if (cstar >= 0) {
                 const uint4* kp = reinterpret_cast<const uint4*>(kg + (int64_t) n * k_sn + (int64_t) h * k_sh + (int64_t) cstar * k_st) + half * (kUD / 16);
+                const uint4* kp_b = reinterpret_cast<const uint4*>(kg + (int64_t) n * k_sn + (int64_t) h * k_sh + (int64_t) min(2, T_SRC - 1) * k_st) + half * (kUD / 16);
                 // row `row` of Q tile g: 128 bytes, its 16-byte chunk c at position c ^ (row & 7) (SWIZZLE_128B)
                 const uint32_t a_q = sm_a + USmem::kQ + (uint32_t) g * kUQ + (uint32_t) row * 128;
 #pragma unroll
@@ -456,9 +459,11 @@ block_attention_umma_kernel(const uint32_t* __restrict__ mask_bits, int P, int p
                     uint4 qv;
                     asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(qv.x), "=r"(qv.y), "=r"(qv.z), "=r"(qv.w) : "r"(a_q + (uint32_t) ((c ^ (row & 7)) << 4)) : "memory");
                     acc = dot8_bf(qv, __ldg(kp + i), acc);
+                    acc_b = dot8_bf(qv, __ldg(kp_b + i), acc_b);
                 }
             }
             sts32(a_xch + (uint32_t) ((4 + half) * kURows) * 4, __float_as_uint(acc));       // (the slots of the final row-sum exchange)
+            sts32(a_xch + (uint32_t) ((2 + half) * kURows) * 4, __float_as_uint(acc_b));     // (the parity-1 slots of the boundary exchange: first used at tile 8)
         }
         SEA_STAMP(10)            // q . k of the first alive element
         // epilogue inputs, requested early
@@ -504,7 +509,8 @@ block_attention_umma_kernel(const uint32_t* __restrict__ mask_bits, int P, int p
                 trig_mx = -INFINITY;
                 if (j == 0 && cstar >= 0) {      // reference exponent from the two half dot products (same value in both threads of the row)
                     const float d0 = __uint_as_float(lds32(a_xch + (uint32_t) (4 * kURows) * 4)), d1 = __uint_as_float(lds32(a_xch + (uint32_t) (5 * kURows) * 4));
-                    nms = -((d0 + d1) * kLog2e + kUMargin);
+                    const float e0 = __uint_as_float(lds32(a_xch + (uint32_t) (2 * kURows) * 4)), e1 = __uint_as_float(lds32(a_xch + (uint32_t) (3 * kURows) * 4));
+                    nms = -(fminf(d0 + d1, e0 + e1) * kLog2e + kUMargin);
                 }
                 if (__any_sync(kFull, mxb > -INFINITY)) {
                     const bool mv = mxb > -INFINITY;

@@ -310,20 +310,22 @@ def test_attention_from_bits_matches_oracle_directly(sea, H, T, P, k, kernel):
     assert float((out.float().cpu() - ref).abs().mean()) < 2e-3
 
 
-@pytest.mark.parametrize('c0', [15.0, -25.0, 0.0])
-def test_block_attention_score_range(sea, c0):
-    """The block kernel subtracts q_t . k_0 instead of the row maximum.  Token 0 as an attention sink (~30 nats above the other scores),
-    as an anti-sink (~50 nats below them: every alive probability overflows the fixed offset and the kernel has to move the reference) and
-    as a zero row, against the gather kernel's max-subtracted fp32 softmax (attention.py:1159-1165)."""
+@pytest.mark.parametrize('tok,c0', [(0, 15.0), (0, -25.0), (0, 0.0), (0, 35.0), (1, 35.0), (1, -25.0), (2, 35.0), (2, -25.0)])
+def test_block_attention_score_range(sea, tok, c0):
+    """The block kernel subtracts min(q_t . k_1, q_t . k_2) instead of the row maximum.  One of the first tokens as an attention sink (~30
+    and ~70 nats above the other scores: as the only probe token that would underflow every other alive probability; the exact range of the
+    scheme is 110 nats above the reference within an 8-tile chunk), as an anti-sink (~50
+    nats below them: every alive probability overflows the fixed offset and the kernel has to move the reference) and as a zero row,
+    against the gather kernel's max-subtracted fp32 softmax (attention.py:1159-1165)."""
     N, H, T, P, k, d = 1, 2, 512, 64, 16, 64
     g = torch.Generator().manual_seed(17)
     mask = (torch.rand(N, H, T, P, generator=g) < 0.4).float()
-    mask[..., 0] = (torch.rand(N, H, T, generator=g) < 0.5).float()        # token 0 alive in about half of the rows
+    mask[..., 0] = (torch.rand(N, H, T, generator=g) < 0.5).float()        # the first pixel (tokens 0 ..) alive in about half of the rows
     bits = sea.ops.mask_to_bits(mask.to(DEV))
     u = torch.nn.functional.normalize(torch.randn(d, generator=g), dim=0)
     q = (torch.randn(N, H, T, d, generator=g) * d ** -0.5 + 2.0 * u).bfloat16().to(DEV)
     kk = torch.randn(N, H, T, d, generator=g)
-    kk[:, :, 0] = c0 * u
+    kk[:, :, tok] = c0 * u
     kk = kk.bfloat16().to(DEV)
     v = torch.randn(N, H, T, d, generator=g).bfloat16().to(DEV)
     scales = torch.randn(N, H, T, 2, generator=g).to(DEV)
